@@ -1,0 +1,144 @@
+/* b200z.h -- C-ABI of libb200z.so, the B200 (sm_100a) DEFLATE engine that replaces the managed inner loops of
+ * ICSharpCode.SharpZipLib.Zip.Compression.{Deflater,Inflater} and ICSharpCode.SharpZipLib.Checksum.{Crc32,Adler32}.
+ *
+ * Plain pointers and sizes only: this is what a P/Invoke (C#), ctypes (Python) or cgo binding declares.
+ * Paths cited below are relative to /root/reference/src/ICSharpCode.SharpZipLib/ .
+ *
+ * Every function returns a b200z_status (0 = OK) unless noted; b200z_last_error() gives the message of the last
+ * failure on the calling thread.  The status -> .NET exception mapping the C# shim applies is in INTEGRATION.md.
+ * There is NO CPU fallback: without a CUDA device every compute entry point fails with B200Z_E_CUDA.
+ */
+#ifndef B200Z_H
+#define B200Z_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum b200z_status {
+	B200Z_OK = 0,
+	B200Z_E_ARG = 1,         /* ArgumentNullException / ArgumentOutOfRangeException / ArgumentException */
+	B200Z_E_STATE = 2,       /* InvalidOperationException ("Finish() already called", "Old input was not completely processed") */
+	B200Z_E_DATA = 3,        /* SharpZipBaseException family (corrupt deflate data, checksum mismatch) */
+	B200Z_E_INTERNAL = 4,    /* the reference would fail with a non-SharpZip exception (e.g. PendingBuffer overflow, trap T12) */
+	B200Z_E_CUDA = 5,        /* CUDA runtime failure / no device */
+	B200Z_E_UNSUPPORTED = 6, /* a call sequence this build does not accelerate; never silently emulated on the CPU */
+	B200Z_E_NOMEM = 7,       /* device or host allocation failed, or an output capacity was too small */
+	B200Z_E_NEED_INPUT = 8   /* inflate: the compressed stream ended before the final block (stream layer: "Unexpected EOF") */
+} b200z_status;
+
+/* wrapper around the raw deflate stream */
+enum { B200Z_WRAP_RAW = 0, B200Z_WRAP_ZLIB = 1, B200Z_WRAP_GZIP = 2 };
+/* DeflateStrategy, Zip/Compression/DeflaterEngine.cs:9-28 */
+enum { B200Z_STRATEGY_DEFAULT = 0, B200Z_STRATEGY_FILTERED = 1, B200Z_STRATEGY_HUFFMAN_ONLY = 2 };
+/* how a deflate plan ends each stream (which Deflater calls the bytes correspond to) */
+enum {
+	B200Z_END_FINISH = 0,       /* SetInput* -> Finish()                       (Deflater.cs:262; DeflaterOutputStream.Finish :100) */
+	B200Z_END_FLUSH_FINISH = 1, /* SetInput* -> Flush() -> Finish()            (test pattern InflaterDeflaterTests.cs:49-62)      */
+	B200Z_END_FLUSH = 2         /* SetInput* -> Flush(), stream continues      (Deflater.cs:252, sync padding :486-504)           */
+};
+
+const char *b200z_last_error(void);
+int b200z_version(void);
+/* Selects the CUDA device for the calling process (one process per GPU) and creates the library context.
+ * Idempotent.  Mirrors nothing in the reference: the reference has no device. */
+int b200z_init(int device);
+/* Static Huffman tables (DeflaterHuffman static ctor :602-642 and InflaterHuffmanTree static ctor :34-70) as one
+ * byte blob, so that rank 0 can broadcast them (NCCL) and the others install them: north_star's only collective. */
+int b200z_static_tables_size(void);
+int b200z_static_tables_export(uint8_t *blob, int32_t cap);
+int b200z_static_tables_import(const uint8_t *blob, int32_t len);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Checksums -- IChecksum (Checksum/IChecksum.cs), Crc32 (Checksum/Crc32.cs:47-171), Adler32 (Checksum/Adler32.cs:56-161).
+ * `value` in/out is the checksum's Value over everything fed so far (Crc32.Reset -> 0, Adler32.Reset -> 1).
+ * Host-buffer forms copy to the device and reduce there; _device forms take device pointers.
+ * ------------------------------------------------------------------------------------------------------------- */
+int b200z_crc32(const uint8_t *buf, int64_t len, uint32_t *value);
+int b200z_adler32(const uint8_t *buf, int64_t len, uint32_t *value);
+/* n independent buffers resident on the device: buffer i is d_data[off[i] .. off[i]+len[i]); seeds/results in
+ * d_value[i] (device).  kind: 0 = CRC32, 1 = Adler32.  off/len are host arrays.  Asynchronous on `stream`. */
+int b200z_checksum_batch_device(int kind, const uint8_t *d_data, const int64_t *off, const int64_t *len, int32_t n,
+                                uint32_t *d_value, void *cuda_stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Batch plans -- what the benchmark drives.  A plan fixes the shape of a batch (number of streams, their sizes,
+ * level/strategy), owns the device workspace, and lays the streams out in one input blob and one output blob at
+ * aligned offsets it reports.  run() only launches kernels on `stream` (no host synchronisation), so it can be
+ * timed with CUDA events or captured in a CUDA graph.  Stream i of the batch is one self-contained DEFLATE stream:
+ * a fresh `new Deflater(level, true)` / `new Inflater(true)` per buffer in the reference.
+ * ------------------------------------------------------------------------------------------------------------- */
+typedef struct b200z_plan b200z_plan;
+
+int b200z_deflate_plan_create(int32_t n, const int64_t *in_len, int level, int strategy, int wrap, int end_mode,
+                              b200z_plan **plan);
+int b200z_inflate_plan_create(int32_t n, const int64_t *comp_len, const int64_t *out_cap, int wrap, b200z_plan **plan);
+int b200z_plan_destroy(b200z_plan *plan);
+int64_t b200z_plan_in_bytes(const b200z_plan *plan);          /* size of the input blob  */
+int64_t b200z_plan_out_bytes(const b200z_plan *plan);         /* size of the output blob */
+int64_t b200z_plan_in_offset(const b200z_plan *plan, int32_t i);
+int64_t b200z_plan_out_offset(const b200z_plan *plan, int32_t i);
+int64_t b200z_plan_out_capacity(const b200z_plan *plan, int32_t i);
+int64_t b200z_plan_workspace_bytes(const b200z_plan *plan);
+/* kernels launched by one run() (for the benchmark's gpu_launches accounting) */
+int32_t b200z_plan_launches(const b200z_plan *plan);
+/* d_in / d_out: device blobs laid out as the plan reports.  d_out_len[n] (int64), d_status[n] (int32, b200z_status)
+ * and d_check[n] (uint32: Adler32 for zlib, CRC32 for gzip, untouched for raw; may be NULL for raw) are device
+ * arrays.  For inflate plans d_in_used[n] (int64, may be NULL) receives the compressed bytes consumed, i.e.
+ * comp_len - Inflater.RemainingInput (Inflater.cs:878, trap T14). */
+int b200z_plan_run(b200z_plan *plan, const uint8_t *d_in, uint8_t *d_out, int64_t *d_out_len, int32_t *d_status,
+                   uint32_t *d_check, int64_t *d_in_used, void *cuda_stream);
+
+/* Host-buffer batch calls: the end-to-end path (pinned staging, H2D, kernels, D2H inside the call).
+ * in[i]/out[i] are HOST pointers; status[i] is per stream.  The return value is the first non-OK status, if any. */
+int b200z_deflate_batch(const uint8_t *const *in, const int64_t *in_len, int32_t n, int level, int strategy, int wrap,
+                        int end_mode, uint8_t *const *out, const int64_t *out_cap, int64_t *out_len, uint32_t *check,
+                        int32_t *status);
+int b200z_inflate_batch(const uint8_t *const *in, const int64_t *in_len, int32_t n, int wrap, uint8_t *const *out,
+                        const int64_t *out_cap, int64_t *out_len, int64_t *in_used, uint32_t *check, int32_t *status);
+/* worst-case compressed size for `len` input bytes at any level (capacity a caller should provide) */
+int64_t b200z_deflate_bound(int64_t len);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Streaming handles -- 1:1 with the members of Deflater (Zip/Compression/Deflater.cs) and Inflater
+ * (Zip/Compression/Inflater.cs) that DeflaterOutputStream / InflaterInputStream / GZip / Zip call
+ * (Streams/DeflaterOutputStream.cs:100-139, 245-275, 388-393, 506-510; Streams/InflaterInputStream.cs:658-690).
+ * A handle buffers input on the host and runs the device pipeline when Flush()/Finish() makes output due; the
+ * concatenated output equals the reference's for the same sequence of calls.  One handle = one
+ * logical thread at a time; different handles may be used from different threads.
+ * ------------------------------------------------------------------------------------------------------------- */
+int b200z_deflater_create(int level, int raw /* noZlibHeaderOrFooter */, void **h); /* Deflater.cs:178 */
+int b200z_deflater_destroy(void *h);
+int b200z_deflater_reset(void *h);                                                  /* :204 */
+int b200z_deflater_set_level(void *h, int level);                                   /* :349 */
+int b200z_deflater_get_level(void *h, int *level);                                  /* :371 */
+int b200z_deflater_set_strategy(void *h, int strategy);                             /* :385 */
+int b200z_deflater_set_dictionary(void *h, const uint8_t *dict, int32_t len);       /* :559 */
+int b200z_deflater_set_input(void *h, const uint8_t *buf, int32_t len);             /* :331 (copies) */
+int b200z_deflater_flush(void *h);                                                  /* :252 */
+int b200z_deflater_finish(void *h);                                                 /* :262 */
+int b200z_deflater_deflate(void *h, uint8_t *out, int32_t cap, int32_t *produced);  /* :427 */
+int b200z_deflater_needs_input(void *h, int *flag);                                 /* :285 */
+int b200z_deflater_is_finished(void *h, int *flag);                                 /* :271 */
+int b200z_deflater_total_in(void *h, int64_t *v);                                   /* :226 */
+int b200z_deflater_total_out(void *h, int64_t *v);                                  /* :237 */
+int b200z_deflater_adler(void *h, uint32_t *v);                                     /* :215 */
+
+int b200z_inflater_create(int raw /* noHeader */, void **h);                        /* Inflater.cs:172 */
+int b200z_inflater_destroy(void *h);
+int b200z_inflater_reset(void *h);                                                  /* :188 */
+int b200z_inflater_set_dictionary(void *h, const uint8_t *dict, int32_t len);       /* :589 */
+int b200z_inflater_set_input(void *h, const uint8_t *buf, int32_t len);             /* :653 (copies) */
+int b200z_inflater_inflate(void *h, uint8_t *out, int32_t cap, int32_t *produced);  /* :715 */
+int b200z_inflater_needs_input(void *h, int *flag);                                 /* :783 */
+int b200z_inflater_needs_dictionary(void *h, int *flag);                            /* :794 */
+int b200z_inflater_is_finished(void *h, int *flag);                                 /* :806 */
+int b200z_inflater_remaining_input(void *h, int32_t *v);                            /* :878 */
+int b200z_inflater_total_in(void *h, int64_t *v);                                   /* :862 */
+int b200z_inflater_total_out(void *h, int64_t *v);                                  /* :848 */
+int b200z_inflater_adler(void *h, uint32_t *v);                                     /* :823 */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200Z_H */

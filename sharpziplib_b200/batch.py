@@ -1,0 +1,107 @@
+"""Batch plans over device tensors (what bench.py drives) and host-buffer batch helpers.
+
+torch is used for device memory and streams only; every kernel launch happens inside libb200z.so.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+
+class _Plan:
+    def __init__(self, handle, n):
+        self._h = handle
+        self.n = n
+        L = _lib.lib()
+        self.in_bytes = L.b200z_plan_in_bytes(handle)
+        self.out_bytes = L.b200z_plan_out_bytes(handle)
+        self.in_offsets = np.array([L.b200z_plan_in_offset(handle, i) for i in range(n)], dtype=np.int64)
+        self.out_offsets = np.array([L.b200z_plan_out_offset(handle, i) for i in range(n)], dtype=np.int64)
+        self.workspace_bytes = L.b200z_plan_workspace_bytes(handle)
+        self.launches = L.b200z_plan_launches(handle)
+
+    def close(self):
+        if self._h:
+            _lib.lib().b200z_plan_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def run(self, d_in, d_out, d_out_len, d_status, d_check=None, d_in_used=None, stream=None):
+        """All arguments are CUDA torch tensors (uint8 blobs, int64 lengths, int32 status, uint32/int32 checks).
+        Launches on `stream` (a torch.cuda.Stream) or the current stream; does not synchronise."""
+        import torch
+        s = stream if stream is not None else torch.cuda.current_stream()
+        assert d_in.is_cuda and d_out.is_cuda and d_in.numel() >= self.in_bytes and d_out.numel() >= self.out_bytes
+        rc = _lib.lib().b200z_plan_run(self._h, d_in.data_ptr(), d_out.data_ptr(), d_out_len.data_ptr(),
+                                       d_status.data_ptr(), d_check.data_ptr() if d_check is not None else None,
+                                       d_in_used.data_ptr() if d_in_used is not None else None, s.cuda_stream)
+        _lib.raise_for(rc)
+
+
+class DeflatePlan(_Plan):
+    """n independent streams, each what `new Deflater(level, true)` + SetInput(all) + Finish() would produce."""
+
+    def __init__(self, in_lens, level=6, strategy=0, wrap=_lib.WRAP_RAW, end_mode=_lib.END_FINISH):
+        lens = np.ascontiguousarray(in_lens, dtype=np.int64)
+        h = C.c_void_p()
+        _lib.raise_for(_lib.lib().b200z_deflate_plan_create(lens.size, lens.ctypes.data, level, strategy, wrap, end_mode,
+                                                           C.byref(h)))
+        self.in_lens = lens
+        super().__init__(h, lens.size)
+
+
+class InflatePlan(_Plan):
+    """n independent raw deflate streams of comp_lens bytes decoding into at most out_caps bytes each."""
+
+    def __init__(self, comp_lens, out_caps, wrap=_lib.WRAP_RAW):
+        cl = np.ascontiguousarray(comp_lens, dtype=np.int64)
+        oc = np.ascontiguousarray(out_caps, dtype=np.int64)
+        h = C.c_void_p()
+        _lib.raise_for(_lib.lib().b200z_inflate_plan_create(cl.size, cl.ctypes.data, oc.ctypes.data, wrap, C.byref(h)))
+        self.comp_lens, self.out_caps = cl, oc
+        super().__init__(h, cl.size)
+
+
+def _ptr_array(arrs):
+    return (C.c_void_p * len(arrs))(*[a.ctypes.data if a.size else None for a in arrs])
+
+
+def deflate_batch(buffers, level=6, strategy=0, wrap=_lib.WRAP_RAW, end_mode=_lib.END_FINISH):
+    """Host buffers in, list of compressed bytes out (b200z_deflate_batch: H2D, kernels, D2H inside the call).
+    Returns (outputs, checks)."""
+    n = len(buffers)
+    ins = [np.ascontiguousarray(np.frombuffer(b, dtype=np.uint8)) for b in buffers]
+    lens = np.array([a.size for a in ins], dtype=np.int64)
+    caps = np.array([_lib.lib().b200z_deflate_bound(int(l)) + 16 for l in lens], dtype=np.int64)
+    outs = [np.empty(int(c), dtype=np.uint8) for c in caps]
+    out_len = np.zeros(n, dtype=np.int64)
+    check = np.zeros(n, dtype=np.uint32)
+    status = np.zeros(n, dtype=np.int32)
+    rc = _lib.lib().b200z_deflate_batch(_ptr_array(ins), lens.ctypes.data, n, level, strategy, wrap, end_mode,
+                                        _ptr_array(outs), caps.ctypes.data, out_len.ctypes.data, check.ctypes.data,
+                                        status.ctypes.data)
+    _lib.raise_for(rc)
+    return [outs[i][:out_len[i]].tobytes() for i in range(n)], check
+
+
+def inflate_batch(buffers, out_caps, raise_on_error=True):
+    """Host raw-deflate buffers in, (outputs, in_used, status) out.  status[i] = code | detail << 8."""
+    n = len(buffers)
+    ins = [np.ascontiguousarray(np.frombuffer(b, dtype=np.uint8)) for b in buffers]
+    lens = np.array([a.size for a in ins], dtype=np.int64)
+    caps = np.ascontiguousarray(out_caps, dtype=np.int64)
+    outs = [np.empty(int(c) + 1, dtype=np.uint8) for c in caps]
+    out_len = np.zeros(n, dtype=np.int64)
+    in_used = np.zeros(n, dtype=np.int64)
+    check = np.zeros(n, dtype=np.uint32)
+    status = np.zeros(n, dtype=np.int32)
+    rc = _lib.lib().b200z_inflate_batch(_ptr_array(ins), lens.ctypes.data, n, _lib.WRAP_RAW, _ptr_array(outs),
+                                        caps.ctypes.data, out_len.ctypes.data, in_used.ctypes.data, check.ctypes.data,
+                                        status.ctypes.data)
+    if raise_on_error:
+        _lib.raise_for(rc)
+    elif rc in (_lib.E_CUDA, _lib.E_ARG):
+        _lib.raise_for(rc)
+    return [outs[i][:out_len[i]].tobytes() for i in range(n)], in_used, status

@@ -1,0 +1,954 @@
+// b200z_api.cu -- the C-ABI of libb200z.so (include/b200z.h): context, plans, host-buffer batch calls and the
+// streaming handles that mirror Deflater.cs / Inflater.cs member for member.  No CPU codec lives here: every byte of
+// compressed or decompressed data is produced by the kernels in b200z_deflate.cu / b200z_inflate.cu.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+#include "b200z_internal.cuh"
+
+namespace b200z {
+
+static thread_local std::string g_err;
+static std::mutex g_mu;
+static int g_device = -1;
+
+void set_error(const char *fmt, ...) {
+	char buf[512];
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(buf, sizeof(buf), fmt, ap);
+	va_end(ap);
+	g_err = buf;
+}
+
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line) {
+	set_error("CUDA error %d (%s) at %s:%d in %s", (int)e, cudaGetErrorString(e), file, line, what);
+	return B200Z_E_CUDA;
+}
+
+int ensure_init() {
+	std::lock_guard<std::mutex> lk(g_mu);
+	if (g_device >= 0) return B200Z_OK;
+	int cnt = 0;
+	cudaError_t e = cudaGetDeviceCount(&cnt);
+	if (e != cudaSuccess || cnt == 0) {
+		set_error("no CUDA device: libb200z has no CPU fallback (%s)", e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+		return B200Z_E_CUDA;
+	}
+	int dev = 0;
+	B200Z_CUDA(cudaGetDevice(&dev));
+	g_device = dev;
+	return B200Z_OK;
+}
+
+int Arena::alloc() {
+	size = align_up(used + 256, 256);
+	cudaError_t e = cudaMalloc(&base, (size_t)size);
+	if (e != cudaSuccess) {
+		base = nullptr;
+		set_error("cudaMalloc of %lld workspace bytes failed: %s", (long long)size, cudaGetErrorString(e));
+		return B200Z_E_NOMEM;
+	}
+	return B200Z_OK;
+}
+void Arena::release() {
+	if (base) cudaFree(base);
+	base = nullptr;
+}
+
+// ---- static tables blob ---------------------------------------------------------------------------
+static void fill_static_blob(uint8_t *b) {
+	// encoder side: DeflaterHuffman static ctor (:602-642); decoder side: InflaterHuffmanTree static ctor (:34-70)
+	size_t o = 0;
+	for (int i = 0; i < kLiteralNum; i++) {
+		uint16_t c = (uint16_t)static_lcode(i);
+		memcpy(b + o, &c, 2);
+		o += 2;
+	}
+	for (int i = 0; i < kLiteralNum; i++) b[o++] = (uint8_t)static_llen(i);
+	for (int i = 0; i < kDistNum; i++) {
+		uint16_t c = (uint16_t)static_dcode(i);
+		memcpy(b + o, &c, 2);
+		o += 2;
+	}
+	for (int i = 0; i < kDistNum; i++) b[o++] = 5;
+	for (int i = 0; i < 288; i++) b[o++] = (uint8_t)(i < 144 ? 8 : (i < 256 ? 9 : (i < 280 ? 7 : 8)));
+	for (int i = 0; i < 32; i++) b[o++] = 5;
+}
+constexpr int kStaticBlob = kLiteralNum * 3 + kDistNum * 3 + 288 + 32;
+
+// ---- small host helpers ----------------------------------------------------------------------------
+struct HostBits { // carries the sub-byte tail of a flushed stream on the host (PendingBuffer's `bits`, :23-24)
+	uint32_t bits = 0;
+	int count = 0;
+	void put(std::vector<uint8_t> &out, uint32_t v, int n) {
+		bits |= v << count;
+		count += n;
+		while (count >= 8) {
+			out.push_back((uint8_t)bits);
+			bits >>= 8;
+			count -= 8;
+		}
+	}
+	void align(std::vector<uint8_t> &out) {
+		if (count > 0) out.push_back((uint8_t)bits);
+		bits = 0;
+		count = 0;
+	}
+};
+
+struct PinnedBuf {
+	uint8_t *p = nullptr;
+	size_t cap = 0;
+	int ensure(size_t n) {
+		if (n <= cap) return B200Z_OK;
+		if (p) cudaFreeHost(p);
+		p = nullptr;
+		cap = 0;
+		cudaError_t e = cudaHostAlloc((void **)&p, n, cudaHostAllocDefault);
+		if (e != cudaSuccess) {
+			set_error("cudaHostAlloc of %zu bytes failed: %s", n, cudaGetErrorString(e));
+			return B200Z_E_NOMEM;
+		}
+		cap = n;
+		return B200Z_OK;
+	}
+	~PinnedBuf() {
+		if (p) cudaFreeHost(p);
+	}
+};
+
+struct DevBuf {
+	uint8_t *p = nullptr;
+	size_t cap = 0;
+	int ensure(size_t n) {
+		if (n <= cap) return B200Z_OK;
+		if (p) cudaFree(p);
+		p = nullptr;
+		cap = 0;
+		cudaError_t e = cudaMalloc((void **)&p, n);
+		if (e != cudaSuccess) {
+			set_error("cudaMalloc of %zu bytes failed: %s", n, cudaGetErrorString(e));
+			return B200Z_E_NOMEM;
+		}
+		cap = n;
+		return B200Z_OK;
+	}
+	~DevBuf() {
+		if (p) cudaFree(p);
+	}
+};
+
+// Runs one plan end to end from host buffers: pinned staging, H2D, kernels, D2H.
+struct HostRunResult {
+	std::vector<int64_t> out_len, in_used;
+	std::vector<int32_t> status;
+	std::vector<uint32_t> check;
+};
+
+static int run_plan_host(b200z_plan *plan, const uint8_t *const *in, PinnedBuf &hin, PinnedBuf &hout, DevBuf &din,
+                         DevBuf &dout, DevBuf &dmeta, HostRunResult &r, bool fetch_all_out) {
+	const int n = plan->n;
+	int rc;
+	if ((rc = hin.ensure((size_t)plan->in_bytes + 256))) return rc;
+	if ((rc = din.ensure((size_t)plan->in_bytes + 256))) return rc;
+	if ((rc = dout.ensure((size_t)plan->out_bytes + 256))) return rc;
+	const size_t meta_bytes = (size_t)n * (8 + 8 + 4 + 4) + 256;
+	if ((rc = dmeta.ensure(meta_bytes))) return rc;
+	for (int i = 0; i < n; i++)
+		if (plan->in_len[i]) memcpy(hin.p + plan->in_off[i], in[i], (size_t)plan->in_len[i]);
+	cudaStream_t s = 0;
+	B200Z_CUDA(cudaMemcpyAsync(din.p, hin.p, (size_t)plan->in_bytes, cudaMemcpyHostToDevice, s));
+	int64_t *d_out_len = reinterpret_cast<int64_t *>(dmeta.p);
+	int64_t *d_in_used = d_out_len + n;
+	int32_t *d_status = reinterpret_cast<int32_t *>(d_in_used + n);
+	uint32_t *d_check = reinterpret_cast<uint32_t *>(d_status + n);
+	rc = b200z_plan_run(plan, din.p, dout.p, d_out_len, d_status, d_check, d_in_used, (void *)s);
+	if (rc) return rc;
+	r.out_len.assign(n, 0);
+	r.in_used.assign(n, 0);
+	r.status.assign(n, 0);
+	r.check.assign(n, 0);
+	B200Z_CUDA(cudaMemcpyAsync(r.out_len.data(), d_out_len, 8ull * n, cudaMemcpyDeviceToHost, s));
+	B200Z_CUDA(cudaMemcpyAsync(r.in_used.data(), d_in_used, 8ull * n, cudaMemcpyDeviceToHost, s));
+	B200Z_CUDA(cudaMemcpyAsync(r.status.data(), d_status, 4ull * n, cudaMemcpyDeviceToHost, s));
+	B200Z_CUDA(cudaMemcpyAsync(r.check.data(), d_check, 4ull * n, cudaMemcpyDeviceToHost, s));
+	if ((rc = hout.ensure((size_t)plan->out_bytes + 256))) return rc;
+	if (fetch_all_out) {
+		B200Z_CUDA(cudaMemcpyAsync(hout.p, dout.p, (size_t)plan->out_bytes, cudaMemcpyDeviceToHost, s));
+		B200Z_CUDA(cudaStreamSynchronize(s));
+	} else {
+		B200Z_CUDA(cudaStreamSynchronize(s));
+		for (int i = 0; i < n; i++) {
+			if (r.out_len[i] > 0)
+				B200Z_CUDA(cudaMemcpyAsync(hout.p + plan->out_off[i], dout.p + plan->out_off[i], (size_t)r.out_len[i],
+				                           cudaMemcpyDeviceToHost, s));
+		}
+		B200Z_CUDA(cudaStreamSynchronize(s));
+	}
+	return B200Z_OK;
+}
+
+} // namespace b200z
+
+using namespace b200z;
+
+extern "C" {
+
+const char *b200z_last_error(void) { return g_err.c_str(); }
+int b200z_version(void) { return 100; }
+
+int b200z_init(int device) {
+	{
+		std::lock_guard<std::mutex> lk(g_mu);
+		int cnt = 0;
+		cudaError_t e = cudaGetDeviceCount(&cnt);
+		if (e != cudaSuccess || cnt == 0) {
+			set_error("no CUDA device: libb200z has no CPU fallback (%s)", e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+			return B200Z_E_CUDA;
+		}
+		if (device < 0 || device >= cnt) {
+			set_error("device %d out of range (%d devices)", device, cnt);
+			return B200Z_E_ARG;
+		}
+		B200Z_CUDA(cudaSetDevice(device));
+		g_device = device;
+	}
+	return checksum_init_tables();
+}
+
+int b200z_static_tables_size(void) { return kStaticBlob; }
+int b200z_static_tables_export(uint8_t *blob, int32_t cap) {
+	if (!blob || cap < kStaticBlob) {
+		set_error("static table blob needs %d bytes", kStaticBlob);
+		return B200Z_E_ARG;
+	}
+	fill_static_blob(blob);
+	return B200Z_OK;
+}
+int b200z_static_tables_import(const uint8_t *blob, int32_t len) {
+	// The kernels derive the static codes arithmetically (b200z_core.cuh static_lcode/static_llen), so installing a
+	// broadcast copy reduces to verifying that the sender's tables are the ones this rank would use.
+	if (!blob || len != kStaticBlob) {
+		set_error("static table blob has %d bytes, expected %d", len, kStaticBlob);
+		return B200Z_E_ARG;
+	}
+	uint8_t mine[kStaticBlob];
+	fill_static_blob(mine);
+	if (memcmp(mine, blob, kStaticBlob) != 0) {
+		set_error("static Huffman tables received from the root differ from the local ones");
+		return B200Z_E_DATA;
+	}
+	return B200Z_OK;
+}
+
+int64_t b200z_deflate_bound(int64_t len) { return len + (len >> 3) + 1024; }
+
+// ---- plans -------------------------------------------------------------------------------------------
+int b200z_deflate_plan_create(int32_t n, const int64_t *in_len, int level, int strategy, int wrap, int end_mode,
+                              b200z_plan **plan) {
+	if (!plan || n < 0 || (n > 0 && !in_len)) {
+		set_error("bad arguments");
+		return B200Z_E_ARG;
+	}
+	if (level == -1) level = 6;
+	if (level < 0 || level > 9) {
+		set_error("level");
+		return B200Z_E_ARG;
+	}
+	if (strategy < 0 || strategy > 2 || wrap < 0 || wrap > 2 || end_mode < 0 || end_mode > 2) {
+		set_error("strategy/wrap/end_mode");
+		return B200Z_E_ARG;
+	}
+	int rc = ensure_init();
+	if (rc) return rc;
+	b200z_plan *p = new b200z_plan();
+	p->kind = 0;
+	p->n = n;
+	p->level = level;
+	p->strategy = strategy;
+	p->wrap = wrap;
+	p->end_mode = end_mode;
+	p->in_len.assign(in_len, in_len + n);
+	rc = deflate_plan_build(p);
+	if (rc) {
+		p->ws.release();
+		delete p;
+		return rc;
+	}
+	*plan = p;
+	return B200Z_OK;
+}
+
+int b200z_inflate_plan_create(int32_t n, const int64_t *comp_len, const int64_t *out_cap, int wrap, b200z_plan **plan) {
+	if (!plan || n < 0 || (n > 0 && (!comp_len || !out_cap)) || wrap < 0 || wrap > 2) {
+		set_error("bad arguments");
+		return B200Z_E_ARG;
+	}
+	int rc = ensure_init();
+	if (rc) return rc;
+	b200z_plan *p = new b200z_plan();
+	p->kind = 1;
+	p->n = n;
+	p->wrap = wrap;
+	p->in_len.assign(comp_len, comp_len + n);
+	p->out_cap.assign(out_cap, out_cap + n);
+	rc = inflate_plan_build(p);
+	if (rc) {
+		p->ws.release();
+		delete p;
+		return rc;
+	}
+	*plan = p;
+	return B200Z_OK;
+}
+
+int b200z_plan_destroy(b200z_plan *plan) {
+	if (!plan) return B200Z_OK;
+	plan->ws.release();
+	delete plan;
+	return B200Z_OK;
+}
+int64_t b200z_plan_in_bytes(const b200z_plan *p) { return p->in_bytes; }
+int64_t b200z_plan_out_bytes(const b200z_plan *p) { return p->out_bytes; }
+int64_t b200z_plan_in_offset(const b200z_plan *p, int32_t i) { return p->in_off[i]; }
+int64_t b200z_plan_out_offset(const b200z_plan *p, int32_t i) { return p->out_off[i]; }
+int64_t b200z_plan_out_capacity(const b200z_plan *p, int32_t i) { return p->out_cap[i]; }
+int64_t b200z_plan_workspace_bytes(const b200z_plan *p) { return p->ws.size; }
+int32_t b200z_plan_launches(const b200z_plan *p) { return p->launches; }
+
+int b200z_plan_run(b200z_plan *plan, const uint8_t *d_in, uint8_t *d_out, int64_t *d_out_len, int32_t *d_status,
+                   uint32_t *d_check, int64_t *d_in_used, void *cuda_stream) {
+	if (!plan || !d_in || !d_out || !d_out_len || !d_status) {
+		set_error("bad arguments");
+		return B200Z_E_ARG;
+	}
+	cudaStream_t s = (cudaStream_t)cuda_stream;
+	if (plan->kind == 0) return deflate_plan_run(plan, d_in, d_out, d_out_len, d_status, d_check, d_in_used, s);
+	return inflate_plan_run(plan, d_in, d_out, d_out_len, d_status, d_check, d_in_used, s);
+}
+
+// ---- checksums ---------------------------------------------------------------------------------------
+static int checksum_host(int kind, const uint8_t *buf, int64_t len, uint32_t *value) {
+	if (!value || len < 0 || (len > 0 && !buf)) {
+		set_error("bad arguments");
+		return B200Z_E_ARG;
+	}
+	int rc = ensure_init();
+	if (rc) return rc;
+	if (len == 0) return B200Z_OK;
+	DevBuf d, meta;
+	if ((rc = d.ensure((size_t)len + 256))) return rc;
+	B200Z_CUDA(cudaMemcpy(d.p, buf, (size_t)len, cudaMemcpyHostToDevice));
+	std::vector<CkTile> tiles;
+	checksum_tiles(&len, 1, tiles, kind);
+	const size_t tb = sizeof(CkTile) * tiles.size();
+	if ((rc = meta.ensure(tb + 256))) return rc;
+	int64_t *d_off = reinterpret_cast<int64_t *>(meta.p);
+	int64_t *d_len = d_off + 1;
+	unsigned long long *d_acc = reinterpret_cast<unsigned long long *>(d_len + 1);
+	uint32_t *d_val = reinterpret_cast<uint32_t *>(d_acc + 2);
+	CkTile *d_tiles = reinterpret_cast<CkTile *>(meta.p + 64);
+	int64_t zero = 0;
+	B200Z_CUDA(cudaMemcpy(d_off, &zero, 8, cudaMemcpyHostToDevice));
+	B200Z_CUDA(cudaMemcpy(d_len, &len, 8, cudaMemcpyHostToDevice));
+	B200Z_CUDA(cudaMemcpy(d_val, value, 4, cudaMemcpyHostToDevice));
+	B200Z_CUDA(cudaMemcpy(d_tiles, tiles.data(), tb, cudaMemcpyHostToDevice));
+	rc = checksum_launch(kind, d.p, d_off, d_len, 1, d_tiles, (int32_t)tiles.size(), d_acc, d_val, 0, 0);
+	if (rc) return rc;
+	B200Z_CUDA(cudaMemcpy(value, d_val, 4, cudaMemcpyDeviceToHost));
+	return B200Z_OK;
+}
+int b200z_crc32(const uint8_t *buf, int64_t len, uint32_t *value) { return checksum_host(0, buf, len, value); }
+int b200z_adler32(const uint8_t *buf, int64_t len, uint32_t *value) { return checksum_host(1, buf, len, value); }
+
+int b200z_checksum_batch_device(int kind, const uint8_t *d_data, const int64_t *off, const int64_t *len, int32_t n,
+                                uint32_t *d_value, void *cuda_stream) {
+	if (kind < 0 || kind > 1 || n < 0 || (n > 0 && (!d_data || !off || !len || !d_value))) {
+		set_error("bad arguments");
+		return B200Z_E_ARG;
+	}
+	int rc = ensure_init();
+	if (rc) return rc;
+	if (n == 0) return B200Z_OK;
+	cudaStream_t s = (cudaStream_t)cuda_stream;
+	std::vector<CkTile> tiles;
+	checksum_tiles(len, n, tiles, kind);
+	const size_t tb = sizeof(CkTile) * tiles.size();
+	uint8_t *meta = nullptr;
+	const size_t bytes = 16ull * n + 16ull * n + tb + 256;
+	B200Z_CUDA(cudaMallocAsync((void **)&meta, bytes, s));
+	int64_t *d_off = reinterpret_cast<int64_t *>(meta);
+	int64_t *d_len = d_off + n;
+	unsigned long long *d_acc = reinterpret_cast<unsigned long long *>(d_len + n);
+	CkTile *d_tiles = reinterpret_cast<CkTile *>(d_acc + 2 * n);
+	B200Z_CUDA(cudaMemcpyAsync(d_off, off, 8ull * n, cudaMemcpyHostToDevice, s));
+	B200Z_CUDA(cudaMemcpyAsync(d_len, len, 8ull * n, cudaMemcpyHostToDevice, s));
+	if (tb) B200Z_CUDA(cudaMemcpyAsync(d_tiles, tiles.data(), tb, cudaMemcpyHostToDevice, s));
+	rc = checksum_launch(kind, d_data, d_off, d_len, n, d_tiles, (int32_t)tiles.size(), d_acc, d_value, 0, s);
+	B200Z_CUDA(cudaStreamSynchronize(s)); // the pageable descriptor copies above must finish before `tiles` dies
+	B200Z_CUDA(cudaFreeAsync(meta, s));
+	return rc;
+}
+
+// ---- host-buffer batch calls ----------------------------------------------------------------------------
+static void zlib_header(int level, uint8_t h[2]) { // Deflater.cs:436-464 (trap T11)
+	int header = (8 + (7 << 4)) << 8;
+	int level_flags = (level - 1) >> 1;
+	if (level_flags < 0 || level_flags > 3) level_flags = 3;
+	header |= level_flags << 6;
+	header += 31 - (header % 31);
+	h[0] = (uint8_t)(header >> 8);
+	h[1] = (uint8_t)header;
+}
+
+int b200z_deflate_batch(const uint8_t *const *in, const int64_t *in_len, int32_t n, int level, int strategy, int wrap,
+                        int end_mode, uint8_t *const *out, const int64_t *out_cap, int64_t *out_len, uint32_t *check,
+                        int32_t *status) {
+	if (n < 0 || (n > 0 && (!in || !in_len || !out || !out_cap || !out_len))) {
+		set_error("bad arguments");
+		return B200Z_E_ARG;
+	}
+	if (wrap == B200Z_WRAP_GZIP) {
+		// GZipOutputStream's header carries caller state (MTIME, FNAME; GzipOutputStream.cs:339-375): the host shim
+		// writes header and trailer around the raw stream and takes the CRC32 from `check`.
+		set_error("gzip framing is written by the host stream layer; deflate with wrap=RAW and use check (CRC32)");
+		return B200Z_E_UNSUPPORTED;
+	}
+	if (level == -1) level = 6;
+	b200z_plan *plan = nullptr;
+	int rc = b200z_deflate_plan_create(n, in_len, level, strategy, wrap, end_mode, &plan);
+	if (rc) return rc;
+	PinnedBuf hin, hout;
+	DevBuf din, dout, dmeta;
+	HostRunResult r;
+	rc = run_plan_host(plan, in, hin, hout, din, dout, dmeta, r, false);
+	int first = B200Z_OK;
+	if (!rc) {
+		for (int i = 0; i < n; i++) {
+			int st = r.status[i] & 0xFF;
+			int64_t need = r.out_len[i] + (wrap == B200Z_WRAP_ZLIB ? 6 : 0);
+			if (st == B200Z_OK && need > out_cap[i]) st = B200Z_E_NOMEM;
+			if (st == B200Z_OK) {
+				uint8_t *o = out[i];
+				if (wrap == B200Z_WRAP_ZLIB) {
+					zlib_header(level, o);
+					o += 2;
+				}
+				memcpy(o, hout.p + plan->out_off[i], (size_t)r.out_len[i]);
+				o += r.out_len[i];
+				if (wrap == B200Z_WRAP_ZLIB) { // Adler32 trailer, big endian (Deflater.cs:509-514)
+					const uint32_t a = r.check[i];
+					o[0] = (uint8_t)(a >> 24);
+					o[1] = (uint8_t)(a >> 16);
+					o[2] = (uint8_t)(a >> 8);
+					o[3] = (uint8_t)a;
+				}
+				out_len[i] = need;
+			} else {
+				out_len[i] = 0;
+				if (first == B200Z_OK) first = st;
+			}
+			if (status) status[i] = st;
+			if (check) check[i] = r.check[i];
+		}
+	}
+	b200z_plan_destroy(plan);
+	if (rc) return rc;
+	if (first != B200Z_OK) set_error("stream failed with status %d", first);
+	return first;
+}
+
+int b200z_inflate_batch(const uint8_t *const *in, const int64_t *in_len, int32_t n, int wrap, uint8_t *const *out,
+                        const int64_t *out_cap, int64_t *out_len, int64_t *in_used, uint32_t *check, int32_t *status) {
+	if (n < 0 || (n > 0 && (!in || !in_len || !out || !out_cap || !out_len))) {
+		set_error("bad arguments");
+		return B200Z_E_ARG;
+	}
+	if (wrap != B200Z_WRAP_RAW) {
+		set_error("zlib/gzip framing is parsed by the host stream layer (Inflater handle / GZipInputStream shim)");
+		return B200Z_E_UNSUPPORTED;
+	}
+	b200z_plan *plan = nullptr;
+	int rc = b200z_inflate_plan_create(n, in_len, out_cap, wrap, &plan);
+	if (rc) return rc;
+	PinnedBuf hin, hout;
+	DevBuf din, dout, dmeta;
+	HostRunResult r;
+	rc = run_plan_host(plan, in, hin, hout, din, dout, dmeta, r, false);
+	int first = B200Z_OK;
+	if (!rc) {
+		for (int i = 0; i < n; i++) {
+			const int st = r.status[i];
+			if (r.out_len[i] > 0) memcpy(out[i], hout.p + plan->out_off[i], (size_t)r.out_len[i]);
+			out_len[i] = r.out_len[i];
+			if (in_used) in_used[i] = r.in_used[i];
+			if (status) status[i] = st;
+			if (check) check[i] = 0;
+			if ((st & 0xFF) != B200Z_OK && first == B200Z_OK) first = st & 0xFF;
+		}
+	}
+	b200z_plan_destroy(plan);
+	if (rc) return rc;
+	if (first != B200Z_OK) set_error("stream failed with status %d", first);
+	return first;
+}
+
+// =====================================================================================================
+// Streaming handles
+// =====================================================================================================
+struct DeflaterH {
+	int level = 6, strategy = 0;
+	bool raw = false;
+	// Deflater.cs state bits (:96-110)
+	bool flushing = false, finishing = false, finished = false;
+	bool header_done = false;
+	bool flushed_once = false; // a sync flush has been emitted for the current segment
+	std::vector<uint8_t> input;    // everything SetInput handed over and not yet compressed
+	std::vector<uint8_t> pending;  // produced bytes not yet drained by Deflate()
+	size_t pending_pos = 0;
+	HostBits tail;                 // sub-byte tail carried between device runs
+	int64_t total_in = 0, total_out = 0;
+	uint32_t adler = 1;
+	PinnedBuf hin, hout;
+	DevBuf din, dout, dmeta;
+};
+
+static int deflater_run_device(DeflaterH *d, int end_mode) {
+	// compresses d->input as one stream; END_FLUSH keeps the stream open and may end inside a byte
+	if (d->tail.count != 0 || d->flushed_once) {
+		set_error("input after a sync Flush() continues a bit-unaligned stream with carried window state; this build "
+		          "only accelerates SetInput* -> [Flush] -> Finish sequences");
+		return B200Z_E_UNSUPPORTED;
+	}
+	const int64_t len = (int64_t)d->input.size();
+	b200z_plan *plan = nullptr;
+	int rc = b200z_deflate_plan_create(1, &len, d->level, d->strategy, d->raw ? B200Z_WRAP_RAW : B200Z_WRAP_ZLIB,
+	                                   end_mode, &plan);
+	if (rc) return rc;
+	const uint8_t *inp = d->input.data();
+	HostRunResult r;
+	rc = run_plan_host(plan, &inp, d->hin, d->hout, d->din, d->dout, d->dmeta, r, false);
+	if (!rc && (r.status[0] & 0xFF) != B200Z_OK) {
+		rc = r.status[0] & 0xFF;
+		set_error("device deflate failed with status %d", rc);
+	}
+	if (!rc) {
+		const uint8_t *o = d->hout.p + plan->out_off[0];
+		const int64_t bits = r.in_used[0]; // deflate plans report the exact bit length here
+		const int64_t whole = bits >> 3;
+		d->pending.insert(d->pending.end(), o, o + whole);
+		if (bits & 7) {
+			// PendingBuffer keeps the sub-byte tail in `bits` until later writes complete the byte (:168-189)
+			d->tail.bits = o[whole] & ((1u << (bits & 7)) - 1u);
+			d->tail.count = (int)(bits & 7);
+		}
+		if (end_mode == B200Z_END_FINISH) d->tail.align(d->pending); // FINISHING_STATE: AlignToByte (:507)
+		if (!d->raw) d->adler = r.check[0];
+		d->total_in += len;
+		d->input.clear();
+	}
+	b200z_plan_destroy(plan);
+	return rc;
+}
+
+int b200z_deflater_create(int level, int raw, void **h) {
+	if (!h) {
+		set_error("h");
+		return B200Z_E_ARG;
+	}
+	if (level == -1) level = 6;
+	else if (level < 0 || level > 9) {
+		set_error("level"); // ArgumentOutOfRangeException(nameof(level)), Deflater.cs:184-187
+		return B200Z_E_ARG;
+	}
+	DeflaterH *d = new DeflaterH();
+	d->level = level;
+	d->raw = raw != 0;
+	*h = d;
+	return B200Z_OK;
+}
+int b200z_deflater_destroy(void *h) {
+	delete (DeflaterH *)h;
+	return B200Z_OK;
+}
+int b200z_deflater_reset(void *h) { // Deflater.Reset :204-210 keeps level and strategy
+	DeflaterH *d = (DeflaterH *)h;
+	d->flushing = d->finishing = d->finished = false;
+	d->header_done = false;
+	d->flushed_once = false;
+	d->input.clear();
+	d->pending.clear();
+	d->pending_pos = 0;
+	d->tail = HostBits();
+	d->total_in = d->total_out = 0;
+	d->adler = 1;
+	return B200Z_OK;
+}
+int b200z_deflater_set_level(void *h, int level) {
+	DeflaterH *d = (DeflaterH *)h;
+	if (level == -1) level = 6;
+	else if (level < 0 || level > 9) {
+		set_error("level");
+		return B200Z_E_ARG;
+	}
+	if (level != d->level && (!d->input.empty() || d->total_in > 0)) {
+		set_error("SetLevel in mid-stream (DeflaterEngine.SetLevel flushes a block, trap T17) is not accelerated");
+		return B200Z_E_UNSUPPORTED;
+	}
+	d->level = level;
+	return B200Z_OK;
+}
+int b200z_deflater_get_level(void *h, int *level) {
+	*level = ((DeflaterH *)h)->level;
+	return B200Z_OK;
+}
+int b200z_deflater_set_strategy(void *h, int strategy) {
+	if (strategy < 0 || strategy > 2) {
+		set_error("strategy");
+		return B200Z_E_ARG;
+	}
+	((DeflaterH *)h)->strategy = strategy;
+	return B200Z_OK;
+}
+int b200z_deflater_set_dictionary(void *h, const uint8_t *, int32_t) {
+	(void)h;
+	set_error("preset dictionaries (Deflater.SetDictionary, DeflaterEngine.cs:198-229) are not accelerated by this build");
+	return B200Z_E_UNSUPPORTED;
+}
+int b200z_deflater_set_input(void *h, const uint8_t *buf, int32_t len) {
+	DeflaterH *d = (DeflaterH *)h;
+	if (d->finishing) {
+		set_error("Finish() already called"); // Deflater.cs:335
+		return B200Z_E_STATE;
+	}
+	if (len < 0 || (len > 0 && !buf)) {
+		set_error("buffer/count");
+		return B200Z_E_ARG;
+	}
+	if (d->flushed_once && len > 0) {
+		set_error("input after a sync Flush() is not accelerated by this build (carried window + bit tail)");
+		return B200Z_E_UNSUPPORTED;
+	}
+	d->input.insert(d->input.end(), buf, buf + len);
+	return B200Z_OK;
+}
+int b200z_deflater_flush(void *h) {
+	((DeflaterH *)h)->flushing = true;
+	return B200Z_OK;
+}
+int b200z_deflater_finish(void *h) {
+	DeflaterH *d = (DeflaterH *)h;
+	d->flushing = d->finishing = true;
+	return B200Z_OK;
+}
+
+int b200z_deflater_deflate(void *h, uint8_t *out, int32_t cap, int32_t *produced) {
+	DeflaterH *d = (DeflaterH *)h;
+	if (!produced || cap < 0 || (cap > 0 && !out)) {
+		set_error("bad arguments");
+		return B200Z_E_ARG;
+	}
+	*produced = 0;
+	// make output due (Deflater.Deflate :427-522)
+	if (!d->finished && d->pending_pos == d->pending.size() && (d->flushing || d->finishing)) {
+		d->pending.clear();
+		d->pending_pos = 0;
+		if (!d->header_done && !d->raw) {
+			uint8_t hd[2];
+			zlib_header(d->level, hd);
+			d->pending.push_back(hd[0]);
+			d->pending.push_back(hd[1]);
+		}
+		d->header_done = true;
+		if (d->finishing) {
+			if (d->flushed_once) {
+				// Flush() already emitted every block + the sync padding; Finish adds the final empty static block
+				// (FlushBlock on an empty buffer: header 011 + EOB 0000000 = value 3 in 10 bits, DeflaterEngine.cs:750-768)
+				d->tail.put(d->pending, 3, 10);
+				d->tail.align(d->pending);
+			} else {
+				int rc = deflater_run_device(d, B200Z_END_FINISH);
+				if (rc) return rc;
+			}
+			if (!d->raw) {
+				d->pending.push_back((uint8_t)(d->adler >> 24));
+				d->pending.push_back((uint8_t)(d->adler >> 16));
+				d->pending.push_back((uint8_t)(d->adler >> 8));
+				d->pending.push_back((uint8_t)d->adler);
+			}
+			d->finished = true;
+		} else {
+			// sync flush (level 0 skips the padding, :488; level 0 is not accelerated anyway)
+			int rc = deflater_run_device(d, B200Z_END_FLUSH);
+			if (rc) return rc;
+			d->flushed_once = true;
+			d->flushing = false;
+		}
+	}
+	size_t avail = d->pending.size() - d->pending_pos;
+	size_t take = avail < (size_t)cap ? avail : (size_t)cap;
+	if (take) memcpy(out, d->pending.data() + d->pending_pos, take);
+	d->pending_pos += take;
+	d->total_out += (int64_t)take;
+	*produced = (int32_t)take;
+	return B200Z_OK;
+}
+int b200z_deflater_needs_input(void *h, int *flag) {
+	*flag = 1; // SetInput copies, so the engine's input is always consumed (DeflaterEngine.NeedsInput :187-190)
+	(void)h;
+	return B200Z_OK;
+}
+int b200z_deflater_is_finished(void *h, int *flag) {
+	DeflaterH *d = (DeflaterH *)h;
+	*flag = (d->finished && d->pending_pos == d->pending.size()) ? 1 : 0; // Deflater.cs:271-277
+	return B200Z_OK;
+}
+int b200z_deflater_total_in(void *h, int64_t *v) {
+	DeflaterH *d = (DeflaterH *)h;
+	*v = d->total_in;
+	return B200Z_OK;
+}
+int b200z_deflater_total_out(void *h, int64_t *v) {
+	*v = ((DeflaterH *)h)->total_out;
+	return B200Z_OK;
+}
+int b200z_deflater_adler(void *h, uint32_t *v) {
+	DeflaterH *d = (DeflaterH *)h;
+	*v = d->raw ? 0u : d->adler;
+	return B200Z_OK;
+}
+
+// ---- Inflater handle ----------------------------------------------------------------------------------
+struct InflaterH {
+	bool raw = false;
+	std::vector<uint8_t> input; // all compressed bytes handed over since Reset
+	bool new_input = false;
+	bool finished = false;
+	bool need_dict = false;
+	bool header_done = false;
+	size_t raw_off = 0; // where the raw deflate data starts inside `input`
+	std::vector<uint8_t> output; // decoded so far
+	size_t delivered = 0;
+	int64_t consumed = 0; // bytes of `input` the decoder has used (header + raw + trailer)
+	uint32_t adler = 1;
+	int error = 0;
+	std::string error_msg;
+	PinnedBuf hin, hout;
+	DevBuf din, dout, dmeta;
+};
+
+static const char *inflate_detail_msg(int detail) {
+	switch (detail) {
+	case 1: return "Unknown block type";
+	case 2: return "broken uncompressed block";
+	case 3: return "Illegal rep length code";
+	case 4: return "Illegal rep dist code";
+	case 5: return "Encountered invalid codelength 0";
+	case 6: return "ValueOutOfRangeException: dynamic header code count";
+	case 7: return "Cannot repeat previous code length when no other code length has been read";
+	case 8: return "Cannot repeat code lengths past total number of data code lengths";
+	case 9: return "Inflater dynamic header end-of-block code missing";
+	case 10: return "Code lengths oversubscribed";
+	default: return "corrupt deflate data";
+	}
+}
+
+// decodes everything available; fills output/consumed/finished
+static int inflater_run_device(InflaterH *d) {
+	const int64_t avail = (int64_t)d->input.size() - (int64_t)d->raw_off;
+	int64_t cap = avail * 8 + 65536;
+	for (int attempt = 0; attempt < 8; attempt++) {
+		b200z_plan *plan = nullptr;
+		int rc = b200z_inflate_plan_create(1, &avail, &cap, B200Z_WRAP_RAW, &plan);
+		if (rc) return rc;
+		const uint8_t *inp = d->input.data() + d->raw_off;
+		HostRunResult r;
+		rc = run_plan_host(plan, &inp, d->hin, d->hout, d->din, d->dout, d->dmeta, r, false);
+		if (rc) {
+			b200z_plan_destroy(plan);
+			return rc;
+		}
+		const int st = r.status[0] & 0xFF, detail = (r.status[0] >> 8) & 0xFF;
+		if (st == B200Z_E_NOMEM) {
+			b200z_plan_destroy(plan);
+			cap *= 8;
+			continue;
+		}
+		d->output.assign(d->hout.p + plan->out_off[0], d->hout.p + plan->out_off[0] + r.out_len[0]);
+		b200z_plan_destroy(plan);
+		if (st == B200Z_OK) {
+			d->finished = true;
+			d->consumed = (int64_t)d->raw_off + r.in_used[0];
+		} else if (st == B200Z_E_NEED_INPUT) {
+			d->consumed = (int64_t)d->input.size();
+		} else {
+			d->error = st;
+			d->error_msg = inflate_detail_msg(detail);
+		}
+		return B200Z_OK;
+	}
+	set_error("output larger than any capacity tried");
+	return B200Z_E_NOMEM;
+}
+
+int b200z_inflater_create(int raw, void **h) {
+	if (!h) {
+		set_error("h");
+		return B200Z_E_ARG;
+	}
+	InflaterH *d = new InflaterH();
+	d->raw = raw != 0;
+	*h = d;
+	return B200Z_OK;
+}
+int b200z_inflater_destroy(void *h) {
+	delete (InflaterH *)h;
+	return B200Z_OK;
+}
+int b200z_inflater_reset(void *h) {
+	InflaterH *d = (InflaterH *)h;
+	d->input.clear();
+	d->output.clear();
+	d->new_input = d->finished = d->need_dict = d->header_done = false;
+	d->raw_off = 0;
+	d->delivered = 0;
+	d->consumed = 0;
+	d->adler = 1;
+	d->error = 0;
+	return B200Z_OK;
+}
+int b200z_inflater_set_dictionary(void *h, const uint8_t *, int32_t) {
+	(void)h;
+	set_error("preset dictionaries (Inflater.SetDictionary, Inflater.cs:589-620) are not accelerated by this build");
+	return B200Z_E_UNSUPPORTED;
+}
+int b200z_inflater_set_input(void *h, const uint8_t *buf, int32_t len) {
+	InflaterH *d = (InflaterH *)h;
+	if (len < 0 || (len > 0 && !buf)) {
+		set_error("buffer/count");
+		return B200Z_E_ARG;
+	}
+	if ((int64_t)d->input.size() > d->consumed && !d->finished) {
+		set_error("Old input was not completely processed"); // StreamManipulator.cs:263
+		return B200Z_E_STATE;
+	}
+	if (d->finished) {
+		// after the end of the stream the reference keeps unread bytes as RemainingInput; replace them
+		d->input.resize((size_t)d->consumed);
+	}
+	d->input.insert(d->input.end(), buf, buf + len);
+	d->new_input = true;
+	return B200Z_OK;
+}
+
+int b200z_inflater_inflate(void *h, uint8_t *out, int32_t cap, int32_t *produced) {
+	InflaterH *d = (InflaterH *)h;
+	if (!produced || cap < 0 || (cap > 0 && !out)) {
+		set_error("bad arguments");
+		return B200Z_E_ARG;
+	}
+	*produced = 0;
+	if (d->error) {
+		set_error("%s", d->error_msg.c_str());
+		return d->error;
+	}
+	if (!d->finished && d->new_input) {
+		d->new_input = false;
+		if (!d->raw && !d->header_done) {
+			if (d->input.size() < 2) {
+				d->consumed = (int64_t)d->input.size();
+				return B200Z_OK; // DecodeHeader needs 16 bits (Inflater.cs:209-215)
+			}
+			const int header = (d->input[0] << 8) | d->input[1];
+			if (header % 31 != 0) {
+				d->error = B200Z_E_DATA;
+				d->error_msg = "Header checksum illegal";
+			} else if ((header & 0x0f00) != (8 << 8)) {
+				d->error = B200Z_E_DATA;
+				d->error_msg = "Compression Method unknown";
+			} else if (header & 0x0020) {
+				set_error("preset dictionaries are not accelerated by this build");
+				return B200Z_E_UNSUPPORTED;
+			}
+			if (d->error) {
+				set_error("%s", d->error_msg.c_str());
+				return d->error;
+			}
+			d->header_done = true;
+			d->raw_off = 2;
+		}
+		const size_t had = d->delivered;
+		int rc = inflater_run_device(d);
+		if (rc) return rc;
+		(void)had;
+		if (d->finished && !d->raw) {
+			// Adler32 trailer, read MSB first (DecodeChksum :397-418); until it is complete the reference withholds
+			// nothing that was already decoded but is not "finished"
+			if ((int64_t)d->input.size() - d->consumed < 4) {
+				d->finished = false;
+				d->consumed = (int64_t)d->input.size();
+				// keep output; it will be re-derived when the trailer arrives
+			} else {
+				const uint8_t *t = d->input.data() + d->consumed;
+				const uint32_t want = ((uint32_t)t[0] << 24) | ((uint32_t)t[1] << 16) | ((uint32_t)t[2] << 8) | t[3];
+				uint32_t got = 1;
+				int rc2 = b200z_adler32(d->output.data(), (int64_t)d->output.size(), &got);
+				if (rc2) return rc2;
+				d->adler = got;
+				if (got != want) {
+					d->error = B200Z_E_DATA;
+					d->error_msg = "Adler chksum doesn't match";
+				}
+				d->consumed += 4;
+			}
+		}
+	}
+	size_t avail = d->output.size() - d->delivered;
+	size_t take = avail < (size_t)cap ? avail : (size_t)cap;
+	if (take) memcpy(out, d->output.data() + d->delivered, take);
+	d->delivered += take;
+	*produced = (int32_t)take;
+	if (take == 0 && d->error) {
+		set_error("%s", d->error_msg.c_str());
+		return d->error;
+	}
+	return B200Z_OK;
+}
+int b200z_inflater_needs_input(void *h, int *flag) {
+	InflaterH *d = (InflaterH *)h;
+	*flag = ((int64_t)d->input.size() <= d->consumed) ? 1 : 0; // StreamManipulator.IsNeedingInput
+	return B200Z_OK;
+}
+int b200z_inflater_needs_dictionary(void *h, int *flag) {
+	*flag = 0;
+	(void)h;
+	return B200Z_OK;
+}
+int b200z_inflater_is_finished(void *h, int *flag) {
+	InflaterH *d = (InflaterH *)h;
+	*flag = (d->finished && d->delivered == d->output.size()) ? 1 : 0; // Inflater.cs:806-812
+	return B200Z_OK;
+}
+int b200z_inflater_remaining_input(void *h, int32_t *v) {
+	InflaterH *d = (InflaterH *)h;
+	*v = (int32_t)((int64_t)d->input.size() - d->consumed);
+	return B200Z_OK;
+}
+int b200z_inflater_total_in(void *h, int64_t *v) {
+	*v = ((InflaterH *)h)->consumed; // totalIn - RemainingInput (Inflater.cs:862-868)
+	return B200Z_OK;
+}
+int b200z_inflater_total_out(void *h, int64_t *v) {
+	*v = (int64_t)((InflaterH *)h)->delivered;
+	return B200Z_OK;
+}
+int b200z_inflater_adler(void *h, uint32_t *v) {
+	InflaterH *d = (InflaterH *)h;
+	*v = d->raw ? 0u : d->adler;
+	return B200Z_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,609 @@
+// b200z_core.cuh -- per-thread building blocks of the B200 DEFLATE engine.
+//
+// Everything here is a __host__ __device__ inline function so that the same code that runs
+// inside the sm_100a kernels can be executed serially by tests/cpu_model (a g++-compiled harness
+// that checks the *parallel decomposition* -- link table, per-position match table, parse state
+// machine, block planner, tree builder, bit emitter -- against the oracle without a GPU).
+//
+// The decomposition (DESIGN.md "Deflate pipeline"), for the reference's lazy levels 5-9
+// (DeflaterEngine.DeflateSlow, DeflaterEngine.cs:741-855):
+//   K1 links   : link[p] = distance to the previous position with the same 15-bit hash
+//                (what head[]/prev[] of DeflaterEngine.InsertString :417-439 encode; in slow mode every
+//                position is inserted, so the chains are a pure function of the bytes)
+//   K2 matches : for EVERY position the result FindLongestMatch (:474-612) would return when entered
+//                with matchLen < goodLength (full chain budget, "A") and with matchLen >= goodLength
+//                (quartered budget, "B"), both from threshold 2; any other incoming threshold m0 < nice
+//                only filters that result (len > m0), see parse_step().
+//   K3 parse   : the sequential lazy-evaluation state machine (prevAvailable, matchLen, matchStart)
+//   K4 plan    : per 16384-symbol block: histograms, the reference's bespoke Huffman construction
+//                (DeflaterHuffman.Tree.BuildTree/BuildLength/BuildCodes :196-329, :475-579, :151-194),
+//                block type decision and exact bit size (FlushBlock :788-857)
+//   K5 scan    : bit offset of every block inside its stream
+//   K6 emit    : header + per-symbol codes at prefix-summed bit offsets
+#pragma once
+#include <stdint.h>
+
+#ifdef __CUDACC__
+#define B200Z_HD __host__ __device__ __forceinline__
+#define B200Z_HDN __host__ __device__ inline
+#else
+#define B200Z_HD inline
+#define B200Z_HDN inline
+#endif
+
+namespace b200z {
+
+// ---- DeflaterConstants.cs ------------------------------------------------------------------
+constexpr int kMaxMatch = 258;
+constexpr int kMinMatch = 3;
+constexpr int kWSize = 32768;
+constexpr int kMaxDist = kWSize - (kMaxMatch + kMinMatch + 1); // 32506, DeflaterConstants.cs:94
+constexpr int kTooFar = 4096;                                  // DeflaterEngine.cs:51
+constexpr int kBlockSyms = 16384;                              // DeflaterHuffman.BUFSIZE, DeflaterHuffman.cs:15
+constexpr int kLiteralNum = 286, kDistNum = 30, kBitlenNum = 19;
+constexpr int kTreeScratchInts = 9 * 286;
+constexpr int kHdrWords = 160; // dynamic header: <= 17 + 57 + 316 * 14 bits = 4498 bits < 160 * 32
+constexpr uint32_t kSlideFirst = 65273; // first input offset whose window index reaches 65274 (trap T8)
+
+struct LevelParams {
+	int good, lazy, nice, chain, func;
+};
+
+B200Z_HD LevelParams level_params(int level) { // DeflaterConstants.cs:124-144
+	const int good[10] = {0, 4, 4, 4, 4, 8, 8, 8, 32, 32};
+	const int lazy[10] = {0, 4, 5, 6, 4, 16, 16, 32, 128, 258};
+	const int nice[10] = {0, 8, 16, 32, 16, 32, 128, 128, 258, 258};
+	const int chain[10] = {0, 4, 8, 32, 16, 32, 128, 256, 1024, 4096};
+	const int func[10] = {0, 1, 1, 1, 1, 2, 2, 2, 2, 2};
+	LevelParams lp;
+	lp.good = good[level];
+	lp.lazy = lazy[level];
+	lp.nice = nice[level];
+	lp.chain = chain[level];
+	lp.func = func[level];
+	return lp;
+}
+
+// 15-bit hash of 3 bytes: the closed form of UpdateHash/InsertString's rolling value
+// (DeflaterEngine.cs:402-420; 3 * HASH_SHIFT == HASH_BITS so older bytes fall out).
+B200Z_HD uint32_t hash3(uint32_t b0, uint32_t b1, uint32_t b2) { return ((b0 << 10) ^ (b1 << 5) ^ b2) & 0x7FFFu; }
+
+// Positions where the reference slides its window exactly when they are a loop top: there the first
+// chain candidate at distance 32506 sits on window index 0 and is rejected by the zero sentinel (T8).
+B200Z_HD bool is_slide_pos(uint32_t p) { return p >= kSlideFirst && ((p - kSlideFirst) & 32767u) == 0; }
+// number of SlideWindow() calls performed once loop top `p` has been entered
+B200Z_HD uint32_t slides_done(uint32_t p) { return p >= kSlideFirst ? ((p - kSlideFirst) >> 15) + 1 : 0; }
+
+B200Z_HD uint32_t pack_match(uint32_t len, uint32_t dist) { return (len << 16) | dist; }
+B200Z_HD uint32_t match_len(uint32_t m) { return m >> 16; }
+B200Z_HD uint32_t match_dist(uint32_t m) { return m & 0xFFFFu; }
+
+// ---- K2: one position's chain walk ------------------------------------------------------------
+// data[q - bias], link[q - bias] address stream position q (bias lets a kernel pass shared-memory windows).
+// Returns A = result with budget `chain`, B = result with budget `chain >> 2`, both from threshold 2 and with
+// the nice-length early exit; 0 when no match of length >= 3 exists.
+template <class DataT, class LinkT>
+B200Z_HD void match_search(const DataT *data, const LinkT *link, uint32_t bias, uint32_t p, uint32_t n,
+                           const LevelParams &lp, uint32_t &resA, uint32_t &resB) {
+	resA = 0;
+	resB = 0;
+	const uint32_t la = n - p; // lookahead at a flushing loop top (or >= 262, where min() gives the same caps)
+	if (la < (uint32_t)kMinMatch) return;
+	uint32_t d = link[p - bias];
+	if (d == 0) return;
+	if (d > (uint32_t)kMaxDist - (is_slide_pos(p) ? 1u : 0u)) return; // DeflaterEngine.cs:788 + trap T8
+	const uint32_t maxlen = la < (uint32_t)kMaxMatch ? la : (uint32_t)kMaxMatch;
+	const uint32_t nice = la < (uint32_t)lp.nice ? la : (uint32_t)lp.nice;
+	const DataT *s = data + (p - bias);
+	uint32_t m = kMinMatch - 1, bd = 0;
+	uint32_t dist = d;
+	const uint32_t budgetB = (uint32_t)lp.chain >> 2;
+	uint32_t cnt = 0;
+	bool haveB = false;
+	uint8_t scan_end1 = s[m - 1], scan_end = s[m];
+	const uint8_t s0 = s[0], s1 = s[1];
+	for (;;) {
+		const DataT *c = s - dist;
+		++cnt;
+		if (c[m] == scan_end && c[m - 1] == scan_end1 && c[0] == s0 && c[1] == s1) {
+			uint32_t l = 2;
+			while (l < maxlen && c[l] == s[l]) ++l;
+			if (l > m) {
+				m = l;
+				bd = dist;
+				if (m >= nice) break;
+				scan_end1 = s[m - 1];
+				scan_end = s[m];
+			}
+		}
+		if (cnt == budgetB) {
+			resB = m >= (uint32_t)kMinMatch ? pack_match(m, bd) : 0;
+			haveB = true;
+		}
+		if (cnt == (uint32_t)lp.chain) break;
+		uint32_t l2 = link[(p - dist) - bias];
+		if (l2 == 0) break;
+		dist += l2;
+		if (dist >= (uint32_t)kMaxDist) break; // chain entries need cur > limit, i.e. distance < 32506 (T7)
+	}
+	resA = m >= (uint32_t)kMinMatch ? pack_match(m, bd) : 0;
+	if (!haveB) resB = resA;
+}
+
+// The rare case parse_step() cannot answer from the table: incoming threshold m0 >= nice (and < maxlen).
+// Walks the first `budget` candidates for the first one strictly longer than m0 (which is then >= nice, so
+// the reference stops there).  Returns packed match or 0.
+template <class DataT, class LinkT>
+B200Z_HDN uint32_t match_search_above(const DataT *data, const LinkT *link, uint32_t p, uint32_t n, uint32_t m0,
+                                      uint32_t budget) {
+	const uint32_t la = n - p;
+	uint32_t d = link[p];
+	if (d == 0 || d > (uint32_t)kMaxDist - (is_slide_pos(p) ? 1u : 0u)) return 0;
+	const uint32_t maxlen = la < (uint32_t)kMaxMatch ? la : (uint32_t)kMaxMatch;
+	uint32_t dist = d, cnt = 0;
+	const DataT *s = data + p;
+	for (;;) {
+		const DataT *c = s - dist;
+		++cnt;
+		uint32_t l = 0;
+		while (l < maxlen && c[l] == s[l]) ++l;
+		if (l > m0) return pack_match(l, dist);
+		if (cnt == budget) break;
+		uint32_t l2 = link[p - dist];
+		if (l2 == 0) break;
+		dist += l2;
+		if (dist >= (uint32_t)kMaxDist) break;
+	}
+	return 0;
+}
+
+// ---- K3: the lazy parse state machine (DeflaterEngine.DeflateSlow :741-855) --------------------
+struct ParseState {
+	uint32_t p;        // strstart as an input offset (window index = p + 1 - 32768 * slides)
+	uint32_t mlen;     // matchLen
+	uint32_t mstart;   // matchStart as an input offset
+	uint32_t prevAvail; // prevAvailable
+};
+
+B200Z_HD void parse_init(ParseState &st) { // DeflaterEngine.Reset :234-253
+	st.p = 0;
+	st.mlen = kMinMatch - 1;
+	st.mstart = 0;
+	st.prevAvail = 0;
+}
+
+// symbol word: literal = byte value; match = (dist << 8) | (len - 3)
+B200Z_HD uint32_t sym_lit(uint32_t b) { return b; }
+B200Z_HD uint32_t sym_match(uint32_t len, uint32_t dist) { return (dist << 8) | (len - 3); }
+B200Z_HD uint32_t sym_dist(uint32_t s) { return s >> 8; }
+B200Z_HD uint32_t sym_len(uint32_t s) { return (s >> 8) ? (s & 0xFF) + 3 : 1; }
+
+// One loop iteration of DeflateSlow at loop top st.p (< n).  `tab` holds (A, B) per position as uint2-like
+// pairs; `emit(sym)` receives the tallied symbol (at most one per step).  strategy: 0 Default, 1 Filtered,
+// 2 HuffmanOnly.  Returns the number of symbols emitted (0 or 1).
+template <class TabFn, class DataFn, class SlowFn>
+B200Z_HD int parse_step(ParseState &st, uint32_t n, const LevelParams &lp, int strategy, TabFn tab, DataFn byte_at,
+                        SlowFn slow_search, uint32_t &out_sym) {
+	const uint32_t p = st.p;
+	const uint32_t prevLen = st.mlen, prevStart = st.mstart;
+	const uint32_t la = n - p;
+	if (la >= (uint32_t)kMinMatch && strategy != 2) {
+		uint32_t a, b;
+		tab(p, a, b);
+		// (a | b) == 0 means either the head test failed (FindLongestMatch not entered) or no candidate of
+		// length >= 3 exists.  Both leave (matchLen, matchStart) such that the decision below is the same:
+		// the only side effect of an unproductive FindLongestMatch is the too-small/too-far discard of a
+		// *carried* match, after which "matchLen <= prevLen" still holds and the previous match is emitted.
+		if ((a | b) != 0) {
+			// FindLongestMatch (:474-612)
+			uint32_t m0 = st.mlen < (uint32_t)(kMinMatch - 1) ? (uint32_t)(kMinMatch - 1) : st.mlen;
+			st.mlen = m0;
+			const uint32_t maxlen = la < (uint32_t)kMaxMatch ? la : (uint32_t)kMaxMatch;
+			bool ret;
+			if (m0 >= maxlen) {
+				ret = false; // "scan + matchLen > scanMax" (:488)
+			} else {
+				const uint32_t nice = la < (uint32_t)lp.nice ? la : (uint32_t)lp.nice;
+				const bool quarter = m0 >= (uint32_t)lp.good;
+				uint32_t r;
+				if (m0 >= nice) r = slow_search(p, m0, quarter ? ((uint32_t)lp.chain >> 2) : (uint32_t)lp.chain);
+				else r = quarter ? b : a;
+				if (match_len(r) > m0) {
+					st.mlen = match_len(r);
+					st.mstart = p - match_dist(r);
+				}
+				ret = st.mlen >= (uint32_t)kMinMatch;
+			}
+			if (ret) {
+				// discard match if too small and too far away (:794-797)
+				if (st.mlen <= 5 && (strategy == 1 || (st.mlen == (uint32_t)kMinMatch && p - st.mstart > (uint32_t)kTooFar)))
+					st.mlen = kMinMatch - 1;
+			}
+		}
+	}
+	int emitted = 0;
+	if (prevLen >= (uint32_t)kMinMatch && st.mlen <= prevLen) {
+		// previous match was better (:802-827)
+		out_sym = sym_match(prevLen, p - 1 - prevStart);
+		emitted = 1;
+		st.p = p + prevLen - 1;
+		st.prevAvail = 0;
+		st.mlen = kMinMatch - 1;
+	} else {
+		if (st.prevAvail) {
+			out_sym = sym_lit(byte_at(p - 1));
+			emitted = 1;
+		}
+		st.prevAvail = 1;
+		st.p = p + 1;
+	}
+	return emitted;
+}
+
+// ---- DeflaterHuffman.cs helpers ----------------------------------------------------------------
+B200Z_HD int lcode(int len_m3) { // Lcode :932-946 (argument is length - 3)
+	if (len_m3 == 255) return 285;
+	int code = 257;
+	while (len_m3 >= 8) {
+		code += 4;
+		len_m3 >>= 1;
+	}
+	return code + len_m3;
+}
+B200Z_HD int dcode(int dist_m1) { // Dcode :948-957 (argument is distance - 1)
+	int code = 0;
+	while (dist_m1 >= 4) {
+		code += 2;
+		dist_m1 >>= 1;
+	}
+	return code + dist_m1;
+}
+B200Z_HD int lcode_extra_bits(int lc) { // CompressBlock :716-720
+	int bits = (lc - 261) / 4;
+	return (bits > 0 && bits <= 5) ? bits : 0;
+}
+B200Z_HD int dcode_extra_bits(int dc) { // CompressBlock :725-729
+	int bits = dc / 2 - 1;
+	return bits > 0 ? bits : 0;
+}
+B200Z_HD uint32_t bit_reverse16(uint32_t v) { // BitReverse :924-930
+	v = ((v & 0x5555u) << 1) | ((v >> 1) & 0x5555u);
+	v = ((v & 0x3333u) << 2) | ((v >> 2) & 0x3333u);
+	v = ((v & 0x0F0Fu) << 4) | ((v >> 4) & 0x0F0Fu);
+	v = ((v & 0x00FFu) << 8) | ((v >> 8) & 0x00FFu);
+	return v & 0xFFFFu;
+}
+B200Z_HD int static_llen(int i) { return i < 144 ? 8 : (i < 256 ? 9 : (i < 280 ? 7 : 8)); } // :611-630
+B200Z_HD uint32_t static_lcode(int i) {
+	if (i < 144) return bit_reverse16((uint32_t)(0x030 + i) << 8);
+	if (i < 256) return bit_reverse16((uint32_t)(0x190 - 144 + i) << 7);
+	if (i < 280) return bit_reverse16((uint32_t)(0x000 - 256 + i) << 9);
+	return bit_reverse16((uint32_t)(0x0c0 - 280 + i) << 8);
+}
+B200Z_HD uint32_t static_dcode(int i) { return bit_reverse16((uint32_t)i << 11); } // :637-641, length 5
+
+// Tree.BuildTree + BuildLength (DeflaterHuffman.cs:196-329, :475-579), operation for operation.
+//   freqs[numSymbols] in; length[numSymbols], bl_counts[maxLength], numCodes out.
+//   scratch: heap[numSymbols] + childs[4*L-2] + values[2*L-1] + lengths[2*L-1] ints with L <= numSymbols
+//            ->  9 * numSymbols ints is enough (kTreeScratchInts for the 286-symbol literal tree).
+B200Z_HDN int build_tree(const int *freqs, int numSymbols, int minNumCodes, int maxLength, uint8_t *length,
+                         int *bl_counts, int *scratch) {
+	int *heap = scratch;
+	int heapLen = 0;
+	int maxCode = 0;
+	for (int n = 0; n < numSymbols; n++) {
+		int freq = freqs[n];
+		if (freq != 0) {
+			int pos = heapLen++;
+			int ppos;
+			while (pos > 0 && freqs[heap[ppos = (pos - 1) / 2]] > freq) {
+				heap[pos] = heap[ppos];
+				pos = ppos;
+			}
+			heap[pos] = n;
+			maxCode = n;
+		}
+	}
+	while (heapLen < 2) {
+		int node = maxCode < 2 ? ++maxCode : 0;
+		heap[heapLen++] = node;
+	}
+	int numCodes = (maxCode + 1 > minNumCodes) ? maxCode + 1 : minNumCodes;
+	int numLeafs = heapLen;
+	int *childs = scratch + numSymbols;            // 4*heapLen - 2
+	int *values = childs + (4 * numLeafs - 2);     // 2*heapLen - 1
+	int *lengths = values + (2 * numLeafs - 1);    // 2*heapLen - 1
+	int numNodes = numLeafs;
+	for (int i = 0; i < heapLen; i++) {
+		int node = heap[i];
+		childs[2 * i] = node;
+		childs[2 * i + 1] = -1;
+		values[i] = freqs[node] << 8;
+		heap[i] = i;
+	}
+	do {
+		int first = heap[0];
+		int last = heap[--heapLen];
+		int ppos = 0;
+		int path = 1;
+		while (path < heapLen) {
+			if (path + 1 < heapLen && values[heap[path]] > values[heap[path + 1]]) path++;
+			heap[ppos] = heap[path];
+			ppos = path;
+			path = path * 2 + 1;
+		}
+		int lastVal = values[last];
+		while ((path = ppos) > 0 && values[heap[ppos = (path - 1) / 2]] > lastVal) heap[path] = heap[ppos];
+		heap[path] = last;
+		int second = heap[0];
+		last = numNodes++;
+		childs[2 * last] = first;
+		childs[2 * last + 1] = second;
+		int d1 = values[first] & 0xff, d2 = values[second] & 0xff;
+		int mindepth = d1 < d2 ? d1 : d2;
+		values[last] = lastVal = values[first] + values[second] - mindepth + 1;
+		ppos = 0;
+		path = 1;
+		while (path < heapLen) {
+			if (path + 1 < heapLen && values[heap[path]] > values[heap[path + 1]]) path++;
+			heap[ppos] = heap[path];
+			ppos = path;
+			path = ppos * 2 + 1;
+		}
+		while ((path = ppos) > 0 && values[heap[ppos = (path - 1) / 2]] > lastVal) heap[path] = heap[ppos];
+		heap[path] = last;
+	} while (heapLen > 1);
+
+	// BuildLength (:475-579); childs.Length / 2 == numNodes == 2 * numLeafs - 1
+	for (int i = 0; i < numSymbols; i++) length[i] = 0;
+	int overflow = 0;
+	for (int i = 0; i < maxLength; i++) bl_counts[i] = 0;
+	lengths[numNodes - 1] = 0;
+	for (int i = numNodes - 1; i >= 0; i--) {
+		if (childs[2 * i + 1] != -1) {
+			int bitLength = lengths[i] + 1;
+			if (bitLength > maxLength) {
+				bitLength = maxLength;
+				overflow++;
+			}
+			lengths[childs[2 * i]] = lengths[childs[2 * i + 1]] = bitLength;
+		} else {
+			int bitLength = lengths[i];
+			bl_counts[bitLength - 1]++;
+			length[childs[2 * i]] = (uint8_t)lengths[i];
+		}
+	}
+	if (overflow == 0) return numCodes;
+	int incrBitLen = maxLength - 1;
+	do {
+		while (bl_counts[--incrBitLen] == 0) {
+		}
+		do {
+			bl_counts[incrBitLen]--;
+			bl_counts[++incrBitLen]++;
+			overflow -= 1 << (maxLength - 1 - incrBitLen);
+		} while (overflow > 0 && incrBitLen < maxLength - 1);
+	} while (overflow > 0);
+	bl_counts[maxLength - 1] += overflow;
+	bl_counts[maxLength - 2] -= overflow;
+	int nodePtr = 2 * numLeafs;
+	for (int bits = maxLength; bits != 0; bits--) {
+		int n = bl_counts[bits - 1];
+		while (n > 0) {
+			int childPtr = 2 * childs[nodePtr++];
+			if (childs[childPtr + 1] == -1) {
+				length[childs[childPtr]] = (uint8_t)bits;
+				n--;
+			}
+		}
+	}
+	return numCodes;
+}
+
+// Tree.BuildCodes (:151-194): canonical codes, left-aligned in 16 bits then bit-reversed.
+B200Z_HDN void build_codes(const uint8_t *length, const int *bl_counts, int maxLength, int numCodes, uint16_t *codes) {
+	int nextCode[15];
+	int code = 0;
+	for (int bits = 0; bits < maxLength; bits++) {
+		nextCode[bits] = code;
+		code += bl_counts[bits] << (15 - bits);
+	}
+	for (int i = 0; i < numCodes; i++) {
+		int bits = length[i];
+		if (bits > 0) {
+			codes[i] = (uint16_t)bit_reverse16((uint32_t)nextCode[bits - 1]);
+			nextCode[bits - 1] += 1 << (16 - bits);
+		} else {
+			codes[i] = 0;
+		}
+	}
+}
+
+// LSB-first bit writer over 32-bit words owned by ONE thread (block headers).  The destination words must be
+// zero; the content is what PendingBuffer.WriteBits (:168-189) would have produced for the same calls.
+struct BitSink {
+	uint32_t *w;
+	uint32_t nbits;
+	B200Z_HD void put(uint32_t v, int count) {
+		if (count == 0) return;
+		uint32_t idx = nbits >> 5, sh = nbits & 31;
+		w[idx] |= v << sh;
+		if (sh + count > 32) w[idx + 1] |= v >> (32 - sh);
+		nbits += count;
+	}
+};
+struct BitCounter {
+	uint32_t nbits;
+	B200Z_HD void put(uint32_t, int count) { nbits += count; }
+};
+
+// Tree.CalcBLFreq (:349-405) and Tree.WriteTree (:411-473) share one run-length walk; Sink decides what a
+// visit does.  visit(symbol) for a bit-length symbol, extra(value, bits) for the repeat counts.
+template <class Visit, class Extra>
+B200Z_HD void walk_code_lengths(const uint8_t *length, int numCodes, Visit visit, Extra extra) {
+	int max_count, min_count, count;
+	int curlen = -1;
+	int i = 0;
+	while (i < numCodes) {
+		count = 1;
+		int nextlen = length[i];
+		if (nextlen == 0) {
+			max_count = 138;
+			min_count = 3;
+		} else {
+			max_count = 6;
+			min_count = 3;
+			if (curlen != nextlen) {
+				visit(nextlen);
+				count = 0;
+			}
+		}
+		curlen = nextlen;
+		i++;
+		while (i < numCodes && curlen == length[i]) {
+			i++;
+			if (++count >= max_count) break;
+		}
+		if (count < min_count) {
+			while (count-- > 0) visit(curlen);
+		} else if (curlen != 0) {
+			visit(16);
+			extra(count - 3, 2);
+		} else if (count <= 10) {
+			visit(17);
+			extra(count - 3, 3);
+		} else {
+			visit(18);
+			extra(count - 11, 7);
+		}
+	}
+}
+
+// Everything FlushBlock (:788-857) decides for one block, from its histograms.
+struct BlockPlan {
+	int type;           // 0 stored, 1 static, 2 dynamic
+	int lit_numCodes, dist_numCodes, blTreeCodes;
+	int opt_len, static_len;
+	uint32_t hdr_bits;  // 3 header bits (+ tree description for dynamic blocks); stored: 3
+	uint32_t body_bits; // symbols + EOB (stored: 0; the payload is byte-aligned separately)
+};
+
+// freqs are the literal (286) and distance (30) histograms with EOB already counted; extra_bits as tallied by
+// TallyDist (:894-916).  Outputs code lengths / codes for the block's chosen trees and, for dynamic blocks, the
+// header bit string into hdr_words (zeroed by the caller, >= kHdrWords words).  scratch >= kTreeScratchInts ints.
+B200Z_HDN void plan_block(const int *lit_freqs, const int *dist_freqs, int extra_bits, int stored_ok, int storedLength,
+                          int lastBlock, uint8_t *lit_len, uint16_t *lit_codes, uint8_t *dist_len, uint16_t *dist_codes,
+                          uint32_t *hdr_words, int *scratch, BlockPlan &plan) {
+	const int BL_ORDER[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+	int lit_blc[15], dist_blc[15], bl_blc[7];
+	int bl_freqs[kBitlenNum];
+	uint8_t bl_len[kBitlenNum];
+	uint16_t bl_codes[kBitlenNum];
+	int lit_nc = build_tree(lit_freqs, kLiteralNum, 257, 15, lit_len, lit_blc, scratch);
+	int dist_nc = build_tree(dist_freqs, kDistNum, 1, 15, dist_len, dist_blc, scratch);
+	for (int i = 0; i < kBitlenNum; i++) bl_freqs[i] = 0;
+	walk_code_lengths(lit_len, lit_nc, [&](int s) { bl_freqs[s]++; }, [&](int, int) {});
+	walk_code_lengths(dist_len, dist_nc, [&](int s) { bl_freqs[s]++; }, [&](int, int) {});
+	build_tree(bl_freqs, kBitlenNum, 4, 7, bl_len, bl_blc, scratch);
+	int blTreeCodes = 4;
+	for (int i = 18; i > blTreeCodes; i--) {
+		if (bl_len[BL_ORDER[i]] > 0) blTreeCodes = i + 1;
+	}
+	int opt_len = 14 + blTreeCodes * 3 + extra_bits;
+	for (int i = 0; i < kBitlenNum; i++) opt_len += bl_freqs[i] * bl_len[i];
+	for (int i = 0; i < kLiteralNum; i++) opt_len += lit_freqs[i] * lit_len[i];
+	for (int i = 0; i < kDistNum; i++) opt_len += dist_freqs[i] * dist_len[i];
+	int static_len = extra_bits;
+	for (int i = 0; i < kLiteralNum; i++) static_len += lit_freqs[i] * static_llen(i);
+	for (int i = 0; i < kDistNum; i++) static_len += dist_freqs[i] * 5;
+	plan.lit_numCodes = lit_nc;
+	plan.dist_numCodes = dist_nc;
+	plan.blTreeCodes = blTreeCodes;
+	plan.static_len = static_len;
+	int dyn_len = opt_len;
+	if (opt_len >= static_len) opt_len = static_len; // force static trees
+	plan.opt_len = opt_len;
+	if (stored_ok && storedLength + 4 < (opt_len >> 3)) {
+		plan.type = 0;
+		plan.hdr_bits = 3;
+		plan.body_bits = 0;
+		hdr_words[0] = (uint32_t)((0 << 1) + (lastBlock ? 1 : 0));
+	} else if (opt_len == static_len) {
+		plan.type = 1;
+		plan.hdr_bits = 3;
+		plan.body_bits = (uint32_t)static_len;
+		hdr_words[0] = (uint32_t)((1 << 1) + (lastBlock ? 1 : 0));
+		for (int i = 0; i < kLiteralNum; i++) {
+			lit_len[i] = (uint8_t)static_llen(i);
+			lit_codes[i] = (uint16_t)static_lcode(i);
+		}
+		for (int i = 0; i < kDistNum; i++) {
+			dist_len[i] = 5;
+			dist_codes[i] = (uint16_t)static_dcode(i);
+		}
+	} else {
+		plan.type = 2;
+		// SendAllTrees (:676-696)
+		build_codes(bl_len, bl_blc, 7, kBitlenNum, bl_codes); // blTree.numCodes is irrelevant: all 19 get codes
+		build_codes(lit_len, lit_blc, 15, lit_nc, lit_codes);
+		build_codes(dist_len, dist_blc, 15, dist_nc, dist_codes);
+		BitSink sink{hdr_words, 0};
+		sink.put((uint32_t)((2 << 1) + (lastBlock ? 1 : 0)), 3);
+		sink.put((uint32_t)(lit_nc - 257), 5);
+		sink.put((uint32_t)(dist_nc - 1), 5);
+		sink.put((uint32_t)(blTreeCodes - 4), 4);
+		for (int rank = 0; rank < blTreeCodes; rank++) sink.put(bl_len[BL_ORDER[rank]], 3);
+		walk_code_lengths(lit_len, lit_nc, [&](int s) { sink.put(bl_codes[s], bl_len[s]); },
+		                  [&](int v, int nb) { sink.put((uint32_t)v, nb); });
+		walk_code_lengths(dist_len, dist_nc, [&](int s) { sink.put(bl_codes[s], bl_len[s]); },
+		                  [&](int v, int nb) { sink.put((uint32_t)v, nb); });
+		plan.hdr_bits = sink.nbits;
+		// body = literal/length + distance code bits + extra bits (dyn_len minus the 14 + 3*blTreeCodes + bl part)
+		int body = extra_bits;
+		for (int i = 0; i < kLiteralNum; i++) body += lit_freqs[i] * lit_len[i];
+		for (int i = 0; i < kDistNum; i++) body += dist_freqs[i] * dist_len[i];
+		plan.body_bits = (uint32_t)body;
+		(void)dyn_len;
+	}
+}
+
+// Code word of one tallied symbol under the block's tables (CompressBlock :701-757): up to 48 bits, LSB first.
+B200Z_HD void encode_symbol(uint32_t sym, const uint16_t *lit_codes, const uint8_t *lit_len, const uint16_t *dist_codes,
+                            const uint8_t *dist_len, uint64_t &bits, int &nbits) {
+	uint32_t dist = sym_dist(sym);
+	if (dist == 0) {
+		bits = lit_codes[sym & 0xFF];
+		nbits = lit_len[sym & 0xFF];
+		return;
+	}
+	int litlen = (int)(sym & 0xFF);
+	int lc = lcode(litlen);
+	uint64_t acc = lit_codes[lc];
+	int nb = lit_len[lc];
+	int eb = lcode_extra_bits(lc);
+	if (eb) {
+		acc |= (uint64_t)(litlen & ((1 << eb) - 1)) << nb;
+		nb += eb;
+	}
+	int dm1 = (int)dist - 1;
+	int dc = dcode(dm1);
+	acc |= (uint64_t)dist_codes[dc] << nb;
+	nb += dist_len[dc];
+	eb = dcode_extra_bits(dc);
+	if (eb) {
+		acc |= (uint64_t)(dm1 & ((1 << eb) - 1)) << nb;
+		nb += eb;
+	}
+	bits = acc;
+	nbits = nb;
+}
+
+// TallyDist's extra_bits contribution (:899-913)
+B200Z_HD int tally_extra_bits(int lc, int dc) {
+	int e = 0;
+	if (lc >= 265 && lc < 285) e += (lc - 261) / 4;
+	if (dc >= 4) e += dc / 2 - 1;
+	return e;
+}
+
+} // namespace b200z

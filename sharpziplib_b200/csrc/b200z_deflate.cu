@@ -1,0 +1,577 @@
+// b200z_deflate.cu -- the sm_100a DEFLATE compressor for the reference's lazy levels (5-9).
+// Kernel decomposition and the reference lines each kernel replaces: see b200z_core.cuh and DESIGN.md.
+//
+//   k_links   (K1)  DeflaterEngine.InsertString / head[] / prev[]         DeflaterEngine.cs:417-439
+//   k_match   (K2)  DeflaterEngine.FindLongestMatch, for every position   DeflaterEngine.cs:474-612
+//   k_parse   (K3)  DeflaterEngine.DeflateSlow state machine              DeflaterEngine.cs:741-855
+//   k_plan    (K4)  DeflaterHuffman.FlushBlock up to the type decision    DeflaterHuffman.cs:788-857
+//   k_scan    (K5)  bit position of every block; Deflater flush padding   Deflater.cs:486-517
+//   k_emit    (K6)  SendAllTrees / CompressBlock / FlushStoredBlock       DeflaterHuffman.cs:676-779
+#include "b200z_internal.cuh"
+
+namespace b200z {
+
+constexpr int kRun = 65536;    // positions per k_links warp
+constexpr int kTile = 32768;   // positions per k_match CTA
+constexpr int kTileData = 2 * kTile + 320; // bytes of window staged per tile (history + tile + max match + pad)
+constexpr int kMatchThreads = 1024;
+constexpr int kParseChunk = 512;
+constexpr int kParseSymBuf = 512;
+constexpr int kParseWarps = 4;
+
+// ------------------------------------------------------------------------------------------------
+// K1: link[p] = distance from p to the previous inserted position with the same hash (0 = none / too far).
+// One warp per run of kRun positions, 32 positions per step; a 16-bit head table in shared memory, re-based
+// every 32768 positions exactly like SlideWindow (DeflaterEngine.cs:441-462) so that entries stay unambiguous.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32) k_links(const uint8_t *__restrict__ in, uint16_t *__restrict__ link,
+                                              const int64_t *__restrict__ in_off, const int64_t *__restrict__ in_len,
+                                              const int2 *__restrict__ run_desc) {
+	extern __shared__ uint16_t head[]; // 32768 entries
+	const int lane = threadIdx.x;
+	const int2 rd = run_desc[blockIdx.x];
+	const uint32_t n = (uint32_t)in_len[rd.x];
+	const uint8_t *data = in + in_off[rd.x];
+	uint16_t *lnk = link + in_off[rd.x];
+	const uint32_t start = (uint32_t)rd.y;
+	const uint32_t run_end = (n - start > (uint32_t)kRun) ? start + kRun : n;
+	const uint32_t warm = start >= 32768u ? start - 32768u : 0u;
+	for (int i = lane; i < 16384; i += 32) reinterpret_cast<uint32_t *>(head)[i] = 0;
+	__syncwarp();
+	uint32_t winbase = warm;
+	// software prefetch of the next step's bytes
+	uint32_t nb0 = (warm + lane < n) ? data[warm + lane] : 0;
+	uint32_t nx = 0;
+	if (lane < 2) nx = (warm + 32 + lane < n) ? data[warm + 32 + lane] : 0;
+	for (uint32_t base = warm; base < run_end; base += 32) {
+		if (base + 32 - winbase > 65535u) {
+			for (int i = lane; i < 16384; i += 32) {
+				uint32_t v = reinterpret_cast<uint32_t *>(head)[i];
+				uint32_t lo = v & 0xFFFFu, hi = v >> 16;
+				lo = lo > 32768u ? lo - 32768u : 0u;
+				hi = hi > 32768u ? hi - 32768u : 0u;
+				reinterpret_cast<uint32_t *>(head)[i] = lo | (hi << 16);
+			}
+			winbase += 32768u;
+			__syncwarp();
+		}
+		const uint32_t b0 = nb0;
+		const uint32_t x0 = __shfl_sync(0xffffffffu, nx, 0), x1 = __shfl_sync(0xffffffffu, nx, 1);
+		// issue next step's loads before the dependent work of this step
+		const uint32_t nbase = base + 32;
+		nb0 = (nbase + lane < n) ? data[nbase + lane] : 0;
+		if (lane < 2) nx = (nbase + 32 + lane < n) ? data[nbase + 32 + lane] : 0;
+		uint32_t b1 = __shfl_down_sync(0xffffffffu, b0, 1);
+		uint32_t b2 = __shfl_down_sync(0xffffffffu, b0, 2);
+		if (lane == 31) { b1 = x0; b2 = x1; }
+		if (lane == 30) { b2 = x0; }
+		const uint32_t p = base + lane;
+		const bool valid = p + 2 < n; // InsertString only while lookahead >= MIN_MATCH (:782, :819)
+		const uint32_t h = valid ? hash3(b0, b1, b2) : (0x8000u + lane);
+		const uint32_t mask = __match_any_sync(0xffffffffu, h);
+		const uint32_t lower = mask & ((1u << lane) - 1u);
+		uint32_t q = 0xFFFFFFFFu;
+		if (valid) {
+			if (lower) q = base + (31 - __clz(lower));
+			else {
+				uint32_t v = head[h];
+				if (v) q = winbase + v - 1;
+			}
+		}
+		__syncwarp();
+		if (valid && (mask >> lane) == 1u) head[h] = (uint16_t)(p - winbase + 1);
+		__syncwarp();
+		if (p >= start && p < run_end) {
+			uint32_t d = (q != 0xFFFFFFFFu) ? p - q : 0u;
+			lnk[p] = (d <= (uint32_t)kMaxDist) ? (uint16_t)d : (uint16_t)0;
+		}
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2: per-position match table.  One CTA per 32 KiB tile; the tile's 64 KiB data window and the window's link
+// entries are staged in shared memory (192 KiB), then each thread walks the chains of 32 positions.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kMatchThreads, 1)
+    k_match(const uint8_t *__restrict__ in, const uint16_t *__restrict__ link, uint2 *__restrict__ mt,
+            const int64_t *__restrict__ in_off, const int64_t *__restrict__ in_len, const int2 *__restrict__ tile_desc,
+            LevelParams lp) {
+	extern __shared__ __align__(16) uint8_t smem[];
+	uint8_t *s_data = smem;
+	uint16_t *s_link = reinterpret_cast<uint16_t *>(smem + kTileData);
+	const int2 td = tile_desc[blockIdx.x];
+	const uint32_t n = (uint32_t)in_len[td.x];
+	const int64_t off = in_off[td.x];
+	const uint8_t *data = in + off;
+	const uint16_t *lnk = link + off;
+	const uint32_t t0 = (uint32_t)td.y;
+	const uint32_t t1 = (n - t0 > (uint32_t)kTile) ? t0 + kTile : n;
+	const uint32_t w0 = t0 >= (uint32_t)kTile ? t0 - kTile : 0u;
+	uint32_t dend = t1 + 272;
+	if (dend > n) dend = n;
+	// stage (w0 and the slot base are 16-byte aligned; tails are covered by the scalar loops)
+	{
+		const uint32_t nbytes = dend - w0;
+		const uint32_t nvec = nbytes >> 4;
+		const uint4 *src = reinterpret_cast<const uint4 *>(data + w0);
+		uint4 *dst = reinterpret_cast<uint4 *>(s_data);
+		for (uint32_t i = threadIdx.x; i < nvec; i += kMatchThreads) dst[i] = __ldg(src + i);
+		for (uint32_t i = (nvec << 4) + threadIdx.x; i < nbytes; i += kMatchThreads) s_data[i] = data[w0 + i];
+		const uint32_t nl = t1 - w0;
+		const uint32_t nlv = nl >> 3;
+		const uint4 *lsrc = reinterpret_cast<const uint4 *>(lnk + w0);
+		uint4 *ldst = reinterpret_cast<uint4 *>(s_link);
+		for (uint32_t i = threadIdx.x; i < nlv; i += kMatchThreads) ldst[i] = __ldg(lsrc + i);
+		for (uint32_t i = (nlv << 3) + threadIdx.x; i < nl; i += kMatchThreads) s_link[i] = lnk[w0 + i];
+	}
+	__syncthreads();
+	uint2 *out = mt + off;
+	for (uint32_t p = t0 + threadIdx.x; p < t1; p += kMatchThreads) {
+		uint32_t a, b;
+		match_search(s_data, s_link, w0, p, n, lp, a, b);
+		out[p] = make_uint2(a, b);
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3: the sequential lazy parse.  One warp per stream: the warp stages the next kParseChunk table entries and
+// bytes in shared memory, lane 0 runs the state machine over them, the warp writes the symbols out coalesced.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kParseWarps * 32)
+    k_parse(const uint8_t *__restrict__ in, const uint16_t *__restrict__ link, const uint2 *__restrict__ mt,
+            uint32_t *__restrict__ sym, const int64_t *__restrict__ in_off, const int64_t *__restrict__ in_len, int nstreams,
+            uint32_t *__restrict__ nsyms, uint32_t *__restrict__ nblocks, const uint32_t *__restrict__ blk_off,
+            uint32_t *__restrict__ blk_start, uint32_t *__restrict__ blk_ptop, LevelParams lp, int strategy, int end_mode) {
+	__shared__ uint2 s_tab[kParseWarps][kParseChunk];
+	__shared__ uint8_t s_dat[kParseWarps][kParseChunk + 16];
+	__shared__ uint32_t s_sym[kParseWarps][kParseSymBuf];
+	const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const int stream = blockIdx.x * kParseWarps + w;
+	if (stream >= nstreams) return;
+	const uint32_t n = (uint32_t)in_len[stream];
+	const int64_t off = in_off[stream];
+	const uint8_t *data = in + off;
+	const uint16_t *lnk = link + off;
+	const uint2 *tab = mt + off;
+	uint32_t *sout = sym + off;
+	uint32_t *bstart = blk_start + blk_off[stream];
+	uint32_t *bptop = blk_ptop + blk_off[stream];
+	uint2 *ctab = s_tab[w];
+	uint8_t *cdat = s_dat[w];
+	uint32_t *csym = s_sym[w];
+
+	ParseState st;
+	parse_init(st);
+	uint32_t total = 0, bytes_done = 0, last_top = 0, nblk = 0;
+	bool ended_full = false;
+	if (lane == 0) bstart[0] = 0;
+	for (;;) {
+		const uint32_t p0 = __shfl_sync(0xffffffffu, st.p, 0);
+		if (p0 >= n) break;
+		const uint32_t cend = (n - p0 > (uint32_t)kParseChunk) ? p0 + kParseChunk : n;
+		const uint32_t cn = cend - p0;
+		for (uint32_t i = lane; i < cn; i += 32) ctab[i] = tab[p0 + i];
+		for (uint32_t i = lane; i <= cn; i += 32) { // byte q = p0 - 1 + i lives at cdat[i]
+			if (p0 + i >= 1 && p0 + i - 1 < n) cdat[i] = data[p0 + i - 1];
+		}
+		__syncwarp();
+		uint32_t cnt = 0;
+		if (lane == 0) {
+			while (st.p < cend && cnt < (uint32_t)kParseSymBuf) {
+				last_top = st.p;
+				uint32_t s;
+				int e = parse_step(
+				    st, n, lp, strategy,
+				    [&](uint32_t p, uint32_t &a, uint32_t &b) {
+					    uint2 t = ctab[p - p0];
+					    a = t.x;
+					    b = t.y;
+				    },
+				    [&](uint32_t q) { return (uint32_t)cdat[q + 1 - p0]; },
+				    [&](uint32_t p, uint32_t m0, uint32_t budget) {
+					    return match_search_above(data, lnk, p, n, m0, budget);
+				    },
+				    s);
+				ended_full = false;
+				if (e) {
+					csym[cnt++] = s;
+					bytes_done += sym_len(s);
+					++total;
+					if ((total & (uint32_t)(kBlockSyms - 1)) == 0) {
+						bptop[nblk] = last_top;
+						++nblk;
+						bstart[nblk] = bytes_done;
+						ended_full = (end_mode == B200Z_END_FINISH) && st.p >= n && !st.prevAvail;
+					}
+				}
+			}
+		}
+		cnt = __shfl_sync(0xffffffffu, cnt, 0);
+		const uint32_t tot = __shfl_sync(0xffffffffu, total, 0);
+		__syncwarp();
+		for (uint32_t i = lane; i < cnt; i += 32) sout[tot - cnt + i] = csym[i];
+		__syncwarp();
+	}
+	if (lane == 0) {
+		if (!ended_full) {
+			// final flush at lookahead == 0 (DeflaterEngine.cs:750-768)
+			if (st.prevAvail) {
+				sout[total++] = sym_lit(data[st.p - 1]);
+				bytes_done += 1;
+			}
+			bptop[nblk] = last_top;
+			++nblk;
+		}
+		nsyms[stream] = total;
+		nblocks[stream] = nblk;
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4: per-block histograms, the reference's Huffman construction and the block type decision.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+    k_plan(const uint32_t *__restrict__ sym, const int64_t *__restrict__ in_off, const int64_t *__restrict__ in_len,
+           const uint32_t *__restrict__ nsyms, const uint32_t *__restrict__ nblocks, const uint32_t *__restrict__ blk_off,
+           const int32_t *__restrict__ blk_desc, const uint32_t *__restrict__ blk_start, const uint32_t *__restrict__ blk_ptop,
+           BlockMeta *__restrict__ meta, BlockTables *__restrict__ tables, int end_mode) {
+	__shared__ int s_lit[kLiteralNum];
+	__shared__ int s_dist[kDistNum];
+	__shared__ int s_extra;
+	__shared__ int s_scratch[kTreeScratchInts];
+	__shared__ BlockTables s_tab;
+	const int g = blockIdx.x;
+	const int stream = blk_desc[g];
+	const uint32_t b = (uint32_t)g - blk_off[stream];
+	const uint32_t nb = nblocks[stream];
+	if (b >= nb) return;
+	const uint32_t ns = nsyms[stream];
+	const uint32_t s0 = b * (uint32_t)kBlockSyms;
+	const uint32_t s1 = (ns - s0 > (uint32_t)kBlockSyms) ? s0 + kBlockSyms : ns;
+	const uint32_t *sp = sym + in_off[stream];
+	for (int i = threadIdx.x; i < kLiteralNum; i += blockDim.x) s_lit[i] = 0;
+	for (int i = threadIdx.x; i < kDistNum; i += blockDim.x) s_dist[i] = 0;
+	for (int i = threadIdx.x; i < kHdrWords; i += blockDim.x) s_tab.hdr[i] = 0;
+	if (threadIdx.x == 0) s_extra = 0;
+	__syncthreads();
+	int extra = 0;
+	for (uint32_t i = s0 + threadIdx.x; i < s1; i += blockDim.x) {
+		const uint32_t s = sp[i];
+		if (sym_dist(s) == 0) {
+			atomicAdd(&s_lit[s & 0xFF], 1);
+		} else {
+			const int lc = lcode((int)(s & 0xFF)), dc = dcode((int)sym_dist(s) - 1);
+			atomicAdd(&s_lit[lc], 1);
+			atomicAdd(&s_dist[dc], 1);
+			extra += tally_extra_bits(lc, dc);
+		}
+	}
+	for (int o = 16; o > 0; o >>= 1) extra += __shfl_down_sync(0xffffffffu, extra, o);
+	if ((threadIdx.x & 31) == 0 && extra) atomicAdd(&s_extra, extra);
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		s_lit[256] += 1; // FlushBlock: literalTree.freqs[EOF_SYMBOL]++ (:790)
+		const uint32_t *bstart = blk_start + blk_off[stream];
+		const uint32_t *bptop = blk_ptop + blk_off[stream];
+		const uint32_t byte_start = bstart[b];
+		const uint32_t n = (uint32_t)in_len[stream];
+		const uint32_t byte_len = (b + 1 < nb ? bstart[b + 1] : n) - byte_start;
+		// storedOffset is window relative and goes negative once the block start has been slid out (trap T4)
+		const long long storedOffset = (long long)byte_start + 1 - 32768ll * (long long)slides_done(bptop[b]);
+		const int last = (b + 1 == nb) && end_mode == B200Z_END_FINISH;
+		BlockPlan plan;
+		plan_block(s_lit, s_dist, s_extra, storedOffset >= 0, (int)byte_len, last, s_tab.lit_len, s_tab.lit_codes,
+		           s_tab.dist_len, s_tab.dist_codes, s_tab.hdr, s_scratch, plan);
+		BlockMeta m;
+		m.byte_start = byte_start;
+		m.byte_len = byte_len;
+		m.nsyms = s1 - s0;
+		m.hdr_bits = plan.hdr_bits;
+		m.body_bits = plan.body_bits;
+		m.type = (uint32_t)plan.type;
+		m.bit_off = 0;
+		meta[g] = m;
+	}
+	__syncthreads();
+	// copy the tables out (16-byte vectors)
+	const uint4 *src = reinterpret_cast<const uint4 *>(&s_tab);
+	uint4 *dst = reinterpret_cast<uint4 *>(&tables[g]);
+	for (int i = threadIdx.x; i < (int)(sizeof(BlockTables) / 16); i += blockDim.x) dst[i] = src[i];
+}
+
+__device__ __forceinline__ void or_bits(uint32_t *out_words, uint64_t bitpos, uint64_t bits, int nbits) {
+	// nbits <= 57; spreads over at most three 32-bit words
+	if (nbits == 0) return;
+	const uint64_t idx = bitpos >> 5;
+	const uint32_t sh = (uint32_t)(bitpos & 31);
+	const uint64_t lo = bits << sh;
+	atomicOr(out_words + idx, (uint32_t)lo);
+	if (sh + nbits > 32) {
+		atomicOr(out_words + idx + 1, (uint32_t)(lo >> 32));
+		if (sh + nbits > 64) atomicOr(out_words + idx + 2, (uint32_t)(bits >> (64 - sh)));
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
+// K5: bit offset of every block inside its stream (stored blocks byte-align), end-of-stream bits, sizes.
+// ------------------------------------------------------------------------------------------------
+__global__ void k_scan(int nstreams, const uint32_t *__restrict__ nblocks, const uint32_t *__restrict__ blk_off,
+                       BlockMeta *__restrict__ meta, uint8_t *__restrict__ out, const int64_t *__restrict__ out_off,
+                       const int64_t *__restrict__ out_cap, int64_t *__restrict__ out_len, int32_t *__restrict__ status,
+                       int64_t *__restrict__ out_bits, int end_mode) {
+	const int stream = blockIdx.x * blockDim.x + threadIdx.x;
+	if (stream >= nstreams) return;
+	const uint32_t nb = nblocks[stream];
+	BlockMeta *m = meta + blk_off[stream];
+	uint64_t cur = 0;
+	for (uint32_t b = 0; b < nb; b++) {
+		m[b].bit_off = cur;
+		if (m[b].type == 0) cur = ((cur + 3 + 7) & ~7ull) + 32 + 8ull * m[b].byte_len;
+		else cur += (uint64_t)m[b].hdr_bits + m[b].body_bits;
+	}
+	uint64_t tail0 = cur;
+	int ntail10 = 0; // number of 10-bit empty static blocks: "WriteBits(2, 10)" (Deflater.cs:486-504)
+	if (end_mode != B200Z_END_FINISH) {
+		int neededbits = 8 + (int)((0 - cur) & 7);
+		while (neededbits > 0) {
+			++ntail10;
+			cur += 10;
+			neededbits -= 10;
+		}
+	}
+	if (end_mode == B200Z_END_FLUSH_FINISH) cur += 10; // the final empty static block (3, 10 bits)
+	const uint64_t nbytes = (cur + 7) >> 3; // FINISHING_STATE: pending.AlignToByte() (Deflater.cs:507)
+	if ((int64_t)(((nbytes + 3) >> 2) << 2) > out_cap[stream]) {
+		status[stream] = B200Z_E_NOMEM;
+		out_len[stream] = 0;
+		if (out_bits) out_bits[stream] = 0;
+		for (uint32_t b = 0; b < nb; b++) m[b].type = 0xFFu; // tells k_emit to skip
+		return;
+	}
+	uint32_t *ow = reinterpret_cast<uint32_t *>(out + out_off[stream]);
+	uint64_t t = tail0;
+	for (int i = 0; i < ntail10; i++, t += 10) or_bits(ow, t, 2, 10);
+	if (end_mode == B200Z_END_FLUSH_FINISH) or_bits(ow, t, 3, 10);
+	status[stream] = B200Z_OK;
+	out_len[stream] = (int64_t)nbytes;
+	if (out_bits) out_bits[stream] = (int64_t)cur; // exact length; a flushed stream may end inside its last byte
+}
+
+// ------------------------------------------------------------------------------------------------
+// K6: bit emission.  One CTA per block; symbols are encoded 256 at a time, a block-wide exclusive scan of the code
+// lengths gives every symbol its bit position, and the code words are OR-ed into the (zeroed) output words.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+    k_emit(const uint8_t *__restrict__ in, const uint32_t *__restrict__ sym, uint8_t *__restrict__ out,
+           const int64_t *__restrict__ in_off, const int64_t *__restrict__ out_off, const uint32_t *__restrict__ nblocks,
+           const uint32_t *__restrict__ blk_off, const int32_t *__restrict__ blk_desc, const BlockMeta *__restrict__ meta,
+           const BlockTables *__restrict__ tables) {
+	__shared__ BlockTables s_tab;
+	__shared__ uint32_t s_warp[8];
+	__shared__ uint64_t s_base;
+	const int g = blockIdx.x;
+	const int stream = blk_desc[g];
+	const uint32_t b = (uint32_t)g - blk_off[stream];
+	if (b >= nblocks[stream]) return;
+	const BlockMeta m = meta[g];
+	if (m.type == 0xFFu) return;
+	uint32_t *ow = reinterpret_cast<uint32_t *>(out + out_off[stream]);
+	if (m.type == 0) {
+		// FlushStoredBlock (:766-779): 3 header bits, pad to byte, LEN, ~LEN, raw bytes
+		const uint8_t *src = in + in_off[stream] + m.byte_start;
+		const uint64_t hb = ((m.bit_off + 3 + 7) & ~7ull);
+		if (threadIdx.x == 0) {
+			or_bits(ow, m.bit_off, tables[g].hdr[0] & 7u, 3);
+			or_bits(ow, hb, m.byte_len & 0xFFFFu, 16);
+			or_bits(ow, hb + 16, (~m.byte_len) & 0xFFFFu, 16);
+		}
+		const uint64_t d0 = (hb + 32) >> 3; // byte offset of the payload in the stream's output
+		uint8_t *ob = out + out_off[stream];
+		// head bytes up to a word boundary and tail bytes go through atomicOr; whole words are plain stores
+		const uint32_t len = m.byte_len;
+		uint32_t headn = (uint32_t)((4 - (d0 & 3)) & 3);
+		if (headn > len) headn = len;
+		const uint32_t nwords = (len - headn) >> 2;
+		const uint32_t tailn = len - headn - (nwords << 2);
+		for (uint32_t i = threadIdx.x; i < headn; i += blockDim.x) or_bits(ow, (d0 + i) << 3, src[i], 8);
+		uint32_t *wdst = reinterpret_cast<uint32_t *>(ob + d0 + headn);
+		for (uint32_t i = threadIdx.x; i < nwords; i += blockDim.x) {
+			const uint8_t *s4 = src + headn + (i << 2);
+			wdst[i] = (uint32_t)s4[0] | ((uint32_t)s4[1] << 8) | ((uint32_t)s4[2] << 16) | ((uint32_t)s4[3] << 24);
+		}
+		for (uint32_t i = threadIdx.x; i < tailn; i += blockDim.x)
+			or_bits(ow, (d0 + headn + (nwords << 2) + i) << 3, src[headn + (nwords << 2) + i], 8);
+		return;
+	}
+	{
+		const uint4 *src = reinterpret_cast<const uint4 *>(&tables[g]);
+		uint4 *dst = reinterpret_cast<uint4 *>(&s_tab);
+		for (int i = threadIdx.x; i < (int)(sizeof(BlockTables) / 16); i += blockDim.x) dst[i] = src[i];
+	}
+	if (threadIdx.x == 0) s_base = m.bit_off + m.hdr_bits;
+	__syncthreads();
+	// header words
+	for (uint32_t i = threadIdx.x; i * 32 < m.hdr_bits; i += blockDim.x) {
+		const uint32_t rem = m.hdr_bits - i * 32;
+		const int nbw = rem < 32 ? (int)rem : 32;
+		uint32_t v = s_tab.hdr[i];
+		if (nbw < 32) v &= (1u << nbw) - 1u;
+		or_bits(ow, m.bit_off + i * 32ull, v, nbw);
+	}
+	const uint32_t *sp = sym + in_off[stream] + b * (uint32_t)kBlockSyms;
+	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+	for (uint32_t i0 = 0; i0 < m.nsyms; i0 += blockDim.x) {
+		const uint32_t i = i0 + threadIdx.x;
+		uint64_t bits = 0;
+		int nb = 0;
+		if (i < m.nsyms) encode_symbol(sp[i], s_tab.lit_codes, s_tab.lit_len, s_tab.dist_codes, s_tab.dist_len, bits, nb);
+		// block-wide exclusive scan of nb
+		uint32_t incl = (uint32_t)nb;
+		for (int o = 1; o < 32; o <<= 1) {
+			uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+			if (lane >= o) incl += t;
+		}
+		if (lane == 31) s_warp[wid] = incl;
+		__syncthreads();
+		uint32_t woff = 0, tot = 0;
+		for (int k = 0; k < 8; k++) {
+			const uint32_t v = s_warp[k];
+			if (k < wid) woff += v;
+			tot += v;
+		}
+		const uint64_t base = s_base;
+		or_bits(ow, base + woff + incl - (uint32_t)nb, bits, nb);
+		__syncthreads();
+		if (threadIdx.x == 0) s_base = base + tot;
+		__syncthreads();
+	}
+	if (threadIdx.x == 0) or_bits(ow, s_base, s_tab.lit_codes[256], s_tab.lit_len[256]); // EOF_SYMBOL (:750)
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+int deflate_plan_build(b200z_plan *p) {
+	const LevelParams lp = level_params(p->level);
+	if (lp.func != 2) {
+		set_error("level %d (DeflateStored/DeflateFast) is not accelerated by this build; levels 5-9 are", p->level);
+		return B200Z_E_UNSUPPORTED;
+	}
+	const int n = p->n;
+	p->in_off.resize(n);
+	p->out_off.resize(n);
+	p->out_cap.resize(n);
+	int64_t io = 0, oo = 0;
+	std::vector<int2> runs, tiles;
+	std::vector<uint32_t> blk_off(n + 1);
+	std::vector<int32_t> blk_desc;
+	uint32_t nblk = 0;
+	for (int i = 0; i < n; i++) {
+		const int64_t len = p->in_len[i];
+		if (len < 0 || len > 0xFFFF0000ll) {
+			set_error("stream %d: length %lld out of range", i, (long long)len);
+			return B200Z_E_ARG;
+		}
+		p->in_off[i] = io;
+		io += align_up(len + 16, kAlign);
+		p->out_off[i] = oo;
+		p->out_cap[i] = align_up(b200z_deflate_bound(len), kAlign);
+		oo += p->out_cap[i];
+		for (int64_t s = 0; s < len; s += kRun) runs.push_back(make_int2(i, (int)s));
+		for (int64_t s = 0; s < len; s += kTile) tiles.push_back(make_int2(i, (int)s));
+		blk_off[i] = nblk;
+		const uint32_t maxb = (uint32_t)(len / kBlockSyms) + 2;
+		for (uint32_t b = 0; b < maxb; b++) blk_desc.push_back(i);
+		nblk += maxb;
+	}
+	blk_off[n] = nblk;
+	p->in_bytes = io;
+	p->out_bytes = oo;
+	p->n_runs = (int)runs.size();
+	p->n_tiles = (int)tiles.size();
+	p->n_blkmax = (int)nblk;
+	Arena &ws = p->ws;
+	p->o_in_off = ws.reserve(8ll * n);
+	p->o_in_len = ws.reserve(8ll * n);
+	p->o_out_off = ws.reserve(8ll * n);
+	p->o_out_cap = ws.reserve(8ll * n);
+	p->o_run_desc = ws.reserve(8ll * (runs.size() + 1));
+	p->o_tile_desc = ws.reserve(8ll * (tiles.size() + 1));
+	p->o_blk_desc = ws.reserve(4ll * (nblk + 1));
+	p->o_blk_off = ws.reserve(4ll * (n + 1));
+	p->o_nsyms = ws.reserve(4ll * n);
+	p->o_nblocks = ws.reserve(4ll * n);
+	p->o_blk_start = ws.reserve(4ll * (nblk + 1));
+	p->o_blk_ptop = ws.reserve(4ll * (nblk + 1));
+	p->o_meta = ws.reserve((int64_t)sizeof(BlockMeta) * (nblk + 1));
+	p->o_tables = ws.reserve((int64_t)sizeof(BlockTables) * (nblk + 1));
+	p->o_link = ws.reserve(2ll * io + 64);
+	p->o_mt = ws.reserve(8ll * io + 64);
+	p->o_sym = ws.reserve(4ll * io + 64);
+	std::vector<CkTile> ck_tiles;
+	if (p->wrap != B200Z_WRAP_RAW) {
+		checksum_tiles(p->in_len.data(), n, ck_tiles, p->wrap == B200Z_WRAP_GZIP ? 0 : 1);
+		p->n_ck_tiles = (int)ck_tiles.size();
+		p->o_ck_desc = ws.reserve((int64_t)sizeof(CkTile) * (ck_tiles.size() + 1));
+		p->o_ck_acc = ws.reserve(16ll * (n + 1));
+	}
+	int rc = ws.alloc();
+	if (rc) return rc;
+	B200Z_CUDA(cudaMemcpy(ws.at<int64_t>(p->o_in_off), p->in_off.data(), 8ll * n, cudaMemcpyHostToDevice));
+	B200Z_CUDA(cudaMemcpy(ws.at<int64_t>(p->o_in_len), p->in_len.data(), 8ll * n, cudaMemcpyHostToDevice));
+	B200Z_CUDA(cudaMemcpy(ws.at<int64_t>(p->o_out_off), p->out_off.data(), 8ll * n, cudaMemcpyHostToDevice));
+	B200Z_CUDA(cudaMemcpy(ws.at<int64_t>(p->o_out_cap), p->out_cap.data(), 8ll * n, cudaMemcpyHostToDevice));
+	if (!runs.empty()) B200Z_CUDA(cudaMemcpy(ws.at<int2>(p->o_run_desc), runs.data(), 8ll * runs.size(), cudaMemcpyHostToDevice));
+	if (!tiles.empty()) B200Z_CUDA(cudaMemcpy(ws.at<int2>(p->o_tile_desc), tiles.data(), 8ll * tiles.size(), cudaMemcpyHostToDevice));
+	B200Z_CUDA(cudaMemcpy(ws.at<int32_t>(p->o_blk_desc), blk_desc.data(), 4ll * nblk, cudaMemcpyHostToDevice));
+	B200Z_CUDA(cudaMemcpy(ws.at<uint32_t>(p->o_blk_off), blk_off.data(), 4ll * (n + 1), cudaMemcpyHostToDevice));
+	if (!ck_tiles.empty())
+		B200Z_CUDA(cudaMemcpy(ws.at<CkTile>(p->o_ck_desc), ck_tiles.data(), sizeof(CkTile) * ck_tiles.size(),
+		                      cudaMemcpyHostToDevice));
+	B200Z_CUDA(cudaFuncSetAttribute(k_links, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+	B200Z_CUDA(cudaFuncSetAttribute(k_match, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileData + 2 * 2 * kTile));
+	p->launches = 6 + (p->wrap != B200Z_WRAP_RAW ? 3 : 0); // + one memset node
+	return B200Z_OK;
+}
+
+int deflate_plan_run(b200z_plan *p, const uint8_t *d_in, uint8_t *d_out, int64_t *d_out_len, int32_t *d_status,
+                     uint32_t *d_check, int64_t *d_out_bits, cudaStream_t s) {
+	const Arena &ws = p->ws;
+	const int n = p->n;
+	if (n == 0) return B200Z_OK;
+	const LevelParams lp = level_params(p->level);
+	const int64_t *in_off = ws.at<int64_t>(p->o_in_off), *in_len = ws.at<int64_t>(p->o_in_len);
+	const int64_t *out_off = ws.at<int64_t>(p->o_out_off), *out_cap = ws.at<int64_t>(p->o_out_cap);
+	uint16_t *link = ws.at<uint16_t>(p->o_link);
+	uint2 *mt = ws.at<uint2>(p->o_mt);
+	uint32_t *sym = ws.at<uint32_t>(p->o_sym);
+	uint32_t *nsyms = ws.at<uint32_t>(p->o_nsyms), *nblocks = ws.at<uint32_t>(p->o_nblocks);
+	uint32_t *blk_off = ws.at<uint32_t>(p->o_blk_off);
+	int32_t *blk_desc = ws.at<int32_t>(p->o_blk_desc);
+	uint32_t *blk_start = ws.at<uint32_t>(p->o_blk_start), *blk_ptop = ws.at<uint32_t>(p->o_blk_ptop);
+	BlockMeta *meta = ws.at<BlockMeta>(p->o_meta);
+	BlockTables *tables = ws.at<BlockTables>(p->o_tables);
+
+	B200Z_CUDA(cudaMemsetAsync(d_out, 0, (size_t)p->out_bytes, s));
+	if (p->n_runs) k_links<<<p->n_runs, 32, 65536, s>>>(d_in, link, in_off, in_len, ws.at<int2>(p->o_run_desc));
+	if (p->n_tiles)
+		k_match<<<p->n_tiles, kMatchThreads, kTileData + 2 * 2 * kTile, s>>>(d_in, link, mt, in_off, in_len,
+		                                                                   ws.at<int2>(p->o_tile_desc), lp);
+	k_parse<<<(n + kParseWarps - 1) / kParseWarps, kParseWarps * 32, 0, s>>>(d_in, link, mt, sym, in_off, in_len, n, nsyms,
+	                                                                        nblocks, blk_off, blk_start, blk_ptop, lp,
+	                                                                        p->strategy, p->end_mode);
+	k_plan<<<p->n_blkmax, 256, 0, s>>>(sym, in_off, in_len, nsyms, nblocks, blk_off, blk_desc, blk_start, blk_ptop, meta,
+	                                   tables, p->end_mode);
+	k_scan<<<(n + 127) / 128, 128, 0, s>>>(n, nblocks, blk_off, meta, d_out, out_off, out_cap, d_out_len, d_status,
+	                                       d_out_bits, p->end_mode);
+	k_emit<<<p->n_blkmax, 256, 0, s>>>(d_in, sym, d_out, in_off, out_off, nblocks, blk_off, blk_desc, meta, tables);
+	if (p->wrap != B200Z_WRAP_RAW && d_check) {
+		int rc = checksum_launch(p->wrap == B200Z_WRAP_GZIP ? 0 : 1, d_in, in_off, in_len, n, ws.at<CkTile>(p->o_ck_desc),
+		                         p->n_ck_tiles, ws.at<unsigned long long>(p->o_ck_acc), d_check, 1, s);
+		if (rc) return rc;
+	}
+	B200Z_CUDA(cudaGetLastError());
+	return B200Z_OK;
+}
+
+} // namespace b200z

@@ -1,0 +1,490 @@
+// b200z_inflate.cu -- the sm_100a DEFLATE decompressor.
+//
+// Replaces the reference's Inflater mode machine and its helpers:
+//   Inflater.Decode / DecodeHuffman          Zip/Compression/Inflater.cs:429-552, :283-386
+//   InflaterDynHeader.CreateStateMachine     Zip/Compression/InflaterDynHeader.cs:42-120
+//   InflaterHuffmanTree.BuildTree/GetSymbol  Zip/Compression/InflaterHuffmanTree.cs:87-169, :181-235
+//   OutputWindow.Write/Repeat/CopyStored     Zip/Compression/Streams/OutputWindow.cs:35-122
+//   StreamManipulator (bit reader)           Zip/Compression/Streams/StreamManipulator.cs:31-298
+//
+// One warp per stream.  Lane 0 owns the bit reader and the Huffman decode and fills a batch of up to 32 tokens; the
+// warp then places the batch: a prefix sum over token lengths gives every token its output offset, literals are
+// stored by their lanes, back-references that only read bytes produced before the batch are copied by their lanes in
+// parallel, and the remaining (batch-dependent) back-references are copied one after another by the whole warp with
+// the overlap rule of OutputWindow.Repeat (byte k comes from source byte k mod distance).  The output buffer itself
+// is the window: a distance reaching before the start of the stream reads zeros, which is what a fresh reference
+// window holds (trap T13: the reference does not check distances).
+#include "b200z_internal.cuh"
+
+namespace b200z {
+
+constexpr int kLitRoot = 10, kDistRoot = 9;
+constexpr int kInfWarps = 4;
+
+// Inflater.cs:39-68
+__constant__ uint16_t c_cplens[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
+__constant__ uint8_t c_cplext[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
+__constant__ uint16_t c_cpdist[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025, 1537, 2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577};
+__constant__ uint8_t c_cpdext[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
+__constant__ uint8_t c_meta_order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15}; // InflaterDynHeader.cs:24
+
+// status detail codes (bits 8..15 of the per-stream status word); messages in INTEGRATION.md
+enum {
+	D_NONE = 0,
+	D_BLOCK_TYPE = 1,   // "Unknown block type"                      Inflater.cs:486
+	D_STORED_LEN = 2,   // "broken uncompressed block"               Inflater.cs:511
+	D_REP_LEN = 3,      // "Illegal rep length code"                 Inflater.cs:325
+	D_REP_DIST = 4,     // "Illegal rep dist code"                   Inflater.cs:358
+	D_CODELEN0 = 5,     // "Encountered invalid codelength 0"        InflaterHuffmanTree.cs:192
+	D_HDR_RANGE = 6,    // ValueOutOfRangeException                  InflaterDynHeader.cs:50-52
+	D_HDR_REPEAT0 = 7,  // "Cannot repeat previous code length ..."  InflaterDynHeader.cs:83
+	D_HDR_OVERRUN = 8,  // "Cannot repeat code lengths past ..."     InflaterDynHeader.cs:106
+	D_HDR_NO_EOB = 9,   // "... end-of-block code missing"           InflaterDynHeader.cs:114
+	D_OVERSUBSCRIBED = 10 // the reference indexes out of range here; reported as a data error
+};
+
+// decode table entry: nb[0..3] | kind[4..7] | extra[8..11] | base[16..31]
+enum { K_INVALID = 0, K_LIT = 1, K_EOB = 2, K_LEN = 3, K_LONG = 4, K_ILLEGAL = 5, K_DIST = 6 };
+__device__ __forceinline__ uint32_t mk_entry(uint32_t nb, uint32_t kind, uint32_t extra, uint32_t base) {
+	return nb | (kind << 4) | (extra << 8) | (base << 16);
+}
+__device__ __forceinline__ uint32_t litlen_entry(uint32_t sym, uint32_t nb) {
+	if (sym < 256) return mk_entry(nb, K_LIT, 0, sym);
+	if (sym == 256) return mk_entry(nb, K_EOB, 0, 0);
+	if (sym - 257 >= 29) return mk_entry(nb, K_ILLEGAL, 0, 0);
+	return mk_entry(nb, K_LEN, c_cplext[sym - 257], c_cplens[sym - 257]);
+}
+__device__ __forceinline__ uint32_t dist_entry(uint32_t sym, uint32_t nb) {
+	if (sym >= 30) return mk_entry(nb, K_ILLEGAL, 0, 0);
+	return mk_entry(nb, K_DIST, c_cpdext[sym], c_cpdist[sym]);
+}
+
+struct Canon { // canonical-code bookkeeping for codes longer than the root table
+	uint16_t first[16], count[16], offs[16];
+};
+
+struct __align__(16) InfShared {
+	uint32_t lit[1 << kLitRoot];
+	uint32_t dist[1 << kDistRoot];
+	uint32_t meta[128];
+	uint16_t lit_sorted[288];
+	uint16_t dist_sorted[32];
+	Canon lit_c, dist_c;
+	uint8_t lens[320];
+	uint16_t tok_len[32];
+	uint16_t tok_val[32];
+};
+
+// Builds a root table of `R` bits + canonical side tables from code lengths (InflaterHuffmanTree.BuildTree :87-169
+// computes the same canonical assignment).  kind: 0 litlen, 1 dist, 2 meta (19 code-length symbols, 7-bit root, no
+// long codes possible).  Returns 0 or a detail code.  Executed by one lane.
+__device__ int build_table(const uint8_t *lens, int nsym, int R, uint32_t *tab, uint16_t *sorted, Canon *cn, int kind) {
+	uint32_t count[16], next[16];
+	for (int i = 0; i < 16; i++) count[i] = 0;
+	for (int s = 0; s < nsym; s++) count[lens[s]]++;
+	count[0] = 0;
+	int left = 1;
+	for (int L = 1; L <= 15; L++) {
+		left = (left << 1) - (int)count[L];
+		if (left < 0) return D_OVERSUBSCRIBED;
+	}
+	uint32_t code = 0, off = 0;
+	for (int L = 1; L <= 15; L++) {
+		next[L] = code;
+		if (cn) {
+			cn->first[L] = (uint16_t)code;
+			cn->count[L] = (uint16_t)count[L];
+			cn->offs[L] = (uint16_t)off;
+		}
+		if (L > R) off += count[L];
+		code = (code + count[L]) << 1;
+	}
+	const int size = 1 << R;
+	for (int i = 0; i < size; i++) tab[i] = 0;
+	for (int s = 0; s < nsym; s++) {
+		const int L = lens[s];
+		if (!L) continue;
+		const uint32_t c = next[L]++;
+		const uint32_t rev = __brev(c) >> (32 - L);
+		if (L <= R) {
+			const uint32_t e = kind == 0 ? litlen_entry(s, L) : (kind == 1 ? dist_entry(s, L) : mk_entry(L, K_LIT, 0, s));
+			for (uint32_t i = rev; i < (uint32_t)size; i += (1u << L)) tab[i] = e;
+		} else {
+			sorted[cn->offs[L] + (c - cn->first[L])] = (uint16_t)s;
+			tab[rev & (size - 1)] = mk_entry(0, K_LONG, 0, 0);
+		}
+	}
+	return 0;
+}
+
+struct BitReader {
+	const uint32_t *words; // 4-byte aligned stream base
+	uint64_t bb;
+	uint32_t bc;     // valid bits in bb
+	uint32_t widx;   // next word to load
+	uint32_t nwords; // words that hold stream bytes (the last one is masked)
+	uint32_t nbytes;
+	uint64_t consumed; // bits handed out so far
+	__device__ __forceinline__ void refill() {
+		if (bc <= 32) {
+			uint32_t w = 0;
+			if (widx < nwords) {
+				w = __ldg(words + widx);
+				if (widx == nwords - 1 && (nbytes & 3)) w &= (1u << (8 * (nbytes & 3))) - 1u;
+			}
+			++widx;
+			bb |= (uint64_t)w << bc;
+			bc += 32;
+		}
+	}
+	__device__ __forceinline__ uint32_t peek(int n) const { return (uint32_t)bb & ((1u << n) - 1u); }
+	__device__ __forceinline__ void drop(int n) {
+		bb >>= n;
+		bc -= n;
+		consumed += n;
+	}
+	__device__ __forceinline__ uint32_t get(int n) {
+		refill();
+		uint32_t v = peek(n);
+		drop(n);
+		return v;
+	}
+	__device__ __forceinline__ bool overrun() const { return consumed > 8ull * nbytes; }
+};
+
+// decodes one symbol of a tree with long-code fallback; returns the entry (nb already dropped) or 0 when invalid
+__device__ __forceinline__ uint32_t decode_sym(BitReader &br, const uint32_t *tab, int R, const uint16_t *sorted,
+                                               const Canon &cn, int kind) {
+	br.refill();
+	uint32_t e = tab[(uint32_t)br.bb & ((1u << R) - 1u)];
+	const uint32_t k = (e >> 4) & 15;
+	if (k != K_LONG) {
+		if (k != K_INVALID) br.drop(e & 15);
+		return e;
+	}
+	const uint32_t x = __brev((uint32_t)br.bb) >> 17; // next 15 stream bits, first bit most significant
+	for (int L = R + 1; L <= 15; L++) {
+		const uint32_t c = x >> (15 - L);
+		const uint32_t idx = c - cn.first[L];
+		if (idx < cn.count[L]) {
+			const uint32_t s = sorted[cn.offs[L] + idx];
+			br.drop(L);
+			return kind == 0 ? litlen_entry(s, L) : dist_entry(s, L);
+		}
+	}
+	return 0;
+}
+
+__global__ void __launch_bounds__(kInfWarps * 32)
+    k_inflate(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, const int64_t *__restrict__ in_off,
+              const int64_t *__restrict__ in_len, const int64_t *__restrict__ out_off, const int64_t *__restrict__ out_cap,
+              int nstreams, int64_t *__restrict__ out_len, int64_t *__restrict__ in_used, int32_t *__restrict__ status) {
+	__shared__ InfShared sh_all[kInfWarps];
+	const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const int stream = blockIdx.x * kInfWarps + w;
+	if (stream >= nstreams) return;
+	InfShared &sh = sh_all[w];
+	uint8_t *dst = out + out_off[stream];
+	const uint64_t cap = (uint64_t)out_cap[stream];
+
+	BitReader br;
+	br.words = reinterpret_cast<const uint32_t *>(in + in_off[stream]);
+	br.nbytes = (uint32_t)in_len[stream];
+	br.nwords = (br.nbytes + 3) >> 2;
+	br.bb = 0;
+	br.bc = 0;
+	br.widx = 0;
+	br.consumed = 0;
+
+	uint64_t opos = 0;   // bytes produced (uniform across the warp)
+	int st = B200Z_OK;   // lane 0 authoritative, broadcast when it changes
+	int detail = 0;
+	bool last = false, in_block = false, have_static = false, done = false;
+	int cur_static = 0;
+
+	while (!done) {
+		// ---- block header (lane 0) -------------------------------------------------------------------
+		int btype = 0;
+		uint32_t stored_len = 0;
+		if (lane == 0) {
+			if (last) {
+				done = true; // Inflater.cs:443-449: raw mode stops right after the final block
+			} else {
+				const uint32_t hdr = br.get(3);
+				if (br.overrun()) {
+					st = B200Z_E_NEED_INPUT;
+				} else {
+					last = (hdr & 1) != 0;
+					btype = (int)(hdr >> 1);
+					if (btype == 0) {
+						// SkipToByteBoundary, LEN, NLEN (:509)
+						br.drop(br.bc & 7);
+						const uint32_t len = br.get(16);
+						const uint32_t nlen = br.get(16);
+						if (br.overrun()) st = B200Z_E_NEED_INPUT;
+						else if (nlen != (len ^ 0xFFFFu)) { st = B200Z_E_DATA; detail = D_STORED_LEN; }
+						stored_len = len;
+					} else if (btype == 1) {
+						if (!have_static || !cur_static) {
+							for (int i = 0; i < 144; i++) sh.lens[i] = 8;
+							for (int i = 144; i < 256; i++) sh.lens[i] = 9;
+							for (int i = 256; i < 280; i++) sh.lens[i] = 7;
+							for (int i = 280; i < 288; i++) sh.lens[i] = 8;
+							build_table(sh.lens, 288, kLitRoot, sh.lit, sh.lit_sorted, &sh.lit_c, 0);
+							for (int i = 0; i < 32; i++) sh.lens[i] = 5;
+							build_table(sh.lens, 32, kDistRoot, sh.dist, sh.dist_sorted, &sh.dist_c, 1);
+							have_static = true;
+							cur_static = 1;
+						}
+					} else if (btype == 2) {
+						cur_static = 0;
+						// InflaterDynHeader.CreateStateMachine (:42-120)
+						const int nlit = (int)br.get(5) + 257, ndist = (int)br.get(5) + 1, nmeta = (int)br.get(4) + 4;
+						if (nlit > 286 || ndist > 30) { st = B200Z_E_DATA; detail = D_HDR_RANGE; }
+						else {
+							for (int i = 0; i < 19; i++) sh.lens[i] = 0;
+							for (int i = 0; i < nmeta; i++) sh.lens[c_meta_order[i]] = (uint8_t)br.get(3);
+							int d = build_table(sh.lens, 19, 7, sh.meta, nullptr, nullptr, 2);
+							if (d) { st = B200Z_E_DATA; detail = d; }
+							const int total = nlit + ndist;
+							int idx = 0;
+							while (st == B200Z_OK && idx < total) {
+								br.refill();
+								const uint32_t e = sh.meta[br.peek(7)];
+								if (((e >> 4) & 15) == K_INVALID) { st = B200Z_E_DATA; detail = D_CODELEN0; break; }
+								br.drop(e & 15);
+								const int sym = (int)(e >> 16);
+								if (sym < 16) {
+									sh.lens[idx++] = (uint8_t)sym;
+								} else {
+									int rep;
+									uint8_t v = 0;
+									if (sym == 16) {
+										if (idx == 0) { st = B200Z_E_DATA; detail = D_HDR_REPEAT0; break; }
+										v = sh.lens[idx - 1];
+										rep = 3 + (int)br.get(2);
+									} else if (sym == 17) rep = 3 + (int)br.get(3);
+									else rep = 11 + (int)br.get(7);
+									if (idx + rep > total) { st = B200Z_E_DATA; detail = D_HDR_OVERRUN; break; }
+									while (rep-- > 0) sh.lens[idx++] = v;
+								}
+								if (br.overrun()) { st = B200Z_E_NEED_INPUT; break; }
+							}
+							if (st == B200Z_OK && br.overrun()) st = B200Z_E_NEED_INPUT;
+							if (st == B200Z_OK && sh.lens[256] == 0) { st = B200Z_E_DATA; detail = D_HDR_NO_EOB; }
+							if (st == B200Z_OK) {
+								// the distance lengths follow the literal/length ones in the same array; build dist first
+								// from a copy so the literal build may reuse sh.lens[0..nlit)
+								uint8_t dl[32];
+								for (int i = 0; i < ndist; i++) dl[i] = sh.lens[nlit + i];
+								d = build_table(sh.lens, nlit, kLitRoot, sh.lit, sh.lit_sorted, &sh.lit_c, 0);
+								if (!d) d = build_table(dl, ndist, kDistRoot, sh.dist, sh.dist_sorted, &sh.dist_c, 1);
+								if (d) { st = B200Z_E_DATA; detail = d; }
+							}
+						}
+					} else {
+						st = B200Z_E_DATA;
+						detail = D_BLOCK_TYPE;
+					}
+				}
+			}
+		}
+		done = __shfl_sync(0xffffffffu, (int)done, 0) != 0;
+		st = __shfl_sync(0xffffffffu, st, 0);
+		if (done || st != B200Z_OK) break;
+		btype = __shfl_sync(0xffffffffu, btype, 0);
+		__syncwarp();
+
+		if (btype == 0) {
+			// ---- stored block: OutputWindow.CopyStored (:100-122), whole warp ---------------------------
+			stored_len = __shfl_sync(0xffffffffu, stored_len, 0);
+			// byte position of the payload in the input
+			uint64_t bitpos = __shfl_sync(0xffffffffu, (unsigned long long)br.consumed, 0);
+			const uint64_t ipos = bitpos >> 3;
+			const uint64_t avail = ipos <= br.nbytes ? br.nbytes - ipos : 0;
+			if (stored_len > avail) st = B200Z_E_NEED_INPUT;
+			else if (opos + stored_len > cap) st = B200Z_E_NOMEM;
+			if (st != B200Z_OK) break;
+			const uint8_t *src = in + in_off[stream] + ipos;
+			for (uint32_t i = lane; i < stored_len; i += 32) dst[opos + i] = src[i];
+			opos += stored_len;
+			if (lane == 0) {
+				// re-seat the bit reader after the payload
+				const uint64_t nb = 8ull * (ipos + stored_len);
+				br.consumed = nb;
+				br.widx = (uint32_t)(nb >> 5);
+				br.bb = 0;
+				br.bc = 0;
+				const uint32_t sk = (uint32_t)(nb & 31);
+				if (sk) {
+					br.refill();
+					br.bb >>= sk;
+					br.bc -= sk;
+				}
+			}
+			__syncwarp();
+			continue;
+		}
+
+		// ---- Huffman block: batches of up to 32 tokens --------------------------------------------------
+		in_block = true;
+		while (in_block) {
+			int ntok = 0;
+			if (lane == 0) {
+				uint64_t budget = cap - opos; // bytes still allowed
+				while (ntok < 32) {
+					uint32_t e = decode_sym(br, sh.lit, kLitRoot, sh.lit_sorted, sh.lit_c, 0);
+					const uint32_t k = (e >> 4) & 15;
+					if (br.overrun()) { st = B200Z_E_NEED_INPUT; break; } // the symbol used bits past the end of the input
+					if (k == K_LIT) {
+						if (budget < 1) { st = B200Z_E_NOMEM; break; }
+						sh.tok_len[ntok] = 1;
+						sh.tok_val[ntok] = (uint16_t)(e >> 16);
+						++ntok;
+						--budget;
+						continue;
+					}
+					if (k == K_LEN) {
+						uint32_t len = e >> 16;
+						const int xb = (int)((e >> 8) & 15);
+						if (xb) len += br.get(xb);
+						uint32_t de = decode_sym(br, sh.dist, kDistRoot, sh.dist_sorted, sh.dist_c, 1);
+						const uint32_t dk = (de >> 4) & 15;
+						if (dk != K_DIST) {
+							st = br.overrun() ? B200Z_E_NEED_INPUT : B200Z_E_DATA;
+							detail = dk == K_ILLEGAL ? D_REP_DIST : D_CODELEN0;
+							break;
+						}
+						uint32_t dist = de >> 16;
+						const int dxb = (int)((de >> 8) & 15);
+						if (dxb) dist += br.get(dxb);
+						if (br.overrun()) { st = B200Z_E_NEED_INPUT; break; }
+						if (budget < len) { st = B200Z_E_NOMEM; break; }
+						sh.tok_len[ntok] = (uint16_t)len;
+						sh.tok_val[ntok] = (uint16_t)dist;
+						++ntok;
+						budget -= len;
+						continue;
+					}
+					if (k == K_EOB) {
+						if (br.overrun()) st = B200Z_E_NEED_INPUT;
+						in_block = false;
+						break;
+					}
+					// invalid / illegal
+					st = br.overrun() ? B200Z_E_NEED_INPUT : B200Z_E_DATA;
+					detail = k == K_ILLEGAL ? D_REP_LEN : D_CODELEN0;
+					break;
+				}
+				if (st == B200Z_OK && br.overrun()) st = B200Z_E_NEED_INPUT;
+			}
+			ntok = __shfl_sync(0xffffffffu, ntok, 0);
+			in_block = __shfl_sync(0xffffffffu, (int)in_block, 0) != 0;
+			st = __shfl_sync(0xffffffffu, st, 0);
+			__syncwarp();
+			// ---- place the batch (tokens decoded before an error are still valid output) ---------------
+			uint32_t len = 0, val = 0;
+			bool is_match = false;
+			if (lane < ntok) {
+				len = sh.tok_len[lane];
+				val = sh.tok_val[lane];
+				is_match = len >= 3; // literals have len 1, matches len >= 3
+			}
+			uint32_t incl = len;
+			for (int o = 1; o < 32; o <<= 1) {
+				const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+				if (lane >= o) incl += t;
+			}
+			const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+			const uint64_t my = opos + incl - len;
+			if (lane < ntok && !is_match) dst[my] = (uint8_t)val;
+			// back-references that read only pre-batch bytes: all lanes at once
+			const bool indep = is_match && (my - opos + (len < val ? len : val)) <= (uint64_t)val;
+			if (indep) {
+				for (uint32_t k2 = 0; k2 < len; k2++) {
+					const uint32_t o = k2 < val ? k2 : k2 % val;
+					const uint64_t sidx = my + o;
+					dst[my + k2] = sidx >= val ? dst[sidx - val] : (uint8_t)0;
+				}
+			}
+			__syncwarp();
+			uint32_t dep = __ballot_sync(0xffffffffu, is_match && !indep);
+			while (dep) {
+				const int l = __ffs(dep) - 1;
+				dep &= dep - 1;
+				const uint32_t mlen = __shfl_sync(0xffffffffu, len, l);
+				const uint32_t mdist = __shfl_sync(0xffffffffu, val, l);
+				const uint64_t mpos = __shfl_sync(0xffffffffu, (unsigned long long)my, l);
+				for (uint32_t k2 = lane; k2 < mlen; k2 += 32) {
+					const uint32_t o = k2 < mdist ? k2 : k2 % mdist;
+					const uint64_t sidx = mpos + o;
+					dst[mpos + k2] = sidx >= mdist ? dst[sidx - mdist] : (uint8_t)0;
+				}
+				__syncwarp();
+			}
+			opos += total;
+			if (st != B200Z_OK) break;
+		}
+		if (st != B200Z_OK) break;
+	}
+	if (lane == 0) {
+		status[stream] = st | (detail << 8);
+		out_len[stream] = (int64_t)opos;
+		if (in_used) {
+			uint64_t used = (br.consumed + 7) >> 3; // n - RemainingInput (trap T14)
+			if (used > br.nbytes) used = br.nbytes;
+			in_used[stream] = (int64_t)used;
+		}
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
+int inflate_plan_build(b200z_plan *p) {
+	const int n = p->n;
+	p->in_off.resize(n);
+	p->out_off.resize(n);
+	int64_t io = 0, oo = 0;
+	for (int i = 0; i < n; i++) {
+		if (p->in_len[i] < 0 || p->in_len[i] > 0xFFFF0000ll || p->out_cap[i] < 0) {
+			set_error("stream %d: size out of range", i);
+			return B200Z_E_ARG;
+		}
+		p->in_off[i] = io;
+		io += align_up(p->in_len[i] + 16, kAlign);
+		p->out_off[i] = oo;
+		oo += align_up(p->out_cap[i] + 16, kAlign);
+	}
+	p->in_bytes = io;
+	p->out_bytes = oo;
+	Arena &ws = p->ws;
+	p->o_in_off = ws.reserve(8ll * (n + 1));
+	p->o_in_len = ws.reserve(8ll * (n + 1));
+	p->o_out_off = ws.reserve(8ll * (n + 1));
+	p->o_out_cap = ws.reserve(8ll * (n + 1));
+	std::vector<CkTile> ck_tiles;
+	int rc = ws.alloc();
+	if (rc) return rc;
+	if (n) {
+		B200Z_CUDA(cudaMemcpy(ws.at<int64_t>(p->o_in_off), p->in_off.data(), 8ll * n, cudaMemcpyHostToDevice));
+		B200Z_CUDA(cudaMemcpy(ws.at<int64_t>(p->o_in_len), p->in_len.data(), 8ll * n, cudaMemcpyHostToDevice));
+		B200Z_CUDA(cudaMemcpy(ws.at<int64_t>(p->o_out_off), p->out_off.data(), 8ll * n, cudaMemcpyHostToDevice));
+		B200Z_CUDA(cudaMemcpy(ws.at<int64_t>(p->o_out_cap), p->out_cap.data(), 8ll * n, cudaMemcpyHostToDevice));
+	}
+	p->launches = 1;
+	return B200Z_OK;
+}
+
+int inflate_plan_run(b200z_plan *p, const uint8_t *d_in, uint8_t *d_out, int64_t *d_out_len, int32_t *d_status,
+                     uint32_t *d_check, int64_t *d_in_used, cudaStream_t s) {
+	const Arena &ws = p->ws;
+	const int n = p->n;
+	if (n == 0) return B200Z_OK;
+	(void)d_check;
+	k_inflate<<<(n + kInfWarps - 1) / kInfWarps, kInfWarps * 32, 0, s>>>(
+	    d_in, d_out, ws.at<int64_t>(p->o_in_off), ws.at<int64_t>(p->o_in_len), ws.at<int64_t>(p->o_out_off),
+	    ws.at<int64_t>(p->o_out_cap), n, d_out_len, d_in_used, d_status);
+	B200Z_CUDA(cudaGetLastError());
+	return B200Z_OK;
+}
+
+} // namespace b200z

@@ -1,0 +1,106 @@
+// b200z_internal.cuh -- shared host-side plumbing of libb200z.so (context, error reporting, plan object).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "../../include/b200z.h"
+#include "b200z_core.cuh"
+#include "b200z_crc.cuh"
+
+namespace b200z {
+
+void set_error(const char *fmt, ...);
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
+
+#define B200Z_CUDA(call)                                                                   \
+	do {                                                                                   \
+		cudaError_t e__ = (call);                                                          \
+		if (e__ != cudaSuccess) return ::b200z::cuda_fail(e__, #call, __FILE__, __LINE__); \
+	} while (0)
+
+int ensure_init(); // picks up the current device if b200z_init() was not called explicitly
+
+constexpr int64_t kAlign = 256; // stream slots in the blobs start on 256-byte boundaries (vector loads / bulk copies)
+inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
+
+// One device allocation carved into typed arrays.
+struct Arena {
+	uint8_t *base = nullptr;
+	int64_t size = 0, used = 0;
+	int64_t reserve(int64_t bytes) { // planning pass: returns offset
+		int64_t off = align_up(used, 256);
+		used = off + bytes;
+		return off;
+	}
+	int alloc();
+	void release();
+	template <class T> T *at(int64_t off) const { return reinterpret_cast<T *>(base + off); }
+};
+
+// per-block tables produced by k_plan and consumed by k_emit
+struct __align__(16) BlockTables {
+	uint16_t lit_codes[kLiteralNum];
+	uint16_t dist_codes[kDistNum];
+	uint8_t lit_len[kLiteralNum];
+	uint8_t dist_len[kDistNum];
+	uint32_t hdr[kHdrWords];
+};
+
+struct __align__(16) BlockMeta {
+	uint32_t byte_start; // first input byte covered by the block
+	uint32_t byte_len;   // storedLength
+	uint32_t nsyms;
+	uint32_t hdr_bits;
+	uint32_t body_bits;
+	uint32_t type; // 0 stored, 1 static, 2 dynamic
+	uint64_t bit_off; // absolute bit offset inside the stream's output slot (k_scan)
+};
+
+// Inflate: one LZ77 back-reference to resolve (phase 2)
+struct __align__(8) MatchTok {
+	uint32_t out_pos;
+	uint16_t len;
+	uint16_t dist;
+};
+
+} // namespace b200z
+
+struct b200z_plan {
+	int kind = 0; // 0 deflate, 1 inflate
+	int n = 0;
+	int level = 6, strategy = 0, wrap = 0, end_mode = 0;
+	std::vector<int64_t> in_len, in_off, out_off, out_cap;
+	int64_t in_bytes = 0, out_bytes = 0;
+	b200z::Arena ws;
+	int launches = 0;
+	// deflate workspace offsets
+	int64_t o_in_off = 0, o_in_len = 0, o_out_off = 0, o_out_cap = 0;
+	int64_t o_run_desc = 0, o_tile_desc = 0, o_blk_desc = 0, o_blk_off = 0;
+	int64_t o_link = 0, o_mt = 0, o_sym = 0, o_nsyms = 0, o_nblocks = 0;
+	int64_t o_blk_start = 0, o_blk_ptop = 0, o_meta = 0, o_tables = 0;
+	int n_runs = 0, n_tiles = 0, n_blkmax = 0;
+	// inflate workspace offsets
+	int64_t o_tok = 0, o_ntok = 0, o_tok_off = 0;
+	// checksum scratch
+	int64_t o_ck_desc = 0, o_ck_acc = 0;
+	int n_ck_tiles = 0;
+};
+
+namespace b200z {
+// implemented in b200z_deflate.cu / b200z_inflate.cu / b200z_checksum.cu
+int deflate_plan_build(b200z_plan *p);
+int deflate_plan_run(b200z_plan *p, const uint8_t *d_in, uint8_t *d_out, int64_t *d_out_len, int32_t *d_status,
+                     uint32_t *d_check, int64_t *d_out_bits, cudaStream_t s);
+int inflate_plan_build(b200z_plan *p);
+int inflate_plan_run(b200z_plan *p, const uint8_t *d_in, uint8_t *d_out, int64_t *d_out_len, int32_t *d_status,
+                     uint32_t *d_check, int64_t *d_in_used, cudaStream_t s);
+// checksum over n device buffers (kind 0 = CRC32, 1 = Adler32); d_acc = 2 x uint64 scratch per stream;
+// value in/out (device uint32), `fresh` != 0 starts from the Reset() value instead of reading d_value.
+int checksum_launch(int kind, const uint8_t *d_data, const int64_t *d_off, const int64_t *d_len, int32_t n,
+                    const CkTile *d_tiles, int32_t n_tiles, unsigned long long *d_acc, uint32_t *d_value, int fresh,
+                    cudaStream_t s);
+int checksum_tiles(const int64_t *len, int32_t n, std::vector<CkTile> &tiles, int kind);
+int checksum_init_tables();
+} // namespace b200z

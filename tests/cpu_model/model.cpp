@@ -1,0 +1,198 @@
+// model.cpp -- TEST INFRASTRUCTURE.  Serial host execution of the *kernel decomposition* in
+// sharpziplib_b200/csrc/b200z_core.cuh (the very same __host__ __device__ functions the sm_100a kernels call),
+// so the exactness of the parallel reformulation can be checked against the oracle in the CPU-only test tier.
+// It is not a fallback: the product library never links it.
+#include "b200z_core.cuh"
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+using namespace b200z;
+
+namespace {
+
+// K1 as the kernel does it: 32 positions per step, a 16-bit head table relative to a sliding base.
+void model_links(const uint8_t *data, uint32_t n, std::vector<uint16_t> &link) {
+	link.assign(n, 0);
+	std::vector<uint16_t> head(32768, 0);
+	uint32_t winbase = 0; // head entry v > 0 means position winbase + v - 1
+	for (uint32_t base = 0; base < n; base += 32) {
+		// re-base so that every stored value stays within 16 bits
+		while (base + 32 - winbase > 65535) {
+			for (auto &v : head) v = v > 32768 ? (uint16_t)(v - 32768) : 0;
+			winbase += 32768;
+		}
+		uint32_t h[32];
+		bool valid[32];
+		for (int l = 0; l < 32; l++) {
+			uint32_t p = base + l;
+			valid[l] = p + 2 < n;
+			h[l] = valid[l] ? hash3(data[p], data[p + 1], data[p + 2]) : 0xFFFFFFFFu;
+		}
+		uint32_t q[32];
+		for (int l = 0; l < 32; l++) {
+			q[l] = 0xFFFFFFFFu;
+			if (!valid[l]) continue;
+			int lower = -1;
+			for (int k = 0; k < l; k++)
+				if (valid[k] && h[k] == h[l]) lower = k;
+			if (lower >= 0) q[l] = base + lower;
+			else if (head[h[l]]) q[l] = winbase + head[h[l]] - 1;
+		}
+		for (int l = 0; l < 32; l++) {
+			if (!valid[l]) continue;
+			bool top = true;
+			for (int k = l + 1; k < 32; k++)
+				if (valid[k] && h[k] == h[l]) top = false;
+			if (top) head[h[l]] = (uint16_t)(base + l - winbase + 1);
+			uint32_t p = base + l;
+			if (q[l] != 0xFFFFFFFFu && p - q[l] <= (uint32_t)kMaxDist) link[p] = (uint16_t)(p - q[l]);
+		}
+	}
+}
+
+struct Writer { // what the emit kernel does with atomicOr on zeroed 32-bit words
+	std::vector<uint32_t> w;
+	void put(uint64_t bitpos, uint64_t bits, int nbits) {
+		while (nbits > 0) {
+			uint64_t idx = bitpos >> 5;
+			int sh = (int)(bitpos & 31);
+			int take = 32 - sh < nbits ? 32 - sh : nbits;
+			if (w.size() <= idx) w.resize(idx + 1, 0);
+			w[idx] |= (uint32_t)((bits & ((take == 64 ? 0 : (1ull << take)) - 1)) << sh);
+			bits >>= take;
+			bitpos += take;
+			nbits -= take;
+		}
+	}
+};
+
+} // namespace
+
+extern "C" int model_deflate(const uint8_t *data, uint32_t n, int level, int strategy, int flush_then_finish,
+                             uint8_t *out, uint64_t cap, uint64_t *outlen) {
+	LevelParams lp = level_params(level);
+	if (lp.func != 2) return 100; // only the lazy levels are modelled
+	std::vector<uint16_t> link;
+	model_links(data, n, link);
+	// K2: every position
+	std::vector<uint32_t> tabA(n), tabB(n);
+	for (uint32_t p = 0; p < n; p++) match_search(data, link.data(), 0u, p, n, lp, tabA[p], tabB[p]);
+	// K3
+	std::vector<uint32_t> syms;
+	std::vector<uint32_t> blk_start; // byte position of each block's first symbol
+	std::vector<uint32_t> blk_ptop;  // loop top at which the block was flushed
+	ParseState st;
+	parse_init(st);
+	uint32_t bytes_done = 0;
+	blk_start.push_back(0);
+	uint32_t last_top = 0;
+	bool ended_full = false;
+	while (st.p < n) {
+		uint32_t sym;
+		last_top = st.p;
+		int e = parse_step(
+		    st, n, lp, strategy, [&](uint32_t p, uint32_t &a, uint32_t &b) { a = tabA[p]; b = tabB[p]; },
+		    [&](uint32_t q) { return (uint32_t)data[q]; },
+		    [&](uint32_t p, uint32_t m0, uint32_t budget) { return match_search_above(data, link.data(), p, n, m0, budget); },
+		    sym);
+		ended_full = false;
+		if (e) {
+			syms.push_back(sym);
+			bytes_done += sym_len(sym);
+			if (syms.size() % kBlockSyms == 0) {
+				blk_ptop.push_back(last_top);
+				blk_start.push_back(bytes_done);
+				ended_full = !flush_then_finish && (st.p >= n) && !st.prevAvail;
+			}
+		}
+	}
+	if (!ended_full) {
+		// final flush at lookahead == 0 (:750-768)
+		if (st.prevAvail) {
+			syms.push_back(sym_lit(data[st.p - 1]));
+			bytes_done += 1;
+		}
+		blk_ptop.push_back(last_top);
+	} else {
+		blk_start.pop_back();
+	}
+	size_t nblocks = blk_ptop.size();
+	Writer W;
+	uint64_t bitpos = 0;
+	std::vector<int> scratch(9 * 286 + 64);
+	for (size_t b = 0; b < nblocks; b++) {
+		size_t s0 = b * (size_t)kBlockSyms;
+		size_t s1 = s0 + kBlockSyms < syms.size() ? s0 + kBlockSyms : syms.size();
+		int lit_freqs[kLiteralNum] = {0}, dist_freqs[kDistNum] = {0};
+		int extra = 0;
+		uint32_t blen = 0;
+		for (size_t i = s0; i < s1; i++) {
+			uint32_t s = syms[i];
+			blen += sym_len(s);
+			if (sym_dist(s) == 0) lit_freqs[s & 0xFF]++;
+			else {
+				int lc = lcode((int)(s & 0xFF)), dc = dcode((int)sym_dist(s) - 1);
+				lit_freqs[lc]++;
+				dist_freqs[dc]++;
+				extra += tally_extra_bits(lc, dc);
+			}
+		}
+		lit_freqs[256]++;
+		bool last = (b + 1 == nblocks) && !flush_then_finish;
+		int64_t storedOffset = (int64_t)blk_start[b] + 1 - 32768ll * (int64_t)slides_done(blk_ptop[b]);
+		uint8_t lit_len[kLiteralNum], dist_len[kDistNum];
+		uint16_t lit_codes[kLiteralNum], dist_codes[kDistNum];
+		uint32_t hdr[192];
+		std::memset(hdr, 0, sizeof(hdr));
+		BlockPlan plan;
+		plan_block(lit_freqs, dist_freqs, extra, storedOffset >= 0, (int)blen, last, lit_len, lit_codes, dist_len,
+		           dist_codes, hdr, scratch.data(), plan);
+		if (plan.type == 0) {
+			W.put(bitpos, hdr[0], 3);
+			bitpos += 3;
+			bitpos = (bitpos + 7) & ~7ull;
+			W.put(bitpos, blen & 0xFFFF, 16);
+			W.put(bitpos + 16, (~blen) & 0xFFFF, 16);
+			bitpos += 32;
+			for (uint32_t i = 0; i < blen; i++) {
+				W.put(bitpos, data[blk_start[b] + i], 8);
+				bitpos += 8;
+			}
+		} else {
+			for (uint32_t i = 0; i < plan.hdr_bits; i += 32) {
+				int nb = plan.hdr_bits - i < 32 ? (int)(plan.hdr_bits - i) : 32;
+				W.put(bitpos + i, hdr[i >> 5] & (nb == 32 ? 0xFFFFFFFFu : ((1u << nb) - 1)), nb);
+			}
+			bitpos += plan.hdr_bits;
+			uint64_t body0 = bitpos;
+			for (size_t i = s0; i < s1; i++) {
+				uint64_t bits;
+				int nb;
+				encode_symbol(syms[i], lit_codes, lit_len, dist_codes, dist_len, bits, nb);
+				W.put(bitpos, bits, nb);
+				bitpos += nb;
+			}
+			W.put(bitpos, lit_codes[256], lit_len[256]);
+			bitpos += lit_len[256];
+			if (bitpos - body0 != plan.body_bits) return 101; // planner and emitter disagree
+		}
+	}
+	if (flush_then_finish) {
+		// Deflater.Deflate FLUSHING_STATE (:486-504) then Finish: an empty final static block
+		int neededbits = 8 + (int)((0 - bitpos) & 7);
+		while (neededbits > 0) {
+			W.put(bitpos, 2, 10);
+			bitpos += 10;
+			neededbits -= 10;
+		}
+		W.put(bitpos, 3, 10);
+		bitpos += 10;
+	}
+	uint64_t nbytes = (bitpos + 7) >> 3;
+	if (nbytes > cap) return 102;
+	W.w.resize((nbytes + 3) / 4 + 1, 0);
+	std::memcpy(out, W.w.data(), nbytes);
+	*outlen = nbytes;
+	return 0;
+}
