@@ -1,0 +1,347 @@
+#!/usr/bin/env python
+"""bench.py -- DEFLATE level-6 compress + inflate throughput (GB/s of uncompressed bytes) on B200.
+
+One "step" = one pass of the hot path over one batch of synthetic input:
+    deflate leg : config C3 -- raw Deflater level 6 on 1024 x 256 KiB Silesia-mix buffers
+    inflate leg : config C2 -- raw Inflater on 256 x 1 MiB text buffers pre-deflated (level 6) by the oracle
+value = (uncompressed bytes of both legs) / (device time of both legs), inputs resident in HBM.
+e2e   = the same step through the public plan API from PINNED HOST buffers: H2D of the inputs, kernels, D2H of the
+        produced sizes and bytes, all inside the timed region.
+With --gpus N > 1 (torchrun, one rank per GPU) every rank runs the same shape on its own buffers (weak scaling), the
+static Huffman tables are broadcast once over NCCL, and rank 0 reports total units / max-over-ranks time.
+--impl reference times the CPU restatement of the reference (oracle/, all host threads) on a bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np  # noqa: E402
+
+METRIC = "DEFLATE level-6 compress + inflate GB/s (uncompressed) at 1/2/4/8 B200 vs C# ref"
+N_DEFLATE, SZ_DEFLATE = 1024, 262144      # C3
+N_INFLATE, SZ_INFLATE = 256, 1 << 20       # C2
+
+
+def _gen_deflate(i):
+    from sharpziplib_b200 import datagen
+    return datagen.silesia_mix(i, SZ_DEFLATE, config=3)
+
+
+def _gen_inflate(i):
+    from sharpziplib_b200 import datagen
+    return datagen.text_buffer(i, SZ_INFLATE, config=2)
+
+
+def make_inputs(rank, n_def, n_inf, workers):
+    """(list of deflate inputs, list of inflate originals) as numpy uint8 arrays; buffer indices are offset per rank"""
+    from concurrent.futures import ProcessPoolExecutor
+    di = [rank * N_DEFLATE + i for i in range(n_def)]
+    ii = [rank * N_INFLATE + i for i in range(n_inf)]
+    if workers > 1:
+        with ProcessPoolExecutor(max_workers=workers) as ex:
+            d = list(ex.map(_gen_deflate, di, chunksize=8))
+            t = list(ex.map(_gen_inflate, ii, chunksize=2))
+    else:
+        d = [_gen_deflate(i) for i in di]
+        t = [_gen_inflate(i) for i in ii]
+    return d, t
+
+
+class ClockSampler:
+    """samples nvidia-smi clocks / throttle reasons while the timed region runs (B200_PROFILING.md recipe)"""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows = []
+        self.proc = None
+        self.gpu = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        j = json.load(open(p))
+        return float(j["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def cpu_sample(threads, n_def, n_inf, d_inputs, comp_inf, inf_caps):
+    """times the oracle (C++ restatement of the reference) on a bounded sample of the same workload"""
+    import oracle_lib as O
+    dsel = [a.tobytes() for a in d_inputs[:n_def]]
+    t0 = time.perf_counter()
+    O.batch(0, dsel, level=6, threads=threads)
+    t1 = time.perf_counter()
+    O.batch(1, comp_inf[:n_inf], threads=threads, out_caps=[c + 64 for c in inf_caps[:n_inf]])
+    t2 = time.perf_counter()
+    ub = sum(len(b) for b in dsel) + sum(inf_caps[:n_inf])
+    return {"value": ub / (t2 - t0) / 1e9, "deflate_gbs": sum(len(b) for b in dsel) / (t1 - t0) / 1e9,
+            "inflate_gbs": sum(inf_caps[:n_inf]) / (t2 - t1) / 1e9, "seconds": t2 - t0}
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU algorithm (oracle port; no .NET on the box) on all host threads"""
+    if rank != 0:
+        return
+    import oracle_lib as O
+    O.build()
+    threads = os.cpu_count() or 1
+    # bounded sample: 1/4 of each leg's buffers per step (64 MiB deflate + 64 MiB inflate of the same generators)
+    n_def, n_inf = max(threads, N_DEFLATE // 4), max(min(threads, N_INFLATE), N_INFLATE // 4)
+    n_def, n_inf = min(n_def, N_DEFLATE), min(n_inf, N_INFLATE)
+    d, t = make_inputs(0, n_def, n_inf, min(threads, 32))
+    comp = O.batch(0, [a.tobytes() for a in t], level=6, threads=threads)
+    caps = [a.size for a in t]
+    for _ in range(args.warmup):
+        cpu_sample(threads, n_def, n_inf, d, comp, caps)
+    times, last = [], None
+    for _ in range(args.steps):
+        last = cpu_sample(threads, n_def, n_inf, d, comp, caps)
+        times.append(last["seconds"])
+    ub = n_def * SZ_DEFLATE + n_inf * SZ_INFLATE
+    val = ub * len(times) / sum(times) / 1e9
+    sample = "%d x 256 KiB deflate L6 + %d x 1 MiB inflate per step, %d threads" % (n_def, n_inf, threads)
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "GB/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1000 * sum(times) / len(times), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": "C3 deflate L6 1024x256KiB + C2 inflate 256x1MiB (bounded CPU sample)", "sample": sample},
+            "cpu_baseline": {"value": val, "unit": "GB/s", "cores": threads, "kind": "port", "sample": sample,
+                             "note": "C++ restatement of SharpZipLib's managed path; no .NET runtime on the box"},
+            "e2e": {"value": val, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "deflate_gbs": last["deflate_gbs"], "inflate_gbs": last["inflate_gbs"], "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200z", choices=["b200z", "reference"])
+    ap.add_argument("--small", action="store_true", help="1/8 size workload for quick checks (not a bench value)")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import oracle_lib as O
+    import sharpziplib_b200 as z
+    from sharpziplib_b200.sharding import broadcast_static_tables
+    torch.cuda.set_device(local_rank)
+    z.init(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local_rank))
+        broadcast_static_tables(dist, device=torch.device("cuda", local_rank))  # the path's only collective
+    n_def = N_DEFLATE // (8 if args.small else 1)
+    n_inf = N_INFLATE // (8 if args.small else 1)
+    ncpu = os.cpu_count() or 1
+    workers = max(1, min(32, ncpu // max(1, world)))
+    t_setup = time.time()
+    d_np, t_np = make_inputs(rank, n_def, n_inf, workers)
+    O.build()
+    comp = O.batch(0, [a.tobytes() for a in t_np], level=6, threads=max(1, ncpu // max(1, world)))
+    setup_s = time.time() - t_setup
+
+    # ---- plans and resident device buffers ---------------------------------------------------------------
+    dplan = z.DeflatePlan([a.size for a in d_np], level=6)
+    iplan = z.InflatePlan([len(c) for c in comp], [a.size for a in t_np])
+    h_din = torch.zeros(dplan.in_bytes, dtype=torch.uint8).pin_memory()
+    for o, a in zip(dplan.in_offsets, d_np):
+        h_din[o:o + a.size] = torch.from_numpy(a)
+    h_iin = torch.zeros(iplan.in_bytes, dtype=torch.uint8).pin_memory()
+    for o, c in zip(iplan.in_offsets, comp):
+        h_iin[o:o + len(c)] = torch.frombuffer(bytearray(c), dtype=torch.uint8)
+    dev = torch.device("cuda", local_rank)
+    d_din = h_din.to(dev)
+    d_iin = h_iin.to(dev)
+    d_dout = torch.empty(dplan.out_bytes, dtype=torch.uint8, device=dev)
+    d_iout = torch.empty(iplan.out_bytes, dtype=torch.uint8, device=dev)
+    d_dlen = torch.zeros(n_def, dtype=torch.int64, device=dev)
+    d_dst = torch.zeros(n_def, dtype=torch.int32, device=dev)
+    d_ilen = torch.zeros(n_inf, dtype=torch.int64, device=dev)
+    d_ist = torch.zeros(n_inf, dtype=torch.int32, device=dev)
+    d_iused = torch.zeros(n_inf, dtype=torch.int64, device=dev)
+    h_dout = torch.empty(dplan.out_bytes, dtype=torch.uint8).pin_memory()
+    h_iout = torch.empty(iplan.out_bytes, dtype=torch.uint8).pin_memory()
+    h_dlen = torch.zeros(n_def, dtype=torch.int64).pin_memory()
+    h_ilen = torch.zeros(n_inf, dtype=torch.int64).pin_memory()
+    U_def = sum(a.size for a in d_np)
+    U_inf = sum(a.size for a in t_np)
+    C_inf = sum(len(c) for c in comp)
+
+    def step_resident():
+        dplan.run(d_din, d_dout, d_dlen, d_dst)
+        iplan.run(d_iin, d_iout, d_ilen, d_ist, None, d_iused)
+
+    def step_e2e():
+        d_din.copy_(h_din, non_blocking=True)
+        d_iin.copy_(h_iin, non_blocking=True)
+        dplan.run(d_din, d_dout, d_dlen, d_dst)
+        iplan.run(d_iin, d_iout, d_ilen, d_ist, None, d_iused)
+        h_dlen.copy_(d_dlen, non_blocking=True)
+        h_ilen.copy_(d_ilen, non_blocking=True)
+        h_dout.copy_(d_dout, non_blocking=True)
+        h_iout.copy_(d_iout, non_blocking=True)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        barrier()
+        return ms
+
+    for _ in range(max(3, args.warmup)):
+        step_resident()
+    torch.cuda.synchronize()
+    # ---- parity of what is being timed (not in the timed region) -------------------------------------------
+    C_def = int(d_dlen.sum().item())
+    assert int((d_dst != 0).sum().item()) == 0 and int((d_ist != 0).sum().item()) == 0, "device status != OK"
+    lens = d_dlen.cpu().numpy()
+    outb = d_dout.cpu().numpy()
+    for i in range(0, n_def, max(1, n_def // 16)):
+        ref = O.deflate(d_np[i].tobytes(), level=6)
+        got = outb[dplan.out_offsets[i]:dplan.out_offsets[i] + lens[i]].tobytes()
+        assert got == ref, "deflate parity failed for buffer %d" % i
+    io = d_iout.cpu().numpy()
+    for i in range(0, n_inf, max(1, n_inf // 16)):
+        assert np.array_equal(io[iplan.out_offsets[i]:iplan.out_offsets[i] + t_np[i].size], t_np[i]), "inflate mismatch %d" % i
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms_total = timed(step_resident, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_step = ms_total / args.steps
+    units = (U_def + U_inf) * world
+    value = units / (ms_step / 1e3) / 1e9
+
+    # ---- per-kernel device times for the roofline (separate steps, events between kernels) -------------------
+    dplan.set_timing(True)
+    iplan.set_timing(True)
+    acc = {}
+    reps = max(3, min(args.steps, 5))
+    for _ in range(reps):
+        step_resident()
+        torch.cuda.synchronize()
+        for k, v in list(dplan.timings().items()) + list(iplan.timings().items()):
+            acc[k] = acc.get(k, 0.0) + v / reps
+    dplan.set_timing(False)
+    iplan.set_timing(False)
+    t_def = sum(v for k, v in acc.items() if k != "k_inflate")
+    t_inf = acc.get("k_inflate", 0.0)
+    dom = max(acc, key=acc.get)
+    peak, peak_src = peaks()
+    alg_bytes = (C_inf + U_inf) if dom == "k_inflate" else (U_def + C_def)
+    achieved = alg_bytes / (acc[dom] / 1e3) / 1e9
+
+    # ---- end to end from pinned host buffers ------------------------------------------------------------------
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed(step_e2e, max(3, args.steps // 2)) / max(3, args.steps // 2)
+    e2e_val = units / (ms_e2e / 1e3) / 1e9
+
+    # ---- CPU baseline: the oracle on one host core, bounded sample ----------------------------------------------
+    cpu = None
+    if rank == 0:
+        ns_d, ns_i = min(n_def, 128), min(n_inf, 64)
+        r = cpu_sample(1, ns_d, ns_i, d_np, comp, [a.size for a in t_np])
+        cpu = {"value": r["value"], "unit": "GB/s", "cores": 1, "kind": "port",
+               "sample": "%d x 256 KiB deflate L6 + %d x 1 MiB inflate, single thread, %.1f s" % (ns_d, ns_i, r["seconds"]),
+               "deflate_gbs": r["deflate_gbs"], "inflate_gbs": r["inflate_gbs"], "host_cores": ncpu,
+               "note": "C++ restatement of SharpZipLib's managed path (oracle/); no .NET runtime on the box"}
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+            "data": "synthetic",
+            "config": {"workload": "C3 deflate L6 %dx256KiB + C2 inflate %dx1MiB per GPU" % (n_def, n_inf),
+                       "l2": "inputs (256 MiB + 64 MiB compressed per leg) exceed the 126 MB L2; no flush needed",
+                       "parity": "deflate bytes == oracle and inflate bytes == original, checked on 16 buffers each before timing",
+                       "ratio_deflate": U_def / max(1, C_def), "ratio_inflate": U_inf / max(1, C_inf), "setup_s": setup_s},
+            "deflate_gbs": U_def / (t_def / 1e3) / 1e9 if t_def else None,
+            "inflate_gbs": U_inf / (t_inf / 1e3) / 1e9 if t_inf else None,
+            "kernels_ms": acc,
+            "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes": alg_bytes},
+            "cpu_baseline": cpu,
+            "e2e": {"value": e2e_val, "unit": "GB/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": int(dplan.in_bytes + iplan.in_bytes),
+                    "d2h_bytes_per_step": int(dplan.out_bytes + iplan.out_bytes + 8 * (n_def + n_inf))},
+            "gpu_launches": int(dplan.launches + iplan.launches),
+            "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

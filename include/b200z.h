@@ -82,6 +82,11 @@ int64_t b200z_plan_out_capacity(const b200z_plan *plan, int32_t i);
 int64_t b200z_plan_workspace_bytes(const b200z_plan *plan);
 /* kernels launched by one run() (for the benchmark's gpu_launches accounting) */
 int32_t b200z_plan_launches(const b200z_plan *plan);
+/* Per-kernel device times: when enabled, run() records CUDA events on its stream between kernels; after the stream
+ * has been synchronised get_timings() returns the milliseconds of each interval of the last run and a ';'-separated
+ * list of kernel names.  Measurement aid for bench.py's roofline line; off by default. */
+int b200z_plan_set_timing(b200z_plan *plan, int enable);
+int b200z_plan_get_timings(b200z_plan *plan, char *names, int32_t names_cap, float *ms, int32_t cap, int32_t *count);
 /* d_in / d_out: device blobs laid out as the plan reports.  d_out_len[n] (int64), d_status[n] (int32, b200z_status)
  * and d_check[n] (uint32: Adler32 for zlib, CRC32 for gzip, untouched for raw; may be NULL for raw) are device
  * arrays.  For inflate plans d_in_used[n] (int64, may be NULL) receives the compressed bytes consumed, i.e.

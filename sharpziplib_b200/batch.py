@@ -28,6 +28,18 @@ class _Plan:
 
     __del__ = close
 
+    def set_timing(self, enable=True):
+        _lib.raise_for(_lib.lib().b200z_plan_set_timing(self._h, 1 if enable else 0))
+
+    def timings(self):
+        """{kernel name: milliseconds} of the last run (call after synchronising the stream)."""
+        names = C.create_string_buffer(1024)
+        ms = (C.c_float * 32)()
+        cnt = C.c_int32(0)
+        _lib.raise_for(_lib.lib().b200z_plan_get_timings(self._h, names, 1024, ms, 32, C.byref(cnt)))
+        keys = names.value.decode().split(";")[:cnt.value]
+        return {k: float(ms[i]) for i, k in enumerate(keys)}
+
     def run(self, d_in, d_out, d_out_len, d_status, d_check=None, d_in_used=None, stream=None):
         """All arguments are CUDA torch tensors (uint8 blobs, int64 lengths, int32 status, uint32/int32 checks).
         Launches on `stream` (a torch.cuda.Stream) or the current stream; does not synchronise."""

@@ -305,8 +305,36 @@ int b200z_inflate_plan_create(int32_t n, const int64_t *comp_len, const int64_t 
 	return B200Z_OK;
 }
 
+int b200z_plan_set_timing(b200z_plan *plan, int enable) {
+	if (!plan) return B200Z_E_ARG;
+	plan->timing = enable != 0;
+	plan->ev_used = 0;
+	return B200Z_OK;
+}
+
+int b200z_plan_get_timings(b200z_plan *plan, char *names, int32_t names_cap, float *ms, int32_t cap, int32_t *count) {
+	if (!plan || !ms || !count) return B200Z_E_ARG;
+	*count = 0;
+	std::string nm;
+	for (int i = 0; i + 1 < plan->ev_used && *count < cap; i++) {
+		float t = 0;
+		cudaError_t e = cudaEventElapsedTime(&t, plan->ev[i], plan->ev[i + 1]);
+		if (e != cudaSuccess) return cuda_fail(e, "cudaEventElapsedTime", __FILE__, __LINE__);
+		ms[*count] = t;
+		nm += plan->ev_name[i];
+		nm += ";";
+		++*count;
+	}
+	if (names && names_cap > 0) {
+		strncpy(names, nm.c_str(), (size_t)names_cap - 1);
+		names[names_cap - 1] = 0;
+	}
+	return B200Z_OK;
+}
+
 int b200z_plan_destroy(b200z_plan *plan) {
 	if (!plan) return B200Z_OK;
+	for (cudaEvent_t e : plan->ev) cudaEventDestroy(e);
 	plan->ws.release();
 	delete plan;
 	return B200Z_OK;

@@ -552,24 +552,34 @@ int deflate_plan_run(b200z_plan *p, const uint8_t *d_in, uint8_t *d_out, int64_t
 	BlockMeta *meta = ws.at<BlockMeta>(p->o_meta);
 	BlockTables *tables = ws.at<BlockTables>(p->o_tables);
 
+	p->ev_used = 0;
+	p->mark(s, "memset");
 	B200Z_CUDA(cudaMemsetAsync(d_out, 0, (size_t)p->out_bytes, s));
+	p->mark(s, "k_links");
 	if (p->n_runs) k_links<<<p->n_runs, 32, 65536, s>>>(d_in, link, in_off, in_len, ws.at<int2>(p->o_run_desc));
+	p->mark(s, "k_match");
 	if (p->n_tiles)
 		k_match<<<p->n_tiles, kMatchThreads, kTileData + 2 * 2 * kTile, s>>>(d_in, link, mt, in_off, in_len,
 		                                                                   ws.at<int2>(p->o_tile_desc), lp);
+	p->mark(s, "k_parse");
 	k_parse<<<(n + kParseWarps - 1) / kParseWarps, kParseWarps * 32, 0, s>>>(d_in, link, mt, sym, in_off, in_len, n, nsyms,
 	                                                                        nblocks, blk_off, blk_start, blk_ptop, lp,
 	                                                                        p->strategy, p->end_mode);
+	p->mark(s, "k_plan");
 	k_plan<<<p->n_blkmax, 256, 0, s>>>(sym, in_off, in_len, nsyms, nblocks, blk_off, blk_desc, blk_start, blk_ptop, meta,
 	                                   tables, p->end_mode);
+	p->mark(s, "k_scan");
 	k_scan<<<(n + 127) / 128, 128, 0, s>>>(n, nblocks, blk_off, meta, d_out, out_off, out_cap, d_out_len, d_status,
 	                                       d_out_bits, p->end_mode);
+	p->mark(s, "k_emit");
 	k_emit<<<p->n_blkmax, 256, 0, s>>>(d_in, sym, d_out, in_off, out_off, nblocks, blk_off, blk_desc, meta, tables);
+	p->mark(s, "checksum");
 	if (p->wrap != B200Z_WRAP_RAW && d_check) {
 		int rc = checksum_launch(p->wrap == B200Z_WRAP_GZIP ? 0 : 1, d_in, in_off, in_len, n, ws.at<CkTile>(p->o_ck_desc),
 		                         p->n_ck_tiles, ws.at<unsigned long long>(p->o_ck_acc), d_check, 1, s);
 		if (rc) return rc;
 	}
+	p->mark(s, "end");
 	B200Z_CUDA(cudaGetLastError());
 	return B200Z_OK;
 }

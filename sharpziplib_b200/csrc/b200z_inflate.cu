@@ -289,6 +289,8 @@ __global__ void __launch_bounds__(kInfWarps * 32)
 				}
 			}
 		}
+		// an error diagnosed from bits past the end of the input is "needs more input", not corrupt data
+		if (lane == 0 && st != B200Z_OK && br.overrun()) { st = B200Z_E_NEED_INPUT; detail = 0; }
 		done = __shfl_sync(0xffffffffu, (int)done, 0) != 0;
 		st = __shfl_sync(0xffffffffu, st, 0);
 		if (done || st != B200Z_OK) break;
@@ -376,7 +378,7 @@ __global__ void __launch_bounds__(kInfWarps * 32)
 					detail = k == K_ILLEGAL ? D_REP_LEN : D_CODELEN0;
 					break;
 				}
-				if (st == B200Z_OK && br.overrun()) st = B200Z_E_NEED_INPUT;
+				if (br.overrun() && st != B200Z_E_NOMEM) { st = B200Z_E_NEED_INPUT; detail = 0; }
 			}
 			ntok = __shfl_sync(0xffffffffu, ntok, 0);
 			in_block = __shfl_sync(0xffffffffu, (int)in_block, 0) != 0;
@@ -480,9 +482,12 @@ int inflate_plan_run(b200z_plan *p, const uint8_t *d_in, uint8_t *d_out, int64_t
 	const int n = p->n;
 	if (n == 0) return B200Z_OK;
 	(void)d_check;
+	p->ev_used = 0;
+	p->mark(s, "k_inflate");
 	k_inflate<<<(n + kInfWarps - 1) / kInfWarps, kInfWarps * 32, 0, s>>>(
 	    d_in, d_out, ws.at<int64_t>(p->o_in_off), ws.at<int64_t>(p->o_in_len), ws.at<int64_t>(p->o_out_off),
 	    ws.at<int64_t>(p->o_out_cap), n, d_out_len, d_in_used, d_status);
+	p->mark(s, "end");
 	B200Z_CUDA(cudaGetLastError());
 	return B200Z_OK;
 }

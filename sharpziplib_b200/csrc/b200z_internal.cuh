@@ -86,6 +86,23 @@ struct b200z_plan {
 	// checksum scratch
 	int64_t o_ck_desc = 0, o_ck_acc = 0;
 	int n_ck_tiles = 0;
+	// optional per-kernel timing (b200z_plan_set_timing): events recorded on the run's stream between kernels
+	bool timing = false;
+	std::vector<cudaEvent_t> ev;
+	std::vector<const char *> ev_name; // ev_name[i] labels the interval ev[i] -> ev[i+1]
+	int ev_used = 0;
+	void mark(cudaStream_t s, const char *next_name) {
+		if (!timing) return;
+		if ((int)ev.size() <= ev_used) {
+			cudaEvent_t e;
+			cudaEventCreate(&e);
+			ev.push_back(e);
+			ev_name.push_back("");
+		}
+		cudaEventRecord(ev[ev_used], s);
+		ev_name[ev_used] = next_name;
+		++ev_used;
+	}
 };
 
 namespace b200z {

@@ -1,0 +1,349 @@
+"""GPU tier (run with -m gpu on the B200 box): every CUDA path against the oracle, through the C-ABI."""
+import io
+import json
+import os
+import zlib
+
+import numpy as np
+import pytest
+
+from helpers import corpus_small, crafted_t8
+
+pytestmark = pytest.mark.gpu
+GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_fixtures.json")))
+
+
+def test_native_library_is_loaded(z):
+    z.deflate_batch([b"abcabcabc"], level=6)
+    maps = open("/proc/self/maps").read()
+    assert "libb200z.so" in maps
+
+
+# ---- checksums -------------------------------------------------------------------------------------------
+def test_checksum_kats(z):
+    for k in GOLD["checksum_kats"]["crc32"]:
+        c = z.Crc32()
+        c.Update(k["ascii"].encode())
+        assert c.Value == k["value"]
+    a = z.Adler32()
+    assert a.Value == 1
+    a.Update(b"123456789")
+    assert a.Value == 0x091E01DE
+    a.Reset()
+    assert a.Value == 1
+    c = z.Crc32()
+    c.Update(b"123456789" * 4, 6, 18)  # unaligned slice (ChecksumTests.cs:139-146)
+    assert c.Value == 0x31CA9A2E
+
+
+def test_checksum_sizes_and_running_updates(z, oracle):
+    from sharpziplib_b200 import datagen
+    for n in (1, 3, 127, 128, 129, 4095, 32767, 32768, 32769, 65537, 1000003, 5 << 20):
+        d = datagen.Rng(n).bytes(n).tobytes()
+        c = z.Crc32()
+        c.Update(d)
+        a = z.Adler32()
+        a.Update(d)
+        assert c.Value == oracle.crc32(d) == zlib.crc32(d), n
+        assert a.Value == oracle.adler32(d) == zlib.adler32(d), n
+        c2 = z.Crc32()
+        a2 = z.Adler32()
+        for lo, hi in ((0, n // 3), (n // 3, n // 3 + 1), (n // 3 + 1, n)):
+            c2.Update(d[lo:hi])
+            a2.Update(d[lo:hi])
+        assert c2.Value == c.Value and a2.Value == a.Value
+    c = z.Crc32()
+    for b in b"123456789":
+        c.Update(b)  # Update(int)
+    assert c.Value == 0xCBF43926
+
+
+def test_checksum_batch_device(z, oracle):
+    import torch
+    from sharpziplib_b200 import datagen
+    bufs = [datagen.silesia_mix(i, 1000 + 37000 * i).tobytes() for i in range(9)]
+    off = np.zeros(len(bufs), dtype=np.int64)
+    lens = np.array([len(b) for b in bufs], dtype=np.int64)
+    off[1:] = np.cumsum(lens + 3)[:-1]  # deliberately unaligned offsets
+    blob = np.zeros(int(off[-1] + lens[-1]), dtype=np.uint8)
+    for o, b in zip(off, bufs):
+        blob[o:o + len(b)] = np.frombuffer(b, dtype=np.uint8)
+    d = torch.from_numpy(blob).cuda()
+    for kind, ref, init in ((0, oracle.crc32, 0), (1, oracle.adler32, 1)):
+        val = torch.full((len(bufs),), init, dtype=torch.int64).to(torch.uint32).cuda() if hasattr(torch, "uint32") else None
+        v = torch.from_numpy(np.full(len(bufs), init, dtype=np.uint32).view(np.int32)).cuda()
+        rc = z.lib().b200z_checksum_batch_device(kind, d.data_ptr(), off.ctypes.data, lens.ctypes.data, len(bufs),
+                                                v.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        assert rc == 0, z.lib().b200z_last_error()
+        torch.cuda.synchronize()
+        got = v.cpu().numpy().view(np.uint32)
+        assert [int(x) for x in got] == [ref(b) for b in bufs]
+
+
+# ---- deflate ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("level", [5, 6, 7, 8, 9])
+def test_deflate_parity_small_corpus(z, oracle, level):
+    names, bufs = zip(*corpus_small())
+    outs, _ = z.deflate_batch(list(bufs), level=level)
+    for name, d, o in zip(names, bufs, outs):
+        assert o == oracle.deflate(d, level=level), (name, level)
+
+
+def test_deflate_default_level_is_6(z, oracle):
+    d = corpus_small()[20][1]
+    assert z.deflate_batch([d], level=-1)[0][0] == oracle.deflate(d, level=6)
+
+
+@pytest.mark.parametrize("strategy", [1, 2])
+def test_deflate_strategies(z, oracle, strategy):
+    items = [(n, d) for n, d in corpus_small() if len(d) in (1000, 20000, 70000)]
+    outs, _ = z.deflate_batch([d for _, d in items], level=6, strategy=strategy)
+    for (name, d), o in zip(items, outs):
+        assert o == oracle.deflate(d, level=6, strategy=strategy), (name, strategy)
+
+
+def test_deflate_flush_then_finish_pattern(z, oracle):
+    # Write(all) -> Flush() -> Finish(): the reference's own round-trip pattern (InflaterDeflaterTests.cs:49-62)
+    items = [(n, d) for n, d in corpus_small() if len(d) in (0, 1, 100, 4096, 70000)]
+    outs, _ = z.deflate_batch([d for _, d in items], level=6, end_mode=1)
+    for (name, d), o in zip(items, outs):
+        assert o == oracle.deflate(d, level=6, pattern=1), name
+        assert zlib.decompress(o, -15) == d
+
+
+def test_deflate_zlib_wrapper(z, oracle):
+    items = [d for _, d in corpus_small() if len(d) in (0, 10, 4096, 70000)]
+    for level in (5, 6, 7, 9):
+        outs, checks = z.deflate_batch(items, level=level, wrap=1)
+        for d, o, c in zip(items, outs, checks):
+            assert o == oracle.deflate(d, level=level, nowrap=False), level
+            assert int(c) == zlib.adler32(d)
+
+
+def test_deflate_window_slides_and_t8(z, oracle):
+    from sharpziplib_b200 import datagen
+    bufs = [crafted_t8(), crafted_t8(40000)]
+    bufs += [datagen.silesia_mix(c, 600000 + 12345 * c, config=7).tobytes() for c in (0, 3, 4, 6)]
+    bufs += [bytes(200000), b"abcdefgh" * 40000]
+    outs, _ = z.deflate_batch(bufs, level=6)
+    for d, o in zip(bufs, outs):
+        assert o == oracle.deflate(d, level=6)
+
+
+def test_deflate_c3_shape_parity_and_properties(z, oracle):
+    """64 buffers of the C3 shape (256 KiB Silesia-mix): bit-exact vs the oracle, valid deflate, round trip."""
+    from sharpziplib_b200 import datagen
+    bufs = [datagen.silesia_mix(i, 262144).tobytes() for i in range(64)]
+    outs, _ = z.deflate_batch(bufs, level=6)
+    refs = oracle.batch(0, bufs, level=6, threads=8)
+    assert outs == refs
+    back, used, status = z.inflate_batch(outs, [len(b) for b in bufs])
+    assert back == bufs and [int(u) for u in used] == [len(o) for o in outs]
+
+
+def test_unsupported_levels_fail_loudly(z):
+    with pytest.raises(z.B200zUnsupported):
+        z.deflate_batch([b"hello"], level=1)
+    with pytest.raises(z.B200zUnsupported):
+        z.deflate_batch([b"hello"], level=0)
+
+
+# ---- inflate ---------------------------------------------------------------------------------------------
+def test_inflate_reference_fixtures(z):
+    raw = bytes.fromhex(GOLD["inflate_ok"]["raw_hex"])
+    out, used, st = z.inflate_batch([raw], [64])
+    assert out[0] == b"testfile contents\n" and int(used[0]) == 20 and int(st[0]) == 0
+    bad = bytes.fromhex(GOLD["inflate_zero_codelength"]["raw_hex"])
+    out, used, st = z.inflate_batch([bad], [1 << 16], raise_on_error=False)
+    assert int(st[0]) & 0xFF == 3 and (int(st[0]) >> 8) == 5  # E_DATA / "Encountered invalid codelength 0"
+    with pytest.raises(z.SharpZipBaseException):
+        z.inflate_batch([bad], [1 << 16])
+
+
+def test_inflate_all_oracle_levels_and_zlib_streams(z, oracle):
+    items = [d for _, d in corpus_small() if len(d) >= 100]
+    for level in range(10):
+        comp = [oracle.deflate(d, level=level) for d in items]  # stored (0), fast (1-4), lazy (5-9) producers
+        out, used, st = z.inflate_batch(comp, [len(d) for d in items])
+        assert out == items and [int(u) for u in used] == [len(c) for c in comp]
+    for level in (1, 6, 9):
+        comp = []
+        for d in items:
+            co = zlib.compressobj(level, zlib.DEFLATED, -15)
+            comp.append(co.compress(d) + co.flush())
+        out, used, st = z.inflate_batch(comp, [len(d) for d in items])
+        assert out == items
+    # sync-flush streams: empty static blocks in the middle (trap T6)
+    comp = [oracle.deflate(d, level=6, pattern=1) for d in items]
+    out, _, _ = z.inflate_batch(comp, [len(d) for d in items])
+    assert out == items
+
+
+def test_inflate_remaining_input_and_truncation(z, oracle):
+    d = corpus_small()[30][1]
+    c = oracle.deflate(d, level=6)
+    out, used, st = z.inflate_batch([c + b"\x01\x02\x03TRAILER"], [len(d)])
+    assert out[0] == d and int(used[0]) == len(c)  # trap T14: RemainingInput counts everything after the last EOB byte
+    for cut in (1, len(c) // 2, len(c) - 1):
+        out, used, st = z.inflate_batch([c[:cut]], [len(d)], raise_on_error=False)
+        assert int(st[0]) & 0xFF == 8  # needs input, not a data error
+        assert d.startswith(out[0])
+    out, used, st = z.inflate_batch([c], [len(d) - 1], raise_on_error=False)
+    assert int(st[0]) & 0xFF == 7  # capacity
+
+
+def test_inflate_error_cases(z):
+    # reserved block type 3; stored block with bad NLEN; distance code 30
+    cases = {bytes([0x07, 0x00]): 1, bytes([0x01, 0x05, 0x00, 0x00, 0x00]): 2}
+    for raw, detail in cases.items():
+        out, used, st = z.inflate_batch([raw], [1024], raise_on_error=False)
+        assert int(st[0]) & 0xFF == 3 and (int(st[0]) >> 8) == detail, (raw.hex(), st)
+
+
+def test_inflate_c2_shape(z, oracle):
+    from sharpziplib_b200 import datagen
+    bufs = [datagen.text_buffer(i, 1 << 20).tobytes() for i in range(8)]
+    comp = oracle.batch(0, bufs, level=6, threads=8)
+    out, used, st = z.inflate_batch(comp, [len(b) for b in bufs])
+    assert out == bufs
+
+
+# ---- device plans (the benchmark's path) -------------------------------------------------------------------
+def test_plans_on_device_tensors(z, oracle):
+    import torch
+    from sharpziplib_b200 import datagen
+    bufs = [datagen.silesia_mix(i, 50000 + 3000 * i).tobytes() for i in range(16)]
+    plan = z.DeflatePlan([len(b) for b in bufs], level=6)
+    host = np.zeros(plan.in_bytes, dtype=np.uint8)
+    for o, b in zip(plan.in_offsets, bufs):
+        host[o:o + len(b)] = np.frombuffer(b, dtype=np.uint8)
+    d_in = torch.from_numpy(host).cuda()
+    d_out = torch.empty(plan.out_bytes, dtype=torch.uint8, device="cuda")
+    d_len = torch.zeros(len(bufs), dtype=torch.int64, device="cuda")
+    d_st = torch.zeros(len(bufs), dtype=torch.int32, device="cuda")
+    plan.run(d_in, d_out, d_len, d_st)
+    plan.run(d_in, d_out, d_len, d_st)  # idempotent
+    torch.cuda.synchronize()
+    lens = d_len.cpu().numpy()
+    out = d_out.cpu().numpy()
+    comp = [out[o:o + l].tobytes() for o, l in zip(plan.out_offsets, lens)]
+    assert comp == [oracle.deflate(b, level=6) for b in bufs]
+    assert plan.launches >= 6
+    ip = z.InflatePlan([len(c) for c in comp], [len(b) for b in bufs])
+    hin = np.zeros(ip.in_bytes, dtype=np.uint8)
+    for o, c in zip(ip.in_offsets, comp):
+        hin[o:o + len(c)] = np.frombuffer(c, dtype=np.uint8)
+    di = torch.from_numpy(hin).cuda()
+    do = torch.empty(ip.out_bytes, dtype=torch.uint8, device="cuda")
+    dl = torch.zeros(len(bufs), dtype=torch.int64, device="cuda")
+    ds = torch.zeros(len(bufs), dtype=torch.int32, device="cuda")
+    du = torch.zeros(len(bufs), dtype=torch.int64, device="cuda")
+    ip.run(di, do, dl, ds, None, du)
+    torch.cuda.synchronize()
+    o2 = do.cpu().numpy()
+    assert [o2[o:o + l].tobytes() for o, l in zip(ip.out_offsets, dl.cpu().numpy())] == bufs
+    assert ds.cpu().numpy().tolist() == [0] * len(bufs)
+
+
+# ---- streaming handles and stream adapters (the reference's own test shapes) ------------------------------
+@pytest.mark.parametrize("level", [5, 6, 9])
+@pytest.mark.parametrize("zlib_wrap", [True, False])
+def test_inflate_deflate_roundtrip_like_reference(z, oracle, level, zlib_wrap):
+    """InflaterDeflaterTests.InflateDeflateZlib / NonZlib (:157-162, :226-231): 100000 random bytes,
+    Write(all) -> Flush() -> Finish(), read back through InflaterInputStream."""
+    from sharpziplib_b200 import datagen
+    original = datagen.Rng(5).bytes(100000).tobytes()
+    ms = io.BytesIO()
+    out = z.DeflaterOutputStream(ms, z.Deflater(level, not zlib_wrap))
+    out.IsStreamOwner = False
+    out.Write(original)
+    out.Flush()
+    out.Finish()
+    comp = ms.getvalue()
+    assert comp == oracle.deflate(original, level=level, nowrap=not zlib_wrap, pattern=1)
+    ins = z.InflaterInputStream(io.BytesIO(comp), z.Inflater(not zlib_wrap))
+    assert ins.read() == original
+
+
+def test_deflater_handle_members(z, oracle):
+    d = corpus_small()[40][1]
+    df = z.Deflater(6, True)
+    assert df.IsNeedingInput and not df.IsFinished and df.GetLevel() == 6
+    df.SetInput(d[:1000])
+    buf = bytearray(512)
+    assert df.Deflate(buf) == 0 and df.IsNeedingInput  # "need more input" is the normal answer (Deflater.cs:480-484)
+    df.SetInput(d[1000:])
+    df.Finish()
+    out = b""
+    while not df.IsFinished:
+        n = df.Deflate(buf)
+        assert n > 0
+        out += bytes(buf[:n])
+    assert out == oracle.deflate(d, level=6)
+    assert df.TotalIn == len(d) and df.TotalOut == len(out)
+    df.Reset()
+    df.SetLevel(9)
+    df.SetInput(d)
+    df.Finish()
+    out = b""
+    while not df.IsFinished:
+        n = df.Deflate(buf)
+        out += bytes(buf[:n])
+    assert out == oracle.deflate(d, level=9)
+    with pytest.raises(z.B200zUnsupported):
+        df2 = z.Deflater(1, True)
+        df2.SetInput(b"abc")
+        df2.Finish()
+        df2.Deflate(buf)
+
+
+def test_inflater_handle_members(z, oracle):
+    d = corpus_small()[41][1]
+    c = oracle.deflate(d, level=6, nowrap=False)
+    inf = z.Inflater(False)
+    assert inf.IsNeedingInput
+    inf.SetInput(c[:100])
+    buf = bytearray(1 << 16)
+    got = b""
+    n = inf.Inflate(buf)
+    got += bytes(buf[:n])
+    assert inf.IsNeedingInput and not inf.IsFinished
+    inf.SetInput(c[100:] + b"EXTRA")
+    while not inf.IsFinished:
+        n = inf.Inflate(buf)
+        if n == 0:
+            break
+        got += bytes(buf[:n])
+    assert got == d and inf.IsFinished
+    assert inf.RemainingInput == 5 and inf.TotalIn == len(c) and inf.TotalOut == len(d)
+    assert inf.Adler == zlib.adler32(d)
+    bad = bytearray(c)
+    bad[-1] ^= 0xFF
+    inf.Reset()
+    inf.SetInput(bytes(bad))
+    with pytest.raises(z.SharpZipBaseException):
+        while True:
+            if inf.Inflate(buf) == 0:
+                break
+    inf2 = z.Inflater(False)
+    inf2.SetInput(b"\x79\x9c\x03\x00")
+    with pytest.raises(z.SharpZipBaseException):
+        inf2.Inflate(buf)  # "Header checksum illegal"
+
+
+def test_gzip_streams(z):
+    import gzip
+    from sharpziplib_b200 import datagen
+    d = datagen.gen_log(300000, 11).tobytes()
+    ms = io.BytesIO()
+    g = z.GZipOutputStream(ms)
+    g.IsStreamOwner = False
+    g.ModifiedTime = 1577836800
+    for i in range(0, len(d), 65536):
+        g.Write(d[i:i + 65536])
+    g.Finish()
+    blob = ms.getvalue()
+    assert blob[:10] == bytes([0x1F, 0x8B, 8, 0, 0x00, 0xE1, 0x0B, 0x5E, 0, 255])  # trap T15: XFL 0, OS 255
+    assert gzip.decompress(blob) == d
+    assert z.GZipInputStream(io.BytesIO(blob)).read() == d
+    assert z.GZipInputStream(io.BytesIO(blob + blob)).read() == d + d  # multi-member
