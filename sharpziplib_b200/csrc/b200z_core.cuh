@@ -240,6 +240,39 @@ B200Z_HD int parse_step(ParseState &st, uint32_t n, const LevelParams &lp, int s
 	return emitted;
 }
 
+// A parse position with everything the next loop top depends on, plus the last loop top processed (needed for the
+// window-slide count at block flush time, slides_done()).
+struct ParseCarry {
+	ParseState st;
+	uint32_t last_top;
+};
+B200Z_HD bool carry_equal(const ParseCarry &a, const ParseCarry &b) {
+	return a.st.p == b.st.p && a.st.mlen == b.st.mlen && a.st.mstart == b.st.mstart && a.st.prevAvail == b.st.prevAvail &&
+	       a.last_top == b.last_top;
+}
+
+// Runs the loop tops in [c.st.p, seg_end) (clipped to n).  Returns the number of symbols tallied.  With EMIT, calls
+// emit(k, sym, loop_top, bytes_after) for the k-th symbol of this run, bytes_after = input bytes covered by all
+// symbols up to and including this one (what blockStart advances to when the block is cut here).
+// The lazy parse is self-synchronising: started from a wrong state it normally falls in step with the true parse
+// after a few symbols, which is what k_parse exploits (speculative segments + entry propagation until stable).
+template <bool EMIT, class TabFn, class DataFn, class SlowFn, class EmitFn>
+B200Z_HD uint32_t parse_run(ParseCarry &c, uint32_t seg_end, uint32_t n, const LevelParams &lp, int strategy, TabFn tab,
+                            DataFn byte_at, SlowFn slow_search, EmitFn emit) {
+	const uint32_t lim = seg_end < n ? seg_end : n;
+	uint32_t cnt = 0;
+	while (c.st.p < lim) {
+		const uint32_t top = c.st.p;
+		c.last_top = top;
+		uint32_t sym = 0;
+		if (parse_step(c.st, n, lp, strategy, tab, byte_at, slow_search, sym)) {
+			if (EMIT) emit(cnt, sym, top, sym_dist(sym) ? top - 1 + sym_len(sym) : top);
+			++cnt;
+		}
+	}
+	return cnt;
+}
+
 // ---- DeflaterHuffman.cs helpers ----------------------------------------------------------------
 B200Z_HD int lcode(int len_m3) { // Lcode :932-946 (argument is length - 3)
 	if (len_m3 == 255) return 285;

@@ -15,9 +15,6 @@ constexpr int kRun = 65536;    // positions per k_links warp
 constexpr int kTile = 32768;   // positions per k_match CTA
 constexpr int kTileData = 2 * kTile + 320; // bytes of window staged per tile (history + tile + max match + pad)
 constexpr int kMatchThreads = 1024;
-constexpr int kParseChunk = 512;
-constexpr int kParseSymBuf = 512;
-constexpr int kParseWarps = 4;
 
 // ------------------------------------------------------------------------------------------------
 // K1: link[p] = distance from p to the previous inserted position with the same hash (0 = none / too far).
@@ -134,20 +131,39 @@ __global__ void __launch_bounds__(kMatchThreads, 1)
 }
 
 // ------------------------------------------------------------------------------------------------
-// K3: the sequential lazy parse.  One warp per stream: the warp stages the next kParseChunk table entries and
-// bytes in shared memory, lane 0 runs the state machine over them, the warp writes the symbols out coalesced.
+// K3: the lazy parse (DeflateSlow's state machine), parallelised inside each stream.
+// One warp per stream, rounds of 32 segments x kSeg positions.  The round's table entries and bytes are staged in
+// shared memory (coalesced), every lane parses its own segment starting from a guessed clean state, then each lane
+// hands its exit state to the next lane as that lane's entry; lanes whose entry changed parse again.  Lane 0's entry
+// is the true carried state, so after k hand-offs the first k+1 lanes are exact; because the parse re-synchronises
+// within a few symbols the hand-offs normally stop changing anything after one or two iterations.  A final pass emits
+// the symbols at prefix-summed offsets and records the block cuts (every 16384 symbols, DeflaterHuffman.cs:863).
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kParseWarps * 32)
+constexpr int kSeg = 128;
+constexpr int kRound = 32 * kSeg;
+constexpr int kSegStride = kSeg + 1; // uint2 entries; the +1 staggers the lanes' banks
+constexpr int kParseSmem = 32 * kSegStride * 8 + kRound + 32;
+
+__device__ __forceinline__ ParseCarry shfl_carry(const ParseCarry &c, int src) {
+	ParseCarry r;
+	r.st.p = __shfl_sync(0xffffffffu, c.st.p, src);
+	r.st.mlen = __shfl_sync(0xffffffffu, c.st.mlen, src);
+	r.st.mstart = __shfl_sync(0xffffffffu, c.st.mstart, src);
+	r.st.prevAvail = __shfl_sync(0xffffffffu, c.st.prevAvail, src);
+	r.last_top = __shfl_sync(0xffffffffu, c.last_top, src);
+	return r;
+}
+
+__global__ void __launch_bounds__(32)
     k_parse(const uint8_t *__restrict__ in, const uint16_t *__restrict__ link, const uint2 *__restrict__ mt,
-            uint32_t *__restrict__ sym, const int64_t *__restrict__ in_off, const int64_t *__restrict__ in_len, int nstreams,
+            uint32_t *__restrict__ sym, const int64_t *__restrict__ in_off, const int64_t *__restrict__ in_len,
             uint32_t *__restrict__ nsyms, uint32_t *__restrict__ nblocks, const uint32_t *__restrict__ blk_off,
             uint32_t *__restrict__ blk_start, uint32_t *__restrict__ blk_ptop, LevelParams lp, int strategy, int end_mode) {
-	__shared__ uint2 s_tab[kParseWarps][kParseChunk];
-	__shared__ uint8_t s_dat[kParseWarps][kParseChunk + 16];
-	__shared__ uint32_t s_sym[kParseWarps][kParseSymBuf];
-	const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	const int stream = blockIdx.x * kParseWarps + w;
-	if (stream >= nstreams) return;
+	extern __shared__ __align__(16) uint8_t smem[];
+	uint2 *s_tab = reinterpret_cast<uint2 *>(smem);
+	uint8_t *s_dat = smem + 32 * kSegStride * 8; // s_dat[i] = byte at position base - 1 + i
+	const int lane = threadIdx.x;
+	const int stream = blockIdx.x;
 	const uint32_t n = (uint32_t)in_len[stream];
 	const int64_t off = in_off[stream];
 	const uint8_t *data = in + off;
@@ -156,70 +172,82 @@ __global__ void __launch_bounds__(kParseWarps * 32)
 	uint32_t *sout = sym + off;
 	uint32_t *bstart = blk_start + blk_off[stream];
 	uint32_t *bptop = blk_ptop + blk_off[stream];
-	uint2 *ctab = s_tab[w];
-	uint8_t *cdat = s_dat[w];
-	uint32_t *csym = s_sym[w];
 
-	ParseState st;
-	parse_init(st);
-	uint32_t total = 0, bytes_done = 0, last_top = 0, nblk = 0;
-	bool ended_full = false;
+	ParseCarry carry; // uniform across the warp
+	parse_init(carry.st);
+	carry.last_top = 0;
+	uint32_t total = 0;
 	if (lane == 0) bstart[0] = 0;
-	for (;;) {
-		const uint32_t p0 = __shfl_sync(0xffffffffu, st.p, 0);
-		if (p0 >= n) break;
-		const uint32_t cend = (n - p0 > (uint32_t)kParseChunk) ? p0 + kParseChunk : n;
-		const uint32_t cn = cend - p0;
-		for (uint32_t i = lane; i < cn; i += 32) ctab[i] = tab[p0 + i];
-		for (uint32_t i = lane; i <= cn; i += 32) { // byte q = p0 - 1 + i lives at cdat[i]
-			if (p0 + i >= 1 && p0 + i - 1 < n) cdat[i] = data[p0 + i - 1];
-		}
+	for (uint32_t base = 0; base < n; base += kRound) {
+		const uint32_t rn = (n - base > (uint32_t)kRound) ? (uint32_t)kRound : n - base;
 		__syncwarp();
+		for (uint32_t i = lane; i < rn; i += 32) s_tab[(i >> 7) * kSegStride + (i & (kSeg - 1))] = tab[base + i];
+		for (uint32_t i = lane; i <= rn; i += 32)
+			if (base + i >= 1) s_dat[i] = data[base + i - 1];
+		__syncwarp();
+		const uint32_t seg_end = base + (uint32_t)(lane + 1) * kSeg;
+		auto tabf = [&](uint32_t p, uint32_t &a, uint32_t &b) {
+			const uint32_t i = p - base;
+			const uint2 t = s_tab[(i >> 7) * kSegStride + (i & (kSeg - 1))];
+			a = t.x;
+			b = t.y;
+		};
+		auto bytef = [&](uint32_t q) { return (uint32_t)s_dat[q + 1 - base]; };
+		auto slowf = [&](uint32_t p, uint32_t m0, uint32_t budget) { return match_search_above(data, lnk, p, n, m0, budget); };
+		ParseCarry entry, ex;
+		if (lane == 0) entry = carry;
+		else {
+			parse_init(entry.st);
+			entry.st.p = base + (uint32_t)lane * kSeg;
+			entry.last_top = 0;
+		}
+		ex = entry;
 		uint32_t cnt = 0;
-		if (lane == 0) {
-			while (st.p < cend && cnt < (uint32_t)kParseSymBuf) {
-				last_top = st.p;
-				uint32_t s;
-				int e = parse_step(
-				    st, n, lp, strategy,
-				    [&](uint32_t p, uint32_t &a, uint32_t &b) {
-					    uint2 t = ctab[p - p0];
-					    a = t.x;
-					    b = t.y;
-				    },
-				    [&](uint32_t q) { return (uint32_t)cdat[q + 1 - p0]; },
-				    [&](uint32_t p, uint32_t m0, uint32_t budget) {
-					    return match_search_above(data, lnk, p, n, m0, budget);
-				    },
-				    s);
-				ended_full = false;
-				if (e) {
-					csym[cnt++] = s;
-					bytes_done += sym_len(s);
-					++total;
-					if ((total & (uint32_t)(kBlockSyms - 1)) == 0) {
-						bptop[nblk] = last_top;
-						++nblk;
-						bstart[nblk] = bytes_done;
-						ended_full = (end_mode == B200Z_END_FINISH) && st.p >= n && !st.prevAvail;
-					}
-				}
+		bool changed = true;
+		for (int it = 0; it < 34; it++) {
+			if (changed) {
+				ex = entry;
+				cnt = parse_run<false>(ex, seg_end, n, lp, strategy, tabf, bytef, slowf, [](uint32_t, uint32_t, uint32_t, uint32_t) {});
 			}
+			const ParseCarry ne = shfl_carry(ex, lane == 0 ? 0 : lane - 1);
+			changed = false;
+			if (lane > 0) {
+				changed = !carry_equal(ne, entry);
+				entry = ne;
+			}
+			if (!__any_sync(0xffffffffu, changed)) break;
 		}
-		cnt = __shfl_sync(0xffffffffu, cnt, 0);
-		const uint32_t tot = __shfl_sync(0xffffffffu, total, 0);
-		__syncwarp();
-		for (uint32_t i = lane; i < cnt; i += 32) sout[tot - cnt + i] = csym[i];
-		__syncwarp();
+		// final pass: emit at prefix-summed offsets
+		uint32_t incl = cnt;
+		for (int o = 1; o < 32; o <<= 1) {
+			const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+			if (lane >= o) incl += t;
+		}
+		const uint32_t o0 = total + incl - cnt;
+		ParseCarry c = entry;
+		parse_run<true>(c, seg_end, n, lp, strategy, tabf, bytef, slowf,
+		                [&](uint32_t k, uint32_t s, uint32_t top, uint32_t bytes_after) {
+			                const uint32_t idx = o0 + k;
+			                sout[idx] = s;
+			                if (((idx + 1) & (uint32_t)(kBlockSyms - 1)) == 0) {
+				                const uint32_t b = (idx + 1) >> 14;
+				                bptop[b - 1] = top;
+				                bstart[b] = bytes_after;
+			                }
+		                });
+		total += __shfl_sync(0xffffffffu, incl, 31);
+		carry = shfl_carry(c, 31);
 	}
 	if (lane == 0) {
-		if (!ended_full) {
+		uint32_t nblk;
+		const bool ended_full = end_mode == B200Z_END_FINISH && total > 0 && (total & (uint32_t)(kBlockSyms - 1)) == 0 && !carry.st.prevAvail;
+		if (ended_full) {
+			nblk = total >> 14;
+		} else {
 			// final flush at lookahead == 0 (DeflaterEngine.cs:750-768)
-			if (st.prevAvail) {
-				sout[total++] = sym_lit(data[st.p - 1]);
-				bytes_done += 1;
-			}
-			bptop[nblk] = last_top;
+			nblk = total >> 14;
+			if (carry.st.prevAvail) sout[total++] = sym_lit(data[carry.st.p - 1]);
+			bptop[nblk] = carry.last_top;
 			++nblk;
 		}
 		nsyms[stream] = total;
@@ -562,9 +590,8 @@ int deflate_plan_run(b200z_plan *p, const uint8_t *d_in, uint8_t *d_out, int64_t
 		k_match<<<p->n_tiles, kMatchThreads, kTileData + 2 * 2 * kTile, s>>>(d_in, link, mt, in_off, in_len,
 		                                                                   ws.at<int2>(p->o_tile_desc), lp);
 	p->mark(s, "k_parse");
-	k_parse<<<(n + kParseWarps - 1) / kParseWarps, kParseWarps * 32, 0, s>>>(d_in, link, mt, sym, in_off, in_len, n, nsyms,
-	                                                                        nblocks, blk_off, blk_start, blk_ptop, lp,
-	                                                                        p->strategy, p->end_mode);
+	k_parse<<<n, 32, kParseSmem, s>>>(d_in, link, mt, sym, in_off, in_len, nsyms, nblocks, blk_off, blk_start, blk_ptop, lp,
+	                                  p->strategy, p->end_mode);
 	p->mark(s, "k_plan");
 	k_plan<<<p->n_blkmax, 256, 0, s>>>(sym, in_off, in_len, nsyms, nblocks, blk_off, blk_desc, blk_start, blk_ptop, meta,
 	                                   tables, p->end_mode);

@@ -7,19 +7,26 @@
 //   OutputWindow.Write/Repeat/CopyStored     Zip/Compression/Streams/OutputWindow.cs:35-122
 //   StreamManipulator (bit reader)           Zip/Compression/Streams/StreamManipulator.cs:31-298
 //
-// One warp per stream.  Lane 0 owns the bit reader and the Huffman decode and fills a batch of up to 32 tokens; the
-// warp then places the batch: a prefix sum over token lengths gives every token its output offset, literals are
-// stored by their lanes, back-references that only read bytes produced before the batch are copied by their lanes in
-// parallel, and the remaining (batch-dependent) back-references are copied one after another by the whole warp with
-// the overlap rule of OutputWindow.Repeat (byte k comes from source byte k mod distance).  The output buffer itself
-// is the window: a distance reaching before the start of the stream reads zeros, which is what a fresh reference
-// window holds (trap T13: the reference does not check distances).
+// One warp per stream.  Block headers (and the code tables they describe) are handled by lane 0.  Inside a Huffman
+// block the warp works in ROUNDS over the next 32 x kSubBits bits of input, staged in shared memory:
+//   1. every lane decodes (count only) the symbols of its own sub-chunk, lane 0 from the true bit position, the others
+//      from a guessed one; each lane then takes the previous lane's exit position as its entry and decodes again if that
+//      changed.  Huffman streams re-synchronise within a few symbols, so this settles after ~2 passes; by induction the
+//      first k+1 lanes are exact after k hand-offs, so it is exact after at most 32.
+//   2. a prefix sum of the produced byte counts places every lane in the round's output window (shared memory); a final
+//      decode pass stores literals there and records back-references (offset, length, distance) per lane.
+//   3. back-references are resolved inside shared memory in multiple rounds: a lane copies a match as soon as all of its
+//      source bytes are final (before the frontier of completed lanes, in the lane's own already-resolved region, or in
+//      earlier rounds' output read back from global memory) -- OutputWindow.Repeat's byte-serial overlap rule
+//      (source byte k mod distance) is kept.
+//   4. the window is flushed to the output buffer with coalesced vector stores.
+// The output buffer itself is the 32 KiB history: a distance reaching before the start of the stream reads zeros, which
+// is what a fresh reference window holds (trap T13: the reference does not check distances).
 #include "b200z_internal.cuh"
 
 namespace b200z {
 
 constexpr int kLitRoot = 10, kDistRoot = 9;
-constexpr int kInfWarps = 4;
 
 // Inflater.cs:39-68
 __constant__ uint16_t c_cplens[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
@@ -175,31 +182,171 @@ __device__ __forceinline__ uint32_t decode_sym(BitReader &br, const uint32_t *ta
 	return 0;
 }
 
-__global__ void __launch_bounds__(kInfWarps * 32)
+constexpr int kSubBits = 512;                 // input bits per lane per round
+constexpr int kRoundWords = 32 * kSubBits / 32;  // 512 words
+constexpr int kInWords = kRoundWords + 8;        // + slack for the last symbol's overshoot
+constexpr int kLaneOutCap = 768;                 // output bytes a lane may produce per round
+constexpr int kOutBytes = 32 * kLaneOutCap + 32; // round output window (+ alignment pad)
+constexpr int kMList = 64;                       // back-references a lane may record per round
+
+struct __align__(16) InfRound {
+	uint32_t in[kInWords];
+	uint8_t out[kOutBytes];
+	uint2 mlist[32][kMList]; // x = offset in the window | len << 16 ; y = distance
+};
+constexpr int kInfSmem = (int)(sizeof(InfShared) + sizeof(InfRound));
+
+enum { F_EOB = 1, F_ERR = 2, F_OVERRUN = 4, F_DEAD = 8 };
+
+// bit reader over the round's staged words; positions are relative to the round's first staged bit
+struct LaneReader {
+	const uint32_t *w;
+	uint64_t bb;
+	uint32_t bc, widx, pos;
+	__device__ __forceinline__ void seek(const uint32_t *words, uint32_t rel) {
+		w = words;
+		widx = rel >> 5;
+		bb = 0;
+		bc = 0;
+		pos = rel;
+		refill();
+		const uint32_t sk = rel & 31;
+		bb >>= sk;
+		bc -= sk;
+	}
+	__device__ __forceinline__ void refill() {
+		if (bc <= 32) {
+			const uint32_t v = widx < (uint32_t)kInWords ? w[widx] : 0u;
+			++widx;
+			bb |= (uint64_t)v << bc;
+			bc += 32;
+		}
+	}
+	__device__ __forceinline__ void drop(uint32_t n) {
+		bb >>= n;
+		bc -= n;
+		pos += n;
+	}
+	__device__ __forceinline__ uint32_t get(uint32_t n) {
+		refill();
+		const uint32_t v = (uint32_t)bb & ((1u << n) - 1u);
+		drop(n);
+		return v;
+	}
+};
+
+__device__ __forceinline__ uint32_t lane_decode_sym(LaneReader &br, const uint32_t *tab, int R, const uint16_t *sorted,
+                                                    const Canon &cn, int kind) {
+	br.refill();
+	uint32_t e = tab[(uint32_t)br.bb & ((1u << R) - 1u)];
+	const uint32_t k = (e >> 4) & 15;
+	if (k != K_LONG) {
+		if (k != K_INVALID) br.drop(e & 15);
+		return e;
+	}
+	const uint32_t x = __brev((uint32_t)br.bb) >> 17;
+	for (int L = R + 1; L <= 15; L++) {
+		const uint32_t c = x >> (15 - L);
+		const uint32_t idx = c - cn.first[L];
+		if (idx < cn.count[L]) {
+			const uint32_t s = sorted[cn.offs[L] + idx];
+			br.drop(L);
+			return kind == 0 ? litlen_entry(s, L) : dist_entry(s, L);
+		}
+	}
+	return 0;
+}
+
+// Decodes the symbols that START in [entry, limit) (relative bit positions).  FINAL = false: counts only.
+// FINAL = true: literals go to win[obase ..], back-references to ml[0 .. nmatch).
+// Returns exit position; out = bytes produced; flags F_*; detail on error.
+template <bool FINAL>
+__device__ __forceinline__ uint32_t decode_span(const InfShared &sh, const uint32_t *words, uint32_t entry, uint32_t limit,
+                                                uint32_t end_rel /* first bit past the input */, uint8_t *win, uint32_t obase,
+                                                uint2 *ml, uint32_t &out, uint32_t &nmatch, uint32_t &flags, uint32_t &detail) {
+	LaneReader br;
+	br.seek(words, entry);
+	uint32_t o = 0, nm = 0, fl = 0;
+	detail = 0;
+	while (br.pos < limit) {
+		// state at the start of the symbol, restored when the symbol does not fit the lane's caps
+		const uint64_t sbb = br.bb;
+		const uint32_t sbc = br.bc, swi = br.widx, spos = br.pos;
+		const uint32_t e = lane_decode_sym(br, sh.lit, kLitRoot, sh.lit_sorted, sh.lit_c, 0);
+		const uint32_t k = (e >> 4) & 15;
+		if (k == K_LIT) {
+			if (br.pos > end_rel) { fl |= F_OVERRUN; br.pos = spos; break; }
+			if (o + 1 > (uint32_t)kLaneOutCap) { br.bb = sbb; br.bc = sbc; br.widx = swi; br.pos = spos; break; }
+			if (FINAL) win[obase + o] = (uint8_t)(e >> 16);
+			++o;
+			continue;
+		}
+		if (k == K_LEN) {
+			uint32_t len = e >> 16;
+			const uint32_t xb = (e >> 8) & 15;
+			if (xb) len += br.get(xb);
+			const uint32_t de = lane_decode_sym(br, sh.dist, kDistRoot, sh.dist_sorted, sh.dist_c, 1);
+			const uint32_t dk = (de >> 4) & 15;
+			if (dk != K_DIST) {
+				if (br.pos > end_rel) fl |= F_OVERRUN;
+				else { fl |= F_ERR; detail = dk == K_ILLEGAL ? D_REP_DIST : D_CODELEN0; }
+				br.pos = spos;
+				break;
+			}
+			uint32_t dist = de >> 16;
+			const uint32_t dxb = (de >> 8) & 15;
+			if (dxb) dist += br.get(dxb);
+			if (br.pos > end_rel) { fl |= F_OVERRUN; br.pos = spos; break; }
+			if (o + len > (uint32_t)kLaneOutCap || nm >= (uint32_t)kMList) { br.bb = sbb; br.bc = sbc; br.widx = swi; br.pos = spos; break; }
+			if (FINAL) ml[nm] = make_uint2((obase + o) | (len << 16), dist);
+			++nm;
+			o += len;
+			continue;
+		}
+		if (k == K_EOB) {
+			if (br.pos > end_rel) { fl |= F_OVERRUN; br.pos = spos; }
+			else fl |= F_EOB;
+			break;
+		}
+		if (br.pos > end_rel || spos + 15 > end_rel) fl |= F_OVERRUN; // diagnosed from bits past the end of the input
+		else { fl |= F_ERR; detail = k == K_ILLEGAL ? D_REP_LEN : D_CODELEN0; }
+		br.pos = spos;
+		break;
+	}
+	out = o;
+	nmatch = nm;
+	flags = fl;
+	return br.pos;
+}
+
+__global__ void __launch_bounds__(32)
     k_inflate(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, const int64_t *__restrict__ in_off,
               const int64_t *__restrict__ in_len, const int64_t *__restrict__ out_off, const int64_t *__restrict__ out_cap,
               int nstreams, int64_t *__restrict__ out_len, int64_t *__restrict__ in_used, int32_t *__restrict__ status) {
-	__shared__ InfShared sh_all[kInfWarps];
-	const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	const int stream = blockIdx.x * kInfWarps + w;
+	extern __shared__ __align__(16) uint8_t smem_raw[];
+	InfShared &sh = *reinterpret_cast<InfShared *>(smem_raw);
+	InfRound &rd = *reinterpret_cast<InfRound *>(smem_raw + sizeof(InfShared));
+	const int lane = threadIdx.x;
+	const int stream = blockIdx.x;
 	if (stream >= nstreams) return;
-	InfShared &sh = sh_all[w];
 	uint8_t *dst = out + out_off[stream];
 	const uint64_t cap = (uint64_t)out_cap[stream];
+	const uint32_t *gwords = reinterpret_cast<const uint32_t *>(in + in_off[stream]);
 
-	BitReader br;
-	br.words = reinterpret_cast<const uint32_t *>(in + in_off[stream]);
+	BitReader br; // lane 0's header reader (global memory)
+	br.words = gwords;
 	br.nbytes = (uint32_t)in_len[stream];
 	br.nwords = (br.nbytes + 3) >> 2;
 	br.bb = 0;
 	br.bc = 0;
 	br.widx = 0;
 	br.consumed = 0;
+	const uint64_t total_bits = 8ull * br.nbytes;
 
-	uint64_t opos = 0;   // bytes produced (uniform across the warp)
-	int st = B200Z_OK;   // lane 0 authoritative, broadcast when it changes
+	uint64_t opos = 0; // bytes produced (uniform across the warp)
+	int st = B200Z_OK; // lane 0 authoritative until broadcast
 	int detail = 0;
-	bool last = false, in_block = false, have_static = false, done = false;
+	bool last = false, done = false;
 	int cur_static = 0;
 
 	while (!done) {
@@ -225,7 +372,7 @@ __global__ void __launch_bounds__(kInfWarps * 32)
 						else if (nlen != (len ^ 0xFFFFu)) { st = B200Z_E_DATA; detail = D_STORED_LEN; }
 						stored_len = len;
 					} else if (btype == 1) {
-						if (!have_static || !cur_static) {
+						if (!cur_static) {
 							for (int i = 0; i < 144; i++) sh.lens[i] = 8;
 							for (int i = 144; i < 256; i++) sh.lens[i] = 9;
 							for (int i = 256; i < 280; i++) sh.lens[i] = 7;
@@ -233,7 +380,6 @@ __global__ void __launch_bounds__(kInfWarps * 32)
 							build_table(sh.lens, 288, kLitRoot, sh.lit, sh.lit_sorted, &sh.lit_c, 0);
 							for (int i = 0; i < 32; i++) sh.lens[i] = 5;
 							build_table(sh.lens, 32, kDistRoot, sh.dist, sh.dist_sorted, &sh.dist_c, 1);
-							have_static = true;
 							cur_static = 1;
 						}
 					} else if (btype == 2) {
@@ -273,8 +419,6 @@ __global__ void __launch_bounds__(kInfWarps * 32)
 							if (st == B200Z_OK && br.overrun()) st = B200Z_E_NEED_INPUT;
 							if (st == B200Z_OK && sh.lens[256] == 0) { st = B200Z_E_DATA; detail = D_HDR_NO_EOB; }
 							if (st == B200Z_OK) {
-								// the distance lengths follow the literal/length ones in the same array; build dist first
-								// from a copy so the literal build may reuse sh.lens[0..nlit)
 								uint8_t dl[32];
 								for (int i = 0; i < ndist; i++) dl[i] = sh.lens[nlit + i];
 								d = build_table(sh.lens, nlit, kLitRoot, sh.lit, sh.lit_sorted, &sh.lit_c, 0);
@@ -288,20 +432,19 @@ __global__ void __launch_bounds__(kInfWarps * 32)
 					}
 				}
 			}
+			// an error diagnosed from bits past the end of the input is "needs more input", not corrupt data
+			if (st != B200Z_OK && br.overrun()) { st = B200Z_E_NEED_INPUT; detail = 0; }
 		}
-		// an error diagnosed from bits past the end of the input is "needs more input", not corrupt data
-		if (lane == 0 && st != B200Z_OK && br.overrun()) { st = B200Z_E_NEED_INPUT; detail = 0; }
 		done = __shfl_sync(0xffffffffu, (int)done, 0) != 0;
 		st = __shfl_sync(0xffffffffu, st, 0);
 		if (done || st != B200Z_OK) break;
 		btype = __shfl_sync(0xffffffffu, btype, 0);
+		uint64_t bitpos = __shfl_sync(0xffffffffu, (unsigned long long)br.consumed, 0);
 		__syncwarp();
 
 		if (btype == 0) {
 			// ---- stored block: OutputWindow.CopyStored (:100-122), whole warp ---------------------------
 			stored_len = __shfl_sync(0xffffffffu, stored_len, 0);
-			// byte position of the payload in the input
-			uint64_t bitpos = __shfl_sync(0xffffffffu, (unsigned long long)br.consumed, 0);
 			const uint64_t ipos = bitpos >> 3;
 			const uint64_t avail = ipos <= br.nbytes ? br.nbytes - ipos : 0;
 			if (stored_len > avail) st = B200Z_E_NEED_INPUT;
@@ -310,124 +453,141 @@ __global__ void __launch_bounds__(kInfWarps * 32)
 			const uint8_t *src = in + in_off[stream] + ipos;
 			for (uint32_t i = lane; i < stored_len; i += 32) dst[opos + i] = src[i];
 			opos += stored_len;
-			if (lane == 0) {
-				// re-seat the bit reader after the payload
-				const uint64_t nb = 8ull * (ipos + stored_len);
-				br.consumed = nb;
-				br.widx = (uint32_t)(nb >> 5);
-				br.bb = 0;
-				br.bc = 0;
-				const uint32_t sk = (uint32_t)(nb & 31);
-				if (sk) {
-					br.refill();
-					br.bb >>= sk;
-					br.bc -= sk;
-				}
-			}
-			__syncwarp();
-			continue;
-		}
-
-		// ---- Huffman block: batches of up to 32 tokens --------------------------------------------------
-		in_block = true;
-		while (in_block) {
-			int ntok = 0;
-			if (lane == 0) {
-				uint64_t budget = cap - opos; // bytes still allowed
-				while (ntok < 32) {
-					uint32_t e = decode_sym(br, sh.lit, kLitRoot, sh.lit_sorted, sh.lit_c, 0);
-					const uint32_t k = (e >> 4) & 15;
-					if (br.overrun()) { st = B200Z_E_NEED_INPUT; break; } // the symbol used bits past the end of the input
-					if (k == K_LIT) {
-						if (budget < 1) { st = B200Z_E_NOMEM; break; }
-						sh.tok_len[ntok] = 1;
-						sh.tok_val[ntok] = (uint16_t)(e >> 16);
-						++ntok;
-						--budget;
-						continue;
+			bitpos = 8ull * (ipos + stored_len);
+		} else {
+			// ---- Huffman block: rounds ----------------------------------------------------------------------
+			bool in_block = true;
+			while (in_block) {
+				// stage the round's input words (zero beyond the end of the stream)
+				const uint32_t w0 = (uint32_t)(bitpos >> 5);
+				for (int i = lane; i < kInWords; i += 32) {
+					const uint32_t wi = w0 + (uint32_t)i;
+					uint32_t v = 0;
+					if (wi < br.nwords) {
+						v = __ldg(gwords + wi);
+						if (wi == br.nwords - 1 && (br.nbytes & 3)) v &= (1u << (8 * (br.nbytes & 3))) - 1u;
 					}
-					if (k == K_LEN) {
-						uint32_t len = e >> 16;
-						const int xb = (int)((e >> 8) & 15);
-						if (xb) len += br.get(xb);
-						uint32_t de = decode_sym(br, sh.dist, kDistRoot, sh.dist_sorted, sh.dist_c, 1);
-						const uint32_t dk = (de >> 4) & 15;
-						if (dk != K_DIST) {
-							st = br.overrun() ? B200Z_E_NEED_INPUT : B200Z_E_DATA;
-							detail = dk == K_ILLEGAL ? D_REP_DIST : D_CODELEN0;
-							break;
-						}
-						uint32_t dist = de >> 16;
-						const int dxb = (int)((de >> 8) & 15);
-						if (dxb) dist += br.get(dxb);
-						if (br.overrun()) { st = B200Z_E_NEED_INPUT; break; }
-						if (budget < len) { st = B200Z_E_NOMEM; break; }
-						sh.tok_len[ntok] = (uint16_t)len;
-						sh.tok_val[ntok] = (uint16_t)dist;
-						++ntok;
-						budget -= len;
-						continue;
-					}
-					if (k == K_EOB) {
-						if (br.overrun()) st = B200Z_E_NEED_INPUT;
-						in_block = false;
-						break;
-					}
-					// invalid / illegal
-					st = br.overrun() ? B200Z_E_NEED_INPUT : B200Z_E_DATA;
-					detail = k == K_ILLEGAL ? D_REP_LEN : D_CODELEN0;
-					break;
-				}
-				if (br.overrun() && st != B200Z_E_NOMEM) { st = B200Z_E_NEED_INPUT; detail = 0; }
-			}
-			ntok = __shfl_sync(0xffffffffu, ntok, 0);
-			in_block = __shfl_sync(0xffffffffu, (int)in_block, 0) != 0;
-			st = __shfl_sync(0xffffffffu, st, 0);
-			__syncwarp();
-			// ---- place the batch (tokens decoded before an error are still valid output) ---------------
-			uint32_t len = 0, val = 0;
-			bool is_match = false;
-			if (lane < ntok) {
-				len = sh.tok_len[lane];
-				val = sh.tok_val[lane];
-				is_match = len >= 3; // literals have len 1, matches len >= 3
-			}
-			uint32_t incl = len;
-			for (int o = 1; o < 32; o <<= 1) {
-				const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-				if (lane >= o) incl += t;
-			}
-			const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-			const uint64_t my = opos + incl - len;
-			if (lane < ntok && !is_match) dst[my] = (uint8_t)val;
-			// back-references that read only pre-batch bytes: all lanes at once
-			const bool indep = is_match && (my - opos + (len < val ? len : val)) <= (uint64_t)val;
-			if (indep) {
-				for (uint32_t k2 = 0; k2 < len; k2++) {
-					const uint32_t o = k2 < val ? k2 : k2 % val;
-					const uint64_t sidx = my + o;
-					dst[my + k2] = sidx >= val ? dst[sidx - val] : (uint8_t)0;
-				}
-			}
-			__syncwarp();
-			uint32_t dep = __ballot_sync(0xffffffffu, is_match && !indep);
-			while (dep) {
-				const int l = __ffs(dep) - 1;
-				dep &= dep - 1;
-				const uint32_t mlen = __shfl_sync(0xffffffffu, len, l);
-				const uint32_t mdist = __shfl_sync(0xffffffffu, val, l);
-				const uint64_t mpos = __shfl_sync(0xffffffffu, (unsigned long long)my, l);
-				for (uint32_t k2 = lane; k2 < mlen; k2 += 32) {
-					const uint32_t o = k2 < mdist ? k2 : k2 % mdist;
-					const uint64_t sidx = mpos + o;
-					dst[mpos + k2] = sidx >= mdist ? dst[sidx - mdist] : (uint8_t)0;
+					rd.in[i] = v;
 				}
 				__syncwarp();
+				const uint32_t r0 = (uint32_t)(bitpos & 31); // relative position of the true entry
+				const uint64_t remain = total_bits - ((uint64_t)w0 << 5);
+				const uint32_t end_rel = remain > 0x7FFFFFFFull ? 0x7FFFFFFFu : (uint32_t)remain;
+				const uint32_t limit = r0 + (uint32_t)(lane + 1) * kSubBits;
+				uint32_t entry = r0 + (uint32_t)lane * kSubBits;
+				uint32_t exitp = entry, obytes = 0, nmatch = 0, flags = 0, det = 0;
+				bool changed = true, dead = false;
+				for (int it = 0; it < 34; it++) {
+					if (changed) {
+						if (dead) { exitp = entry; obytes = 0; nmatch = 0; flags = F_DEAD; }
+						else exitp = decode_span<false>(sh, rd.in, entry, limit, end_rel, nullptr, 0, nullptr, obytes, nmatch, flags, det);
+					}
+					const uint32_t pe = __shfl_up_sync(0xffffffffu, exitp, 1);
+					const uint32_t pf = __shfl_up_sync(0xffffffffu, flags, 1);
+					changed = false;
+					if (lane > 0) {
+						const bool nd = pf != 0; // the previous lane ended the block, failed or is dead itself
+						changed = (pe != entry) || (nd != dead);
+						entry = pe;
+						dead = nd;
+					}
+					if (!__any_sync(0xffffffffu, changed)) break;
+				}
+				// lanes up to and including the first one that stopped the block are exact; the rest are dead
+				const uint32_t stopmask = __ballot_sync(0xffffffffu, (flags & (F_EOB | F_ERR | F_OVERRUN)) != 0);
+				const int lastlane = stopmask ? (__ffs(stopmask) - 1) : 31;
+				if (lane > lastlane) { obytes = 0; nmatch = 0; }
+				uint32_t incl = obytes;
+				for (int o = 1; o < 32; o <<= 1) {
+					const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+					if (lane >= o) incl += t;
+				}
+				const uint32_t round_out = __shfl_sync(0xffffffffu, incl, 31);
+				const uint32_t lflags = __shfl_sync(0xffffffffu, flags, lastlane);
+				const uint32_t ldet = __shfl_sync(0xffffffffu, det, lastlane);
+				const uint32_t lexit = __shfl_sync(0xffffffffu, exitp, lastlane);
+				if (opos + round_out > cap) { st = B200Z_E_NOMEM; break; }
+				const uint32_t pad = (uint32_t)(opos & 15); // keep the window congruent to the output mod 16
+				const uint32_t seg0 = pad + incl - obytes;
+				if (lane <= lastlane && obytes) {
+					uint32_t o2, n2, f2, d2;
+					decode_span<true>(sh, rd.in, entry, limit, end_rel, rd.out, seg0, rd.mlist[lane], o2, n2, f2, d2);
+				}
+				__syncwarp();
+				// ---- resolve back-references inside the window (multi-round) ------------------------------------
+				{
+					uint32_t cur = 0;
+					const uint32_t seg1 = seg0 + obytes;
+					for (int it = 0; it < 33; it++) {
+						const bool pending = cur < nmatch;
+						const uint32_t pmask = __ballot_sync(0xffffffffu, pending);
+						if (!pmask) break;
+						const int first = __ffs(pmask) - 1;
+						const uint32_t mypos = pending ? (rd.mlist[lane][cur].x & 0xFFFFu) : seg1;
+						const uint32_t F = __shfl_sync(0xffffffffu, mypos, first); // every byte before F is final
+						while (cur < nmatch) {
+							const uint2 m = rd.mlist[lane][cur];
+							const uint32_t mo = m.x & 0xFFFFu, mlen = m.x >> 16, mdist = m.y;
+							// source bytes live in [mo - mdist, mo); positions below `pad` are earlier rounds (global)
+							const int64_t slo = (int64_t)mo - (int64_t)mdist;
+							const int64_t shi = slo + (int64_t)(mlen < mdist ? mlen : mdist);
+							const bool ready = (F >= seg0) || shi <= (int64_t)F || slo >= (int64_t)seg0;
+							if (!ready) break;
+							for (uint32_t k2 = 0; k2 < mlen; k2++) {
+								const int64_t si = slo + (int64_t)(k2 < mdist ? k2 : k2 % mdist);
+								uint8_t v;
+								if (si >= (int64_t)pad) v = rd.out[si];
+								else {
+									const int64_t gi = (int64_t)opos + (si - (int64_t)pad);
+									v = gi >= 0 ? dst[gi] : (uint8_t)0;
+								}
+								rd.out[mo + k2] = v;
+							}
+							++cur;
+						}
+						__syncwarp();
+					}
+				}
+				__syncwarp();
+				// ---- flush the window: bytes [pad, pad + round_out) -> dst[opos ..) -------------------------------
+				{
+					const uint32_t b0 = pad, b1 = pad + round_out;
+					const uint32_t v0 = (b0 + 15) & ~15u, v1 = b1 & ~15u;
+					uint8_t *d0 = dst + opos - pad; // d0 + i is the destination of window byte i; 16-byte aligned
+					if (v0 < v1) {
+						for (uint32_t i = b0 + lane; i < v0; i += 32) d0[i] = rd.out[i];
+						const uint4 *sv = reinterpret_cast<const uint4 *>(rd.out);
+						uint4 *dv = reinterpret_cast<uint4 *>(d0);
+						for (uint32_t i = (v0 >> 4) + lane; i < (v1 >> 4); i += 32) dv[i] = sv[i];
+						for (uint32_t i = v1 + lane; i < b1; i += 32) d0[i] = rd.out[i];
+					} else {
+						for (uint32_t i = b0 + lane; i < b1; i += 32) d0[i] = rd.out[i];
+					}
+				}
+				opos += round_out;
+				bitpos = ((uint64_t)w0 << 5) + lexit;
+				__syncwarp();
+				if (lflags & F_EOB) in_block = false;
+				else if (lflags & F_OVERRUN) { st = B200Z_E_NEED_INPUT; break; }
+				else if (lflags & F_ERR) { st = B200Z_E_DATA; detail = (int)ldet; break; }
+				else if (round_out == 0 && lexit == r0) { st = B200Z_E_INTERNAL; break; } // cannot happen: a symbol always fits
 			}
-			opos += total;
 			if (st != B200Z_OK) break;
 		}
-		if (st != B200Z_OK) break;
+		// re-seat lane 0's header reader at the new bit position
+		if (lane == 0) {
+			br.consumed = bitpos;
+			br.widx = (uint32_t)(bitpos >> 5);
+			br.bb = 0;
+			br.bc = 0;
+			const uint32_t sk = (uint32_t)(bitpos & 31);
+			if (sk) {
+				br.refill();
+				br.bb >>= sk;
+				br.bc -= sk;
+			}
+		}
+		__syncwarp();
 	}
 	if (lane == 0) {
 		status[stream] = st | (detail << 8);
@@ -472,6 +632,7 @@ int inflate_plan_build(b200z_plan *p) {
 		B200Z_CUDA(cudaMemcpy(ws.at<int64_t>(p->o_out_off), p->out_off.data(), 8ll * n, cudaMemcpyHostToDevice));
 		B200Z_CUDA(cudaMemcpy(ws.at<int64_t>(p->o_out_cap), p->out_cap.data(), 8ll * n, cudaMemcpyHostToDevice));
 	}
+	B200Z_CUDA(cudaFuncSetAttribute(k_inflate, cudaFuncAttributeMaxDynamicSharedMemorySize, kInfSmem));
 	p->launches = 1;
 	return B200Z_OK;
 }
@@ -484,7 +645,7 @@ int inflate_plan_run(b200z_plan *p, const uint8_t *d_in, uint8_t *d_out, int64_t
 	(void)d_check;
 	p->ev_used = 0;
 	p->mark(s, "k_inflate");
-	k_inflate<<<(n + kInfWarps - 1) / kInfWarps, kInfWarps * 32, 0, s>>>(
+	k_inflate<<<n, 32, kInfSmem, s>>>(
 	    d_in, d_out, ws.at<int64_t>(p->o_in_off), ws.at<int64_t>(p->o_in_len), ws.at<int64_t>(p->o_out_off),
 	    ws.at<int64_t>(p->o_out_cap), n, d_out_len, d_in_used, d_status);
 	p->mark(s, "end");

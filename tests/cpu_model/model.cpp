@@ -3,6 +3,7 @@
 // so the exactness of the parallel reformulation can be checked against the oracle in the CPU-only test tier.
 // It is not a fallback: the product library never links it.
 #include "b200z_core.cuh"
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -78,46 +79,91 @@ extern "C" int model_deflate(const uint8_t *data, uint32_t n, int level, int str
 	// K2: every position
 	std::vector<uint32_t> tabA(n), tabB(n);
 	for (uint32_t p = 0; p < n; p++) match_search(data, link.data(), 0u, p, n, lp, tabA[p], tabB[p]);
-	// K3
+	// K3 as k_parse does it: rounds of 32 segments x kSeg positions; every lane parses its segment speculatively from a
+	// clean state, entries are handed lane -> lane until nothing changes, then a final pass emits at prefix-summed offsets
+	const uint32_t kSeg = 128, kRound = 32 * kSeg;
 	std::vector<uint32_t> syms;
-	std::vector<uint32_t> blk_start; // byte position of each block's first symbol
-	std::vector<uint32_t> blk_ptop;  // loop top at which the block was flushed
-	ParseState st;
-	parse_init(st);
-	uint32_t bytes_done = 0;
-	blk_start.push_back(0);
-	uint32_t last_top = 0;
-	bool ended_full = false;
-	while (st.p < n) {
-		uint32_t sym;
-		last_top = st.p;
-		int e = parse_step(
-		    st, n, lp, strategy, [&](uint32_t p, uint32_t &a, uint32_t &b) { a = tabA[p]; b = tabB[p]; },
-		    [&](uint32_t q) { return (uint32_t)data[q]; },
-		    [&](uint32_t p, uint32_t m0, uint32_t budget) { return match_search_above(data, link.data(), p, n, m0, budget); },
-		    sym);
-		ended_full = false;
-		if (e) {
-			syms.push_back(sym);
-			bytes_done += sym_len(sym);
-			if (syms.size() % kBlockSyms == 0) {
-				blk_ptop.push_back(last_top);
-				blk_start.push_back(bytes_done);
-				ended_full = !flush_then_finish && (st.p >= n) && !st.prevAvail;
+	std::vector<uint32_t> blk_start(n / kBlockSyms + 3, 0), blk_ptop(n / kBlockSyms + 3, 0);
+	auto tabf = [&](uint32_t p, uint32_t &a, uint32_t &b) { a = tabA[p]; b = tabB[p]; };
+	auto bytef = [&](uint32_t q) { return (uint32_t)data[q]; };
+	auto slowf = [&](uint32_t p, uint32_t m0, uint32_t budget) { return match_search_above(data, link.data(), p, n, m0, budget); };
+	ParseCarry carry;
+	parse_init(carry.st);
+	carry.last_top = 0;
+	uint32_t total = 0;
+	int max_iters = 0;
+	for (uint32_t base = 0; base < n; base += kRound) {
+		ParseCarry entry[32], ex[32];
+		uint32_t cnt[32];
+		bool changed[32];
+		for (int l = 0; l < 32; l++) {
+			if (l == 0) entry[l] = carry;
+			else {
+				parse_init(entry[l].st);
+				entry[l].st.p = base + l * kSeg;
+				entry[l].last_top = 0;
 			}
+			changed[l] = true;
 		}
+		int it = 0;
+		for (; it < 40; it++) {
+			for (int l = 0; l < 32; l++) {
+				if (changed[l]) {
+					ex[l] = entry[l];
+					cnt[l] = parse_run<false>(ex[l], base + (l + 1) * kSeg, n, lp, strategy, tabf, bytef, slowf,
+					                          [](uint32_t, uint32_t, uint32_t, uint32_t) {});
+				}
+			}
+			bool any = false;
+			ParseCarry ne[32];
+			for (int l = 1; l < 32; l++) ne[l] = ex[l - 1];
+			changed[0] = false;
+			for (int l = 1; l < 32; l++) {
+				changed[l] = !carry_equal(ne[l], entry[l]);
+				entry[l] = ne[l];
+				any |= changed[l];
+			}
+			if (!any) break;
+		}
+		if (it > max_iters) max_iters = it;
+		uint32_t off = total;
+		for (int l = 0; l < 32; l++) {
+			ParseCarry c = entry[l];
+			const uint32_t o = off;
+			if (syms.size() < o + cnt[l]) syms.resize(o + cnt[l]);
+			uint32_t got = parse_run<true>(c, base + (l + 1) * kSeg, n, lp, strategy, tabf, bytef, slowf,
+			                               [&](uint32_t k, uint32_t sym, uint32_t top, uint32_t bytes_after) {
+				                               const uint32_t idx = o + k;
+				                               syms[idx] = sym;
+				                               if (((idx + 1) & (kBlockSyms - 1)) == 0) {
+					                               const uint32_t b = (idx + 1) / kBlockSyms;
+					                               blk_ptop[b - 1] = top;
+					                               blk_start[b] = bytes_after;
+				                               }
+			                               });
+			if (got != cnt[l] || !carry_equal(c, ex[l])) return 103; // final pass disagrees with the converged run
+			off += cnt[l];
+			if (l == 31) carry = c;
+		}
+		total = off;
 	}
-	if (!ended_full) {
-		// final flush at lookahead == 0 (:750-768)
-		if (st.prevAvail) {
-			syms.push_back(sym_lit(data[st.p - 1]));
-			bytes_done += 1;
-		}
-		blk_ptop.push_back(last_top);
+	if (getenv("B200Z_MODEL_VERBOSE")) fprintf(stderr, "parse: max propagation iterations %d\n", max_iters);
+	size_t nfull = total / kBlockSyms;
+	const bool ended_full = !flush_then_finish && total > 0 && (total % kBlockSyms) == 0 && !carry.st.prevAvail;
+	size_t nblocks;
+	if (ended_full) {
+		nblocks = nfull;
 	} else {
-		blk_start.pop_back();
+		// final flush at lookahead == 0 (:750-768)
+		if (carry.st.prevAvail) {
+			syms.push_back(sym_lit(data[carry.st.p - 1]));
+			total++;
+		}
+		nfull = (total - (carry.st.prevAvail ? 1 : 0)) / kBlockSyms;
+		blk_ptop[nfull] = carry.last_top;
+		nblocks = nfull + 1;
 	}
-	size_t nblocks = blk_ptop.size();
+	syms.resize(total);
 	Writer W;
 	uint64_t bitpos = 0;
 	std::vector<int> scratch(9 * 286 + 64);
