@@ -7,6 +7,8 @@
 //   k_plan    (K4)  DeflaterHuffman.FlushBlock up to the type decision    DeflaterHuffman.cs:788-857
 //   k_scan    (K5)  bit position of every block; Deflater flush padding   Deflater.cs:486-517
 //   k_emit    (K6)  SendAllTrees / CompressBlock / FlushStoredBlock       DeflaterHuffman.cs:676-779
+#include <cuda_pipeline.h>
+
 #include "b200z_internal.cuh"
 
 namespace b200z {
@@ -21,6 +23,18 @@ constexpr int kMatchThreads = 1024;
 // One warp per run of kRun positions, 32 positions per step; a 16-bit head table in shared memory, re-based
 // every 32768 positions exactly like SlideWindow (DeflaterEngine.cs:441-462) so that entries stay unambiguous.
 // ------------------------------------------------------------------------------------------------
+// lanes holding the same 15-bit hash, from 16 ballots (MATCH.ANY showed ~360 cycles of latency per step in ncu)
+__device__ __forceinline__ uint32_t same_hash_mask(uint32_t h, bool valid, int lane) {
+	uint32_t eq = __ballot_sync(0xffffffffu, valid);
+#pragma unroll
+	for (int b = 0; b < 15; b++) {
+		const bool bit = (h >> b) & 1u;
+		const uint32_t bal = __ballot_sync(0xffffffffu, bit);
+		eq &= bit ? bal : ~bal;
+	}
+	return valid ? eq : (1u << lane);
+}
+
 __global__ void __launch_bounds__(32) k_links(const uint8_t *__restrict__ in, uint16_t *__restrict__ link,
                                               const int64_t *__restrict__ in_off, const int64_t *__restrict__ in_len,
                                               const int2 *__restrict__ run_desc) {
@@ -36,10 +50,22 @@ __global__ void __launch_bounds__(32) k_links(const uint8_t *__restrict__ in, ui
 	for (int i = lane; i < 16384; i += 32) reinterpret_cast<uint32_t *>(head)[i] = 0;
 	__syncwarp();
 	uint32_t winbase = warm;
-	// software prefetch of the next step's bytes
-	uint32_t nb0 = (warm + lane < n) ? data[warm + lane] : 0;
-	uint32_t nx = 0;
-	if (lane < 2) nx = (warm + 32 + lane < n) ? data[warm + 32 + lane] : 0;
+	// Each lane keeps the next 16 steps' bytes in registers-free form: one 32-bit load covers bytes p..p+3 of a step, so
+	// the hash needs no shuffles; loads for step k+2 are issued while step k is processed (software pipeline, depth 2).
+	auto load3 = [&](uint32_t base) -> uint32_t {
+		// bytes at base+lane, +1, +2 packed little endian; positions beyond n read as 0 (those lanes are invalid anyway)
+		const uint32_t p = base + lane;
+		uint32_t v = 0;
+		if (p + 2 < n) {
+			v = (uint32_t)data[p] | ((uint32_t)data[p + 1] << 8) | ((uint32_t)data[p + 2] << 16);
+		}
+		return v;
+	};
+	uint32_t w0 = load3(warm), w1 = load3(warm + 32);
+	// hash and same-hash mask of the step about to be processed are computed one step ahead
+	bool valid = warm + lane + 2 < n;
+	uint32_t h = hash3(w0 & 0xFF, (w0 >> 8) & 0xFF, (w0 >> 16) & 0xFF);
+	uint32_t mask = same_hash_mask(h, valid, lane);
 	for (uint32_t base = warm; base < run_end; base += 32) {
 		if (base + 32 - winbase > 65535u) {
 			for (int i = lane; i < 16384; i += 32) {
@@ -52,28 +78,20 @@ __global__ void __launch_bounds__(32) k_links(const uint8_t *__restrict__ in, ui
 			winbase += 32768u;
 			__syncwarp();
 		}
-		const uint32_t b0 = nb0;
-		const uint32_t x0 = __shfl_sync(0xffffffffu, nx, 0), x1 = __shfl_sync(0xffffffffu, nx, 1);
-		// issue next step's loads before the dependent work of this step
-		const uint32_t nbase = base + 32;
-		nb0 = (nbase + lane < n) ? data[nbase + lane] : 0;
-		if (lane < 2) nx = (nbase + 32 + lane < n) ? data[nbase + 32 + lane] : 0;
-		uint32_t b1 = __shfl_down_sync(0xffffffffu, b0, 1);
-		uint32_t b2 = __shfl_down_sync(0xffffffffu, b0, 2);
-		if (lane == 31) { b1 = x0; b2 = x1; }
-		if (lane == 30) { b2 = x0; }
 		const uint32_t p = base + lane;
-		const bool valid = p + 2 < n; // InsertString only while lookahead >= MIN_MATCH (:782, :819)
-		const uint32_t h = valid ? hash3(b0, b1, b2) : (0x8000u + lane);
-		const uint32_t mask = __match_any_sync(0xffffffffu, h);
 		const uint32_t lower = mask & ((1u << lane) - 1u);
+		// table read for this step (InsertString only while lookahead >= MIN_MATCH, DeflaterEngine.cs:782, :819)
+		uint32_t v = 0;
+		if (valid && !lower) v = head[h];
+		// ... and while that is in flight: next step's hash + mask, and the loads of the step after it
+		const uint32_t w2 = load3(base + 64);
+		const bool nvalid = base + 32 + lane + 2 < n;
+		const uint32_t nh = hash3(w1 & 0xFF, (w1 >> 8) & 0xFF, (w1 >> 16) & 0xFF);
+		const uint32_t nmask = same_hash_mask(nh, nvalid, lane);
 		uint32_t q = 0xFFFFFFFFu;
 		if (valid) {
 			if (lower) q = base + (31 - __clz(lower));
-			else {
-				uint32_t v = head[h];
-				if (v) q = winbase + v - 1;
-			}
+			else if (v) q = winbase + v - 1;
 		}
 		__syncwarp();
 		if (valid && (mask >> lane) == 1u) head[h] = (uint16_t)(p - winbase + 1);
@@ -82,6 +100,10 @@ __global__ void __launch_bounds__(32) k_links(const uint8_t *__restrict__ in, ui
 			uint32_t d = (q != 0xFFFFFFFFu) ? p - q : 0u;
 			lnk[p] = (d <= (uint32_t)kMaxDist) ? (uint16_t)d : (uint16_t)0;
 		}
+		w1 = w2;
+		h = nh;
+		mask = nmask;
+		valid = nvalid;
 	}
 }
 
@@ -123,10 +145,64 @@ __global__ void __launch_bounds__(kMatchThreads, 1)
 	}
 	__syncthreads();
 	uint2 *out = mt + off;
+	// match_search() of b200z_core.cuh with the byte-wise extension loop replaced by 4-byte compares on aligned
+	// shared-memory words (ncu: the byte loop ran with ~2 of 32 lanes active and took ~30 % of the kernel).
+	const uint32_t chain = (uint32_t)lp.chain, budgetB = chain >> 2;
 	for (uint32_t p = t0 + threadIdx.x; p < t1; p += kMatchThreads) {
-		uint32_t a, b;
-		match_search(s_data, s_link, w0, p, n, lp, a, b);
-		out[p] = make_uint2(a, b);
+		uint32_t resA = 0, resB = 0;
+		const uint32_t la = n - p;
+		uint32_t d = la >= (uint32_t)kMinMatch ? (uint32_t)s_link[p - w0] : 0u;
+		if (d > (uint32_t)kMaxDist - (is_slide_pos(p) ? 1u : 0u)) d = 0; // DeflaterEngine.cs:788 + trap T8
+		if (d != 0) {
+			const uint32_t maxlen = la < (uint32_t)kMaxMatch ? la : (uint32_t)kMaxMatch;
+			const uint32_t nice = la < (uint32_t)lp.nice ? la : (uint32_t)lp.nice;
+			const uint32_t is = p - w0;
+			const uint8_t *sp = s_data + is;
+			uint32_t m = kMinMatch - 1, bd = 0, dist = d, cnt = 0;
+			bool haveB = false;
+			const uint32_t s0 = sp[0], s1 = sp[1];
+			uint32_t scan_end1 = s1, scan_end = sp[2];
+			for (;;) {
+				const uint32_t ic = is - dist;
+				const uint8_t *c = s_data + ic;
+				++cnt;
+				if (c[m] == scan_end && c[m - 1] == scan_end1 && c[0] == s0 && c[1] == s1) {
+					uint32_t l = 2;
+					while (l + 4 <= maxlen) {
+						const uint32_t ac = ic + l, as = is + l;
+						const uint32_t *wc = reinterpret_cast<const uint32_t *>(s_data + (ac & ~3u));
+						const uint32_t *ws = reinterpret_cast<const uint32_t *>(s_data + (as & ~3u));
+						const uint32_t x = __funnelshift_r(wc[0], wc[1], (ac & 3u) * 8u) ^ __funnelshift_r(ws[0], ws[1], (as & 3u) * 8u);
+						if (x) {
+							l += (uint32_t)(__ffs((int)x) - 1) >> 3;
+							goto lcp_done;
+						}
+						l += 4;
+					}
+					while (l < maxlen && c[l] == sp[l]) ++l;
+				lcp_done:
+					if (l > m) {
+						m = l;
+						bd = dist;
+						if (m >= nice) break;
+						scan_end1 = sp[m - 1];
+						scan_end = sp[m];
+					}
+				}
+				if (cnt == budgetB) {
+					resB = m >= (uint32_t)kMinMatch ? pack_match(m, bd) : 0u;
+					haveB = true;
+				}
+				if (cnt == chain) break;
+				const uint32_t l2 = s_link[is - dist];
+				if (l2 == 0) break;
+				dist += l2;
+				if (dist >= (uint32_t)kMaxDist) break; // chain entries need distance < 32506 (T7)
+			}
+			resA = m >= (uint32_t)kMinMatch ? pack_match(m, bd) : 0u;
+			if (!haveB) resB = resA;
+		}
+		out[p] = make_uint2(resA, resB);
 	}
 }
 
@@ -141,8 +217,9 @@ __global__ void __launch_bounds__(kMatchThreads, 1)
 // ------------------------------------------------------------------------------------------------
 constexpr int kSeg = 128;
 constexpr int kRound = 32 * kSeg;
-constexpr int kSegStride = kSeg + 1; // uint2 entries; the +1 staggers the lanes' banks
-constexpr int kParseSmem = 32 * kSegStride * 8 + kRound + 32;
+constexpr int kSegStride = kSeg + 2; // uint2 entries; +2 keeps 16-byte alignment for cp.async and staggers the banks
+constexpr int kParseDatOff = 32 * kSegStride * 8;
+constexpr int kParseSmem = kParseDatOff + kRound + 48;
 
 __device__ __forceinline__ ParseCarry shfl_carry(const ParseCarry &c, int src) {
 	ParseCarry r;
@@ -161,7 +238,7 @@ __global__ void __launch_bounds__(32)
             uint32_t *__restrict__ blk_start, uint32_t *__restrict__ blk_ptop, LevelParams lp, int strategy, int end_mode) {
 	extern __shared__ __align__(16) uint8_t smem[];
 	uint2 *s_tab = reinterpret_cast<uint2 *>(smem);
-	uint8_t *s_dat = smem + 32 * kSegStride * 8; // s_dat[i] = byte at position base - 1 + i
+	uint8_t *s_dat = smem + kParseDatOff; // s_dat[16 + i] = byte at position base + i (16 bytes of history in front)
 	const int lane = threadIdx.x;
 	const int stream = blockIdx.x;
 	const uint32_t n = (uint32_t)in_len[stream];
@@ -181,9 +258,17 @@ __global__ void __launch_bounds__(32)
 	for (uint32_t base = 0; base < n; base += kRound) {
 		const uint32_t rn = (n - base > (uint32_t)kRound) ? (uint32_t)kRound : n - base;
 		__syncwarp();
-		for (uint32_t i = lane; i < rn; i += 32) s_tab[(i >> 7) * kSegStride + (i & (kSeg - 1))] = tab[base + i];
-		for (uint32_t i = lane; i <= rn; i += 32)
-			if (base + i >= 1) s_dat[i] = data[base + i - 1];
+		// stage the round with 16-byte async copies (LDGSTS): all of them are in flight at once, no register staging
+		for (uint32_t i = 2 * lane; i + 1 < rn; i += 64)
+			__pipeline_memcpy_async(&s_tab[(i >> 7) * kSegStride + (i & (kSeg - 1))], &tab[base + i], 16);
+		{
+			// bytes [base - 16, base + rn) rounded up to 16 (the input slot has 16 bytes of slack behind n)
+			const uint32_t c0 = base ? 0u : 1u, c1 = (16 + rn + 15) >> 4;
+			for (uint32_t c = c0 + lane; c < c1; c += 32) __pipeline_memcpy_async(s_dat + 16 * c, data + base - 16 + 16 * c, 16);
+		}
+		__pipeline_commit();
+		if ((rn & 1) && lane == 0) s_tab[((rn - 1) >> 7) * kSegStride + ((rn - 1) & (kSeg - 1))] = tab[base + rn - 1];
+		__pipeline_wait_prior(0);
 		__syncwarp();
 		const uint32_t seg_end = base + (uint32_t)(lane + 1) * kSeg;
 		auto tabf = [&](uint32_t p, uint32_t &a, uint32_t &b) {
@@ -192,7 +277,7 @@ __global__ void __launch_bounds__(32)
 			a = t.x;
 			b = t.y;
 		};
-		auto bytef = [&](uint32_t q) { return (uint32_t)s_dat[q + 1 - base]; };
+		auto bytef = [&](uint32_t q) { return (uint32_t)s_dat[q + 16 - base]; };
 		auto slowf = [&](uint32_t p, uint32_t m0, uint32_t budget) { return match_search_above(data, lnk, p, n, m0, budget); };
 		ParseCarry entry, ex;
 		if (lane == 0) entry = carry;
@@ -204,10 +289,22 @@ __global__ void __launch_bounds__(32)
 		ex = entry;
 		uint32_t cnt = 0;
 		bool changed = true;
+		const uint32_t lim = seg_end < n ? seg_end : n;
 		for (int it = 0; it < 34; it++) {
+			// all lanes step together and re-converge every iteration (a per-lane loop would leave them diverged)
 			if (changed) {
 				ex = entry;
-				cnt = parse_run<false>(ex, seg_end, n, lp, strategy, tabf, bytef, slowf, [](uint32_t, uint32_t, uint32_t, uint32_t) {});
+				cnt = 0;
+			}
+			bool act = changed && ex.st.p < lim;
+			while (__any_sync(0xffffffffu, act)) {
+				if (act) {
+					ex.last_top = ex.st.p;
+					uint32_t s2;
+					cnt += (uint32_t)parse_step(ex.st, n, lp, strategy, tabf, bytef, slowf, s2);
+					act = ex.st.p < lim;
+				}
+				__syncwarp();
 			}
 			const ParseCarry ne = shfl_carry(ex, lane == 0 ? 0 : lane - 1);
 			changed = false;
@@ -223,18 +320,29 @@ __global__ void __launch_bounds__(32)
 			const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
 			if (lane >= o) incl += t;
 		}
-		const uint32_t o0 = total + incl - cnt;
+		uint32_t idx = total + incl - cnt;
 		ParseCarry c = entry;
-		parse_run<true>(c, seg_end, n, lp, strategy, tabf, bytef, slowf,
-		                [&](uint32_t k, uint32_t s, uint32_t top, uint32_t bytes_after) {
-			                const uint32_t idx = o0 + k;
-			                sout[idx] = s;
-			                if (((idx + 1) & (uint32_t)(kBlockSyms - 1)) == 0) {
-				                const uint32_t b = (idx + 1) >> 14;
-				                bptop[b - 1] = top;
-				                bstart[b] = bytes_after;
-			                }
-		                });
+		{
+			bool act = c.st.p < lim;
+			while (__any_sync(0xffffffffu, act)) {
+				if (act) {
+					const uint32_t top = c.st.p;
+					c.last_top = top;
+					uint32_t s2;
+					if (parse_step(c.st, n, lp, strategy, tabf, bytef, slowf, s2)) {
+						sout[idx] = s2;
+						if (((idx + 1) & (uint32_t)(kBlockSyms - 1)) == 0) {
+							const uint32_t b = (idx + 1) >> 14;
+							bptop[b - 1] = top;
+							bstart[b] = sym_dist(s2) ? top - 1 + sym_len(s2) : top; // bytes covered once this symbol is in
+						}
+						++idx;
+					}
+					act = c.st.p < lim;
+				}
+				__syncwarp();
+			}
+		}
 		total += __shfl_sync(0xffffffffu, incl, 31);
 		carry = shfl_carry(c, 31);
 	}

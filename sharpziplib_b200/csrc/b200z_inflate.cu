@@ -13,15 +13,14 @@
 //      from a guessed one; each lane then takes the previous lane's exit position as its entry and decodes again if that
 //      changed.  Huffman streams re-synchronise within a few symbols, so this settles after ~2 passes; by induction the
 //      first k+1 lanes are exact after k hand-offs, so it is exact after at most 32.
-//   2. a prefix sum of the produced byte counts places every lane in the round's output window (shared memory); a final
-//      decode pass stores literals there and records back-references (offset, length, distance) per lane.
-//   3. back-references are resolved inside shared memory in multiple rounds: a lane copies a match as soon as all of its
-//      source bytes are final (before the frontier of completed lanes, in the lane's own already-resolved region, or in
-//      earlier rounds' output read back from global memory) -- OutputWindow.Repeat's byte-serial overlap rule
-//      (source byte k mod distance) is kept.
-//   4. the window is flushed to the output buffer with coalesced vector stores.
-// The output buffer itself is the 32 KiB history: a distance reaching before the start of the stream reads zeros, which
-// is what a fresh reference window holds (trap T13: the reference does not check distances).
+//   2. a prefix sum of the produced byte counts gives every lane its output position; a final decode pass stores the
+//      literals into a 64 KiB output ring in shared memory (the reference's OutputWindow, doubled so that a whole round
+//      fits behind 32 KiB of history) and records the back-references (position, length, distance) per lane.
+//   3. back-references are resolved in stream order, each copied by the whole warp inside the ring with
+//      OutputWindow.Repeat's byte-serial overlap rule (byte k comes from source byte k mod distance).
+//   4. the round's bytes are flushed from the ring to the output buffer with coalesced vector stores.
+// The ring starts zeroed: a distance reaching before the start of the stream reads zeros, which is what a fresh
+// reference window holds (trap T13: the reference does not check distances).
 #include "b200z_internal.cuh"
 
 namespace b200z {
@@ -186,13 +185,13 @@ constexpr int kSubBits = 512;                 // input bits per lane per round
 constexpr int kRoundWords = 32 * kSubBits / 32;  // 512 words
 constexpr int kInWords = kRoundWords + 8;        // + slack for the last symbol's overshoot
 constexpr int kLaneOutCap = 768;                 // output bytes a lane may produce per round
-constexpr int kOutBytes = 32 * kLaneOutCap + 32; // round output window (+ alignment pad)
+constexpr int kRing = 65536;                     // output ring: >= 32 KiB of history + one round (32 x kLaneOutCap)
 constexpr int kMList = 64;                       // back-references a lane may record per round
 
 struct __align__(16) InfRound {
 	uint32_t in[kInWords];
-	uint8_t out[kOutBytes];
-	uint2 mlist[32][kMList]; // x = offset in the window | len << 16 ; y = distance
+	uint8_t ring[kRing];     // ring[pos & 65535] = output byte `pos`; doubles as OutputWindow (Streams/OutputWindow.cs:15-23)
+	uint2 mlist[32][kMList]; // x = output position (low 32 bits), y = len | dist << 16
 };
 constexpr int kInfSmem = (int)(sizeof(InfShared) + sizeof(InfRound));
 
@@ -257,66 +256,65 @@ __device__ __forceinline__ uint32_t lane_decode_sym(LaneReader &br, const uint32
 	return 0;
 }
 
-// Decodes the symbols that START in [entry, limit) (relative bit positions).  FINAL = false: counts only.
-// FINAL = true: literals go to win[obase ..], back-references to ml[0 .. nmatch).
-// Returns exit position; out = bytes produced; flags F_*; detail on error.
-template <bool FINAL>
-__device__ __forceinline__ uint32_t decode_span(const InfShared &sh, const uint32_t *words, uint32_t entry, uint32_t limit,
-                                                uint32_t end_rel /* first bit past the input */, uint8_t *win, uint32_t obase,
-                                                uint2 *ml, uint32_t &out, uint32_t &nmatch, uint32_t &flags, uint32_t &detail) {
+// Per-lane decode state of one span (the symbols that START in [entry, limit), relative bit positions).
+struct Span {
 	LaneReader br;
-	br.seek(words, entry);
-	uint32_t o = 0, nm = 0, fl = 0;
-	detail = 0;
-	while (br.pos < limit) {
-		// state at the start of the symbol, restored when the symbol does not fit the lane's caps
-		const uint64_t sbb = br.bb;
-		const uint32_t sbc = br.bc, swi = br.widx, spos = br.pos;
-		const uint32_t e = lane_decode_sym(br, sh.lit, kLitRoot, sh.lit_sorted, sh.lit_c, 0);
-		const uint32_t k = (e >> 4) & 15;
-		if (k == K_LIT) {
-			if (br.pos > end_rel) { fl |= F_OVERRUN; br.pos = spos; break; }
-			if (o + 1 > (uint32_t)kLaneOutCap) { br.bb = sbb; br.bc = sbc; br.widx = swi; br.pos = spos; break; }
-			if (FINAL) win[obase + o] = (uint8_t)(e >> 16);
-			++o;
-			continue;
-		}
-		if (k == K_LEN) {
-			uint32_t len = e >> 16;
-			const uint32_t xb = (e >> 8) & 15;
-			if (xb) len += br.get(xb);
-			const uint32_t de = lane_decode_sym(br, sh.dist, kDistRoot, sh.dist_sorted, sh.dist_c, 1);
-			const uint32_t dk = (de >> 4) & 15;
-			if (dk != K_DIST) {
-				if (br.pos > end_rel) fl |= F_OVERRUN;
-				else { fl |= F_ERR; detail = dk == K_ILLEGAL ? D_REP_DIST : D_CODELEN0; }
-				br.pos = spos;
-				break;
-			}
-			uint32_t dist = de >> 16;
-			const uint32_t dxb = (de >> 8) & 15;
-			if (dxb) dist += br.get(dxb);
-			if (br.pos > end_rel) { fl |= F_OVERRUN; br.pos = spos; break; }
-			if (o + len > (uint32_t)kLaneOutCap || nm >= (uint32_t)kMList) { br.bb = sbb; br.bc = sbc; br.widx = swi; br.pos = spos; break; }
-			if (FINAL) ml[nm] = make_uint2((obase + o) | (len << 16), dist);
-			++nm;
-			o += len;
-			continue;
-		}
-		if (k == K_EOB) {
-			if (br.pos > end_rel) { fl |= F_OVERRUN; br.pos = spos; }
-			else fl |= F_EOB;
-			break;
-		}
-		if (br.pos > end_rel || spos + 15 > end_rel) fl |= F_OVERRUN; // diagnosed from bits past the end of the input
-		else { fl |= F_ERR; detail = k == K_ILLEGAL ? D_REP_LEN : D_CODELEN0; }
-		br.pos = spos;
-		break;
+	uint32_t o, nm, fl, det;
+};
+
+// Decodes ONE symbol of the span.  Returns true while the lane should keep going.  The callers drive it in a
+// warp-synchronous loop (all lanes step together and re-converge every iteration) -- a per-lane `while` loop leaves the
+// 32 lanes diverged for the whole span, which ncu showed as 3.6 active threads per instruction.
+// FINAL = false: counts only.  FINAL = true: literals go to the ring at output position obase + o, back-references
+// to ml[0 .. nm).
+template <bool FINAL>
+__device__ __forceinline__ bool span_step(const InfShared &sh, Span &s, uint32_t limit, uint32_t end_rel, uint8_t *win,
+                                          uint32_t obase, uint2 *ml) {
+	LaneReader &br = s.br;
+	if (br.pos >= limit) return false;
+	// state at the start of the symbol, restored when the symbol does not fit the lane's caps
+	const uint64_t sbb = br.bb;
+	const uint32_t sbc = br.bc, swi = br.widx, spos = br.pos;
+	const uint32_t e = lane_decode_sym(br, sh.lit, kLitRoot, sh.lit_sorted, sh.lit_c, 0);
+	const uint32_t k = (e >> 4) & 15;
+	if (k == K_LIT) {
+		if (br.pos > end_rel) { s.fl |= F_OVERRUN; br.pos = spos; return false; }
+		if (s.o + 1 > (uint32_t)kLaneOutCap) { br.bb = sbb; br.bc = sbc; br.widx = swi; br.pos = spos; return false; }
+		if (FINAL) win[(obase + s.o) & (uint32_t)(kRing - 1)] = (uint8_t)(e >> 16);
+		++s.o;
+		return true;
 	}
-	out = o;
-	nmatch = nm;
-	flags = fl;
-	return br.pos;
+	if (k == K_LEN) {
+		uint32_t len = e >> 16;
+		const uint32_t xb = (e >> 8) & 15;
+		if (xb) len += br.get(xb);
+		const uint32_t de = lane_decode_sym(br, sh.dist, kDistRoot, sh.dist_sorted, sh.dist_c, 1);
+		const uint32_t dk = (de >> 4) & 15;
+		if (dk != K_DIST) {
+			if (br.pos > end_rel || spos + 48 > end_rel) s.fl |= F_OVERRUN;
+			else { s.fl |= F_ERR; s.det = dk == K_ILLEGAL ? D_REP_DIST : D_CODELEN0; }
+			br.pos = spos;
+			return false;
+		}
+		uint32_t dist = de >> 16;
+		const uint32_t dxb = (de >> 8) & 15;
+		if (dxb) dist += br.get(dxb);
+		if (br.pos > end_rel) { s.fl |= F_OVERRUN; br.pos = spos; return false; }
+		if (s.o + len > (uint32_t)kLaneOutCap || s.nm >= (uint32_t)kMList) { br.bb = sbb; br.bc = sbc; br.widx = swi; br.pos = spos; return false; }
+		if (FINAL) ml[s.nm] = make_uint2(obase + s.o, len | (dist << 16));
+		++s.nm;
+		s.o += len;
+		return true;
+	}
+	if (k == K_EOB) {
+		if (br.pos > end_rel) { s.fl |= F_OVERRUN; br.pos = spos; }
+		else s.fl |= F_EOB;
+		return false;
+	}
+	if (br.pos > end_rel || spos + 15 > end_rel) s.fl |= F_OVERRUN; // diagnosed from bits past the end of the input
+	else { s.fl |= F_ERR; s.det = k == K_ILLEGAL ? D_REP_LEN : D_CODELEN0; }
+	br.pos = spos;
+	return false;
 }
 
 __global__ void __launch_bounds__(32)
@@ -343,6 +341,8 @@ __global__ void __launch_bounds__(32)
 	br.consumed = 0;
 	const uint64_t total_bits = 8ull * br.nbytes;
 
+	for (int i = lane; i < kRing / 16; i += 32) reinterpret_cast<uint4 *>(rd.ring)[i] = make_uint4(0, 0, 0, 0); // fresh window = zeros
+	__syncwarp();
 	uint64_t opos = 0; // bytes produced (uniform across the warp)
 	int st = B200Z_OK; // lane 0 authoritative until broadcast
 	int detail = 0;
@@ -451,7 +451,11 @@ __global__ void __launch_bounds__(32)
 			else if (opos + stored_len > cap) st = B200Z_E_NOMEM;
 			if (st != B200Z_OK) break;
 			const uint8_t *src = in + in_off[stream] + ipos;
-			for (uint32_t i = lane; i < stored_len; i += 32) dst[opos + i] = src[i];
+			for (uint32_t i = lane; i < stored_len; i += 32) {
+				const uint8_t v = src[i];
+				dst[opos + i] = v;
+				rd.ring[(uint32_t)(opos + i) & (uint32_t)(kRing - 1)] = v;
+			}
 			opos += stored_len;
 			bitpos = 8ull * (ipos + stored_len);
 		} else {
@@ -478,9 +482,26 @@ __global__ void __launch_bounds__(32)
 				uint32_t exitp = entry, obytes = 0, nmatch = 0, flags = 0, det = 0;
 				bool changed = true, dead = false;
 				for (int it = 0; it < 34; it++) {
+					Span sp;
+					bool act = changed && !dead;
 					if (changed) {
-						if (dead) { exitp = entry; obytes = 0; nmatch = 0; flags = F_DEAD; }
-						else exitp = decode_span<false>(sh, rd.in, entry, limit, end_rel, nullptr, 0, nullptr, obytes, nmatch, flags, det);
+						sp.o = 0;
+						sp.nm = 0;
+						sp.fl = dead ? (uint32_t)F_DEAD : 0u;
+						sp.det = 0;
+						sp.br.pos = entry;
+						if (act) sp.br.seek(rd.in, entry);
+					}
+					while (__any_sync(0xffffffffu, act)) {
+						if (act) act = span_step<false>(sh, sp, limit, end_rel, nullptr, 0, nullptr);
+						__syncwarp();
+					}
+					if (changed) {
+						exitp = sp.br.pos;
+						obytes = sp.o;
+						nmatch = sp.nm;
+						flags = sp.fl;
+						det = sp.det;
 					}
 					const uint32_t pe = __shfl_up_sync(0xffffffffu, exitp, 1);
 					const uint32_t pf = __shfl_up_sync(0xffffffffu, flags, 1);
@@ -507,61 +528,52 @@ __global__ void __launch_bounds__(32)
 				const uint32_t ldet = __shfl_sync(0xffffffffu, det, lastlane);
 				const uint32_t lexit = __shfl_sync(0xffffffffu, exitp, lastlane);
 				if (opos + round_out > cap) { st = B200Z_E_NOMEM; break; }
-				const uint32_t pad = (uint32_t)(opos & 15); // keep the window congruent to the output mod 16
-				const uint32_t seg0 = pad + incl - obytes;
-				if (lane <= lastlane && obytes) {
-					uint32_t o2, n2, f2, d2;
-					decode_span<true>(sh, rd.in, entry, limit, end_rel, rd.out, seg0, rd.mlist[lane], o2, n2, f2, d2);
-				}
-				__syncwarp();
-				// ---- resolve back-references inside the window (multi-round) ------------------------------------
+				const uint32_t obase = (uint32_t)opos + incl - obytes; // this lane's first output position (low 32 bits)
 				{
-					uint32_t cur = 0;
-					const uint32_t seg1 = seg0 + obytes;
-					for (int it = 0; it < 33; it++) {
-						const bool pending = cur < nmatch;
-						const uint32_t pmask = __ballot_sync(0xffffffffu, pending);
-						if (!pmask) break;
-						const int first = __ffs(pmask) - 1;
-						const uint32_t mypos = pending ? (rd.mlist[lane][cur].x & 0xFFFFu) : seg1;
-						const uint32_t F = __shfl_sync(0xffffffffu, mypos, first); // every byte before F is final
-						while (cur < nmatch) {
-							const uint2 m = rd.mlist[lane][cur];
-							const uint32_t mo = m.x & 0xFFFFu, mlen = m.x >> 16, mdist = m.y;
-							// source bytes live in [mo - mdist, mo); positions below `pad` are earlier rounds (global)
-							const int64_t slo = (int64_t)mo - (int64_t)mdist;
-							const int64_t shi = slo + (int64_t)(mlen < mdist ? mlen : mdist);
-							const bool ready = (F >= seg0) || shi <= (int64_t)F || slo >= (int64_t)seg0;
-							if (!ready) break;
-							for (uint32_t k2 = 0; k2 < mlen; k2++) {
-								const int64_t si = slo + (int64_t)(k2 < mdist ? k2 : k2 % mdist);
-								uint8_t v;
-								if (si >= (int64_t)pad) v = rd.out[si];
-								else {
-									const int64_t gi = (int64_t)opos + (si - (int64_t)pad);
-									v = gi >= 0 ? dst[gi] : (uint8_t)0;
-								}
-								rd.out[mo + k2] = v;
-							}
-							++cur;
-						}
+					Span sp;
+					bool act = lane <= lastlane && obytes != 0;
+					sp.o = 0;
+					sp.nm = 0;
+					sp.fl = 0;
+					sp.det = 0;
+					sp.br.pos = entry;
+					if (act) sp.br.seek(rd.in, entry);
+					while (__any_sync(0xffffffffu, act)) {
+						if (act) act = span_step<true>(sh, sp, limit, end_rel, rd.ring, obase, rd.mlist[lane]);
 						__syncwarp();
 					}
 				}
 				__syncwarp();
-				// ---- flush the window: bytes [pad, pad + round_out) -> dst[opos ..) -------------------------------
+				// ---- back-references, in stream order, each copied by the whole warp (OutputWindow.Repeat :63-92) ----
+				// All sources are in the ring (distance <= 32768 < ring size - round size); byte k comes from source byte
+				// k mod distance, which only reads bytes that were final before this match.
+				for (int l = 0; l <= lastlane; l++) {
+					const uint32_t nm = __shfl_sync(0xffffffffu, nmatch, l);
+					for (uint32_t i = 0; i < nm; i++) {
+						const uint2 m = rd.mlist[l][i];
+						const uint32_t mo = m.x, mlen = m.y & 0xFFFFu, mdist = m.y >> 16;
+						const uint32_t sbase = mo - mdist;
+						if (mdist >= mlen) {
+							for (uint32_t k2 = lane; k2 < mlen; k2 += 32)
+								rd.ring[(mo + k2) & (uint32_t)(kRing - 1)] = rd.ring[(sbase + k2) & (uint32_t)(kRing - 1)];
+						} else {
+							for (uint32_t k2 = lane; k2 < mlen; k2 += 32)
+								rd.ring[(mo + k2) & (uint32_t)(kRing - 1)] = rd.ring[(sbase + k2 % mdist) & (uint32_t)(kRing - 1)];
+						}
+						__syncwarp();
+					}
+				}
+				// ---- flush the round: ring[opos .. opos + round_out) -> dst, 16-byte vectors where aligned ------------
 				{
-					const uint32_t b0 = pad, b1 = pad + round_out;
-					const uint32_t v0 = (b0 + 15) & ~15u, v1 = b1 & ~15u;
-					uint8_t *d0 = dst + opos - pad; // d0 + i is the destination of window byte i; 16-byte aligned
+					const uint64_t b0 = opos, b1 = opos + round_out;
+					const uint64_t v0 = (b0 + 15) & ~15ull, v1 = b1 & ~15ull;
 					if (v0 < v1) {
-						for (uint32_t i = b0 + lane; i < v0; i += 32) d0[i] = rd.out[i];
-						const uint4 *sv = reinterpret_cast<const uint4 *>(rd.out);
-						uint4 *dv = reinterpret_cast<uint4 *>(d0);
-						for (uint32_t i = (v0 >> 4) + lane; i < (v1 >> 4); i += 32) dv[i] = sv[i];
-						for (uint32_t i = v1 + lane; i < b1; i += 32) d0[i] = rd.out[i];
+						for (uint64_t i = b0 + lane; i < v0; i += 32) dst[i] = rd.ring[(uint32_t)i & (uint32_t)(kRing - 1)];
+						for (uint64_t i = v0 + 16ull * lane; i < v1; i += 512)
+							*reinterpret_cast<uint4 *>(dst + i) = *reinterpret_cast<const uint4 *>(rd.ring + ((uint32_t)i & (uint32_t)(kRing - 1)));
+						for (uint64_t i = v1 + lane; i < b1; i += 32) dst[i] = rd.ring[(uint32_t)i & (uint32_t)(kRing - 1)];
 					} else {
-						for (uint32_t i = b0 + lane; i < b1; i += 32) d0[i] = rd.out[i];
+						for (uint64_t i = b0 + lane; i < b1; i += 32) dst[i] = rd.ring[(uint32_t)i & (uint32_t)(kRing - 1)];
 					}
 				}
 				opos += round_out;

@@ -92,6 +92,7 @@ extern "C" int model_deflate(const uint8_t *data, uint32_t n, int level, int str
 	carry.last_top = 0;
 	uint32_t total = 0;
 	int max_iters = 0;
+	long sum_iters = 0, n_rounds = 0;
 	for (uint32_t base = 0; base < n; base += kRound) {
 		ParseCarry entry[32], ex[32];
 		uint32_t cnt[32];
@@ -126,6 +127,8 @@ extern "C" int model_deflate(const uint8_t *data, uint32_t n, int level, int str
 			if (!any) break;
 		}
 		if (it > max_iters) max_iters = it;
+		sum_iters += it + 1;
+		++n_rounds;
 		uint32_t off = total;
 		for (int l = 0; l < 32; l++) {
 			ParseCarry c = entry[l];
@@ -147,7 +150,7 @@ extern "C" int model_deflate(const uint8_t *data, uint32_t n, int level, int str
 		}
 		total = off;
 	}
-	if (getenv("B200Z_MODEL_VERBOSE")) fprintf(stderr, "parse: max propagation iterations %d\n", max_iters);
+	if (getenv("B200Z_MODEL_VERBOSE")) fprintf(stderr, "parse: max propagation iterations %d, mean runs per round %.2f over %ld rounds\n", max_iters, n_rounds ? (double)sum_iters / n_rounds : 0.0, n_rounds);
 	size_t nfull = total / kBlockSyms;
 	const bool ended_full = !flush_then_finish && total > 0 && (total % kBlockSyms) == 0 && !carry.st.prevAvail;
 	size_t nblocks;
