@@ -524,16 +524,32 @@ struct BlockPlan {
 // freqs are the literal (286) and distance (30) histograms with EOB already counted; extra_bits as tallied by
 // TallyDist (:894-916).  Outputs code lengths / codes for the block's chosen trees and, for dynamic blocks, the
 // header bit string into hdr_words (zeroed by the caller, >= kHdrWords words).  scratch >= kTreeScratchInts ints.
+// plan_block() = build_tree(lit) + build_tree(dist) + plan_block_finish(); the kernel runs the two tree builds on two
+// threads at once and then calls plan_block_finish() on one of them.
+B200Z_HDN void plan_block_finish(const int *lit_freqs, const int *dist_freqs, int extra_bits, int stored_ok, int storedLength,
+                                 int lastBlock, int lit_nc, const int *lit_blc, int dist_nc, const int *dist_blc, uint8_t *lit_len,
+                                 uint16_t *lit_codes, uint8_t *dist_len, uint16_t *dist_codes, uint32_t *hdr_words, int *scratch,
+                                 BlockPlan &plan);
+
 B200Z_HDN void plan_block(const int *lit_freqs, const int *dist_freqs, int extra_bits, int stored_ok, int storedLength,
                           int lastBlock, uint8_t *lit_len, uint16_t *lit_codes, uint8_t *dist_len, uint16_t *dist_codes,
                           uint32_t *hdr_words, int *scratch, BlockPlan &plan) {
+	int lit_blc[15], dist_blc[15];
+	int lit_nc = build_tree(lit_freqs, kLiteralNum, 257, 15, lit_len, lit_blc, scratch);
+	int dist_nc = build_tree(dist_freqs, kDistNum, 1, 15, dist_len, dist_blc, scratch);
+	plan_block_finish(lit_freqs, dist_freqs, extra_bits, stored_ok, storedLength, lastBlock, lit_nc, lit_blc, dist_nc, dist_blc,
+	                  lit_len, lit_codes, dist_len, dist_codes, hdr_words, scratch, plan);
+}
+
+B200Z_HDN void plan_block_finish(const int *lit_freqs, const int *dist_freqs, int extra_bits, int stored_ok, int storedLength,
+                                 int lastBlock, int lit_nc, const int *lit_blc, int dist_nc, const int *dist_blc, uint8_t *lit_len,
+                                 uint16_t *lit_codes, uint8_t *dist_len, uint16_t *dist_codes, uint32_t *hdr_words, int *scratch,
+                                 BlockPlan &plan) {
 	const int BL_ORDER[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
-	int lit_blc[15], dist_blc[15], bl_blc[7];
+	int bl_blc[7];
 	int bl_freqs[kBitlenNum];
 	uint8_t bl_len[kBitlenNum];
 	uint16_t bl_codes[kBitlenNum];
-	int lit_nc = build_tree(lit_freqs, kLiteralNum, 257, 15, lit_len, lit_blc, scratch);
-	int dist_nc = build_tree(dist_freqs, kDistNum, 1, 15, dist_len, dist_blc, scratch);
 	for (int i = 0; i < kBitlenNum; i++) bl_freqs[i] = 0;
 	walk_code_lengths(lit_len, lit_nc, [&](int s) { bl_freqs[s]++; }, [&](int, int) {});
 	walk_code_lengths(dist_len, dist_nc, [&](int s) { bl_freqs[s]++; }, [&](int, int) {});

@@ -35,10 +35,16 @@ __device__ __forceinline__ uint32_t same_hash_mask(uint32_t h, bool valid, int l
 	return valid ? eq : (1u << lane);
 }
 
+constexpr int kLinkChunk = 2048;                 // positions staged per cp.async group
+constexpr int kLinkBuf = kLinkChunk + 32;        // + the 2 look-ahead bytes, rounded to 16
+constexpr int kLinksSmem = 65536 + 2 * kLinkBuf;
+
 __global__ void __launch_bounds__(32) k_links(const uint8_t *__restrict__ in, uint16_t *__restrict__ link,
                                               const int64_t *__restrict__ in_off, const int64_t *__restrict__ in_len,
                                               const int2 *__restrict__ run_desc) {
-	extern __shared__ uint16_t head[]; // 32768 entries
+	extern __shared__ __align__(16) uint8_t lsm[];
+	uint16_t *head = reinterpret_cast<uint16_t *>(lsm); // 32768 entries
+	uint8_t *buf = lsm + 65536;                          // two staging buffers of kLinkBuf bytes
 	const int lane = threadIdx.x;
 	const int2 rd = run_desc[blockIdx.x];
 	const uint32_t n = (uint32_t)in_len[rd.x];
@@ -48,62 +54,62 @@ __global__ void __launch_bounds__(32) k_links(const uint8_t *__restrict__ in, ui
 	const uint32_t run_end = (n - start > (uint32_t)kRun) ? start + kRun : n;
 	const uint32_t warm = start >= 32768u ? start - 32768u : 0u;
 	for (int i = lane; i < 16384; i += 32) reinterpret_cast<uint32_t *>(head)[i] = 0;
-	__syncwarp();
 	uint32_t winbase = warm;
-	// Each lane keeps the next 16 steps' bytes in registers-free form: one 32-bit load covers bytes p..p+3 of a step, so
-	// the hash needs no shuffles; loads for step k+2 are issued while step k is processed (software pipeline, depth 2).
-	auto load3 = [&](uint32_t base) -> uint32_t {
-		// bytes at base+lane, +1, +2 packed little endian; positions beyond n read as 0 (those lanes are invalid anyway)
-		const uint32_t p = base + lane;
-		uint32_t v = 0;
-		if (p + 2 < n) {
-			v = (uint32_t)data[p] | ((uint32_t)data[p + 1] << 8) | ((uint32_t)data[p + 2] << 16);
+	// The step loop is a serial dependency chain through the head table, so nothing in it may wait on global memory:
+	// the input is staged 2 KiB ahead with cp.async (double buffered).  The slot has 16 bytes of slack behind n and
+	// chunk bases are multiples of 2048, so 16-byte copies that straddle n stay inside the allocation.
+	auto stage = [&](uint32_t cb, int which) {
+		if (cb < run_end) {
+			const uint32_t lim = (n + 15u) & ~15u; // never read past the slot's slack
+			for (uint32_t o = 16u * lane; o < (uint32_t)kLinkBuf; o += 512u)
+				if (cb + o < lim) __pipeline_memcpy_async(buf + which * kLinkBuf + o, data + cb + o, 16);
 		}
-		return v;
+		__pipeline_commit();
 	};
-	uint32_t w0 = load3(warm), w1 = load3(warm + 32);
-	// hash and same-hash mask of the step about to be processed are computed one step ahead
-	bool valid = warm + lane + 2 < n;
-	uint32_t h = hash3(w0 & 0xFF, (w0 >> 8) & 0xFF, (w0 >> 16) & 0xFF);
-	uint32_t mask = same_hash_mask(h, valid, lane);
-	for (uint32_t base = warm; base < run_end; base += 32) {
-		if (base + 32 - winbase > 65535u) {
-			for (int i = lane; i < 16384; i += 32) {
-				uint32_t v = reinterpret_cast<uint32_t *>(head)[i];
-				uint32_t lo = v & 0xFFFFu, hi = v >> 16;
-				lo = lo > 32768u ? lo - 32768u : 0u;
-				hi = hi > 32768u ? hi - 32768u : 0u;
-				reinterpret_cast<uint32_t *>(head)[i] = lo | (hi << 16);
+	stage(warm, 0);
+	int which = 0;
+	for (uint32_t cb = warm; cb < run_end; cb += kLinkChunk, which ^= 1) {
+		stage(cb + kLinkChunk, which ^ 1);
+		__pipeline_wait_prior(1);
+		__syncwarp();
+		const uint8_t *cbuf = buf + which * kLinkBuf;
+		const uint32_t cend = (run_end - cb > (uint32_t)kLinkChunk) ? cb + kLinkChunk : run_end;
+		for (uint32_t base = cb; base < cend; base += 32) {
+			if (base + 32 - winbase > 65535u) {
+				// re-base the 16-bit entries exactly like SlideWindow (DeflaterEngine.cs:441-462)
+				for (int i = lane; i < 16384; i += 32) {
+					uint32_t v = reinterpret_cast<uint32_t *>(head)[i];
+					uint32_t lo = v & 0xFFFFu, hi = v >> 16;
+					lo = lo > 32768u ? lo - 32768u : 0u;
+					hi = hi > 32768u ? hi - 32768u : 0u;
+					reinterpret_cast<uint32_t *>(head)[i] = lo | (hi << 16);
+				}
+				winbase += 32768u;
+				__syncwarp();
 			}
-			winbase += 32768u;
+			const uint32_t p = base + lane;
+			const uint32_t o = p - cb;
+			const bool valid = p + 2 < n; // InsertString only while lookahead >= MIN_MATCH (DeflaterEngine.cs:782, :819)
+			const uint32_t h = hash3(cbuf[o], cbuf[o + 1], cbuf[o + 2]);
+			const uint32_t mask = same_hash_mask(h, valid, lane);
+			const uint32_t lower = mask & ((1u << lane) - 1u);
+			uint32_t q = 0xFFFFFFFFu;
+			if (valid) {
+				if (lower) q = base + (31 - __clz(lower));
+				else {
+					const uint32_t v = head[h];
+					if (v) q = winbase + v - 1;
+				}
+			}
 			__syncwarp();
-		}
-		const uint32_t p = base + lane;
-		const uint32_t lower = mask & ((1u << lane) - 1u);
-		// table read for this step (InsertString only while lookahead >= MIN_MATCH, DeflaterEngine.cs:782, :819)
-		uint32_t v = 0;
-		if (valid && !lower) v = head[h];
-		// ... and while that is in flight: next step's hash + mask, and the loads of the step after it
-		const uint32_t w2 = load3(base + 64);
-		const bool nvalid = base + 32 + lane + 2 < n;
-		const uint32_t nh = hash3(w1 & 0xFF, (w1 >> 8) & 0xFF, (w1 >> 16) & 0xFF);
-		const uint32_t nmask = same_hash_mask(nh, nvalid, lane);
-		uint32_t q = 0xFFFFFFFFu;
-		if (valid) {
-			if (lower) q = base + (31 - __clz(lower));
-			else if (v) q = winbase + v - 1;
+			if (valid && (mask >> lane) == 1u) head[h] = (uint16_t)(p - winbase + 1);
+			__syncwarp();
+			if (p >= start && p < run_end) {
+				const uint32_t d = (q != 0xFFFFFFFFu) ? p - q : 0u;
+				lnk[p] = (d <= (uint32_t)kMaxDist) ? (uint16_t)d : (uint16_t)0;
+			}
 		}
 		__syncwarp();
-		if (valid && (mask >> lane) == 1u) head[h] = (uint16_t)(p - winbase + 1);
-		__syncwarp();
-		if (p >= start && p < run_end) {
-			uint32_t d = (q != 0xFFFFFFFFu) ? p - q : 0u;
-			lnk[p] = (d <= (uint32_t)kMaxDist) ? (uint16_t)d : (uint16_t)0;
-		}
-		w1 = w2;
-		h = nh;
-		mask = nmask;
-		valid = nvalid;
 	}
 }
 
@@ -366,7 +372,8 @@ __global__ void __launch_bounds__(32)
 // ------------------------------------------------------------------------------------------------
 // K4: per-block histograms, the reference's Huffman construction and the block type decision.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+constexpr int kPlanThreads = 64;
+__global__ void __launch_bounds__(kPlanThreads)
     k_plan(const uint32_t *__restrict__ sym, const int64_t *__restrict__ in_off, const int64_t *__restrict__ in_len,
            const uint32_t *__restrict__ nsyms, const uint32_t *__restrict__ nblocks, const uint32_t *__restrict__ blk_off,
            const int32_t *__restrict__ blk_desc, const uint32_t *__restrict__ blk_start, const uint32_t *__restrict__ blk_ptop,
@@ -375,6 +382,8 @@ __global__ void __launch_bounds__(256)
 	__shared__ int s_dist[kDistNum];
 	__shared__ int s_extra;
 	__shared__ int s_scratch[kTreeScratchInts];
+	__shared__ int s_scratch2[9 * kDistNum];
+	__shared__ int s_lit_blc[15], s_dist_blc[15], s_nc[2];
 	__shared__ BlockTables s_tab;
 	const int g = blockIdx.x;
 	const int stream = blk_desc[g];
@@ -405,8 +414,13 @@ __global__ void __launch_bounds__(256)
 	for (int o = 16; o > 0; o >>= 1) extra += __shfl_down_sync(0xffffffffu, extra, o);
 	if ((threadIdx.x & 31) == 0 && extra) atomicAdd(&s_extra, extra);
 	__syncthreads();
+	if (threadIdx.x == 0) s_lit[256] += 1; // FlushBlock: literalTree.freqs[EOF_SYMBOL]++ (:790)
+	__syncthreads();
+	// the two big trees are independent: build them on two warps at once
+	if (threadIdx.x == 0) s_nc[0] = build_tree(s_lit, kLiteralNum, 257, 15, s_tab.lit_len, s_lit_blc, s_scratch);
+	if (threadIdx.x == 32) s_nc[1] = build_tree(s_dist, kDistNum, 1, 15, s_tab.dist_len, s_dist_blc, s_scratch2);
+	__syncthreads();
 	if (threadIdx.x == 0) {
-		s_lit[256] += 1; // FlushBlock: literalTree.freqs[EOF_SYMBOL]++ (:790)
 		const uint32_t *bstart = blk_start + blk_off[stream];
 		const uint32_t *bptop = blk_ptop + blk_off[stream];
 		const uint32_t byte_start = bstart[b];
@@ -416,8 +430,8 @@ __global__ void __launch_bounds__(256)
 		const long long storedOffset = (long long)byte_start + 1 - 32768ll * (long long)slides_done(bptop[b]);
 		const int last = (b + 1 == nb) && end_mode == B200Z_END_FINISH;
 		BlockPlan plan;
-		plan_block(s_lit, s_dist, s_extra, storedOffset >= 0, (int)byte_len, last, s_tab.lit_len, s_tab.lit_codes,
-		           s_tab.dist_len, s_tab.dist_codes, s_tab.hdr, s_scratch, plan);
+		plan_block_finish(s_lit, s_dist, s_extra, storedOffset >= 0, (int)byte_len, last, s_nc[0], s_lit_blc, s_nc[1], s_dist_blc,
+		                  s_tab.lit_len, s_tab.lit_codes, s_tab.dist_len, s_tab.dist_codes, s_tab.hdr, s_scratch, plan);
 		BlockMeta m;
 		m.byte_start = byte_start;
 		m.byte_len = byte_len;
@@ -664,7 +678,7 @@ int deflate_plan_build(b200z_plan *p) {
 	if (!ck_tiles.empty())
 		B200Z_CUDA(cudaMemcpy(ws.at<CkTile>(p->o_ck_desc), ck_tiles.data(), sizeof(CkTile) * ck_tiles.size(),
 		                      cudaMemcpyHostToDevice));
-	B200Z_CUDA(cudaFuncSetAttribute(k_links, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+	B200Z_CUDA(cudaFuncSetAttribute(k_links, cudaFuncAttributeMaxDynamicSharedMemorySize, kLinksSmem));
 	B200Z_CUDA(cudaFuncSetAttribute(k_match, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileData + 2 * 2 * kTile));
 	p->launches = 6 + (p->wrap != B200Z_WRAP_RAW ? 3 : 0); // + one memset node
 	return B200Z_OK;
@@ -692,7 +706,7 @@ int deflate_plan_run(b200z_plan *p, const uint8_t *d_in, uint8_t *d_out, int64_t
 	p->mark(s, "memset");
 	B200Z_CUDA(cudaMemsetAsync(d_out, 0, (size_t)p->out_bytes, s));
 	p->mark(s, "k_links");
-	if (p->n_runs) k_links<<<p->n_runs, 32, 65536, s>>>(d_in, link, in_off, in_len, ws.at<int2>(p->o_run_desc));
+	if (p->n_runs) k_links<<<p->n_runs, 32, kLinksSmem, s>>>(d_in, link, in_off, in_len, ws.at<int2>(p->o_run_desc));
 	p->mark(s, "k_match");
 	if (p->n_tiles)
 		k_match<<<p->n_tiles, kMatchThreads, kTileData + 2 * 2 * kTile, s>>>(d_in, link, mt, in_off, in_len,
@@ -701,7 +715,7 @@ int deflate_plan_run(b200z_plan *p, const uint8_t *d_in, uint8_t *d_out, int64_t
 	k_parse<<<n, 32, kParseSmem, s>>>(d_in, link, mt, sym, in_off, in_len, nsyms, nblocks, blk_off, blk_start, blk_ptop, lp,
 	                                  p->strategy, p->end_mode);
 	p->mark(s, "k_plan");
-	k_plan<<<p->n_blkmax, 256, 0, s>>>(sym, in_off, in_len, nsyms, nblocks, blk_off, blk_desc, blk_start, blk_ptop, meta,
+	k_plan<<<p->n_blkmax, kPlanThreads, 0, s>>>(sym, in_off, in_len, nsyms, nblocks, blk_off, blk_desc, blk_start, blk_ptop, meta,
 	                                   tables, p->end_mode);
 	p->mark(s, "k_scan");
 	k_scan<<<(n + 127) / 128, 128, 0, s>>>(n, nblocks, blk_off, meta, d_out, out_off, out_cap, d_out_len, d_status,
