@@ -191,129 +191,100 @@ constexpr int kMList = 64;                       // back-references a lane may r
 struct __align__(16) InfRound {
 	uint32_t in[kInWords];
 	uint8_t ring[kRing];     // ring[pos & 65535] = output byte `pos`; doubles as OutputWindow (Streams/OutputWindow.cs:15-23)
-	uint2 mlist[32][kMList]; // x = output position (low 32 bits), y = len | dist << 16
+	uint2 mlist[32 * kMList]; // flat, in stream order: x = output position (low 32 bits), y = len | dist << 16
 };
 constexpr int kInfSmem = (int)(sizeof(InfShared) + sizeof(InfRound));
 
 enum { F_EOB = 1, F_ERR = 2, F_OVERRUN = 4, F_DEAD = 8 };
 
-// bit reader over the round's staged words; positions are relative to the round's first staged bit
-struct LaneReader {
-	const uint32_t *w;
-	uint64_t bb;
-	uint32_t bc, widx, pos;
-	__device__ __forceinline__ void seek(const uint32_t *words, uint32_t rel) {
-		w = words;
-		widx = rel >> 5;
-		bb = 0;
-		bc = 0;
-		pos = rel;
-		refill();
-		const uint32_t sk = rel & 31;
-		bb >>= sk;
-		bc -= sk;
-	}
-	__device__ __forceinline__ void refill() {
-		if (bc <= 32) {
-			const uint32_t v = widx < (uint32_t)kInWords ? w[widx] : 0u;
-			++widx;
-			bb |= (uint64_t)v << bc;
-			bc += 32;
-		}
-	}
-	__device__ __forceinline__ void drop(uint32_t n) {
-		bb >>= n;
-		bc -= n;
-		pos += n;
-	}
-	__device__ __forceinline__ uint32_t get(uint32_t n) {
-		refill();
-		const uint32_t v = (uint32_t)bb & ((1u << n) - 1u);
-		drop(n);
-		return v;
-	}
-};
+// The round's input lives in shared memory, so a lane needs no bit buffer: the 32 bits that start at any bit position
+// are two words and a funnel shift away.  The decode state of a lane is just its bit position.
+__device__ __forceinline__ uint32_t peek32(const uint32_t *w, uint32_t pos) {
+	const uint32_t i = pos >> 5;
+	return __funnelshift_r(w[i], w[i + 1], pos & 31u); // i + 1 < kInWords is guaranteed by the staging slack
+}
 
-__device__ __forceinline__ uint32_t lane_decode_sym(LaneReader &br, const uint32_t *tab, int R, const uint16_t *sorted,
-                                                    const Canon &cn, int kind) {
-	br.refill();
-	uint32_t e = tab[(uint32_t)br.bb & ((1u << R) - 1u)];
+// decodes one symbol of a tree at `v` (the next 32 stream bits); returns the entry and the code length in nb
+__device__ __forceinline__ uint32_t lane_decode_sym(uint32_t v, const uint32_t *tab, int R, const uint16_t *sorted,
+                                                    const Canon &cn, int kind, uint32_t &nb) {
+	const uint32_t e = tab[v & ((1u << R) - 1u)];
 	const uint32_t k = (e >> 4) & 15;
-	if (k != K_LONG) {
-		if (k != K_INVALID) br.drop(e & 15);
-		return e;
-	}
-	const uint32_t x = __brev((uint32_t)br.bb) >> 17;
+	nb = e & 15;
+	if (k != K_LONG) return e;
+	const uint32_t x = __brev(v) >> 17; // next 15 stream bits, first bit most significant
 	for (int L = R + 1; L <= 15; L++) {
 		const uint32_t c = x >> (15 - L);
 		const uint32_t idx = c - cn.first[L];
 		if (idx < cn.count[L]) {
 			const uint32_t s = sorted[cn.offs[L] + idx];
-			br.drop(L);
+			nb = (uint32_t)L;
 			return kind == 0 ? litlen_entry(s, L) : dist_entry(s, L);
 		}
 	}
+	nb = 0;
 	return 0;
 }
 
 // Per-lane decode state of one span (the symbols that START in [entry, limit), relative bit positions).
 struct Span {
-	LaneReader br;
-	uint32_t o, nm, fl, det;
+	uint32_t pos, o, nm, fl, det;
 };
 
 // Decodes ONE symbol of the span.  Returns true while the lane should keep going.  The callers drive it in a
 // warp-synchronous loop (all lanes step together and re-converge every iteration) -- a per-lane `while` loop leaves the
 // 32 lanes diverged for the whole span, which ncu showed as 3.6 active threads per instruction.
 // FINAL = false: counts only.  FINAL = true: literals go to the ring at output position obase + o, back-references
-// to ml[0 .. nm).
+// to ml[0 .. nm).  A symbol that does not fit the lane's caps, or that needs bits past the end of the input, is not
+// consumed (pos stays at its first bit).
 template <bool FINAL>
-__device__ __forceinline__ bool span_step(const InfShared &sh, Span &s, uint32_t limit, uint32_t end_rel, uint8_t *win,
-                                          uint32_t obase, uint2 *ml) {
-	LaneReader &br = s.br;
-	if (br.pos >= limit) return false;
-	// state at the start of the symbol, restored when the symbol does not fit the lane's caps
-	const uint64_t sbb = br.bb;
-	const uint32_t sbc = br.bc, swi = br.widx, spos = br.pos;
-	const uint32_t e = lane_decode_sym(br, sh.lit, kLitRoot, sh.lit_sorted, sh.lit_c, 0);
+__device__ __forceinline__ bool span_step(const InfShared &sh, const uint32_t *words, Span &s, uint32_t limit,
+                                          uint32_t end_rel, uint8_t *win, uint32_t obase, uint2 *ml) {
+	const uint32_t spos = s.pos;
+	if (spos >= limit) return false;
+	uint32_t v = peek32(words, spos);
+	uint32_t nb;
+	const uint32_t e = lane_decode_sym(v, sh.lit, kLitRoot, sh.lit_sorted, sh.lit_c, 0, nb);
 	const uint32_t k = (e >> 4) & 15;
 	if (k == K_LIT) {
-		if (br.pos > end_rel) { s.fl |= F_OVERRUN; br.pos = spos; return false; }
-		if (s.o + 1 > (uint32_t)kLaneOutCap) { br.bb = sbb; br.bc = sbc; br.widx = swi; br.pos = spos; return false; }
+		if (spos + nb > end_rel) { s.fl |= F_OVERRUN; return false; }
+		if (s.o + 1 > (uint32_t)kLaneOutCap) return false;
 		if (FINAL) win[(obase + s.o) & (uint32_t)(kRing - 1)] = (uint8_t)(e >> 16);
 		++s.o;
+		s.pos = spos + nb;
 		return true;
 	}
 	if (k == K_LEN) {
-		uint32_t len = e >> 16;
+		// length code (<= 15 bits) + extra (<= 5) fit the first peek; the distance code + extra (<= 28) a second one
 		const uint32_t xb = (e >> 8) & 15;
-		if (xb) len += br.get(xb);
-		const uint32_t de = lane_decode_sym(br, sh.dist, kDistRoot, sh.dist_sorted, sh.dist_c, 1);
+		const uint32_t len = (e >> 16) + ((v >> nb) & ((1u << xb) - 1u));
+		uint32_t pos = spos + nb + xb;
+		v = peek32(words, pos);
+		uint32_t dnb;
+		const uint32_t de = lane_decode_sym(v, sh.dist, kDistRoot, sh.dist_sorted, sh.dist_c, 1, dnb);
 		const uint32_t dk = (de >> 4) & 15;
 		if (dk != K_DIST) {
-			if (br.pos > end_rel || spos + 48 > end_rel) s.fl |= F_OVERRUN;
+			if (pos + 15 > end_rel) s.fl |= F_OVERRUN; // diagnosed from bits past the end of the input
 			else { s.fl |= F_ERR; s.det = dk == K_ILLEGAL ? D_REP_DIST : D_CODELEN0; }
-			br.pos = spos;
 			return false;
 		}
-		uint32_t dist = de >> 16;
 		const uint32_t dxb = (de >> 8) & 15;
-		if (dxb) dist += br.get(dxb);
-		if (br.pos > end_rel) { s.fl |= F_OVERRUN; br.pos = spos; return false; }
-		if (s.o + len > (uint32_t)kLaneOutCap || s.nm >= (uint32_t)kMList) { br.bb = sbb; br.bc = sbc; br.widx = swi; br.pos = spos; return false; }
+		const uint32_t dist = (de >> 16) + ((v >> dnb) & ((1u << dxb) - 1u));
+		pos += dnb + dxb;
+		if (pos > end_rel) { s.fl |= F_OVERRUN; return false; }
+		if (s.o + len > (uint32_t)kLaneOutCap || s.nm >= (uint32_t)kMList) return false;
 		if (FINAL) ml[s.nm] = make_uint2(obase + s.o, len | (dist << 16));
 		++s.nm;
 		s.o += len;
+		s.pos = pos;
 		return true;
 	}
 	if (k == K_EOB) {
-		if (br.pos > end_rel) { s.fl |= F_OVERRUN; br.pos = spos; }
-		else s.fl |= F_EOB;
+		if (spos + nb > end_rel) s.fl |= F_OVERRUN;
+		else { s.fl |= F_EOB; s.pos = spos + nb; }
 		return false;
 	}
-	if (br.pos > end_rel || spos + 15 > end_rel) s.fl |= F_OVERRUN; // diagnosed from bits past the end of the input
+	if (spos + 15 > end_rel) s.fl |= F_OVERRUN; // diagnosed from bits past the end of the input
 	else { s.fl |= F_ERR; s.det = k == K_ILLEGAL ? D_REP_LEN : D_CODELEN0; }
-	br.pos = spos;
 	return false;
 }
 
@@ -489,15 +460,14 @@ __global__ void __launch_bounds__(32)
 						sp.nm = 0;
 						sp.fl = dead ? (uint32_t)F_DEAD : 0u;
 						sp.det = 0;
-						sp.br.pos = entry;
-						if (act) sp.br.seek(rd.in, entry);
+						sp.pos = entry;
 					}
 					while (__any_sync(0xffffffffu, act)) {
-						if (act) act = span_step<false>(sh, sp, limit, end_rel, nullptr, 0, nullptr);
+						if (act) act = span_step<false>(sh, rd.in, sp, limit, end_rel, nullptr, 0, nullptr);
 						__syncwarp();
 					}
 					if (changed) {
-						exitp = sp.br.pos;
+						exitp = sp.pos;
 						obytes = sp.o;
 						nmatch = sp.nm;
 						flags = sp.fl;
@@ -529,6 +499,13 @@ __global__ void __launch_bounds__(32)
 				const uint32_t lexit = __shfl_sync(0xffffffffu, exitp, lastlane);
 				if (opos + round_out > cap) { st = B200Z_E_NOMEM; break; }
 				const uint32_t obase = (uint32_t)opos + incl - obytes; // this lane's first output position (low 32 bits)
+				// back-references go to one flat list in stream order: lane offsets from the counted pass
+				uint32_t mincl = nmatch;
+				for (int o = 1; o < 32; o <<= 1) {
+					const uint32_t t = __shfl_up_sync(0xffffffffu, mincl, o);
+					if (lane >= o) mincl += t;
+				}
+				const uint32_t total_m = __shfl_sync(0xffffffffu, mincl, 31);
 				{
 					Span sp;
 					bool act = lane <= lastlane && obytes != 0;
@@ -536,31 +513,60 @@ __global__ void __launch_bounds__(32)
 					sp.nm = 0;
 					sp.fl = 0;
 					sp.det = 0;
-					sp.br.pos = entry;
-					if (act) sp.br.seek(rd.in, entry);
+					sp.pos = entry;
+					uint2 *ml = rd.mlist + (mincl - nmatch);
 					while (__any_sync(0xffffffffu, act)) {
-						if (act) act = span_step<true>(sh, sp, limit, end_rel, rd.ring, obase, rd.mlist[lane]);
+						if (act) act = span_step<true>(sh, rd.in, sp, limit, end_rel, rd.ring, obase, ml);
 						__syncwarp();
 					}
 				}
 				__syncwarp();
-				// ---- back-references, in stream order, each copied by the whole warp (OutputWindow.Repeat :63-92) ----
+				// ---- back-references in stream order (OutputWindow.Repeat :63-92) ------------------------------------
+				// Four matches per step, each copied by a group of 8 lanes, when none of them reads bytes another match
+				// of the same step writes; otherwise the step's matches are copied one after another by the whole warp.
 				// All sources are in the ring (distance <= 32768 < ring size - round size); byte k comes from source byte
 				// k mod distance, which only reads bytes that were final before this match.
-				for (int l = 0; l <= lastlane; l++) {
-					const uint32_t nm = __shfl_sync(0xffffffffu, nmatch, l);
-					for (uint32_t i = 0; i < nm; i++) {
-						const uint2 m = rd.mlist[l][i];
+				{
+					const int grp = lane >> 3, sub = lane & 7;
+					for (uint32_t k0 = 0; k0 < total_m; k0 += 4) {
+						const uint32_t mi = k0 + (uint32_t)grp;
+						const bool have = mi < total_m;
+						const uint2 m = have ? rd.mlist[mi] : make_uint2(0u, 0u);
 						const uint32_t mo = m.x, mlen = m.y & 0xFFFFu, mdist = m.y >> 16;
-						const uint32_t sbase = mo - mdist;
-						if (mdist >= mlen) {
-							for (uint32_t k2 = lane; k2 < mlen; k2 += 32)
-								rd.ring[(mo + k2) & (uint32_t)(kRing - 1)] = rd.ring[(sbase + k2) & (uint32_t)(kRing - 1)];
+						const uint32_t step_lo = __shfl_sync(0xffffffffu, mo, 0); // first destination byte of this step
+						// a later match of the step depends on the step if its source reaches step_lo or beyond
+						const uint32_t shi = mo - mdist + (mlen < mdist ? mlen : mdist);
+						const bool dep = have && grp > 0 && (int32_t)(shi - step_lo) > 0;
+						if (!__any_sync(0xffffffffu, dep)) {
+							if (have) {
+								const uint32_t sbase = mo - mdist;
+								if (mdist >= mlen) {
+									for (uint32_t k2 = sub; k2 < mlen; k2 += 8)
+										rd.ring[(mo + k2) & (uint32_t)(kRing - 1)] = rd.ring[(sbase + k2) & (uint32_t)(kRing - 1)];
+								} else {
+									for (uint32_t k2 = sub; k2 < mlen; k2 += 8)
+										rd.ring[(mo + k2) & (uint32_t)(kRing - 1)] = rd.ring[(sbase + k2 % mdist) & (uint32_t)(kRing - 1)];
+								}
+							}
+							__syncwarp();
 						} else {
-							for (uint32_t k2 = lane; k2 < mlen; k2 += 32)
-								rd.ring[(mo + k2) & (uint32_t)(kRing - 1)] = rd.ring[(sbase + k2 % mdist) & (uint32_t)(kRing - 1)];
+							for (int g = 0; g < 4; g++) {
+								const uint32_t gmo = __shfl_sync(0xffffffffu, mo, g * 8);
+								const uint32_t gy = __shfl_sync(0xffffffffu, m.y, g * 8);
+								const bool ghave = __shfl_sync(0xffffffffu, (int)have, g * 8) != 0;
+								if (ghave) {
+									const uint32_t glen = gy & 0xFFFFu, gdist = gy >> 16, gs = gmo - gdist;
+									if (gdist >= glen) {
+										for (uint32_t k2 = lane; k2 < glen; k2 += 32)
+											rd.ring[(gmo + k2) & (uint32_t)(kRing - 1)] = rd.ring[(gs + k2) & (uint32_t)(kRing - 1)];
+									} else {
+										for (uint32_t k2 = lane; k2 < glen; k2 += 32)
+											rd.ring[(gmo + k2) & (uint32_t)(kRing - 1)] = rd.ring[(gs + k2 % gdist) & (uint32_t)(kRing - 1)];
+									}
+								}
+								__syncwarp();
+							}
 						}
-						__syncwarp();
 					}
 				}
 				// ---- flush the round: ring[opos .. opos + round_out) -> dst, 16-byte vectors where aligned ------------
