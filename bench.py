@@ -112,21 +112,27 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def cpu_sample(threads, n_def, n_inf, d_inputs, comp_inf, inf_caps):
-    """times the oracle (C++ restatement of the reference) on a bounded sample of the same workload"""
-    import oracle_lib as O
-    dsel = [a.tobytes() for a in d_inputs[:n_def]]
-    t0 = time.perf_counter()
-    O.batch(0, dsel, level=6, threads=threads)
-    t1 = time.perf_counter()
-    O.batch(1, comp_inf[:n_inf], threads=threads, out_caps=[c + 64 for c in inf_caps[:n_inf]])
-    t2 = time.perf_counter()
-    ub = sum(len(b) for b in dsel) + sum(inf_caps[:n_inf])
-    return {"value": ub / (t2 - t0) / 1e9, "deflate_gbs": sum(len(b) for b in dsel) / (t1 - t0) / 1e9,
-            "inflate_gbs": sum(inf_caps[:n_inf]) / (t2 - t1) / 1e9, "seconds": t2 - t0}
+class CpuSample:
+    """the oracle (C++ restatement of the reference) on a bounded sample of the same workload; only the C calls are timed"""
+
+    def __init__(self, n_def, n_inf, d_inputs, comp_inf, inf_caps):
+        import oracle_lib as O
+        self.dj = O.BatchJob(0, [a.tobytes() for a in d_inputs[:n_def]], level=6)
+        self.ij = O.BatchJob(1, comp_inf[:n_inf], out_caps=[c + 64 for c in inf_caps[:n_inf]])
+        self.ud = int(self.dj.lens.sum())
+        self.ui = int(sum(inf_caps[:n_inf]))
+
+    def run(self, threads):
+        t0 = time.perf_counter()
+        self.dj.run(threads)
+        t1 = time.perf_counter()
+        self.ij.run(threads)
+        t2 = time.perf_counter()
+        return {"value": (self.ud + self.ui) / (t2 - t0) / 1e9, "deflate_gbs": self.ud / (t1 - t0) / 1e9,
+                "inflate_gbs": self.ui / (t2 - t1) / 1e9, "seconds": t2 - t0}
 
 
-def run_reference(args, rank, world):
+def run_reference(args, rank, world, out):
     """--impl reference: the reference's CPU algorithm (oracle port; no .NET on the box) on all host threads"""
     if rank != 0:
         return
@@ -139,11 +145,12 @@ def run_reference(args, rank, world):
     d, t = make_inputs(0, n_def, n_inf, min(threads, 32))
     comp = O.batch(0, [a.tobytes() for a in t], level=6, threads=threads)
     caps = [a.size for a in t]
+    job = CpuSample(n_def, n_inf, d, comp, caps)
     for _ in range(args.warmup):
-        cpu_sample(threads, n_def, n_inf, d, comp, caps)
+        job.run(threads)
     times, last = [], None
     for _ in range(args.steps):
-        last = cpu_sample(threads, n_def, n_inf, d, comp, caps)
+        last = job.run(threads)
         times.append(last["seconds"])
     ub = n_def * SZ_DEFLATE + n_inf * SZ_INFLATE
     val = ub * len(times) / sum(times) / 1e9
@@ -156,10 +163,21 @@ def run_reference(args, rank, world):
                              "note": "C++ restatement of SharpZipLib's managed path; no .NET runtime on the box"},
             "e2e": {"value": val, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "deflate_gbs": last["deflate_gbs"], "inflate_gbs": last["inflate_gbs"], "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
+def _claim_stdout():
+    """Libraries (NCCL's version banner, torchrun children) may print to fd 1; the contract is ONE JSON line on stdout.
+    Everything else is redirected to stderr and the JSON line is written to the saved descriptor."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    return os.fdopen(saved, "w")
 
 
 def main():
+    out = _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -171,7 +189,7 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
-        run_reference(args, rank, world)
+        run_reference(args, rank, world, out)
         return
 
     import torch
@@ -311,7 +329,7 @@ def main():
     cpu = None
     if rank == 0:
         ns_d, ns_i = min(n_def, 128), min(n_inf, 64)
-        r = cpu_sample(1, ns_d, ns_i, d_np, comp, [a.size for a in t_np])
+        r = CpuSample(ns_d, ns_i, d_np, comp, [a.size for a in t_np]).run(1)
         cpu = {"value": r["value"], "unit": "GB/s", "cores": 1, "kind": "port",
                "sample": "%d x 256 KiB deflate L6 + %d x 1 MiB inflate, single thread, %.1f s" % (ns_d, ns_i, r["seconds"]),
                "deflate_gbs": r["deflate_gbs"], "inflate_gbs": r["inflate_gbs"], "host_cores": ncpu,
@@ -337,7 +355,8 @@ def main():
             "gpu_launches": int(dplan.launches + iplan.launches),
             "clocks": clocks,
         }
-        print(json.dumps(line), flush=True)
+        out.write(json.dumps(line) + "\n")
+        out.flush()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -693,10 +693,16 @@ int b200z_deflater_deflate(void *h, uint8_t *out, int32_t cap, int32_t *produced
 		d->header_done = true;
 		if (d->finishing) {
 			if (d->flushed_once) {
-				// Flush() already emitted every block + the sync padding; Finish adds the final empty static block
-				// (FlushBlock on an empty buffer: header 011 + EOB 0000000 = value 3 in 10 bits, DeflaterEngine.cs:750-768)
-				d->tail.put(d->pending, 3, 10);
-				d->tail.align(d->pending);
+				// Flush() already emitted every block + the sync padding; Finish adds the final empty block:
+				// levels 1-9 FlushBlock on an empty buffer = static header 011 + EOB 0000000 = value 3 in 10 bits
+				// (DeflaterEngine.cs:750-768); level 0 an empty stored block 01 00 00 FF FF (:614-649)
+				if (d->level == 0) {
+					const uint8_t e5[5] = {1, 0, 0, 0xFF, 0xFF};
+					d->pending.insert(d->pending.end(), e5, e5 + 5);
+				} else {
+					d->tail.put(d->pending, 3, 10);
+					d->tail.align(d->pending);
+				}
 			} else {
 				int rc = deflater_run_device(d, B200Z_END_FINISH);
 				if (rc) return rc;

@@ -273,6 +273,248 @@ B200Z_HD uint32_t parse_run(ParseCarry &c, uint32_t seg_end, uint32_t n, const L
 	return cnt;
 }
 
+// ---- levels 1-4: DeflaterEngine.DeflateFast (:651-739) -----------------------------------------------
+// In the greedy levels the hash chains depend on the parse (positions inside a match longer than max_lazy are not
+// inserted, :699-715), so a stream is parsed serially, with the reference's own data structures: head[]/prev[] hold
+// 16-bit WINDOW indices, SlideWindow (:441-462) re-bases them, and the zero sentinel, the FillWindow schedule (:366-400)
+// and the "strstart > 65274" slide test (:668) are reproduced literally.  The 64 KiB window itself is not copied:
+// window[w] is input byte  w - 1 + 32768 * slides.  One thread per stream; all streams of a batch run concurrently.
+//
+// Call pattern emulated: SetInput(all) -> Deflate() until IsNeedingInput (DeflaterOutputStream.Write :506-510) -> Finish()
+// (or Flush()) -> drain.  emit(sym) receives the tallied symbols; block(byte_start, stored_ok) is called for every
+// FlushBlock with the block's first input byte and whether storedOffset >= 0 (trap T4).
+struct FastEngine {
+	uint32_t n;           // input length
+	const uint8_t *in;    // input bytes
+	uint16_t *head;       // 32768 entries, zeroed by the caller
+	uint16_t *prev;       // 32768 entries, zeroed by the caller
+	int strstart, blockStart, lookahead, matchStart, matchLen, ins_h;
+	uint32_t slides;      // number of SlideWindow calls so far
+	uint32_t inputOff;    // bytes handed to the window so far
+	uint32_t nsym;        // symbols tallied in the current block
+	int coop;             // 1: never slide inside the engine, report kFeNeedSlide instead (the kernel slides warp-wide)
+};
+constexpr int kFeFalse = 0, kFeTrue = 1, kFeNeedSlide = 2;
+
+B200Z_HD uint32_t fe_win(const FastEngine &e, int w) { return (uint32_t)e.in[(uint32_t)(w - 1) + 32768u * e.slides]; }
+
+B200Z_HD void fe_init(FastEngine &e, const uint8_t *in, uint32_t n, uint16_t *head, uint16_t *prev) {
+	e.n = n;
+	e.in = in;
+	e.head = head;
+	e.prev = prev;
+	e.strstart = e.blockStart = 1; // DeflaterEngine.cs:91-93
+	e.lookahead = 0;
+	e.matchStart = 0;
+	e.matchLen = kMinMatch - 1;
+	e.ins_h = 0;
+	e.slides = 0;
+	e.inputOff = 0;
+	e.nsym = 0;
+	e.coop = 0;
+}
+
+B200Z_HD void fe_update_hash(FastEngine &e) { e.ins_h = (int)((fe_win(e, e.strstart) << 5) ^ fe_win(e, e.strstart + 1)); } // :402-410
+
+B200Z_HD int fe_insert_string(FastEngine &e) { // :417-439
+	const int hash = (int)(((uint32_t)e.ins_h << 5) ^ fe_win(e, e.strstart + 2)) & 0x7FFF;
+	const uint16_t match = e.head[hash];
+	e.prev[e.strstart & 32767] = match;
+	e.head[hash] = (uint16_t)e.strstart;
+	e.ins_h = hash;
+	return (int)match;
+}
+
+B200Z_HD void fe_slide_scalars(FastEngine &e) { // :443-446
+	e.matchStart -= kWSize;
+	e.strstart -= kWSize;
+	e.blockStart -= kWSize;
+	e.slides += 1;
+}
+B200Z_HDN void fe_slide(FastEngine &e) { // :441-462
+	fe_slide_scalars(e);
+	for (int i = 0; i < 32768; ++i) {
+		const int m = e.head[i];
+		e.head[i] = (uint16_t)(m >= kWSize ? m - kWSize : 0);
+	}
+	for (int i = 0; i < 32768; ++i) {
+		const int m = e.prev[i];
+		e.prev[i] = (uint16_t)(m >= kWSize ? m - kWSize : 0);
+	}
+}
+
+// returns false (and does nothing) when a slide is due and the engine runs in cooperative mode
+B200Z_HD bool fe_fill_window(FastEngine &e) { // :366-400
+	if (e.strstart >= kWSize + kMaxDist) {
+		if (e.coop) return false;
+		fe_slide(e);
+	}
+	if (e.lookahead < kMaxMatch + kMinMatch + 1 && e.inputOff < e.n) {
+		uint32_t more = (uint32_t)(2 * kWSize - e.lookahead - e.strstart);
+		if (more > e.n - e.inputOff) more = e.n - e.inputOff;
+		e.inputOff += more;
+		e.lookahead += (int)more;
+	}
+	if (e.lookahead >= kMinMatch) fe_update_hash(e);
+	return true;
+}
+
+B200Z_HDN bool fe_find_longest_match(FastEngine &e, int curMatch, const LevelParams &lp) { // :474-612
+	const int scan0 = e.strstart;
+	const int maxlen = e.lookahead < kMaxMatch ? e.lookahead : kMaxMatch;
+	const int scanMax = scan0 + maxlen - 1;
+	const int limit = scan0 - kMaxDist > 0 ? scan0 - kMaxDist : 0;
+	int chainLength = lp.chain;
+	const int niceLength = lp.nice < e.lookahead ? lp.nice : e.lookahead;
+	if (e.matchLen < kMinMatch - 1) e.matchLen = kMinMatch - 1;
+	if (scan0 + e.matchLen > scanMax) return false;
+	uint32_t scan_end1 = fe_win(e, scan0 + e.matchLen - 1), scan_end = fe_win(e, scan0 + e.matchLen);
+	if (e.matchLen >= lp.good) chainLength >>= 2;
+	do {
+		const int match = curMatch;
+		if (fe_win(e, match + e.matchLen) == scan_end && fe_win(e, match + e.matchLen - 1) == scan_end1 &&
+		    fe_win(e, match) == fe_win(e, scan0) && fe_win(e, match + 1) == fe_win(e, scan0 + 1)) {
+			int l = 2;
+			while (l < maxlen && fe_win(e, match + l) == fe_win(e, scan0 + l)) ++l;
+			if (l > e.matchLen) {
+				e.matchStart = curMatch;
+				e.matchLen = l;
+				if (e.matchLen >= niceLength) break;
+				scan_end1 = fe_win(e, scan0 + l - 1);
+				scan_end = fe_win(e, scan0 + l);
+			}
+		}
+	} while ((curMatch = (int)e.prev[curMatch & 32767]) > limit && 0 != --chainLength);
+	return e.matchLen >= kMinMatch;
+}
+
+// DeflateFast (:651-739).  Returns the reference's `progress` value (kFeFalse / kFeTrue), or kFeNeedSlide in cooperative
+// mode: nothing has been done at the current loop top then, and calling again after the slide resumes transparently.
+template <class EmitFn, class BlockFn>
+B200Z_HDN int fe_deflate_fast(FastEngine &e, bool flush, bool finish, const LevelParams &lp, int strategy, EmitFn emit,
+                               BlockFn block) {
+	const int kMinLookahead = kMaxMatch + kMinMatch + 1;
+	if (e.lookahead < kMinLookahead && !flush) return kFeFalse;
+	while (e.lookahead >= kMinLookahead || flush) {
+		if (e.lookahead == 0) {
+			// we are flushing everything
+			block((uint32_t)(e.blockStart - 1) + 32768u * e.slides, e.blockStart >= 0, finish);
+			e.nsym = 0;
+			e.blockStart = e.strstart;
+			return kFeFalse;
+		}
+		if (e.strstart > 2 * kWSize - kMinLookahead) {
+			if (e.coop) return kFeNeedSlide;
+			fe_slide(e);
+		}
+		int hashHead;
+		if (e.lookahead >= kMinMatch && (hashHead = fe_insert_string(e)) != 0 && strategy != 2 &&
+		    e.strstart - hashHead <= kMaxDist && fe_find_longest_match(e, hashHead, lp)) {
+			emit(sym_match((uint32_t)e.matchLen, (uint32_t)(e.strstart - e.matchStart)));
+			const bool full = ++e.nsym >= (uint32_t)kBlockSyms;
+			e.lookahead -= e.matchLen;
+			if (e.matchLen <= lp.lazy && e.lookahead >= kMinMatch) {
+				while (--e.matchLen > 0) {
+					++e.strstart;
+					fe_insert_string(e);
+				}
+				++e.strstart;
+			} else {
+				e.strstart += e.matchLen;
+				if (e.lookahead >= kMinMatch - 1) fe_update_hash(e);
+			}
+			e.matchLen = kMinMatch - 1;
+			if (!full) continue;
+		} else {
+			// no match found
+			emit(sym_lit(fe_win(e, e.strstart)));
+			++e.nsym;
+			++e.strstart;
+			--e.lookahead;
+		}
+		if (e.nsym >= (uint32_t)kBlockSyms) {
+			const bool lastBlock = finish && e.lookahead == 0;
+			block((uint32_t)(e.blockStart - 1) + 32768u * e.slides, e.blockStart >= 0, lastBlock);
+			e.nsym = 0;
+			e.blockStart = e.strstart;
+			return lastBlock ? kFeFalse : kFeTrue;
+		}
+	}
+	return kFeTrue;
+}
+
+// Whole stream, call pattern above.  end_mode: B200Z_END_* (0 finish, 1 flush then finish, 2 flush).
+template <class EmitFn, class BlockFn>
+B200Z_HDN void fe_run(FastEngine &e, const LevelParams &lp, int strategy, int end_mode, EmitFn emit, BlockFn block) {
+	// BUSY_STATE: Deflater.Deflate -> engine.Deflate(false, false) until it reports "needs input" (:104-137)
+	for (;;) {
+		fe_fill_window(e);
+		if (fe_deflate_fast(e, false, false, lp, strategy, emit, block) == kFeFalse) break;
+	}
+	// Flush() or Finish(): flush = true, finish as requested; canFlush holds because the input is exhausted
+	const bool finish = end_mode == 0;
+	for (;;) {
+		fe_fill_window(e);
+		if (fe_deflate_fast(e, true, finish, lp, strategy, emit, block) == kFeFalse) break;
+	}
+	// (end_mode 1: the sync padding and the final empty static block that Finish() adds are appended by k_scan)
+}
+
+// ---- level 0: DeflaterEngine.DeflateStored (:614-649) --------------------------------------------------
+// Only block boundaries are decided here (pure integer bookkeeping); block(byte_start, length, last) is called for
+// every FlushStoredBlock.  Same call pattern as fe_run.  Sync-flush padding is skipped at level 0 (Deflater.cs:488).
+template <class BlockFn>
+inline void stored_run(uint32_t n, int end_mode, BlockFn block) { // host only: run when a plan is built
+	int strstart = 1, blockStart = 1, lookahead = 0;
+	uint32_t slides = 0, inputOff = 0;
+	const int kMaxBlock = 65531; // DeflaterConstants.MAX_BLOCK_SIZE
+	auto fill = [&]() {
+		if (strstart >= kWSize + kMaxDist) {
+			strstart -= kWSize;
+			blockStart -= kWSize;
+			slides += 1;
+		}
+		if (lookahead < kMaxMatch + kMinMatch + 1 && inputOff < n) {
+			uint32_t more = (uint32_t)(2 * kWSize - lookahead - strstart);
+			if (more > n - inputOff) more = n - inputOff;
+			inputOff += more;
+			lookahead += (int)more;
+		}
+	};
+	auto stored = [&](bool flush, bool finish) -> bool {
+		if (!flush && lookahead == 0) return false;
+		strstart += lookahead;
+		lookahead = 0;
+		int storedLength = strstart - blockStart;
+		if (storedLength >= kMaxBlock || (blockStart < kWSize && storedLength >= kMaxDist) || flush) {
+			bool lastBlock = finish;
+			if (storedLength > kMaxBlock) {
+				storedLength = kMaxBlock;
+				lastBlock = false;
+			}
+			block((uint32_t)(blockStart - 1) + 32768u * slides, (uint32_t)storedLength, lastBlock);
+			blockStart += storedLength;
+			return !(lastBlock || storedLength == 0);
+		}
+		return true;
+	};
+	for (;;) {
+		fill();
+		if (!stored(false, false)) break;
+	}
+	const bool finish = end_mode == 0;
+	for (;;) {
+		fill();
+		if (!stored(inputOff == n, finish)) break;
+	}
+	if (end_mode == 1) {
+		for (;;) {
+			fill();
+			if (!stored(inputOff == n, true)) break;
+		}
+	}
+}
+
 // ---- DeflaterHuffman.cs helpers ----------------------------------------------------------------
 B200Z_HD int lcode(int len_m3) { // Lcode :932-946 (argument is length - 3)
 	if (len_m3 == 255) return 285;

@@ -370,6 +370,118 @@ __global__ void __launch_bounds__(32)
 }
 
 // ------------------------------------------------------------------------------------------------
+// Levels 1-4: DeflateFast.  The chains depend on the parse, so a stream is parsed serially by lane 0 with the
+// reference's own head[]/prev[] tables (shared memory, 128 KiB); SlideWindow's table sweep is done by the whole warp.
+// All streams of the batch run concurrently (one warp each).  Symbols and block cuts feed k_plan / k_scan / k_emit.
+// ------------------------------------------------------------------------------------------------
+constexpr int kFastSmem = 2 * 32768 * 2;
+
+__global__ void __launch_bounds__(32)
+    k_fast(const uint8_t *__restrict__ in, uint32_t *__restrict__ sym, const int64_t *__restrict__ in_off,
+           const int64_t *__restrict__ in_len, uint32_t *__restrict__ nsyms, uint32_t *__restrict__ nblocks,
+           const uint32_t *__restrict__ blk_off, uint32_t *__restrict__ blk_start, uint32_t *__restrict__ blk_ptop,
+           LevelParams lp, int strategy, int end_mode) {
+	extern __shared__ __align__(16) uint8_t fsm[];
+	uint16_t *head = reinterpret_cast<uint16_t *>(fsm);
+	uint16_t *prev = head + 32768;
+	const int lane = threadIdx.x;
+	const int stream = blockIdx.x;
+	const uint32_t n = (uint32_t)in_len[stream];
+	const int64_t off = in_off[stream];
+	uint32_t *sout = sym + off;
+	uint32_t *bstart = blk_start + blk_off[stream];
+	uint32_t *bptop = blk_ptop + blk_off[stream];
+	for (int i = lane; i < 32768; i += 32) reinterpret_cast<uint32_t *>(fsm)[i] = 0;
+	__syncwarp();
+	FastEngine e;
+	fe_init(e, in + off, n, head, prev);
+	e.coop = 1;
+	uint32_t total = 0, nblk = 0;
+	int phase = 0;           // 0: BUSY_STATE drain, 1: Flush()/Finish()
+	bool in_deflate = false; // re-entering DeflateFast after a cooperative slide must not run FillWindow again
+	const bool finish = end_mode == B200Z_END_FINISH;
+	for (;;) {
+		int r = kFeTrue;
+		if (lane == 0) {
+			bool filled = true;
+			if (!in_deflate) filled = fe_fill_window(e);
+			if (!filled) {
+				r = kFeNeedSlide;
+			} else {
+				in_deflate = true;
+				r = fe_deflate_fast(
+				    e, phase == 1, phase == 1 && finish, lp, strategy, [&](uint32_t s2) { sout[total++] = s2; },
+				    [&](uint32_t start, bool ok, bool) {
+					    bstart[nblk] = start;
+					    bptop[nblk] = ok ? 0xFFFFFFFEu : 0xFFFFFFFFu; // storedOffset sign decided by the engine (trap T4)
+					    ++nblk;
+				    });
+				if (r != kFeNeedSlide) in_deflate = false;
+			}
+		}
+		r = __shfl_sync(0xffffffffu, r, 0);
+		if (r == kFeNeedSlide) {
+			// SlideWindow (DeflaterEngine.cs:441-462): scalars by lane 0, both tables by the warp
+			if (lane == 0) fe_slide_scalars(e);
+			for (int i = lane; i < 32768; i += 32) { // 2 entries per 32-bit word, head and prev are contiguous
+				uint32_t v = reinterpret_cast<uint32_t *>(fsm)[i];
+				uint32_t lo = v & 0xFFFFu, hi = v >> 16;
+				lo = lo >= 32768u ? lo - 32768u : 0u;
+				hi = hi >= 32768u ? hi - 32768u : 0u;
+				reinterpret_cast<uint32_t *>(fsm)[i] = lo | (hi << 16);
+			}
+			__syncwarp();
+			continue;
+		}
+		if (r == kFeFalse) {
+			if (phase == 1) break;
+			phase = 1;
+		}
+	}
+	if (lane == 0) {
+		nsyms[stream] = total;
+		nblocks[stream] = nblk;
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
+// Level 0: DeflateStored.  Block boundaries are pure bookkeeping (stored_run, computed when the plan is built);
+// the kernel writes 1 header byte, LEN, ~LEN and copies the bytes (FlushStoredBlock, DeflaterHuffman.cs:766-779).
+// ------------------------------------------------------------------------------------------------
+struct StoredBlock {
+	int32_t stream;
+	uint32_t src;     // first input byte inside the stream
+	uint32_t len;
+	uint32_t last;
+	uint64_t dst;     // byte offset of the block inside the stream's output slot
+};
+
+__global__ void __launch_bounds__(256)
+    k_stored(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, const int64_t *__restrict__ in_off,
+             const int64_t *__restrict__ out_off, const StoredBlock *__restrict__ blocks) {
+	const StoredBlock b = blocks[blockIdx.x];
+	const uint8_t *src = in + in_off[b.stream] + b.src;
+	uint8_t *dst = out + out_off[b.stream] + b.dst;
+	if (threadIdx.x == 0) {
+		dst[0] = (uint8_t)(b.last ? 1 : 0); // 3 header bits (STORED_BLOCK << 1 | last) then AlignToByte
+		dst[1] = (uint8_t)b.len;
+		dst[2] = (uint8_t)(b.len >> 8);
+		dst[3] = (uint8_t)~b.len;
+		dst[4] = (uint8_t)(~b.len >> 8);
+	}
+	for (uint32_t i = threadIdx.x; i < b.len; i += blockDim.x) dst[5 + i] = src[i];
+}
+
+__global__ void k_set_results(int n, const int64_t *__restrict__ lens, int64_t *__restrict__ out_len, int32_t *__restrict__ status,
+                              int64_t *__restrict__ out_bits) {
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	out_len[i] = lens[i];
+	status[i] = B200Z_OK;
+	if (out_bits) out_bits[i] = 8 * lens[i];
+}
+
+// ------------------------------------------------------------------------------------------------
 // K4: per-block histograms, the reference's Huffman construction and the block type decision.
 // ------------------------------------------------------------------------------------------------
 constexpr int kPlanThreads = 64;
@@ -427,7 +539,8 @@ __global__ void __launch_bounds__(kPlanThreads)
 		const uint32_t n = (uint32_t)in_len[stream];
 		const uint32_t byte_len = (b + 1 < nb ? bstart[b + 1] : n) - byte_start;
 		// storedOffset is window relative and goes negative once the block start has been slid out (trap T4)
-		const long long storedOffset = (long long)byte_start + 1 - 32768ll * (long long)slides_done(bptop[b]);
+		long long storedOffset = (long long)byte_start + 1 - 32768ll * (long long)slides_done(bptop[b]);
+		if (bptop[b] >= 0xFFFFFFFEu) storedOffset = bptop[b] == 0xFFFFFFFEu ? 0 : -1; // levels 1-4: decided by k_fast
 		const int last = (b + 1 == nb) && end_mode == B200Z_END_FINISH;
 		BlockPlan plan;
 		plan_block_finish(s_lit, s_dist, s_extra, storedOffset >= 0, (int)byte_len, last, s_nc[0], s_lit_blc, s_nc[1], s_dist_blc,
@@ -603,11 +716,9 @@ __global__ void __launch_bounds__(256)
 // ------------------------------------------------------------------------------------------------
 int deflate_plan_build(b200z_plan *p) {
 	const LevelParams lp = level_params(p->level);
-	if (lp.func != 2) {
-		set_error("level %d (DeflateStored/DeflateFast) is not accelerated by this build; levels 5-9 are", p->level);
-		return B200Z_E_UNSUPPORTED;
-	}
 	const int n = p->n;
+	std::vector<StoredBlock> sblocks; // level 0 only
+	std::vector<int64_t> slens;
 	p->in_off.resize(n);
 	p->out_off.resize(n);
 	p->out_cap.resize(n);
@@ -633,6 +744,18 @@ int deflate_plan_build(b200z_plan *p) {
 		const uint32_t maxb = (uint32_t)(len / kBlockSyms) + 2;
 		for (uint32_t b = 0; b < maxb; b++) blk_desc.push_back(i);
 		nblk += maxb;
+		if (lp.func == 0) {
+			uint64_t dst = 0;
+			stored_run((uint32_t)len, p->end_mode, [&](uint32_t start, uint32_t blen, bool last) {
+				sblocks.push_back(StoredBlock{i, start, blen, last ? 1u : 0u, dst});
+				dst += 5 + (uint64_t)blen;
+			});
+			slens.push_back((int64_t)dst);
+		}
+	}
+	if (lp.func != 2) {
+		runs.clear();
+		tiles.clear();
 	}
 	blk_off[n] = nblk;
 	p->in_bytes = io;
@@ -655,9 +778,16 @@ int deflate_plan_build(b200z_plan *p) {
 	p->o_blk_ptop = ws.reserve(4ll * (nblk + 1));
 	p->o_meta = ws.reserve((int64_t)sizeof(BlockMeta) * (nblk + 1));
 	p->o_tables = ws.reserve((int64_t)sizeof(BlockTables) * (nblk + 1));
-	p->o_link = ws.reserve(2ll * io + 64);
-	p->o_mt = ws.reserve(8ll * io + 64);
-	p->o_sym = ws.reserve(4ll * io + 64);
+	if (lp.func == 2) {
+		p->o_link = ws.reserve(2ll * io + 64);
+		p->o_mt = ws.reserve(8ll * io + 64);
+	}
+	if (lp.func != 0) p->o_sym = ws.reserve(4ll * io + 64);
+	if (lp.func == 0) {
+		p->n_stored = (int)sblocks.size();
+		p->o_stored = ws.reserve((int64_t)sizeof(StoredBlock) * (sblocks.size() + 1));
+		p->o_slens = ws.reserve(8ll * (n + 1));
+	}
 	std::vector<CkTile> ck_tiles;
 	if (p->wrap != B200Z_WRAP_RAW) {
 		checksum_tiles(p->in_len.data(), n, ck_tiles, p->wrap == B200Z_WRAP_GZIP ? 0 : 1);
@@ -678,9 +808,13 @@ int deflate_plan_build(b200z_plan *p) {
 	if (!ck_tiles.empty())
 		B200Z_CUDA(cudaMemcpy(ws.at<CkTile>(p->o_ck_desc), ck_tiles.data(), sizeof(CkTile) * ck_tiles.size(),
 		                      cudaMemcpyHostToDevice));
+	if (!sblocks.empty())
+		B200Z_CUDA(cudaMemcpy(ws.at<StoredBlock>(p->o_stored), sblocks.data(), sizeof(StoredBlock) * sblocks.size(), cudaMemcpyHostToDevice));
+	if (!slens.empty()) B200Z_CUDA(cudaMemcpy(ws.at<int64_t>(p->o_slens), slens.data(), 8ll * slens.size(), cudaMemcpyHostToDevice));
+	B200Z_CUDA(cudaFuncSetAttribute(k_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, kFastSmem));
 	B200Z_CUDA(cudaFuncSetAttribute(k_links, cudaFuncAttributeMaxDynamicSharedMemorySize, kLinksSmem));
 	B200Z_CUDA(cudaFuncSetAttribute(k_match, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileData + 2 * 2 * kTile));
-	p->launches = 6 + (p->wrap != B200Z_WRAP_RAW ? 3 : 0); // + one memset node
+	p->launches = (lp.func == 2 ? 6 : (lp.func == 1 ? 4 : 2)) + (p->wrap != B200Z_WRAP_RAW ? 3 : 0); // + one memset node
 	return B200Z_OK;
 }
 
@@ -692,9 +826,9 @@ int deflate_plan_run(b200z_plan *p, const uint8_t *d_in, uint8_t *d_out, int64_t
 	const LevelParams lp = level_params(p->level);
 	const int64_t *in_off = ws.at<int64_t>(p->o_in_off), *in_len = ws.at<int64_t>(p->o_in_len);
 	const int64_t *out_off = ws.at<int64_t>(p->o_out_off), *out_cap = ws.at<int64_t>(p->o_out_cap);
-	uint16_t *link = ws.at<uint16_t>(p->o_link);
-	uint2 *mt = ws.at<uint2>(p->o_mt);
-	uint32_t *sym = ws.at<uint32_t>(p->o_sym);
+	uint16_t *link = lp.func == 2 ? ws.at<uint16_t>(p->o_link) : nullptr;
+	uint2 *mt = lp.func == 2 ? ws.at<uint2>(p->o_mt) : nullptr;
+	uint32_t *sym = lp.func != 0 ? ws.at<uint32_t>(p->o_sym) : nullptr;
 	uint32_t *nsyms = ws.at<uint32_t>(p->o_nsyms), *nblocks = ws.at<uint32_t>(p->o_nblocks);
 	uint32_t *blk_off = ws.at<uint32_t>(p->o_blk_off);
 	int32_t *blk_desc = ws.at<int32_t>(p->o_blk_desc);
@@ -703,17 +837,38 @@ int deflate_plan_run(b200z_plan *p, const uint8_t *d_in, uint8_t *d_out, int64_t
 	BlockTables *tables = ws.at<BlockTables>(p->o_tables);
 
 	p->ev_used = 0;
+	if (lp.func == 0) {
+		// level 0: stored blocks laid out when the plan was built
+		p->mark(s, "k_stored");
+		if (p->n_stored) k_stored<<<p->n_stored, 256, 0, s>>>(d_in, d_out, in_off, out_off, ws.at<StoredBlock>(p->o_stored));
+		k_set_results<<<(n + 127) / 128, 128, 0, s>>>(n, ws.at<int64_t>(p->o_slens), d_out_len, d_status, d_out_bits);
+		p->mark(s, "checksum");
+		if (p->wrap != B200Z_WRAP_RAW && d_check) {
+			int rc = checksum_launch(p->wrap == B200Z_WRAP_GZIP ? 0 : 1, d_in, in_off, in_len, n, ws.at<CkTile>(p->o_ck_desc),
+			                         p->n_ck_tiles, ws.at<unsigned long long>(p->o_ck_acc), d_check, 1, s);
+			if (rc) return rc;
+		}
+		p->mark(s, "end");
+		B200Z_CUDA(cudaGetLastError());
+		return B200Z_OK;
+	}
 	p->mark(s, "memset");
 	B200Z_CUDA(cudaMemsetAsync(d_out, 0, (size_t)p->out_bytes, s));
-	p->mark(s, "k_links");
-	if (p->n_runs) k_links<<<p->n_runs, 32, kLinksSmem, s>>>(d_in, link, in_off, in_len, ws.at<int2>(p->o_run_desc));
-	p->mark(s, "k_match");
-	if (p->n_tiles)
-		k_match<<<p->n_tiles, kMatchThreads, kTileData + 2 * 2 * kTile, s>>>(d_in, link, mt, in_off, in_len,
-		                                                                   ws.at<int2>(p->o_tile_desc), lp);
-	p->mark(s, "k_parse");
-	k_parse<<<n, 32, kParseSmem, s>>>(d_in, link, mt, sym, in_off, in_len, nsyms, nblocks, blk_off, blk_start, blk_ptop, lp,
-	                                  p->strategy, p->end_mode);
+	if (lp.func == 1) {
+		p->mark(s, "k_fast");
+		k_fast<<<n, 32, kFastSmem, s>>>(d_in, sym, in_off, in_len, nsyms, nblocks, blk_off, blk_start, blk_ptop, lp, p->strategy,
+		                                p->end_mode);
+	} else {
+		p->mark(s, "k_links");
+		if (p->n_runs) k_links<<<p->n_runs, 32, kLinksSmem, s>>>(d_in, link, in_off, in_len, ws.at<int2>(p->o_run_desc));
+		p->mark(s, "k_match");
+		if (p->n_tiles)
+			k_match<<<p->n_tiles, kMatchThreads, kTileData + 2 * 2 * kTile, s>>>(d_in, link, mt, in_off, in_len,
+			                                                                   ws.at<int2>(p->o_tile_desc), lp);
+		p->mark(s, "k_parse");
+		k_parse<<<n, 32, kParseSmem, s>>>(d_in, link, mt, sym, in_off, in_len, nsyms, nblocks, blk_off, blk_start, blk_ptop, lp,
+		                                  p->strategy, p->end_mode);
+	}
 	p->mark(s, "k_plan");
 	k_plan<<<p->n_blkmax, kPlanThreads, 0, s>>>(sym, in_off, in_len, nsyms, nblocks, blk_off, blk_desc, blk_start, blk_ptop, meta,
 	                                   tables, p->end_mode);

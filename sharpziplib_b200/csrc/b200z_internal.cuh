@@ -81,6 +81,8 @@ struct b200z_plan {
 	int64_t o_link = 0, o_mt = 0, o_sym = 0, o_nsyms = 0, o_nblocks = 0;
 	int64_t o_blk_start = 0, o_blk_ptop = 0, o_meta = 0, o_tables = 0;
 	int n_runs = 0, n_tiles = 0, n_blkmax = 0;
+	int64_t o_stored = 0, o_slens = 0; // level 0: stored-block list and per-stream output lengths
+	int n_stored = 0;
 	// inflate workspace offsets
 	int64_t o_tok = 0, o_ntok = 0, o_tok_off = 0;
 	// checksum scratch

@@ -73,24 +73,62 @@ struct Writer { // what the emit kernel does with atomicOr on zeroed 32-bit word
 extern "C" int model_deflate(const uint8_t *data, uint32_t n, int level, int strategy, int flush_then_finish,
                              uint8_t *out, uint64_t cap, uint64_t *outlen) {
 	LevelParams lp = level_params(level);
-	if (lp.func != 2) return 100; // only the lazy levels are modelled
+	std::vector<uint32_t> syms;
+	std::vector<uint32_t> blk_start(n / kBlockSyms + 3, 0), blk_ptop(n / kBlockSyms + 3, 0);
+	size_t nblocks = 0;
+	uint32_t total = 0;
+	if (lp.func == 0) {
+		// level 0: stored blocks only (each block: 3 header bits, pad, LEN, ~LEN, bytes)
+		Writer W0;
+		uint64_t bp = 0;
+		stored_run(n, flush_then_finish ? 1 : 0, [&](uint32_t start, uint32_t len, bool last) {
+			W0.put(bp, last ? 1 : 0, 3);
+			bp = (bp + 3 + 7) & ~7ull;
+			W0.put(bp, len & 0xFFFF, 16);
+			W0.put(bp + 16, (~len) & 0xFFFF, 16);
+			bp += 32;
+			for (uint32_t i = 0; i < len; i++, bp += 8) W0.put(bp, data[start + i], 8);
+		});
+		uint64_t nb0 = (bp + 7) >> 3;
+		if (nb0 > cap) return 102;
+		W0.w.resize((nb0 + 3) / 4 + 1, 0);
+		std::memcpy(out, W0.w.data(), nb0);
+		*outlen = nb0;
+		return 0;
+	}
 	std::vector<uint16_t> link;
+	std::vector<uint32_t> tabA, tabB;
+	if (lp.func == 1) {
+		// levels 1-4: the serial DeflateFast emulation (what k_fast runs, one thread per stream)
+		std::vector<uint16_t> head(32768, 0), prev(32768, 0);
+		FastEngine fe;
+		fe_init(fe, data, n, head.data(), prev.data());
+		blk_start.assign(n / kBlockSyms + 3, 0);
+		fe_run(fe, lp, strategy, flush_then_finish ? 2 : 0, [&](uint32_t sym) { syms.push_back(sym); },
+		       [&](uint32_t start, bool ok, bool last) {
+			       (void)last;
+			       blk_start[nblocks] = start;
+			       blk_ptop[nblocks] = ok ? 0xFFFFFFFEu : 0xFFFFFFFFu;
+			       ++nblocks;
+		       });
+		total = (uint32_t)syms.size();
+		goto emit_blocks;
+	}
 	model_links(data, n, link);
 	// K2: every position
-	std::vector<uint32_t> tabA(n), tabB(n);
+	tabA.resize(n);
+	tabB.resize(n);
 	for (uint32_t p = 0; p < n; p++) match_search(data, link.data(), 0u, p, n, lp, tabA[p], tabB[p]);
+	{
 	// K3 as k_parse does it: rounds of 32 segments x kSeg positions; every lane parses its segment speculatively from a
 	// clean state, entries are handed lane -> lane until nothing changes, then a final pass emits at prefix-summed offsets
 	const uint32_t kSeg = 128, kRound = 32 * kSeg;
-	std::vector<uint32_t> syms;
-	std::vector<uint32_t> blk_start(n / kBlockSyms + 3, 0), blk_ptop(n / kBlockSyms + 3, 0);
 	auto tabf = [&](uint32_t p, uint32_t &a, uint32_t &b) { a = tabA[p]; b = tabB[p]; };
 	auto bytef = [&](uint32_t q) { return (uint32_t)data[q]; };
 	auto slowf = [&](uint32_t p, uint32_t m0, uint32_t budget) { return match_search_above(data, link.data(), p, n, m0, budget); };
 	ParseCarry carry;
 	parse_init(carry.st);
 	carry.last_top = 0;
-	uint32_t total = 0;
 	int max_iters = 0;
 	long sum_iters = 0, n_rounds = 0;
 	for (uint32_t base = 0; base < n; base += kRound) {
@@ -153,7 +191,6 @@ extern "C" int model_deflate(const uint8_t *data, uint32_t n, int level, int str
 	if (getenv("B200Z_MODEL_VERBOSE")) fprintf(stderr, "parse: max propagation iterations %d, mean runs per round %.2f over %ld rounds\n", max_iters, n_rounds ? (double)sum_iters / n_rounds : 0.0, n_rounds);
 	size_t nfull = total / kBlockSyms;
 	const bool ended_full = !flush_then_finish && total > 0 && (total % kBlockSyms) == 0 && !carry.st.prevAvail;
-	size_t nblocks;
 	if (ended_full) {
 		nblocks = nfull;
 	} else {
@@ -167,6 +204,8 @@ extern "C" int model_deflate(const uint8_t *data, uint32_t n, int level, int str
 		nblocks = nfull + 1;
 	}
 	syms.resize(total);
+	}
+emit_blocks:
 	Writer W;
 	uint64_t bitpos = 0;
 	std::vector<int> scratch(9 * 286 + 64);
@@ -190,6 +229,7 @@ extern "C" int model_deflate(const uint8_t *data, uint32_t n, int level, int str
 		lit_freqs[256]++;
 		bool last = (b + 1 == nblocks) && !flush_then_finish;
 		int64_t storedOffset = (int64_t)blk_start[b] + 1 - 32768ll * (int64_t)slides_done(blk_ptop[b]);
+		if (blk_ptop[b] >= 0xFFFFFFFEu) storedOffset = blk_ptop[b] == 0xFFFFFFFEu ? 0 : -1; // fast levels: decided by the engine
 		uint8_t lit_len[kLiteralNum], dist_len[kDistNum];
 		uint16_t lit_codes[kLiteralNum], dist_codes[kDistNum];
 		uint32_t hdr[192];

@@ -81,7 +81,7 @@ def test_checksum_batch_device(z, oracle):
 
 
 # ---- deflate ---------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("level", [5, 6, 7, 8, 9])
+@pytest.mark.parametrize("level", [0, 1, 2, 3, 4, 5, 6, 7, 8, 9])
 def test_deflate_parity_small_corpus(z, oracle, level):
     names, bufs = zip(*corpus_small())
     outs, _ = z.deflate_batch(list(bufs), level=level)
@@ -141,11 +141,35 @@ def test_deflate_c3_shape_parity_and_properties(z, oracle):
     assert back == bufs and [int(u) for u in used] == [len(o) for o in outs]
 
 
-def test_unsupported_levels_fail_loudly(z):
+@pytest.mark.parametrize("level", [0, 1, 4])
+def test_deflate_fast_and_stored_levels(z, oracle, level):
+    """DeflateFast (levels 1-4) and DeflateStored (0): window slides, flush pattern, zlib wrapper, strategies."""
+    from sharpziplib_b200 import datagen
+    bufs = [datagen.silesia_mix(c, 300000 + 7777 * c, config=6).tobytes() for c in range(8)] + [bytes(250000), crafted_t8()]
+    outs, _ = z.deflate_batch(bufs, level=level)
+    assert outs == [oracle.deflate(b, level=level) for b in bufs]
+    outs, _ = z.deflate_batch(bufs[:4], level=level, end_mode=1)
+    assert outs == [oracle.deflate(b, level=level, pattern=1) for b in bufs[:4]]
+    outs, checks = z.deflate_batch(bufs[:4], level=level, wrap=1)
+    assert outs == [oracle.deflate(b, level=level, nowrap=False) for b in bufs[:4]]
+    if level:
+        for strategy in (1, 2):
+            outs, _ = z.deflate_batch(bufs[:3], level=level, strategy=strategy)
+            assert outs == [oracle.deflate(b, level=level, strategy=strategy) for b in bufs[:3]]
+
+
+def test_unsupported_sequences_fail_loudly(z):
+    d = z.Deflater(6, False)
     with pytest.raises(z.B200zUnsupported):
-        z.deflate_batch([b"hello"], level=1)
+        d.SetDictionary(b"hello hello")
+    d = z.Deflater(6, True)
+    d.SetInput(b"abc" * 100)
+    d.Flush()
+    buf = bytearray(512)
+    while d.Deflate(buf) > 0:
+        pass
     with pytest.raises(z.B200zUnsupported):
-        z.deflate_batch([b"hello"], level=0)
+        d.SetInput(b"more input after a sync flush")
 
 
 # ---- inflate ---------------------------------------------------------------------------------------------
@@ -246,7 +270,7 @@ def test_plans_on_device_tensors(z, oracle):
 
 
 # ---- streaming handles and stream adapters (the reference's own test shapes) ------------------------------
-@pytest.mark.parametrize("level", [5, 6, 9])
+@pytest.mark.parametrize("level", [0, 1, 5, 6, 9])
 @pytest.mark.parametrize("zlib_wrap", [True, False])
 def test_inflate_deflate_roundtrip_like_reference(z, oracle, level, zlib_wrap):
     """InflaterDeflaterTests.InflateDeflateZlib / NonZlib (:157-162, :226-231): 100000 random bytes,
@@ -290,11 +314,15 @@ def test_deflater_handle_members(z, oracle):
         n = df.Deflate(buf)
         out += bytes(buf[:n])
     assert out == oracle.deflate(d, level=9)
-    with pytest.raises(z.B200zUnsupported):
-        df2 = z.Deflater(1, True)
-        df2.SetInput(b"abc")
+    for lvl in (0, 1, 3):
+        df2 = z.Deflater(lvl, False)
+        df2.SetInput(d)
         df2.Finish()
-        df2.Deflate(buf)
+        out = b""
+        while not df2.IsFinished:
+            n = df2.Deflate(buf)
+            out += bytes(buf[:n])
+        assert out == oracle.deflate(d, level=lvl, nowrap=False)
 
 
 def test_inflater_handle_members(z, oracle):
