@@ -247,8 +247,10 @@ struct ParseCarry {
 	uint32_t last_top;
 };
 B200Z_HD bool carry_equal(const ParseCarry &a, const ParseCarry &b) {
-	return a.st.p == b.st.p && a.st.mlen == b.st.mlen && a.st.mstart == b.st.mstart && a.st.prevAvail == b.st.prevAvail &&
-	       a.last_top == b.last_top;
+	// matchStart is dead while matchLen < MIN_MATCH (it is only read for a pending match), so it must not keep two
+	// otherwise identical states apart -- literal runs would never look converged
+	const bool ms = (a.st.mlen < (uint32_t)kMinMatch && b.st.mlen < (uint32_t)kMinMatch) || a.st.mstart == b.st.mstart;
+	return a.st.p == b.st.p && a.st.mlen == b.st.mlen && ms && a.st.prevAvail == b.st.prevAvail && a.last_top == b.last_top;
 }
 
 // Runs the loop tops in [c.st.p, seg_end) (clipped to n).  Returns the number of symbols tallied.  With EMIT, calls

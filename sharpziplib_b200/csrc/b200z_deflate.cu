@@ -221,7 +221,8 @@ __global__ void __launch_bounds__(kMatchThreads, 1)
 // within a few symbols the hand-offs normally stop changing anything after one or two iterations.  A final pass emits
 // the symbols at prefix-summed offsets and records the block cuts (every 16384 symbols, DeflaterHuffman.cs:863).
 // ------------------------------------------------------------------------------------------------
-constexpr int kSeg = 128;
+constexpr int kSegShift = 6;
+constexpr int kSeg = 1 << kSegShift; // 64 positions per lane: 19 KiB of shared memory per warp, 11 warps per SM
 constexpr int kRound = 32 * kSeg;
 constexpr int kSegStride = kSeg + 2; // uint2 entries; +2 keeps 16-byte alignment for cp.async and staggers the banks
 constexpr int kParseDatOff = 32 * kSegStride * 8;
@@ -266,20 +267,20 @@ __global__ void __launch_bounds__(32)
 		__syncwarp();
 		// stage the round with 16-byte async copies (LDGSTS): all of them are in flight at once, no register staging
 		for (uint32_t i = 2 * lane; i + 1 < rn; i += 64)
-			__pipeline_memcpy_async(&s_tab[(i >> 7) * kSegStride + (i & (kSeg - 1))], &tab[base + i], 16);
+			__pipeline_memcpy_async(&s_tab[(i >> kSegShift) * kSegStride + (i & (kSeg - 1))], &tab[base + i], 16);
 		{
 			// bytes [base - 16, base + rn) rounded up to 16 (the input slot has 16 bytes of slack behind n)
 			const uint32_t c0 = base ? 0u : 1u, c1 = (16 + rn + 15) >> 4;
 			for (uint32_t c = c0 + lane; c < c1; c += 32) __pipeline_memcpy_async(s_dat + 16 * c, data + base - 16 + 16 * c, 16);
 		}
 		__pipeline_commit();
-		if ((rn & 1) && lane == 0) s_tab[((rn - 1) >> 7) * kSegStride + ((rn - 1) & (kSeg - 1))] = tab[base + rn - 1];
+		if ((rn & 1) && lane == 0) s_tab[((rn - 1) >> kSegShift) * kSegStride + ((rn - 1) & (kSeg - 1))] = tab[base + rn - 1];
 		__pipeline_wait_prior(0);
 		__syncwarp();
 		const uint32_t seg_end = base + (uint32_t)(lane + 1) * kSeg;
 		auto tabf = [&](uint32_t p, uint32_t &a, uint32_t &b) {
 			const uint32_t i = p - base;
-			const uint2 t = s_tab[(i >> 7) * kSegStride + (i & (kSeg - 1))];
+			const uint2 t = s_tab[(i >> kSegShift) * kSegStride + (i & (kSeg - 1))];
 			a = t.x;
 			b = t.y;
 		};

@@ -122,7 +122,7 @@ extern "C" int model_deflate(const uint8_t *data, uint32_t n, int level, int str
 	{
 	// K3 as k_parse does it: rounds of 32 segments x kSeg positions; every lane parses its segment speculatively from a
 	// clean state, entries are handed lane -> lane until nothing changes, then a final pass emits at prefix-summed offsets
-	const uint32_t kSeg = 128, kRound = 32 * kSeg;
+	const uint32_t kSeg = 64, kRound = 32 * kSeg;
 	auto tabf = [&](uint32_t p, uint32_t &a, uint32_t &b) { a = tabA[p]; b = tabB[p]; };
 	auto bytef = [&](uint32_t q) { return (uint32_t)data[q]; };
 	auto slowf = [&](uint32_t p, uint32_t m0, uint32_t budget) { return match_search_above(data, link.data(), p, n, m0, budget); };
