@@ -94,6 +94,12 @@ int b200z_plan_get_timings(b200z_plan *plan, char *names, int32_t names_cap, flo
 int b200z_plan_run(b200z_plan *plan, const uint8_t *d_in, uint8_t *d_out, int64_t *d_out_len, int32_t *d_status,
                    uint32_t *d_check, int64_t *d_in_used, void *cuda_stream);
 
+/* Packs the streams a run produced back to back (16-byte aligned starts) into d_packed, so a caller copies only the
+ * produced bytes to the host: d_packed_off[n + 1] (device) receives the start of every stream and, last, the total.
+ * d_packed needs b200z_plan_out_bytes() of room.  Asynchronous on `stream`. */
+int b200z_plan_pack(b200z_plan *plan, const uint8_t *d_out, const int64_t *d_out_len, uint8_t *d_packed,
+                    int64_t *d_packed_off, void *cuda_stream);
+
 /* Host-buffer batch calls: the end-to-end path (pinned staging, H2D, kernels, D2H inside the call).
  * in[i]/out[i] are HOST pointers; status[i] is per stream.  The return value is the first non-OK status, if any. */
 int b200z_deflate_batch(const uint8_t *const *in, const int64_t *in_len, int32_t n, int level, int strategy, int wrap,

@@ -52,6 +52,14 @@ class _Plan:
         _lib.raise_for(rc)
 
 
+    def pack(self, d_out, d_out_len, d_packed, d_packed_off, stream=None):
+        """streams of the last run back to back in d_packed; d_packed_off (int64, n + 1) gets starts and the total"""
+        import torch
+        s = stream if stream is not None else torch.cuda.current_stream()
+        _lib.raise_for(_lib.lib().b200z_plan_pack(self._h, d_out.data_ptr(), d_out_len.data_ptr(), d_packed.data_ptr(),
+                                                  d_packed_off.data_ptr(), s.cuda_stream))
+
+
 class DeflatePlan(_Plan):
     """n independent streams, each what `new Deflater(level, true)` + SetInput(all) + Finish() would produce."""
 

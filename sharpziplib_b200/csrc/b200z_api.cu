@@ -358,6 +358,67 @@ int b200z_plan_run(b200z_plan *plan, const uint8_t *d_in, uint8_t *d_out, int64_
 	return inflate_plan_run(plan, d_in, d_out, d_out_len, d_status, d_check, d_in_used, s);
 }
 
+} // extern "C" (reopened below)
+
+// ---- packing the produced streams back to back (so a caller copies only what was produced) -----------------
+namespace b200z {
+__global__ void k_pack_offsets(int n, const int64_t *__restrict__ len, int64_t *__restrict__ off) {
+	// n is a batch size (thousands at most): one thread block, serial carry between 1024-element chunks
+	__shared__ int64_t s_part[32];
+	__shared__ int64_t s_carry;
+	if (threadIdx.x == 0) s_carry = 0;
+	__syncthreads();
+	for (int base = 0; base < n; base += 1024) {
+		const int i = base + threadIdx.x;
+		const int64_t v = i < n ? ((len[i] + 15) & ~15ll) : 0; // 16-byte aligned starts: vector copies on both sides
+		int64_t incl = v;
+		for (int o = 1; o < 32; o <<= 1) {
+			const int64_t t = __shfl_up_sync(0xffffffffu, incl, o);
+			if ((threadIdx.x & 31) >= o) incl += t;
+		}
+		if ((threadIdx.x & 31) == 31) s_part[threadIdx.x >> 5] = incl;
+		__syncthreads();
+		int64_t woff = 0;
+		for (int k = 0; k < (int)(threadIdx.x >> 5); k++) woff += s_part[k];
+		const int64_t carry = s_carry;
+		if (i < n) off[i] = carry + woff + incl - v;
+		__syncthreads();
+		if (threadIdx.x == 1023) s_carry = carry + woff + incl;
+		__syncthreads();
+	}
+	if (threadIdx.x == 0) off[n] = s_carry;
+}
+
+__global__ void __launch_bounds__(256)
+    k_pack(const uint8_t *__restrict__ out, const int64_t *__restrict__ out_off, const int64_t *__restrict__ len,
+           const int64_t *__restrict__ off, uint8_t *__restrict__ packed) {
+	const int i = blockIdx.x;
+	const uint8_t *src = out + out_off[i];
+	uint8_t *dst = packed + off[i];
+	const int64_t nb = len[i];
+	const int64_t nv = (nb + 15) >> 4; // the slot is 256-byte aligned and at least 16 bytes longer than the data
+	const uint4 *sv = reinterpret_cast<const uint4 *>(src);
+	uint4 *dv = reinterpret_cast<uint4 *>(dst);
+	for (int64_t k = threadIdx.x; k < nv; k += blockDim.x) dv[k] = sv[k];
+}
+} // namespace b200z
+
+extern "C" int b200z_plan_pack(b200z_plan *plan, const uint8_t *d_out, const int64_t *d_out_len, uint8_t *d_packed,
+                               int64_t *d_packed_off, void *cuda_stream) {
+	if (!plan || !d_out || !d_out_len || !d_packed || !d_packed_off) {
+		set_error("bad arguments");
+		return B200Z_E_ARG;
+	}
+	if (plan->n == 0) return B200Z_OK;
+	cudaStream_t s = (cudaStream_t)cuda_stream;
+	k_pack_offsets<<<1, 1024, 0, s>>>(plan->n, d_out_len, d_packed_off);
+	k_pack<<<plan->n, 256, 0, s>>>(d_out, plan->ws.at<int64_t>(plan->o_out_off), d_out_len, d_packed_off, d_packed);
+	B200Z_CUDA(cudaGetLastError());
+	return B200Z_OK;
+}
+
+extern "C" {
+
 // ---- checksums ---------------------------------------------------------------------------------------
 static int checksum_host(int kind, const uint8_t *buf, int64_t len, uint32_t *value) {
 	if (!value || len < 0 || (len > 0 && !buf)) {

@@ -188,13 +188,6 @@ constexpr int kLaneOutCap = 768;                 // output bytes a lane may prod
 constexpr int kRing = 65536;                     // output ring: >= 32 KiB of history + one round (32 x kLaneOutCap)
 constexpr int kMList = 64;                       // back-references a lane may record per round
 
-struct __align__(16) InfRound {
-	uint32_t in[kInWords];
-	uint8_t ring[kRing];     // ring[pos & 65535] = output byte `pos`; doubles as OutputWindow (Streams/OutputWindow.cs:15-23)
-	uint2 mlist[32 * kMList]; // flat, in stream order: x = output position (low 32 bits), y = len | dist << 16
-};
-constexpr int kInfSmem = (int)(sizeof(InfShared) + sizeof(InfRound));
-
 enum { F_EOB = 1, F_ERR = 2, F_OVERRUN = 4, F_DEAD = 8 };
 
 // The round's input lives in shared memory, so a lane needs no bit buffer: the 32 bits that start at any bit position
@@ -288,21 +281,47 @@ __device__ __forceinline__ bool span_step(const InfShared &sh, const uint32_t *w
 	return false;
 }
 
-__global__ void __launch_bounds__(32)
+// What warp A hands to warp B for one round.
+struct RoundInfo {
+	uint32_t entry[32];  // true entry bit position of every lane (relative to the round's first staged bit)
+	uint32_t obytes[32]; // bytes each lane produces (0 beyond the last live lane)
+	uint32_t nmatch[32]; // back-references each lane records
+	uint64_t opos;       // output position of the round
+	uint32_t end_rel;
+	int lastlane;
+	int tab;             // which InfShared the round's block uses
+	int valid;
+};
+
+struct __align__(16) InfBlockShared {
+	InfShared sh[2];          // code tables, double buffered: A may build the next block's while B still decodes
+	uint32_t in[2][kInWords]; // staged input words, double buffered
+	RoundInfo ri[2];
+	__align__(16) uint8_t ring[kRing]; // ring[pos & 65535] = output byte `pos`; doubles as OutputWindow (Streams/OutputWindow.cs:15-23)
+	__align__(16) uint2 mlist[32 * kMList]; // flat, in stream order: x = output position (low 32 bits), y = len | dist << 16
+	int a_done;
+};
+constexpr int kInfSmem2 = (int)sizeof(InfBlockShared);
+
+// Two warps per stream.  Warp A (producer): block headers, code tables, and the counted decode passes of round t
+// (speculative lanes, exit -> entry hand-off until stable).  Warp B (consumer): final decode pass of round t-1 (literals
+// and back-reference records), the copies, and the flush.  One __syncthreads per round keeps them one round apart; a
+// single warp per stream is latency bound (ncu: IPC 0.16), so the two halves overlap almost for free.
+__global__ void __launch_bounds__(64)
     k_inflate(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, const int64_t *__restrict__ in_off,
               const int64_t *__restrict__ in_len, const int64_t *__restrict__ out_off, const int64_t *__restrict__ out_cap,
               int nstreams, int64_t *__restrict__ out_len, int64_t *__restrict__ in_used, int32_t *__restrict__ status) {
 	extern __shared__ __align__(16) uint8_t smem_raw[];
-	InfShared &sh = *reinterpret_cast<InfShared *>(smem_raw);
-	InfRound &rd = *reinterpret_cast<InfRound *>(smem_raw + sizeof(InfShared));
-	const int lane = threadIdx.x;
+	InfBlockShared &S = *reinterpret_cast<InfBlockShared *>(smem_raw);
+	const int lane = threadIdx.x & 31;
+	const bool isA = threadIdx.x < 32;
 	const int stream = blockIdx.x;
 	if (stream >= nstreams) return;
 	uint8_t *dst = out + out_off[stream];
 	const uint64_t cap = (uint64_t)out_cap[stream];
 	const uint32_t *gwords = reinterpret_cast<const uint32_t *>(in + in_off[stream]);
 
-	BitReader br; // lane 0's header reader (global memory)
+	BitReader br; // warp A lane 0's header reader (global memory)
 	br.words = gwords;
 	br.nbytes = (uint32_t)in_len[stream];
 	br.nwords = (br.nbytes + 3) >> 2;
@@ -312,200 +331,279 @@ __global__ void __launch_bounds__(32)
 	br.consumed = 0;
 	const uint64_t total_bits = 8ull * br.nbytes;
 
-	for (int i = lane; i < kRing / 16; i += 32) reinterpret_cast<uint4 *>(rd.ring)[i] = make_uint4(0, 0, 0, 0); // fresh window = zeros
-	__syncwarp();
-	uint64_t opos = 0; // bytes produced (uniform across the warp)
-	int st = B200Z_OK; // lane 0 authoritative until broadcast
-	int detail = 0;
-	bool last = false, done = false;
-	int cur_static = 0;
+	for (int i = threadIdx.x; i < kRing / 16; i += 64) reinterpret_cast<uint4 *>(S.ring)[i] = make_uint4(0, 0, 0, 0); // fresh window = zeros
+	if (threadIdx.x == 0) {
+		S.ri[0].valid = 0;
+		S.ri[1].valid = 0;
+		S.a_done = 0;
+	}
+	__syncthreads();
 
-	while (!done) {
-		// ---- block header (lane 0) -------------------------------------------------------------------
-		int btype = 0;
-		uint32_t stored_len = 0;
-		if (lane == 0) {
-			if (last) {
-				done = true; // Inflater.cs:443-449: raw mode stops right after the final block
-			} else {
-				const uint32_t hdr = br.get(3);
-				if (br.overrun()) {
-					st = B200Z_E_NEED_INPUT;
+	// ---- warp A state (uniform across the warp unless noted) ----
+	uint64_t opos = 0;   // bytes produced by all rounds handed over so far
+	uint64_t bitpos = 0; // true bit position of the next symbol / header
+	int st = B200Z_OK, detail = 0;
+	bool last = false, in_block = false, a_done = false, pending_stored = false;
+	uint32_t stored_len = 0;
+	int tab = 0, static_in = -1; // static_in: which table buffer currently holds the static tables (-1 none)
+
+	for (uint32_t t = 0;; t++) {
+		const int cur = (int)(t & 1), prv = cur ^ 1;
+		if (isA) {
+			// ============================ producer ============================
+			int valid = 0;
+			if (!a_done) {
+				const bool b_busy = S.ri[prv].valid != 0; // B is consuming the previous round during this iteration
+				if (pending_stored) {
+					if (!b_busy) {
+						// ---- stored block: OutputWindow.CopyStored (:100-122); B is idle, so the ring and dst are ours
+						const uint64_t ipos = bitpos >> 3;
+						const uint64_t avail = ipos <= br.nbytes ? br.nbytes - ipos : 0;
+						if (stored_len > avail) st = B200Z_E_NEED_INPUT;
+						else if (opos + stored_len > cap) st = B200Z_E_NOMEM;
+						if (st == B200Z_OK) {
+							const uint8_t *src = in + in_off[stream] + ipos;
+							for (uint32_t i = lane; i < stored_len; i += 32) {
+								const uint8_t v = src[i];
+								dst[opos + i] = v;
+								S.ring[(uint32_t)(opos + i) & (uint32_t)(kRing - 1)] = v;
+							}
+							opos += stored_len;
+							bitpos = 8ull * (ipos + stored_len);
+							pending_stored = false;
+						} else {
+							a_done = true;
+						}
+					}
 				} else {
-					last = (hdr & 1) != 0;
-					btype = (int)(hdr >> 1);
-					if (btype == 0) {
-						// SkipToByteBoundary, LEN, NLEN (:509)
-						br.drop(br.bc & 7);
-						const uint32_t len = br.get(16);
-						const uint32_t nlen = br.get(16);
-						if (br.overrun()) st = B200Z_E_NEED_INPUT;
-						else if (nlen != (len ^ 0xFFFFu)) { st = B200Z_E_DATA; detail = D_STORED_LEN; }
-						stored_len = len;
-					} else if (btype == 1) {
-						if (!cur_static) {
-							for (int i = 0; i < 144; i++) sh.lens[i] = 8;
-							for (int i = 144; i < 256; i++) sh.lens[i] = 9;
-							for (int i = 256; i < 280; i++) sh.lens[i] = 7;
-							for (int i = 280; i < 288; i++) sh.lens[i] = 8;
-							build_table(sh.lens, 288, kLitRoot, sh.lit, sh.lit_sorted, &sh.lit_c, 0);
-							for (int i = 0; i < 32; i++) sh.lens[i] = 5;
-							build_table(sh.lens, 32, kDistRoot, sh.dist, sh.dist_sorted, &sh.dist_c, 1);
-							cur_static = 1;
-						}
-					} else if (btype == 2) {
-						cur_static = 0;
-						// InflaterDynHeader.CreateStateMachine (:42-120)
-						const int nlit = (int)br.get(5) + 257, ndist = (int)br.get(5) + 1, nmeta = (int)br.get(4) + 4;
-						if (nlit > 286 || ndist > 30) { st = B200Z_E_DATA; detail = D_HDR_RANGE; }
-						else {
-							for (int i = 0; i < 19; i++) sh.lens[i] = 0;
-							for (int i = 0; i < nmeta; i++) sh.lens[c_meta_order[i]] = (uint8_t)br.get(3);
-							int d = build_table(sh.lens, 19, 7, sh.meta, nullptr, nullptr, 2);
-							if (d) { st = B200Z_E_DATA; detail = d; }
-							const int total = nlit + ndist;
-							int idx = 0;
-							while (st == B200Z_OK && idx < total) {
+					if (!in_block) {
+						// ---- block header (lane 0) -------------------------------------------------------
+						int btype = 0;
+						const int ntab = tab ^ 1; // B may still be decoding the previous round with `tab`
+						if (lane == 0) {
+							// re-seat the header reader at the true bit position
+							br.consumed = bitpos;
+							br.widx = (uint32_t)(bitpos >> 5);
+							br.bb = 0;
+							br.bc = 0;
+							const uint32_t sk = (uint32_t)(bitpos & 31);
+							if (sk) {
 								br.refill();
-								const uint32_t e = sh.meta[br.peek(7)];
-								if (((e >> 4) & 15) == K_INVALID) { st = B200Z_E_DATA; detail = D_CODELEN0; break; }
-								br.drop(e & 15);
-								const int sym = (int)(e >> 16);
-								if (sym < 16) {
-									sh.lens[idx++] = (uint8_t)sym;
+								br.bb >>= sk;
+								br.bc -= sk;
+							}
+							if (last) {
+								btype = -1; // Inflater.cs:443-449: raw mode stops right after the final block
+							} else {
+								const uint32_t hdr = br.get(3);
+								if (br.overrun()) {
+									st = B200Z_E_NEED_INPUT;
 								} else {
-									int rep;
-									uint8_t v = 0;
-									if (sym == 16) {
-										if (idx == 0) { st = B200Z_E_DATA; detail = D_HDR_REPEAT0; break; }
-										v = sh.lens[idx - 1];
-										rep = 3 + (int)br.get(2);
-									} else if (sym == 17) rep = 3 + (int)br.get(3);
-									else rep = 11 + (int)br.get(7);
-									if (idx + rep > total) { st = B200Z_E_DATA; detail = D_HDR_OVERRUN; break; }
-									while (rep-- > 0) sh.lens[idx++] = v;
+									last = (hdr & 1) != 0;
+									btype = (int)(hdr >> 1);
+									InfShared &sh = S.sh[ntab];
+									if (btype == 0) {
+										// SkipToByteBoundary, LEN, NLEN (:509)
+										br.drop(br.bc & 7);
+										const uint32_t len = br.get(16);
+										const uint32_t nlen = br.get(16);
+										if (br.overrun()) st = B200Z_E_NEED_INPUT;
+										else if (nlen != (len ^ 0xFFFFu)) { st = B200Z_E_DATA; detail = D_STORED_LEN; }
+										stored_len = len;
+									} else if (btype == 1) {
+										if (static_in != ntab) {
+											for (int i = 0; i < 144; i++) sh.lens[i] = 8;
+											for (int i = 144; i < 256; i++) sh.lens[i] = 9;
+											for (int i = 256; i < 280; i++) sh.lens[i] = 7;
+											for (int i = 280; i < 288; i++) sh.lens[i] = 8;
+											build_table(sh.lens, 288, kLitRoot, sh.lit, sh.lit_sorted, &sh.lit_c, 0);
+											for (int i = 0; i < 32; i++) sh.lens[i] = 5;
+											build_table(sh.lens, 32, kDistRoot, sh.dist, sh.dist_sorted, &sh.dist_c, 1);
+											static_in = ntab;
+										}
+									} else if (btype == 2) {
+										if (static_in == ntab) static_in = -1;
+										// InflaterDynHeader.CreateStateMachine (:42-120)
+										const int nlit = (int)br.get(5) + 257, ndist = (int)br.get(5) + 1, nmeta = (int)br.get(4) + 4;
+										if (nlit > 286 || ndist > 30) { st = B200Z_E_DATA; detail = D_HDR_RANGE; }
+										else {
+											for (int i = 0; i < 19; i++) sh.lens[i] = 0;
+											for (int i = 0; i < nmeta; i++) sh.lens[c_meta_order[i]] = (uint8_t)br.get(3);
+											int d = build_table(sh.lens, 19, 7, sh.meta, nullptr, nullptr, 2);
+											if (d) { st = B200Z_E_DATA; detail = d; }
+											const int total = nlit + ndist;
+											int idx = 0;
+											while (st == B200Z_OK && idx < total) {
+												br.refill();
+												const uint32_t e = sh.meta[br.peek(7)];
+												if (((e >> 4) & 15) == K_INVALID) { st = B200Z_E_DATA; detail = D_CODELEN0; break; }
+												br.drop(e & 15);
+												const int sym = (int)(e >> 16);
+												if (sym < 16) {
+													sh.lens[idx++] = (uint8_t)sym;
+												} else {
+													int rep;
+													uint8_t v = 0;
+													if (sym == 16) {
+														if (idx == 0) { st = B200Z_E_DATA; detail = D_HDR_REPEAT0; break; }
+														v = sh.lens[idx - 1];
+														rep = 3 + (int)br.get(2);
+													} else if (sym == 17) rep = 3 + (int)br.get(3);
+													else rep = 11 + (int)br.get(7);
+													if (idx + rep > total) { st = B200Z_E_DATA; detail = D_HDR_OVERRUN; break; }
+													while (rep-- > 0) sh.lens[idx++] = v;
+												}
+												if (br.overrun()) { st = B200Z_E_NEED_INPUT; break; }
+											}
+											if (st == B200Z_OK && br.overrun()) st = B200Z_E_NEED_INPUT;
+											if (st == B200Z_OK && sh.lens[256] == 0) { st = B200Z_E_DATA; detail = D_HDR_NO_EOB; }
+											if (st == B200Z_OK) {
+												uint8_t dl[32];
+												for (int i = 0; i < ndist; i++) dl[i] = sh.lens[nlit + i];
+												d = build_table(sh.lens, nlit, kLitRoot, sh.lit, sh.lit_sorted, &sh.lit_c, 0);
+												if (!d) d = build_table(dl, ndist, kDistRoot, sh.dist, sh.dist_sorted, &sh.dist_c, 1);
+												if (d) { st = B200Z_E_DATA; detail = d; }
+											}
+										}
+									} else {
+										st = B200Z_E_DATA;
+										detail = D_BLOCK_TYPE;
+									}
 								}
-								if (br.overrun()) { st = B200Z_E_NEED_INPUT; break; }
 							}
-							if (st == B200Z_OK && br.overrun()) st = B200Z_E_NEED_INPUT;
-							if (st == B200Z_OK && sh.lens[256] == 0) { st = B200Z_E_DATA; detail = D_HDR_NO_EOB; }
-							if (st == B200Z_OK) {
-								uint8_t dl[32];
-								for (int i = 0; i < ndist; i++) dl[i] = sh.lens[nlit + i];
-								d = build_table(sh.lens, nlit, kLitRoot, sh.lit, sh.lit_sorted, &sh.lit_c, 0);
-								if (!d) d = build_table(dl, ndist, kDistRoot, sh.dist, sh.dist_sorted, &sh.dist_c, 1);
-								if (d) { st = B200Z_E_DATA; detail = d; }
-							}
+							// an error diagnosed from bits past the end of the input is "needs more input", not corrupt data
+							if (st != B200Z_OK && br.overrun()) { st = B200Z_E_NEED_INPUT; detail = 0; }
 						}
-					} else {
-						st = B200Z_E_DATA;
-						detail = D_BLOCK_TYPE;
-					}
-				}
-			}
-			// an error diagnosed from bits past the end of the input is "needs more input", not corrupt data
-			if (st != B200Z_OK && br.overrun()) { st = B200Z_E_NEED_INPUT; detail = 0; }
-		}
-		done = __shfl_sync(0xffffffffu, (int)done, 0) != 0;
-		st = __shfl_sync(0xffffffffu, st, 0);
-		if (done || st != B200Z_OK) break;
-		btype = __shfl_sync(0xffffffffu, btype, 0);
-		uint64_t bitpos = __shfl_sync(0xffffffffu, (unsigned long long)br.consumed, 0);
-		__syncwarp();
-
-		if (btype == 0) {
-			// ---- stored block: OutputWindow.CopyStored (:100-122), whole warp ---------------------------
-			stored_len = __shfl_sync(0xffffffffu, stored_len, 0);
-			const uint64_t ipos = bitpos >> 3;
-			const uint64_t avail = ipos <= br.nbytes ? br.nbytes - ipos : 0;
-			if (stored_len > avail) st = B200Z_E_NEED_INPUT;
-			else if (opos + stored_len > cap) st = B200Z_E_NOMEM;
-			if (st != B200Z_OK) break;
-			const uint8_t *src = in + in_off[stream] + ipos;
-			for (uint32_t i = lane; i < stored_len; i += 32) {
-				const uint8_t v = src[i];
-				dst[opos + i] = v;
-				rd.ring[(uint32_t)(opos + i) & (uint32_t)(kRing - 1)] = v;
-			}
-			opos += stored_len;
-			bitpos = 8ull * (ipos + stored_len);
-		} else {
-			// ---- Huffman block: rounds ----------------------------------------------------------------------
-			bool in_block = true;
-			while (in_block) {
-				// stage the round's input words (zero beyond the end of the stream)
-				const uint32_t w0 = (uint32_t)(bitpos >> 5);
-				for (int i = lane; i < kInWords; i += 32) {
-					const uint32_t wi = w0 + (uint32_t)i;
-					uint32_t v = 0;
-					if (wi < br.nwords) {
-						v = __ldg(gwords + wi);
-						if (wi == br.nwords - 1 && (br.nbytes & 3)) v &= (1u << (8 * (br.nbytes & 3))) - 1u;
-					}
-					rd.in[i] = v;
-				}
-				__syncwarp();
-				const uint32_t r0 = (uint32_t)(bitpos & 31); // relative position of the true entry
-				const uint64_t remain = total_bits - ((uint64_t)w0 << 5);
-				const uint32_t end_rel = remain > 0x7FFFFFFFull ? 0x7FFFFFFFu : (uint32_t)remain;
-				const uint32_t limit = r0 + (uint32_t)(lane + 1) * kSubBits;
-				uint32_t entry = r0 + (uint32_t)lane * kSubBits;
-				uint32_t exitp = entry, obytes = 0, nmatch = 0, flags = 0, det = 0;
-				bool changed = true, dead = false;
-				for (int it = 0; it < 34; it++) {
-					Span sp;
-					bool act = changed && !dead;
-					if (changed) {
-						sp.o = 0;
-						sp.nm = 0;
-						sp.fl = dead ? (uint32_t)F_DEAD : 0u;
-						sp.det = 0;
-						sp.pos = entry;
-					}
-					while (__any_sync(0xffffffffu, act)) {
-						if (act) act = span_step<false>(sh, rd.in, sp, limit, end_rel, nullptr, 0, nullptr);
+						st = __shfl_sync(0xffffffffu, st, 0);
+						btype = __shfl_sync(0xffffffffu, btype, 0);
+						last = __shfl_sync(0xffffffffu, (int)last, 0) != 0;
+						static_in = __shfl_sync(0xffffffffu, static_in, 0);
+						bitpos = __shfl_sync(0xffffffffu, (unsigned long long)br.consumed, 0);
+						stored_len = __shfl_sync(0xffffffffu, stored_len, 0);
 						__syncwarp();
+						if (st != B200Z_OK || btype == -1) {
+							a_done = true;
+						} else if (btype == 0) {
+							pending_stored = true; // copied in a later iteration, once B is idle
+						} else {
+							tab = ntab;
+							in_block = true;
+						}
 					}
-					if (changed) {
-						exitp = sp.pos;
-						obytes = sp.o;
-						nmatch = sp.nm;
-						flags = sp.fl;
-						det = sp.det;
+					if (in_block && !a_done) {
+						// ---- one round: stage words, counted passes with exit -> entry hand-off ---------------------
+						uint32_t *words = S.in[cur];
+						const InfShared &sh = S.sh[tab];
+						const uint32_t w0 = (uint32_t)(bitpos >> 5);
+						for (int i = lane; i < kInWords; i += 32) {
+							const uint32_t wi = w0 + (uint32_t)i;
+							uint32_t v = 0;
+							if (wi < br.nwords) {
+								v = __ldg(gwords + wi);
+								if (wi == br.nwords - 1 && (br.nbytes & 3)) v &= (1u << (8 * (br.nbytes & 3))) - 1u;
+							}
+							words[i] = v;
+						}
+						__syncwarp();
+						const uint32_t r0 = (uint32_t)(bitpos & 31);
+						const uint64_t remain = total_bits - ((uint64_t)w0 << 5);
+						const uint32_t end_rel = remain > 0x7FFFFFFFull ? 0x7FFFFFFFu : (uint32_t)remain;
+						const uint32_t limit = r0 + (uint32_t)(lane + 1) * kSubBits;
+						uint32_t entry = r0 + (uint32_t)lane * kSubBits;
+						uint32_t exitp = entry, obytes = 0, nmatch = 0, flags = 0, det = 0;
+						bool changed = true, dead = false;
+						for (int it = 0; it < 34; it++) {
+							Span sp;
+							bool act = changed && !dead;
+							if (changed) {
+								sp.o = 0;
+								sp.nm = 0;
+								sp.fl = dead ? (uint32_t)F_DEAD : 0u;
+								sp.det = 0;
+								sp.pos = entry;
+							}
+							while (__any_sync(0xffffffffu, act)) {
+								if (act) act = span_step<false>(sh, words, sp, limit, end_rel, nullptr, 0, nullptr);
+								__syncwarp();
+							}
+							if (changed) {
+								exitp = sp.pos;
+								obytes = sp.o;
+								nmatch = sp.nm;
+								flags = sp.fl;
+								det = sp.det;
+							}
+							const uint32_t pe = __shfl_up_sync(0xffffffffu, exitp, 1);
+							const uint32_t pf = __shfl_up_sync(0xffffffffu, flags, 1);
+							changed = false;
+							if (lane > 0) {
+								const bool nd = pf != 0; // the previous lane ended the block, failed or is dead itself
+								changed = (pe != entry) || (nd != dead);
+								entry = pe;
+								dead = nd;
+							}
+							if (!__any_sync(0xffffffffu, changed)) break;
+						}
+						// lanes up to and including the first one that stopped the block are exact; the rest are dead
+						const uint32_t stopmask = __ballot_sync(0xffffffffu, (flags & (F_EOB | F_ERR | F_OVERRUN)) != 0);
+						const int lastlane = stopmask ? (__ffs(stopmask) - 1) : 31;
+						if (lane > lastlane) { obytes = 0; nmatch = 0; }
+						uint32_t tot = obytes;
+						for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+						const uint32_t lflags = __shfl_sync(0xffffffffu, flags, lastlane);
+						const uint32_t ldet = __shfl_sync(0xffffffffu, det, lastlane);
+						const uint32_t lexit = __shfl_sync(0xffffffffu, exitp, lastlane);
+						if (opos + tot > cap) {
+							st = B200Z_E_NOMEM;
+							a_done = true;
+						} else {
+							RoundInfo &ri = S.ri[cur];
+							ri.entry[lane] = entry;
+							ri.obytes[lane] = obytes;
+							ri.nmatch[lane] = nmatch;
+							if (lane == 0) {
+								ri.opos = opos;
+								ri.end_rel = end_rel;
+								ri.lastlane = lastlane;
+								ri.tab = tab;
+							}
+							valid = 1;
+							opos += tot;
+							bitpos = ((uint64_t)w0 << 5) + lexit;
+							if (lflags & F_EOB) in_block = false;
+							else if (lflags & F_OVERRUN) { st = B200Z_E_NEED_INPUT; a_done = true; }
+							else if (lflags & F_ERR) { st = B200Z_E_DATA; detail = (int)ldet; a_done = true; }
+							else if (tot == 0 && lexit == r0) { st = B200Z_E_INTERNAL; a_done = true; } // cannot happen: a symbol always fits
+						}
 					}
-					const uint32_t pe = __shfl_up_sync(0xffffffffu, exitp, 1);
-					const uint32_t pf = __shfl_up_sync(0xffffffffu, flags, 1);
-					changed = false;
-					if (lane > 0) {
-						const bool nd = pf != 0; // the previous lane ended the block, failed or is dead itself
-						changed = (pe != entry) || (nd != dead);
-						entry = pe;
-						dead = nd;
-					}
-					if (!__any_sync(0xffffffffu, changed)) break;
 				}
-				// lanes up to and including the first one that stopped the block are exact; the rest are dead
-				const uint32_t stopmask = __ballot_sync(0xffffffffu, (flags & (F_EOB | F_ERR | F_OVERRUN)) != 0);
-				const int lastlane = stopmask ? (__ffs(stopmask) - 1) : 31;
-				if (lane > lastlane) { obytes = 0; nmatch = 0; }
-				uint32_t incl = obytes;
+			}
+			if (lane == 0) {
+				S.ri[cur].valid = valid;
+				S.a_done = a_done ? 1 : 0;
+			}
+		} else {
+			// ============================ consumer ============================
+			const RoundInfo &ri = S.ri[prv];
+			if (ri.valid) {
+				const InfShared &sh = S.sh[ri.tab];
+				const uint32_t *words = S.in[prv];
+				const uint32_t entry = ri.entry[lane], obytes = ri.obytes[lane], nmatch = ri.nmatch[lane];
+				const uint64_t ropos = ri.opos;
+				const int lastlane = ri.lastlane;
+				const uint32_t end_rel = ri.end_rel;
+				uint32_t incl = obytes, mincl = nmatch;
 				for (int o = 1; o < 32; o <<= 1) {
-					const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-					if (lane >= o) incl += t;
+					const uint32_t t1 = __shfl_up_sync(0xffffffffu, incl, o);
+					const uint32_t t2 = __shfl_up_sync(0xffffffffu, mincl, o);
+					if (lane >= o) { incl += t1; mincl += t2; }
 				}
 				const uint32_t round_out = __shfl_sync(0xffffffffu, incl, 31);
-				const uint32_t lflags = __shfl_sync(0xffffffffu, flags, lastlane);
-				const uint32_t ldet = __shfl_sync(0xffffffffu, det, lastlane);
-				const uint32_t lexit = __shfl_sync(0xffffffffu, exitp, lastlane);
-				if (opos + round_out > cap) { st = B200Z_E_NOMEM; break; }
-				const uint32_t obase = (uint32_t)opos + incl - obytes; // this lane's first output position (low 32 bits)
-				// back-references go to one flat list in stream order: lane offsets from the counted pass
-				uint32_t mincl = nmatch;
-				for (int o = 1; o < 32; o <<= 1) {
-					const uint32_t t = __shfl_up_sync(0xffffffffu, mincl, o);
-					if (lane >= o) mincl += t;
-				}
 				const uint32_t total_m = __shfl_sync(0xffffffffu, mincl, 31);
+				const uint32_t obase = (uint32_t)ropos + incl - obytes; // this lane's first output position (low 32 bits)
+				// lane l's span ends where lane l + 1's nominal sub-chunk starts; r0 is lane 0's entry
+				const uint32_t r0 = __shfl_sync(0xffffffffu, entry, 0);
+				const uint32_t lim = r0 + (uint32_t)(lane + 1) * kSubBits;
 				{
 					Span sp;
 					bool act = lane <= lastlane && obytes != 0;
@@ -514,14 +612,14 @@ __global__ void __launch_bounds__(32)
 					sp.fl = 0;
 					sp.det = 0;
 					sp.pos = entry;
-					uint2 *ml = rd.mlist + (mincl - nmatch);
+					uint2 *ml = S.mlist + (mincl - nmatch);
 					while (__any_sync(0xffffffffu, act)) {
-						if (act) act = span_step<true>(sh, rd.in, sp, limit, end_rel, rd.ring, obase, ml);
+						if (act) act = span_step<true>(sh, words, sp, lim, end_rel, S.ring, obase, ml);
 						__syncwarp();
 					}
 				}
 				__syncwarp();
-				// ---- back-references in stream order (OutputWindow.Repeat :63-92) ------------------------------------
+				// ---- back-references in stream order (OutputWindow.Repeat :63-92) ----------------------------------
 				// Four matches per step, each copied by a group of 8 lanes, when none of them reads bytes another match
 				// of the same step writes; otherwise the step's matches are copied one after another by the whole warp.
 				// All sources are in the ring (distance <= 32768 < ring size - round size); byte k comes from source byte
@@ -531,7 +629,7 @@ __global__ void __launch_bounds__(32)
 					for (uint32_t k0 = 0; k0 < total_m; k0 += 4) {
 						const uint32_t mi = k0 + (uint32_t)grp;
 						const bool have = mi < total_m;
-						const uint2 m = have ? rd.mlist[mi] : make_uint2(0u, 0u);
+						const uint2 m = have ? S.mlist[mi] : make_uint2(0u, 0u);
 						const uint32_t mo = m.x, mlen = m.y & 0xFFFFu, mdist = m.y >> 16;
 						const uint32_t step_lo = __shfl_sync(0xffffffffu, mo, 0); // first destination byte of this step
 						// a later match of the step depends on the step if its source reaches step_lo or beyond
@@ -542,10 +640,10 @@ __global__ void __launch_bounds__(32)
 								const uint32_t sbase = mo - mdist;
 								if (mdist >= mlen) {
 									for (uint32_t k2 = sub; k2 < mlen; k2 += 8)
-										rd.ring[(mo + k2) & (uint32_t)(kRing - 1)] = rd.ring[(sbase + k2) & (uint32_t)(kRing - 1)];
+										S.ring[(mo + k2) & (uint32_t)(kRing - 1)] = S.ring[(sbase + k2) & (uint32_t)(kRing - 1)];
 								} else {
 									for (uint32_t k2 = sub; k2 < mlen; k2 += 8)
-										rd.ring[(mo + k2) & (uint32_t)(kRing - 1)] = rd.ring[(sbase + k2 % mdist) & (uint32_t)(kRing - 1)];
+										S.ring[(mo + k2) & (uint32_t)(kRing - 1)] = S.ring[(sbase + k2 % mdist) & (uint32_t)(kRing - 1)];
 								}
 							}
 							__syncwarp();
@@ -558,10 +656,10 @@ __global__ void __launch_bounds__(32)
 									const uint32_t glen = gy & 0xFFFFu, gdist = gy >> 16, gs = gmo - gdist;
 									if (gdist >= glen) {
 										for (uint32_t k2 = lane; k2 < glen; k2 += 32)
-											rd.ring[(gmo + k2) & (uint32_t)(kRing - 1)] = rd.ring[(gs + k2) & (uint32_t)(kRing - 1)];
+											S.ring[(gmo + k2) & (uint32_t)(kRing - 1)] = S.ring[(gs + k2) & (uint32_t)(kRing - 1)];
 									} else {
 										for (uint32_t k2 = lane; k2 < glen; k2 += 32)
-											rd.ring[(gmo + k2) & (uint32_t)(kRing - 1)] = rd.ring[(gs + k2 % gdist) & (uint32_t)(kRing - 1)];
+											S.ring[(gmo + k2) & (uint32_t)(kRing - 1)] = S.ring[(gs + k2 % gdist) & (uint32_t)(kRing - 1)];
 									}
 								}
 								__syncwarp();
@@ -571,47 +669,27 @@ __global__ void __launch_bounds__(32)
 				}
 				// ---- flush the round: ring[opos .. opos + round_out) -> dst, 16-byte vectors where aligned ------------
 				{
-					const uint64_t b0 = opos, b1 = opos + round_out;
+					const uint64_t b0 = ropos, b1 = ropos + round_out;
 					const uint64_t v0 = (b0 + 15) & ~15ull, v1 = b1 & ~15ull;
 					if (v0 < v1) {
-						for (uint64_t i = b0 + lane; i < v0; i += 32) dst[i] = rd.ring[(uint32_t)i & (uint32_t)(kRing - 1)];
+						for (uint64_t i = b0 + lane; i < v0; i += 32) dst[i] = S.ring[(uint32_t)i & (uint32_t)(kRing - 1)];
 						for (uint64_t i = v0 + 16ull * lane; i < v1; i += 512)
-							*reinterpret_cast<uint4 *>(dst + i) = *reinterpret_cast<const uint4 *>(rd.ring + ((uint32_t)i & (uint32_t)(kRing - 1)));
-						for (uint64_t i = v1 + lane; i < b1; i += 32) dst[i] = rd.ring[(uint32_t)i & (uint32_t)(kRing - 1)];
+							*reinterpret_cast<uint4 *>(dst + i) = *reinterpret_cast<const uint4 *>(S.ring + ((uint32_t)i & (uint32_t)(kRing - 1)));
+						for (uint64_t i = v1 + lane; i < b1; i += 32) dst[i] = S.ring[(uint32_t)i & (uint32_t)(kRing - 1)];
 					} else {
-						for (uint64_t i = b0 + lane; i < b1; i += 32) dst[i] = rd.ring[(uint32_t)i & (uint32_t)(kRing - 1)];
+						for (uint64_t i = b0 + lane; i < b1; i += 32) dst[i] = S.ring[(uint32_t)i & (uint32_t)(kRing - 1)];
 					}
 				}
-				opos += round_out;
-				bitpos = ((uint64_t)w0 << 5) + lexit;
-				__syncwarp();
-				if (lflags & F_EOB) in_block = false;
-				else if (lflags & F_OVERRUN) { st = B200Z_E_NEED_INPUT; break; }
-				else if (lflags & F_ERR) { st = B200Z_E_DATA; detail = (int)ldet; break; }
-				else if (round_out == 0 && lexit == r0) { st = B200Z_E_INTERNAL; break; } // cannot happen: a symbol always fits
-			}
-			if (st != B200Z_OK) break;
-		}
-		// re-seat lane 0's header reader at the new bit position
-		if (lane == 0) {
-			br.consumed = bitpos;
-			br.widx = (uint32_t)(bitpos >> 5);
-			br.bb = 0;
-			br.bc = 0;
-			const uint32_t sk = (uint32_t)(bitpos & 31);
-			if (sk) {
-				br.refill();
-				br.bb >>= sk;
-				br.bc -= sk;
 			}
 		}
-		__syncwarp();
+		__syncthreads();
+		if (S.a_done && !S.ri[cur].valid) break; // A has nothing more and B has consumed every round
 	}
-	if (lane == 0) {
+	if (threadIdx.x == 0) {
 		status[stream] = st | (detail << 8);
 		out_len[stream] = (int64_t)opos;
 		if (in_used) {
-			uint64_t used = (br.consumed + 7) >> 3; // n - RemainingInput (trap T14)
+			uint64_t used = (bitpos + 7) >> 3; // n - RemainingInput (trap T14)
 			if (used > br.nbytes) used = br.nbytes;
 			in_used[stream] = (int64_t)used;
 		}
@@ -650,7 +728,7 @@ int inflate_plan_build(b200z_plan *p) {
 		B200Z_CUDA(cudaMemcpy(ws.at<int64_t>(p->o_out_off), p->out_off.data(), 8ll * n, cudaMemcpyHostToDevice));
 		B200Z_CUDA(cudaMemcpy(ws.at<int64_t>(p->o_out_cap), p->out_cap.data(), 8ll * n, cudaMemcpyHostToDevice));
 	}
-	B200Z_CUDA(cudaFuncSetAttribute(k_inflate, cudaFuncAttributeMaxDynamicSharedMemorySize, kInfSmem));
+	B200Z_CUDA(cudaFuncSetAttribute(k_inflate, cudaFuncAttributeMaxDynamicSharedMemorySize, kInfSmem2));
 	p->launches = 1;
 	return B200Z_OK;
 }
@@ -663,7 +741,7 @@ int inflate_plan_run(b200z_plan *p, const uint8_t *d_in, uint8_t *d_out, int64_t
 	(void)d_check;
 	p->ev_used = 0;
 	p->mark(s, "k_inflate");
-	k_inflate<<<n, 32, kInfSmem, s>>>(
+	k_inflate<<<n, 64, kInfSmem2, s>>>(
 	    d_in, d_out, ws.at<int64_t>(p->o_in_off), ws.at<int64_t>(p->o_in_len), ws.at<int64_t>(p->o_out_off),
 	    ws.at<int64_t>(p->o_out_cap), n, d_out_len, d_in_used, d_status);
 	p->mark(s, "end");
