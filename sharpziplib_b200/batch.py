@@ -22,9 +22,12 @@ class _Plan:
         self.launches = L.b200z_plan_launches(handle)
 
     def close(self):
-        if self._h:
-            _lib.lib().b200z_plan_destroy(self._h)
-            self._h = None
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            try:
+                _lib.lib().b200z_plan_destroy(h)
+            except Exception:  # interpreter shutdown: the module globals may already be gone
+                pass
 
     __del__ = close
 
