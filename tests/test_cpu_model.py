@@ -54,3 +54,15 @@ def test_model_multi_slide(model, oracle):
     for cls in (0, 4, 6):
         d = datagen.silesia_mix(cls, 400000, config=8).tobytes()
         assert model(d, 6) == oracle.deflate(d, level=6), cls
+
+
+def test_model_fast_and_stored_levels(model, oracle):
+    """levels 1-4 (serial DeflateFast engine, what k_fast runs) and level 0 (stored_run bookkeeping)"""
+    from sharpziplib_b200 import datagen
+    items = [(n, d) for n, d in corpus_small() if len(d) in (0, 3, 100, 4096, 70000)]
+    items.append(("mix3_400k", datagen.silesia_mix(3, 400000, config=8).tobytes()))
+    items.append(("zeros_300k", bytes(300000)))
+    for name, d in items:
+        for level in (0, 1, 2, 3, 4):
+            assert model(d, level) == oracle.deflate(d, level=level), (name, level)
+            assert model(d, level, 0, 1) == oracle.deflate(d, level=level, pattern=1), (name, level)
