@@ -213,13 +213,20 @@ __global__ void __launch_bounds__(kMatchThreads, 1)
 }
 
 // ------------------------------------------------------------------------------------------------
-// K3: the lazy parse (DeflateSlow's state machine), parallelised inside each stream.
-// One warp per stream, rounds of 32 segments x kSeg positions.  The round's table entries and bytes are staged in
-// shared memory (coalesced), every lane parses its own segment starting from a guessed clean state, then each lane
-// hands its exit state to the next lane as that lane's entry; lanes whose entry changed parse again.  Lane 0's entry
-// is the true carried state, so after k hand-offs the first k+1 lanes are exact; because the parse re-synchronises
-// within a few symbols the hand-offs normally stop changing anything after one or two iterations.  A final pass emits
-// the symbols at prefix-summed offsets and records the block cuts (every 16384 symbols, DeflaterHuffman.cs:863).
+// K3: the lazy parse (DeflateSlow's state machine, DeflaterEngine.cs:741-855), parallel at three levels.
+//
+//  lanes   : a ROUND is 32 segments x kSeg positions.  The round's table entries and bytes are staged in shared memory
+//            (cp.async), every lane parses its own segment starting from a guessed clean state, then each lane hands
+//            its exit state to the next lane as that lane's entry; lanes whose entry changed parse again.  Lane 0's
+//            entry is the true carried state, so after k hand-offs the first k+1 lanes are exact; because the parse
+//            re-synchronises within a few symbols the hand-offs normally stop changing anything after one iteration.
+//            A final pass emits the round's symbols into the round's own slot.
+//  chunks  : k_parse_chunk runs one warp per CHUNK of a stream (many chunks per stream, all concurrent), every chunk
+//            but the first starting from a guessed clean state; per round it records the exit state and symbol count.
+//  fix-up  : k_parse_fix walks the chunks of a stream in order and re-runs rounds of a chunk from the true entry state
+//            until a round's exit state equals the recorded one -- from there on the speculative result stands.
+//  gather  : k_parse_scan prefix-sums the rounds' symbol counts, k_parse_gather moves the symbols to their final
+//            positions and records the block cuts (every 16384 symbols, DeflaterHuffman.cs:863).
 // ------------------------------------------------------------------------------------------------
 constexpr int kSegShift = 6;
 constexpr int kSeg = 1 << kSegShift; // 64 positions per lane: 19 KiB of shared memory per warp, 11 warps per SM
@@ -227,6 +234,11 @@ constexpr int kRound = 32 * kSeg;
 constexpr int kSegStride = kSeg + 2; // uint2 entries; +2 keeps 16-byte alignment for cp.async and staggers the banks
 constexpr int kParseDatOff = 32 * kSegStride * 8;
 constexpr int kParseSmem = kParseDatOff + kRound + 48;
+
+struct ChunkDesc {
+	int32_t stream;
+	uint32_t c0, c1; // positions [c0, c1) of the stream, c0 a multiple of kRound
+};
 
 __device__ __forceinline__ ParseCarry shfl_carry(const ParseCarry &c, int src) {
 	ParseCarry r;
@@ -238,135 +250,274 @@ __device__ __forceinline__ ParseCarry shfl_carry(const ParseCarry &c, int src) {
 	return r;
 }
 
-__global__ void __launch_bounds__(32)
-    k_parse(const uint8_t *__restrict__ in, const uint16_t *__restrict__ link, const uint2 *__restrict__ mt,
-            uint32_t *__restrict__ sym, const int64_t *__restrict__ in_off, const int64_t *__restrict__ in_len,
-            uint32_t *__restrict__ nsyms, uint32_t *__restrict__ nblocks, const uint32_t *__restrict__ blk_off,
-            uint32_t *__restrict__ blk_start, uint32_t *__restrict__ blk_ptop, LevelParams lp, int strategy, int end_mode) {
-	extern __shared__ __align__(16) uint8_t smem[];
+__device__ __forceinline__ ParseCarry clean_carry(uint32_t p) {
+	ParseCarry c;
+	parse_init(c.st);
+	c.st.p = p;
+	c.last_top = p;
+	return c;
+}
+
+struct RoundRec { // what a round leaves behind (5 + 1 words)
+	uint32_t p, mlen, mstart, prevAvail, last_top, cnt;
+};
+__device__ __forceinline__ ParseCarry rec_carry(const RoundRec &r) {
+	ParseCarry c;
+	c.st.p = r.p;
+	c.st.mlen = r.mlen;
+	c.st.mstart = r.mstart;
+	c.st.prevAvail = r.prevAvail;
+	c.last_top = r.last_top;
+	return c;
+}
+
+// One round [base, base + kRound) of a stream, entered with `carry` (uniform across the warp; updated to the round's
+// exit state).  The round's symbols go to sround[0 .. cnt).  Returns cnt (uniform).
+__device__ __forceinline__ uint32_t parse_round(uint8_t *smem, const uint8_t *data, const uint16_t *lnk, const uint2 *tab,
+                                                uint32_t n, uint32_t base, const LevelParams &lp, int strategy,
+                                                ParseCarry &carry, uint32_t *sround) {
 	uint2 *s_tab = reinterpret_cast<uint2 *>(smem);
 	uint8_t *s_dat = smem + kParseDatOff; // s_dat[16 + i] = byte at position base + i (16 bytes of history in front)
-	const int lane = threadIdx.x;
+	const int lane = threadIdx.x & 31;
+	const uint32_t rn = (n - base > (uint32_t)kRound) ? (uint32_t)kRound : n - base;
+	__syncwarp();
+	// stage the round with 16-byte async copies (LDGSTS): all of them are in flight at once, no register staging
+	for (uint32_t i = 2 * lane; i + 1 < rn; i += 64)
+		__pipeline_memcpy_async(&s_tab[(i >> kSegShift) * kSegStride + (i & (kSeg - 1))], &tab[base + i], 16);
+	{
+		// bytes [base - 16, base + rn) rounded up to 16 (the input slot has 16 bytes of slack behind n)
+		const uint32_t c0 = base ? 0u : 1u, c1 = (16 + rn + 15) >> 4;
+		for (uint32_t c = c0 + lane; c < c1; c += 32) __pipeline_memcpy_async(s_dat + 16 * c, data + base - 16 + 16 * c, 16);
+	}
+	__pipeline_commit();
+	if ((rn & 1) && lane == 0) s_tab[((rn - 1) >> kSegShift) * kSegStride + ((rn - 1) & (kSeg - 1))] = tab[base + rn - 1];
+	__pipeline_wait_prior(0);
+	__syncwarp();
+	const uint32_t seg_end = base + (uint32_t)(lane + 1) * kSeg;
+	auto tabf = [&](uint32_t p, uint32_t &a, uint32_t &b) {
+		const uint32_t i = p - base;
+		const uint2 t = s_tab[(i >> kSegShift) * kSegStride + (i & (kSeg - 1))];
+		a = t.x;
+		b = t.y;
+	};
+	auto bytef = [&](uint32_t q) { return (uint32_t)s_dat[q + 16 - base]; };
+	auto slowf = [&](uint32_t p, uint32_t m0, uint32_t budget) { return match_search_above(data, lnk, p, n, m0, budget); };
+	ParseCarry entry, ex;
+	if (lane == 0) entry = carry;
+	else entry = clean_carry(base + (uint32_t)lane * kSeg);
+	ex = entry;
+	uint32_t cnt = 0;
+	bool changed = true;
+	const uint32_t lim = seg_end < n ? seg_end : n;
+	for (int it = 0; it < 34; it++) {
+		// all lanes step together and re-converge every iteration (a per-lane loop would leave them diverged)
+		if (changed) {
+			ex = entry;
+			cnt = 0;
+		}
+		bool act = changed && ex.st.p < lim;
+		while (__any_sync(0xffffffffu, act)) {
+			if (act) {
+				ex.last_top = ex.st.p;
+				uint32_t s2;
+				cnt += (uint32_t)parse_step(ex.st, n, lp, strategy, tabf, bytef, slowf, s2);
+				act = ex.st.p < lim;
+			}
+			__syncwarp();
+		}
+		const ParseCarry ne = shfl_carry(ex, lane == 0 ? 0 : lane - 1);
+		changed = false;
+		if (lane > 0) {
+			changed = !carry_equal(ne, entry);
+			entry = ne;
+		}
+		if (!__any_sync(0xffffffffu, changed)) break;
+	}
+	// final pass: emit at prefix-summed offsets inside the round's slot
+	uint32_t incl = cnt;
+	for (int o = 1; o < 32; o <<= 1) {
+		const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+		if (lane >= o) incl += t;
+	}
+	uint32_t idx = incl - cnt;
+	ParseCarry c = entry;
+	{
+		bool act = c.st.p < lim;
+		while (__any_sync(0xffffffffu, act)) {
+			if (act) {
+				c.last_top = c.st.p;
+				uint32_t s2;
+				if (parse_step(c.st, n, lp, strategy, tabf, bytef, slowf, s2)) sround[idx++] = s2;
+				act = c.st.p < lim;
+			}
+			__syncwarp();
+		}
+	}
+	carry = shfl_carry(c, 31);
+	return __shfl_sync(0xffffffffu, incl, 31);
+}
+
+__global__ void __launch_bounds__(32)
+    k_parse_chunk(const uint8_t *__restrict__ in, const uint16_t *__restrict__ link, const uint2 *__restrict__ mt,
+                  uint32_t *__restrict__ sym_local, const int64_t *__restrict__ in_off, const int64_t *__restrict__ in_len,
+                  const ChunkDesc *__restrict__ chunks, const uint32_t *__restrict__ rnd_off, RoundRec *__restrict__ recs,
+                  LevelParams lp, int strategy) {
+	extern __shared__ __align__(16) uint8_t smem[];
+	const ChunkDesc cd = chunks[blockIdx.x];
+	const uint32_t n = (uint32_t)in_len[cd.stream];
+	const int64_t off = in_off[cd.stream];
+	RoundRec *rr = recs + rnd_off[cd.stream];
+	ParseCarry carry = clean_carry(cd.c0); // exact for c0 == 0 (DeflaterEngine.Reset :234-253), a guess otherwise
+	if (cd.c0 == 0) carry.last_top = 0;
+	for (uint32_t base = cd.c0; base < cd.c1; base += kRound) {
+		const uint32_t cnt = parse_round(smem, in + off, link + off, mt + off, n, base, lp, strategy, carry, sym_local + off + base);
+		if (threadIdx.x == 0) {
+			RoundRec r;
+			r.p = carry.st.p;
+			r.mlen = carry.st.mlen;
+			r.mstart = carry.st.mstart;
+			r.prevAvail = carry.st.prevAvail;
+			r.last_top = carry.last_top;
+			r.cnt = cnt;
+			rr[base / kRound] = r;
+		}
+	}
+}
+
+__global__ void __launch_bounds__(32)
+    k_parse_fix(const uint8_t *__restrict__ in, const uint16_t *__restrict__ link, const uint2 *__restrict__ mt,
+                uint32_t *__restrict__ sym_local, const int64_t *__restrict__ in_off, const int64_t *__restrict__ in_len,
+                const uint32_t *__restrict__ rnd_off, RoundRec *__restrict__ recs, uint32_t chunk, LevelParams lp, int strategy) {
+	extern __shared__ __align__(16) uint8_t smem[];
 	const int stream = blockIdx.x;
 	const uint32_t n = (uint32_t)in_len[stream];
+	if (n <= chunk) return; // a single chunk was parsed from the true initial state
 	const int64_t off = in_off[stream];
-	const uint8_t *data = in + off;
-	const uint16_t *lnk = link + off;
-	const uint2 *tab = mt + off;
-	uint32_t *sout = sym + off;
-	uint32_t *bstart = blk_start + blk_off[stream];
-	uint32_t *bptop = blk_ptop + blk_off[stream];
-
-	ParseCarry carry; // uniform across the warp
-	parse_init(carry.st);
-	carry.last_top = 0;
-	uint32_t total = 0;
-	if (lane == 0) bstart[0] = 0;
-	for (uint32_t base = 0; base < n; base += kRound) {
-		const uint32_t rn = (n - base > (uint32_t)kRound) ? (uint32_t)kRound : n - base;
-		__syncwarp();
-		// stage the round with 16-byte async copies (LDGSTS): all of them are in flight at once, no register staging
-		for (uint32_t i = 2 * lane; i + 1 < rn; i += 64)
-			__pipeline_memcpy_async(&s_tab[(i >> kSegShift) * kSegStride + (i & (kSeg - 1))], &tab[base + i], 16);
+	RoundRec *rr = recs + rnd_off[stream];
+	for (uint32_t c0 = chunk; c0 < n; c0 += chunk) {
+		const uint32_t c1 = (n - c0 > chunk) ? c0 + chunk : n;
+		ParseCarry truth = rec_carry(rr[c0 / kRound - 1]); // exit of the previous chunk's last round, exact by induction
 		{
-			// bytes [base - 16, base + rn) rounded up to 16 (the input slot has 16 bytes of slack behind n)
-			const uint32_t c0 = base ? 0u : 1u, c1 = (16 + rn + 15) >> 4;
-			for (uint32_t c = c0 + lane; c < c1; c += 32) __pipeline_memcpy_async(s_dat + 16 * c, data + base - 16 + 16 * c, 16);
+			ParseCarry guess = clean_carry(c0);
+			guess.last_top = truth.last_top; // irrelevant here: the chunk processes at least one loop top
+			if (carry_equal(truth, guess)) continue; // the guess was right
 		}
-		__pipeline_commit();
-		if ((rn & 1) && lane == 0) s_tab[((rn - 1) >> kSegShift) * kSegStride + ((rn - 1) & (kSeg - 1))] = tab[base + rn - 1];
-		__pipeline_wait_prior(0);
-		__syncwarp();
-		const uint32_t seg_end = base + (uint32_t)(lane + 1) * kSeg;
-		auto tabf = [&](uint32_t p, uint32_t &a, uint32_t &b) {
-			const uint32_t i = p - base;
-			const uint2 t = s_tab[(i >> kSegShift) * kSegStride + (i & (kSeg - 1))];
-			a = t.x;
-			b = t.y;
-		};
-		auto bytef = [&](uint32_t q) { return (uint32_t)s_dat[q + 16 - base]; };
-		auto slowf = [&](uint32_t p, uint32_t m0, uint32_t budget) { return match_search_above(data, lnk, p, n, m0, budget); };
-		ParseCarry entry, ex;
-		if (lane == 0) entry = carry;
-		else {
-			parse_init(entry.st);
-			entry.st.p = base + (uint32_t)lane * kSeg;
-			entry.last_top = 0;
+		for (uint32_t base = c0; base < c1; base += kRound) {
+			const ParseCarry old_exit = rec_carry(rr[base / kRound]);
+			const uint32_t cnt = parse_round(smem, in + off, link + off, mt + off, n, base, lp, strategy, truth, sym_local + off + base);
+			__syncwarp();
+			if (threadIdx.x == 0) {
+				RoundRec r;
+				r.p = truth.st.p;
+				r.mlen = truth.st.mlen;
+				r.mstart = truth.st.mstart;
+				r.prevAvail = truth.st.prevAvail;
+				r.last_top = truth.last_top;
+				r.cnt = cnt;
+				rr[base / kRound] = r;
+			}
+			__syncwarp();
+			if (carry_equal(truth, old_exit)) break; // re-synchronised: the rest of the chunk stands as parsed
 		}
-		ex = entry;
-		uint32_t cnt = 0;
-		bool changed = true;
-		const uint32_t lim = seg_end < n ? seg_end : n;
-		for (int it = 0; it < 34; it++) {
-			// all lanes step together and re-converge every iteration (a per-lane loop would leave them diverged)
-			if (changed) {
-				ex = entry;
-				cnt = 0;
-			}
-			bool act = changed && ex.st.p < lim;
-			while (__any_sync(0xffffffffu, act)) {
-				if (act) {
-					ex.last_top = ex.st.p;
-					uint32_t s2;
-					cnt += (uint32_t)parse_step(ex.st, n, lp, strategy, tabf, bytef, slowf, s2);
-					act = ex.st.p < lim;
-				}
-				__syncwarp();
-			}
-			const ParseCarry ne = shfl_carry(ex, lane == 0 ? 0 : lane - 1);
-			changed = false;
-			if (lane > 0) {
-				changed = !carry_equal(ne, entry);
-				entry = ne;
-			}
-			if (!__any_sync(0xffffffffu, changed)) break;
-		}
-		// final pass: emit at prefix-summed offsets
-		uint32_t incl = cnt;
+	}
+}
+
+// exclusive scan of the rounds' symbol counts of one stream; also the end-of-stream bookkeeping
+__global__ void __launch_bounds__(256)
+    k_parse_scan(const uint8_t *__restrict__ in, const int64_t *__restrict__ in_off, const int64_t *__restrict__ in_len,
+                 const uint32_t *__restrict__ rnd_off, const RoundRec *__restrict__ recs, uint32_t *__restrict__ rnd_symoff,
+                 uint32_t *__restrict__ sym, uint32_t *__restrict__ nsyms, uint32_t *__restrict__ nblocks,
+                 const uint32_t *__restrict__ blk_off, uint32_t *__restrict__ blk_start, uint32_t *__restrict__ blk_ptop, int end_mode) {
+	__shared__ uint32_t s_part[8];
+	__shared__ uint32_t s_carry;
+	const int stream = blockIdx.x;
+	const uint32_t n = (uint32_t)in_len[stream];
+	const uint32_t nr = (n + kRound - 1) / kRound;
+	const RoundRec *rr = recs + rnd_off[stream];
+	uint32_t *so = rnd_symoff + rnd_off[stream];
+	if (threadIdx.x == 0) s_carry = 0;
+	__syncthreads();
+	for (uint32_t b = 0; b < nr; b += 256) {
+		const uint32_t i = b + threadIdx.x;
+		const uint32_t v = i < nr ? rr[i].cnt : 0u;
+		uint32_t incl = v;
 		for (int o = 1; o < 32; o <<= 1) {
 			const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-			if (lane >= o) incl += t;
+			if ((threadIdx.x & 31) >= o) incl += t;
 		}
-		uint32_t idx = total + incl - cnt;
-		ParseCarry c = entry;
-		{
-			bool act = c.st.p < lim;
-			while (__any_sync(0xffffffffu, act)) {
-				if (act) {
-					const uint32_t top = c.st.p;
-					c.last_top = top;
-					uint32_t s2;
-					if (parse_step(c.st, n, lp, strategy, tabf, bytef, slowf, s2)) {
-						sout[idx] = s2;
-						if (((idx + 1) & (uint32_t)(kBlockSyms - 1)) == 0) {
-							const uint32_t b = (idx + 1) >> 14;
-							bptop[b - 1] = top;
-							bstart[b] = sym_dist(s2) ? top - 1 + sym_len(s2) : top; // bytes covered once this symbol is in
-						}
-						++idx;
-					}
-					act = c.st.p < lim;
-				}
-				__syncwarp();
-			}
-		}
-		total += __shfl_sync(0xffffffffu, incl, 31);
-		carry = shfl_carry(c, 31);
+		if ((threadIdx.x & 31) == 31) s_part[threadIdx.x >> 5] = incl;
+		__syncthreads();
+		uint32_t woff = 0;
+		for (int k = 0; k < (int)(threadIdx.x >> 5); k++) woff += s_part[k];
+		const uint32_t carry = s_carry;
+		if (i < nr) so[i] = carry + woff + incl - v;
+		__syncthreads();
+		if (threadIdx.x == 255) s_carry = carry + woff + incl;
+		__syncthreads();
 	}
-	if (lane == 0) {
-		uint32_t nblk;
-		const bool ended_full = end_mode == B200Z_END_FINISH && total > 0 && (total & (uint32_t)(kBlockSyms - 1)) == 0 && !carry.st.prevAvail;
-		if (ended_full) {
-			nblk = total >> 14;
-		} else {
+	if (threadIdx.x == 0) {
+		uint32_t total = s_carry;
+		ParseCarry fin = nr ? rec_carry(rr[nr - 1]) : clean_carry(0);
+		if (nr == 0) fin.last_top = 0;
+		uint32_t *bstart = blk_start + blk_off[stream];
+		uint32_t *bptop = blk_ptop + blk_off[stream];
+		bstart[0] = 0;
+		uint32_t nblk = total >> 14;
+		const bool ended_full = end_mode == B200Z_END_FINISH && total > 0 && (total & (uint32_t)(kBlockSyms - 1)) == 0 && !fin.st.prevAvail;
+		if (!ended_full) {
 			// final flush at lookahead == 0 (DeflaterEngine.cs:750-768)
-			nblk = total >> 14;
-			if (carry.st.prevAvail) sout[total++] = sym_lit(data[carry.st.p - 1]);
-			bptop[nblk] = carry.last_top;
+			if (fin.st.prevAvail) (sym + in_off[stream])[total++] = sym_lit(in[in_off[stream] + fin.st.p - 1]);
+			bptop[nblk] = fin.last_top;
 			++nblk;
 		}
 		nsyms[stream] = total;
 		nblocks[stream] = nblk;
+	}
+}
+
+// moves every round's symbols to their final place and records the block cuts that fall inside the round
+__global__ void __launch_bounds__(128)
+    k_parse_gather(const uint32_t *__restrict__ sym_local, uint32_t *__restrict__ sym, const int64_t *__restrict__ in_off,
+                   const int64_t *__restrict__ in_len, const int2 *__restrict__ rnd_desc, const uint32_t *__restrict__ rnd_off,
+                   const RoundRec *__restrict__ recs, const uint32_t *__restrict__ rnd_symoff, const uint32_t *__restrict__ blk_off,
+                   uint32_t *__restrict__ blk_start, uint32_t *__restrict__ blk_ptop) {
+	const int2 d = rnd_desc[blockIdx.x]; // (stream, first round of this CTA's group of 4)
+	const int64_t off = in_off[d.x];
+	const uint32_t n = (uint32_t)in_len[d.x];
+	const uint32_t nr = (n + kRound - 1) / kRound;
+	const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const uint32_t r = (uint32_t)d.y + (uint32_t)w;
+	if (r >= nr) return;
+	const RoundRec *rr = recs + rnd_off[d.x];
+	const uint32_t cnt = rr[r].cnt;
+	const uint32_t dst0 = rnd_symoff[rnd_off[d.x] + r];
+	const uint32_t *src = sym_local + off + r * (uint32_t)kRound;
+	uint32_t *dst = sym + off + dst0;
+	for (uint32_t i = lane; i < cnt; i += 32) dst[i] = src[i];
+	// block cuts: global symbol index idx with (idx + 1) % 16384 == 0
+	if (lane == 0 && cnt) {
+		const uint32_t first_b = (dst0 + (uint32_t)kBlockSyms) >> 14;          // smallest b with b * 16384 - 1 >= dst0
+		const uint32_t last_idx = dst0 + cnt - 1;
+		if (first_b * (uint32_t)kBlockSyms - 1 <= last_idx) {
+			// bytes covered before this round's first symbol: entry.p, minus the pending literal if there is one
+			uint32_t bytes;
+			if (r == 0) bytes = 0;
+			else bytes = rr[r - 1].p - (rr[r - 1].prevAvail ? 1u : 0u);
+			uint32_t *bstart = blk_start + blk_off[d.x];
+			uint32_t *bptop = blk_ptop + blk_off[d.x];
+			uint32_t nextb = first_b;
+			for (uint32_t i = 0; i < cnt; i++) {
+				const uint32_t s2 = src[i];
+				const uint32_t L = sym_len(s2);
+				bytes += L;
+				if (dst0 + i + 1 == nextb * (uint32_t)kBlockSyms) {
+					// the loop top at which the symbol was tallied: literal -> the position after it; match -> its start + 1
+					bptop[nextb - 1] = sym_dist(s2) ? bytes - L + 1 : bytes;
+					bstart[nextb] = bytes;
+					++nextb;
+				}
+			}
+		}
 	}
 }
 
@@ -724,7 +875,19 @@ int deflate_plan_build(b200z_plan *p) {
 	p->out_off.resize(n);
 	p->out_cap.resize(n);
 	int64_t io = 0, oo = 0;
-	std::vector<int2> runs, tiles;
+	std::vector<int2> runs, tiles, rgroups;
+	std::vector<ChunkDesc> chunks;
+	std::vector<uint32_t> rnd_off(n + 1);
+	uint32_t nrounds = 0;
+	int64_t maxlen = 0;
+	for (int i = 0; i < n; i++) maxlen = p->in_len[i] > maxlen ? p->in_len[i] : maxlen;
+	// chunk of the parse: 32 Ki positions, grown so that no stream has more than ~1024 chunks (k_parse_fix walks them serially)
+	uint32_t chunk = 32768;
+	{
+		const int64_t need = (maxlen / 1024 + kRound - 1) / kRound * kRound;
+		if (need > (int64_t)chunk) chunk = (uint32_t)need;
+	}
+	p->parse_chunk = chunk;
 	std::vector<uint32_t> blk_off(n + 1);
 	std::vector<int32_t> blk_desc;
 	uint32_t nblk = 0;
@@ -741,6 +904,12 @@ int deflate_plan_build(b200z_plan *p) {
 		oo += p->out_cap[i];
 		for (int64_t s = 0; s < len; s += kRun) runs.push_back(make_int2(i, (int)s));
 		for (int64_t s = 0; s < len; s += kTile) tiles.push_back(make_int2(i, (int)s));
+		for (int64_t s = 0; s < len; s += chunk)
+			chunks.push_back(ChunkDesc{i, (uint32_t)s, (uint32_t)(len - s > (int64_t)chunk ? s + chunk : len)});
+		rnd_off[i] = nrounds;
+		const uint32_t nr = (uint32_t)((len + kRound - 1) / kRound);
+		for (uint32_t r = 0; r < nr; r += 4) rgroups.push_back(make_int2(i, (int)r));
+		nrounds += nr;
 		blk_off[i] = nblk;
 		const uint32_t maxb = (uint32_t)(len / kBlockSyms) + 2;
 		for (uint32_t b = 0; b < maxb; b++) blk_desc.push_back(i);
@@ -754,10 +923,15 @@ int deflate_plan_build(b200z_plan *p) {
 			slens.push_back((int64_t)dst);
 		}
 	}
+	rnd_off[n] = nrounds;
 	if (lp.func != 2) {
 		runs.clear();
 		tiles.clear();
+		chunks.clear();
+		rgroups.clear();
 	}
+	p->n_chunks = (int)chunks.size();
+	p->n_rgroups = (int)rgroups.size();
 	blk_off[n] = nblk;
 	p->in_bytes = io;
 	p->out_bytes = oo;
@@ -782,6 +956,12 @@ int deflate_plan_build(b200z_plan *p) {
 	if (lp.func == 2) {
 		p->o_link = ws.reserve(2ll * io + 64);
 		p->o_mt = ws.reserve(8ll * io + 64);
+		p->o_sym_local = ws.reserve(4ll * io + 64);
+		p->o_chunks = ws.reserve((int64_t)sizeof(ChunkDesc) * (chunks.size() + 1));
+		p->o_rgroups = ws.reserve(8ll * (rgroups.size() + 1));
+		p->o_rnd_off = ws.reserve(4ll * (n + 1));
+		p->o_recs = ws.reserve((int64_t)sizeof(RoundRec) * (nrounds + 1));
+		p->o_rnd_symoff = ws.reserve(4ll * (nrounds + 1));
 	}
 	if (lp.func != 0) p->o_sym = ws.reserve(4ll * io + 64);
 	if (lp.func == 0) {
@@ -809,13 +989,20 @@ int deflate_plan_build(b200z_plan *p) {
 	if (!ck_tiles.empty())
 		B200Z_CUDA(cudaMemcpy(ws.at<CkTile>(p->o_ck_desc), ck_tiles.data(), sizeof(CkTile) * ck_tiles.size(),
 		                      cudaMemcpyHostToDevice));
+	if (lp.func == 2) {
+		if (!chunks.empty())
+			B200Z_CUDA(cudaMemcpy(ws.at<ChunkDesc>(p->o_chunks), chunks.data(), sizeof(ChunkDesc) * chunks.size(), cudaMemcpyHostToDevice));
+		if (!rgroups.empty())
+			B200Z_CUDA(cudaMemcpy(ws.at<int2>(p->o_rgroups), rgroups.data(), 8ll * rgroups.size(), cudaMemcpyHostToDevice));
+		B200Z_CUDA(cudaMemcpy(ws.at<uint32_t>(p->o_rnd_off), rnd_off.data(), 4ll * (n + 1), cudaMemcpyHostToDevice));
+	}
 	if (!sblocks.empty())
 		B200Z_CUDA(cudaMemcpy(ws.at<StoredBlock>(p->o_stored), sblocks.data(), sizeof(StoredBlock) * sblocks.size(), cudaMemcpyHostToDevice));
 	if (!slens.empty()) B200Z_CUDA(cudaMemcpy(ws.at<int64_t>(p->o_slens), slens.data(), 8ll * slens.size(), cudaMemcpyHostToDevice));
 	B200Z_CUDA(cudaFuncSetAttribute(k_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, kFastSmem));
 	B200Z_CUDA(cudaFuncSetAttribute(k_links, cudaFuncAttributeMaxDynamicSharedMemorySize, kLinksSmem));
 	B200Z_CUDA(cudaFuncSetAttribute(k_match, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileData + 2 * 2 * kTile));
-	p->launches = (lp.func == 2 ? 6 : (lp.func == 1 ? 4 : 2)) + (p->wrap != B200Z_WRAP_RAW ? 3 : 0); // + one memset node
+	p->launches = (lp.func == 2 ? 9 : (lp.func == 1 ? 4 : 2)) + (p->wrap != B200Z_WRAP_RAW ? 3 : 0); // + one memset node
 	return B200Z_OK;
 }
 
@@ -867,8 +1054,21 @@ int deflate_plan_run(b200z_plan *p, const uint8_t *d_in, uint8_t *d_out, int64_t
 			k_match<<<p->n_tiles, kMatchThreads, kTileData + 2 * 2 * kTile, s>>>(d_in, link, mt, in_off, in_len,
 			                                                                   ws.at<int2>(p->o_tile_desc), lp);
 		p->mark(s, "k_parse");
-		k_parse<<<n, 32, kParseSmem, s>>>(d_in, link, mt, sym, in_off, in_len, nsyms, nblocks, blk_off, blk_start, blk_ptop, lp,
-		                                  p->strategy, p->end_mode);
+		{
+			uint32_t *sym_local = ws.at<uint32_t>(p->o_sym_local);
+			const uint32_t *rnd_off = ws.at<uint32_t>(p->o_rnd_off);
+			RoundRec *recs = ws.at<RoundRec>(p->o_recs);
+			uint32_t *rnd_symoff = ws.at<uint32_t>(p->o_rnd_symoff);
+			if (p->n_chunks)
+				k_parse_chunk<<<p->n_chunks, 32, kParseSmem, s>>>(d_in, link, mt, sym_local, in_off, in_len, ws.at<ChunkDesc>(p->o_chunks),
+				                                                 rnd_off, recs, lp, p->strategy);
+			k_parse_fix<<<n, 32, kParseSmem, s>>>(d_in, link, mt, sym_local, in_off, in_len, rnd_off, recs, p->parse_chunk, lp, p->strategy);
+			k_parse_scan<<<n, 256, 0, s>>>(d_in, in_off, in_len, rnd_off, recs, rnd_symoff, sym, nsyms, nblocks, blk_off, blk_start,
+			                               blk_ptop, p->end_mode);
+			if (p->n_rgroups)
+				k_parse_gather<<<p->n_rgroups, 128, 0, s>>>(sym_local, sym, in_off, in_len, ws.at<int2>(p->o_rgroups), rnd_off, recs,
+				                                           rnd_symoff, blk_off, blk_start, blk_ptop);
+		}
 	}
 	p->mark(s, "k_plan");
 	k_plan<<<p->n_blkmax, kPlanThreads, 0, s>>>(sym, in_off, in_len, nsyms, nblocks, blk_off, blk_desc, blk_start, blk_ptop, meta,

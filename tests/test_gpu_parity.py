@@ -130,6 +130,18 @@ def test_deflate_window_slides_and_t8(z, oracle):
         assert o == oracle.deflate(d, level=6)
 
 
+def test_deflate_long_single_streams(z, oracle):
+    """C4 shape in small: one long stream is parsed by hundreds of speculative chunks that are then stitched"""
+    from sharpziplib_b200 import datagen
+    bufs = [datagen.log_stream(16 << 20).tobytes(), datagen.gen_db(5 << 20, 77).tobytes(), bytes(3 << 20),
+            datagen.Rng(9).bytes(2 << 20).tobytes()]
+    outs, _ = z.deflate_batch(bufs, level=6)
+    refs = oracle.batch(0, bufs, level=6, threads=4)
+    assert outs == refs
+    back, used, status = z.inflate_batch(outs, [len(b) for b in bufs])
+    assert back == bufs
+
+
 def test_deflate_c3_shape_parity_and_properties(z, oracle):
     """64 buffers of the C3 shape (256 KiB Silesia-mix): bit-exact vs the oracle, valid deflate, round trip."""
     from sharpziplib_b200 import datagen
