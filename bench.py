@@ -104,6 +104,29 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def host_threads():
+    """threads the reference arm may really use: logical CPUs, capped by the affinity mask and the cgroup CPU quota"""
+    n = os.cpu_count() or 1
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except Exception:
+        pass
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            txt = open(path).read().split()
+            if path.endswith("cpu.max"):
+                if txt[0] != "max":
+                    n = min(n, max(1, int(float(txt[0]) / float(txt[1]) + 0.5)))
+            else:
+                q = int(txt[0])
+                if q > 0:
+                    per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+                    n = min(n, max(1, int(q / per + 0.5)))
+        except Exception:
+            pass
+    return n
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -138,7 +161,7 @@ def run_reference(args, rank, world, out):
         return
     import oracle_lib as O
     O.build()
-    threads = os.cpu_count() or 1
+    threads = host_threads()
     # bounded sample: 1/4 of each leg's buffers per step (64 MiB deflate + 64 MiB inflate of the same generators)
     n_def, n_inf = max(threads, N_DEFLATE // 4), max(min(threads, N_INFLATE), N_INFLATE // 4)
     n_def, n_inf = min(n_def, N_DEFLATE), min(n_inf, N_INFLATE)
@@ -204,7 +227,7 @@ def main():
         broadcast_static_tables(dist, device=torch.device("cuda", local_rank))  # the path's only collective
     n_def = N_DEFLATE // (8 if args.small else 1)
     n_inf = N_INFLATE // (8 if args.small else 1)
-    ncpu = os.cpu_count() or 1
+    ncpu = host_threads()
     workers = max(1, min(32, ncpu // max(1, world)))
     t_setup = time.time()
     d_np, t_np = make_inputs(rank, n_def, n_inf, workers)
