@@ -70,13 +70,49 @@ int b200z_checksum_batch_device(int kind, const uint8_t *d_data, const int64_t *
  * ------------------------------------------------------------------------------------------------------------- */
 typedef struct b200z_plan b200z_plan;
 
+/* ---- streams with history ---------------------------------------------------------------------------------
+ * A deflate stream whose window is not empty when the data starts:
+ *   B200Z_HIST_DICTIONARY  Deflater.SetDictionary (Deflater.cs:372-381 -> DeflaterEngine.SetDictionary :198-229): the
+ *                          history is the dictionary cut to its last MAX_DIST (32506) bytes; dictionaries shorter than
+ *                          MIN_MATCH are ignored by the reference, pass hist_len 0 for them.  All levels.
+ *   B200Z_HIST_CONTINUE    more input after Deflater.Flush() (Deflater.cs:488-506 leaves the engine re-entrant): the
+ *                          history is the last min(32768, bytes so far) bytes of everything the window has seen
+ *                          (dictionary included).  Levels 5-9 (DeflateSlow) only, B200Z_E_UNSUPPORTED below.
+ * Input slot i of such a plan holds hist_len[i] history bytes directly followed by the in_len[i] data bytes;
+ * b200z_plan_in_offset(i) is the start of the history.  The checksum covers the data only; with check_seeded the
+ * d_check array handed to b200z_plan_run carries the running values in and the updated values out (Adler32.Update /
+ * Crc32.Update on an existing value).  The produced bits start at bit `bit_base` of output byte 0 (the bits below are
+ * left zero: OR in the tail of the previous segment, PendingBuffer.cs:168-189 keeps it in its bit register). */
+#define B200Z_HIST_NONE 0
+#define B200Z_HIST_DICTIONARY 1
+#define B200Z_HIST_CONTINUE 2
+typedef struct b200z_history {
+	int32_t kind;                   /* B200Z_HIST_* for every stream of the plan */
+	int32_t check_seeded;           /* != 0: d_check is in/out (running checksum) instead of out */
+	const int64_t *hist_len;        /* [n] history bytes in front of the data */
+	const int64_t *pos_base;        /* [n] CONTINUE: bytes the window has seen before the data (dictionary + TotalIn);
+	                                   decides the SlideWindow phase (DeflaterEngine.cs:441-462); NULL/DICTIONARY: hist_len */
+	const int32_t *bit_base;        /* [n] 0..7 bits already taken in the first output byte; NULL = 0 */
+	const uint8_t *const *hist_mask; /* [n] hist_len[i] flags, 1 = position was never entered into the hash chains
+	                                   (InsertString needs MIN_MATCH bytes of lookahead, :782/:819: the last two positions
+	                                   of every earlier segment); NULL entry = the last two history positions */
+} b200z_history;
+int b200z_deflate_plan_create_ex(int32_t n, const int64_t *in_len, int level, int strategy, int wrap, int end_mode,
+                                 const b200z_history *hist, b200z_plan **plan);
+
 int b200z_deflate_plan_create(int32_t n, const int64_t *in_len, int level, int strategy, int wrap, int end_mode,
                               b200z_plan **plan);
 int b200z_inflate_plan_create(int32_t n, const int64_t *comp_len, const int64_t *out_cap, int wrap, b200z_plan **plan);
+/* Inflater.SetDictionary (Inflater.cs:589-620 -> OutputWindow.CopyDict, OutputWindow.cs:151-171): dict_len[i] <= 32768
+ * bytes (the dictionary's tail) stored directly in front of stream i's compressed bytes; b200z_plan_in_offset(i) is
+ * where the dictionary starts, b200z_plan_data_offset(i) where the compressed bytes start (16-byte aligned). */
+int b200z_inflate_plan_create_ex(int32_t n, const int64_t *comp_len, const int64_t *out_cap, int wrap,
+                                 const int64_t *dict_len, b200z_plan **plan);
 int b200z_plan_destroy(b200z_plan *plan);
 int64_t b200z_plan_in_bytes(const b200z_plan *plan);          /* size of the input blob  */
 int64_t b200z_plan_out_bytes(const b200z_plan *plan);         /* size of the output blob */
-int64_t b200z_plan_in_offset(const b200z_plan *plan, int32_t i);
+int64_t b200z_plan_in_offset(const b200z_plan *plan, int32_t i);   /* start of slot i (history/dictionary first) */
+int64_t b200z_plan_data_offset(const b200z_plan *plan, int32_t i); /* start of slot i's data behind the history */
 int64_t b200z_plan_out_offset(const b200z_plan *plan, int32_t i);
 int64_t b200z_plan_out_capacity(const b200z_plan *plan, int32_t i);
 int64_t b200z_plan_workspace_bytes(const b200z_plan *plan);

@@ -70,7 +70,11 @@ _SIGS = {
     "b200z_adler32": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(C.c_uint32)]),
     "b200z_checksum_batch_device": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "b200z_deflate_plan_create": (C.c_int, [C.c_int32, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "b200z_deflate_plan_create_ex": (C.c_int, [C.c_int32, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                               C.POINTER(C.c_void_p)]),
     "b200z_inflate_plan_create": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]),
+    "b200z_inflate_plan_create_ex": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "b200z_plan_data_offset": (C.c_int64, [C.c_void_p, C.c_int32]),
     "b200z_plan_destroy": (C.c_int, [C.c_void_p]),
     "b200z_plan_in_bytes": (C.c_int64, [C.c_void_p]),
     "b200z_plan_out_bytes": (C.c_int64, [C.c_void_p]),
@@ -118,6 +122,14 @@ _SIGS = {
 }
 
 EXPORTS = tuple(sorted(_SIGS))
+
+HIST_NONE, HIST_DICTIONARY, HIST_CONTINUE = 0, 1, 2
+
+
+class History(C.Structure):
+    """b200z_history (include/b200z.h): what a stream's window already holds when its data starts"""
+    _fields_ = [("kind", C.c_int32), ("check_seeded", C.c_int32), ("hist_len", C.c_void_p), ("pos_base", C.c_void_p),
+                ("bit_base", C.c_void_p), ("hist_mask", C.c_void_p)]
 
 
 def lib():

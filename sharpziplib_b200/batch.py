@@ -17,6 +17,8 @@ class _Plan:
         self.in_bytes = L.b200z_plan_in_bytes(handle)
         self.out_bytes = L.b200z_plan_out_bytes(handle)
         self.in_offsets = np.array([L.b200z_plan_in_offset(handle, i) for i in range(n)], dtype=np.int64)
+        # where slot i's data starts (behind a history / preset dictionary, if the plan has one)
+        self.data_offsets = np.array([L.b200z_plan_data_offset(handle, i) for i in range(n)], dtype=np.int64)
         self.out_offsets = np.array([L.b200z_plan_out_offset(handle, i) for i in range(n)], dtype=np.int64)
         self.workspace_bytes = L.b200z_plan_workspace_bytes(handle)
         self.launches = L.b200z_plan_launches(handle)
@@ -66,11 +68,21 @@ class _Plan:
 class DeflatePlan(_Plan):
     """n independent streams, each what `new Deflater(level, true)` + SetInput(all) + Finish() would produce."""
 
-    def __init__(self, in_lens, level=6, strategy=0, wrap=_lib.WRAP_RAW, end_mode=_lib.END_FINISH):
+    def __init__(self, in_lens, level=6, strategy=0, wrap=_lib.WRAP_RAW, end_mode=_lib.END_FINISH, dict_lens=None):
+        """dict_lens: per-stream preset-dictionary bytes (Deflater.SetDictionary; at most 32506, the reference keeps the
+        dictionary's tail) stored in the input slot directly in front of the stream's data."""
         lens = np.ascontiguousarray(in_lens, dtype=np.int64)
         h = C.c_void_p()
-        _lib.raise_for(_lib.lib().b200z_deflate_plan_create(lens.size, lens.ctypes.data, level, strategy, wrap, end_mode,
-                                                           C.byref(h)))
+        if dict_lens is None:
+            _lib.raise_for(_lib.lib().b200z_deflate_plan_create(lens.size, lens.ctypes.data, level, strategy, wrap, end_mode,
+                                                               C.byref(h)))
+            self.dict_lens = np.zeros(lens.size, dtype=np.int64)
+        else:
+            dl = np.ascontiguousarray(dict_lens, dtype=np.int64)
+            hs = _lib.History(_lib.HIST_DICTIONARY, 0, dl.ctypes.data, None, None, None)
+            _lib.raise_for(_lib.lib().b200z_deflate_plan_create_ex(lens.size, lens.ctypes.data, level, strategy, wrap, end_mode,
+                                                                  C.addressof(hs), C.byref(h)))
+            self.dict_lens = dl
         self.in_lens = lens
         super().__init__(h, lens.size)
 
@@ -78,11 +90,14 @@ class DeflatePlan(_Plan):
 class InflatePlan(_Plan):
     """n independent raw deflate streams of comp_lens bytes decoding into at most out_caps bytes each."""
 
-    def __init__(self, comp_lens, out_caps, wrap=_lib.WRAP_RAW):
+    def __init__(self, comp_lens, out_caps, wrap=_lib.WRAP_RAW, dict_lens=None):
         cl = np.ascontiguousarray(comp_lens, dtype=np.int64)
         oc = np.ascontiguousarray(out_caps, dtype=np.int64)
         h = C.c_void_p()
-        _lib.raise_for(_lib.lib().b200z_inflate_plan_create(cl.size, cl.ctypes.data, oc.ctypes.data, wrap, C.byref(h)))
+        dl = None if dict_lens is None else np.ascontiguousarray(dict_lens, dtype=np.int64)
+        _lib.raise_for(_lib.lib().b200z_inflate_plan_create_ex(cl.size, cl.ctypes.data, oc.ctypes.data, wrap,
+                                                              None if dl is None else dl.ctypes.data, C.byref(h)))
+        self.dict_lens = dl
         self.comp_lens, self.out_caps = cl, oc
         super().__init__(h, cl.size)
 

@@ -149,7 +149,7 @@ struct HostRunResult {
 };
 
 static int run_plan_host(b200z_plan *plan, const uint8_t *const *in, PinnedBuf &hin, PinnedBuf &hout, DevBuf &din,
-                         DevBuf &dout, DevBuf &dmeta, HostRunResult &r, bool fetch_all_out) {
+                         DevBuf &dout, DevBuf &dmeta, HostRunResult &r, bool fetch_all_out, const uint32_t *check_seed = nullptr) {
 	const int n = plan->n;
 	int rc;
 	if ((rc = hin.ensure((size_t)plan->in_bytes + 256))) return rc;
@@ -165,6 +165,7 @@ static int run_plan_host(b200z_plan *plan, const uint8_t *const *in, PinnedBuf &
 	int64_t *d_in_used = d_out_len + n;
 	int32_t *d_status = reinterpret_cast<int32_t *>(d_in_used + n);
 	uint32_t *d_check = reinterpret_cast<uint32_t *>(d_status + n);
+	if (check_seed) B200Z_CUDA(cudaMemcpyAsync(d_check, check_seed, 4ull * n, cudaMemcpyHostToDevice, s)); // running values
 	rc = b200z_plan_run(plan, din.p, dout.p, d_out_len, d_status, d_check, d_in_used, (void *)s);
 	if (rc) return rc;
 	r.out_len.assign(n, 0);
@@ -249,6 +250,11 @@ int64_t b200z_deflate_bound(int64_t len) { return len + (len >> 3) + 1024; }
 // ---- plans -------------------------------------------------------------------------------------------
 int b200z_deflate_plan_create(int32_t n, const int64_t *in_len, int level, int strategy, int wrap, int end_mode,
                               b200z_plan **plan) {
+	return b200z_deflate_plan_create_ex(n, in_len, level, strategy, wrap, end_mode, nullptr, plan);
+}
+
+int b200z_deflate_plan_create_ex(int32_t n, const int64_t *in_len, int level, int strategy, int wrap, int end_mode,
+                                 const b200z_history *hist, b200z_plan **plan) {
 	if (!plan || n < 0 || (n > 0 && !in_len)) {
 		set_error("bad arguments");
 		return B200Z_E_ARG;
@@ -272,6 +278,44 @@ int b200z_deflate_plan_create(int32_t n, const int64_t *in_len, int level, int s
 	p->wrap = wrap;
 	p->end_mode = end_mode;
 	p->in_len.assign(in_len, in_len + n);
+	if (hist && hist->kind != B200Z_HIST_NONE && n > 0) {
+		if ((hist->kind != B200Z_HIST_DICTIONARY && hist->kind != B200Z_HIST_CONTINUE) || !hist->hist_len) {
+			set_error("history: kind/hist_len");
+			delete p;
+			return B200Z_E_ARG;
+		}
+		if (hist->kind == B200Z_HIST_CONTINUE && level < 5) {
+			// DeflateStored/DeflateFast keep window-relative state across Deflate() calls that is not a function of the
+			// stream position (strstart vs. blockStart after partial fills); only DeflateSlow (levels 5-9) is re-entrant here
+			set_error("continuing a stream after Flush() is accelerated for levels 5-9 only");
+			delete p;
+			return B200Z_E_UNSUPPORTED;
+		}
+		p->hist_kind = hist->kind;
+		p->check_seeded = hist->check_seeded != 0;
+		p->hist.assign(hist->hist_len, hist->hist_len + n);
+		p->pos_base.resize(n);
+		p->bit_base.resize(n);
+		p->hist_mask.resize(n);
+		for (int i = 0; i < n; i++) {
+			const int64_t H = p->hist[i];
+			if (H < 0 || H > 32768 || (hist->kind == B200Z_HIST_DICTIONARY && H > kMaxDist)) {
+				set_error("stream %d: history of %lld bytes (at most %d)", i, (long long)H,
+				          hist->kind == B200Z_HIST_DICTIONARY ? kMaxDist : 32768);
+				delete p;
+				return B200Z_E_ARG;
+			}
+			p->pos_base[i] = (hist->pos_base && hist->kind == B200Z_HIST_CONTINUE) ? hist->pos_base[i] : H;
+			p->bit_base[i] = hist->bit_base ? hist->bit_base[i] : 0;
+			if (p->pos_base[i] < H || p->pos_base[i] > 0xFFFF0000ll || p->bit_base[i] < 0 || p->bit_base[i] > 7) {
+				set_error("stream %d: pos_base/bit_base", i);
+				delete p;
+				return B200Z_E_ARG;
+			}
+			if (hist->hist_mask && hist->hist_mask[i]) p->hist_mask[i].assign(hist->hist_mask[i], hist->hist_mask[i] + H);
+			p->in_len[i] += H; // the input slot holds history + data
+		}
+	}
 	rc = deflate_plan_build(p);
 	if (rc) {
 		p->ws.release();
@@ -283,6 +327,11 @@ int b200z_deflate_plan_create(int32_t n, const int64_t *in_len, int level, int s
 }
 
 int b200z_inflate_plan_create(int32_t n, const int64_t *comp_len, const int64_t *out_cap, int wrap, b200z_plan **plan) {
+	return b200z_inflate_plan_create_ex(n, comp_len, out_cap, wrap, nullptr, plan);
+}
+
+int b200z_inflate_plan_create_ex(int32_t n, const int64_t *comp_len, const int64_t *out_cap, int wrap, const int64_t *dict_len,
+                                 b200z_plan **plan) {
 	if (!plan || n < 0 || (n > 0 && (!comp_len || !out_cap)) || wrap < 0 || wrap > 2) {
 		set_error("bad arguments");
 		return B200Z_E_ARG;
@@ -295,6 +344,18 @@ int b200z_inflate_plan_create(int32_t n, const int64_t *comp_len, const int64_t 
 	p->wrap = wrap;
 	p->in_len.assign(comp_len, comp_len + n);
 	p->out_cap.assign(out_cap, out_cap + n);
+	if (dict_len && n > 0) {
+		p->hist_kind = B200Z_HIST_DICTIONARY;
+		p->hist.assign(dict_len, dict_len + n);
+		for (int i = 0; i < n; i++) {
+			if (p->hist[i] < 0 || p->hist[i] > 32768) { // OutputWindow.CopyDict keeps the last WindowSize bytes (:160-166)
+				set_error("stream %d: dictionary of %lld bytes (at most 32768)", i, (long long)p->hist[i]);
+				delete p;
+				return B200Z_E_ARG;
+			}
+			p->in_len[i] += p->hist[i];
+		}
+	}
 	rc = inflate_plan_build(p);
 	if (rc) {
 		p->ws.release();
@@ -342,6 +403,9 @@ int b200z_plan_destroy(b200z_plan *plan) {
 int64_t b200z_plan_in_bytes(const b200z_plan *p) { return p->in_bytes; }
 int64_t b200z_plan_out_bytes(const b200z_plan *p) { return p->out_bytes; }
 int64_t b200z_plan_in_offset(const b200z_plan *p, int32_t i) { return p->in_off[i]; }
+int64_t b200z_plan_data_offset(const b200z_plan *p, int32_t i) {
+	return p->in_off[i] + (p->hist.empty() ? 0 : p->hist[i]); // behind the history / dictionary
+}
 int64_t b200z_plan_out_offset(const b200z_plan *p, int32_t i) { return p->out_off[i]; }
 int64_t b200z_plan_out_capacity(const b200z_plan *p, int32_t i) { return p->out_cap[i]; }
 int64_t b200z_plan_workspace_bytes(const b200z_plan *p) { return p->ws.size; }
@@ -483,11 +547,12 @@ int b200z_checksum_batch_device(int kind, const uint8_t *d_data, const int64_t *
 }
 
 // ---- host-buffer batch calls ----------------------------------------------------------------------------
-static void zlib_header(int level, uint8_t h[2]) { // Deflater.cs:436-464 (trap T11)
+static void zlib_header(int level, uint8_t h[2], bool preset_dict = false) { // Deflater.cs:436-464 (trap T11)
 	int header = (8 + (7 << 4)) << 8;
 	int level_flags = (level - 1) >> 1;
 	if (level_flags < 0 || level_flags > 3) level_flags = 3;
 	header |= level_flags << 6;
+	if (preset_dict) header |= 0x20; // DeflaterConstants.PRESET_DICT
 	header += 31 - (header % 31);
 	h[0] = (uint8_t)(header >> 8);
 	h[1] = (uint8_t)header;
@@ -594,7 +659,13 @@ struct DeflaterH {
 	// Deflater.cs state bits (:96-110)
 	bool flushing = false, finishing = false, finished = false;
 	bool header_done = false;
-	bool flushed_once = false; // a sync flush has been emitted for the current segment
+	bool flushed_once = false; // a sync flush has been emitted and nothing was compressed since
+	// what the engine's window has seen so far, cut to its last 32768 bytes (preset dictionary, then every compressed
+	// segment); hist_mask flags the positions InsertString never saw (the last two of the dictionary / of each segment)
+	std::vector<uint8_t> history, hist_mask;
+	int64_t window_seen = 0;  // dictionary bytes kept + TotalIn: the SlideWindow phase of the next segment
+	bool dict_set = false, deflate_called = false;
+	uint32_t dict_adler = 0;
 	std::vector<uint8_t> input;    // everything SetInput handed over and not yet compressed
 	std::vector<uint8_t> pending;  // produced bytes not yet drained by Deflate()
 	size_t pending_pos = 0;
@@ -605,38 +676,73 @@ struct DeflaterH {
 	DevBuf din, dout, dmeta;
 };
 
+static void deflater_remember(DeflaterH *d, const uint8_t *seg, size_t len, size_t uninserted) {
+	// append a dictionary/segment to the carried window image
+	d->history.insert(d->history.end(), seg, seg + len);
+	d->hist_mask.insert(d->hist_mask.end(), len, 0);
+	for (size_t k = 0; k < uninserted && k < len; k++) d->hist_mask[d->hist_mask.size() - 1 - k] = 1;
+	if (d->history.size() > 32768) {
+		const size_t cut = d->history.size() - 32768;
+		d->history.erase(d->history.begin(), d->history.begin() + (ptrdiff_t)cut);
+		d->hist_mask.erase(d->hist_mask.begin(), d->hist_mask.begin() + (ptrdiff_t)cut);
+	}
+	d->window_seen += (int64_t)len;
+}
+
 static int deflater_run_device(DeflaterH *d, int end_mode) {
-	// compresses d->input as one stream; END_FLUSH keeps the stream open and may end inside a byte
-	if (d->tail.count != 0 || d->flushed_once) {
-		set_error("input after a sync Flush() continues a bit-unaligned stream with carried window state; this build "
-		          "only accelerates SetInput* -> [Flush] -> Finish sequences");
+	// compresses d->input as the next segment of the stream; END_FLUSH keeps the stream open and may end inside a byte
+	const int64_t len = (int64_t)d->input.size();
+	const int64_t H = (int64_t)d->history.size();
+	const bool continuing = d->total_in > 0 || d->flushed_once;
+	if (continuing && d->level == 0) {
+		set_error("level 0: input after a sync Flush() is not accelerated (DeflateStored block state is not positional)");
 		return B200Z_E_UNSUPPORTED;
 	}
-	const int64_t len = (int64_t)d->input.size();
+	b200z_history hs;
+	memset(&hs, 0, sizeof hs);
+	const int64_t pos_base = d->window_seen;
+	const int32_t bit_base = d->tail.count;
+	const uint8_t *mask = d->hist_mask.data();
+	hs.kind = continuing ? B200Z_HIST_CONTINUE : (H ? B200Z_HIST_DICTIONARY : B200Z_HIST_NONE);
+	hs.check_seeded = 1;
+	hs.hist_len = &H;
+	hs.pos_base = &pos_base;
+	hs.bit_base = &bit_base;
+	hs.hist_mask = &mask;
 	b200z_plan *plan = nullptr;
-	int rc = b200z_deflate_plan_create(1, &len, d->level, d->strategy, d->raw ? B200Z_WRAP_RAW : B200Z_WRAP_ZLIB,
-	                                   end_mode, &plan);
+	int rc = b200z_deflate_plan_create_ex(1, &len, d->level, d->strategy, d->raw ? B200Z_WRAP_RAW : B200Z_WRAP_ZLIB, end_mode,
+	                                      hs.kind != B200Z_HIST_NONE ? &hs : nullptr, &plan);
 	if (rc) return rc;
+	std::vector<uint8_t> slot;
 	const uint8_t *inp = d->input.data();
+	if (H) {
+		slot.reserve((size_t)(H + len));
+		slot.insert(slot.end(), d->history.begin(), d->history.end());
+		slot.insert(slot.end(), d->input.begin(), d->input.end());
+		inp = slot.data();
+	}
 	HostRunResult r;
-	rc = run_plan_host(plan, &inp, d->hin, d->hout, d->din, d->dout, d->dmeta, r, false);
+	const uint32_t seed = d->adler;
+	rc = run_plan_host(plan, &inp, d->hin, d->hout, d->din, d->dout, d->dmeta, r, false,
+	                   (plan->check_seeded && !d->raw) ? &seed : nullptr);
 	if (!rc && (r.status[0] & 0xFF) != B200Z_OK) {
 		rc = r.status[0] & 0xFF;
 		set_error("device deflate failed with status %d", rc);
 	}
 	if (!rc) {
 		const uint8_t *o = d->hout.p + plan->out_off[0];
-		const int64_t bits = r.in_used[0]; // deflate plans report the exact bit length here
+		const int64_t bits = r.in_used[0]; // deflate plans report the exact bit length here (bit_base included)
 		const int64_t whole = bits >> 3;
-		d->pending.insert(d->pending.end(), o, o + whole);
-		if (bits & 7) {
-			// PendingBuffer keeps the sub-byte tail in `bits` until later writes complete the byte (:168-189)
-			d->tail.bits = o[whole] & ((1u << (bits & 7)) - 1u);
-			d->tail.count = (int)(bits & 7);
-		}
+		std::vector<uint8_t> seg(o, o + ((bits + 7) >> 3));
+		if (!seg.empty()) seg[0] |= (uint8_t)d->tail.bits; // the carried sub-byte tail completes the first byte
+		d->pending.insert(d->pending.end(), seg.begin(), seg.begin() + (ptrdiff_t)whole);
+		// PendingBuffer keeps the sub-byte tail in `bits` until later writes complete the byte (:168-189)
+		d->tail.count = (int)(bits & 7);
+		d->tail.bits = d->tail.count ? (seg[(size_t)whole] & ((1u << d->tail.count) - 1u)) : 0u;
 		if (end_mode == B200Z_END_FINISH) d->tail.align(d->pending); // FINISHING_STATE: AlignToByte (:507)
 		if (!d->raw) d->adler = r.check[0];
 		d->total_in += len;
+		deflater_remember(d, d->input.data(), (size_t)len, 2);
 		d->input.clear();
 	}
 	b200z_plan_destroy(plan);
@@ -674,6 +780,11 @@ int b200z_deflater_reset(void *h) { // Deflater.Reset :204-210 keeps level and s
 	d->tail = HostBits();
 	d->total_in = d->total_out = 0;
 	d->adler = 1;
+	d->history.clear();
+	d->hist_mask.clear();
+	d->window_seen = 0;
+	d->dict_set = d->deflate_called = false;
+	d->dict_adler = 0;
 	return B200Z_OK;
 }
 int b200z_deflater_set_level(void *h, int level) {
@@ -702,10 +813,30 @@ int b200z_deflater_set_strategy(void *h, int strategy) {
 	((DeflaterH *)h)->strategy = strategy;
 	return B200Z_OK;
 }
-int b200z_deflater_set_dictionary(void *h, const uint8_t *, int32_t) {
-	(void)h;
-	set_error("preset dictionaries (Deflater.SetDictionary, DeflaterEngine.cs:198-229) are not accelerated by this build");
-	return B200Z_E_UNSUPPORTED;
+int b200z_deflater_set_dictionary(void *h, const uint8_t *dict, int32_t len) {
+	DeflaterH *d = (DeflaterH *)h;
+	// Deflater.SetDictionary :372-381: only in INIT_STATE (before the header went out); the header's FDICT bit and
+	// DICTID come from the engine's Adler-32 over the dictionary, which is then reset (:386-401)
+	if (d->raw || d->deflate_called || d->header_done || d->total_in > 0 || d->dict_set) {
+		// state != INIT_STATE (:561): a raw deflater starts in BUSY_STATE (:206), Deflate() leaves INIT_STATE (:436-464)
+		set_error("SetDictionary: not in the initial state"); // InvalidOperationException
+		return B200Z_E_STATE;
+	}
+	if (len < 0 || (len > 0 && !dict)) {
+		set_error("dictionary/count");
+		return B200Z_E_ARG;
+	}
+	uint32_t a = 1;
+	if (len > 0) {
+		int rc = b200z_adler32(dict, len, &a);
+		if (rc) return rc;
+	}
+	d->dict_adler = a;
+	d->dict_set = true;
+	if (len < kMinMatch) return B200Z_OK; // DeflaterEngine.cs:207-210: too short to matter, not even copied
+	const int32_t keep = len > kMaxDist ? kMaxDist : len; // :212-216
+	deflater_remember(d, dict + (len - keep), (size_t)keep, 2);
+	return B200Z_OK;
 }
 int b200z_deflater_set_input(void *h, const uint8_t *buf, int32_t len) {
 	DeflaterH *d = (DeflaterH *)h;
@@ -717,10 +848,7 @@ int b200z_deflater_set_input(void *h, const uint8_t *buf, int32_t len) {
 		set_error("buffer/count");
 		return B200Z_E_ARG;
 	}
-	if (d->flushed_once && len > 0) {
-		set_error("input after a sync Flush() is not accelerated by this build (carried window + bit tail)");
-		return B200Z_E_UNSUPPORTED;
-	}
+	if (len > 0) d->flushed_once = false;
 	d->input.insert(d->input.end(), buf, buf + len);
 	return B200Z_OK;
 }
@@ -741,15 +869,19 @@ int b200z_deflater_deflate(void *h, uint8_t *out, int32_t cap, int32_t *produced
 		return B200Z_E_ARG;
 	}
 	*produced = 0;
+	d->deflate_called = true;
 	// make output due (Deflater.Deflate :427-522)
 	if (!d->finished && d->pending_pos == d->pending.size() && (d->flushing || d->finishing)) {
 		d->pending.clear();
 		d->pending_pos = 0;
 		if (!d->header_done && !d->raw) {
 			uint8_t hd[2];
-			zlib_header(d->level, hd);
+			zlib_header(d->level, hd, d->dict_set);
 			d->pending.push_back(hd[0]);
 			d->pending.push_back(hd[1]);
+			if (d->dict_set) { // DICTID = Adler-32 of the whole dictionary, MSB first (:455-461)
+				for (int sh = 24; sh >= 0; sh -= 8) d->pending.push_back((uint8_t)(d->dict_adler >> sh));
+			}
 		}
 		d->header_done = true;
 		if (d->finishing) {
@@ -824,6 +956,8 @@ struct InflaterH {
 	bool finished = false;
 	bool need_dict = false;
 	bool header_done = false;
+	uint32_t read_adler = 0;   // DICTID from the header (Inflater.readAdler)
+	std::vector<uint8_t> dict; // last <= 32768 bytes of the dictionary SetDictionary accepted
 	size_t raw_off = 0; // where the raw deflate data starts inside `input`
 	std::vector<uint8_t> output; // decoded so far
 	size_t delivered = 0;
@@ -857,9 +991,17 @@ static int inflater_run_device(InflaterH *d) {
 	int64_t cap = avail * 8 + 65536;
 	for (int attempt = 0; attempt < 8; attempt++) {
 		b200z_plan *plan = nullptr;
-		int rc = b200z_inflate_plan_create(1, &avail, &cap, B200Z_WRAP_RAW, &plan);
+		const int64_t D = (int64_t)d->dict.size();
+		int rc = b200z_inflate_plan_create_ex(1, &avail, &cap, B200Z_WRAP_RAW, D ? &D : nullptr, &plan);
 		if (rc) return rc;
 		const uint8_t *inp = d->input.data() + d->raw_off;
+		std::vector<uint8_t> slot;
+		if (D) { // dictionary directly in front of the compressed bytes
+			slot.reserve((size_t)(D + avail));
+			slot.insert(slot.end(), d->dict.begin(), d->dict.end());
+			slot.insert(slot.end(), inp, inp + avail);
+			inp = slot.data();
+		}
 		HostRunResult r;
 		rc = run_plan_host(plan, &inp, d->hin, d->hout, d->din, d->dout, d->dmeta, r, false);
 		if (rc) {
@@ -913,12 +1055,36 @@ int b200z_inflater_reset(void *h) {
 	d->consumed = 0;
 	d->adler = 1;
 	d->error = 0;
+	d->read_adler = 0;
+	d->dict.clear();
 	return B200Z_OK;
 }
-int b200z_inflater_set_dictionary(void *h, const uint8_t *, int32_t) {
-	(void)h;
-	set_error("preset dictionaries (Inflater.SetDictionary, Inflater.cs:589-620) are not accelerated by this build");
-	return B200Z_E_UNSUPPORTED;
+int b200z_inflater_set_dictionary(void *h, const uint8_t *dict, int32_t len) {
+	InflaterH *d = (InflaterH *)h;
+	// Inflater.SetDictionary :589-620
+	if (len < 0 || (len > 0 && !dict)) {
+		set_error("buffer/count");
+		return B200Z_E_ARG;
+	}
+	if (!d->need_dict) {
+		set_error("Dictionary is not needed"); // InvalidOperationException
+		return B200Z_E_STATE;
+	}
+	uint32_t a = 1;
+	if (len > 0) {
+		int rc = b200z_adler32(dict, len, &a);
+		if (rc) return rc;
+	}
+	if (a != d->read_adler) {
+		set_error("Wrong adler checksum"); // SharpZipBaseException
+		return B200Z_E_DATA;
+	}
+	const int32_t keep = len > 32768 ? 32768 : len; // OutputWindow.CopyDict :160-166
+	d->dict.assign(dict + (len - keep), dict + len);
+	d->need_dict = false;
+	d->adler = 1;
+	d->new_input = true; // what was handed over behind the header can be decoded now
+	return B200Z_OK;
 }
 int b200z_inflater_set_input(void *h, const uint8_t *buf, int32_t len) {
 	InflaterH *d = (InflaterH *)h;
@@ -964,16 +1130,33 @@ int b200z_inflater_inflate(void *h, uint8_t *out, int32_t cap, int32_t *produced
 			} else if ((header & 0x0f00) != (8 << 8)) {
 				d->error = B200Z_E_DATA;
 				d->error_msg = "Compression Method unknown";
-			} else if (header & 0x0020) {
-				set_error("preset dictionaries are not accelerated by this build");
-				return B200Z_E_UNSUPPORTED;
 			}
 			if (d->error) {
 				set_error("%s", d->error_msg.c_str());
 				return d->error;
 			}
+			if (header & 0x0020) {
+				// PRESET_DICT: DecodeDict reads the 4-byte DICTID MSB first (:185-203); Inflate() then returns 0 until
+				// SetDictionary supplies a dictionary with that Adler-32
+				if (d->input.size() < 6) {
+					d->consumed = (int64_t)d->input.size();
+					return B200Z_OK;
+				}
+				d->read_adler = ((uint32_t)d->input[2] << 24) | ((uint32_t)d->input[3] << 16) | ((uint32_t)d->input[4] << 8) | d->input[5];
+				d->need_dict = true;
+				d->adler = d->read_adler; // Inflater.Adler reports readAdler while the dictionary is awaited (:823-836)
+				d->header_done = true;
+				d->raw_off = 6;
+				d->consumed = 6;
+				d->new_input = true; // the bytes behind the DICTID wait for SetDictionary
+				return B200Z_OK;
+			}
 			d->header_done = true;
 			d->raw_off = 2;
+		}
+		if (d->need_dict) {
+			d->new_input = true;
+			return B200Z_OK;
 		}
 		const size_t had = d->delivered;
 		int rc = inflater_run_device(d);
@@ -1018,8 +1201,7 @@ int b200z_inflater_needs_input(void *h, int *flag) {
 	return B200Z_OK;
 }
 int b200z_inflater_needs_dictionary(void *h, int *flag) {
-	*flag = 0;
-	(void)h;
+	*flag = ((InflaterH *)h)->need_dict ? 1 : 0; // mode == DECODE_DICT && neededBits == 0 (Inflater.cs:792-798)
 	return B200Z_OK;
 }
 int b200z_inflater_is_finished(void *h, int *flag) {

@@ -84,14 +84,14 @@ B200Z_HD uint32_t match_dist(uint32_t m) { return m & 0xFFFFu; }
 // the nice-length early exit; 0 when no match of length >= 3 exists.
 template <class DataT, class LinkT>
 B200Z_HD void match_search(const DataT *data, const LinkT *link, uint32_t bias, uint32_t p, uint32_t n,
-                           const LevelParams &lp, uint32_t &resA, uint32_t &resB) {
+                           const LevelParams &lp, uint32_t &resA, uint32_t &resB, uint32_t abs_bias = 0) {
 	resA = 0;
 	resB = 0;
 	const uint32_t la = n - p; // lookahead at a flushing loop top (or >= 262, where min() gives the same caps)
 	if (la < (uint32_t)kMinMatch) return;
 	uint32_t d = link[p - bias];
 	if (d == 0) return;
-	if (d > (uint32_t)kMaxDist - (is_slide_pos(p) ? 1u : 0u)) return; // DeflaterEngine.cs:788 + trap T8
+	if (d > (uint32_t)kMaxDist - (is_slide_pos(p + abs_bias) ? 1u : 0u)) return; // DeflaterEngine.cs:788 + trap T8
 	const uint32_t maxlen = la < (uint32_t)kMaxMatch ? la : (uint32_t)kMaxMatch;
 	const uint32_t nice = la < (uint32_t)lp.nice ? la : (uint32_t)lp.nice;
 	const DataT *s = data + (p - bias);
@@ -135,10 +135,10 @@ B200Z_HD void match_search(const DataT *data, const LinkT *link, uint32_t bias, 
 // the reference stops there).  Returns packed match or 0.
 template <class DataT, class LinkT>
 B200Z_HDN uint32_t match_search_above(const DataT *data, const LinkT *link, uint32_t p, uint32_t n, uint32_t m0,
-                                      uint32_t budget) {
+                                      uint32_t budget, uint32_t abs_bias = 0) {
 	const uint32_t la = n - p;
 	uint32_t d = link[p];
-	if (d == 0 || d > (uint32_t)kMaxDist - (is_slide_pos(p) ? 1u : 0u)) return 0;
+	if (d == 0 || d > (uint32_t)kMaxDist - (is_slide_pos(p + abs_bias) ? 1u : 0u)) return 0;
 	const uint32_t maxlen = la < (uint32_t)kMaxMatch ? la : (uint32_t)kMaxMatch;
 	uint32_t dist = d, cnt = 0;
 	const DataT *s = data + p;
@@ -327,6 +327,20 @@ B200Z_HD int fe_insert_string(FastEngine &e) { // :417-439
 	return (int)match;
 }
 
+// DeflaterEngine.SetDictionary (:198-229): the dictionary (>= MIN_MATCH bytes, already cut to its last MAX_DIST bytes)
+// sits in front of the data in the same buffer; every position but its last two is inserted
+B200Z_HDN void fe_set_dictionary(FastEngine &e, uint32_t dict_len) {
+	if (dict_len < (uint32_t)kMinMatch) return;
+	fe_update_hash(e);
+	for (uint32_t k = 0; k + 2 < dict_len; ++k) {
+		fe_insert_string(e);
+		++e.strstart;
+	}
+	e.strstart += 2;
+	e.blockStart = e.strstart;
+	e.inputOff = dict_len;
+}
+
 B200Z_HD void fe_slide_scalars(FastEngine &e) { // :443-446
 	e.matchStart -= kWSize;
 	e.strstart -= kWSize;
@@ -466,8 +480,9 @@ B200Z_HDN void fe_run(FastEngine &e, const LevelParams &lp, int strategy, int en
 // Only block boundaries are decided here (pure integer bookkeeping); block(byte_start, length, last) is called for
 // every FlushStoredBlock.  Same call pattern as fe_run.  Sync-flush padding is skipped at level 0 (Deflater.cs:488).
 template <class BlockFn>
-inline void stored_run(uint32_t n, int end_mode, BlockFn block) { // host only: run when a plan is built
-	int strstart = 1, blockStart = 1, lookahead = 0;
+inline void stored_run(uint32_t n, uint32_t dict_len, int end_mode, BlockFn block) { // host only: run when a plan is built
+	// dict_len: a preset dictionary in front of the n data bytes (SetDictionary leaves strstart = blockStart = 1 + length)
+	int strstart = 1 + (int)dict_len, blockStart = 1 + (int)dict_len, lookahead = 0;
 	uint32_t slides = 0, inputOff = 0;
 	const int kMaxBlock = 65531; // DeflaterConstants.MAX_BLOCK_SIZE
 	auto fill = [&]() {

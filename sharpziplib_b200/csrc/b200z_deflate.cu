@@ -41,7 +41,8 @@ constexpr int kLinksSmem = 65536 + 2 * kLinkBuf;
 
 __global__ void __launch_bounds__(32) k_links(const uint8_t *__restrict__ in, uint16_t *__restrict__ link,
                                               const int64_t *__restrict__ in_off, const int64_t *__restrict__ in_len,
-                                              const int2 *__restrict__ run_desc) {
+                                              const int2 *__restrict__ run_desc, const uint32_t *__restrict__ hist,
+                                              const uint8_t *__restrict__ hmask, const int64_t *__restrict__ hm_off) {
 	extern __shared__ __align__(16) uint8_t lsm[];
 	uint16_t *head = reinterpret_cast<uint16_t *>(lsm); // 32768 entries
 	uint8_t *buf = lsm + 65536;                          // two staging buffers of kLinkBuf bytes
@@ -53,6 +54,10 @@ __global__ void __launch_bounds__(32) k_links(const uint8_t *__restrict__ in, ui
 	const uint32_t start = (uint32_t)rd.y;
 	const uint32_t run_end = (n - start > (uint32_t)kRun) ? start + kRun : n;
 	const uint32_t warm = start >= 32768u ? start - 32768u : 0u;
+	// history (preset dictionary / earlier segments of the same stream): positions the reference never inserted
+	// (the last two of a dictionary, DeflaterEngine.cs:217-226, or of a flushed segment, trap T9) are masked
+	const uint32_t H = hist[rd.x];
+	const uint8_t *hm = hmask + hm_off[rd.x];
 	for (int i = lane; i < 16384; i += 32) reinterpret_cast<uint32_t *>(head)[i] = 0;
 	uint32_t winbase = warm;
 	// The step loop is a serial dependency chain through the head table, so nothing in it may wait on global memory:
@@ -89,7 +94,8 @@ __global__ void __launch_bounds__(32) k_links(const uint8_t *__restrict__ in, ui
 			}
 			const uint32_t p = base + lane;
 			const uint32_t o = p - cb;
-			const bool valid = p + 2 < n; // InsertString only while lookahead >= MIN_MATCH (DeflaterEngine.cs:782, :819)
+			bool valid = p + 2 < n; // InsertString only while lookahead >= MIN_MATCH (DeflaterEngine.cs:782, :819)
+			if (p < H) valid = hm[p] == 0;
 			const uint32_t h = hash3(cbuf[o], cbuf[o + 1], cbuf[o + 2]);
 			const uint32_t mask = same_hash_mask(h, valid, lane);
 			const uint32_t lower = mask & ((1u << lane) - 1u);
@@ -120,7 +126,7 @@ __global__ void __launch_bounds__(32) k_links(const uint8_t *__restrict__ in, ui
 __global__ void __launch_bounds__(kMatchThreads, 1)
     k_match(const uint8_t *__restrict__ in, const uint16_t *__restrict__ link, uint2 *__restrict__ mt,
             const int64_t *__restrict__ in_off, const int64_t *__restrict__ in_len, const int2 *__restrict__ tile_desc,
-            LevelParams lp) {
+            const uint32_t *__restrict__ hist, const int64_t *__restrict__ bias, LevelParams lp) {
 	extern __shared__ __align__(16) uint8_t smem[];
 	uint8_t *s_data = smem;
 	uint16_t *s_link = reinterpret_cast<uint16_t *>(smem + kTileData);
@@ -154,11 +160,14 @@ __global__ void __launch_bounds__(kMatchThreads, 1)
 	// match_search() of b200z_core.cuh with the byte-wise extension loop replaced by 4-byte compares on aligned
 	// shared-memory words (ncu: the byte loop ran with ~2 of 32 lanes active and took ~30 % of the kernel).
 	const uint32_t chain = (uint32_t)lp.chain, budgetB = chain >> 2;
+	const uint32_t H = hist[td.x];            // positions below H are history: candidates only
+	const uint32_t ab = (uint32_t)bias[td.x]; // absolute stream offset of buffer position 0 (window-slide phase, trap T8)
 	for (uint32_t p = t0 + threadIdx.x; p < t1; p += kMatchThreads) {
+		if (p < H) continue;
 		uint32_t resA = 0, resB = 0;
 		const uint32_t la = n - p;
 		uint32_t d = la >= (uint32_t)kMinMatch ? (uint32_t)s_link[p - w0] : 0u;
-		if (d > (uint32_t)kMaxDist - (is_slide_pos(p) ? 1u : 0u)) d = 0; // DeflaterEngine.cs:788 + trap T8
+		if (d > (uint32_t)kMaxDist - (is_slide_pos(p + ab) ? 1u : 0u)) d = 0; // DeflaterEngine.cs:788 + trap T8
 		if (d != 0) {
 			const uint32_t maxlen = la < (uint32_t)kMaxMatch ? la : (uint32_t)kMaxMatch;
 			const uint32_t nice = la < (uint32_t)lp.nice ? la : (uint32_t)lp.nice;
@@ -274,8 +283,8 @@ __device__ __forceinline__ ParseCarry rec_carry(const RoundRec &r) {
 // One round [base, base + kRound) of a stream, entered with `carry` (uniform across the warp; updated to the round's
 // exit state).  The round's symbols go to sround[0 .. cnt).  Returns cnt (uniform).
 __device__ __forceinline__ uint32_t parse_round(uint8_t *smem, const uint8_t *data, const uint16_t *lnk, const uint2 *tab,
-                                                uint32_t n, uint32_t base, const LevelParams &lp, int strategy,
-                                                ParseCarry &carry, uint32_t *sround) {
+                                                uint32_t n, uint32_t H, uint32_t ab, uint32_t base, const LevelParams &lp,
+                                                int strategy, ParseCarry &carry, uint32_t *sround) {
 	uint2 *s_tab = reinterpret_cast<uint2 *>(smem);
 	uint8_t *s_dat = smem + kParseDatOff; // s_dat[16 + i] = byte at position base + i (16 bytes of history in front)
 	const int lane = threadIdx.x & 31;
@@ -301,10 +310,13 @@ __device__ __forceinline__ uint32_t parse_round(uint8_t *smem, const uint8_t *da
 		b = t.y;
 	};
 	auto bytef = [&](uint32_t q) { return (uint32_t)s_dat[q + 16 - base]; };
-	auto slowf = [&](uint32_t p, uint32_t m0, uint32_t budget) { return match_search_above(data, lnk, p, n, m0, budget); };
+	auto slowf = [&](uint32_t p, uint32_t m0, uint32_t budget) { return match_search_above(data, lnk, p, n, m0, budget, ab); };
 	ParseCarry entry, ex;
 	if (lane == 0) entry = carry;
-	else entry = clean_carry(base + (uint32_t)lane * kSeg);
+	else {
+		const uint32_t ss = base + (uint32_t)lane * kSeg;
+		entry = clean_carry(ss > H ? ss : H); // history positions are never parsed; the state at H is exactly "clean"
+	}
 	ex = entry;
 	uint32_t cnt = 0;
 	bool changed = true;
@@ -361,16 +373,18 @@ __global__ void __launch_bounds__(32)
     k_parse_chunk(const uint8_t *__restrict__ in, const uint16_t *__restrict__ link, const uint2 *__restrict__ mt,
                   uint32_t *__restrict__ sym_local, const int64_t *__restrict__ in_off, const int64_t *__restrict__ in_len,
                   const ChunkDesc *__restrict__ chunks, const uint32_t *__restrict__ rnd_off, RoundRec *__restrict__ recs,
-                  LevelParams lp, int strategy) {
+                  const uint32_t *__restrict__ hist, const int64_t *__restrict__ bias, LevelParams lp, int strategy) {
 	extern __shared__ __align__(16) uint8_t smem[];
 	const ChunkDesc cd = chunks[blockIdx.x];
 	const uint32_t n = (uint32_t)in_len[cd.stream];
 	const int64_t off = in_off[cd.stream];
 	RoundRec *rr = recs + rnd_off[cd.stream];
-	ParseCarry carry = clean_carry(cd.c0); // exact for c0 == 0 (DeflaterEngine.Reset :234-253), a guess otherwise
-	if (cd.c0 == 0) carry.last_top = 0;
+	const uint32_t H = hist[cd.stream], ab = (uint32_t)bias[cd.stream];
+	// exact for the first chunk (DeflaterEngine.Reset :234-253; also the state right after a dictionary or a flush),
+	// a guess otherwise
+	ParseCarry carry = clean_carry(cd.c0 > H ? cd.c0 : H);
 	for (uint32_t base = cd.c0; base < cd.c1; base += kRound) {
-		const uint32_t cnt = parse_round(smem, in + off, link + off, mt + off, n, base, lp, strategy, carry, sym_local + off + base);
+		const uint32_t cnt = parse_round(smem, in + off, link + off, mt + off, n, H, ab, base, lp, strategy, carry, sym_local + off + base);
 		if (threadIdx.x == 0) {
 			RoundRec r;
 			r.p = carry.st.p;
@@ -387,13 +401,15 @@ __global__ void __launch_bounds__(32)
 __global__ void __launch_bounds__(32)
     k_parse_fix(const uint8_t *__restrict__ in, const uint16_t *__restrict__ link, const uint2 *__restrict__ mt,
                 uint32_t *__restrict__ sym_local, const int64_t *__restrict__ in_off, const int64_t *__restrict__ in_len,
-                const uint32_t *__restrict__ rnd_off, RoundRec *__restrict__ recs, uint32_t chunk, LevelParams lp, int strategy) {
+                const uint32_t *__restrict__ rnd_off, RoundRec *__restrict__ recs, uint32_t chunk, const uint32_t *__restrict__ hist,
+                const int64_t *__restrict__ bias, LevelParams lp, int strategy) {
 	extern __shared__ __align__(16) uint8_t smem[];
 	const int stream = blockIdx.x;
 	const uint32_t n = (uint32_t)in_len[stream];
 	if (n <= chunk) return; // a single chunk was parsed from the true initial state
 	const int64_t off = in_off[stream];
 	RoundRec *rr = recs + rnd_off[stream];
+	const uint32_t H = hist[stream], ab = (uint32_t)bias[stream];
 	for (uint32_t c0 = chunk; c0 < n; c0 += chunk) {
 		const uint32_t c1 = (n - c0 > chunk) ? c0 + chunk : n;
 		ParseCarry truth = rec_carry(rr[c0 / kRound - 1]); // exit of the previous chunk's last round, exact by induction
@@ -404,7 +420,7 @@ __global__ void __launch_bounds__(32)
 		}
 		for (uint32_t base = c0; base < c1; base += kRound) {
 			const ParseCarry old_exit = rec_carry(rr[base / kRound]);
-			const uint32_t cnt = parse_round(smem, in + off, link + off, mt + off, n, base, lp, strategy, truth, sym_local + off + base);
+			const uint32_t cnt = parse_round(smem, in + off, link + off, mt + off, n, H, ab, base, lp, strategy, truth, sym_local + off + base);
 			__syncwarp();
 			if (threadIdx.x == 0) {
 				RoundRec r;
@@ -427,7 +443,8 @@ __global__ void __launch_bounds__(256)
     k_parse_scan(const uint8_t *__restrict__ in, const int64_t *__restrict__ in_off, const int64_t *__restrict__ in_len,
                  const uint32_t *__restrict__ rnd_off, const RoundRec *__restrict__ recs, uint32_t *__restrict__ rnd_symoff,
                  uint32_t *__restrict__ sym, uint32_t *__restrict__ nsyms, uint32_t *__restrict__ nblocks,
-                 const uint32_t *__restrict__ blk_off, uint32_t *__restrict__ blk_start, uint32_t *__restrict__ blk_ptop, int end_mode) {
+                 const uint32_t *__restrict__ blk_off, uint32_t *__restrict__ blk_start, uint32_t *__restrict__ blk_ptop,
+                 const uint32_t *__restrict__ hist, int end_mode) {
 	__shared__ uint32_t s_part[8];
 	__shared__ uint32_t s_carry;
 	const int stream = blockIdx.x;
@@ -457,11 +474,11 @@ __global__ void __launch_bounds__(256)
 	}
 	if (threadIdx.x == 0) {
 		uint32_t total = s_carry;
-		ParseCarry fin = nr ? rec_carry(rr[nr - 1]) : clean_carry(0);
-		if (nr == 0) fin.last_top = 0;
+		const uint32_t H = hist[stream];
+		ParseCarry fin = nr ? rec_carry(rr[nr - 1]) : clean_carry(H);
 		uint32_t *bstart = blk_start + blk_off[stream];
 		uint32_t *bptop = blk_ptop + blk_off[stream];
-		bstart[0] = 0;
+		bstart[0] = H;
 		uint32_t nblk = total >> 14;
 		const bool ended_full = end_mode == B200Z_END_FINISH && total > 0 && (total & (uint32_t)(kBlockSyms - 1)) == 0 && !fin.st.prevAvail;
 		if (!ended_full) {
@@ -480,7 +497,7 @@ __global__ void __launch_bounds__(128)
     k_parse_gather(const uint32_t *__restrict__ sym_local, uint32_t *__restrict__ sym, const int64_t *__restrict__ in_off,
                    const int64_t *__restrict__ in_len, const int2 *__restrict__ rnd_desc, const uint32_t *__restrict__ rnd_off,
                    const RoundRec *__restrict__ recs, const uint32_t *__restrict__ rnd_symoff, const uint32_t *__restrict__ blk_off,
-                   uint32_t *__restrict__ blk_start, uint32_t *__restrict__ blk_ptop) {
+                   uint32_t *__restrict__ blk_start, uint32_t *__restrict__ blk_ptop, const uint32_t *__restrict__ hist) {
 	const int2 d = rnd_desc[blockIdx.x]; // (stream, first round of this CTA's group of 4)
 	const int64_t off = in_off[d.x];
 	const uint32_t n = (uint32_t)in_len[d.x];
@@ -501,7 +518,7 @@ __global__ void __launch_bounds__(128)
 		if (first_b * (uint32_t)kBlockSyms - 1 <= last_idx) {
 			// bytes covered before this round's first symbol: entry.p, minus the pending literal if there is one
 			uint32_t bytes;
-			if (r == 0) bytes = 0;
+			if (r == 0) bytes = hist[d.x];
 			else bytes = rr[r - 1].p - (rr[r - 1].prevAvail ? 1u : 0u);
 			uint32_t *bstart = blk_start + blk_off[d.x];
 			uint32_t *bptop = blk_ptop + blk_off[d.x];
@@ -532,7 +549,7 @@ __global__ void __launch_bounds__(32)
     k_fast(const uint8_t *__restrict__ in, uint32_t *__restrict__ sym, const int64_t *__restrict__ in_off,
            const int64_t *__restrict__ in_len, uint32_t *__restrict__ nsyms, uint32_t *__restrict__ nblocks,
            const uint32_t *__restrict__ blk_off, uint32_t *__restrict__ blk_start, uint32_t *__restrict__ blk_ptop,
-           LevelParams lp, int strategy, int end_mode) {
+           const uint32_t *__restrict__ hist, LevelParams lp, int strategy, int end_mode) {
 	extern __shared__ __align__(16) uint8_t fsm[];
 	uint16_t *head = reinterpret_cast<uint16_t *>(fsm);
 	uint16_t *prev = head + 32768;
@@ -547,6 +564,7 @@ __global__ void __launch_bounds__(32)
 	__syncwarp();
 	FastEngine e;
 	fe_init(e, in + off, n, head, prev);
+	if (lane == 0) fe_set_dictionary(e, hist[stream]); // preset dictionary in front of the data (0 = none)
 	e.coop = 1;
 	uint32_t total = 0, nblk = 0;
 	int phase = 0;           // 0: BUSY_STATE drain, 1: Flush()/Finish()
@@ -641,7 +659,7 @@ __global__ void __launch_bounds__(kPlanThreads)
     k_plan(const uint32_t *__restrict__ sym, const int64_t *__restrict__ in_off, const int64_t *__restrict__ in_len,
            const uint32_t *__restrict__ nsyms, const uint32_t *__restrict__ nblocks, const uint32_t *__restrict__ blk_off,
            const int32_t *__restrict__ blk_desc, const uint32_t *__restrict__ blk_start, const uint32_t *__restrict__ blk_ptop,
-           BlockMeta *__restrict__ meta, BlockTables *__restrict__ tables, int end_mode) {
+           BlockMeta *__restrict__ meta, BlockTables *__restrict__ tables, const int64_t *__restrict__ bias, int end_mode) {
 	__shared__ int s_lit[kLiteralNum];
 	__shared__ int s_dist[kDistNum];
 	__shared__ int s_extra;
@@ -691,7 +709,8 @@ __global__ void __launch_bounds__(kPlanThreads)
 		const uint32_t n = (uint32_t)in_len[stream];
 		const uint32_t byte_len = (b + 1 < nb ? bstart[b + 1] : n) - byte_start;
 		// storedOffset is window relative and goes negative once the block start has been slid out (trap T4)
-		long long storedOffset = (long long)byte_start + 1 - 32768ll * (long long)slides_done(bptop[b]);
+		const long long ab = bias[stream]; // absolute stream offset of buffer position 0
+		long long storedOffset = (long long)byte_start + ab + 1 - 32768ll * (long long)slides_done((uint32_t)(bptop[b] + ab));
 		if (bptop[b] >= 0xFFFFFFFEu) storedOffset = bptop[b] == 0xFFFFFFFEu ? 0 : -1; // levels 1-4: decided by k_fast
 		const int last = (b + 1 == nb) && end_mode == B200Z_END_FINISH;
 		BlockPlan plan;
@@ -733,12 +752,12 @@ __device__ __forceinline__ void or_bits(uint32_t *out_words, uint64_t bitpos, ui
 __global__ void k_scan(int nstreams, const uint32_t *__restrict__ nblocks, const uint32_t *__restrict__ blk_off,
                        BlockMeta *__restrict__ meta, uint8_t *__restrict__ out, const int64_t *__restrict__ out_off,
                        const int64_t *__restrict__ out_cap, int64_t *__restrict__ out_len, int32_t *__restrict__ status,
-                       int64_t *__restrict__ out_bits, int end_mode) {
+                       int64_t *__restrict__ out_bits, const uint32_t *__restrict__ bit_base, int end_mode) {
 	const int stream = blockIdx.x * blockDim.x + threadIdx.x;
 	if (stream >= nstreams) return;
 	const uint32_t nb = nblocks[stream];
 	BlockMeta *m = meta + blk_off[stream];
-	uint64_t cur = 0;
+	uint64_t cur = bit_base[stream]; // 0..7: a continued stream starts inside the byte the previous segment ended in
 	for (uint32_t b = 0; b < nb; b++) {
 		m[b].bit_off = cur;
 		if (m[b].type == 0) cur = ((cur + 3 + 7) & ~7ull) + 32 + 8ull * m[b].byte_len;
@@ -891,11 +910,26 @@ int deflate_plan_build(b200z_plan *p) {
 	std::vector<uint32_t> blk_off(n + 1);
 	std::vector<int32_t> blk_desc;
 	uint32_t nblk = 0;
+	const bool has_hist = !p->hist.empty();
+	std::vector<uint32_t> hist32(n, 0u), bitbase32(n, 0u);
+	std::vector<int64_t> bias64(n, 0), hm_off(n, 0), ck_off(n), ck_len(n);
+	std::vector<uint8_t> hmask;
 	for (int i = 0; i < n; i++) {
 		const int64_t len = p->in_len[i];
 		if (len < 0 || len > 0xFFFF0000ll) {
 			set_error("stream %d: length %lld out of range", i, (long long)len);
 			return B200Z_E_ARG;
+		}
+		const int64_t H = has_hist ? p->hist[i] : 0;
+		if (has_hist) {
+			hist32[i] = (uint32_t)H;
+			bias64[i] = p->pos_base[i] - H;
+			bitbase32[i] = (uint32_t)p->bit_base[i];
+			hm_off[i] = (int64_t)hmask.size();
+			hmask.resize(hmask.size() + (size_t)H + 1, 0);
+			uint8_t *m = hmask.data() + hm_off[i];
+			if (i < (int)p->hist_mask.size() && !p->hist_mask[i].empty()) memcpy(m, p->hist_mask[i].data(), (size_t)H);
+			else if (H) m[H - 1] = 1, m[H > 1 ? H - 2 : 0] = 1; // the last two positions of a dictionary/segment are never inserted
 		}
 		p->in_off[i] = io;
 		io += align_up(len + 16, kAlign);
@@ -916,7 +950,7 @@ int deflate_plan_build(b200z_plan *p) {
 		nblk += maxb;
 		if (lp.func == 0) {
 			uint64_t dst = 0;
-			stored_run((uint32_t)len, p->end_mode, [&](uint32_t start, uint32_t blen, bool last) {
+			stored_run((uint32_t)(len - H), (uint32_t)H, p->end_mode, [&](uint32_t start, uint32_t blen, bool last) {
 				sblocks.push_back(StoredBlock{i, start, blen, last ? 1u : 0u, dst});
 				dst += 5 + (uint64_t)blen;
 			});
@@ -969,9 +1003,20 @@ int deflate_plan_build(b200z_plan *p) {
 		p->o_stored = ws.reserve((int64_t)sizeof(StoredBlock) * (sblocks.size() + 1));
 		p->o_slens = ws.reserve(8ll * (n + 1));
 	}
+	p->o_hist = ws.reserve(4ll * (n + 1));
+	p->o_bias = ws.reserve(8ll * (n + 1));
+	p->o_bitbase = ws.reserve(4ll * (n + 1));
+	p->o_hm_off = ws.reserve(8ll * (n + 1));
+	p->o_hmask = ws.reserve((int64_t)hmask.size() + 16);
 	std::vector<CkTile> ck_tiles;
 	if (p->wrap != B200Z_WRAP_RAW) {
-		checksum_tiles(p->in_len.data(), n, ck_tiles, p->wrap == B200Z_WRAP_GZIP ? 0 : 1);
+		for (int i = 0; i < n; i++) { // the checksum covers the data, never the history
+			ck_off[i] = p->in_off[i] + hist32[i];
+			ck_len[i] = p->in_len[i] - hist32[i];
+		}
+		p->o_ck_off = ws.reserve(8ll * (n + 1));
+		p->o_ck_len = ws.reserve(8ll * (n + 1));
+		checksum_tiles(ck_len.data(), n, ck_tiles, p->wrap == B200Z_WRAP_GZIP ? 0 : 1);
 		p->n_ck_tiles = (int)ck_tiles.size();
 		p->o_ck_desc = ws.reserve((int64_t)sizeof(CkTile) * (ck_tiles.size() + 1));
 		p->o_ck_acc = ws.reserve(16ll * (n + 1));
@@ -982,6 +1027,17 @@ int deflate_plan_build(b200z_plan *p) {
 	B200Z_CUDA(cudaMemcpy(ws.at<int64_t>(p->o_in_len), p->in_len.data(), 8ll * n, cudaMemcpyHostToDevice));
 	B200Z_CUDA(cudaMemcpy(ws.at<int64_t>(p->o_out_off), p->out_off.data(), 8ll * n, cudaMemcpyHostToDevice));
 	B200Z_CUDA(cudaMemcpy(ws.at<int64_t>(p->o_out_cap), p->out_cap.data(), 8ll * n, cudaMemcpyHostToDevice));
+	if (n) {
+		B200Z_CUDA(cudaMemcpy(ws.at<uint32_t>(p->o_hist), hist32.data(), 4ll * n, cudaMemcpyHostToDevice));
+		B200Z_CUDA(cudaMemcpy(ws.at<int64_t>(p->o_bias), bias64.data(), 8ll * n, cudaMemcpyHostToDevice));
+		B200Z_CUDA(cudaMemcpy(ws.at<uint32_t>(p->o_bitbase), bitbase32.data(), 4ll * n, cudaMemcpyHostToDevice));
+		B200Z_CUDA(cudaMemcpy(ws.at<int64_t>(p->o_hm_off), hm_off.data(), 8ll * n, cudaMemcpyHostToDevice));
+		if (!hmask.empty()) B200Z_CUDA(cudaMemcpy(ws.at<uint8_t>(p->o_hmask), hmask.data(), hmask.size(), cudaMemcpyHostToDevice));
+		if (p->wrap != B200Z_WRAP_RAW) {
+			B200Z_CUDA(cudaMemcpy(ws.at<int64_t>(p->o_ck_off), ck_off.data(), 8ll * n, cudaMemcpyHostToDevice));
+			B200Z_CUDA(cudaMemcpy(ws.at<int64_t>(p->o_ck_len), ck_len.data(), 8ll * n, cudaMemcpyHostToDevice));
+		}
+	}
 	if (!runs.empty()) B200Z_CUDA(cudaMemcpy(ws.at<int2>(p->o_run_desc), runs.data(), 8ll * runs.size(), cudaMemcpyHostToDevice));
 	if (!tiles.empty()) B200Z_CUDA(cudaMemcpy(ws.at<int2>(p->o_tile_desc), tiles.data(), 8ll * tiles.size(), cudaMemcpyHostToDevice));
 	B200Z_CUDA(cudaMemcpy(ws.at<int32_t>(p->o_blk_desc), blk_desc.data(), 4ll * nblk, cudaMemcpyHostToDevice));
@@ -1023,6 +1079,9 @@ int deflate_plan_run(b200z_plan *p, const uint8_t *d_in, uint8_t *d_out, int64_t
 	uint32_t *blk_start = ws.at<uint32_t>(p->o_blk_start), *blk_ptop = ws.at<uint32_t>(p->o_blk_ptop);
 	BlockMeta *meta = ws.at<BlockMeta>(p->o_meta);
 	BlockTables *tables = ws.at<BlockTables>(p->o_tables);
+	const uint32_t *hist = ws.at<uint32_t>(p->o_hist), *bit_base = ws.at<uint32_t>(p->o_bitbase);
+	const int64_t *bias = ws.at<int64_t>(p->o_bias);
+	const int ck_fresh = p->check_seeded ? 0 : 1;
 
 	p->ev_used = 0;
 	if (lp.func == 0) {
@@ -1032,8 +1091,9 @@ int deflate_plan_run(b200z_plan *p, const uint8_t *d_in, uint8_t *d_out, int64_t
 		k_set_results<<<(n + 127) / 128, 128, 0, s>>>(n, ws.at<int64_t>(p->o_slens), d_out_len, d_status, d_out_bits);
 		p->mark(s, "checksum");
 		if (p->wrap != B200Z_WRAP_RAW && d_check) {
-			int rc = checksum_launch(p->wrap == B200Z_WRAP_GZIP ? 0 : 1, d_in, in_off, in_len, n, ws.at<CkTile>(p->o_ck_desc),
-			                         p->n_ck_tiles, ws.at<unsigned long long>(p->o_ck_acc), d_check, 1, s);
+			int rc = checksum_launch(p->wrap == B200Z_WRAP_GZIP ? 0 : 1, d_in, ws.at<int64_t>(p->o_ck_off), ws.at<int64_t>(p->o_ck_len), n,
+			                         ws.at<CkTile>(p->o_ck_desc), p->n_ck_tiles, ws.at<unsigned long long>(p->o_ck_acc), d_check,
+			                         ck_fresh, s);
 			if (rc) return rc;
 		}
 		p->mark(s, "end");
@@ -1044,15 +1104,16 @@ int deflate_plan_run(b200z_plan *p, const uint8_t *d_in, uint8_t *d_out, int64_t
 	B200Z_CUDA(cudaMemsetAsync(d_out, 0, (size_t)p->out_bytes, s));
 	if (lp.func == 1) {
 		p->mark(s, "k_fast");
-		k_fast<<<n, 32, kFastSmem, s>>>(d_in, sym, in_off, in_len, nsyms, nblocks, blk_off, blk_start, blk_ptop, lp, p->strategy,
+		k_fast<<<n, 32, kFastSmem, s>>>(d_in, sym, in_off, in_len, nsyms, nblocks, blk_off, blk_start, blk_ptop, hist, lp, p->strategy,
 		                                p->end_mode);
 	} else {
 		p->mark(s, "k_links");
-		if (p->n_runs) k_links<<<p->n_runs, 32, kLinksSmem, s>>>(d_in, link, in_off, in_len, ws.at<int2>(p->o_run_desc));
+		if (p->n_runs) k_links<<<p->n_runs, 32, kLinksSmem, s>>>(d_in, link, in_off, in_len, ws.at<int2>(p->o_run_desc), hist,
+			                                                         ws.at<uint8_t>(p->o_hmask), ws.at<int64_t>(p->o_hm_off));
 		p->mark(s, "k_match");
 		if (p->n_tiles)
 			k_match<<<p->n_tiles, kMatchThreads, kTileData + 2 * 2 * kTile, s>>>(d_in, link, mt, in_off, in_len,
-			                                                                   ws.at<int2>(p->o_tile_desc), lp);
+			                                                                   ws.at<int2>(p->o_tile_desc), hist, bias, lp);
 		p->mark(s, "k_parse");
 		{
 			uint32_t *sym_local = ws.at<uint32_t>(p->o_sym_local);
@@ -1061,27 +1122,29 @@ int deflate_plan_run(b200z_plan *p, const uint8_t *d_in, uint8_t *d_out, int64_t
 			uint32_t *rnd_symoff = ws.at<uint32_t>(p->o_rnd_symoff);
 			if (p->n_chunks)
 				k_parse_chunk<<<p->n_chunks, 32, kParseSmem, s>>>(d_in, link, mt, sym_local, in_off, in_len, ws.at<ChunkDesc>(p->o_chunks),
-				                                                 rnd_off, recs, lp, p->strategy);
-			k_parse_fix<<<n, 32, kParseSmem, s>>>(d_in, link, mt, sym_local, in_off, in_len, rnd_off, recs, p->parse_chunk, lp, p->strategy);
+				                                                 rnd_off, recs, hist, bias, lp, p->strategy);
+			k_parse_fix<<<n, 32, kParseSmem, s>>>(d_in, link, mt, sym_local, in_off, in_len, rnd_off, recs, p->parse_chunk, hist, bias,
+			                                      lp, p->strategy);
 			k_parse_scan<<<n, 256, 0, s>>>(d_in, in_off, in_len, rnd_off, recs, rnd_symoff, sym, nsyms, nblocks, blk_off, blk_start,
-			                               blk_ptop, p->end_mode);
+			                               blk_ptop, hist, p->end_mode);
 			if (p->n_rgroups)
 				k_parse_gather<<<p->n_rgroups, 128, 0, s>>>(sym_local, sym, in_off, in_len, ws.at<int2>(p->o_rgroups), rnd_off, recs,
-				                                           rnd_symoff, blk_off, blk_start, blk_ptop);
+				                                           rnd_symoff, blk_off, blk_start, blk_ptop, hist);
 		}
 	}
 	p->mark(s, "k_plan");
 	k_plan<<<p->n_blkmax, kPlanThreads, 0, s>>>(sym, in_off, in_len, nsyms, nblocks, blk_off, blk_desc, blk_start, blk_ptop, meta,
-	                                   tables, p->end_mode);
+	                                   tables, bias, p->end_mode);
 	p->mark(s, "k_scan");
 	k_scan<<<(n + 127) / 128, 128, 0, s>>>(n, nblocks, blk_off, meta, d_out, out_off, out_cap, d_out_len, d_status,
-	                                       d_out_bits, p->end_mode);
+	                                       d_out_bits, bit_base, p->end_mode);
 	p->mark(s, "k_emit");
 	k_emit<<<p->n_blkmax, 256, 0, s>>>(d_in, sym, d_out, in_off, out_off, nblocks, blk_off, blk_desc, meta, tables);
 	p->mark(s, "checksum");
 	if (p->wrap != B200Z_WRAP_RAW && d_check) {
-		int rc = checksum_launch(p->wrap == B200Z_WRAP_GZIP ? 0 : 1, d_in, in_off, in_len, n, ws.at<CkTile>(p->o_ck_desc),
-		                         p->n_ck_tiles, ws.at<unsigned long long>(p->o_ck_acc), d_check, 1, s);
+		int rc = checksum_launch(p->wrap == B200Z_WRAP_GZIP ? 0 : 1, d_in, ws.at<int64_t>(p->o_ck_off), ws.at<int64_t>(p->o_ck_len), n,
+		                         ws.at<CkTile>(p->o_ck_desc), p->n_ck_tiles, ws.at<unsigned long long>(p->o_ck_acc), d_check,
+		                         ck_fresh, s);
 		if (rc) return rc;
 	}
 	p->mark(s, "end");

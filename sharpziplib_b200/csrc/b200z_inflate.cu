@@ -310,7 +310,8 @@ constexpr int kInfSmem2 = (int)sizeof(InfBlockShared);
 __global__ void __launch_bounds__(64)
     k_inflate(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, const int64_t *__restrict__ in_off,
               const int64_t *__restrict__ in_len, const int64_t *__restrict__ out_off, const int64_t *__restrict__ out_cap,
-              int nstreams, int64_t *__restrict__ out_len, int64_t *__restrict__ in_used, int32_t *__restrict__ status) {
+              int nstreams, int64_t *__restrict__ out_len, int64_t *__restrict__ in_used, int32_t *__restrict__ status,
+              const uint32_t *__restrict__ dict_len) {
 	extern __shared__ __align__(16) uint8_t smem_raw[];
 	InfBlockShared &S = *reinterpret_cast<InfBlockShared *>(smem_raw);
 	const int lane = threadIdx.x & 31;
@@ -338,6 +339,14 @@ __global__ void __launch_bounds__(64)
 		S.a_done = 0;
 	}
 	__syncthreads();
+	{
+		// preset dictionary (Inflater.SetDictionary -> OutputWindow.CopyDict, OutputWindow.cs:151-171): its last <= 32768
+		// bytes lie directly in front of the compressed data and become the window contents behind output position 0
+		const uint32_t D = dict_len[stream];
+		const uint8_t *dsrc = in + in_off[stream] - D;
+		for (uint32_t i = threadIdx.x; i < D; i += 64) S.ring[(uint32_t)kRing - D + i] = dsrc[i];
+		if (D) __syncthreads();
+	}
 
 	// ---- warp A state (uniform across the warp unless noted) ----
 	uint64_t opos = 0;   // bytes produced by all rounds handed over so far
@@ -702,13 +711,23 @@ int inflate_plan_build(b200z_plan *p) {
 	p->in_off.resize(n);
 	p->out_off.resize(n);
 	int64_t io = 0, oo = 0;
+	const bool has_dict = !p->hist.empty();
+	std::vector<int64_t> dev_off(n), dev_len(n);
+	std::vector<uint32_t> dict32(n, 0u);
 	for (int i = 0; i < n; i++) {
 		if (p->in_len[i] < 0 || p->in_len[i] > 0xFFFF0000ll || p->out_cap[i] < 0) {
 			set_error("stream %d: size out of range", i);
 			return B200Z_E_ARG;
 		}
-		p->in_off[i] = io;
-		io += align_up(p->in_len[i] + 16, kAlign);
+		// slot: [pad][dictionary][compressed data], the compressed data 16-byte aligned; in_len[] counts dictionary + data
+		const int64_t D = has_dict ? p->hist[i] : 0;
+		const int64_t comp = io + align_up(D, 16);
+		p->in_off[i] = comp - D;
+		dev_off[i] = comp;
+		dev_len[i] = p->in_len[i] - D;
+		dict32[i] = (uint32_t)D;
+		io = comp + align_up(dev_len[i] + 16, kAlign);
+		io = align_up(io, kAlign);
 		p->out_off[i] = oo;
 		oo += align_up(p->out_cap[i] + 16, kAlign);
 	}
@@ -719,12 +738,14 @@ int inflate_plan_build(b200z_plan *p) {
 	p->o_in_len = ws.reserve(8ll * (n + 1));
 	p->o_out_off = ws.reserve(8ll * (n + 1));
 	p->o_out_cap = ws.reserve(8ll * (n + 1));
+	p->o_hist = ws.reserve(4ll * (n + 1));
 	std::vector<CkTile> ck_tiles;
 	int rc = ws.alloc();
 	if (rc) return rc;
 	if (n) {
-		B200Z_CUDA(cudaMemcpy(ws.at<int64_t>(p->o_in_off), p->in_off.data(), 8ll * n, cudaMemcpyHostToDevice));
-		B200Z_CUDA(cudaMemcpy(ws.at<int64_t>(p->o_in_len), p->in_len.data(), 8ll * n, cudaMemcpyHostToDevice));
+		B200Z_CUDA(cudaMemcpy(ws.at<int64_t>(p->o_in_off), dev_off.data(), 8ll * n, cudaMemcpyHostToDevice));
+		B200Z_CUDA(cudaMemcpy(ws.at<int64_t>(p->o_in_len), dev_len.data(), 8ll * n, cudaMemcpyHostToDevice));
+		B200Z_CUDA(cudaMemcpy(ws.at<uint32_t>(p->o_hist), dict32.data(), 4ll * n, cudaMemcpyHostToDevice));
 		B200Z_CUDA(cudaMemcpy(ws.at<int64_t>(p->o_out_off), p->out_off.data(), 8ll * n, cudaMemcpyHostToDevice));
 		B200Z_CUDA(cudaMemcpy(ws.at<int64_t>(p->o_out_cap), p->out_cap.data(), 8ll * n, cudaMemcpyHostToDevice));
 	}
@@ -743,7 +764,7 @@ int inflate_plan_run(b200z_plan *p, const uint8_t *d_in, uint8_t *d_out, int64_t
 	p->mark(s, "k_inflate");
 	k_inflate<<<n, 64, kInfSmem2, s>>>(
 	    d_in, d_out, ws.at<int64_t>(p->o_in_off), ws.at<int64_t>(p->o_in_len), ws.at<int64_t>(p->o_out_off),
-	    ws.at<int64_t>(p->o_out_cap), n, d_out_len, d_in_used, d_status);
+	    ws.at<int64_t>(p->o_out_cap), n, d_out_len, d_in_used, d_status, ws.at<uint32_t>(p->o_hist));
 	p->mark(s, "end");
 	B200Z_CUDA(cudaGetLastError());
 	return B200Z_OK;

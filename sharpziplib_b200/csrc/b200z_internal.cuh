@@ -73,6 +73,14 @@ struct b200z_plan {
 	int level = 6, strategy = 0, wrap = 0, end_mode = 0;
 	std::vector<int64_t> in_len, in_off, out_off, out_cap;
 	int64_t in_bytes = 0, out_bytes = 0;
+	// deflate with history (b200z_deflate_plan_create_ex): in_len[] is history + data; an inflate plan keeps the
+	// preset-dictionary lengths in hist[]
+	int hist_kind = 0; // B200Z_HIST_*
+	bool check_seeded = false;
+	std::vector<int64_t> hist, pos_base;
+	std::vector<int32_t> bit_base;
+	std::vector<std::vector<uint8_t>> hist_mask;
+	int64_t o_hist = 0, o_bias = 0, o_bitbase = 0, o_hm_off = 0, o_hmask = 0, o_ck_off = 0, o_ck_len = 0;
 	b200z::Arena ws;
 	int launches = 0;
 	// deflate workspace offsets

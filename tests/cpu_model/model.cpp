@@ -13,7 +13,7 @@ using namespace b200z;
 namespace {
 
 // K1 as the kernel does it: 32 positions per step, a 16-bit head table relative to a sliding base.
-void model_links(const uint8_t *data, uint32_t n, std::vector<uint16_t> &link) {
+void model_links(const uint8_t *data, uint32_t n, std::vector<uint16_t> &link, uint32_t H = 0, const uint8_t *hmask = nullptr) {
 	link.assign(n, 0);
 	std::vector<uint16_t> head(32768, 0);
 	uint32_t winbase = 0; // head entry v > 0 means position winbase + v - 1
@@ -28,6 +28,7 @@ void model_links(const uint8_t *data, uint32_t n, std::vector<uint16_t> &link) {
 		for (int l = 0; l < 32; l++) {
 			uint32_t p = base + l;
 			valid[l] = p + 2 < n;
+			if (p < H) valid[l] = hmask ? hmask[p] == 0 : p + 2 < H;
 			h[l] = valid[l] ? hash3(data[p], data[p + 1], data[p + 2]) : 0xFFFFFFFFu;
 		}
 		uint32_t q[32];
@@ -70,9 +71,30 @@ struct Writer { // what the emit kernel does with atomicOr on zeroed 32-bit word
 
 } // namespace
 
+// History form (b200z_deflate_plan_create_ex): data = H history bytes + the segment, n = both; abs_bias = pos_base - H;
+// the bits start at bit_base; end_mode 0 finish / 2 flush (stream stays open); *outbits = total bits (bit_base included)
+static int model_run(const uint8_t *data, uint32_t n, uint32_t H, uint32_t abs_bias, uint32_t bit_base, const uint8_t *hmask,
+                     int level, int strategy, int flush_then_finish, int flush_only, uint8_t *out, uint64_t cap, uint64_t *outlen,
+                     uint64_t *outbits);
+
 extern "C" int model_deflate(const uint8_t *data, uint32_t n, int level, int strategy, int flush_then_finish,
                              uint8_t *out, uint64_t cap, uint64_t *outlen) {
+	uint64_t bits;
+	return model_run(data, n, 0, 0, 0, nullptr, level, strategy, flush_then_finish, 0, out, cap, outlen, &bits);
+}
+
+extern "C" int model_deflate_ex(const uint8_t *data, uint32_t n, uint32_t hist, uint32_t pos_base, uint32_t bit_base,
+                                const uint8_t *hmask, int level, int strategy, int end_mode, uint8_t *out, uint64_t cap,
+                                uint64_t *outbits) {
+	uint64_t len;
+	return model_run(data, n, hist, pos_base - hist, bit_base, hmask, level, strategy, 0, end_mode == 2, out, cap, &len, outbits);
+}
+
+static int model_run(const uint8_t *data, uint32_t n, uint32_t H, uint32_t abs_bias, uint32_t bit_base, const uint8_t *hmask,
+                     int level, int strategy, int flush_then_finish, int flush_only, uint8_t *out, uint64_t cap, uint64_t *outlen,
+                     uint64_t *outbits) {
 	LevelParams lp = level_params(level);
+	*outbits = 0;
 	std::vector<uint32_t> syms;
 	std::vector<uint32_t> blk_start(n / kBlockSyms + 3, 0), blk_ptop(n / kBlockSyms + 3, 0);
 	size_t nblocks = 0;
@@ -81,7 +103,7 @@ extern "C" int model_deflate(const uint8_t *data, uint32_t n, int level, int str
 		// level 0: stored blocks only (each block: 3 header bits, pad, LEN, ~LEN, bytes)
 		Writer W0;
 		uint64_t bp = 0;
-		stored_run(n, flush_then_finish ? 1 : 0, [&](uint32_t start, uint32_t len, bool last) {
+		stored_run(n - H, H, flush_then_finish ? 1 : (flush_only ? 2 : 0), [&](uint32_t start, uint32_t len, bool last) {
 			W0.put(bp, last ? 1 : 0, 3);
 			bp = (bp + 3 + 7) & ~7ull;
 			W0.put(bp, len & 0xFFFF, 16);
@@ -103,8 +125,9 @@ extern "C" int model_deflate(const uint8_t *data, uint32_t n, int level, int str
 		std::vector<uint16_t> head(32768, 0), prev(32768, 0);
 		FastEngine fe;
 		fe_init(fe, data, n, head.data(), prev.data());
+		fe_set_dictionary(fe, H);
 		blk_start.assign(n / kBlockSyms + 3, 0);
-		fe_run(fe, lp, strategy, flush_then_finish ? 2 : 0, [&](uint32_t sym) { syms.push_back(sym); },
+		fe_run(fe, lp, strategy, (flush_then_finish || flush_only) ? 2 : 0, [&](uint32_t sym) { syms.push_back(sym); },
 		       [&](uint32_t start, bool ok, bool last) {
 			       (void)last;
 			       blk_start[nblocks] = start;
@@ -114,21 +137,23 @@ extern "C" int model_deflate(const uint8_t *data, uint32_t n, int level, int str
 		total = (uint32_t)syms.size();
 		goto emit_blocks;
 	}
-	model_links(data, n, link);
-	// K2: every position
-	tabA.resize(n);
-	tabB.resize(n);
-	for (uint32_t p = 0; p < n; p++) match_search(data, link.data(), 0u, p, n, lp, tabA[p], tabB[p]);
+	model_links(data, n, link, H, hmask);
+	// K2: every position of the segment (history positions are candidates only)
+	tabA.assign(n, 0);
+	tabB.assign(n, 0);
+	for (uint32_t p = H; p < n; p++) match_search(data, link.data(), 0u, p, n, lp, tabA[p], tabB[p], abs_bias);
+	blk_start[0] = H;
 	{
 	// K3 as k_parse does it: rounds of 32 segments x kSeg positions; every lane parses its segment speculatively from a
 	// clean state, entries are handed lane -> lane until nothing changes, then a final pass emits at prefix-summed offsets
 	const uint32_t kSeg = 64, kRound = 32 * kSeg;
 	auto tabf = [&](uint32_t p, uint32_t &a, uint32_t &b) { a = tabA[p]; b = tabB[p]; };
 	auto bytef = [&](uint32_t q) { return (uint32_t)data[q]; };
-	auto slowf = [&](uint32_t p, uint32_t m0, uint32_t budget) { return match_search_above(data, link.data(), p, n, m0, budget); };
+	auto slowf = [&](uint32_t p, uint32_t m0, uint32_t budget) { return match_search_above(data, link.data(), p, n, m0, budget, abs_bias); };
 	ParseCarry carry;
 	parse_init(carry.st);
-	carry.last_top = 0;
+	carry.st.p = H;
+	carry.last_top = H;
 	int max_iters = 0;
 	long sum_iters = 0, n_rounds = 0;
 	for (uint32_t base = 0; base < n; base += kRound) {
@@ -139,8 +164,8 @@ extern "C" int model_deflate(const uint8_t *data, uint32_t n, int level, int str
 			if (l == 0) entry[l] = carry;
 			else {
 				parse_init(entry[l].st);
-				entry[l].st.p = base + l * kSeg;
-				entry[l].last_top = 0;
+				entry[l].st.p = base + l * kSeg > H ? base + l * kSeg : H;
+				entry[l].last_top = entry[l].st.p;
 			}
 			changed[l] = true;
 		}
@@ -190,7 +215,7 @@ extern "C" int model_deflate(const uint8_t *data, uint32_t n, int level, int str
 	}
 	if (getenv("B200Z_MODEL_VERBOSE")) fprintf(stderr, "parse: max propagation iterations %d, mean runs per round %.2f over %ld rounds\n", max_iters, n_rounds ? (double)sum_iters / n_rounds : 0.0, n_rounds);
 	size_t nfull = total / kBlockSyms;
-	const bool ended_full = !flush_then_finish && total > 0 && (total % kBlockSyms) == 0 && !carry.st.prevAvail;
+	const bool ended_full = !flush_then_finish && !flush_only && total > 0 && (total % kBlockSyms) == 0 && !carry.st.prevAvail;
 	if (ended_full) {
 		nblocks = nfull;
 	} else {
@@ -207,7 +232,7 @@ extern "C" int model_deflate(const uint8_t *data, uint32_t n, int level, int str
 	}
 emit_blocks:
 	Writer W;
-	uint64_t bitpos = 0;
+	uint64_t bitpos = bit_base;
 	std::vector<int> scratch(9 * 286 + 64);
 	for (size_t b = 0; b < nblocks; b++) {
 		size_t s0 = b * (size_t)kBlockSyms;
@@ -227,8 +252,8 @@ emit_blocks:
 			}
 		}
 		lit_freqs[256]++;
-		bool last = (b + 1 == nblocks) && !flush_then_finish;
-		int64_t storedOffset = (int64_t)blk_start[b] + 1 - 32768ll * (int64_t)slides_done(blk_ptop[b]);
+		bool last = (b + 1 == nblocks) && !flush_then_finish && !flush_only;
+		int64_t storedOffset = (int64_t)blk_start[b] + abs_bias + 1 - 32768ll * (int64_t)slides_done(blk_ptop[b] + abs_bias);
 		if (blk_ptop[b] >= 0xFFFFFFFEu) storedOffset = blk_ptop[b] == 0xFFFFFFFEu ? 0 : -1; // fast levels: decided by the engine
 		uint8_t lit_len[kLiteralNum], dist_len[kDistNum];
 		uint16_t lit_codes[kLiteralNum], dist_codes[kDistNum];
@@ -267,7 +292,7 @@ emit_blocks:
 			if (bitpos - body0 != plan.body_bits) return 101; // planner and emitter disagree
 		}
 	}
-	if (flush_then_finish) {
+	if (flush_then_finish || flush_only) {
 		// Deflater.Deflate FLUSHING_STATE (:486-504) then Finish: an empty final static block
 		int neededbits = 8 + (int)((0 - bitpos) & 7);
 		while (neededbits > 0) {
@@ -275,9 +300,12 @@ emit_blocks:
 			bitpos += 10;
 			neededbits -= 10;
 		}
-		W.put(bitpos, 3, 10);
-		bitpos += 10;
+		if (flush_then_finish) {
+			W.put(bitpos, 3, 10);
+			bitpos += 10;
+		}
 	}
+	*outbits = bitpos;
 	uint64_t nbytes = (bitpos + 7) >> 3;
 	if (nbytes > cap) return 102;
 	W.w.resize((nbytes + 3) / 4 + 1, 0);

@@ -66,3 +66,124 @@ def test_model_fast_and_stored_levels(model, oracle):
         for level in (0, 1, 2, 3, 4):
             assert model(d, level) == oracle.deflate(d, level=level), (name, level)
             assert model(d, level, 0, 1) == oracle.deflate(d, level=level, pattern=1), (name, level)
+
+
+# ---- streams with history: preset dictionary, input after Flush() -------------------------------------------
+class _SegmentedModel:
+    """The bookkeeping of the Deflater handle in b200z_api.cu (carried window image, uninserted-position mask, window
+    phase, sub-byte tail), driving the CPU model segment by segment."""
+
+    def __init__(self, root, level, strategy=0):
+        so = os.path.join(root, "tests", "cpu_model", "_build", "libmodel.so")
+        self.M = C.CDLL(so)
+        self.M.model_deflate_ex.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_int,
+                                            C.c_int, C.c_int, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
+        self.level, self.strategy = level, strategy
+        self.hist = bytearray()
+        self.mask = bytearray()
+        self.seen = 0
+        self.tail_bits, self.tail_count = 0, 0
+        self.out = bytearray()
+
+    def remember(self, seg, uninserted=2):
+        self.hist += seg
+        m = bytearray(len(seg))
+        for k in range(min(uninserted, len(seg))):
+            m[len(seg) - 1 - k] = 1
+        self.mask += m
+        if len(self.hist) > 32768:
+            cut = len(self.hist) - 32768
+            del self.hist[:cut]
+            del self.mask[:cut]
+        self.seen += len(seg)
+
+    def set_dictionary(self, d):
+        if len(d) < 3:
+            return
+        self.remember(d[-32506:])
+
+    def segment(self, seg, end_mode):
+        H = len(self.hist)
+        buf = np.frombuffer(bytes(self.hist) + bytes(seg) + b"\0", dtype=np.uint8).copy()
+        mask = np.frombuffer(bytes(self.mask) + b"\0", dtype=np.uint8).copy()
+        cap = len(seg) + len(seg) // 8 + 1024
+        out = np.zeros(cap, np.uint8)
+        bits = C.c_uint64(0)
+        rc = self.M.model_deflate_ex(buf.ctypes.data, H + len(seg), H, self.seen, self.tail_count, mask.ctypes.data, self.level,
+                                     self.strategy, end_mode, out.ctypes.data, cap, C.byref(bits))
+        assert rc == 0, rc
+        nb = bits.value
+        o = bytearray(out[:(nb + 7) // 8].tobytes())
+        if o:
+            o[0] |= self.tail_bits
+        whole = nb // 8
+        self.out += o[:whole]
+        self.tail_count = nb & 7
+        self.tail_bits = (o[whole] & ((1 << self.tail_count) - 1)) if self.tail_count else 0
+        if end_mode == 0 and self.tail_count:
+            self.out.append(self.tail_bits)
+            self.tail_bits = self.tail_count = 0
+        self.remember(seg)
+
+
+def _oracle_segments(oracle_mod, level, segs, dictionary=None, strategy=0):
+    """reference call sequence: [SetDictionary] (SetInput, Flush, drain)* SetInput, Finish, drain -- zlib framing stripped"""
+    from oracle_lib import Deflater
+    d = Deflater(level, nowrap=dictionary is None)
+    d.set_strategy(strategy)
+    if dictionary is not None:
+        d.set_dictionary(dictionary)
+    out = bytearray()
+
+    def drain():
+        while True:
+            b = d.deflate(65536)
+            if not b:
+                break
+            out.extend(b)
+    for i, s in enumerate(segs):
+        d.set_input(s)
+        if i + 1 < len(segs):
+            d.flush()
+        else:
+            d.finish()
+        drain()
+    return bytes(out)
+
+
+def _model_segments(level, segs, dictionary=None, strategy=0):
+    m = _SegmentedModel(ROOT, level, strategy)
+    if dictionary is not None:
+        m.set_dictionary(dictionary)
+    for i, s in enumerate(segs):
+        m.segment(s, 2 if i + 1 < len(segs) else 0)
+    return bytes(m.out)
+
+
+def test_model_dictionary(model, oracle):
+    from sharpziplib_b200 import datagen
+    text = datagen.gen_text(120000, 5).tobytes()
+    for level in (1, 4, 5, 6, 9):
+        for dlen in (2, 3, 100, 32506, 40000):
+            dic = text[:dlen]
+            data = text[20000:20000 + 70000]
+            ref = _oracle_segments(oracle, level, [data], dictionary=dic)
+            # zlib framing: 2 header bytes + 4 DICTID bytes in front, 4 Adler bytes behind
+            assert ref[1] & 0x20
+            got = _model_segments(level, [data], dictionary=dic)
+            assert got == ref[6:-4], (level, dlen)
+
+
+def test_model_flush_continue(model, oracle):
+    from sharpziplib_b200 import datagen
+    text = datagen.gen_text(300000, 9).tobytes()
+    mixed = datagen.silesia_mix(4, 200000, config=3).tobytes()
+    cases = [
+        [text[:1000], text[1000:5000], text[5000:5001], text[5001:5003], text[5003:90000]],
+        [text[:40000], text[40000:140000], text[140000:300000]],   # crosses the first window slides
+        [mixed[:65000], mixed[65000:65300], mixed[65300:131000], b"", mixed[131000:]],
+        [b"", text[:10], b"", text[10:20000]],
+    ]
+    for level in (5, 6, 9):
+        for ci, segs in enumerate(cases):
+            assert _model_segments(level, segs) == _oracle_segments(oracle, level, segs), (level, ci)

@@ -8,6 +8,7 @@ import numpy as np
 import pytest
 
 from helpers import corpus_small, crafted_t8
+from sharpziplib_b200 import datagen
 
 pytestmark = pytest.mark.gpu
 GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_fixtures.json")))
@@ -170,18 +171,175 @@ def test_deflate_fast_and_stored_levels(z, oracle, level):
             assert outs == [oracle.deflate(b, level=level, strategy=strategy) for b in bufs[:3]]
 
 
-def test_unsupported_sequences_fail_loudly(z):
-    d = z.Deflater(6, False)
-    with pytest.raises(z.B200zUnsupported):
-        d.SetDictionary(b"hello hello")
+def _drain(d):
+    out = bytearray()
+    buf = bytearray(65536)
+    while True:
+        k = d.Deflate(buf)
+        if k <= 0:
+            break
+        out += buf[:k]
+    return bytes(out)
+
+
+def _ref_segments(level, segs, dictionary=None, nowrap=True, strategy=0):
+    from oracle_lib import Deflater
+    d = Deflater(level, nowrap=nowrap)
+    d.set_strategy(strategy)
+    if dictionary is not None:
+        d.set_dictionary(dictionary)
+    out = bytearray()
+    for i, s in enumerate(segs):
+        d.set_input(s)
+        d.flush() if i + 1 < len(segs) else d.finish()
+        while True:
+            b = d.deflate(65536)
+            if not b:
+                break
+            out += b
+    return bytes(out), d.adler & 0xFFFFFFFF, d.total_in, d.total_out
+
+
+def _gpu_segments(z, level, segs, dictionary=None, nowrap=True, strategy=0):
+    d = z.Deflater(level, nowrap)
+    d.SetStrategy(strategy)
+    if dictionary is not None:
+        d.SetDictionary(dictionary)
+    out = bytearray()
+    for i, s in enumerate(segs):
+        d.SetInput(s)
+        d.Flush() if i + 1 < len(segs) else d.Finish()
+        out += _drain(d)
+    return bytes(out), d.Adler & 0xFFFFFFFF, d.TotalIn, d.TotalOut
+
+
+@pytest.mark.parametrize("level", [5, 6, 9])
+def test_deflater_input_after_flush(z, oracle, level):
+    """SetInput after a sync Flush(): window, hash chains, slide phase and the sub-byte tail carry over (levels 5-9)"""
+    text = datagen.gen_text(300000, 9).tobytes()
+    mixed = datagen.silesia_mix(4, 200000, config=3).tobytes()
+    cases = [
+        [text[:1000], text[1000:5000], text[5000:5001], text[5001:5003], text[5003:90000]],
+        [text[:40000], text[40000:140000], text[140000:300000]],
+        [mixed[:65000], mixed[65000:65300], mixed[65300:131000], b"", mixed[131000:]],
+        [b"", text[:10], b"", text[10:20000]],
+        [crafted_t8()[:65273], crafted_t8()[65273:]],
+    ]
+    for ci, segs in enumerate(cases):
+        for nowrap in (True, False):
+            assert _gpu_segments(z, level, segs, nowrap=nowrap) == _ref_segments(level, segs, nowrap=nowrap), (ci, nowrap)
+    assert _gpu_segments(z, level, cases[1], strategy=1) == _ref_segments(level, cases[1], strategy=1)
+
+
+@pytest.mark.parametrize("level", [0, 1, 4, 5, 6, 9])
+def test_deflater_preset_dictionary(z, oracle, level):
+    """Deflater.SetDictionary: FDICT header + DICTID, dictionary tail as match history (all levels)"""
+    text = datagen.gen_text(120000, 5).tobytes()
+    data = text[20000:90000]
+    for dlen in (2, 3, 100, 32506, 40000):
+        dic = text[:dlen]
+        got = _gpu_segments(z, level, [data], dictionary=dic, nowrap=False)
+        assert got == _ref_segments(level, [data], dictionary=dic, nowrap=False), dlen
+        assert got[0][1] & 0x20
+    if level >= 5:  # dictionary, then input after a flush
+        segs = [data[:30000], data[30000:30002], data[30002:]]
+        assert _gpu_segments(z, level, segs, dictionary=text[:5000], nowrap=False) == \
+            _ref_segments(level, segs, dictionary=text[:5000], nowrap=False)
+
+
+def test_dictionary_state_errors(z):
     d = z.Deflater(6, True)
-    d.SetInput(b"abc" * 100)
-    d.Flush()
-    buf = bytearray(512)
-    while d.Deflate(buf) > 0:
-        pass
-    with pytest.raises(z.B200zUnsupported):
+    with pytest.raises(Exception):  # a raw deflater never is in INIT_STATE (Deflater.cs:206, :561)
+        d.SetDictionary(b"hello hello")
+    d = z.Deflater(6, False)
+    d.SetDictionary(b"hello hello")
+    with pytest.raises(Exception):
+        d.SetDictionary(b"twice")
+    i = z.Inflater(False)
+    with pytest.raises(Exception):  # "Dictionary is not needed"
+        i.SetDictionary(b"abc")
+
+
+def test_unsupported_sequences_fail_loudly(z):
+    for level in (0, 3):  # DeflateStored / DeflateFast are not re-entrant on the device
+        d = z.Deflater(level, True)
+        d.SetInput(b"abc" * 100)
+        d.Flush()
+        _drain(d)
         d.SetInput(b"more input after a sync flush")
+        d.Finish()
+        with pytest.raises(z.B200zUnsupported):
+            _drain(d)
+
+
+def test_inflater_preset_dictionary(z, oracle):
+    from oracle_lib import Deflater
+    text = datagen.gen_text(150000, 7).tobytes()
+    for dlen, level in ((100, 6), (32506, 9), (50000, 1), (40000, 0)):
+        dic, data = text[:dlen], text[60000:150000]
+        comp, adler, _, _ = _ref_segments(level, [data], dictionary=dic, nowrap=False)
+        inf = z.Inflater(False)
+        inf.SetInput(comp)
+        buf = bytearray(len(data) + 100)
+        assert inf.Inflate(buf) == 0 and inf.IsNeedingDictionary
+        assert (inf.Adler & 0xFFFFFFFF) == int.from_bytes(comp[2:6], "big")
+        with pytest.raises(z.SharpZipBaseException):  # "Wrong adler checksum"
+            inf.SetDictionary(dic[:-1] + b"?")
+        inf.SetDictionary(dic)
+        got = bytearray()
+        while not inf.IsFinished:
+            k = inf.Inflate(buf)
+            if k == 0 and inf.IsNeedingInput:
+                break
+            got += buf[:k]
+        assert bytes(got) == data and inf.IsFinished, (dlen, level)
+        assert (inf.Adler & 0xFFFFFFFF) == (adler & 0xFFFFFFFF)
+
+
+def test_device_plans_with_dictionaries(z, oracle):
+    """batch form: every stream of a plan with its own preset dictionary in front of its data"""
+    import torch
+    text = datagen.gen_text(200000, 11).tobytes()
+    items = [(text[:1000], text[50000:120000]), (text[1000:33506], text[100000:200000]), (b"", text[:5000]), (text[:40], b"")]
+    lens = [len(d) for _, d in items]
+    dls = [len(k) for k, _ in items]
+    for level in (1, 6):
+        plan = z.DeflatePlan(lens, level=level, dict_lens=dls)
+        blob = np.zeros(plan.in_bytes, np.uint8)
+        for i, (k, d) in enumerate(items):
+            o = int(plan.in_offsets[i])
+            blob[o:o + len(k) + len(d)] = np.frombuffer(k + d, np.uint8)
+            assert int(plan.data_offsets[i]) == o + len(k)
+        d_in = torch.from_numpy(blob).cuda()
+        d_out = torch.zeros(plan.out_bytes, dtype=torch.uint8, device="cuda")
+        d_len = torch.zeros(plan.n, dtype=torch.int64, device="cuda")
+        d_st = torch.zeros(plan.n, dtype=torch.int32, device="cuda")
+        plan.run(d_in, d_out, d_len, d_st)
+        torch.cuda.synchronize()
+        assert d_st.cpu().tolist() == [0] * plan.n
+        outs = []
+        for i, (k, d) in enumerate(items):
+            o = int(plan.out_offsets[i])
+            got = d_out[o:o + int(d_len[i])].cpu().numpy().tobytes()
+            want = _ref_segments(level, [d], dictionary=k, nowrap=False)[0]
+            want = want[6:-4]  # zlib framing: header + DICTID in front, Adler-32 behind
+            assert got == want, (level, i)
+            outs.append(got)
+        # and back through an inflate plan with the same dictionaries
+        ip = z.InflatePlan([len(o) for o in outs], [l + 64 for l in lens], dict_lens=dls)
+        blob = np.zeros(ip.in_bytes, np.uint8)
+        for i, (k, _) in enumerate(items):
+            o = int(ip.in_offsets[i])
+            blob[o:o + len(k) + len(outs[i])] = np.frombuffer(k + outs[i], np.uint8)
+        d_in = torch.from_numpy(blob).cuda()
+        d_out = torch.zeros(ip.out_bytes, dtype=torch.uint8, device="cuda")
+        d_used = torch.zeros(ip.n, dtype=torch.int64, device="cuda")
+        ip.run(d_in, d_out, d_len, d_st, None, d_used)
+        torch.cuda.synchronize()
+        assert d_st.cpu().tolist() == [0] * ip.n
+        for i, (_, d) in enumerate(items):
+            o = int(ip.out_offsets[i])
+            assert d_out[o:o + int(d_len[i])].cpu().numpy().tobytes() == d, (level, i)
 
 
 # ---- inflate ---------------------------------------------------------------------------------------------
