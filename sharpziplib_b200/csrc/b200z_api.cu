@@ -664,7 +664,7 @@ struct DeflaterH {
 	// segment); hist_mask flags the positions InsertString never saw (the last two of the dictionary / of each segment)
 	std::vector<uint8_t> history, hist_mask;
 	int64_t window_seen = 0;  // dictionary bytes kept + TotalIn: the SlideWindow phase of the next segment
-	bool dict_set = false, deflate_called = false;
+	bool dict_set = false, deflate_called = false, started = false;
 	uint32_t dict_adler = 0;
 	std::vector<uint8_t> input;    // everything SetInput handed over and not yet compressed
 	std::vector<uint8_t> pending;  // produced bytes not yet drained by Deflate()
@@ -693,7 +693,7 @@ static int deflater_run_device(DeflaterH *d, int end_mode) {
 	// compresses d->input as the next segment of the stream; END_FLUSH keeps the stream open and may end inside a byte
 	const int64_t len = (int64_t)d->input.size();
 	const int64_t H = (int64_t)d->history.size();
-	const bool continuing = d->total_in > 0 || d->flushed_once;
+	const bool continuing = d->started; // an earlier segment (possibly empty) has been emitted
 	if (continuing && d->level == 0) {
 		set_error("level 0: input after a sync Flush() is not accelerated (DeflateStored block state is not positional)");
 		return B200Z_E_UNSUPPORTED;
@@ -742,6 +742,7 @@ static int deflater_run_device(DeflaterH *d, int end_mode) {
 		if (end_mode == B200Z_END_FINISH) d->tail.align(d->pending); // FINISHING_STATE: AlignToByte (:507)
 		if (!d->raw) d->adler = r.check[0];
 		d->total_in += len;
+		d->started = true;
 		deflater_remember(d, d->input.data(), (size_t)len, 2);
 		d->input.clear();
 	}
@@ -783,7 +784,7 @@ int b200z_deflater_reset(void *h) { // Deflater.Reset :204-210 keeps level and s
 	d->history.clear();
 	d->hist_mask.clear();
 	d->window_seen = 0;
-	d->dict_set = d->deflate_called = false;
+	d->dict_set = d->deflate_called = d->started = false;
 	d->dict_adler = 0;
 	return B200Z_OK;
 }

@@ -191,6 +191,15 @@ def _ref_segments(level, segs, dictionary=None, nowrap=True, strategy=0):
     out = bytearray()
     for i, s in enumerate(segs):
         d.set_input(s)
+        if level == 0:
+            # DeflaterOutputStream order (Write drains before Finish): at level 0 a Finish() that precedes the drain marks a
+            # size-triggered stored block final and drops the rest of the input (DeflaterEngine.cs:629-641), a reference
+            # quirk the stream classes never exercise
+            while True:
+                b = d.deflate(65536)
+                if not b:
+                    break
+                out += b
         d.flush() if i + 1 < len(segs) else d.finish()
         while True:
             b = d.deflate(65536)
