@@ -17,6 +17,7 @@ constexpr int kRun = 65536;    // positions per k_links warp
 constexpr int kTile = 32768;   // positions per k_match CTA
 constexpr int kTileData = 2 * kTile + 320; // bytes of window staged per tile (history + tile + max match + pad)
 constexpr int kMatchThreads = 1024;
+constexpr int kMatchClasses = 8; // expected-walk-length classes of k_match (0 = nothing to search)
 
 // ------------------------------------------------------------------------------------------------
 // K1: link[p] = distance from p to the previous inserted position with the same hash (0 = none / too far).
@@ -126,7 +127,7 @@ __global__ void __launch_bounds__(32) k_links(const uint8_t *__restrict__ in, ui
 __global__ void __launch_bounds__(kMatchThreads, 1)
     k_match(const uint8_t *__restrict__ in, const uint16_t *__restrict__ link, uint2 *__restrict__ mt,
             const int64_t *__restrict__ in_off, const int64_t *__restrict__ in_len, const int2 *__restrict__ tile_desc,
-            const uint32_t *__restrict__ hist, const int64_t *__restrict__ bias, LevelParams lp) {
+            const uint32_t *__restrict__ hist, const int64_t *__restrict__ bias, uint32_t *__restrict__ scratch, LevelParams lp) {
 	extern __shared__ __align__(16) uint8_t smem[];
 	uint8_t *s_data = smem;
 	uint16_t *s_link = reinterpret_cast<uint16_t *>(smem + kTileData);
@@ -162,12 +163,77 @@ __global__ void __launch_bounds__(kMatchThreads, 1)
 	const uint32_t chain = (uint32_t)lp.chain, budgetB = chain >> 2;
 	const uint32_t H = hist[td.x];            // positions below H are history: candidates only
 	const uint32_t ab = (uint32_t)bias[td.x]; // absolute stream offset of buffer position 0 (window-slide phase, trap T8)
-	for (uint32_t p = t0 + threadIdx.x; p < t1; p += kMatchThreads) {
-		if (p < H) continue;
+	// ---- order the tile's positions by expected chain length ----
+	// A warp runs as long as its longest chain walk (ncu: 13 of 32 lanes active in the candidate loop).  So the positions
+	// are bucketed by an estimate of their walk length (the first hops are exact, beyond that the hop density of the first
+	// four extrapolated over the window) and handed to the threads longest first: warps then hold walks of similar length.
+	// The order only decides who computes what; every position's result is unchanged.
+	__shared__ uint32_t s_cls[2][kMatchClasses];
+	if (threadIdx.x < 2 * kMatchClasses) (&s_cls[0][0])[threadIdx.x] = 0;
+	__syncthreads();
+	uint16_t *order = reinterpret_cast<uint16_t *>(scratch + off + t0); // 4 bytes per position are free here until k_parse_gather
+	uint32_t cw[4] = {0u, 0u, 0u, 0u};                                   // 32 x 4 bits: this thread's classes
+	const int lane = threadIdx.x & 31;
+#pragma unroll
+	for (int k = 0; k < kTile / kMatchThreads; k++) {
+		const uint32_t p = t0 + threadIdx.x + (uint32_t)k * kMatchThreads;
+		uint32_t cls = 0;
+		if (p < t1 && p >= H) {
+			const uint32_t la = n - p;
+			uint32_t d = la >= (uint32_t)kMinMatch ? (uint32_t)s_link[p - w0] : 0u;
+			if (d > (uint32_t)kMaxDist - (is_slide_pos(p + ab) ? 1u : 0u)) d = 0; // DeflaterEngine.cs:788 + trap T8
+			if (d == 0) out[p] = make_uint2(0u, 0u);
+			else {
+				const uint32_t is = p - w0;
+				uint32_t dist = d, hops = 1;
+				while (hops < 4) {
+					const uint32_t l2 = s_link[is - dist];
+					if (l2 == 0 || dist + l2 >= (uint32_t)kMaxDist) break;
+					dist += l2;
+					++hops;
+				}
+				if (hops < 4) cls = hops <= 2 ? 1u : 2u;
+				else {
+					const uint32_t est = (4u * (uint32_t)kMaxDist) / dist; // candidates if the chain stays this dense
+					cls = est <= 8 ? 3u : est <= 16 ? 4u : est <= 32 ? 5u : est <= 64 ? 6u : 7u;
+				}
+			}
+		}
+		const uint32_t peers = __match_any_sync(0xffffffffu, cls);
+		if (cls && lane == __ffs((int)peers) - 1) atomicAdd(&s_cls[0][cls], (uint32_t)__popc(peers));
+		cw[k >> 3] |= cls << ((k & 7) * 4);
+	}
+	__syncthreads();
+	uint32_t total = 0;
+	{
+		// class bases, longest walks first
+		uint32_t b = 0;
+		uint32_t mine = 0;
+		for (int c = kMatchClasses - 1; c >= 1; c--) {
+			if ((int)threadIdx.x == c) mine = b;
+			b += s_cls[0][c];
+		}
+		total = b;
+		__syncthreads();
+		if (threadIdx.x >= 1 && threadIdx.x < kMatchClasses) s_cls[1][threadIdx.x] = mine;
+		__syncthreads();
+	}
+#pragma unroll
+	for (int k = 0; k < kTile / kMatchThreads; k++) {
+		const uint32_t cls = (cw[k >> 3] >> ((k & 7) * 4)) & 15u;
+		const uint32_t peers = __match_any_sync(0xffffffffu, cls);
+		uint32_t slot = 0;
+		const int leader = __ffs((int)peers) - 1;
+		if (cls && lane == leader) slot = atomicAdd(&s_cls[1][cls], (uint32_t)__popc(peers));
+		slot = __shfl_sync(0xffffffffu, slot, leader);
+		if (cls) order[slot + (uint32_t)__popc(peers & ((1u << lane) - 1u))] = (uint16_t)(threadIdx.x + (uint32_t)k * kMatchThreads);
+	}
+	__syncthreads();
+	for (uint32_t i = threadIdx.x; i < total; i += kMatchThreads) {
+		const uint32_t p = t0 + (uint32_t)__ldcg(&order[i]);
 		uint32_t resA = 0, resB = 0;
 		const uint32_t la = n - p;
-		uint32_t d = la >= (uint32_t)kMinMatch ? (uint32_t)s_link[p - w0] : 0u;
-		if (d > (uint32_t)kMaxDist - (is_slide_pos(p + ab) ? 1u : 0u)) d = 0; // DeflaterEngine.cs:788 + trap T8
+		const uint32_t d = (uint32_t)s_link[p - w0];
 		if (d != 0) {
 			const uint32_t maxlen = la < (uint32_t)kMaxMatch ? la : (uint32_t)kMaxMatch;
 			const uint32_t nice = la < (uint32_t)lp.nice ? la : (uint32_t)lp.nice;
@@ -1113,7 +1179,7 @@ int deflate_plan_run(b200z_plan *p, const uint8_t *d_in, uint8_t *d_out, int64_t
 		p->mark(s, "k_match");
 		if (p->n_tiles)
 			k_match<<<p->n_tiles, kMatchThreads, kTileData + 2 * 2 * kTile, s>>>(d_in, link, mt, in_off, in_len,
-			                                                                   ws.at<int2>(p->o_tile_desc), hist, bias, lp);
+			                                                                   ws.at<int2>(p->o_tile_desc), hist, bias, sym, lp);
 		p->mark(s, "k_parse");
 		{
 			uint32_t *sym_local = ws.at<uint32_t>(p->o_sym_local);
