@@ -243,12 +243,37 @@ __global__ void __launch_bounds__(kMatchThreads, 1)
 			bool haveB = false;
 			const uint32_t s0 = sp[0], s1 = sp[1];
 			uint32_t scan_end1 = s1, scan_end = sp[2];
+			// bytes 2..9 of the scan string stay in registers: most extensions end inside them
+			uint32_t sw0, sw1;
+			{
+				const uint32_t as = is + 2;
+				const uint32_t *ws = reinterpret_cast<const uint32_t *>(s_data + (as & ~3u));
+				const uint32_t w1 = ws[1], sh = (as & 3u) * 8u;
+				sw0 = __funnelshift_r(ws[0], w1, sh);
+				sw1 = __funnelshift_r(w1, ws[2], sh);
+			}
 			for (;;) {
 				const uint32_t ic = is - dist;
 				const uint8_t *c = s_data + ic;
 				++cnt;
 				if (c[m] == scan_end && c[m - 1] == scan_end1 && c[0] == s0 && c[1] == s1) {
 					uint32_t l = 2;
+					if (maxlen >= 10) {
+						const uint32_t ac = ic + 2;
+						const uint32_t *wc = reinterpret_cast<const uint32_t *>(s_data + (ac & ~3u));
+						const uint32_t w1 = wc[1], sh = (ac & 3u) * 8u;
+						uint32_t x = __funnelshift_r(wc[0], w1, sh) ^ sw0;
+						if (x) {
+							l = 2 + ((uint32_t)(__ffs((int)x) - 1) >> 3);
+							goto lcp_done;
+						}
+						x = __funnelshift_r(w1, wc[2], sh) ^ sw1;
+						if (x) {
+							l = 6 + ((uint32_t)(__ffs((int)x) - 1) >> 3);
+							goto lcp_done;
+						}
+						l = 10;
+					}
 					while (l + 4 <= maxlen) {
 						const uint32_t ac = ic + l, as = is + l;
 						const uint32_t *wc = reinterpret_cast<const uint32_t *>(s_data + (ac & ~3u));
