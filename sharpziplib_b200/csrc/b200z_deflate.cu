@@ -17,7 +17,7 @@ constexpr int kRun = 65536;    // positions per k_links warp
 constexpr int kTile = 32768;   // positions per k_match CTA
 constexpr int kTileData = 2 * kTile + 320; // bytes of window staged per tile (history + tile + max match + pad)
 constexpr int kMatchThreads = 1024;
-constexpr int kMatchClasses = 8; // expected-walk-length classes of k_match (0 = nothing to search)
+constexpr int kMatchClasses = 16; // expected-walk-length classes of k_match (0 = nothing to search)
 
 // ------------------------------------------------------------------------------------------------
 // K1: link[p] = distance from p to the previous inserted position with the same hash (0 = none / too far).
@@ -212,16 +212,18 @@ __global__ void __launch_bounds__(kMatchThreads, 1)
 			else {
 				const uint32_t is = p - w0;
 				uint32_t dist = d, hops = 1;
-				while (hops < 4) {
+				while (hops < 8) {
 					const uint32_t l2 = s_link[is - dist];
 					if (l2 == 0 || dist + l2 >= (uint32_t)kMaxDist) break;
 					dist += l2;
 					++hops;
 				}
-				if (hops < 4) cls = hops <= 2 ? 1u : 2u;
+				if (hops < 8) cls = hops <= 1 ? 1u : hops <= 2 ? 2u : hops <= 4 ? 3u : hops <= 6 ? 4u : 5u;
 				else {
-					const uint32_t est = (4u * (uint32_t)kMaxDist) / dist; // candidates if the chain stays this dense
-					cls = est <= 8 ? 3u : est <= 16 ? 4u : est <= 32 ? 5u : est <= 64 ? 6u : 7u;
+					uint32_t est = (8u * (uint32_t)kMaxDist) / dist; // candidates if the chain stays this dense
+					if (est > chain) est = chain;
+					cls = est <= 11 ? 6u : est <= 16 ? 7u : est <= 23 ? 8u : est <= 32 ? 9u : est <= 45 ? 10u : est <= 64 ? 11u
+					      : est <= 91 ? 12u : est <= 128 ? 13u : est <= 512 ? 14u : 15u;
 				}
 			}
 		}
