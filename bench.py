@@ -262,9 +262,26 @@ def main():
     U_inf = sum(a.size for a in t_np)
     C_inf = sum(len(c) for c in comp)
 
-    def step_resident():
-        dplan.run(d_din, d_dout, d_dlen, d_dst)
-        iplan.run(d_iin, d_iout, d_ilen, d_ist, None, d_iused)
+    # The two legs are independent: the inflate leg (one long, latency-bound kernel on few warps) runs on a second stream
+    # next to the deflate leg's kernels instead of after them.
+    s_leg = torch.cuda.Stream(device=dev)
+    ev_leg0, ev_leg1 = torch.cuda.Event(), torch.cuda.Event()
+
+    def step_resident(overlap=True):
+        cur = torch.cuda.current_stream()
+        if not overlap:
+            dplan.run(d_din, d_dout, d_dlen, d_dst)
+            iplan.run(d_iin, d_iout, d_ilen, d_ist, None, d_iused)
+            return
+        # the inflate kernel starts when the match search (whose CTAs take a whole SM's shared memory) is through and
+        # then shares the SMs with the parse / Huffman / bit-packing kernels
+        dplan.run(d_din, d_dout, d_dlen, d_dst, stages=z.STAGE_SEARCH)
+        ev_leg0.record(cur)
+        s_leg.wait_event(ev_leg0)
+        iplan.run(d_iin, d_iout, d_ilen, d_ist, None, d_iused, stream=s_leg)
+        ev_leg1.record(s_leg)
+        dplan.run(d_din, d_dout, d_dlen, d_dst, stages=z.STAGE_ENCODE)
+        cur.wait_event(ev_leg1)
 
     # ---- end to end from pinned host buffers, public plan API.  Three streams (upload / kernels / download) and two sets
     # of device buffers, run as a software pipeline the way a server would: while step i's kernels run, step i+1's inputs
@@ -272,7 +289,7 @@ def main():
     # reads all of its results (inflated bytes, packed deflate output, lengths) back inside the timed region; the last
     # step's downloads are drained before the closing timestamp.  The only host wait is for the packed size of the
     # PREVIOUS step (b200z_plan_pack: only the bytes actually produced cross PCIe).
-    s_up, s_run, s_down = (torch.cuda.Stream(device=dev) for _ in range(3))
+    s_up, s_run, s_run2, s_down = (torch.cuda.Stream(device=dev) for _ in range(4))  # s_run2: the inflate leg
 
     class Slot:
         def __init__(self, first):
@@ -286,7 +303,7 @@ def main():
             self.d_poff = torch.zeros(n_def + 1, dtype=torch.int64, device=dev)
             self.h_poff = torch.zeros(n_def + 1, dtype=torch.int64).pin_memory()
             self.h_dlen = torch.zeros(n_def, dtype=torch.int64).pin_memory()
-            self.ev_hi, self.ev_hd, self.ev_i, self.ev_d, self.ev_dl = (torch.cuda.Event() for _ in range(5))
+            self.ev_hi, self.ev_hd, self.ev_i, self.ev_d, self.ev_dl, self.ev_s = (torch.cuda.Event() for _ in range(6))
             self.used = False
 
     slots = [Slot(True), Slot(False)]
@@ -308,11 +325,12 @@ def main():
         pipe["k"] += 1
         if not sl.used:
             cur = torch.cuda.current_stream()
-            for st in (s_up, s_run, s_down):
+            for st in (s_up, s_run, s_run2, s_down):
                 st.wait_stream(cur)
         with torch.cuda.stream(s_up):
             if sl.used:
                 s_up.wait_event(sl.ev_d)   # the kernels that read this slot's inputs two steps ago are done
+                s_up.wait_event(sl.ev_i)
             sl.d_iin.copy_(h_iin, non_blocking=True)
             sl.ev_hi.record(s_up)
             sl.d_din.copy_(h_din, non_blocking=True)
@@ -320,11 +338,17 @@ def main():
         with torch.cuda.stream(s_run):
             if sl.used:
                 s_run.wait_event(sl.ev_dl)  # this slot's previous outputs have left the device
-            s_run.wait_event(sl.ev_hi)
-            iplan.run(sl.d_iin, sl.d_iout, sl.d_ilen, sl.d_ist, None, sl.d_iused, stream=s_run)
-            sl.ev_i.record(s_run)
             s_run.wait_event(sl.ev_hd)
-            dplan.run(sl.d_din, sl.d_dout, sl.d_dlen, sl.d_dst, stream=s_run)
+            dplan.run(sl.d_din, sl.d_dout, sl.d_dlen, sl.d_dst, stream=s_run, stages=z.STAGE_SEARCH)
+            sl.ev_s.record(s_run)
+        with torch.cuda.stream(s_run2):
+            if sl.used:
+                s_run2.wait_event(sl.ev_dl)
+            s_run2.wait_event(sl.ev_hi)  # free-running next to the deflate leg (gating it on ev_s measured slower here)
+            iplan.run(sl.d_iin, sl.d_iout, sl.d_ilen, sl.d_ist, None, sl.d_iused, stream=s_run2)
+            sl.ev_i.record(s_run2)
+        with torch.cuda.stream(s_run):
+            dplan.run(sl.d_din, sl.d_dout, sl.d_dlen, sl.d_dst, stream=s_run, stages=z.STAGE_ENCODE)
             dplan.pack(sl.d_dout, sl.d_dlen, sl.d_pack, sl.d_poff, stream=s_run)
             sl.h_poff.copy_(sl.d_poff, non_blocking=True)
             sl.h_dlen.copy_(sl.d_dlen, non_blocking=True)
@@ -343,7 +367,7 @@ def main():
             finish(pipe["pending"])
             pipe["pending"] = None
         cur = torch.cuda.current_stream()
-        for st in (s_up, s_run, s_down):
+        for st in (s_up, s_run, s_run2, s_down):
             cur.wait_stream(st)
 
     def barrier():
@@ -401,7 +425,7 @@ def main():
     acc = {}
     reps = max(3, min(args.steps, 5))
     for _ in range(reps):
-        step_resident()
+        step_resident(overlap=False)  # one kernel at a time: these are per-kernel durations
         torch.cuda.synchronize()
         for k, v in list(dplan.timings().items()) + list(iplan.timings().items()):
             acc[k] = acc.get(k, 0.0) + v / reps
@@ -459,7 +483,7 @@ def main():
             "e2e": {"value": e2e_val, "unit": "GB/s", "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": int(dplan.in_bytes + iplan.in_bytes),
                     "d2h_bytes_per_step": int(e2e_d2h[0]),
-                    "how": "pinned host buffers; upload / kernel / download streams over two device buffer sets (step i+1 uploads and step i-1 downloads overlap step i's kernels); packed D2H of the deflate output; %d steps + drain timed" % n_e2e},
+                    "how": "pinned host buffers; upload / deflate-leg / inflate-leg / download streams over two device buffer sets (step i+1 uploads and step i-1 downloads overlap step i's kernels); packed D2H of the deflate output; %d steps + drain timed" % n_e2e},
             "gpu_launches": int(dplan.launches + iplan.launches),
             "clocks": clocks,
         }

@@ -129,6 +129,14 @@ int b200z_plan_get_timings(b200z_plan *plan, char *names, int32_t names_cap, flo
  * comp_len - Inflater.RemainingInput (Inflater.cs:878, trap T14). */
 int b200z_plan_run(b200z_plan *plan, const uint8_t *d_in, uint8_t *d_out, int64_t *d_out_len, int32_t *d_status,
                    uint32_t *d_check, int64_t *d_in_used, void *cuda_stream);
+/* The same in two halves, for callers that overlap independent work on other streams: SEARCH is the match finding of a
+ * level 5-9 deflate plan (its kernels take a whole SM's shared memory), ENCODE everything else (parse, Huffman planning,
+ * bit packing, checksums; all of a level 0-4 or inflate plan).  Run SEARCH then ENCODE with the same arguments on the
+ * same stream; b200z_plan_run is both.  Per-kernel timing is only recorded by whole runs. */
+#define B200Z_STAGE_SEARCH 1
+#define B200Z_STAGE_ENCODE 2
+int b200z_plan_run_stages(b200z_plan *plan, const uint8_t *d_in, uint8_t *d_out, int64_t *d_out_len, int32_t *d_status,
+                          uint32_t *d_check, int64_t *d_in_used, int stages, void *cuda_stream);
 
 /* Packs the streams a run produced back to back (16-byte aligned starts) into d_packed, so a caller copies only the
  * produced bytes to the host: d_packed_off[n + 1] (device) receives the start of every stream and, last, the total.

@@ -5,7 +5,7 @@ batch plans the benchmark drives.  Names and argument meaning follow the referen
 file:line it mirrors).  All compression work happens on the GPU inside libb200z.so; nothing here falls back to a CPU codec.
 """
 from ._lib import (SharpZipBaseException, StreamDecodingException, B200zUnsupported, B200zCudaError,  # noqa: F401
-                   InvalidOperationException, init, lib, SO_PATH, EXPORTS)
+                   InvalidOperationException, init, lib, SO_PATH, EXPORTS, STAGE_SEARCH, STAGE_ENCODE, STAGE_ALL)
 from .checksum import Crc32, Adler32  # noqa: F401
 from .codec import Deflater, Inflater, DeflateStrategy  # noqa: F401
 from .streams import DeflaterOutputStream, InflaterInputStream, GZipOutputStream, GZipInputStream  # noqa: F401

@@ -87,6 +87,8 @@ _SIGS = {
     "b200z_plan_get_timings": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int32, C.c_void_p, C.c_int32, C.POINTER(C.c_int32)]),
     "b200z_plan_pack": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "b200z_plan_run": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "b200z_plan_run_stages": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                        C.c_void_p]),
     "b200z_deflate_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "b200z_inflate_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "b200z_deflate_bound": (C.c_int64, [C.c_int64]),
@@ -124,6 +126,7 @@ _SIGS = {
 EXPORTS = tuple(sorted(_SIGS))
 
 HIST_NONE, HIST_DICTIONARY, HIST_CONTINUE = 0, 1, 2
+STAGE_SEARCH, STAGE_ENCODE, STAGE_ALL = 1, 2, 3
 
 
 class History(C.Structure):

@@ -45,15 +45,16 @@ class _Plan:
         keys = names.value.decode().split(";")[:cnt.value]
         return {k: float(ms[i]) for i, k in enumerate(keys)}
 
-    def run(self, d_in, d_out, d_out_len, d_status, d_check=None, d_in_used=None, stream=None):
+    def run(self, d_in, d_out, d_out_len, d_status, d_check=None, d_in_used=None, stream=None, stages=_lib.STAGE_ALL):
         """All arguments are CUDA torch tensors (uint8 blobs, int64 lengths, int32 status, uint32/int32 checks).
-        Launches on `stream` (a torch.cuda.Stream) or the current stream; does not synchronise."""
+        Launches on `stream` (a torch.cuda.Stream) or the current stream; does not synchronise.
+        stages: STAGE_SEARCH / STAGE_ENCODE run the two halves separately (b200z_plan_run_stages)."""
         import torch
         s = stream if stream is not None else torch.cuda.current_stream()
         assert d_in.is_cuda and d_out.is_cuda and d_in.numel() >= self.in_bytes and d_out.numel() >= self.out_bytes
-        rc = _lib.lib().b200z_plan_run(self._h, d_in.data_ptr(), d_out.data_ptr(), d_out_len.data_ptr(),
-                                       d_status.data_ptr(), d_check.data_ptr() if d_check is not None else None,
-                                       d_in_used.data_ptr() if d_in_used is not None else None, s.cuda_stream)
+        rc = _lib.lib().b200z_plan_run_stages(self._h, d_in.data_ptr(), d_out.data_ptr(), d_out_len.data_ptr(),
+                                              d_status.data_ptr(), d_check.data_ptr() if d_check is not None else None,
+                                              d_in_used.data_ptr() if d_in_used is not None else None, stages, s.cuda_stream)
         _lib.raise_for(rc)
 
 

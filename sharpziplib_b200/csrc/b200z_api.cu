@@ -413,12 +413,19 @@ int32_t b200z_plan_launches(const b200z_plan *p) { return p->launches; }
 
 int b200z_plan_run(b200z_plan *plan, const uint8_t *d_in, uint8_t *d_out, int64_t *d_out_len, int32_t *d_status,
                    uint32_t *d_check, int64_t *d_in_used, void *cuda_stream) {
-	if (!plan || !d_in || !d_out || !d_out_len || !d_status) {
+	return b200z_plan_run_stages(plan, d_in, d_out, d_out_len, d_status, d_check, d_in_used, B200Z_STAGE_SEARCH | B200Z_STAGE_ENCODE,
+	                             cuda_stream);
+}
+
+int b200z_plan_run_stages(b200z_plan *plan, const uint8_t *d_in, uint8_t *d_out, int64_t *d_out_len, int32_t *d_status,
+                          uint32_t *d_check, int64_t *d_in_used, int stages, void *cuda_stream) {
+	if (!plan || !d_in || !d_out || !d_out_len || !d_status || (stages & ~3) || stages == 0) {
 		set_error("bad arguments");
 		return B200Z_E_ARG;
 	}
 	cudaStream_t s = (cudaStream_t)cuda_stream;
-	if (plan->kind == 0) return deflate_plan_run(plan, d_in, d_out, d_out_len, d_status, d_check, d_in_used, s);
+	if (plan->kind == 0) return deflate_plan_run(plan, d_in, d_out, d_out_len, d_status, d_check, d_in_used, s, stages);
+	if (!(stages & B200Z_STAGE_ENCODE)) return B200Z_OK; // an inflate plan is a single stage
 	return inflate_plan_run(plan, d_in, d_out, d_out_len, d_status, d_check, d_in_used, s);
 }
 

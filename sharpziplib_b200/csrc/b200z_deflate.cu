@@ -1182,7 +1182,7 @@ int deflate_plan_build(b200z_plan *p) {
 }
 
 int deflate_plan_run(b200z_plan *p, const uint8_t *d_in, uint8_t *d_out, int64_t *d_out_len, int32_t *d_status,
-                     uint32_t *d_check, int64_t *d_out_bits, cudaStream_t s) {
+                     uint32_t *d_check, int64_t *d_out_bits, cudaStream_t s, int stages) {
 	const Arena &ws = p->ws;
 	const int n = p->n;
 	if (n == 0) return B200Z_OK;
@@ -1202,6 +1202,18 @@ int deflate_plan_run(b200z_plan *p, const uint8_t *d_in, uint8_t *d_out, int64_t
 	const int64_t *bias = ws.at<int64_t>(p->o_bias);
 	const int ck_fresh = p->check_seeded ? 0 : 1;
 
+	// stages: B200Z_STAGE_SEARCH = match finding (levels 5-9: k_links, k_match), B200Z_STAGE_ENCODE = everything else.
+	// Splitting lets a caller put other work (e.g. an inflate plan on a second stream) next to the ENCODE kernels, which
+	// leave most of an SM's shared memory free, instead of next to k_match, which takes all of it.
+	const bool do_search = (stages & B200Z_STAGE_SEARCH) != 0, do_encode = (stages & B200Z_STAGE_ENCODE) != 0;
+	const bool was_timing = p->timing;
+	if (stages != (B200Z_STAGE_SEARCH | B200Z_STAGE_ENCODE)) p->timing = false; // per-kernel times are for whole runs
+	struct TimingRestore {
+		b200z_plan *p;
+		bool v;
+		~TimingRestore() { p->timing = v; }
+	} timing_restore{p, was_timing};
+	if (lp.func != 2 && !do_encode) return B200Z_OK; // levels 0-4 have no separate search stage
 	p->ev_used = 0;
 	if (lp.func == 0) {
 		// level 0: stored blocks laid out when the plan was built
@@ -1219,13 +1231,16 @@ int deflate_plan_run(b200z_plan *p, const uint8_t *d_in, uint8_t *d_out, int64_t
 		B200Z_CUDA(cudaGetLastError());
 		return B200Z_OK;
 	}
-	p->mark(s, "memset");
-	B200Z_CUDA(cudaMemsetAsync(d_out, 0, (size_t)p->out_bytes, s));
+	if (do_encode) {
+		p->mark(s, "memset");
+		B200Z_CUDA(cudaMemsetAsync(d_out, 0, (size_t)p->out_bytes, s));
+	}
 	if (lp.func == 1) {
 		p->mark(s, "k_fast");
 		k_fast<<<n, 32, kFastSmem, s>>>(d_in, sym, in_off, in_len, nsyms, nblocks, blk_off, blk_start, blk_ptop, hist, lp, p->strategy,
 		                                p->end_mode);
 	} else {
+		if (do_search) {
 		p->mark(s, "k_links");
 		if (p->n_runs) k_links<<<p->n_runs, kLinkThreads, kLinksSmem, s>>>(d_in, link, in_off, in_len, ws.at<int2>(p->o_run_desc), hist,
 			                                                         ws.at<uint8_t>(p->o_hmask), ws.at<int64_t>(p->o_hm_off));
@@ -1233,6 +1248,11 @@ int deflate_plan_run(b200z_plan *p, const uint8_t *d_in, uint8_t *d_out, int64_t
 		if (p->n_tiles)
 			k_match<<<p->n_tiles, kMatchThreads, kTileData + 2 * 2 * kTile, s>>>(d_in, link, mt, in_off, in_len,
 			                                                                   ws.at<int2>(p->o_tile_desc), hist, bias, sym, lp);
+		}
+		if (!do_encode) {
+			B200Z_CUDA(cudaGetLastError());
+			return B200Z_OK;
+		}
 		p->mark(s, "k_parse");
 		{
 			uint32_t *sym_local = ws.at<uint32_t>(p->o_sym_local);

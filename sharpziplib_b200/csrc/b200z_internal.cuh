@@ -122,7 +122,7 @@ namespace b200z {
 // implemented in b200z_deflate.cu / b200z_inflate.cu / b200z_checksum.cu
 int deflate_plan_build(b200z_plan *p);
 int deflate_plan_run(b200z_plan *p, const uint8_t *d_in, uint8_t *d_out, int64_t *d_out_len, int32_t *d_status,
-                     uint32_t *d_check, int64_t *d_out_bits, cudaStream_t s);
+                     uint32_t *d_check, int64_t *d_out_bits, cudaStream_t s, int stages);
 int inflate_plan_build(b200z_plan *p);
 int inflate_plan_run(b200z_plan *p, const uint8_t *d_in, uint8_t *d_out, int64_t *d_out_len, int32_t *d_status,
                      uint32_t *d_check, int64_t *d_in_used, cudaStream_t s);

@@ -305,6 +305,28 @@ def test_inflater_preset_dictionary(z, oracle):
         assert (inf.Adler & 0xFFFFFFFF) == (adler & 0xFFFFFFFF)
 
 
+def test_plan_run_in_two_stages(z, oracle):
+    """b200z_plan_run_stages: SEARCH then ENCODE equals one run (levels 5-9 split, the others run whole in ENCODE)"""
+    import torch
+    bufs = [datagen.silesia_mix(c, 150000 + 999 * c, config=2).tobytes() for c in range(6)]
+    for level in (6, 2, 0):
+        plan = z.DeflatePlan([len(b) for b in bufs], level=level)
+        blob = np.zeros(plan.in_bytes, np.uint8)
+        for o, b in zip(plan.in_offsets, bufs):
+            blob[o:o + len(b)] = np.frombuffer(b, np.uint8)
+        d_in = torch.from_numpy(blob).cuda()
+        d_out = torch.zeros(plan.out_bytes, dtype=torch.uint8, device="cuda")
+        d_len = torch.zeros(plan.n, dtype=torch.int64, device="cuda")
+        d_st = torch.ones(plan.n, dtype=torch.int32, device="cuda")
+        plan.run(d_in, d_out, d_len, d_st, stages=z.STAGE_SEARCH)
+        plan.run(d_in, d_out, d_len, d_st, stages=z.STAGE_ENCODE)
+        torch.cuda.synchronize()
+        assert d_st.cpu().tolist() == [0] * plan.n
+        for i, b in enumerate(bufs):
+            o = int(plan.out_offsets[i])
+            assert d_out[o:o + int(d_len[i])].cpu().numpy().tobytes() == oracle.deflate(b, level=level), (level, i)
+
+
 def test_device_plans_with_dictionaries(z, oracle):
     """batch form: every stream of a plan with its own preset dictionary in front of its data"""
     import torch
