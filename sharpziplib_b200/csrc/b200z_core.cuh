@@ -41,7 +41,7 @@ constexpr int kMaxDist = kWSize - (kMaxMatch + kMinMatch + 1); // 32506, Deflate
 constexpr int kTooFar = 4096;                                  // DeflaterEngine.cs:51
 constexpr int kBlockSyms = 16384;                              // DeflaterHuffman.BUFSIZE, DeflaterHuffman.cs:15
 constexpr int kLiteralNum = 286, kDistNum = 30, kBitlenNum = 19;
-constexpr int kTreeScratchInts = 9 * 286;
+constexpr int kTreeScratchInts = 10 * 286;
 constexpr int kHdrWords = 160; // dynamic header: <= 17 + 57 + 316 * 14 bits = 4498 bits < 160 * 32
 constexpr uint32_t kSlideFirst = 65273; // first input offset whose window index reaches 65274 (trap T8)
 
@@ -577,7 +577,7 @@ B200Z_HD uint32_t static_dcode(int i) { return bit_reverse16((uint32_t)i << 11);
 // Tree.BuildTree + BuildLength (DeflaterHuffman.cs:196-329, :475-579), operation for operation.
 //   freqs[numSymbols] in; length[numSymbols], bl_counts[maxLength], numCodes out.
 //   scratch: heap[numSymbols] + childs[4*L-2] + values[2*L-1] + lengths[2*L-1] ints with L <= numSymbols
-//            ->  9 * numSymbols ints is enough (kTreeScratchInts for the 286-symbol literal tree).
+//            ->  9 * numSymbols ints, plus numSymbols for hval[] below (kTreeScratchInts for the 286-symbol literal tree).
 B200Z_HDN int build_tree(const int *freqs, int numSymbols, int minNumCodes, int maxLength, uint8_t *length,
                          int *bl_counts, int *scratch) {
 	int *heap = scratch;
@@ -605,45 +605,75 @@ B200Z_HDN int build_tree(const int *freqs, int numSymbols, int minNumCodes, int 
 	int *childs = scratch + numSymbols;            // 4*heapLen - 2
 	int *values = childs + (4 * numLeafs - 2);     // 2*heapLen - 1
 	int *lengths = values + (2 * numLeafs - 1);    // 2*heapLen - 1
+	// hval[i] caches values[heap[i]] (always kept equal), so that a heap comparison is one load instead of two dependent
+	// ones -- the tree is built by a single thread and its time is the sum of these load latencies
+	int *hval = scratch + 9 * numSymbols;
 	int numNodes = numLeafs;
 	for (int i = 0; i < heapLen; i++) {
 		int node = heap[i];
 		childs[2 * i] = node;
 		childs[2 * i + 1] = -1;
-		values[i] = freqs[node] << 8;
+		values[i] = hval[i] = freqs[node] << 8;
 		heap[i] = i;
 	}
 	do {
 		int first = heap[0];
+		int firstVal = hval[0];
 		int last = heap[--heapLen];
+		int lastVal = hval[heapLen];
 		int ppos = 0;
 		int path = 1;
 		while (path < heapLen) {
-			if (path + 1 < heapLen && values[heap[path]] > values[heap[path + 1]]) path++;
-			heap[ppos] = heap[path];
+			// both children are fetched before the comparison decides
+			const int v0 = hval[path], h0 = heap[path];
+			int v1 = 0, h1 = 0;
+			if (path + 1 < heapLen) {
+				v1 = hval[path + 1];
+				h1 = heap[path + 1];
+			}
+			const bool right = path + 1 < heapLen && v0 > v1;
+			if (right) path++;
+			heap[ppos] = right ? h1 : h0;
+			hval[ppos] = right ? v1 : v0;
 			ppos = path;
 			path = path * 2 + 1;
 		}
-		int lastVal = values[last];
-		while ((path = ppos) > 0 && values[heap[ppos = (path - 1) / 2]] > lastVal) heap[path] = heap[ppos];
+		while ((path = ppos) > 0 && hval[ppos = (path - 1) / 2] > lastVal) {
+			heap[path] = heap[ppos];
+			hval[path] = hval[ppos];
+		}
 		heap[path] = last;
+		hval[path] = lastVal;
 		int second = heap[0];
+		int secondVal = hval[0];
 		last = numNodes++;
 		childs[2 * last] = first;
 		childs[2 * last + 1] = second;
-		int d1 = values[first] & 0xff, d2 = values[second] & 0xff;
+		int d1 = firstVal & 0xff, d2 = secondVal & 0xff;
 		int mindepth = d1 < d2 ? d1 : d2;
-		values[last] = lastVal = values[first] + values[second] - mindepth + 1;
+		values[last] = lastVal = firstVal + secondVal - mindepth + 1;
 		ppos = 0;
 		path = 1;
 		while (path < heapLen) {
-			if (path + 1 < heapLen && values[heap[path]] > values[heap[path + 1]]) path++;
-			heap[ppos] = heap[path];
+			const int v0 = hval[path], h0 = heap[path];
+			int v1 = 0, h1 = 0;
+			if (path + 1 < heapLen) {
+				v1 = hval[path + 1];
+				h1 = heap[path + 1];
+			}
+			const bool right = path + 1 < heapLen && v0 > v1;
+			if (right) path++;
+			heap[ppos] = right ? h1 : h0;
+			hval[ppos] = right ? v1 : v0;
 			ppos = path;
 			path = ppos * 2 + 1;
 		}
-		while ((path = ppos) > 0 && values[heap[ppos = (path - 1) / 2]] > lastVal) heap[path] = heap[ppos];
+		while ((path = ppos) > 0 && hval[ppos = (path - 1) / 2] > lastVal) {
+			heap[path] = heap[ppos];
+			hval[path] = hval[ppos];
+		}
 		heap[path] = last;
+		hval[path] = lastVal;
 	} while (heapLen > 1);
 
 	// BuildLength (:475-579); childs.Length / 2 == numNodes == 2 * numLeafs - 1

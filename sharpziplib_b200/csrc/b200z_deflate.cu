@@ -783,7 +783,7 @@ __global__ void __launch_bounds__(kPlanThreads)
 	__shared__ int s_dist[kDistNum];
 	__shared__ int s_extra;
 	__shared__ int s_scratch[kTreeScratchInts];
-	__shared__ int s_scratch2[9 * kDistNum];
+	__shared__ int s_scratch2[10 * kDistNum];
 	__shared__ int s_lit_blc[15], s_dist_blc[15], s_nc[2];
 	__shared__ BlockTables s_tab;
 	const int g = blockIdx.x;

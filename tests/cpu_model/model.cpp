@@ -233,7 +233,7 @@ static int model_run(const uint8_t *data, uint32_t n, uint32_t H, uint32_t abs_b
 emit_blocks:
 	Writer W;
 	uint64_t bitpos = bit_base;
-	std::vector<int> scratch(9 * 286 + 64);
+	std::vector<int> scratch(kTreeScratchInts + 64);
 	for (size_t b = 0; b < nblocks; b++) {
 		size_t s0 = b * (size_t)kBlockSyms;
 		size_t s1 = s0 + kBlockSyms < syms.size() ? s0 + kBlockSyms : syms.size();
