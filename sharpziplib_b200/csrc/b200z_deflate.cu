@@ -269,6 +269,7 @@ __global__ void __launch_bounds__(kMatchThreads, 1)
 			const uint8_t *sp = s_data + is;
 			uint32_t m = kMinMatch - 1, bd = 0, dist = d, cnt = 0;
 			bool haveB = false;
+			uint32_t stop = budgetB ? budgetB : chain;
 			const uint32_t s0 = sp[0], s1 = sp[1];
 			uint32_t scan_end1 = s1, scan_end = sp[2];
 			// bytes 2..9 of the scan string stay in registers: most extensions end inside them
@@ -323,11 +324,12 @@ __global__ void __launch_bounds__(kMatchThreads, 1)
 						scan_end = sp[m];
 					}
 				}
-				if (cnt == budgetB) {
+				if (cnt == stop) { // one test per candidate: first the quarter budget (B's snapshot), then the full one
+					if (stop == chain) break;
 					resB = m >= (uint32_t)kMinMatch ? pack_match(m, bd) : 0u;
 					haveB = true;
+					stop = chain;
 				}
-				if (cnt == chain) break;
 				const uint32_t l2 = s_link[is - dist];
 				if (l2 == 0) break;
 				dist += l2;
@@ -801,15 +803,26 @@ __global__ void __launch_bounds__(kPlanThreads)
 	if (threadIdx.x == 0) s_extra = 0;
 	__syncthreads();
 	int extra = 0;
-	for (uint32_t i = s0 + threadIdx.x; i < s1; i += blockDim.x) {
-		const uint32_t s = sp[i];
-		if (sym_dist(s) == 0) {
-			atomicAdd(&s_lit[s & 0xFF], 1);
-		} else {
-			const int lc = lcode((int)(s & 0xFF)), dc = dcode((int)sym_dist(s) - 1);
-			atomicAdd(&s_lit[lc], 1);
-			atomicAdd(&s_dist[dc], 1);
-			extra += tally_extra_bits(lc, dc);
+	for (uint32_t i0 = s0 + threadIdx.x; i0 < s1; i0 += 8 * blockDim.x) {
+		// eight independent loads in flight per thread (ncu: the one-load-per-trip loop sat on long_scoreboard)
+		uint32_t sv[8];
+#pragma unroll
+		for (int k = 0; k < 8; k++) {
+			const uint32_t i = i0 + (uint32_t)k * blockDim.x;
+			sv[k] = i < s1 ? __ldg(sp + i) : 0xFFFFFFFFu;
+		}
+#pragma unroll
+		for (int k = 0; k < 8; k++) {
+			const uint32_t s = sv[k];
+			if (s == 0xFFFFFFFFu) continue; // (not a symbol: distances stop at 32506)
+			if (sym_dist(s) == 0) {
+				atomicAdd(&s_lit[s & 0xFF], 1);
+			} else {
+				const int lc = lcode((int)(s & 0xFF)), dc = dcode((int)sym_dist(s) - 1);
+				atomicAdd(&s_lit[lc], 1);
+				atomicAdd(&s_dist[dc], 1);
+				extra += tally_extra_bits(lc, dc);
+			}
 		}
 	}
 	for (int o = 16; o > 0; o >>= 1) extra += __shfl_down_sync(0xffffffffu, extra, o);
