@@ -184,9 +184,9 @@ __device__ __forceinline__ uint32_t decode_sym(BitReader &br, const uint32_t *ta
 constexpr int kSubBits = 512;                 // input bits per lane per round
 constexpr int kRoundWords = 32 * kSubBits / 32;  // 512 words
 constexpr int kInWords = kRoundWords + 8;        // + slack for the last symbol's overshoot
-constexpr int kLaneOutCap = 768;                 // output bytes a lane may produce per round
-constexpr int kRing = 65536;                     // output ring: >= 32 KiB of history + one round (32 x kLaneOutCap)
-constexpr int kMList = 64;                       // back-references a lane may record per round
+constexpr int kLaneOutCap = 512;                 // output bytes a lane may produce per round
+constexpr int kRing = 65536;                     // output ring: 32 KiB of history + the two rounds the consumer warps hold (2 x 32 x kLaneOutCap)
+constexpr int kMList = 32;                       // back-references a lane may record per round
 
 enum { F_EOB = 1, F_ERR = 2, F_OVERRUN = 4, F_DEAD = 8 };
 
@@ -296,18 +296,21 @@ struct RoundInfo {
 struct __align__(16) InfBlockShared {
 	InfShared sh[2];          // code tables, double buffered: A may build the next block's while B still decodes
 	uint32_t in[2][kInWords]; // staged input words, double buffered
-	RoundInfo ri[2];
+	RoundInfo ri[3];          // round r lives in ri[r % 3]: written by A, read by B1 one iteration later and by B2 two later
+	uint32_t rs_out[3], rs_nm[3]; // per round, from B1 to B2: bytes produced, back-references recorded
 	__align__(16) uint8_t ring[kRing]; // ring[pos & 65535] = output byte `pos`; doubles as OutputWindow (Streams/OutputWindow.cs:15-23)
-	__align__(16) uint2 mlist[32 * kMList]; // flat, in stream order: x = output position (low 32 bits), y = len | dist << 16
+	__align__(16) uint2 mlist[2][32 * kMList]; // flat, in stream order: x = output position (low 32 bits), y = len | dist << 16
 	int a_done;
 };
 constexpr int kInfSmem2 = (int)sizeof(InfBlockShared);
 
-// Two warps per stream.  Warp A (producer): block headers, code tables, and the counted decode passes of round t
-// (speculative lanes, exit -> entry hand-off until stable).  Warp B (consumer): final decode pass of round t-1 (literals
-// and back-reference records), the copies, and the flush.  One __syncthreads per round keeps them one round apart; a
-// single warp per stream is latency bound (ncu: IPC 0.16), so the two halves overlap almost for free.
-__global__ void __launch_bounds__(64)
+// Three warps per stream, one round apart each.  Warp A (producer): block headers, code tables, and the counted decode
+// passes of round t (speculative lanes, exit -> entry hand-off until stable).  Warp B1: final decode pass of round t-1
+// (literals into the ring, back-reference records into a list).  Warp B2: the copies of round t-2 and its flush.  One
+// __syncthreads per round keeps them in step; a single warp per stream is latency bound (ncu: IPC 0.16), and with two
+// warps the consumer (decode + copies + flush) was the longer half, so the stages overlap almost for free.
+constexpr int kInfThreads = 96;
+__global__ void __launch_bounds__(kInfThreads)
     k_inflate(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, const int64_t *__restrict__ in_off,
               const int64_t *__restrict__ in_len, const int64_t *__restrict__ out_off, const int64_t *__restrict__ out_cap,
               int nstreams, int64_t *__restrict__ out_len, int64_t *__restrict__ in_used, int32_t *__restrict__ status,
@@ -315,7 +318,7 @@ __global__ void __launch_bounds__(64)
 	extern __shared__ __align__(16) uint8_t smem_raw[];
 	InfBlockShared &S = *reinterpret_cast<InfBlockShared *>(smem_raw);
 	const int lane = threadIdx.x & 31;
-	const bool isA = threadIdx.x < 32;
+	const bool isA = threadIdx.x < 32, isB1 = threadIdx.x >= 32 && threadIdx.x < 64;
 	const int stream = blockIdx.x;
 	if (stream >= nstreams) return;
 	uint8_t *dst = out + out_off[stream];
@@ -332,10 +335,11 @@ __global__ void __launch_bounds__(64)
 	br.consumed = 0;
 	const uint64_t total_bits = 8ull * br.nbytes;
 
-	for (int i = threadIdx.x; i < kRing / 16; i += 64) reinterpret_cast<uint4 *>(S.ring)[i] = make_uint4(0, 0, 0, 0); // fresh window = zeros
+	for (int i = threadIdx.x; i < kRing / 16; i += kInfThreads) reinterpret_cast<uint4 *>(S.ring)[i] = make_uint4(0, 0, 0, 0); // fresh window = zeros
 	if (threadIdx.x == 0) {
 		S.ri[0].valid = 0;
 		S.ri[1].valid = 0;
+		S.ri[2].valid = 0;
 		S.a_done = 0;
 	}
 	__syncthreads();
@@ -344,7 +348,7 @@ __global__ void __launch_bounds__(64)
 		// bytes lie directly in front of the compressed data and become the window contents behind output position 0
 		const uint32_t D = dict_len[stream];
 		const uint8_t *dsrc = in + in_off[stream] - D;
-		for (uint32_t i = threadIdx.x; i < D; i += 64) S.ring[(uint32_t)kRing - D + i] = dsrc[i];
+		for (uint32_t i = threadIdx.x; i < D; i += kInfThreads) S.ring[(uint32_t)kRing - D + i] = dsrc[i];
 		if (D) __syncthreads();
 	}
 
@@ -357,12 +361,13 @@ __global__ void __launch_bounds__(64)
 	int tab = 0, static_in = -1; // static_in: which table buffer currently holds the static tables (-1 none)
 
 	for (uint32_t t = 0;; t++) {
-		const int cur = (int)(t & 1), prv = cur ^ 1;
+		const int cur = (int)(t & 1), prv = cur ^ 1;                                   // input staging / match list buffers
+		const int r0i = (int)(t % 3), r1i = (int)((t + 2) % 3), r2i = (int)((t + 1) % 3); // RoundInfo of rounds t, t-1, t-2
 		if (isA) {
 			// ============================ producer ============================
 			int valid = 0;
 			if (!a_done) {
-				const bool b_busy = S.ri[prv].valid != 0; // B is consuming the previous round during this iteration
+				const bool b_busy = S.ri[r1i].valid != 0 || S.ri[r2i].valid != 0; // B1 / B2 still hold earlier rounds
 				if (pending_stored) {
 					if (!b_busy) {
 						// ---- stored block: OutputWindow.CopyStored (:100-122); B is idle, so the ring and dst are ours
@@ -566,7 +571,7 @@ __global__ void __launch_bounds__(64)
 							st = B200Z_E_NOMEM;
 							a_done = true;
 						} else {
-							RoundInfo &ri = S.ri[cur];
+							RoundInfo &ri = S.ri[r0i];
 							ri.entry[lane] = entry;
 							ri.obytes[lane] = obytes;
 							ri.nmatch[lane] = nmatch;
@@ -588,12 +593,12 @@ __global__ void __launch_bounds__(64)
 				}
 			}
 			if (lane == 0) {
-				S.ri[cur].valid = valid;
+				S.ri[r0i].valid = valid;
 				S.a_done = a_done ? 1 : 0;
 			}
-		} else {
-			// ============================ consumer ============================
-			const RoundInfo &ri = S.ri[prv];
+		} else if (isB1) {
+			// ============================ consumer, first half: final decode pass of round t-1 ============================
+			const RoundInfo &ri = S.ri[r1i];
 			if (ri.valid) {
 				const InfShared &sh = S.sh[ri.tab];
 				const uint32_t *words = S.in[prv];
@@ -621,13 +626,25 @@ __global__ void __launch_bounds__(64)
 					sp.fl = 0;
 					sp.det = 0;
 					sp.pos = entry;
-					uint2 *ml = S.mlist + (mincl - nmatch);
+					uint2 *ml = S.mlist[prv] + (mincl - nmatch);
 					while (__any_sync(0xffffffffu, act)) {
 						if (act) act = span_step<true>(sh, words, sp, lim, end_rel, S.ring, obase, ml);
 						__syncwarp();
 					}
 				}
 				__syncwarp();
+				if (lane == 0) {
+					S.rs_out[r1i] = round_out;
+					S.rs_nm[r1i] = total_m;
+				}
+			}
+		} else {
+			// ============================ consumer, second half: copies and flush of round t-2 ============================
+			const RoundInfo &ri = S.ri[r2i];
+			if (ri.valid) {
+				const uint64_t ropos = ri.opos;
+				const uint32_t round_out = S.rs_out[r2i], total_m = S.rs_nm[r2i];
+				const uint2 *mlist = S.mlist[cur]; // round t-2 has the parity of t
 				// ---- back-references in stream order (OutputWindow.Repeat :63-92) ----------------------------------
 				// Four matches per step, each copied by a group of 8 lanes, when none of them reads bytes another match
 				// of the same step writes; otherwise the step's matches are copied one after another by the whole warp.
@@ -638,7 +655,7 @@ __global__ void __launch_bounds__(64)
 					for (uint32_t k0 = 0; k0 < total_m; k0 += 4) {
 						const uint32_t mi = k0 + (uint32_t)grp;
 						const bool have = mi < total_m;
-						const uint2 m = have ? S.mlist[mi] : make_uint2(0u, 0u);
+						const uint2 m = have ? mlist[mi] : make_uint2(0u, 0u);
 						const uint32_t mo = m.x, mlen = m.y & 0xFFFFu, mdist = m.y >> 16;
 						const uint32_t step_lo = __shfl_sync(0xffffffffu, mo, 0); // first destination byte of this step
 						// a later match of the step depends on the step if its source reaches step_lo or beyond
@@ -692,7 +709,7 @@ __global__ void __launch_bounds__(64)
 			}
 		}
 		__syncthreads();
-		if (S.a_done && !S.ri[cur].valid) break; // A has nothing more and B has consumed every round
+		if (S.a_done && !S.ri[r0i].valid && !S.ri[r1i].valid) break; // A has nothing more, B1 and B2 nothing left to take over
 	}
 	if (threadIdx.x == 0) {
 		status[stream] = st | (detail << 8);
@@ -762,7 +779,7 @@ int inflate_plan_run(b200z_plan *p, const uint8_t *d_in, uint8_t *d_out, int64_t
 	(void)d_check;
 	p->ev_used = 0;
 	p->mark(s, "k_inflate");
-	k_inflate<<<n, 64, kInfSmem2, s>>>(
+	k_inflate<<<n, kInfThreads, kInfSmem2, s>>>(
 	    d_in, d_out, ws.at<int64_t>(p->o_in_off), ws.at<int64_t>(p->o_in_len), ws.at<int64_t>(p->o_out_off),
 	    ws.at<int64_t>(p->o_out_cap), n, d_out_len, d_in_used, d_status, ws.at<uint32_t>(p->o_hist));
 	p->mark(s, "end");
