@@ -135,6 +135,17 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def captured_traffic(kernel, small):
+    """dram bytes (read + write) of one launch of `kernel` on this workload, from the committed ncu --set full capture"""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if small or not os.path.exists(p):
+        return None, None
+    j = json.load(open(p))
+    if j.get("kernel") != kernel:
+        return None, None
+    return int(j["dram_bytes_per_launch"]), j.get("source")
+
+
 class CpuSample:
     """the oracle (C++ restatement of the reference) on a bounded sample of the same workload; only the C calls are timed"""
 
@@ -437,6 +448,7 @@ def main():
     peak, peak_src = peaks()
     alg_bytes = (C_inf + U_inf) if dom == "k_inflate" else (U_def + C_def)
     achieved = alg_bytes / (acc[dom] / 1e3) / 1e9
+    traffic, traffic_src = captured_traffic(dom, args.small)
 
     # ---- end to end from pinned host buffers ------------------------------------------------------------------
     for _ in range(3):
@@ -477,7 +489,7 @@ def main():
             "inflate_gbs": U_inf / (t_inf / 1e3) / 1e9 if t_inf else None,
             "kernels_ms": acc,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src,
+                         "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                          "algorithmic_bytes": alg_bytes},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_val, "unit": "GB/s", "ms_per_step": ms_e2e,
