@@ -576,3 +576,36 @@ def test_gzip_streams(z):
     assert gzip.decompress(blob) == d
     assert z.GZipInputStream(io.BytesIO(blob)).read() == d
     assert z.GZipInputStream(io.BytesIO(blob + blob)).read() == d + d  # multi-member
+
+
+# ---- randomised shapes ------------------------------------------------------------------------------------
+def test_fuzz_deflate_inflate_against_oracle(z, oracle):
+    """seeded random batches: ragged sizes around every block / window / round boundary, all levels and strategies, the three
+    wrappers; every stream must equal the oracle's bytes and must come back through the device inflater unchanged"""
+    import random
+    rnd = random.Random(20240917)
+    edges = [0, 1, 2, 3, 4, 31, 32, 33, 257, 258, 259, 1023, 1024, 1025, 16383, 16384, 16385, 32505, 32506, 32507, 32767, 32768,
+             32769, 65273, 65274, 65535, 65536, 65537, 98041, 98042, 131071, 131072, 200000]
+    for trial in range(6):
+        n = rnd.randrange(3, 12)
+        bufs = []
+        for _ in range(n):
+            size = rnd.choice(edges) if rnd.random() < 0.6 else rnd.randrange(0, 150000)
+            cls = rnd.randrange(8)
+            b = datagen.silesia_mix(cls, max(size, 1), config=rnd.randrange(1, 9)).tobytes()[:size]
+            if rnd.random() < 0.2 and size:
+                b = bytes([b[0]]) * size            # a single-byte run: nice-length exits, maximal matches
+            bufs.append(b)
+        level = rnd.choice([0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 6, 9])
+        strategy = rnd.choice([0, 0, 1, 2])
+        wrap = rnd.choice([0, 1])
+        end_mode = rnd.choice([0, 0, 1])
+        outs, _ = z.deflate_batch(bufs, level=level, strategy=strategy, wrap=wrap, end_mode=end_mode)
+        want = [oracle.deflate(b, level=level, strategy=strategy, nowrap=(wrap == 0), pattern=(1 if end_mode else 0)) for b in bufs]
+        for i, (g, w) in enumerate(zip(outs, want)):
+            assert g == w, (trial, i, len(bufs[i]), level, strategy, wrap, end_mode)
+        raw = [o[2:-4] if wrap else o for o in outs]
+        back, used, st = z.inflate_batch(raw, [len(b) + 16 for b in bufs])
+        assert [int(x) for x in st] == [0] * n
+        for i, b in enumerate(bufs):
+            assert back[i] == b and int(used[i]) == len(raw[i]), (trial, i)
