@@ -184,6 +184,10 @@ __device__ __forceinline__ uint32_t decode_sym(BitReader &br, const uint32_t *ta
 constexpr int kSubBits = 512;                 // input bits per lane per round
 constexpr int kRoundWords = 32 * kSubBits / 32;  // 512 words
 constexpr int kInWords = kRoundWords + 8;        // + slack for the last symbol's overshoot
+// Lane l reads around word 16 l: laid out linearly, all 32 lanes would hit two shared-memory banks (16-way conflicts on
+// every peek).  One pad word per 16 moves lane l to 17 l.
+__device__ __forceinline__ uint32_t in_slot(uint32_t i) { return i + (i >> 4); }
+constexpr int kInSlots = kInWords + kInWords / 16 + 1;
 constexpr int kLaneOutCap = 512;                 // output bytes a lane may produce per round
 constexpr int kRing = 65536;                     // output ring: 32 KiB of history + the two rounds the consumer warps hold (2 x 32 x kLaneOutCap)
 constexpr int kMList = 32;                       // back-references a lane may record per round
@@ -194,7 +198,7 @@ enum { F_EOB = 1, F_ERR = 2, F_OVERRUN = 4, F_DEAD = 8 };
 // are two words and a funnel shift away.  The decode state of a lane is just its bit position.
 __device__ __forceinline__ uint32_t peek32(const uint32_t *w, uint32_t pos) {
 	const uint32_t i = pos >> 5;
-	return __funnelshift_r(w[i], w[i + 1], pos & 31u); // i + 1 < kInWords is guaranteed by the staging slack
+	return __funnelshift_r(w[in_slot(i)], w[in_slot(i + 1)], pos & 31u); // i + 1 < kInWords is guaranteed by the staging slack
 }
 
 // decodes one symbol of a tree at `v` (the next 32 stream bits); returns the entry and the code length in nb
@@ -295,7 +299,7 @@ struct RoundInfo {
 
 struct __align__(16) InfBlockShared {
 	InfShared sh[2];          // code tables, double buffered: A may build the next block's while B still decodes
-	uint32_t in[2][kInWords]; // staged input words, double buffered
+	uint32_t in[2][kInSlots]; // staged input words (in_slot layout), double buffered
 	RoundInfo ri[3];          // round r lives in ri[r % 3]: written by A, read by B1 one iteration later and by B2 two later
 	uint32_t rs_out[3], rs_nm[3]; // per round, from B1 to B2: bytes produced, back-references recorded
 	__align__(16) uint8_t ring[kRing]; // ring[pos & 65535] = output byte `pos`; doubles as OutputWindow (Streams/OutputWindow.cs:15-23)
@@ -516,7 +520,7 @@ __global__ void __launch_bounds__(kInfThreads)
 								v = __ldg(gwords + wi);
 								if (wi == br.nwords - 1 && (br.nbytes & 3)) v &= (1u << (8 * (br.nbytes & 3))) - 1u;
 							}
-							words[i] = v;
+							words[in_slot((uint32_t)i)] = v;
 						}
 						__syncwarp();
 						const uint32_t r0 = (uint32_t)(bitpos & 31);
