@@ -670,7 +670,10 @@ __global__ void __launch_bounds__(32)
     k_fast(const uint8_t *__restrict__ in, uint32_t *__restrict__ sym, const int64_t *__restrict__ in_off,
            const int64_t *__restrict__ in_len, uint32_t *__restrict__ nsyms, uint32_t *__restrict__ nblocks,
            const uint32_t *__restrict__ blk_off, uint32_t *__restrict__ blk_start, uint32_t *__restrict__ blk_ptop,
-           const uint32_t *__restrict__ hist, LevelParams lp, int strategy, int end_mode) {
+           const uint32_t *__restrict__ hist, LevelParams lp, int strategy, int end_mode, int prev_entries) {
+	// prev[] is indexed by window position & 32767; when no stream of the batch is longer than prev_entries - 2 bytes the
+	// positions never reach prev_entries, so the table (and the CTA's shared-memory footprint) can be that much smaller
+	// and three CTAs share an SM instead of one.
 	extern __shared__ __align__(16) uint8_t fsm[];
 	uint16_t *head = reinterpret_cast<uint16_t *>(fsm);
 	uint16_t *prev = head + 32768;
@@ -681,7 +684,7 @@ __global__ void __launch_bounds__(32)
 	uint32_t *sout = sym + off;
 	uint32_t *bstart = blk_start + blk_off[stream];
 	uint32_t *bptop = blk_ptop + blk_off[stream];
-	for (int i = lane; i < 32768; i += 32) reinterpret_cast<uint32_t *>(fsm)[i] = 0;
+	for (int i = lane; i < (32768 + prev_entries) / 2; i += 32) reinterpret_cast<uint32_t *>(fsm)[i] = 0;
 	__syncwarp();
 	FastEngine e;
 	fe_init(e, in + off, n, head, prev);
@@ -1039,6 +1042,13 @@ int deflate_plan_build(b200z_plan *p) {
 		if (need > (int64_t)chunk) chunk = (uint32_t)need;
 	}
 	p->parse_chunk = chunk;
+	{
+		// levels 1-4: size of k_fast's prev[] table (see there)
+		int64_t need = maxlen + 2;
+		int pe = 32768;
+		if (need <= 32768) pe = (int)((need + 255) / 256 * 256);
+		p->fast_prev_entries = pe;
+	}
 	std::vector<uint32_t> blk_off(n + 1);
 	std::vector<int32_t> blk_desc;
 	uint32_t nblk = 0;
@@ -1250,8 +1260,8 @@ int deflate_plan_run(b200z_plan *p, const uint8_t *d_in, uint8_t *d_out, int64_t
 	}
 	if (lp.func == 1) {
 		p->mark(s, "k_fast");
-		k_fast<<<n, 32, kFastSmem, s>>>(d_in, sym, in_off, in_len, nsyms, nblocks, blk_off, blk_start, blk_ptop, hist, lp, p->strategy,
-		                                p->end_mode);
+		k_fast<<<n, 32, 65536 + 2 * p->fast_prev_entries, s>>>(d_in, sym, in_off, in_len, nsyms, nblocks, blk_off, blk_start, blk_ptop,
+		                                                       hist, lp, p->strategy, p->end_mode, p->fast_prev_entries);
 	} else {
 		if (do_search) {
 		p->mark(s, "k_links");
