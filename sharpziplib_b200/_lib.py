@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.path.join(_HERE, "libb200z.so")
 
 OK, E_ARG, E_STATE, E_DATA, E_INTERNAL, E_CUDA, E_UNSUPPORTED, E_NOMEM, E_NEED_INPUT = range(9)
-WRAP_RAW, WRAP_ZLIB, WRAP_GZIP = 0, 1, 2
+WRAP_RAW, WRAP_ZLIB, WRAP_GZIP, WRAP_RAW_CRC32 = 0, 1, 2, 3
 END_FINISH, END_FLUSH_FINISH, END_FLUSH = 0, 1, 2
 
 

@@ -125,8 +125,11 @@ def deflate_batch(buffers, level=6, strategy=0, wrap=_lib.WRAP_RAW, end_mode=_li
     return [outs[i][:out_len[i]].tobytes() for i in range(n)], check
 
 
-def inflate_batch(buffers, out_caps, raise_on_error=True):
-    """Host raw-deflate buffers in, (outputs, in_used, status) out.  status[i] = code | detail << 8."""
+def inflate_batch(buffers, out_caps, raise_on_error=True, wrap=_lib.WRAP_RAW, return_checks=False):
+    """Host buffers in, (outputs, in_used, status) out.  status[i] = code | detail << 8.  wrap: WRAP_RAW (raw deflate),
+    WRAP_ZLIB / WRAP_GZIP (header parsed, output checksum compared with the trailer on the device; gzip: one member,
+    in_used says where the next one starts), WRAP_RAW_CRC32 (raw deflate, CRC-32 of the output reported: zip entries).
+    return_checks: also return the checksums of the outputs."""
     n = len(buffers)
     ins = [np.ascontiguousarray(np.frombuffer(b, dtype=np.uint8)) for b in buffers]
     lens = np.array([a.size for a in ins], dtype=np.int64)
@@ -136,11 +139,14 @@ def inflate_batch(buffers, out_caps, raise_on_error=True):
     in_used = np.zeros(n, dtype=np.int64)
     check = np.zeros(n, dtype=np.uint32)
     status = np.zeros(n, dtype=np.int32)
-    rc = _lib.lib().b200z_inflate_batch(_ptr_array(ins), lens.ctypes.data, n, _lib.WRAP_RAW, _ptr_array(outs),
+    rc = _lib.lib().b200z_inflate_batch(_ptr_array(ins), lens.ctypes.data, n, wrap, _ptr_array(outs),
                                         caps.ctypes.data, out_len.ctypes.data, in_used.ctypes.data, check.ctypes.data,
                                         status.ctypes.data)
     if raise_on_error:
         _lib.raise_for(rc)
     elif rc in (_lib.E_CUDA, _lib.E_ARG):
         _lib.raise_for(rc)
-    return [outs[i][:out_len[i]].tobytes() for i in range(n)], in_used, status
+    res = [outs[i][:out_len[i]].tobytes() for i in range(n)]
+    if return_checks:
+        return res, in_used, status, check
+    return res, in_used, status

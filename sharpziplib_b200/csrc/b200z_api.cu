@@ -332,7 +332,7 @@ int b200z_inflate_plan_create(int32_t n, const int64_t *comp_len, const int64_t 
 
 int b200z_inflate_plan_create_ex(int32_t n, const int64_t *comp_len, const int64_t *out_cap, int wrap, const int64_t *dict_len,
                                  b200z_plan **plan) {
-	if (!plan || n < 0 || (n > 0 && (!comp_len || !out_cap)) || wrap < 0 || wrap > 2) {
+	if (!plan || n < 0 || (n > 0 && (!comp_len || !out_cap)) || wrap < 0 || wrap > B200Z_WRAP_RAW_CRC32) {
 		set_error("bad arguments");
 		return B200Z_E_ARG;
 	}
@@ -622,15 +622,13 @@ int b200z_deflate_batch(const uint8_t *const *in, const int64_t *in_len, int32_t
 	return first;
 }
 
+static const char *inflate_detail_msg(int detail);
+
 int b200z_inflate_batch(const uint8_t *const *in, const int64_t *in_len, int32_t n, int wrap, uint8_t *const *out,
                         const int64_t *out_cap, int64_t *out_len, int64_t *in_used, uint32_t *check, int32_t *status) {
 	if (n < 0 || (n > 0 && (!in || !in_len || !out || !out_cap || !out_len))) {
 		set_error("bad arguments");
 		return B200Z_E_ARG;
-	}
-	if (wrap != B200Z_WRAP_RAW) {
-		set_error("zlib/gzip framing is parsed by the host stream layer (Inflater handle / GZipInputStream shim)");
-		return B200Z_E_UNSUPPORTED;
 	}
 	b200z_plan *plan = nullptr;
 	int rc = b200z_inflate_plan_create(n, in_len, out_cap, wrap, &plan);
@@ -639,7 +637,7 @@ int b200z_inflate_batch(const uint8_t *const *in, const int64_t *in_len, int32_t
 	DevBuf din, dout, dmeta;
 	HostRunResult r;
 	rc = run_plan_host(plan, in, hin, hout, din, dout, dmeta, r, false);
-	int first = B200Z_OK;
+	int first = B200Z_OK, first_detail = 0;
 	if (!rc) {
 		for (int i = 0; i < n; i++) {
 			const int st = r.status[i];
@@ -647,13 +645,17 @@ int b200z_inflate_batch(const uint8_t *const *in, const int64_t *in_len, int32_t
 			out_len[i] = r.out_len[i];
 			if (in_used) in_used[i] = r.in_used[i];
 			if (status) status[i] = st;
-			if (check) check[i] = 0;
-			if ((st & 0xFF) != B200Z_OK && first == B200Z_OK) first = st & 0xFF;
+			if (check) check[i] = wrap != B200Z_WRAP_RAW ? r.check[i] : 0u;
+			if ((st & 0xFF) != B200Z_OK && first == B200Z_OK) {
+				first = st & 0xFF;
+				first_detail = (st >> 8) & 0xFF;
+			}
 		}
 	}
 	b200z_plan_destroy(plan);
 	if (rc) return rc;
-	if (first != B200Z_OK) set_error("stream failed with status %d", first);
+	if (first == B200Z_E_DATA) set_error("%s", inflate_detail_msg(first_detail)); // the reference's exception message
+	else if (first != B200Z_OK) set_error("stream failed with status %d", first);
 	return first;
 }
 
@@ -989,6 +991,17 @@ static const char *inflate_detail_msg(int detail) {
 	case 8: return "Cannot repeat code lengths past total number of data code lengths";
 	case 9: return "Inflater dynamic header end-of-block code missing";
 	case 10: return "Code lengths oversubscribed";
+	case 11: return "Adler chksum doesn't match";
+	case 12: return "GZIP crc sum mismatch";
+	case 13: return "Number of bytes mismatch in footer";
+	case 14: return "Error GZIP header, first magic byte doesn't match";
+	case 15: return "Error GZIP header,  second magic byte doesn't match";
+	case 16: return "Error GZIP header, data not in deflate format";
+	case 17: return "Reserved flag bits in GZIP header != 0";
+	case 18: return "Header CRC value mismatch";
+	case 19: return "Header checksum illegal";
+	case 20: return "Compression Method unknown";
+	case 22: return "Needs a preset dictionary";
 	default: return "corrupt deflate data";
 	}
 }

@@ -32,12 +32,13 @@ int checksum_init_tables() {
 }
 
 // tile list for n streams; mult is filled per kind by the caller through fill_mults()
-int checksum_tiles(const int64_t *len, int32_t n, std::vector<CkTile> &tiles, int kind) {
+int checksum_tiles(const int64_t *len, int32_t n, std::vector<CkTile> &tiles, int kind, bool dynamic) {
 	tiles.clear();
 	for (int32_t i = 0; i < n; i++) {
 		const int64_t L = len[i];
 		const size_t first = tiles.size();
-		for (int64_t s = 0; s < L; s += kCkTile) tiles.push_back(CkTile{i, (uint32_t)s, 0u, 0u});
+		for (int64_t s = 0; s < L; s += kCkTile) tiles.push_back(CkTile{i, (uint32_t)s, 0u, dynamic ? kCkDynamic : 0u});
+		if (dynamic) continue; // len[] are capacities: the kernel works the multipliers out from the device-side lengths
 		// multipliers from the last tile backwards: one mulmod per tile
 		uint32_t m = 1u << 31; // x^0
 		uint64_t after = 0;
@@ -64,10 +65,16 @@ __global__ void __launch_bounds__(kCkThreads)
 	__shared__ uint32_t s_words[kCkThreads * 33];
 	__shared__ uint32_t s_tab[4][256];
 	__shared__ unsigned long long s_red[2][kCkThreads / 32];
-	const CkTile td = tiles[blockIdx.x];
+	CkTile td = tiles[blockIdx.x];
 	const uint64_t n = (uint64_t)len[td.stream];
+	if ((uint64_t)td.start >= n) return; // tiles laid out for a capacity (inflate output): nothing of this stream here
 	const uint8_t *src = data + off[td.stream] + td.start;
 	const uint32_t tlen = n - td.start < (uint64_t)kCkTile ? (uint32_t)(n - td.start) : (uint32_t)kCkTile;
+	if (td.pad == kCkDynamic) {
+		// the length was not known when the tiles were made: derive the multiplier from the bytes behind this tile
+		const uint64_t after = n - ((uint64_t)td.start + tlen);
+		td.mult = KIND == 0 ? crc_xpow8(after) : (uint32_t)(after % kAdlerBase);
+	}
 	const int tid = threadIdx.x;
 	if (KIND == 0) {
 		for (int i = tid; i < 1024; i += kCkThreads) (&s_tab[0][0])[i] = (&c_crc_tab[0][0])[i];

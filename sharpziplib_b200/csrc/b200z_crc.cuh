@@ -53,6 +53,7 @@ B200Z_HD uint32_t crc_table0_entry(uint32_t i) {
 	return res;
 }
 
+constexpr uint32_t kCkDynamic = 0xD1CEu; // CkTile.pad: multiplier to be computed on the device (length known only there)
 struct CkTile {
 	int32_t stream;
 	uint32_t start; // first byte of the tile inside its stream

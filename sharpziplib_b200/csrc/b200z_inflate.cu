@@ -46,7 +46,19 @@ enum {
 	D_HDR_REPEAT0 = 7,  // "Cannot repeat previous code length ..."  InflaterDynHeader.cs:83
 	D_HDR_OVERRUN = 8,  // "Cannot repeat code lengths past ..."     InflaterDynHeader.cs:106
 	D_HDR_NO_EOB = 9,   // "... end-of-block code missing"           InflaterDynHeader.cs:114
-	D_OVERSUBSCRIBED = 10 // the reference indexes out of range here; reported as a data error
+	D_OVERSUBSCRIBED = 10, // the reference indexes out of range here; reported as a data error
+	// framing (zlib: Inflater.DecodeHeader / DecodeChksum; gzip: GZipInputStream.ReadHeader / ReadFooter)
+	D_ADLER = 11,        // "Adler chksum doesn't match"               Inflater.cs:413
+	D_GZIP_CRC = 12,     // "GZIP crc sum mismatch"                    GzipInputStream.cs:338
+	D_GZIP_ISIZE = 13,   // "Number of bytes mismatch in footer"       GzipInputStream.cs:350
+	D_GZIP_MAGIC1 = 14,  // "Error GZIP header, first magic byte ..."  GzipInputStream.cs:194
+	D_GZIP_MAGIC2 = 15,  // "... second magic byte doesn't match"      GzipInputStream.cs:200
+	D_GZIP_METHOD = 16,  // "... data not in deflate format"          GzipInputStream.cs:209
+	D_GZIP_FLAGS = 17,   // "Reserved flag bits in GZIP header != 0"   GzipInputStream.cs:222
+	D_GZIP_HCRC = 18,    // "Header CRC value mismatch"                GzipInputStream.cs:305
+	D_ZLIB_HCHECK = 19,  // "Header checksum illegal"                  Inflater.cs:224
+	D_ZLIB_METHOD = 20,  // "Compression Method unknown"               Inflater.cs:229
+	D_NEED_DICT = 22     // FDICT set and the plan holds no dictionary for the stream (Inflater.IsNeedingDictionary)
 };
 
 // decode table entry: nb[0..3] | kind[4..7] | extra[8..11] | base[16..31]
@@ -318,13 +330,21 @@ __global__ void __launch_bounds__(kInfThreads)
     k_inflate(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, const int64_t *__restrict__ in_off,
               const int64_t *__restrict__ in_len, const int64_t *__restrict__ out_off, const int64_t *__restrict__ out_cap,
               int nstreams, int64_t *__restrict__ out_len, int64_t *__restrict__ in_used, int32_t *__restrict__ status,
-              const uint32_t *__restrict__ dict_len) {
+              const uint32_t *__restrict__ dict_len, const uint32_t *__restrict__ start_bit, const int32_t *__restrict__ pre) {
 	extern __shared__ __align__(16) uint8_t smem_raw[];
 	InfBlockShared &S = *reinterpret_cast<InfBlockShared *>(smem_raw);
 	const int lane = threadIdx.x & 31;
 	const bool isA = threadIdx.x < 32, isB1 = threadIdx.x >= 32 && threadIdx.x < 64;
 	const int stream = blockIdx.x;
 	if (stream >= nstreams) return;
+	if (pre && pre[stream] != B200Z_OK) { // the framing header was rejected (k_wrap_head): nothing to decode
+		if (threadIdx.x == 0) {
+			status[stream] = pre[stream];
+			out_len[stream] = 0;
+			if (in_used) in_used[stream] = 0;
+		}
+		return;
+	}
 	uint8_t *dst = out + out_off[stream];
 	const uint64_t cap = (uint64_t)out_cap[stream];
 	const uint32_t *gwords = reinterpret_cast<const uint32_t *>(in + in_off[stream]);
@@ -358,7 +378,7 @@ __global__ void __launch_bounds__(kInfThreads)
 
 	// ---- warp A state (uniform across the warp unless noted) ----
 	uint64_t opos = 0;   // bytes produced by all rounds handed over so far
-	uint64_t bitpos = 0; // true bit position of the next symbol / header
+	uint64_t bitpos = start_bit ? start_bit[stream] : 0u; // true bit position of the next symbol / header (behind a framing header)
 	int st = B200Z_OK, detail = 0;
 	bool last = false, in_block = false, a_done = false, pending_stored = false;
 	uint32_t stored_len = 0;
@@ -727,6 +747,115 @@ __global__ void __launch_bounds__(kInfThreads)
 }
 
 // ------------------------------------------------------------------------------------------------
+// Framing around the raw stream, one thread per stream.  zlib: Inflater.DecodeHeader (:209-247) and DecodeChksum
+// (:397-418); gzip: GZipInputStream.ReadHeader (:169-311) and ReadFooter (:313-357), one member per plan slot (a caller
+// with multi-member input runs the rest again, in_used tells where it starts).
+// ------------------------------------------------------------------------------------------------
+__global__ void k_wrap_head(const uint8_t *__restrict__ in, const int64_t *__restrict__ in_off, const int64_t *__restrict__ in_len,
+                            const uint32_t *__restrict__ dict_len, int n, int wrap, uint32_t *__restrict__ start_bit,
+                            int32_t *__restrict__ pre) {
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const uint8_t *p = in + in_off[i];
+	const uint64_t len = (uint64_t)in_len[i];
+	int st = B200Z_OK, det = 0;
+	uint64_t pos = 0;
+	if (wrap == B200Z_WRAP_ZLIB) {
+		if (len < 2) st = B200Z_E_NEED_INPUT;
+		else {
+			const uint32_t header = ((uint32_t)p[0] << 8) | p[1];
+			if (header % 31 != 0) { st = B200Z_E_DATA; det = D_ZLIB_HCHECK; }
+			else if ((header & 0x0f00) != (8u << 8)) { st = B200Z_E_DATA; det = D_ZLIB_METHOD; }
+			else {
+				pos = 2;
+				if (header & 0x0020) { // PRESET_DICT: DICTID follows (:185-203); the caller has checked it against its dictionary
+					if (len < 6) st = B200Z_E_NEED_INPUT;
+					else if (dict_len[i] == 0) { st = B200Z_E_DATA; det = D_NEED_DICT; }
+					else pos = 6;
+				}
+			}
+		}
+	} else if (wrap == B200Z_WRAP_GZIP) {
+		// header CRC over every header byte read (:190-283), byte at a time with the table-0 recurrence
+		uint32_t crc = 0xFFFFFFFFu;
+		auto upd = [&](uint32_t b) { crc = crc_table0_entry((crc ^ b) & 0xFFu) ^ (crc >> 8); };
+		auto need = [&](uint64_t k) {
+			if (pos + k > len) { st = B200Z_E_NEED_INPUT; return false; } // "EOS reading GZIP header"
+			return true;
+		};
+		if (need(10)) {
+			if (p[0] != 0x1F) { st = B200Z_E_DATA; det = D_GZIP_MAGIC1; }
+			else if (p[1] != 0x8B) { st = B200Z_E_DATA; det = D_GZIP_MAGIC2; }
+			else if (p[2] != 8) { st = B200Z_E_DATA; det = D_GZIP_METHOD; }
+			else if (p[3] & 0xE0) { st = B200Z_E_DATA; det = D_GZIP_FLAGS; }
+		}
+		if (st == B200Z_OK) {
+			const uint32_t flags = p[3];
+			for (int k = 0; k < 10; k++) upd(p[k]);
+			pos = 10;
+			if (flags & 4) { // FEXTRA
+				if (need(2)) {
+					const uint32_t xlen = (uint32_t)p[pos] | ((uint32_t)p[pos + 1] << 8);
+					upd(p[pos]);
+					upd(p[pos + 1]);
+					pos += 2;
+					if (need(xlen)) {
+						for (uint32_t k = 0; k < xlen; k++) upd(p[pos + k]);
+						pos += xlen;
+					}
+				}
+			}
+			for (int field = 0; field < 2 && st == B200Z_OK; field++) { // FNAME, FCOMMENT: zero terminated
+				if (!(flags & (field == 0 ? 8u : 16u))) continue;
+				for (;;) {
+					if (!need(1)) break;
+					const uint32_t b = p[pos++];
+					upd(b);
+					if (b == 0) break;
+				}
+			}
+			if (st == B200Z_OK && (flags & 2)) { // FHCRC: the reference reads it high byte first (:286-306)
+				if (need(2)) {
+					const uint32_t crcval = ((uint32_t)p[pos] << 8) | p[pos + 1];
+					pos += 2;
+					if (crcval != ((crc ^ 0xFFFFFFFFu) & 0xFFFFu)) { st = B200Z_E_DATA; det = D_GZIP_HCRC; }
+				}
+			}
+		}
+	}
+	start_bit[i] = (uint32_t)(8u * pos);
+	pre[i] = st | (det << 8);
+}
+
+__global__ void k_wrap_tail(const uint8_t *__restrict__ in, const int64_t *__restrict__ in_off, const int64_t *__restrict__ in_len,
+                            int n, int wrap, int64_t *__restrict__ in_used, const int64_t *__restrict__ out_len,
+                            const uint32_t *__restrict__ check, int32_t *__restrict__ status) {
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	if ((status[i] & 0xFF) != B200Z_OK) return; // the stream did not end: nothing to compare
+	const uint8_t *p = in + in_off[i];
+	const uint64_t len = (uint64_t)in_len[i];
+	uint64_t used = (uint64_t)in_used[i];
+	const uint64_t want = wrap == B200Z_WRAP_ZLIB ? 4u : 8u;
+	if (used + want > len) { // DecodeChksum waits for more input; "EOS reading GZIP footer"
+		status[i] = B200Z_E_NEED_INPUT;
+		in_used[i] = (int64_t)len;
+		return;
+	}
+	const uint8_t *t = p + used;
+	if (wrap == B200Z_WRAP_ZLIB) {
+		const uint32_t theirs = ((uint32_t)t[0] << 24) | ((uint32_t)t[1] << 16) | ((uint32_t)t[2] << 8) | t[3];
+		if (theirs != check[i]) status[i] = B200Z_E_DATA | (D_ADLER << 8);
+	} else {
+		const uint32_t crcval = (uint32_t)t[0] | ((uint32_t)t[1] << 8) | ((uint32_t)t[2] << 16) | ((uint32_t)t[3] << 24);
+		const uint32_t total = (uint32_t)t[4] | ((uint32_t)t[5] << 8) | ((uint32_t)t[6] << 16) | ((uint32_t)t[7] << 24);
+		if (crcval != check[i]) status[i] = B200Z_E_DATA | (D_GZIP_CRC << 8);
+		else if (total != (uint32_t)((uint64_t)out_len[i] & 0xFFFFFFFFu)) status[i] = B200Z_E_DATA | (D_GZIP_ISIZE << 8);
+	}
+	in_used[i] = (int64_t)(used + want);
+}
+
+// ------------------------------------------------------------------------------------------------
 int inflate_plan_build(b200z_plan *p) {
 	const int n = p->n;
 	p->in_off.resize(n);
@@ -760,18 +889,30 @@ int inflate_plan_build(b200z_plan *p) {
 	p->o_out_off = ws.reserve(8ll * (n + 1));
 	p->o_out_cap = ws.reserve(8ll * (n + 1));
 	p->o_hist = ws.reserve(4ll * (n + 1));
+	p->o_start_bit = ws.reserve(4ll * (n + 1));
+	p->o_pre = ws.reserve(4ll * (n + 1));
 	std::vector<CkTile> ck_tiles;
+	if (p->wrap != B200Z_WRAP_RAW) {
+		// checksum of the OUTPUT (Adler-32 for zlib, CRC-32 for gzip and raw+CRC): tiles over the capacities, the kernel takes
+		// the real lengths from d_out_len
+		checksum_tiles(p->out_cap.data(), n, ck_tiles, p->wrap == B200Z_WRAP_ZLIB ? 1 : 0, true);
+		p->n_ck_tiles = (int)ck_tiles.size();
+		p->o_ck_desc = ws.reserve((int64_t)sizeof(CkTile) * (ck_tiles.size() + 1));
+		p->o_ck_acc = ws.reserve(16ll * (n + 1));
+	}
 	int rc = ws.alloc();
 	if (rc) return rc;
 	if (n) {
 		B200Z_CUDA(cudaMemcpy(ws.at<int64_t>(p->o_in_off), dev_off.data(), 8ll * n, cudaMemcpyHostToDevice));
 		B200Z_CUDA(cudaMemcpy(ws.at<int64_t>(p->o_in_len), dev_len.data(), 8ll * n, cudaMemcpyHostToDevice));
 		B200Z_CUDA(cudaMemcpy(ws.at<uint32_t>(p->o_hist), dict32.data(), 4ll * n, cudaMemcpyHostToDevice));
+		if (!ck_tiles.empty())
+			B200Z_CUDA(cudaMemcpy(ws.at<CkTile>(p->o_ck_desc), ck_tiles.data(), sizeof(CkTile) * ck_tiles.size(), cudaMemcpyHostToDevice));
 		B200Z_CUDA(cudaMemcpy(ws.at<int64_t>(p->o_out_off), p->out_off.data(), 8ll * n, cudaMemcpyHostToDevice));
 		B200Z_CUDA(cudaMemcpy(ws.at<int64_t>(p->o_out_cap), p->out_cap.data(), 8ll * n, cudaMemcpyHostToDevice));
 	}
 	B200Z_CUDA(cudaFuncSetAttribute(k_inflate, cudaFuncAttributeMaxDynamicSharedMemorySize, kInfSmem2));
-	p->launches = 1;
+	p->launches = p->wrap == B200Z_WRAP_RAW ? 1 : (p->wrap == B200Z_WRAP_RAW_CRC32 ? 4 : 6);
 	return B200Z_OK;
 }
 
@@ -780,12 +921,30 @@ int inflate_plan_run(b200z_plan *p, const uint8_t *d_in, uint8_t *d_out, int64_t
 	const Arena &ws = p->ws;
 	const int n = p->n;
 	if (n == 0) return B200Z_OK;
-	(void)d_check;
 	p->ev_used = 0;
+	const int wrap = p->wrap;
+	const bool framed = wrap == B200Z_WRAP_ZLIB || wrap == B200Z_WRAP_GZIP;
+	if (wrap != B200Z_WRAP_RAW && (!d_check || !d_in_used)) {
+		set_error("inflate plans with framing or checksums need d_check and d_in_used");
+		return B200Z_E_ARG;
+	}
+	const int64_t *in_off = ws.at<int64_t>(p->o_in_off), *in_len = ws.at<int64_t>(p->o_in_len);
+	uint32_t *start_bit = framed ? ws.at<uint32_t>(p->o_start_bit) : nullptr;
+	int32_t *pre = framed ? ws.at<int32_t>(p->o_pre) : nullptr;
+	if (framed) {
+		p->mark(s, "k_wrap");
+		k_wrap_head<<<(n + 127) / 128, 128, 0, s>>>(d_in, in_off, in_len, ws.at<uint32_t>(p->o_hist), n, wrap, start_bit, pre);
+	}
 	p->mark(s, "k_inflate");
-	k_inflate<<<n, kInfThreads, kInfSmem2, s>>>(
-	    d_in, d_out, ws.at<int64_t>(p->o_in_off), ws.at<int64_t>(p->o_in_len), ws.at<int64_t>(p->o_out_off),
-	    ws.at<int64_t>(p->o_out_cap), n, d_out_len, d_in_used, d_status, ws.at<uint32_t>(p->o_hist));
+	k_inflate<<<n, kInfThreads, kInfSmem2, s>>>(d_in, d_out, in_off, in_len, ws.at<int64_t>(p->o_out_off), ws.at<int64_t>(p->o_out_cap),
+	                                           n, d_out_len, d_in_used, d_status, ws.at<uint32_t>(p->o_hist), start_bit, pre);
+	if (wrap != B200Z_WRAP_RAW) {
+		p->mark(s, "checksum");
+		int rc = checksum_launch(wrap == B200Z_WRAP_ZLIB ? 1 : 0, d_out, ws.at<int64_t>(p->o_out_off), d_out_len, n,
+		                         ws.at<CkTile>(p->o_ck_desc), p->n_ck_tiles, ws.at<unsigned long long>(p->o_ck_acc), d_check, 1, s);
+		if (rc) return rc;
+		if (framed) k_wrap_tail<<<(n + 127) / 128, 128, 0, s>>>(d_in, in_off, in_len, n, wrap, d_in_used, d_out_len, d_check, d_status);
+	}
 	p->mark(s, "end");
 	B200Z_CUDA(cudaGetLastError());
 	return B200Z_OK;

@@ -97,6 +97,7 @@ struct b200z_plan {
 	int n_stored = 0;
 	// inflate workspace offsets
 	int64_t o_tok = 0, o_ntok = 0, o_tok_off = 0;
+	int64_t o_start_bit = 0, o_pre = 0; // inflate framing: first deflate bit and header verdict per stream
 	// checksum scratch
 	int64_t o_ck_desc = 0, o_ck_acc = 0;
 	int n_ck_tiles = 0;
@@ -132,6 +133,6 @@ int inflate_plan_run(b200z_plan *p, const uint8_t *d_in, uint8_t *d_out, int64_t
 int checksum_launch(int kind, const uint8_t *d_data, const int64_t *d_off, const int64_t *d_len, int32_t n,
                     const CkTile *d_tiles, int32_t n_tiles, unsigned long long *d_acc, uint32_t *d_value, int fresh,
                     cudaStream_t s);
-int checksum_tiles(const int64_t *len, int32_t n, std::vector<CkTile> &tiles, int kind);
+int checksum_tiles(const int64_t *len, int32_t n, std::vector<CkTile> &tiles, int kind, bool dynamic = false);
 int checksum_init_tables();
 } // namespace b200z

@@ -609,3 +609,83 @@ def test_fuzz_deflate_inflate_against_oracle(z, oracle):
         assert [int(x) for x in st] == [0] * n
         for i, b in enumerate(bufs):
             assert back[i] == b and int(used[i]) == len(raw[i]), (trial, i)
+
+
+# ---- framing on the device: zlib / gzip headers and trailers around inflate plans ---------------------------------
+def _gzip_member(data, level=6, fname=None, extra=None, comment=None, hcrc=False, mtime=0):
+    """a gzip member as GZipOutputStream would frame it, with optional header fields; FHCRC written the way the reference
+    READS it (high byte first, GzipInputStream.cs:286-306)"""
+    import struct
+    flags = (4 if extra is not None else 0) | (8 if fname is not None else 0) | (16 if comment is not None else 0) | (2 if hcrc else 0)
+    h = bytearray([0x1F, 0x8B, 8, flags]) + struct.pack("<I", mtime) + bytes([0, 255])
+    if extra is not None:
+        h += struct.pack("<H", len(extra)) + extra
+    if fname is not None:
+        h += fname + b"\0"
+    if comment is not None:
+        h += comment + b"\0"
+    if hcrc:
+        c = zlib.crc32(bytes(h)) & 0xFFFF
+        h += bytes([c >> 8, c & 0xFF])
+    co = zlib.compressobj(level, zlib.DEFLATED, -15)
+    raw = co.compress(data) + co.flush()
+    return bytes(h) + raw + struct.pack("<II", zlib.crc32(data) & 0xFFFFFFFF, len(data) & 0xFFFFFFFF), len(h)
+
+
+def test_inflate_zlib_framing_on_device(z, oracle):
+    bufs = [d for _, d in corpus_small() if len(d) >= 10][:12] + [b"", datagen.gen_text(300000, 3).tobytes()]
+    comp = [oracle.deflate(b, level=6, nowrap=False) for b in bufs]
+    out, used, st, chk = z.inflate_batch(comp, [len(b) + 8 for b in bufs], wrap=1, return_checks=True)
+    assert [int(x) for x in st] == [0] * len(bufs)
+    for i, b in enumerate(bufs):
+        assert out[i] == b and int(used[i]) == len(comp[i]) and int(chk[i]) == zlib.adler32(b), i
+    # trailing bytes are not consumed; a wrong trailer, header check and method are the reference's errors
+    c = comp[3]
+    cases = [(c + b"xyz", 0, 0, len(c)), (c[:-1] + bytes([c[-1] ^ 1]), 3, 11, None), (bytes([c[0], c[1] ^ 1]) + c[2:], 3, 19, None),
+             (bytes([0x79, 0x9C ^ 0x1F]) + c[2:], 3, None, None), (c[:-2], 8, 0, len(c) - 2), (c[:1], 8, 0, None)]
+    for blob, code, det, want_used in cases:
+        o, u, s = z.inflate_batch([blob], [len(bufs[3]) + 8], wrap=1, raise_on_error=False)
+        assert int(s[0]) & 0xFF == code, (code, int(s[0]))
+        if det is not None:
+            assert int(s[0]) >> 8 == det
+        if want_used is not None:
+            assert int(u[0]) == want_used
+    with pytest.raises(z.SharpZipBaseException, match="Adler chksum"):
+        z.inflate_batch([c[:-1] + bytes([c[-1] ^ 1])], [len(bufs[3]) + 8], wrap=1)
+
+
+def test_inflate_gzip_framing_on_device(z):
+    data = datagen.gen_text(200000, 21).tobytes()
+    variants = [dict(), dict(fname=b"file.txt"), dict(extra=b"\x01\x02abcd"), dict(comment=b"hello"), dict(hcrc=True),
+                dict(fname=b"n", extra=b"", comment=b"c", hcrc=True, mtime=123456789)]
+    members = [_gzip_member(data[: 1000 * (i + 1) * 37], **v) for i, v in enumerate(variants)]
+    blobs = [m for m, _ in members]
+    out, used, st, chk = z.inflate_batch(blobs, [len(data) + 8] * len(blobs), wrap=2, return_checks=True)
+    assert [int(x) for x in st] == [0] * len(blobs)
+    for i in range(len(blobs)):
+        want = data[: 1000 * (i + 1) * 37]
+        assert out[i] == want and int(used[i]) == len(blobs[i]) and int(chk[i]) == zlib.crc32(want), i
+    # two members back to back: the first run stops behind the first footer, the rest starts a new header there
+    two = blobs[1] + blobs[2]
+    o, u, s = z.inflate_batch([two], [len(data) + 8], wrap=2)
+    assert int(s[0]) == 0 and int(u[0]) == len(blobs[1]) and o[0] == data[:74000]
+    o, u, s = z.inflate_batch([two[int(u[0]):]], [len(data) + 8], wrap=2)
+    assert int(s[0]) == 0 and o[0] == data[:111000]
+    # every header / footer error of GZipInputStream (detail codes in INTEGRATION.md)
+    g, hl = members[5]
+    bad = lambda i, v: g[:i] + bytes([v]) + g[i + 1:]
+    cases = [(bad(0, 0x1E), 3, 14), (bad(1, 0x8C), 3, 15), (bad(2, 7), 3, 16), (bad(3, g[3] | 0x20), 3, 17),
+             (bad(hl - 1, g[hl - 1] ^ 1), 3, 18), (bad(len(g) - 8, g[-8] ^ 1), 3, 12), (bad(len(g) - 1, g[-1] ^ 1), 3, 13),
+             (g[:-3], 8, 0), (g[:hl - 1], 8, 0), (g[:5], 8, 0)]
+    for blob, code, det in cases:
+        o, u, s = z.inflate_batch([blob], [len(data) + 8], wrap=2, raise_on_error=False)
+        assert (int(s[0]) & 0xFF, int(s[0]) >> 8) == (code, det), (code, det, int(s[0]))
+
+
+def test_inflate_raw_with_crc_for_zip_entries(z, oracle):
+    bufs = [datagen.silesia_mix(c, 90000 + 1111 * c, config=4).tobytes() for c in range(6)] + [b""]
+    comp = [oracle.deflate(b, level=9) for b in bufs]
+    out, used, st, chk = z.inflate_batch(comp, [len(b) + 8 for b in bufs], wrap=3, return_checks=True)
+    assert [int(x) for x in st] == [0] * len(bufs)
+    for i, b in enumerate(bufs):
+        assert out[i] == b and int(chk[i]) == zlib.crc32(b) and int(used[i]) == len(comp[i]), i
