@@ -28,7 +28,7 @@ typedef enum b200z_status {
 } b200z_status;
 
 /* wrapper around the raw deflate stream */
-enum { B200Z_WRAP_RAW = 0, B200Z_WRAP_ZLIB = 1, B200Z_WRAP_GZIP = 2, B200Z_WRAP_RAW_CRC32 = 3 /* inflate plans: raw stream, CRC-32 of the output (zip entries) */ };
+enum { B200Z_WRAP_RAW = 0, B200Z_WRAP_ZLIB = 1, B200Z_WRAP_GZIP = 2, B200Z_WRAP_RAW_CRC32 = 3 /* raw stream plus the CRC-32 of the uncompressed bytes in `check`: zip entries */ };
 /* DeflateStrategy, Zip/Compression/DeflaterEngine.cs:9-28 */
 enum { B200Z_STRATEGY_DEFAULT = 0, B200Z_STRATEGY_FILTERED = 1, B200Z_STRATEGY_HUFFMAN_ONLY = 2 };
 /* how a deflate plan ends each stream (which Deflater calls the bytes correspond to) */

@@ -150,3 +150,23 @@ def inflate_batch(buffers, out_caps, raise_on_error=True, wrap=_lib.WRAP_RAW, re
     if return_checks:
         return res, in_used, status, check
     return res, in_used, status
+
+
+def zip_entries(buffers, level=6):
+    """Compresses the payloads of many zip entries in one device batch.  Returns, per entry, what the reference's
+    ZipOutputStream.PutNextPassthroughEntry (Zip/ZipOutputStream.cs:283-333) asks for: the raw deflate stream, the CRC-32
+    and the size of the uncompressed bytes (CompressedSize is len(raw)) -- the container itself (local headers, central
+    directory, Zip64, name encoding) stays with the reference's own ZipOutputStream."""
+    outs, checks = deflate_batch(buffers, level=level, wrap=_lib.WRAP_RAW_CRC32)
+    return [{"raw": o, "crc": int(c), "size": len(b)} for o, c, b in zip(outs, checks, buffers)]
+
+
+def unzip_entries(raw_streams, sizes, crcs=None):
+    """The read side (ZipFile.GetInputStream + the CRC test of ZipFile.TestArchive / ZipInputStream): inflates raw entry
+    streams in one device batch, CRC-32 of every output computed on the device; raises on a mismatch with `crcs`."""
+    outs, used, status, checks = inflate_batch(raw_streams, sizes, wrap=_lib.WRAP_RAW_CRC32, return_checks=True)
+    if crcs is not None:
+        for i, (got, want) in enumerate(zip(checks, crcs)):
+            if int(got) != int(want) & 0xFFFFFFFF:
+                raise _lib.SharpZipBaseException("CRC mismatch in entry %d" % i)
+    return outs

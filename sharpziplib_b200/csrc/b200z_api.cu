@@ -264,7 +264,7 @@ int b200z_deflate_plan_create_ex(int32_t n, const int64_t *in_len, int level, in
 		set_error("level");
 		return B200Z_E_ARG;
 	}
-	if (strategy < 0 || strategy > 2 || wrap < 0 || wrap > 2 || end_mode < 0 || end_mode > 2) {
+	if (strategy < 0 || strategy > 2 || wrap < 0 || wrap > B200Z_WRAP_RAW_CRC32 || end_mode < 0 || end_mode > 2) {
 		set_error("strategy/wrap/end_mode");
 		return B200Z_E_ARG;
 	}
@@ -575,7 +575,7 @@ int b200z_deflate_batch(const uint8_t *const *in, const int64_t *in_len, int32_t
 	if (wrap == B200Z_WRAP_GZIP) {
 		// GZipOutputStream's header carries caller state (MTIME, FNAME; GzipOutputStream.cs:339-375): the host shim
 		// writes header and trailer around the raw stream and takes the CRC32 from `check`.
-		set_error("gzip framing is written by the host stream layer; deflate with wrap=RAW and use check (CRC32)");
+		set_error("gzip framing is written by the host stream layer; deflate with wrap=B200Z_WRAP_RAW_CRC32 and use check (CRC32)");
 		return B200Z_E_UNSUPPORTED;
 	}
 	if (level == -1) level = 6;

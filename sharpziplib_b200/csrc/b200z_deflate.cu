@@ -1158,7 +1158,7 @@ int deflate_plan_build(b200z_plan *p) {
 		}
 		p->o_ck_off = ws.reserve(8ll * (n + 1));
 		p->o_ck_len = ws.reserve(8ll * (n + 1));
-		checksum_tiles(ck_len.data(), n, ck_tiles, p->wrap == B200Z_WRAP_GZIP ? 0 : 1);
+		checksum_tiles(ck_len.data(), n, ck_tiles, p->wrap == B200Z_WRAP_ZLIB ? 1 : 0);
 		p->n_ck_tiles = (int)ck_tiles.size();
 		p->o_ck_desc = ws.reserve((int64_t)sizeof(CkTile) * (ck_tiles.size() + 1));
 		p->o_ck_acc = ws.reserve(16ll * (n + 1));
@@ -1245,7 +1245,7 @@ int deflate_plan_run(b200z_plan *p, const uint8_t *d_in, uint8_t *d_out, int64_t
 		k_set_results<<<(n + 127) / 128, 128, 0, s>>>(n, ws.at<int64_t>(p->o_slens), d_out_len, d_status, d_out_bits);
 		p->mark(s, "checksum");
 		if (p->wrap != B200Z_WRAP_RAW && d_check) {
-			int rc = checksum_launch(p->wrap == B200Z_WRAP_GZIP ? 0 : 1, d_in, ws.at<int64_t>(p->o_ck_off), ws.at<int64_t>(p->o_ck_len), n,
+			int rc = checksum_launch(p->wrap == B200Z_WRAP_ZLIB ? 1 : 0, d_in, ws.at<int64_t>(p->o_ck_off), ws.at<int64_t>(p->o_ck_len), n,
 			                         ws.at<CkTile>(p->o_ck_desc), p->n_ck_tiles, ws.at<unsigned long long>(p->o_ck_acc), d_check,
 			                         ck_fresh, s);
 			if (rc) return rc;
@@ -1304,7 +1304,7 @@ int deflate_plan_run(b200z_plan *p, const uint8_t *d_in, uint8_t *d_out, int64_t
 	k_emit<<<p->n_blkmax, 256, 0, s>>>(d_in, sym, d_out, in_off, out_off, nblocks, blk_off, blk_desc, meta, tables);
 	p->mark(s, "checksum");
 	if (p->wrap != B200Z_WRAP_RAW && d_check) {
-		int rc = checksum_launch(p->wrap == B200Z_WRAP_GZIP ? 0 : 1, d_in, ws.at<int64_t>(p->o_ck_off), ws.at<int64_t>(p->o_ck_len), n,
+		int rc = checksum_launch(p->wrap == B200Z_WRAP_ZLIB ? 1 : 0, d_in, ws.at<int64_t>(p->o_ck_off), ws.at<int64_t>(p->o_ck_len), n,
 		                         ws.at<CkTile>(p->o_ck_desc), p->n_ck_tiles, ws.at<unsigned long long>(p->o_ck_acc), d_check,
 		                         ck_fresh, s);
 		if (rc) return rc;

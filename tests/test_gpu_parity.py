@@ -689,3 +689,33 @@ def test_inflate_raw_with_crc_for_zip_entries(z, oracle):
     assert [int(x) for x in st] == [0] * len(bufs)
     for i, b in enumerate(bufs):
         assert out[i] == b and int(chk[i]) == zlib.crc32(b) and int(used[i]) == len(comp[i]), i
+
+
+def test_zip_entry_batch_roundtrip_through_a_real_container(z, oracle):
+    """f2: entry payloads compressed in one batch (raw stream + CRC-32 + size = a passthrough entry); assembled into a
+    minimal container here and read back by Python's zipfile, then through the device read path"""
+    import struct
+    import zipfile
+    names = ["a.txt", "dir/b.bin", "empty", "c.log"]
+    datas = [datagen.gen_text(70000, 1).tobytes(), datagen.silesia_mix(5, 123457, config=2).tobytes(), b"",
+             datagen.gen_log(200000, 9).tobytes()]
+    ents = z.zip_entries(datas, level=6)
+    for e, d in zip(ents, datas):
+        assert e["raw"] == oracle.deflate(d, level=6) and e["crc"] == zlib.crc32(d) and e["size"] == len(d)
+    blob, central = bytearray(), bytearray()
+    for name, e in zip(names, ents):
+        n = name.encode()
+        off = len(blob)
+        blob += struct.pack("<IHHHHHIIIHH", 0x04034B50, 20, 0, 8, 0, 0x21, e["crc"], len(e["raw"]), e["size"], len(n), 0) + n + e["raw"]
+        central += struct.pack("<IHHHHHHIIIHHHHHII", 0x02014B50, 20, 20, 0, 8, 0, 0x21, e["crc"], len(e["raw"]), e["size"], len(n), 0, 0,
+                               0, 0, 0, off) + n
+    cd_off = len(blob)
+    blob += central + struct.pack("<IHHHHIIH", 0x06054B50, 0, 0, len(names), len(names), len(central), cd_off, 0)
+    with zipfile.ZipFile(io.BytesIO(bytes(blob))) as zf:
+        assert zf.testzip() is None
+        for name, d in zip(names, datas):
+            assert zf.read(name) == d
+    back = z.unzip_entries([e["raw"] for e in ents], [e["size"] for e in ents], [e["crc"] for e in ents])
+    assert back == datas
+    with pytest.raises(z.SharpZipBaseException):
+        z.unzip_entries([ents[0]["raw"]], [ents[0]["size"]], [ents[0]["crc"] ^ 1])
