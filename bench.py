@@ -496,7 +496,10 @@ def main():
                     "h2d_bytes_per_step": int(dplan.in_bytes + iplan.in_bytes),
                     "d2h_bytes_per_step": int(e2e_d2h[0]),
                     "how": "pinned host buffers; upload / deflate-leg / inflate-leg / download streams over two device buffer sets (step i+1 uploads and step i-1 downloads overlap step i's kernels); packed D2H of the deflate output; %d steps + drain timed" % n_e2e},
-            "gpu_launches": int(dplan.launches + iplan.launches),
+            # kernels of libb200z.so launched inside the timed region of `value` (per step: k_links, k_match, 4 x k_parse_*,
+            # k_plan, k_scan, k_emit, k_inflate)
+            "gpu_launches": int(dplan.launches + iplan.launches) * args.steps,
+            "gpu_launches_per_step": int(dplan.launches + iplan.launches),
             "clocks": clocks,
         }
         out.write(json.dumps(line) + "\n")
