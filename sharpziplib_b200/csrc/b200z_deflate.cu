@@ -191,8 +191,8 @@ __global__ void __launch_bounds__(kMatchThreads, 1)
 	const uint32_t ab = (uint32_t)bias[td.x]; // absolute stream offset of buffer position 0 (window-slide phase, trap T8)
 	// ---- order the tile's positions by expected chain length ----
 	// A warp runs as long as its longest chain walk (ncu: 13 of 32 lanes active in the candidate loop).  So the positions
-	// are bucketed by an estimate of their walk length (the first hops are exact, beyond that the hop density of the first
-	// four extrapolated over the window) and handed to the threads longest first: warps then hold walks of similar length.
+	// are bucketed by an estimate of their walk length (the first eight hops are exact, beyond that their hop density
+	// extrapolated over the window) and handed to the threads longest first: warps then hold walks of similar length.
 	// The order only decides who computes what; every position's result is unchanged.
 	__shared__ uint32_t s_cls[2][kMatchClasses];
 	if (threadIdx.x < 2 * kMatchClasses) (&s_cls[0][0])[threadIdx.x] = 0;
