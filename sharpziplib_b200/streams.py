@@ -48,6 +48,9 @@ class DeflaterOutputStream:
         self.deflater_.SetInput(buffer, offset, count)
         self._deflate(False)
 
+    def WriteByte(self, value):  # Stream.WriteByte -> Write of one byte (:495-504)
+        self.Write(bytes([value & 0xFF]))
+
     def Flush(self):  # :388-393
         self.deflater_.Flush()
         self._deflate(True)
@@ -201,58 +204,83 @@ class GZipOutputStream(DeflaterOutputStream):
 
 
 class GZipInputStream(InflaterInputStream):
-    """Single/multi-member gzip reader -- GZip/GzipInputStream.cs:38-360, reduced to what the codec boundary needs:
-    header parse, inflate, CRC32 + ISIZE check from the bytes the Inflater reports as RemainingInput (trap T14)."""
+    """Single/multi-member gzip reader -- GZip/GzipInputStream.cs:38-360.  Header parse (FEXTRA / FNAME / FCOMMENT / FHCRC),
+    inflate, CRC-32 of the output and the CRC / ISIZE comparison with the footer all run on the device, one member per
+    call of the batch ABI with B200Z_WRAP_GZIP (k_wrap_head, k_inflate, checksum kernel, k_wrap_tail); this class only
+    loops over the members the way Read (:96-155) does: a header that fails after at least one complete member is
+    trailing garbage and ends the stream quietly (:107-123), a member cut short hands out what was decoded and then
+    raises."""
 
     def __init__(self, baseInputStream, size=4096):
         super().__init__(baseInputStream, Inflater(True), size)
-        self._data = baseInputStream.read()
-        self._pos = 0
+        self._data = None
+        self._out = bytearray()
+        self._served = 0
+        self._error = None
+        self._fileName = None
+
+    def GetFilename(self):  # :160-163: the FNAME field of the (last read) member header
+        self._decode()
+        return self._fileName
+
+    def _decode(self):
+        if self._data is not None:
+            return
+        from . import _lib
+        from .batch import inflate_batch
+        d = self._data = self.baseInputStream.read()
+        pos, completed = 0, False
+        while pos < len(d):
+            blob = d[pos:]
+            cap = max(1 << 16, 8 * len(blob))
+            while True:
+                outs, used, st = inflate_batch([blob], [cap], raise_on_error=False, wrap=_lib.WRAP_GZIP)
+                code, detail = int(st[0]) & 0xFF, int(st[0]) >> 8
+                if code != _lib.E_NOMEM or cap > (1 << 34):
+                    break
+                cap *= 8
+            header_failed = int(used[0]) == 0 and (code == _lib.E_NEED_INPUT or (code == _lib.E_DATA and 14 <= detail <= 18))
+            if code == _lib.OK:
+                self._out += outs[0]
+                if blob[3] & 0x08:  # FNAME: zero terminated, behind the optional FEXTRA (:248-270)
+                    q = 10 + ((2 + (blob[10] | (blob[11] << 8))) if blob[3] & 0x04 else 0)
+                    self._fileName = bytes(blob[q:blob.index(0, q)]).decode("cp1252", "replace")
+                else:
+                    self._fileName = None
+                pos += int(used[0])
+                completed = True
+                continue
+            if header_failed and completed:
+                break  # trailing garbage behind a complete member
+            self._out += outs[0]  # whatever was decoded before the stream broke off
+            msg = _lib.lib().b200z_last_error().decode("utf-8", "replace") if code == _lib.E_DATA else \
+                ("EOS reading GZIP header" if header_failed else "Unexpected EOF")
+            self._error = SharpZipBaseException(msg)
+            break
+
+    def Read(self, buffer, offset=0, count=None):  # :96-155
+        self._decode()
+        if count is None:
+            count = len(buffer) - offset
+        n = min(count, len(self._out) - self._served)
+        if n == 0 and self._error is not None:
+            err, self._error = self._error, None
+            raise err
+        buffer[offset:offset + n] = self._out[self._served:self._served + n]
+        self._served += n
+        return n
+
+    def ReadByte(self):
+        b = bytearray(1)
+        return b[0] if self.Read(b, 0, 1) == 1 else -1
 
     def read(self, n=-1):
-        out = bytearray()
-        while self._pos < len(self._data):
-            d = self._data
-            p = self._pos
-            if len(d) - p < 10 or d[p] != 0x1F or d[p + 1] != 0x8B:
-                if out:
-                    break  # trailing garbage after a complete member is tolerated (:107-154)
-                raise SharpZipBaseException("Error GZIP header, first magic byte doesn't match")
-            if d[p + 2] != 8:
-                raise SharpZipBaseException("Error GZIP header,  data not in deflate format")
-            flg = d[p + 3]
-            q = p + 10
-            if flg & 0x04:
-                xlen = d[q] | (d[q + 1] << 8)
-                q += 2 + xlen
-            if flg & 0x08:
-                q = d.index(0, q) + 1
-            if flg & 0x10:
-                q = d.index(0, q) + 1
-            if flg & 0x02:
-                q += 2
-            self.inf.Reset()
-            self.inf.SetInput(d[q:])
-            member = bytearray()
-            buf = bytearray(1 << 16)
-            while not self.inf.IsFinished:
-                got = self.inf.Inflate(buf, 0, len(buf))
-                if got == 0:
-                    if self.inf.IsNeedingInput:
-                        raise SharpZipBaseException("Unexpected EOF")
-                    break
-                member += buf[:got]
-            rem = self.inf.RemainingInput
-            t = len(d) - rem
-            if rem < 8:
-                raise SharpZipBaseException("EOS reading GZIP footer")
-            crcval, isize = struct.unpack_from("<II", d, t)
-            c = Crc32()
-            c.Update(bytes(member))
-            if crcval != c.Value:
-                raise SharpZipBaseException("GZIP crc sum mismatch")
-            if isize != (len(member) & 0xFFFFFFFF):
-                raise SharpZipBaseException("Number of bytes mismatch in footer")
-            out += member
-            self._pos = t + 8
-        return bytes(out)
+        self._decode()
+        avail = len(self._out) - self._served
+        if avail == 0 and self._error is not None:
+            err, self._error = self._error, None
+            raise err
+        k = avail if n < 0 else min(n, avail)
+        r = bytes(self._out[self._served:self._served + k])
+        self._served += k
+        return r

@@ -719,3 +719,95 @@ def test_zip_entry_batch_roundtrip_through_a_real_container(z, oracle):
     assert back == datas
     with pytest.raises(z.SharpZipBaseException):
         z.unzip_entries([ents[0]["raw"]], [ents[0]["size"]], [ents[0]["crc"] ^ 1])
+
+
+# ---- the reference's own GZip stream tests, against the mirror (test/ICSharpCode.SharpZipLib.Tests/GZip/GZipTests.cs) ----
+def _dummy_bytes(size, seed=1):
+    return datagen.Rng(1000 + seed).bytes(size).tobytes()
+
+
+def test_gzip_reference_tests_delayed_header(z):
+    """DelayedHeaderWriteNoData / FlushNoData / WithData / FlushWithData (:65-160)"""
+    ms = io.BytesIO()
+    g = z.GZipOutputStream(ms)
+    g.IsStreamOwner = False
+    assert len(ms.getvalue()) == 0
+    g.Close()
+    assert len(ms.getvalue()) != 0
+    ms = io.BytesIO()
+    g = z.GZipOutputStream(ms)
+    g.IsStreamOwner = False
+    g.Flush()  # issue 382: flushing before anything was written
+    g.Close()
+    assert z.GZipInputStream(io.BytesIO(ms.getvalue())).read() == b""
+    ms = io.BytesIO()
+    g = z.GZipOutputStream(ms)
+    g.IsStreamOwner = False
+    g.WriteByte(45)
+    assert len(ms.getvalue()) == 10  # the header, with one byte in the compression pipeline
+    g.Close()
+    assert z.GZipInputStream(io.BytesIO(ms.getvalue())).read() == bytes([45])
+    ms = io.BytesIO()
+    g = z.GZipOutputStream(ms)
+    g.IsStreamOwner = False
+    g.Flush()
+    g.WriteByte(45)  # input after a sync flush
+    g.Close()
+    assert z.GZipInputStream(io.BytesIO(ms.getvalue())).read() == bytes([45])
+
+
+def test_gzip_reference_tests_reader(z):
+    """ZeroLengthInputStream (:166), DoubleFooter (:241), TrailingGarbage (:291), FlushToUnderlyingStream (:343),
+    OriginalFilename (:480)"""
+    assert z.GZipInputStream(io.BytesIO(b"")).ReadByte() == -1
+    ms = io.BytesIO()
+    g = z.GZipOutputStream(ms)
+    g.IsStreamOwner = False
+    g.Finish()
+    length = len(ms.getvalue())
+    g.Close()  # a second Finish must not write a second footer
+    assert len(ms.getvalue()) == length
+    buf = _dummy_bytes(100000, 3)
+    ms = io.BytesIO()
+    g = z.GZipOutputStream(ms)
+    g.IsStreamOwner = False
+    g.Write(buf)
+    g.Flush()
+    g.Finish()
+    garbage = _dummy_bytes(4096, 4)
+    r = z.GZipInputStream(io.BytesIO(ms.getvalue() + garbage))
+    got = bytearray(len(buf))
+    idx = 0
+    while idx < len(got):
+        n = r.Read(got, idx, len(got) - idx)
+        if n <= 0:
+            break
+        idx += n
+    assert idx == len(buf) and bytes(got) == buf and r.Read(bytearray(16), 0, 16) == 0
+    ms = io.BytesIO()
+    g = z.GZipOutputStream(ms)
+    g.IsStreamOwner = False
+    g.Write(buf)
+    g.Flush()  # flushed, not finished: everything written so far must be readable
+    r = z.GZipInputStream(io.BytesIO(ms.getvalue()))
+    got, idx = bytearray(len(buf)), 0
+    try:
+        while idx < len(got):
+            n = r.Read(got, idx, len(got) - idx)
+            if n <= 0:
+                break
+            idx += n
+        r.Read(bytearray(1), 0, 1)
+        raised = False
+    except z.SharpZipBaseException:
+        raised = True  # "unexpected EOF" once all data has been read
+    assert idx == len(buf) and bytes(got) == buf and raised
+    ms = io.BytesIO()
+    g = z.GZipOutputStream(ms)
+    g.IsStreamOwner = False
+    g.FileName = "/path/to/file.ext"
+    g.Write(b"FileContents")
+    g.Flush()
+    g.Finish()
+    r = z.GZipInputStream(io.BytesIO(ms.getvalue()))
+    assert r.read(12) == b"FileContents" and r.GetFilename() == "file.ext"
