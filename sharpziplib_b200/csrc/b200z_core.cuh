@@ -375,6 +375,27 @@ B200Z_HD bool fe_fill_window(FastEngine &e) { // :366-400
 	return true;
 }
 
+// four window bytes starting at window index w, first byte in the low bits.  The device reads two aligned words (the input
+// slot is 256-byte aligned and has 16 bytes of slack behind n); the host copy stays inside [0, n).
+B200Z_HD uint32_t fe_word(const FastEngine &e, int w) {
+	const uint32_t a = (uint32_t)(w - 1) + 32768u * e.slides;
+#ifdef __CUDA_ARCH__
+	const uint32_t *p = reinterpret_cast<const uint32_t *>(e.in + (a & ~3u));
+	return __funnelshift_r(p[0], p[1], (a & 3u) * 8u);
+#else
+	uint32_t v = 0;
+	for (uint32_t k = 0; k < 4 && a + k < e.n; k++) v |= (uint32_t)e.in[a + k] << (8 * k);
+	return v;
+#endif
+}
+B200Z_HD uint32_t fe_ctz(uint32_t x) {
+#ifdef __CUDA_ARCH__
+	return (uint32_t)(__ffs((int)x) - 1);
+#else
+	return (uint32_t)__builtin_ctz(x);
+#endif
+}
+
 B200Z_HDN bool fe_find_longest_match(FastEngine &e, int curMatch, const LevelParams &lp) { // :474-612
 	const int scan0 = e.strstart;
 	const int maxlen = e.lookahead < kMaxMatch ? e.lookahead : kMaxMatch;
@@ -385,13 +406,24 @@ B200Z_HDN bool fe_find_longest_match(FastEngine &e, int curMatch, const LevelPar
 	if (e.matchLen < kMinMatch - 1) e.matchLen = kMinMatch - 1;
 	if (scan0 + e.matchLen > scanMax) return false;
 	uint32_t scan_end1 = fe_win(e, scan0 + e.matchLen - 1), scan_end = fe_win(e, scan0 + e.matchLen);
+	const uint32_t s0 = fe_win(e, scan0), s1 = fe_win(e, scan0 + 1);
 	if (e.matchLen >= lp.good) chainLength >>= 2;
 	do {
 		const int match = curMatch;
 		if (fe_win(e, match + e.matchLen) == scan_end && fe_win(e, match + e.matchLen - 1) == scan_end1 &&
-		    fe_win(e, match) == fe_win(e, scan0) && fe_win(e, match + 1) == fe_win(e, scan0 + 1)) {
+		    fe_win(e, match) == s0 && fe_win(e, match + 1) == s1) {
+			// the reference extends byte by byte (:548-590); four bytes per compare give the same length
 			int l = 2;
+			while (l + 4 <= maxlen) {
+				const uint32_t x = fe_word(e, match + l) ^ fe_word(e, scan0 + l);
+				if (x) {
+					l += (int)(fe_ctz(x) >> 3);
+					goto extended;
+				}
+				l += 4;
+			}
 			while (l < maxlen && fe_win(e, match + l) == fe_win(e, scan0 + l)) ++l;
+		extended:
 			if (l > e.matchLen) {
 				e.matchStart = curMatch;
 				e.matchLen = l;
