@@ -187,3 +187,23 @@ def test_model_flush_continue(model, oracle):
     for level in (5, 6, 9):
         for ci, segs in enumerate(cases):
             assert _model_segments(level, segs) == _oracle_segments(oracle, level, segs), (level, ci)
+
+
+def test_model_random_segments_and_dictionaries(model, oracle):
+    """seeded random call sequences: [SetDictionary] (SetInput, Flush)* SetInput, Finish with cuts at and around the window
+    slide positions, levels 5-9, all strategies -- the segment bookkeeping of the Deflater handle over the kernel model"""
+    import random
+    from sharpziplib_b200 import datagen
+    rnd = random.Random(77)
+    special = [32768, 65272, 65273, 65274, 98041, 98042]
+    for trial in range(14):
+        n = rnd.choice([3000, 70000, 140000])
+        d = datagen.silesia_mix(rnd.randrange(8), n, config=rnd.randrange(1, 9)).tobytes()
+        cuts = sorted(min(len(d), rnd.choice([rnd.randrange(0, len(d) + 1)] + special)) for _ in range(rnd.randrange(1, 6)))
+        segs = [d[a:b] for a, b in zip([0] + cuts, cuts + [len(d)])]
+        level, strat = rnd.choice([5, 6, 7, 8, 9]), rnd.choice([0, 0, 0, 1, 2])
+        dic = d[:rnd.choice([5, 1000, 32506, 50000])] if rnd.random() < 0.4 else None
+        ref = _oracle_segments(oracle, level, segs, dictionary=dic, strategy=strat)
+        if dic is not None:
+            ref = ref[6:-4]
+        assert _model_segments(level, segs, dictionary=dic, strategy=strat) == ref, (trial, n, cuts, level, strat)
