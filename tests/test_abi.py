@@ -58,3 +58,13 @@ def test_no_cpu_fallback():
     with pytest.raises(z.B200zCudaError):
         c = z.Crc32()
         c.Update(b"123456789")
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/b200z.h is what a cgo / P/Invoke / ctypes binding declares: it must compile as C99, no C++ in the signatures"""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "abi_check.c"
+    src.write_text('#include "b200z.h"\nint main(void) { b200z_history h; (void)h; return b200z_version() > 0 ? 0 : 1; }\n')
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only",
+                           "-I", os.path.join(root, "include"), str(src)])
