@@ -78,6 +78,42 @@ uint32_t szl_adler32_bytewise(const uint8_t *buf, uint64_t n) {
 	return a.Value();
 }
 
+// ---- the test inputs of the reference's own tests ---------------------------------------------
+// .NET's seeded System.Random (Knuth's subtractive generator; `new Random(seed).NextBytes(buf)`), which the reference's
+// tests use for their data: Utils.GetDummyBytes (test/.../TestSupport/Utils.cs:79-85, seed 5) and the 256 MiB Adler-32
+// known-answer test (test/.../Checksum/ChecksumTests.cs:41-64, seed 1).  Not part of SharpZipLib: restated from the
+// published algorithm (Numerical Recipes ran3 as .NET seeds it) and pinned by that Adler-32 value in tests/test_oracle.py.
+void szl_dotnet_random_bytes(int32_t seed, uint8_t *out, uint64_t n) {
+	const int32_t MBIG = 2147483647, MSEED = 161803398;
+	int32_t sa[56] = {0};
+	const int32_t sub = seed == INT32_MIN ? MBIG : (seed < 0 ? -seed : seed);
+	int32_t mj = MSEED - sub, mk = 1;
+	sa[55] = mj;
+	for (int i = 1; i < 55; i++) {
+		const int ii = (21 * i) % 55;
+		sa[ii] = mk;
+		mk = mj - mk;
+		if (mk < 0) mk += MBIG;
+		mj = sa[ii];
+	}
+	for (int k = 1; k < 5; k++)
+		for (int i = 1; i < 56; i++) {
+			// the subtraction wraps like C#'s unchecked int arithmetic
+			sa[i] = (int32_t)((uint32_t)sa[i] - (uint32_t)sa[1 + (i + 30) % 55]);
+			if (sa[i] < 0) sa[i] += MBIG;
+		}
+	int inext = 0, inextp = 21;
+	for (uint64_t j = 0; j < n; j++) {
+		if (++inext >= 56) inext = 1;
+		if (++inextp >= 56) inextp = 1;
+		int32_t r = (int32_t)((uint32_t)sa[inext] - (uint32_t)sa[inextp]);
+		if (r == MBIG) r--;
+		if (r < 0) r += MBIG;
+		sa[inext] = r;
+		out[j] = (uint8_t)r; // NextBytes: (byte)InternalSample()
+	}
+}
+
 // ---- Deflater handle ------------------------------------------------------------------------
 int szl_deflater_new(int level, int nowrap, void **out) {
 	SZL_TRY

@@ -134,6 +134,16 @@ def adler32_update(value, data):
     return lib().szl_adler32_update(value, a.ctypes.data, a.size)
 
 
+def dotnet_random_bytes(seed, n):
+    """`new System.Random(seed).NextBytes(new byte[n])` -- the data source of the reference's own tests."""
+    out = np.empty(n, np.uint8)
+    f = lib().szl_dotnet_random_bytes
+    f.restype = None
+    f.argtypes = [C.c_int32, C.c_void_p, C.c_uint64]
+    f(seed, out.ctypes.data, n)
+    return out
+
+
 def deflate_bound(n):
     return n + (n >> 3) + 1024
 

@@ -476,8 +476,7 @@ def test_plans_on_device_tensors(z, oracle):
 def test_inflate_deflate_roundtrip_like_reference(z, oracle, level, zlib_wrap):
     """InflaterDeflaterTests.InflateDeflateZlib / NonZlib (:157-162, :226-231): 100000 random bytes,
     Write(all) -> Flush() -> Finish(), read back through InflaterInputStream."""
-    from sharpziplib_b200 import datagen
-    original = datagen.Rng(5).bytes(100000).tobytes()
+    original = oracle.dotnet_random_bytes(5, 100000).tobytes()  # Utils.GetDummyBytes(100000): new Random(5).NextBytes
     ms = io.BytesIO()
     out = z.DeflaterOutputStream(ms, z.Deflater(level, not zlib_wrap))
     out.IsStreamOwner = False

@@ -34,6 +34,27 @@ def test_checksum_vs_zlib_and_bytewise(oracle):
         assert oracle.adler32_update(oracle.adler32(d[:n // 2]), d[n // 2:]) == zlib.adler32(d)
 
 
+def test_adler32_256mib_dotnet_random_kat(oracle):
+    """ChecksumTests.Adler_32_Performance (test/.../Checksum/ChecksumTests.cs:41-64): Adler-32 of 256 MiB from
+    `new Random(1).NextBytes`, then of "123456789", must be 0xD4897DA3.  Pins both the oracle's Adler32 on a long
+    input (deferred modulo, Adler32.cs:134-161) and the restated System.Random the other reference-shaped tests use."""
+    buf = oracle.dotnet_random_bytes(1, 256 * 1024 * 1024)
+    a = oracle.adler32(buf)
+    assert oracle.adler32_update(a, b"123456789") == 0xD4897DA3
+
+
+@pytest.mark.parametrize("nowrap", [False, True])
+def test_inflate_deflate_reference_shape(oracle, nowrap):
+    """InflaterDeflaterTests.InflateDeflateZlib / NonZlib (test/.../Base/InflaterDeflaterTests.cs:157-162, :226-231)
+    on the reference's own input, Utils.GetDummyBytes(100000) = Random(5): Write(all) -> Flush() -> Finish()."""
+    original = oracle.dotnet_random_bytes(5, 100000).tobytes()
+    for level in range(10):
+        comp = oracle.deflate(original, level=level, nowrap=nowrap, pattern=1)
+        assert zlib.decompress(comp, -15 if nowrap else 15) == original
+        back, rem, fin = oracle.inflate(comp, nowrap=nowrap, max_out=len(original) + 64)
+        assert back == original and fin and rem == 0
+
+
 def test_inflater_reference_fixture(oracle):
     raw = bytes.fromhex(GOLD["inflate_ok"]["raw_hex"])
     out, remaining, finished = oracle.inflate(raw)
