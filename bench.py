@@ -470,7 +470,7 @@ def main():
     # ---- CPU baseline: the oracle on one host core, bounded sample ----------------------------------------------
     cpu = None
     if rank == 0:
-        ns_d, ns_i = min(n_def, 128), min(n_inf, 64)
+        ns_d, ns_i = n_def, n_inf  # the whole step once on one core: ~10 s (128 / 64 buffers took 1.4 s, too short a sample)
         r = CpuSample(ns_d, ns_i, d_np, comp, [a.size for a in t_np]).run(1)
         cpu = {"value": r["value"], "unit": "GB/s", "cores": 1, "kind": "port",
                "sample": "%d x 256 KiB deflate L6 + %d x 1 MiB inflate, single thread, %.1f s" % (ns_d, ns_i, r["seconds"]),

@@ -108,6 +108,15 @@ int b200z_inflate_plan_create(int32_t n, const int64_t *comp_len, const int64_t 
  * where the dictionary starts, b200z_plan_data_offset(i) where the compressed bytes start (16-byte aligned). */
 int b200z_inflate_plan_create_ex(int32_t n, const int64_t *comp_len, const int64_t *out_cap, int wrap,
                                  const int64_t *dict_len, b200z_plan **plan);
+/* Decoding a stream in pieces (what Inflater does between SetInput calls, Inflater.cs:73-86 / :429-552: its mode machine
+ * stops anywhere and resumes).  Across a block boundary the decoder carries only the window (= the last 32 KiB of
+ * output) and the bit position, so a raw inflate plan can start in the middle of a stream: at bit start_bit[i] (0..7) of
+ * the first compressed byte handed over, a block header, with the window image passed as the "dictionary".  After a run,
+ * restart points tell where the last block header the decoder reached lies: bit[i] (counted from the first compressed
+ * byte of the slot) and out_pos[i] (bytes of output in front of it).  A stream that ended with B200Z_E_NEED_INPUT is
+ * continued from there once more input has arrived.  Host arrays of n entries; get_restart_points synchronises the stream. */
+int b200z_inflate_plan_set_start_bits(b200z_plan *plan, const int32_t *start_bit);
+int b200z_plan_get_restart_points(b200z_plan *plan, int64_t *bit, int64_t *out_pos, void *cuda_stream);
 int b200z_plan_destroy(b200z_plan *plan);
 int64_t b200z_plan_in_bytes(const b200z_plan *plan);          /* size of the input blob  */
 int64_t b200z_plan_out_bytes(const b200z_plan *plan);         /* size of the output blob */

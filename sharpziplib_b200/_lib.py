@@ -74,6 +74,8 @@ _SIGS = {
                                                C.POINTER(C.c_void_p)]),
     "b200z_inflate_plan_create": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]),
     "b200z_inflate_plan_create_ex": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "b200z_inflate_plan_set_start_bits": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "b200z_plan_get_restart_points": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "b200z_plan_data_offset": (C.c_int64, [C.c_void_p, C.c_int32]),
     "b200z_plan_destroy": (C.c_int, [C.c_void_p]),
     "b200z_plan_in_bytes": (C.c_int64, [C.c_void_p]),

@@ -102,6 +102,23 @@ class InflatePlan(_Plan):
         self.comp_lens, self.out_caps = cl, oc
         super().__init__(h, cl.size)
 
+    def set_start_bits(self, start_bits):
+        """Raw plans: stream i's first block header starts at bit start_bits[i] (0..7) of its first compressed byte --
+        decoding a stream on from a restart point, with the window image passed as the dictionary."""
+        sb = np.ascontiguousarray(start_bits, dtype=np.int32)
+        assert sb.size == self.n
+        _lib.raise_for(_lib.lib().b200z_inflate_plan_set_start_bits(self._h, sb.ctypes.data))
+
+    def restart_points(self, stream=None):
+        """(bit, out_pos) int64 arrays of the last run: where the last block header each stream's decoder reached lies
+        (bits from the first compressed byte of the slot; output bytes in front of it).  Synchronises the stream."""
+        import torch
+        s = stream if stream is not None else torch.cuda.current_stream()
+        bit = np.zeros(self.n, dtype=np.int64)
+        pos = np.zeros(self.n, dtype=np.int64)
+        _lib.raise_for(_lib.lib().b200z_plan_get_restart_points(self._h, bit.ctypes.data, pos.ctypes.data, s.cuda_stream))
+        return bit, pos
+
 
 def _ptr_array(arrs):
     return (C.c_void_p * len(arrs))(*[a.ctypes.data if a.size else None for a in arrs])

@@ -366,6 +366,45 @@ int b200z_inflate_plan_create_ex(int32_t n, const int64_t *comp_len, const int64
 	return B200Z_OK;
 }
 
+int b200z_inflate_plan_set_start_bits(b200z_plan *plan, const int32_t *start_bit) {
+	if (!plan || plan->kind != 1 || (plan->n > 0 && !start_bit)) {
+		set_error("bad arguments");
+		return B200Z_E_ARG;
+	}
+	if (plan->wrap != B200Z_WRAP_RAW && plan->wrap != B200Z_WRAP_RAW_CRC32) {
+		set_error("start bits are for raw streams (a framed stream starts behind its header)");
+		return B200Z_E_ARG;
+	}
+	std::vector<uint32_t> sb((size_t)plan->n);
+	for (int i = 0; i < plan->n; i++) {
+		if (start_bit[i] < 0 || start_bit[i] > 7) {
+			set_error("stream %d: start bit %d (0..7)", i, start_bit[i]);
+			return B200Z_E_ARG;
+		}
+		sb[(size_t)i] = (uint32_t)start_bit[i];
+	}
+	if (plan->n) B200Z_CUDA(cudaMemcpy(plan->ws.at<uint32_t>(plan->o_start_bit), sb.data(), 4ull * plan->n, cudaMemcpyHostToDevice));
+	plan->has_start_bits = true;
+	return B200Z_OK;
+}
+
+int b200z_plan_get_restart_points(b200z_plan *plan, int64_t *bit, int64_t *out_pos, void *cuda_stream) {
+	if (!plan || plan->kind != 1 || (plan->n > 0 && (!bit || !out_pos))) {
+		set_error("bad arguments");
+		return B200Z_E_ARG;
+	}
+	if (plan->n == 0) return B200Z_OK;
+	std::vector<int64_t> rp(2 * (size_t)plan->n);
+	cudaStream_t s = (cudaStream_t)cuda_stream;
+	B200Z_CUDA(cudaMemcpyAsync(rp.data(), plan->ws.at<int64_t>(plan->o_restart), 16ull * plan->n, cudaMemcpyDeviceToHost, s));
+	B200Z_CUDA(cudaStreamSynchronize(s));
+	for (int i = 0; i < plan->n; i++) {
+		bit[i] = rp[2 * (size_t)i];
+		out_pos[i] = rp[2 * (size_t)i + 1];
+	}
+	return B200Z_OK;
+}
+
 int b200z_plan_set_timing(b200z_plan *plan, int enable) {
 	if (!plan) return B200Z_E_ARG;
 	plan->timing = enable != 0;
@@ -959,24 +998,37 @@ int b200z_deflater_adler(void *h, uint32_t *v) {
 }
 
 // ---- Inflater handle ----------------------------------------------------------------------------------
+// The reference's Inflater is a mode machine that stops at any bit and resumes (Inflater.cs:73-86, :429-552).  The kernel
+// decodes whole plans, so the handle resumes at BLOCK granularity: k_inflate reports the last block header it reached
+// (bit position, output position -- the "restart point"); when more input arrives decoding continues from that header
+// with the last 32 KiB of output in front of it as the window image.  Bytes of a block that was only partly available
+// are decoded again by the next run (they were already delivered; the new run's output replaces them byte for byte).
+// Work is linear in the stream for any SetInput granularity as long as blocks are bounded (the reference's own Deflater
+// cuts a block every 16384 symbols), and the handle holds one block of input / output plus the window, not the stream.
 struct InflaterH {
 	bool raw = false;
-	std::vector<uint8_t> input; // all compressed bytes handed over since Reset
+	std::vector<uint8_t> input; // compressed bytes from absolute offset in_base on (what lies in front of the restart point is dropped)
+	int64_t in_base = 0, in_total = 0; // in_total = bytes handed over since Reset = in_base + input.size()
 	bool new_input = false;
 	bool finished = false;
 	bool need_dict = false;
 	bool header_done = false;
 	uint32_t read_adler = 0;   // DICTID from the header (Inflater.readAdler)
-	std::vector<uint8_t> dict; // last <= 32768 bytes of the dictionary SetDictionary accepted
-	size_t raw_off = 0; // where the raw deflate data starts inside `input`
-	std::vector<uint8_t> output; // decoded so far
-	size_t delivered = 0;
-	int64_t consumed = 0; // bytes of `input` the decoder has used (header + raw + trailer)
+	int64_t raw_off = 0;       // where the raw deflate data starts (behind the zlib header)
+	int64_t rs_bit = 0;        // restart point: bit offset from raw_off of the block header decoding continues at
+	int64_t rs_out = 0;        //                output position of that header
+	std::vector<uint8_t> window; // last <= 32768 bytes of (dictionary ++ output[0, rs_out)): OutputWindow's contents there
+	uint32_t run_adler = 1;    // Adler-32 of output[0, rs_out)
+	std::vector<uint8_t> output; // decoded bytes from output position out_base on (delivered bytes in front of rs_out are dropped)
+	int64_t out_base = 0;
+	int64_t delivered = 0;
+	int64_t consumed = 0; // bytes of input the decoder has used (header + raw + trailer), absolute
 	uint32_t adler = 1;
 	int error = 0;
 	std::string error_msg;
 	PinnedBuf hin, hout;
 	DevBuf din, dout, dmeta;
+	int64_t out_total() const { return out_base + (int64_t)output.size(); }
 };
 
 static const char *inflate_detail_msg(int detail) {
@@ -1006,25 +1058,38 @@ static const char *inflate_detail_msg(int detail) {
 	}
 }
 
-// decodes everything available; fills output/consumed/finished
+// decodes from the restart point to the end of what is available; fills output / consumed / finished and moves the
+// restart point forward
 static int inflater_run_device(InflaterH *d) {
-	const int64_t avail = (int64_t)d->input.size() - (int64_t)d->raw_off;
+	const int64_t slice_abs = d->raw_off + (d->rs_bit >> 3); // absolute offset of the first compressed byte of this run
+	const int32_t sbit = (int32_t)(d->rs_bit & 7);
+	const int64_t avail = d->in_total - slice_abs;
+	if (avail < 0 || slice_abs < d->in_base) {
+		set_error("inflater restart point outside the kept input");
+		return B200Z_E_INTERNAL;
+	}
 	int64_t cap = avail * 8 + 65536;
 	for (int attempt = 0; attempt < 8; attempt++) {
 		b200z_plan *plan = nullptr;
-		const int64_t D = (int64_t)d->dict.size();
+		const int64_t D = (int64_t)d->window.size();
 		int rc = b200z_inflate_plan_create_ex(1, &avail, &cap, B200Z_WRAP_RAW, D ? &D : nullptr, &plan);
 		if (rc) return rc;
-		const uint8_t *inp = d->input.data() + d->raw_off;
+		if (sbit && (rc = b200z_inflate_plan_set_start_bits(plan, &sbit))) {
+			b200z_plan_destroy(plan);
+			return rc;
+		}
+		const uint8_t *inp = d->input.data() + (slice_abs - d->in_base);
 		std::vector<uint8_t> slot;
-		if (D) { // dictionary directly in front of the compressed bytes
+		if (D) { // window image (dictionary, earlier output) directly in front of the compressed bytes
 			slot.reserve((size_t)(D + avail));
-			slot.insert(slot.end(), d->dict.begin(), d->dict.end());
+			slot.insert(slot.end(), d->window.begin(), d->window.end());
 			slot.insert(slot.end(), inp, inp + avail);
 			inp = slot.data();
 		}
 		HostRunResult r;
 		rc = run_plan_host(plan, &inp, d->hin, d->hout, d->din, d->dout, d->dmeta, r, false);
+		int64_t rbit = 0, rout = 0;
+		if (!rc) rc = b200z_plan_get_restart_points(plan, &rbit, &rout, nullptr);
 		if (rc) {
 			b200z_plan_destroy(plan);
 			return rc;
@@ -1035,21 +1100,59 @@ static int inflater_run_device(InflaterH *d) {
 			cap *= 8;
 			continue;
 		}
-		d->output.assign(d->hout.p + plan->out_off[0], d->hout.p + plan->out_off[0] + r.out_len[0]);
+		// this run's output is output[rs_out, rs_out + out_len): it replaces what an earlier run decoded behind the
+		// restart point (the same bytes, and at least as many)
+		const uint8_t *o = d->hout.p + plan->out_off[0];
+		d->output.resize((size_t)(d->rs_out - d->out_base));
+		d->output.insert(d->output.end(), o, o + r.out_len[0]);
 		b200z_plan_destroy(plan);
 		if (st == B200Z_OK) {
 			d->finished = true;
-			d->consumed = (int64_t)d->raw_off + r.in_used[0];
+			d->consumed = slice_abs + r.in_used[0];
 		} else if (st == B200Z_E_NEED_INPUT) {
-			d->consumed = (int64_t)d->input.size();
+			d->consumed = d->in_total;
 		} else {
 			d->error = st;
 			d->error_msg = inflate_detail_msg(detail);
+			return B200Z_OK;
+		}
+		if (rout < 0 || rout > r.out_len[0] || rbit < sbit || rbit > 8 * avail) {
+			set_error("inflater restart point out of range");
+			return B200Z_E_INTERNAL;
+		}
+		if (rout > 0 || rbit != sbit) {
+			// move the restart point: checksum and window advance over output[rs_out, rs_out + rout)
+			const uint8_t *seg = d->output.data() + (d->rs_out - d->out_base);
+			if (!d->raw && rout > 0 && (rc = b200z_adler32(seg, rout, &d->run_adler))) return rc;
+			if (rout >= 32768) d->window.assign(seg + rout - 32768, seg + rout);
+			else {
+				d->window.insert(d->window.end(), seg, seg + rout);
+				if (d->window.size() > 32768) d->window.erase(d->window.begin(), d->window.end() - 32768);
+			}
+			d->rs_out += rout;
+			d->rs_bit = (d->rs_bit & ~7ll) + rbit;
+		}
+		if (st == B200Z_E_NEED_INPUT) {
+			// compressed bytes in front of the restart point are never looked at again
+			const int64_t keep_from = d->raw_off + (d->rs_bit >> 3);
+			if (keep_from > d->in_base) {
+				d->input.erase(d->input.begin(), d->input.begin() + (keep_from - d->in_base));
+				d->in_base = keep_from;
+			}
 		}
 		return B200Z_OK;
 	}
 	set_error("output larger than any capacity tried");
 	return B200Z_E_NOMEM;
+}
+
+// output in front of both the restart point and the delivery position is not needed any more
+static void inflater_trim_output(InflaterH *d) {
+	const int64_t keep_from = d->delivered < d->rs_out ? d->delivered : d->rs_out;
+	if (keep_from - d->out_base >= 65536) {
+		d->output.erase(d->output.begin(), d->output.begin() + (keep_from - d->out_base));
+		d->out_base = keep_from;
+	}
 }
 
 int b200z_inflater_create(int raw, void **h) {
@@ -1070,14 +1173,18 @@ int b200z_inflater_reset(void *h) {
 	InflaterH *d = (InflaterH *)h;
 	d->input.clear();
 	d->output.clear();
+	d->window.clear();
 	d->new_input = d->finished = d->need_dict = d->header_done = false;
+	d->in_base = d->in_total = 0;
 	d->raw_off = 0;
+	d->rs_bit = d->rs_out = 0;
+	d->run_adler = 1;
+	d->out_base = 0;
 	d->delivered = 0;
 	d->consumed = 0;
 	d->adler = 1;
 	d->error = 0;
 	d->read_adler = 0;
-	d->dict.clear();
 	return B200Z_OK;
 }
 int b200z_inflater_set_dictionary(void *h, const uint8_t *dict, int32_t len) {
@@ -1101,7 +1208,7 @@ int b200z_inflater_set_dictionary(void *h, const uint8_t *dict, int32_t len) {
 		return B200Z_E_DATA;
 	}
 	const int32_t keep = len > 32768 ? 32768 : len; // OutputWindow.CopyDict :160-166
-	d->dict.assign(dict + (len - keep), dict + len);
+	d->window.assign(dict + (len - keep), dict + len);
 	d->need_dict = false;
 	d->adler = 1;
 	d->new_input = true; // what was handed over behind the header can be decoded now
@@ -1113,15 +1220,17 @@ int b200z_inflater_set_input(void *h, const uint8_t *buf, int32_t len) {
 		set_error("buffer/count");
 		return B200Z_E_ARG;
 	}
-	if ((int64_t)d->input.size() > d->consumed && !d->finished) {
+	if (d->in_total > d->consumed && !d->finished) {
 		set_error("Old input was not completely processed"); // StreamManipulator.cs:263
 		return B200Z_E_STATE;
 	}
 	if (d->finished) {
 		// after the end of the stream the reference keeps unread bytes as RemainingInput; replace them
-		d->input.resize((size_t)d->consumed);
+		d->input.resize((size_t)(d->consumed - d->in_base));
+		d->in_total = d->consumed;
 	}
 	d->input.insert(d->input.end(), buf, buf + len);
+	d->in_total += len;
 	d->new_input = true;
 	return B200Z_OK;
 }
@@ -1140,6 +1249,7 @@ int b200z_inflater_inflate(void *h, uint8_t *out, int32_t cap, int32_t *produced
 	if (!d->finished && d->new_input) {
 		d->new_input = false;
 		if (!d->raw && !d->header_done) {
+			// (nothing is dropped from `input` before the header is done: in_base == 0 here)
 			if (d->input.size() < 2) {
 				d->consumed = (int64_t)d->input.size();
 				return B200Z_OK; // DecodeHeader needs 16 bits (Inflater.cs:209-215)
@@ -1179,22 +1289,21 @@ int b200z_inflater_inflate(void *h, uint8_t *out, int32_t cap, int32_t *produced
 			d->new_input = true;
 			return B200Z_OK;
 		}
-		const size_t had = d->delivered;
 		int rc = inflater_run_device(d);
 		if (rc) return rc;
-		(void)had;
 		if (d->finished && !d->raw) {
 			// Adler32 trailer, read MSB first (DecodeChksum :397-418); until it is complete the reference withholds
 			// nothing that was already decoded but is not "finished"
-			if ((int64_t)d->input.size() - d->consumed < 4) {
+			if (d->in_total - d->consumed < 4) {
 				d->finished = false;
-				d->consumed = (int64_t)d->input.size();
-				// keep output; it will be re-derived when the trailer arrives
+				d->consumed = d->in_total;
+				// keep output; the last block is decoded again when the trailer arrives
 			} else {
-				const uint8_t *t = d->input.data() + d->consumed;
+				const uint8_t *t = d->input.data() + (d->consumed - d->in_base);
 				const uint32_t want = ((uint32_t)t[0] << 24) | ((uint32_t)t[1] << 16) | ((uint32_t)t[2] << 8) | t[3];
-				uint32_t got = 1;
-				int rc2 = b200z_adler32(d->output.data(), (int64_t)d->output.size(), &got);
+				uint32_t got = d->run_adler; // output[0, rs_out) is in it already
+				const int64_t rest = d->out_total() - d->rs_out;
+				int rc2 = rest > 0 ? b200z_adler32(d->output.data() + (d->rs_out - d->out_base), rest, &got) : B200Z_OK;
 				if (rc2) return rc2;
 				d->adler = got;
 				if (got != want) {
@@ -1205,11 +1314,12 @@ int b200z_inflater_inflate(void *h, uint8_t *out, int32_t cap, int32_t *produced
 			}
 		}
 	}
-	size_t avail = d->output.size() - d->delivered;
+	size_t avail = (size_t)(d->out_total() - d->delivered);
 	size_t take = avail < (size_t)cap ? avail : (size_t)cap;
-	if (take) memcpy(out, d->output.data() + d->delivered, take);
-	d->delivered += take;
+	if (take) memcpy(out, d->output.data() + (d->delivered - d->out_base), take);
+	d->delivered += (int64_t)take;
 	*produced = (int32_t)take;
+	inflater_trim_output(d);
 	if (take == 0 && d->error) {
 		set_error("%s", d->error_msg.c_str());
 		return d->error;
@@ -1218,7 +1328,7 @@ int b200z_inflater_inflate(void *h, uint8_t *out, int32_t cap, int32_t *produced
 }
 int b200z_inflater_needs_input(void *h, int *flag) {
 	InflaterH *d = (InflaterH *)h;
-	*flag = ((int64_t)d->input.size() <= d->consumed) ? 1 : 0; // StreamManipulator.IsNeedingInput
+	*flag = (d->in_total <= d->consumed) ? 1 : 0; // StreamManipulator.IsNeedingInput
 	return B200Z_OK;
 }
 int b200z_inflater_needs_dictionary(void *h, int *flag) {
@@ -1227,12 +1337,12 @@ int b200z_inflater_needs_dictionary(void *h, int *flag) {
 }
 int b200z_inflater_is_finished(void *h, int *flag) {
 	InflaterH *d = (InflaterH *)h;
-	*flag = (d->finished && d->delivered == d->output.size()) ? 1 : 0; // Inflater.cs:806-812
+	*flag = (d->finished && d->delivered == d->out_total()) ? 1 : 0; // Inflater.cs:806-812
 	return B200Z_OK;
 }
 int b200z_inflater_remaining_input(void *h, int32_t *v) {
 	InflaterH *d = (InflaterH *)h;
-	*v = (int32_t)((int64_t)d->input.size() - d->consumed);
+	*v = (int32_t)(d->in_total - d->consumed);
 	return B200Z_OK;
 }
 int b200z_inflater_total_in(void *h, int64_t *v) {
@@ -1240,7 +1350,7 @@ int b200z_inflater_total_in(void *h, int64_t *v) {
 	return B200Z_OK;
 }
 int b200z_inflater_total_out(void *h, int64_t *v) {
-	*v = (int64_t)((InflaterH *)h)->delivered;
+	*v = ((InflaterH *)h)->delivered;
 	return B200Z_OK;
 }
 int b200z_inflater_adler(void *h, uint32_t *v) {

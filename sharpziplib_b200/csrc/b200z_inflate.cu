@@ -330,7 +330,8 @@ __global__ void __launch_bounds__(kInfThreads)
     k_inflate(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, const int64_t *__restrict__ in_off,
               const int64_t *__restrict__ in_len, const int64_t *__restrict__ out_off, const int64_t *__restrict__ out_cap,
               int nstreams, int64_t *__restrict__ out_len, int64_t *__restrict__ in_used, int32_t *__restrict__ status,
-              const uint32_t *__restrict__ dict_len, const uint32_t *__restrict__ start_bit, const int32_t *__restrict__ pre) {
+              const uint32_t *__restrict__ dict_len, const uint32_t *__restrict__ start_bit, const int32_t *__restrict__ pre,
+              int64_t *__restrict__ restart) {
 	extern __shared__ __align__(16) uint8_t smem_raw[];
 	InfBlockShared &S = *reinterpret_cast<InfBlockShared *>(smem_raw);
 	const int lane = threadIdx.x & 31;
@@ -342,6 +343,8 @@ __global__ void __launch_bounds__(kInfThreads)
 			status[stream] = pre[stream];
 			out_len[stream] = 0;
 			if (in_used) in_used[stream] = 0;
+			restart[2 * stream] = 0;
+			restart[2 * stream + 1] = 0;
 		}
 		return;
 	}
@@ -382,6 +385,10 @@ __global__ void __launch_bounds__(kInfThreads)
 	int st = B200Z_OK, detail = 0;
 	bool last = false, in_block = false, a_done = false, pending_stored = false;
 	uint32_t stored_len = 0;
+	// restart point: bit position of the last block header reached and the output position there.  A caller that only
+	// has part of a stream (the Inflater handle between SetInput calls) decodes on from this header instead of from the
+	// start: everything the decoder carries across a block boundary is the window (the output) and the bit position.
+	uint64_t rs_bit = bitpos, rs_out = 0;
 	int tab = 0, static_in = -1; // static_in: which table buffer currently holds the static tables (-1 none)
 
 	for (uint32_t t = 0;; t++) {
@@ -418,6 +425,10 @@ __global__ void __launch_bounds__(kInfThreads)
 						// ---- block header (lane 0) -------------------------------------------------------
 						int btype = 0;
 						const int ntab = tab ^ 1; // B may still be decoding the previous round with `tab`
+						if (!last) {
+							rs_bit = bitpos;
+							rs_out = opos;
+						}
 						if (lane == 0) {
 							// re-seat the header reader at the true bit position
 							br.consumed = bitpos;
@@ -743,6 +754,8 @@ __global__ void __launch_bounds__(kInfThreads)
 			if (used > br.nbytes) used = br.nbytes;
 			in_used[stream] = (int64_t)used;
 		}
+		restart[2 * stream] = (int64_t)rs_bit;
+		restart[2 * stream + 1] = (int64_t)rs_out;
 	}
 }
 
@@ -891,6 +904,7 @@ int inflate_plan_build(b200z_plan *p) {
 	p->o_hist = ws.reserve(4ll * (n + 1));
 	p->o_start_bit = ws.reserve(4ll * (n + 1));
 	p->o_pre = ws.reserve(4ll * (n + 1));
+	p->o_restart = ws.reserve(16ll * (n + 1));
 	std::vector<CkTile> ck_tiles;
 	if (p->wrap != B200Z_WRAP_RAW) {
 		// checksum of the OUTPUT (Adler-32 for zlib, CRC-32 for gzip and raw+CRC): tiles over the capacities, the kernel takes
@@ -929,7 +943,7 @@ int inflate_plan_run(b200z_plan *p, const uint8_t *d_in, uint8_t *d_out, int64_t
 		return B200Z_E_ARG;
 	}
 	const int64_t *in_off = ws.at<int64_t>(p->o_in_off), *in_len = ws.at<int64_t>(p->o_in_len);
-	uint32_t *start_bit = framed ? ws.at<uint32_t>(p->o_start_bit) : nullptr;
+	uint32_t *start_bit = (framed || p->has_start_bits) ? ws.at<uint32_t>(p->o_start_bit) : nullptr;
 	int32_t *pre = framed ? ws.at<int32_t>(p->o_pre) : nullptr;
 	if (framed) {
 		p->mark(s, "k_wrap");
@@ -937,7 +951,8 @@ int inflate_plan_run(b200z_plan *p, const uint8_t *d_in, uint8_t *d_out, int64_t
 	}
 	p->mark(s, "k_inflate");
 	k_inflate<<<n, kInfThreads, kInfSmem2, s>>>(d_in, d_out, in_off, in_len, ws.at<int64_t>(p->o_out_off), ws.at<int64_t>(p->o_out_cap),
-	                                           n, d_out_len, d_in_used, d_status, ws.at<uint32_t>(p->o_hist), start_bit, pre);
+	                                           n, d_out_len, d_in_used, d_status, ws.at<uint32_t>(p->o_hist), start_bit, pre,
+	                                           ws.at<int64_t>(p->o_restart));
 	if (wrap != B200Z_WRAP_RAW) {
 		p->mark(s, "checksum");
 		int rc = checksum_launch(wrap == B200Z_WRAP_ZLIB ? 1 : 0, d_out, ws.at<int64_t>(p->o_out_off), d_out_len, n,

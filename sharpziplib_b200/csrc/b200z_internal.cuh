@@ -98,6 +98,8 @@ struct b200z_plan {
 	// inflate workspace offsets
 	int64_t o_tok = 0, o_ntok = 0, o_tok_off = 0;
 	int64_t o_start_bit = 0, o_pre = 0; // inflate framing: first deflate bit and header verdict per stream
+	int64_t o_restart = 0;              // inflate: per stream (bit, output position) of the last block header reached
+	bool has_start_bits = false;        // raw inflate plans: caller-supplied first bit (b200z_inflate_plan_set_start_bits)
 	// checksum scratch
 	int64_t o_ck_desc = 0, o_ck_acc = 0;
 	int n_ck_tiles = 0;
