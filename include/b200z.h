@@ -77,7 +77,16 @@ typedef struct b200z_plan b200z_plan;
  *                          MIN_MATCH are ignored by the reference, pass hist_len 0 for them.  All levels.
  *   B200Z_HIST_CONTINUE    more input after Deflater.Flush() (Deflater.cs:488-506 leaves the engine re-entrant): the
  *                          history is the last min(32768, bytes so far) bytes of everything the window has seen
- *                          (dictionary included).  Levels 5-9 (DeflateSlow) only, B200Z_E_UNSUPPORTED below.
+ *                          (dictionary included).  Levels 5-9 (DeflateSlow) need nothing else; DeflateFast (1-4) and
+ *                          DeflateStored (0) keep window-relative state across Deflate() calls that is not a function of
+ *                          the stream position (DeflaterEngine.cs:80-94: head/prev, strstart, blockStart), so every
+ *                          segment of such a stream must be run with engine_state / stored_state (below), which the
+ *                          run of one segment fills and the run of the next one reads; B200Z_E_UNSUPPORTED without.
+ * Levels 0-4 also depend on HOW the data arrives (SURVEY.md trap T9: FillWindow slides at strstart >= 65274 whenever it is
+ * called, DeflateFast at > 65274; DeflateStored cuts blocks by what it has seen so far): chunk_count / chunk_len give the
+ * SetInput calls that delivered a stream's data, each followed by Deflate() until IsNeedingInput as DeflaterOutputStream
+ * .Write does (Streams/DeflaterOutputStream.cs:506-510); without them one SetInput with everything is assumed.  Levels 5-9
+ * ignore the schedule (their output does not depend on it).
  * Input slot i of such a plan holds hist_len[i] history bytes directly followed by the in_len[i] data bytes;
  * b200z_plan_in_offset(i) is the start of the history.  The checksum covers the data only; with check_seeded the
  * d_check array handed to b200z_plan_run carries the running values in and the updated values out (Adler32.Update /
@@ -96,7 +105,22 @@ typedef struct b200z_history {
 	const uint8_t *const *hist_mask; /* [n] hist_len[i] flags, 1 = position was never entered into the hash chains
 	                                   (InsertString needs MIN_MATCH bytes of lookahead, :782/:819: the last two positions
 	                                   of every earlier segment); NULL entry = the last two history positions */
+	/* ---- levels 0-4 (all optional; kind may be B200Z_HIST_NONE, hist_len then may be NULL) ---- */
+	const int32_t *chunk_count;     /* [n] number of SetInput calls that delivered stream i's data; NULL or 0 = one */
+	const int64_t *const *chunk_len; /* [n] chunk_count[i] sizes (>= 0) summing to in_len[i] */
+	const int32_t *undrained_last;  /* [n] != 0: Flush() / Finish() came right behind the last SetInput, no Deflate() call in
+	                                   between (a raw Deflater user; the stream classes always drain); NULL = 0 */
+	void *const *engine_state;      /* [n] levels 1-4: DEVICE buffers of b200z_engine_state_bytes() bytes, one per stream:
+	                                   head[], prev[] and DeflateFast's scalars, written at the end of every run, read at
+	                                   the start of a B200Z_HIST_CONTINUE run */
+	struct b200z_stored_state *stored_state; /* [n] level 0: HOST array, read by a B200Z_HIST_CONTINUE plan when it is
+	                                   created and overwritten with the state behind this segment */
 } b200z_history;
+typedef struct b200z_stored_state { /* DeflateStored's fields between Deflate() calls (DeflaterEngine.cs:614-649) */
+	int32_t strstart, block_start;
+	uint32_t slides, input_off;
+} b200z_stored_state;
+int64_t b200z_engine_state_bytes(void);
 int b200z_deflate_plan_create_ex(int32_t n, const int64_t *in_len, int level, int strategy, int wrap, int end_mode,
                                  const b200z_history *hist, b200z_plan **plan);
 

@@ -94,6 +94,7 @@ _SIGS = {
     "b200z_deflate_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "b200z_inflate_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "b200z_deflate_bound": (C.c_int64, [C.c_int64]),
+    "b200z_engine_state_bytes": (C.c_int64, []),
     "b200z_deflater_create": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     "b200z_deflater_destroy": (C.c_int, [C.c_void_p]),
     "b200z_deflater_reset": (C.c_int, [C.c_void_p]),
@@ -134,7 +135,10 @@ STAGE_SEARCH, STAGE_ENCODE, STAGE_ALL = 1, 2, 3
 class History(C.Structure):
     """b200z_history (include/b200z.h): what a stream's window already holds when its data starts"""
     _fields_ = [("kind", C.c_int32), ("check_seeded", C.c_int32), ("hist_len", C.c_void_p), ("pos_base", C.c_void_p),
-                ("bit_base", C.c_void_p), ("hist_mask", C.c_void_p)]
+                ("bit_base", C.c_void_p), ("hist_mask", C.c_void_p),
+                # levels 0-4: SetInput schedule and engine state between segments (NULL = one SetInput, no state)
+                ("chunk_count", C.c_void_p), ("chunk_len", C.c_void_p), ("undrained_last", C.c_void_p),
+                ("engine_state", C.c_void_p), ("stored_state", C.c_void_p)]
 
 
 def lib():

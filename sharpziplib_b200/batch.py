@@ -69,12 +69,26 @@ class _Plan:
 class DeflatePlan(_Plan):
     """n independent streams, each what `new Deflater(level, true)` + SetInput(all) + Finish() would produce."""
 
-    def __init__(self, in_lens, level=6, strategy=0, wrap=_lib.WRAP_RAW, end_mode=_lib.END_FINISH, dict_lens=None):
+    def __init__(self, in_lens, level=6, strategy=0, wrap=_lib.WRAP_RAW, end_mode=_lib.END_FINISH, dict_lens=None,
+                 chunk_lens=None):
         """dict_lens: per-stream preset-dictionary bytes (Deflater.SetDictionary; at most 32506, the reference keeps the
-        dictionary's tail) stored in the input slot directly in front of the stream's data."""
+        dictionary's tail) stored in the input slot directly in front of the stream's data.
+        chunk_lens: per stream, the sizes of the SetInput calls that deliver its data (each followed by Deflate() until
+        IsNeedingInput, as DeflaterOutputStream.Write does); levels 0-4 depend on it (SURVEY.md trap T9), 5-9 ignore it."""
         lens = np.ascontiguousarray(in_lens, dtype=np.int64)
         h = C.c_void_p()
-        if dict_lens is None:
+        if chunk_lens is not None:
+            assert len(chunk_lens) == lens.size
+            arrs = [np.ascontiguousarray(c, dtype=np.int64) for c in chunk_lens]
+            counts = np.array([a.size for a in arrs], dtype=np.int32)
+            ptrs = (C.c_void_p * lens.size)(*[a.ctypes.data if a.size else None for a in arrs])
+            dl = None if dict_lens is None else np.ascontiguousarray(dict_lens, dtype=np.int64)
+            hs = _lib.History(_lib.HIST_NONE if dl is None else _lib.HIST_DICTIONARY, 0, None if dl is None else dl.ctypes.data,
+                              None, None, None, counts.ctypes.data, C.addressof(ptrs), None, None, None)
+            _lib.raise_for(_lib.lib().b200z_deflate_plan_create_ex(lens.size, lens.ctypes.data, level, strategy, wrap, end_mode,
+                                                                  C.addressof(hs), C.byref(h)))
+            self.dict_lens = np.zeros(lens.size, dtype=np.int64) if dl is None else dl
+        elif dict_lens is None:
             _lib.raise_for(_lib.lib().b200z_deflate_plan_create(lens.size, lens.ctypes.data, level, strategy, wrap, end_mode,
                                                                C.byref(h)))
             self.dict_lens = np.zeros(lens.size, dtype=np.int64)

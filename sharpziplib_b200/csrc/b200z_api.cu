@@ -246,6 +246,7 @@ int b200z_static_tables_import(const uint8_t *blob, int32_t len) {
 }
 
 int64_t b200z_deflate_bound(int64_t len) { return len + (len >> 3) + 1024; }
+int64_t b200z_engine_state_bytes(void) { return kFastStateBytes; }
 
 // ---- plans -------------------------------------------------------------------------------------------
 int b200z_deflate_plan_create(int32_t n, const int64_t *in_len, int level, int strategy, int wrap, int end_mode,
@@ -278,6 +279,39 @@ int b200z_deflate_plan_create_ex(int32_t n, const int64_t *in_len, int level, in
 	p->wrap = wrap;
 	p->end_mode = end_mode;
 	p->in_len.assign(in_len, in_len + n);
+	if (hist && n > 0 && level <= 4) {
+		// levels 0-4: the call pattern and the engine state between segments (header: "streams with history")
+		if (hist->chunk_count) {
+			if (!hist->chunk_len) {
+				set_error("history: chunk_count without chunk_len");
+				delete p;
+				return B200Z_E_ARG;
+			}
+			p->sched_cum.resize(n);
+			for (int i = 0; i < n; i++) {
+				int64_t sum = 0;
+				for (int k = 0; k < hist->chunk_count[i]; k++) {
+					const int64_t c = hist->chunk_len[i] ? hist->chunk_len[i][k] : -1;
+					if (c < 0) {
+						set_error("stream %d: SetInput size %d", i, k);
+						delete p;
+						return B200Z_E_ARG;
+					}
+					sum += c;
+					p->sched_cum[i].push_back((uint32_t)sum);
+				}
+				if (hist->chunk_count[i] < 0 || (hist->chunk_count[i] > 0 && sum != in_len[i])) {
+					set_error("stream %d: the SetInput sizes add up to %lld, the stream has %lld bytes", i, (long long)sum,
+					          (long long)in_len[i]);
+					delete p;
+					return B200Z_E_ARG;
+				}
+			}
+		}
+		if (hist->undrained_last) p->undrained.assign(hist->undrained_last, hist->undrained_last + n);
+		if (hist->engine_state && level >= 1) p->engine_state.assign(hist->engine_state, hist->engine_state + n);
+		if (hist->stored_state && level == 0) p->stored_state = hist->stored_state;
+	}
 	if (hist && hist->kind != B200Z_HIST_NONE && n > 0) {
 		if ((hist->kind != B200Z_HIST_DICTIONARY && hist->kind != B200Z_HIST_CONTINUE) || !hist->hist_len) {
 			set_error("history: kind/hist_len");
@@ -285,11 +319,16 @@ int b200z_deflate_plan_create_ex(int32_t n, const int64_t *in_len, int level, in
 			return B200Z_E_ARG;
 		}
 		if (hist->kind == B200Z_HIST_CONTINUE && level < 5) {
-			// DeflateStored/DeflateFast keep window-relative state across Deflate() calls that is not a function of the
-			// stream position (strstart vs. blockStart after partial fills); only DeflateSlow (levels 5-9) is re-entrant here
-			set_error("continuing a stream after Flush() is accelerated for levels 5-9 only");
-			delete p;
-			return B200Z_E_UNSUPPORTED;
+			// DeflateStored / DeflateFast keep window-relative state across Deflate() calls that is not a function of the
+			// stream position: it has to come from the run of the previous segment
+			bool have = level == 0 ? p->stored_state != nullptr : !p->engine_state.empty();
+			for (void *q : p->engine_state) have = have && q != nullptr;
+			if (!have) {
+				set_error("continuing a stream after Flush() at levels 0-4 needs the engine state of the previous segment "
+				          "(b200z_history.engine_state / stored_state)");
+				delete p;
+				return B200Z_E_UNSUPPORTED;
+			}
 		}
 		p->hist_kind = hist->kind;
 		p->check_seeded = hist->check_seeded != 0;
@@ -720,6 +759,12 @@ struct DeflaterH {
 	HostBits tail;                 // sub-byte tail carried between device runs
 	int64_t total_in = 0, total_out = 0;
 	uint32_t adler = 1;
+	// levels 0-4 depend on the call pattern (trap T9) and keep engine state across Flush(): the sizes of the SetInput calls
+	// since the last run, whether Deflate() was called behind the last of them, and what the engines carry
+	std::vector<int64_t> chunks;
+	bool undrained = false;
+	b200z_stored_state sstate = {0, 0, 0, 0}; // level 0 (DeflateStored)
+	DevBuf fstate;                            // levels 1-4 (DeflateFast: head[], prev[], scalars), on the device
 	PinnedBuf hin, hout;
 	DevBuf din, dout, dmeta;
 };
@@ -742,12 +787,24 @@ static int deflater_run_device(DeflaterH *d, int end_mode) {
 	const int64_t len = (int64_t)d->input.size();
 	const int64_t H = (int64_t)d->history.size();
 	const bool continuing = d->started; // an earlier segment (possibly empty) has been emitted
-	if (continuing && d->level == 0) {
-		set_error("level 0: input after a sync Flush() is not accelerated (DeflateStored block state is not positional)");
-		return B200Z_E_UNSUPPORTED;
-	}
 	b200z_history hs;
 	memset(&hs, 0, sizeof hs);
+	const int32_t n_chunks = (int32_t)d->chunks.size();
+	const int64_t *chunk_ptr = d->chunks.data();
+	const int32_t undrained = (d->undrained && n_chunks > 0) ? 1 : 0;
+	void *fstate_ptr = nullptr;
+	if (d->level <= 4) {
+		hs.chunk_count = &n_chunks;
+		hs.chunk_len = &chunk_ptr;
+		hs.undrained_last = &undrained;
+		if (d->level == 0) hs.stored_state = &d->sstate;
+		else {
+			int rc0 = d->fstate.ensure((size_t)b200z_engine_state_bytes());
+			if (rc0) return rc0;
+			fstate_ptr = d->fstate.p;
+			hs.engine_state = &fstate_ptr;
+		}
+	}
 	const int64_t pos_base = d->window_seen;
 	const int32_t bit_base = d->tail.count;
 	const uint8_t *mask = d->hist_mask.data();
@@ -757,9 +814,10 @@ static int deflater_run_device(DeflaterH *d, int end_mode) {
 	hs.pos_base = &pos_base;
 	hs.bit_base = &bit_base;
 	hs.hist_mask = &mask;
+	const uint32_t stored_before = d->sstate.input_off;
 	b200z_plan *plan = nullptr;
 	int rc = b200z_deflate_plan_create_ex(1, &len, d->level, d->strategy, d->raw ? B200Z_WRAP_RAW : B200Z_WRAP_ZLIB, end_mode,
-	                                      hs.kind != B200Z_HIST_NONE ? &hs : nullptr, &plan);
+	                                      (hs.kind != B200Z_HIST_NONE || d->level <= 4) ? &hs : nullptr, &plan);
 	if (rc) return rc;
 	std::vector<uint8_t> slot;
 	const uint8_t *inp = d->input.data();
@@ -789,10 +847,13 @@ static int deflater_run_device(DeflaterH *d, int end_mode) {
 		d->tail.bits = d->tail.count ? (seg[(size_t)whole] & ((1u << d->tail.count) - 1u)) : 0u;
 		if (end_mode == B200Z_END_FINISH) d->tail.align(d->pending); // FINISHING_STATE: AlignToByte (:507)
 		if (!d->raw) d->adler = r.check[0];
-		d->total_in += len;
+		// (level 0: Finish() behind an undrained SetInput can end the stream before all input is taken, see stored_run)
+		d->total_in += d->level == 0 ? (int64_t)(uint32_t)(d->sstate.input_off - stored_before) : len;
 		d->started = true;
 		deflater_remember(d, d->input.data(), (size_t)len, 2);
 		d->input.clear();
+		d->chunks.clear();
+		d->undrained = false;
 	}
 	b200z_plan_destroy(plan);
 	return rc;
@@ -834,6 +895,9 @@ int b200z_deflater_reset(void *h) { // Deflater.Reset :204-210 keeps level and s
 	d->window_seen = 0;
 	d->dict_set = d->deflate_called = d->started = false;
 	d->dict_adler = 0;
+	d->chunks.clear();
+	d->undrained = false;
+	d->sstate = b200z_stored_state{0, 0, 0, 0};
 	return B200Z_OK;
 }
 int b200z_deflater_set_level(void *h, int level) {
@@ -899,6 +963,12 @@ int b200z_deflater_set_input(void *h, const uint8_t *buf, int32_t len) {
 	}
 	if (len > 0) d->flushed_once = false;
 	d->input.insert(d->input.end(), buf, buf + len);
+	if (len > 0) {
+		// engine.NeedsInput (DeflaterEngine.cs:187-190) is false until Deflate() has taken the bytes; a zero-length SetInput
+		// leaves it true, so the stream classes do not even call Deflate() for it
+		d->undrained = true;
+		if (d->level <= 4) d->chunks.push_back(len); // the schedule matters for DeflateStored / DeflateFast only (trap T9)
+	}
 	return B200Z_OK;
 }
 int b200z_deflater_flush(void *h) {
@@ -919,6 +989,7 @@ int b200z_deflater_deflate(void *h, uint8_t *out, int32_t cap, int32_t *produced
 	}
 	*produced = 0;
 	d->deflate_called = true;
+	if (!d->flushing && !d->finishing) d->undrained = false; // BUSY_STATE: the engine takes everything SetInput handed over
 	// make output due (Deflater.Deflate :427-522)
 	if (!d->finished && d->pending_pos == d->pending.size() && (d->flushing || d->finishing)) {
 		d->pending.clear();
@@ -957,7 +1028,7 @@ int b200z_deflater_deflate(void *h, uint8_t *out, int32_t cap, int32_t *produced
 			}
 			d->finished = true;
 		} else {
-			// sync flush (level 0 skips the padding, :488; level 0 is not accelerated anyway)
+			// sync flush (level 0 skips the padding, :488)
 			int rc = deflater_run_device(d, B200Z_END_FLUSH);
 			if (rc) return rc;
 			d->flushed_once = true;
@@ -973,8 +1044,11 @@ int b200z_deflater_deflate(void *h, uint8_t *out, int32_t cap, int32_t *produced
 	return B200Z_OK;
 }
 int b200z_deflater_needs_input(void *h, int *flag) {
-	*flag = 1; // SetInput copies, so the engine's input is always consumed (DeflaterEngine.NeedsInput :187-190)
-	(void)h;
+	// DeflaterEngine.NeedsInput (:187-190): false between SetInput and the Deflate() call that takes the bytes.  The
+	// handle copies on SetInput, but it reports what the reference reports: DeflaterOutputStream.Write calls Deflate()
+	// exactly while this is false (Streams/DeflaterOutputStream.cs:245-275), and whether that call happened before
+	// Flush() / Finish() changes the bytes at levels 0-4 (b200z_history.undrained_last)
+	*flag = ((DeflaterH *)h)->undrained ? 0 : 1;
 	return B200Z_OK;
 }
 int b200z_deflater_is_finished(void *h, int *flag) {
@@ -1337,7 +1411,9 @@ int b200z_inflater_needs_dictionary(void *h, int *flag) {
 }
 int b200z_inflater_is_finished(void *h, int *flag) {
 	InflaterH *d = (InflaterH *)h;
-	*flag = (d->finished && d->delivered == d->out_total()) ? 1 : 0; // Inflater.cs:806-812
+	// Inflater.cs:806-812; a trailer that did not verify is an exception from Inflate() in the reference (DecodeChksum
+	// :397-418), so the stream is not "finished" as long as that error has not been delivered
+	*flag = (d->finished && !d->error && d->delivered == d->out_total()) ? 1 : 0;
 	return B200Z_OK;
 }
 int b200z_inflater_remaining_input(void *h, int32_t *v) {

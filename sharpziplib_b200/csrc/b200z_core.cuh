@@ -286,23 +286,35 @@ B200Z_HD uint32_t parse_run(ParseCarry &c, uint32_t seg_end, uint32_t n, const L
 // (or Flush()) -> drain.  emit(sym) receives the tallied symbols; block(byte_start, stored_ok) is called for every
 // FlushBlock with the block's first input byte and whether storedOffset >= 0 (trap T4).
 struct FastEngine {
-	uint32_t n;           // input length
-	const uint8_t *in;    // input bytes
+	uint32_t n;           // stream bytes handed over so far (inputEnd, counted from the start of the stream)
+	const uint8_t *in;    // the slot: history (a dictionary, or the last bytes of earlier segments) followed by the data
+	uint32_t slot_len;    // bytes in the slot
+	uint32_t woff;        // window index w holds slot byte w + woff (= 32768 * slides - 1 - stream offset of slot byte 0)
 	uint16_t *head;       // 32768 entries, zeroed by the caller
 	uint16_t *prev;       // 32768 entries, zeroed by the caller
 	int strstart, blockStart, lookahead, matchStart, matchLen, ins_h;
 	uint32_t slides;      // number of SlideWindow calls so far
-	uint32_t inputOff;    // bytes handed to the window so far
+	uint32_t inputOff;    // stream bytes handed to the window so far
 	uint32_t nsym;        // symbols tallied in the current block
 	int coop;             // 1: never slide inside the engine, report kFeNeedSlide instead (the kernel slides warp-wide)
 };
 constexpr int kFeFalse = 0, kFeTrue = 1, kFeNeedSlide = 2;
 
-B200Z_HD uint32_t fe_win(const FastEngine &e, int w) { return (uint32_t)e.in[(uint32_t)(w - 1) + 32768u * e.slides]; }
+// What DeflateFast carries from one Deflate() call to the next besides head[] / prev[] (DeflaterEngine's fields): saved
+// when a segment ends with Flush(), loaded when the stream goes on (b200z_history.engine_state).
+struct FastCarry {
+	int32_t strstart, blockStart, lookahead, matchStart, matchLen, ins_h;
+	uint32_t slides, inputOff;
+};
+constexpr int kFastStateBytes = 2 * 65536 + 64; // head[32768], prev[32768], FastCarry
+
+B200Z_HD uint32_t fe_win(const FastEngine &e, int w) { return (uint32_t)e.in[(uint32_t)w + e.woff]; }
 
 B200Z_HD void fe_init(FastEngine &e, const uint8_t *in, uint32_t n, uint16_t *head, uint16_t *prev) {
 	e.n = n;
 	e.in = in;
+	e.slot_len = n;
+	e.woff = 0xFFFFFFFFu; // window index 1 is slot byte 0 (DeflaterEngine.cs:91-93)
 	e.head = head;
 	e.prev = prev;
 	e.strstart = e.blockStart = 1; // DeflaterEngine.cs:91-93
@@ -312,6 +324,36 @@ B200Z_HD void fe_init(FastEngine &e, const uint8_t *in, uint32_t n, uint16_t *he
 	e.ins_h = 0;
 	e.slides = 0;
 	e.inputOff = 0;
+	e.nsym = 0;
+	e.coop = 0;
+}
+B200Z_HD void fe_save(const FastEngine &e, FastCarry &c) {
+	c.strstart = e.strstart;
+	c.blockStart = e.blockStart;
+	c.lookahead = e.lookahead;
+	c.matchStart = e.matchStart;
+	c.matchLen = e.matchLen;
+	c.ins_h = e.ins_h;
+	c.slides = e.slides;
+	c.inputOff = e.inputOff;
+}
+// the stream goes on: the slot holds its last `hist` bytes followed by the new data (the tables are the caller's business)
+B200Z_HD void fe_load(FastEngine &e, const FastCarry &c, const uint8_t *slot, uint32_t slot_len, uint32_t hist, uint16_t *head,
+                      uint16_t *prev) {
+	e.in = slot;
+	e.slot_len = slot_len;
+	e.head = head;
+	e.prev = prev;
+	e.strstart = c.strstart;
+	e.blockStart = c.blockStart;
+	e.lookahead = c.lookahead;
+	e.matchStart = c.matchStart;
+	e.matchLen = c.matchLen;
+	e.ins_h = c.ins_h;
+	e.slides = c.slides;
+	e.inputOff = c.inputOff;
+	e.n = c.inputOff; // nothing new is visible before the first SetInput of the segment
+	e.woff = 32768u * c.slides - 1u - (c.inputOff - hist); // slot byte 0 is stream byte inputOff - hist
 	e.nsym = 0;
 	e.coop = 0;
 }
@@ -346,6 +388,7 @@ B200Z_HD void fe_slide_scalars(FastEngine &e) { // :443-446
 	e.strstart -= kWSize;
 	e.blockStart -= kWSize;
 	e.slides += 1;
+	e.woff += (uint32_t)kWSize;
 }
 B200Z_HDN void fe_slide(FastEngine &e) { // :441-462
 	fe_slide_scalars(e);
@@ -378,13 +421,13 @@ B200Z_HD bool fe_fill_window(FastEngine &e) { // :366-400
 // four window bytes starting at window index w, first byte in the low bits.  The device reads two aligned words (the input
 // slot is 256-byte aligned and has 16 bytes of slack behind n); the host copy stays inside [0, n).
 B200Z_HD uint32_t fe_word(const FastEngine &e, int w) {
-	const uint32_t a = (uint32_t)(w - 1) + 32768u * e.slides;
+	const uint32_t a = (uint32_t)w + e.woff;
 #ifdef __CUDA_ARCH__
 	const uint32_t *p = reinterpret_cast<const uint32_t *>(e.in + (a & ~3u));
 	return __funnelshift_r(p[0], p[1], (a & 3u) * 8u);
 #else
 	uint32_t v = 0;
-	for (uint32_t k = 0; k < 4 && a + k < e.n; k++) v |= (uint32_t)e.in[a + k] << (8 * k);
+	for (uint32_t k = 0; k < 4 && a + k < e.slot_len; k++) v |= (uint32_t)e.in[a + k] << (8 * k);
 	return v;
 #endif
 }
@@ -446,7 +489,7 @@ B200Z_HDN int fe_deflate_fast(FastEngine &e, bool flush, bool finish, const Leve
 	while (e.lookahead >= kMinLookahead || flush) {
 		if (e.lookahead == 0) {
 			// we are flushing everything
-			block((uint32_t)(e.blockStart - 1) + 32768u * e.slides, e.blockStart >= 0, finish);
+			block((uint32_t)e.blockStart + e.woff, e.blockStart >= 0, finish);
 			e.nsym = 0;
 			e.blockStart = e.strstart;
 			return kFeFalse;
@@ -482,7 +525,7 @@ B200Z_HDN int fe_deflate_fast(FastEngine &e, bool flush, bool finish, const Leve
 		}
 		if (e.nsym >= (uint32_t)kBlockSyms) {
 			const bool lastBlock = finish && e.lookahead == 0;
-			block((uint32_t)(e.blockStart - 1) + 32768u * e.slides, e.blockStart >= 0, lastBlock);
+			block((uint32_t)e.blockStart + e.woff, e.blockStart >= 0, lastBlock);
 			e.nsym = 0;
 			e.blockStart = e.strstart;
 			return lastBlock ? kFeFalse : kFeTrue;
@@ -491,19 +534,34 @@ B200Z_HDN int fe_deflate_fast(FastEngine &e, bool flush, bool finish, const Leve
 	return kFeTrue;
 }
 
-// Whole stream, call pattern above.  end_mode: B200Z_END_* (0 finish, 1 flush then finish, 2 flush).
+// One segment of a stream (everything up to a Flush() or Finish()), call pattern above.  The segment's bytes arrive in
+// `nchunks` SetInput calls, cum[i] bytes after the first i + 1 of them (nchunks == 0: one call with everything); each is
+// followed by Deflate() until IsNeedingInput.  For DeflateFast the result depends on that schedule (trap T9: FillWindow
+// slides at strstart >= 65274 when it is called, DeflateFast at > 65274), so the handle records it.
+// end_mode: B200Z_END_* (0 finish, 1 flush then finish, 2 flush).
 template <class EmitFn, class BlockFn>
-B200Z_HDN void fe_run(FastEngine &e, const LevelParams &lp, int strategy, int end_mode, EmitFn emit, BlockFn block) {
-	// BUSY_STATE: Deflater.Deflate -> engine.Deflate(false, false) until it reports "needs input" (:104-137)
-	for (;;) {
-		fe_fill_window(e);
-		if (fe_deflate_fast(e, false, false, lp, strategy, emit, block) == kFeFalse) break;
+B200Z_HDN void fe_run(FastEngine &e, const LevelParams &lp, int strategy, int end_mode, EmitFn emit, BlockFn block,
+                      const uint32_t *cum = nullptr, int nchunks = 0, bool busy_last = true) {
+	const uint32_t seg_base = e.inputOff;
+	// slot byte 0 is stream byte 32768 * slides - 1 - woff; the segment is what the slot holds behind inputOff
+	const uint32_t seg_len = 32768u * e.slides - 1u - e.woff + e.slot_len - e.inputOff;
+	// busy_last = false: Flush() / Finish() follows the last SetInput directly, without a Deflate() call in between
+	const int nc = nchunks > 0 ? nchunks : 1;
+	for (int ci = 0; ci < nc; ci++) {
+		e.n = seg_base + (nchunks > 0 ? cum[ci] : seg_len);
+		if (ci == nc - 1 && !busy_last) break;
+		// BUSY_STATE: Deflater.Deflate -> engine.Deflate(false, false) until it reports "needs input" (:104-137)
+		for (;;) {
+			fe_fill_window(e);
+			if (fe_deflate_fast(e, false, false, lp, strategy, emit, block) == kFeFalse) break;
+		}
 	}
-	// Flush() or Finish(): flush = true, finish as requested; canFlush holds because the input is exhausted
+	// Flush() or Finish(): engine.Deflate(flush, finish) runs the function with canFlush = flush && inputOff == inputEnd
+	// (DeflaterEngine.cs:104-137) -- false as long as part of an undrained last SetInput is still outside the window
 	const bool finish = end_mode == 0;
 	for (;;) {
 		fe_fill_window(e);
-		if (fe_deflate_fast(e, true, finish, lp, strategy, emit, block) == kFeFalse) break;
+		if (fe_deflate_fast(e, e.inputOff == e.n, finish, lp, strategy, emit, block) == kFeFalse) break;
 	}
 	// (end_mode 1: the sync padding and the final empty static block that Finish() adds are appended by k_scan)
 }
@@ -511,11 +569,30 @@ B200Z_HDN void fe_run(FastEngine &e, const LevelParams &lp, int strategy, int en
 // ---- level 0: DeflaterEngine.DeflateStored (:614-649) --------------------------------------------------
 // Only block boundaries are decided here (pure integer bookkeeping); block(byte_start, length, last) is called for
 // every FlushStoredBlock.  Same call pattern as fe_run.  Sync-flush padding is skipped at level 0 (Deflater.cs:488).
+// What DeflateStored carries from one Deflate() call to the next (b200z_history.stored_state, in/out).
+struct StoredCarry {
+	int32_t strstart, blockStart;
+	uint32_t slides, inputOff;
+};
+// One segment of n bytes in `nchunks` SetInput calls (cum[] as for fe_run; stored-block boundaries depend on the schedule,
+// trap T9).  `carry`: in = the state a flushed earlier segment left (NULL: start of the stream, dict_len bytes of preset
+// dictionary in front); out = the state after this segment.  Block starts are stream offsets minus `start_bias`.
 template <class BlockFn>
-inline void stored_run(uint32_t n, uint32_t dict_len, int end_mode, BlockFn block) { // host only: run when a plan is built
+inline void stored_run(uint32_t n, uint32_t dict_len, int end_mode, BlockFn block, const uint32_t *cum = nullptr, int nchunks = 0,
+                       const StoredCarry *carry_in = nullptr, StoredCarry *carry_out = nullptr, uint32_t start_bias = 0,
+                       bool busy_last = true) {
+	// host only: run when a plan is built
 	// dict_len: a preset dictionary in front of the n data bytes (SetDictionary leaves strstart = blockStart = 1 + length)
 	int strstart = 1 + (int)dict_len, blockStart = 1 + (int)dict_len, lookahead = 0;
 	uint32_t slides = 0, inputOff = 0;
+	if (carry_in) {
+		strstart = carry_in->strstart;
+		blockStart = carry_in->blockStart;
+		slides = carry_in->slides;
+		inputOff = carry_in->inputOff;
+	}
+	const uint32_t seg_base = inputOff;
+	uint32_t vis = seg_base; // inputEnd: stream bytes handed over so far
 	const int kMaxBlock = 65531; // DeflaterConstants.MAX_BLOCK_SIZE
 	auto fill = [&]() {
 		if (strstart >= kWSize + kMaxDist) {
@@ -523,9 +600,9 @@ inline void stored_run(uint32_t n, uint32_t dict_len, int end_mode, BlockFn bloc
 			blockStart -= kWSize;
 			slides += 1;
 		}
-		if (lookahead < kMaxMatch + kMinMatch + 1 && inputOff < n) {
+		if (lookahead < kMaxMatch + kMinMatch + 1 && inputOff < vis) {
 			uint32_t more = (uint32_t)(2 * kWSize - lookahead - strstart);
-			if (more > n - inputOff) more = n - inputOff;
+			if (more > vis - inputOff) more = vis - inputOff;
 			inputOff += more;
 			lookahead += (int)more;
 		}
@@ -541,26 +618,38 @@ inline void stored_run(uint32_t n, uint32_t dict_len, int end_mode, BlockFn bloc
 				storedLength = kMaxBlock;
 				lastBlock = false;
 			}
-			block((uint32_t)(blockStart - 1) + 32768u * slides, (uint32_t)storedLength, lastBlock);
+			// window index w is stream byte w - 1 + 32768 * slides minus what the dictionary took (it is not stream data)
+			block((uint32_t)(blockStart - 1) + 32768u * slides - start_bias, (uint32_t)storedLength, lastBlock);
 			blockStart += storedLength;
 			return !(lastBlock || storedLength == 0);
 		}
 		return true;
 	};
-	for (;;) {
-		fill();
-		if (!stored(false, false)) break;
+	const int nc = nchunks > 0 ? nchunks : 1;
+	for (int ci = 0; ci < nc; ci++) {
+		vis = seg_base + (nchunks > 0 ? cum[ci] : n);
+		if (ci == nc - 1 && !busy_last) break;
+		for (;;) {
+			fill();
+			if (!stored(false, false)) break;
+		}
 	}
 	const bool finish = end_mode == 0;
 	for (;;) {
 		fill();
-		if (!stored(inputOff == n, finish)) break;
+		if (!stored(inputOff == vis, finish)) break;
 	}
 	if (end_mode == 1) {
 		for (;;) {
 			fill();
-			if (!stored(inputOff == n, true)) break;
+			if (!stored(inputOff == vis, true)) break;
 		}
+	}
+	if (carry_out) {
+		carry_out->strstart = strstart;
+		carry_out->blockStart = blockStart;
+		carry_out->slides = slides;
+		carry_out->inputOff = inputOff;
 	}
 }
 

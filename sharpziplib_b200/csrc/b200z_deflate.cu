@@ -670,10 +670,12 @@ __global__ void __launch_bounds__(32)
     k_fast(const uint8_t *__restrict__ in, uint32_t *__restrict__ sym, const int64_t *__restrict__ in_off,
            const int64_t *__restrict__ in_len, uint32_t *__restrict__ nsyms, uint32_t *__restrict__ nblocks,
            const uint32_t *__restrict__ blk_off, uint32_t *__restrict__ blk_start, uint32_t *__restrict__ blk_ptop,
-           const uint32_t *__restrict__ hist, LevelParams lp, int strategy, int end_mode, int prev_entries) {
+           const uint32_t *__restrict__ hist, LevelParams lp, int strategy, int end_mode, int prev_entries,
+           const uint32_t *__restrict__ sched, const uint32_t *__restrict__ sched_off, const int32_t *__restrict__ undrained,
+           uint8_t *const *__restrict__ fstate, int cont) {
 	// prev[] is indexed by window position & 32767; when no stream of the batch is longer than prev_entries - 2 bytes the
 	// positions never reach prev_entries, so the table (and the CTA's shared-memory footprint) can be that much smaller
-	// and three CTAs share an SM instead of one.
+	// and three CTAs share an SM instead of one.  (Plans that carry engine state between segments use whole tables.)
 	extern __shared__ __align__(16) uint8_t fsm[];
 	uint16_t *head = reinterpret_cast<uint16_t *>(fsm);
 	uint16_t *prev = head + 32768;
@@ -684,14 +686,37 @@ __global__ void __launch_bounds__(32)
 	uint32_t *sout = sym + off;
 	uint32_t *bstart = blk_start + blk_off[stream];
 	uint32_t *bptop = blk_ptop + blk_off[stream];
-	for (int i = lane; i < (32768 + prev_entries) / 2; i += 32) reinterpret_cast<uint32_t *>(fsm)[i] = 0;
-	__syncwarp();
+	uint8_t *st = fstate[stream]; // engine state carried between the segments of this stream (b200z_history.engine_state)
+	const bool resume = cont != 0 && st != nullptr;
 	FastEngine e;
-	fe_init(e, in + off, n, head, prev);
-	if (lane == 0) fe_set_dictionary(e, hist[stream]); // preset dictionary in front of the data (0 = none)
+	if (resume) {
+		// the stream goes on behind a Flush(): tables and scalars as the previous segment's run left them
+		const uint4 *src = reinterpret_cast<const uint4 *>(st);
+		for (int i = lane; i < 131072 / 16; i += 32) reinterpret_cast<uint4 *>(fsm)[i] = src[i];
+		__syncwarp();
+		FastCarry c = *reinterpret_cast<const FastCarry *>(st + 131072);
+		fe_load(e, c, in + off, n, hist[stream], head, prev);
+	} else {
+		for (int i = lane; i < (32768 + prev_entries) / 2; i += 32) reinterpret_cast<uint32_t *>(fsm)[i] = 0;
+		__syncwarp();
+		fe_init(e, in + off, n, head, prev);
+		if (lane == 0) fe_set_dictionary(e, hist[stream]); // preset dictionary in front of the data (0 = none)
+	}
 	e.coop = 1;
+	// the SetInput schedule of the segment (fe_run in b200z_core.cuh is the serial statement of this loop)
+	const uint32_t *cum = sched + sched_off[stream];
+	const int nsched = (int)(sched_off[stream + 1] - sched_off[stream]);
+	const int nc = nsched > 0 ? nsched : 1;
+	const bool busy_last = undrained[stream] == 0;
+	uint32_t seg_base = 0, seg_len = 0;
+	if (lane == 0) {
+		seg_base = e.inputOff;
+		seg_len = 32768u * e.slides - 1u - e.woff + e.slot_len - e.inputOff;
+		e.n = seg_base + (nsched > 0 ? cum[0] : seg_len);
+	}
 	uint32_t total = 0, nblk = 0;
-	int phase = 0;           // 0: BUSY_STATE drain, 1: Flush()/Finish()
+	int ci = 0;
+	int phase = (nc == 1 && !busy_last) ? 1 : 0; // 0: BUSY_STATE drain of chunk ci, 1: Flush()/Finish()
 	bool in_deflate = false; // re-entering DeflateFast after a cooperative slide must not run FillWindow again
 	const bool finish = end_mode == B200Z_END_FINISH;
 	for (;;) {
@@ -703,8 +728,9 @@ __global__ void __launch_bounds__(32)
 				r = kFeNeedSlide;
 			} else {
 				in_deflate = true;
+				// engine.Deflate(flush, finish): canFlush = flush && inputOff == inputEnd (DeflaterEngine.cs:104-137)
 				r = fe_deflate_fast(
-				    e, phase == 1, phase == 1 && finish, lp, strategy, [&](uint32_t s2) { sout[total++] = s2; },
+				    e, phase == 1 && e.inputOff == e.n, phase == 1 && finish, lp, strategy, [&](uint32_t s2) { sout[total++] = s2; },
 				    [&](uint32_t start, bool ok, bool) {
 					    bstart[nblk] = start;
 					    bptop[nblk] = ok ? 0xFFFFFFFEu : 0xFFFFFFFFu; // storedOffset sign decided by the engine (trap T4)
@@ -729,12 +755,32 @@ __global__ void __launch_bounds__(32)
 		}
 		if (r == kFeFalse) {
 			if (phase == 1) break;
-			phase = 1;
+			// chunk ci is drained ("needs input"): the next SetInput, or Flush()/Finish()
+			++ci;
+			if (ci < nc) {
+				if (lane == 0) e.n = seg_base + cum[ci];
+				if (ci == nc - 1 && !busy_last) phase = 1;
+			} else {
+				phase = 1;
+			}
 		}
 	}
 	if (lane == 0) {
 		nsyms[stream] = total;
 		nblocks[stream] = nblk;
+	}
+	if (st) {
+		// what the next segment of this stream starts from
+		__syncwarp();
+		uint4 *dst = reinterpret_cast<uint4 *>(st);
+		const int words = (32768 + prev_entries) * 2 / 16;
+		for (int i = lane; i < words; i += 32) dst[i] = reinterpret_cast<const uint4 *>(fsm)[i];
+		for (int i = words + lane; i < 131072 / 16; i += 32) dst[i] = make_uint4(0u, 0u, 0u, 0u);
+		if (lane == 0) {
+			FastCarry c;
+			fe_save(e, c);
+			*reinterpret_cast<FastCarry *>(st + 131072) = c;
+		}
 	}
 }
 
@@ -1046,7 +1092,7 @@ int deflate_plan_build(b200z_plan *p) {
 		// levels 1-4: size of k_fast's prev[] table (see there)
 		int64_t need = maxlen + 2;
 		int pe = 32768;
-		if (need <= 32768) pe = (int)((need + 255) / 256 * 256);
+		if (need <= 32768 && p->engine_state.empty()) pe = (int)((need + 255) / 256 * 256); // (a carried state holds whole tables)
 		p->fast_prev_entries = pe;
 	}
 	std::vector<uint32_t> blk_off(n + 1);
@@ -1056,6 +1102,7 @@ int deflate_plan_build(b200z_plan *p) {
 	std::vector<uint32_t> hist32(n, 0u), bitbase32(n, 0u);
 	std::vector<int64_t> bias64(n, 0), hm_off(n, 0), ck_off(n), ck_len(n);
 	std::vector<uint8_t> hmask;
+	std::vector<int64_t> stored_taken(n, -1);
 	for (int i = 0; i < n; i++) {
 		const int64_t len = p->in_len[i];
 		if (len < 0 || len > 0xFFFF0000ll) {
@@ -1092,10 +1139,31 @@ int deflate_plan_build(b200z_plan *p) {
 		nblk += maxb;
 		if (lp.func == 0) {
 			uint64_t dst = 0;
-			stored_run((uint32_t)(len - H), (uint32_t)H, p->end_mode, [&](uint32_t start, uint32_t blen, bool last) {
+			const bool cont = p->hist_kind == B200Z_HIST_CONTINUE;
+			const uint32_t *cum = (i < (int)p->sched_cum.size() && !p->sched_cum[i].empty()) ? p->sched_cum[i].data() : nullptr;
+			const int nch = cum ? (int)p->sched_cum[i].size() : 0;
+			const bool busy_last = !(i < (int)p->undrained.size() && p->undrained[i]);
+			StoredCarry cin{0, 0, 0, 0}, cout{0, 0, 0, 0};
+			if (cont) { // checked when the plan was created: stored_state is there
+				cin.strstart = p->stored_state[i].strstart;
+				cin.blockStart = p->stored_state[i].block_start;
+				cin.slides = p->stored_state[i].slides;
+				cin.inputOff = p->stored_state[i].input_off;
+			}
+			stored_run((uint32_t)(len - H), cont ? 0u : (uint32_t)H, p->end_mode, [&](uint32_t start, uint32_t blen, bool last) {
 				sblocks.push_back(StoredBlock{i, start, blen, last ? 1u : 0u, dst});
 				dst += 5 + (uint64_t)blen;
-			});
+			}, cum, nch, cont ? &cin : nullptr, &cout, cont ? (uint32_t)(p->pos_base[i] - H) : 0u, busy_last);
+			// what the window took in: everything, except when Finish() right behind an undrained SetInput makes
+			// DeflateStored end the stream early (lastBlock = finish although input is left, DeflaterEngine.cs:629-641);
+			// TotalIn and the Adler-32 of the reference then cover the consumed bytes only, and so do ours
+			stored_taken[i] = (int64_t)(uint32_t)(cout.inputOff - (cont ? cin.inputOff : 0u));
+			if (p->stored_state) {
+				p->stored_state[i].strstart = cout.strstart;
+				p->stored_state[i].block_start = cout.blockStart;
+				p->stored_state[i].slides = cout.slides;
+				p->stored_state[i].input_off = cout.inputOff;
+			}
 			slens.push_back((int64_t)dst);
 		}
 	}
@@ -1145,6 +1213,22 @@ int deflate_plan_build(b200z_plan *p) {
 		p->o_stored = ws.reserve((int64_t)sizeof(StoredBlock) * (sblocks.size() + 1));
 		p->o_slens = ws.reserve(8ll * (n + 1));
 	}
+	std::vector<uint32_t> sched_flat, sched_off(n + 1, 0u);
+	std::vector<int32_t> undrained32(n, 0);
+	std::vector<void *> fstate(n, nullptr);
+	if (lp.func == 1) {
+		for (int i = 0; i < n; i++) {
+			sched_off[i] = (uint32_t)sched_flat.size();
+			if (i < (int)p->sched_cum.size()) sched_flat.insert(sched_flat.end(), p->sched_cum[i].begin(), p->sched_cum[i].end());
+			if (i < (int)p->undrained.size()) undrained32[i] = p->undrained[i] ? 1 : 0;
+			if (i < (int)p->engine_state.size()) fstate[i] = p->engine_state[i];
+		}
+		sched_off[n] = (uint32_t)sched_flat.size();
+		p->o_sched = ws.reserve(4ll * (sched_flat.size() + 1));
+		p->o_sched_off = ws.reserve(4ll * (n + 1));
+		p->o_undrained = ws.reserve(4ll * (n + 1));
+		p->o_fstate = ws.reserve(8ll * (n + 1));
+	}
 	p->o_hist = ws.reserve(4ll * (n + 1));
 	p->o_bias = ws.reserve(8ll * (n + 1));
 	p->o_bitbase = ws.reserve(4ll * (n + 1));
@@ -1155,6 +1239,7 @@ int deflate_plan_build(b200z_plan *p) {
 		for (int i = 0; i < n; i++) { // the checksum covers the data, never the history
 			ck_off[i] = p->in_off[i] + hist32[i];
 			ck_len[i] = p->in_len[i] - hist32[i];
+			if (stored_taken[i] >= 0 && stored_taken[i] < ck_len[i]) ck_len[i] = stored_taken[i]; // level 0, see above
 		}
 		p->o_ck_off = ws.reserve(8ll * (n + 1));
 		p->o_ck_len = ws.reserve(8ll * (n + 1));
@@ -1193,6 +1278,13 @@ int deflate_plan_build(b200z_plan *p) {
 		if (!rgroups.empty())
 			B200Z_CUDA(cudaMemcpy(ws.at<int2>(p->o_rgroups), rgroups.data(), 8ll * rgroups.size(), cudaMemcpyHostToDevice));
 		B200Z_CUDA(cudaMemcpy(ws.at<uint32_t>(p->o_rnd_off), rnd_off.data(), 4ll * (n + 1), cudaMemcpyHostToDevice));
+	}
+	if (lp.func == 1 && n) {
+		if (!sched_flat.empty())
+			B200Z_CUDA(cudaMemcpy(ws.at<uint32_t>(p->o_sched), sched_flat.data(), 4ll * sched_flat.size(), cudaMemcpyHostToDevice));
+		B200Z_CUDA(cudaMemcpy(ws.at<uint32_t>(p->o_sched_off), sched_off.data(), 4ll * (n + 1), cudaMemcpyHostToDevice));
+		B200Z_CUDA(cudaMemcpy(ws.at<int32_t>(p->o_undrained), undrained32.data(), 4ll * n, cudaMemcpyHostToDevice));
+		B200Z_CUDA(cudaMemcpy(ws.at<void *>(p->o_fstate), fstate.data(), 8ll * n, cudaMemcpyHostToDevice));
 	}
 	if (!sblocks.empty())
 		B200Z_CUDA(cudaMemcpy(ws.at<StoredBlock>(p->o_stored), sblocks.data(), sizeof(StoredBlock) * sblocks.size(), cudaMemcpyHostToDevice));
@@ -1261,7 +1353,10 @@ int deflate_plan_run(b200z_plan *p, const uint8_t *d_in, uint8_t *d_out, int64_t
 	if (lp.func == 1) {
 		p->mark(s, "k_fast");
 		k_fast<<<n, 32, 65536 + 2 * p->fast_prev_entries, s>>>(d_in, sym, in_off, in_len, nsyms, nblocks, blk_off, blk_start, blk_ptop,
-		                                                       hist, lp, p->strategy, p->end_mode, p->fast_prev_entries);
+		                                                       hist, lp, p->strategy, p->end_mode, p->fast_prev_entries,
+		                                                       ws.at<uint32_t>(p->o_sched), ws.at<uint32_t>(p->o_sched_off),
+		                                                       ws.at<int32_t>(p->o_undrained), ws.at<uint8_t *>(p->o_fstate),
+		                                                       p->hist_kind == B200Z_HIST_CONTINUE ? 1 : 0);
 	} else {
 		if (do_search) {
 		p->mark(s, "k_links");

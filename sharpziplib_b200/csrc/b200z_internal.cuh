@@ -94,6 +94,13 @@ struct b200z_plan {
 	uint32_t parse_chunk = 32768;
 	int fast_prev_entries = 32768; // k_fast's prev[] size for this batch
 	int64_t o_stored = 0, o_slens = 0; // level 0: stored-block list and per-stream output lengths
+	// levels 0-4: the SetInput schedule of every stream (cumulative sizes), "Flush()/Finish() behind an undrained SetInput",
+	// and the engine state carried between the segments of a stream (b200z_history)
+	std::vector<std::vector<uint32_t>> sched_cum;
+	std::vector<int32_t> undrained;
+	std::vector<void *> engine_state;             // device pointers (levels 1-4)
+	struct b200z_stored_state *stored_state = nullptr; // caller's host array (level 0), used while the plan is built
+	int64_t o_sched = 0, o_sched_off = 0, o_undrained = 0, o_fstate = 0;
 	int n_stored = 0;
 	// inflate workspace offsets
 	int64_t o_tok = 0, o_ntok = 0, o_tok_off = 0;

@@ -73,9 +73,19 @@ struct Writer { // what the emit kernel does with atomicOr on zeroed 32-bit word
 
 // History form (b200z_deflate_plan_create_ex): data = H history bytes + the segment, n = both; abs_bias = pos_base - H;
 // the bits start at bit_base; end_mode 0 finish / 2 flush (stream stays open); *outbits = total bits (bit_base included)
+// sched: the segment's SetInput schedule (cum[i] = bytes after the first i + 1 calls; nchunks 0 = one call); state: the
+// engine state of levels 0-4 between segments (kFastStateBytes: head[], prev[], FastCarry / StoredCarry), read when cont != 0
+// and written at the end -- what b200z_history.engine_state / stored_state carry for the kernels
+struct ModelSched {
+	const uint32_t *cum = nullptr;
+	int nchunks = 0;
+	uint8_t *state = nullptr;
+	int cont = 0;
+	int busy_last = 1; // 0: Flush() / Finish() right behind the last SetInput, no Deflate() call in between
+};
 static int model_run(const uint8_t *data, uint32_t n, uint32_t H, uint32_t abs_bias, uint32_t bit_base, const uint8_t *hmask,
                      int level, int strategy, int flush_then_finish, int flush_only, uint8_t *out, uint64_t cap, uint64_t *outlen,
-                     uint64_t *outbits);
+                     uint64_t *outbits, const ModelSched &ms = ModelSched());
 
 extern "C" int model_deflate(const uint8_t *data, uint32_t n, int level, int strategy, int flush_then_finish,
                              uint8_t *out, uint64_t cap, uint64_t *outlen) {
@@ -90,9 +100,24 @@ extern "C" int model_deflate_ex(const uint8_t *data, uint32_t n, uint32_t hist, 
 	return model_run(data, n, hist, pos_base - hist, bit_base, hmask, level, strategy, 0, end_mode == 2, out, cap, &len, outbits);
 }
 
+extern "C" int model_state_bytes() { return kFastStateBytes; }
+
+extern "C" int model_deflate_ex2(const uint8_t *data, uint32_t n, uint32_t hist, uint32_t pos_base, uint32_t bit_base,
+                                 const uint8_t *hmask, int level, int strategy, int end_mode, const uint32_t *cum, int nchunks,
+                                 int busy_last, uint8_t *state, int cont, uint8_t *out, uint64_t cap, uint64_t *outbits) {
+	uint64_t len;
+	ModelSched ms;
+	ms.cum = cum;
+	ms.nchunks = nchunks;
+	ms.state = state;
+	ms.cont = cont;
+	ms.busy_last = busy_last;
+	return model_run(data, n, hist, pos_base - hist, bit_base, hmask, level, strategy, 0, end_mode == 2, out, cap, &len, outbits, ms);
+}
+
 static int model_run(const uint8_t *data, uint32_t n, uint32_t H, uint32_t abs_bias, uint32_t bit_base, const uint8_t *hmask,
                      int level, int strategy, int flush_then_finish, int flush_only, uint8_t *out, uint64_t cap, uint64_t *outlen,
-                     uint64_t *outbits) {
+                     uint64_t *outbits, const ModelSched &ms) {
 	LevelParams lp = level_params(level);
 	*outbits = 0;
 	std::vector<uint32_t> syms;
@@ -103,14 +128,18 @@ static int model_run(const uint8_t *data, uint32_t n, uint32_t H, uint32_t abs_b
 		// level 0: stored blocks only (each block: 3 header bits, pad, LEN, ~LEN, bytes)
 		Writer W0;
 		uint64_t bp = 0;
-		stored_run(n - H, H, flush_then_finish ? 1 : (flush_only ? 2 : 0), [&](uint32_t start, uint32_t len, bool last) {
+		StoredCarry cin, cout;
+		if (ms.cont) std::memcpy(&cin, ms.state, sizeof cin);
+		stored_run(n - H, ms.cont ? 0 : H, flush_then_finish ? 1 : (flush_only ? 2 : 0), [&](uint32_t start, uint32_t len, bool last) {
 			W0.put(bp, last ? 1 : 0, 3);
 			bp = (bp + 3 + 7) & ~7ull;
 			W0.put(bp, len & 0xFFFF, 16);
 			W0.put(bp + 16, (~len) & 0xFFFF, 16);
 			bp += 32;
 			for (uint32_t i = 0; i < len; i++, bp += 8) W0.put(bp, data[start + i], 8);
-		});
+		}, ms.cum, ms.nchunks, ms.cont ? &cin : nullptr, &cout, ms.cont ? abs_bias : 0, ms.busy_last != 0);
+		if (ms.state) std::memcpy(ms.state, &cout, sizeof cout);
+		*outbits = bp;
 		uint64_t nb0 = (bp + 7) >> 3;
 		if (nb0 > cap) return 102;
 		W0.w.resize((nb0 + 3) / 4 + 1, 0);
@@ -124,8 +153,17 @@ static int model_run(const uint8_t *data, uint32_t n, uint32_t H, uint32_t abs_b
 		// levels 1-4: the serial DeflateFast emulation (what k_fast runs, one thread per stream)
 		std::vector<uint16_t> head(32768, 0), prev(32768, 0);
 		FastEngine fe;
-		fe_init(fe, data, n, head.data(), prev.data());
-		fe_set_dictionary(fe, H);
+		if (ms.cont) {
+			// k_fast: tables and scalars come back from the state buffer the previous segment's run filled
+			FastCarry c;
+			std::memcpy(head.data(), ms.state, 65536);
+			std::memcpy(prev.data(), ms.state + 65536, 65536);
+			std::memcpy(&c, ms.state + 131072, sizeof c);
+			fe_load(fe, c, data, n, H, head.data(), prev.data());
+		} else {
+			fe_init(fe, data, n, head.data(), prev.data());
+			fe_set_dictionary(fe, H);
+		}
 		blk_start.assign(n / kBlockSyms + 3, 0);
 		fe_run(fe, lp, strategy, (flush_then_finish || flush_only) ? 2 : 0, [&](uint32_t sym) { syms.push_back(sym); },
 		       [&](uint32_t start, bool ok, bool last) {
@@ -133,7 +171,14 @@ static int model_run(const uint8_t *data, uint32_t n, uint32_t H, uint32_t abs_b
 			       blk_start[nblocks] = start;
 			       blk_ptop[nblocks] = ok ? 0xFFFFFFFEu : 0xFFFFFFFFu;
 			       ++nblocks;
-		       });
+		       }, ms.cum, ms.nchunks, ms.busy_last != 0);
+		if (ms.state) {
+			FastCarry c;
+			fe_save(fe, c);
+			std::memcpy(ms.state, head.data(), 65536);
+			std::memcpy(ms.state + 65536, prev.data(), 65536);
+			std::memcpy(ms.state + 131072, &c, sizeof c);
+		}
 		total = (uint32_t)syms.size();
 		goto emit_blocks;
 	}

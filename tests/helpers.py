@@ -29,3 +29,56 @@ def corpus_small():
     out.append(("ab_70000", b"ab" * 35000))
     out.append(("t8", crafted_t8()))
     return out
+
+
+def oracle_calls(level, segs, dictionary=None, busy_last=True, nowrap=None):
+    """reference call sequence over oracle.Deflater: per segment SetInput(chunk) + Deflate-until-needs-input for every
+    chunk (the last one only if busy_last), then Flush() (Finish() for the last segment) and drain"""
+    from oracle_lib import Deflater
+    d = Deflater(level, nowrap=(dictionary is None) if nowrap is None else nowrap)
+    if dictionary is not None:
+        d.set_dictionary(dictionary)
+    out = bytearray()
+
+    def drain():
+        while True:
+            b = d.deflate(4096)
+            if not b:
+                break
+            out.extend(b)
+    for i, (seg, chunks) in enumerate(segs):
+        pos = 0
+        for k, c in enumerate(chunks):
+            d.set_input(seg[pos:pos + c])
+            pos += c
+            if busy_last or k + 1 < len(chunks):
+                drain()
+                assert d.needs_input
+        if i + 1 < len(segs):
+            d.flush()
+        else:
+            d.finish()
+        drain()
+    return bytes(out)
+
+
+def random_chunks(rnd, n):
+    if n == 0:
+        return [0] if rnd.random() < 0.5 else []
+    style = rnd.choice(["one", "small", "mixed", "window"])
+    if style == "one":
+        return [n]
+    out, left = [], n
+    while left:
+        if style == "small":
+            c = rnd.choice([1, 2, 3, 100, 512, 4096])
+        elif style == "mixed":
+            c = rnd.randrange(1, 70000)
+        else:
+            c = rnd.choice([32767, 32768, 65273, 65274, 65275, 262, 261, 1])
+        c = min(c, left)
+        out.append(c)
+        left -= c
+    return out
+
+

@@ -3,11 +3,12 @@ serially by tests/cpu_model/model.cpp must reproduce the oracle bit for bit."""
 import ctypes as C
 import os
 import subprocess
+import zlib
 
 import numpy as np
 import pytest
 
-from helpers import corpus_small
+from helpers import corpus_small, oracle_calls as _oracle_calls, random_chunks as _random_chunks
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -78,6 +79,13 @@ class _SegmentedModel:
         self.M = C.CDLL(so)
         self.M.model_deflate_ex.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_int,
                                             C.c_int, C.c_int, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
+        self.M.model_deflate_ex2.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_int,
+                                             C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
+                                             C.c_uint64, C.POINTER(C.c_uint64)]
+        # levels 0-4: what the engine carries between segments (head[] / prev[] / scalars), as k_fast keeps it in
+        # b200z_history.engine_state
+        self.state = np.zeros(self.M.model_state_bytes(), np.uint8)
+        self.started = False
         self.level, self.strategy = level, strategy
         self.hist = bytearray()
         self.mask = bytearray()
@@ -102,15 +110,27 @@ class _SegmentedModel:
             return
         self.remember(d[-32506:])
 
-    def segment(self, seg, end_mode):
+    def segment(self, seg, end_mode, chunks=None, busy_last=True):
+        """chunks: the sizes of the SetInput calls that delivered `seg` (None: one call); busy_last: Deflate() was called
+        behind the last of them before Flush() / Finish()"""
         H = len(self.hist)
         buf = np.frombuffer(bytes(self.hist) + bytes(seg) + b"\0", dtype=np.uint8).copy()
         mask = np.frombuffer(bytes(self.mask) + b"\0", dtype=np.uint8).copy()
-        cap = len(seg) + len(seg) // 8 + 1024
+        cap = len(seg) + len(seg) // 8 + 1024 + 5 * (len(chunks) if chunks else 0)
         out = np.zeros(cap, np.uint8)
         bits = C.c_uint64(0)
-        rc = self.M.model_deflate_ex(buf.ctypes.data, H + len(seg), H, self.seen, self.tail_count, mask.ctypes.data, self.level,
-                                     self.strategy, end_mode, out.ctypes.data, cap, C.byref(bits))
+        if self.level >= 5 and chunks is None:
+            rc = self.M.model_deflate_ex(buf.ctypes.data, H + len(seg), H, self.seen, self.tail_count, mask.ctypes.data,
+                                         self.level, self.strategy, end_mode, out.ctypes.data, cap, C.byref(bits))
+        else:
+            if chunks:
+                assert sum(chunks) == len(seg)
+            cum = np.cumsum(np.array(chunks if chunks else [len(seg)], dtype=np.uint32), dtype=np.uint32)
+            rc = self.M.model_deflate_ex2(buf.ctypes.data, H + len(seg), H, self.seen, self.tail_count, mask.ctypes.data,
+                                          self.level, self.strategy, end_mode, cum.ctypes.data, len(cum), 1 if busy_last else 0,
+                                          self.state.ctypes.data, 1 if self.started else 0, out.ctypes.data, cap,
+                                          C.byref(bits))
+        self.started = True
         assert rc == 0, rc
         nb = bits.value
         o = bytearray(out[:(nb + 7) // 8].tobytes())
@@ -207,3 +227,52 @@ def test_model_random_segments_and_dictionaries(model, oracle):
         if dic is not None:
             ref = ref[6:-4]
         assert _model_segments(level, segs, dictionary=dic, strategy=strat) == ref, (trial, n, cuts, level, strat)
+
+
+# ---- levels 0-4: SetInput schedules (trap T9) and input after Flush() ----------------------------------------------
+def _model_calls(level, segs, dictionary=None, busy_last=True):
+    m = _SegmentedModel(ROOT, level)
+    if dictionary is not None:
+        m.set_dictionary(dictionary)
+    for i, (seg, chunks) in enumerate(segs):
+        m.segment(seg, 2 if i + 1 < len(segs) else 0, chunks=chunks, busy_last=busy_last)
+    return bytes(m.out)
+
+
+@pytest.mark.parametrize("level", [0, 1, 2, 3, 4])
+def test_model_setinput_schedules_and_flush_levels_0_to_4(model, oracle, level):
+    """DeflateStored / DeflateFast depend on how the input arrives (trap T9) and keep window-relative state across
+    Flush(): the engine code the kernels run (stored_run / fe_run with a schedule, FastCarry / StoredCarry between
+    segments) must reproduce the reference for arbitrary call sequences."""
+    import random
+    from sharpziplib_b200 import datagen
+    rnd = random.Random(1000 + level)
+    text = datagen.gen_text(400000, 31).tobytes()
+    mixed = datagen.silesia_mix(3, 300000, config=5).tobytes()
+    for trial in range(int(os.environ.get('B200Z_SCHED_TRIALS', '10'))):
+        src = text if trial % 2 == 0 else mixed
+        n = rnd.choice([0, 5, 3000, 66000, 140000, 250000])
+        nseg = rnd.choice([1, 1, 2, 3, 5])
+        cuts = sorted(rnd.randrange(0, n + 1) for _ in range(nseg - 1))
+        bounds = [0] + cuts + [n]
+        segs = []
+        for a, b in zip(bounds[:-1], bounds[1:]):
+            seg = src[a:b]
+            chunks = _random_chunks(rnd, len(seg))
+            segs.append((seg, chunks))
+        busy_last = rnd.random() < 0.7
+        dictionary = None
+        if level != 0 and rnd.random() < 0.3:
+            dictionary = src[-rnd.choice([3, 500, 32506, 40000]):]
+        ref = _oracle_calls(level, segs, dictionary, busy_last)
+        if dictionary is not None:
+            ref = ref[6:-4]
+        got = _model_calls(level, segs, dictionary, busy_last)
+        assert got == ref, (level, trial, n, [len(s) for s, _ in segs], [c[:6] for _, c in segs], busy_last,
+                            None if dictionary is None else len(dictionary))
+        do = zlib.decompressobj(-15) if dictionary is None else zlib.decompressobj(-15, zdict=dictionary)
+        back, whole = do.decompress(got), b"".join(s for s, _ in segs)
+        # Finish() right behind an undrained SetInput at level 0 ends the stream early in the reference itself
+        # (DeflateStored takes lastBlock = finish even while input is still outside the window, DeflaterEngine.cs:631):
+        # reproduced, not repaired
+        assert back == whole or (level == 0 and not busy_last and whole.startswith(back))
