@@ -1,0 +1,178 @@
+// k_tile_parse.cuh -- EXPERIMENTAL, NOT PART OF libb200z.so (build.sh does not compile it; tools/check_experimental.sh only
+// compiles it to look at registers / shared memory / SASS).  Written at the end of round 1 without GPU time left: it has
+// never run.  It is the round-2 starting point that DESIGN.md 7b describes, kept next to the kernels it is meant to replace.
+//
+// Why: tools/match_stats.cpp shows that k_match (a match table for EVERY position) walks 7.0x the chain candidates the
+// reference walks at level 6 (24.6x at level 9): DeflateSlow only searches at the positions it visits (49.6 % on the bench
+// mix, 18-28 % on the compressible classes), and those are the cheap ones.  This kernel lets the parse drive the search.
+//
+// What: one CTA per tile of kFTile positions.  The tile's window (32 KiB of history + the tile + the longest match) and the
+// window's link entries are staged in shared memory exactly as k_match stages them.  Thread t owns the 32-position segment
+// t of the tile; a warp is therefore one ROUND of 1024 positions (the unit k_parse_scan / k_parse_gather work on).  Every
+// thread parses its segment speculatively from a clean state with parse_step() (b200z_core.cuh, unchanged), its table
+// function searching ON DEMAND in the staged window with match_search() (unchanged) and remembering the answer per
+// position, so that the exit -> entry hand-off passes (across the whole CTA here, through shared memory) never search a
+// position twice.  The final pass emits every round's symbols into the round's slot and leaves a RoundRec per round, which
+// is what k_parse_chunk leaves today; tiles are stitched by k_parse_fix with chunk = kFTile, whose table function has to fall
+// back to a search in global memory where this kernel left "not computed" (mt[p].x == kFNone).
+//
+// Replaces: k_match + k_parse_chunk (k_links, k_parse_fix / _scan / _gather, k_plan, k_scan, k_emit stay).
+// To wire it (round 2): #include at the end of b200z_deflate.cu inside namespace b200z; tiles of kFTile instead of kTile in
+// deflate_plan_build; p->parse_chunk = kFTile; parse_round() needs the lazy table function for the fix-up.
+#pragma once
+
+constexpr int kFTile = 16384;                 // positions per CTA
+constexpr int kFThreads = kFTile / kSeg;      // 512 threads, one per 32-position segment; 16 warps = 16 rounds
+constexpr int kFHist = 32768;                 // history staged in front of the tile
+constexpr int kFData = kFHist + kFTile + 320; // bytes of window staged (tile + max match + pad), a multiple of 16
+constexpr uint32_t kFNone = 0xFFFFFFFFu;      // memo: position not searched yet
+constexpr uint32_t kFNeedB = 0x80000000u;     // memo: quarter-budget result differs from the full one, search again if asked
+constexpr int kFSmem = kFData + 2 * (kFHist + kFTile) + 4 * kFTile + kFThreads * 20 + 64;
+static_assert(kFData % 16 == 0, "staging uses 16-byte copies");
+static_assert(kFSmem <= 227 * 1024, "one CTA per SM");
+
+struct FCarry { // ParseCarry as five words in shared memory
+	uint32_t p, mlen, mstart, prevAvail, last_top;
+};
+__device__ __forceinline__ FCarry f_pack(const ParseCarry &c) { return FCarry{c.st.p, c.st.mlen, c.st.mstart, c.st.prevAvail, c.last_top}; }
+__device__ __forceinline__ ParseCarry f_unpack(const FCarry &f) {
+	ParseCarry c;
+	c.st.p = f.p;
+	c.st.mlen = f.mlen;
+	c.st.mstart = f.mstart;
+	c.st.prevAvail = f.prevAvail;
+	c.last_top = f.last_top;
+	return c;
+}
+
+__global__ void __launch_bounds__(kFThreads, 1)
+    k_tile_parse(const uint8_t *__restrict__ in, const uint16_t *__restrict__ link, uint2 *__restrict__ mt,
+                 uint32_t *__restrict__ sym_local, const int64_t *__restrict__ in_off, const int64_t *__restrict__ in_len,
+                 const int2 *__restrict__ tile_desc, const uint32_t *__restrict__ rnd_off, RoundRec *__restrict__ recs,
+                 const uint32_t *__restrict__ hist, const int64_t *__restrict__ bias, LevelParams lp, int strategy) {
+	extern __shared__ __align__(16) uint8_t smem[];
+	uint8_t *s_data = smem;
+	uint16_t *s_link = reinterpret_cast<uint16_t *>(smem + kFData);
+	uint32_t *s_memo = reinterpret_cast<uint32_t *>(smem + kFData + 2 * (kFHist + kFTile));
+	FCarry *s_exit = reinterpret_cast<FCarry *>(smem + kFData + 2 * (kFHist + kFTile) + 4 * kFTile);
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const int2 td = tile_desc[blockIdx.x]; // (stream, first position of the tile: a multiple of kFTile)
+	const uint32_t n = (uint32_t)in_len[td.x];
+	const int64_t off = in_off[td.x];
+	const uint8_t *data = in + off;
+	const uint16_t *lnk = link + off;
+	const uint32_t t0 = (uint32_t)td.y;
+	const uint32_t t1 = (n - t0 > (uint32_t)kFTile) ? t0 + kFTile : n;
+	const uint32_t w0 = t0 >= (uint32_t)kFHist ? t0 - kFHist : 0u;
+	uint32_t dend = t1 + 272;
+	if (dend > n) dend = n;
+	const uint32_t H = hist[td.x], ab = (uint32_t)bias[td.x];
+	// ---- stage the window (as k_match does; w0 and the slot base are 16-byte aligned) ----
+	{
+		const uint32_t nbytes = dend - w0, nvec = nbytes >> 4;
+		const uint4 *src = reinterpret_cast<const uint4 *>(data + w0);
+		uint4 *dst = reinterpret_cast<uint4 *>(s_data);
+		for (uint32_t i = tid; i < nvec; i += kFThreads) dst[i] = __ldg(src + i);
+		for (uint32_t i = (nvec << 4) + tid; i < nbytes; i += kFThreads) s_data[i] = data[w0 + i];
+		const uint32_t nl = t1 - w0, nlv = nl >> 3;
+		const uint4 *lsrc = reinterpret_cast<const uint4 *>(lnk + w0);
+		uint4 *ldst = reinterpret_cast<uint4 *>(s_link);
+		for (uint32_t i = tid; i < nlv; i += kFThreads) ldst[i] = __ldg(lsrc + i);
+		for (uint32_t i = (nlv << 3) + tid; i < nl; i += kFThreads) s_link[i] = lnk[w0 + i];
+		for (uint32_t i = tid; i < (uint32_t)kFTile; i += kFThreads) s_memo[i] = kFNone;
+	}
+	__syncthreads();
+	// ---- the table function: search on demand, once per position ----
+	auto tabf = [&](uint32_t p, uint32_t &a, uint32_t &b) {
+		const uint32_t m = s_memo[p - t0]; // only the thread that owns p's segment ever touches this word
+		if (m == kFNone) {
+			match_search(s_data, s_link, w0, p, n, lp, a, b, ab);
+			s_memo[p - t0] = a | (a != b ? kFNeedB : 0u);
+		} else {
+			a = m & ~kFNeedB;
+			b = a;
+			if (m & kFNeedB) { // rare: a hand-off pass asks again for a position whose quarter-budget answer differs
+				LevelParams lq = lp;
+				lq.chain = lp.chain >> 2;
+				uint32_t dummy;
+				match_search(s_data, s_link, w0, p, n, lq, b, dummy, ab);
+			}
+		}
+	};
+	auto bytef = [&](uint32_t q) { return (uint32_t)s_data[q - w0]; };
+	auto slowf = [&](uint32_t p, uint32_t m0, uint32_t budget) { return match_search_above(data, lnk, p, n, m0, budget, ab); };
+	// ---- speculative parse of every segment, exit -> entry hand-off across the CTA until nothing changes ----
+	const uint32_t seg0 = t0 + (uint32_t)tid * kSeg, seg_end = seg0 + kSeg;
+	const uint32_t lim = seg_end < n ? seg_end : n;
+	// thread 0's entry is exact for the first tile of a stream (Reset state, also right behind a dictionary or a flush) and a
+	// guess otherwise; k_parse_fix repairs the guess
+	ParseCarry entry = clean_carry(seg0 > H ? seg0 : H), ex = entry;
+	uint32_t cnt = 0;
+	bool changed = true;
+	for (int it = 0; it < kFThreads + 2; it++) {
+		if (changed) {
+			ex = entry;
+			cnt = 0;
+		}
+		bool act = changed && ex.st.p < lim;
+		while (__any_sync(0xffffffffu, act)) { // the lanes of a warp step together (a per-lane loop would leave them diverged)
+			if (act) {
+				ex.last_top = ex.st.p;
+				uint32_t s2;
+				cnt += (uint32_t)parse_step(ex.st, n, lp, strategy, tabf, bytef, slowf, s2);
+				act = ex.st.p < lim;
+			}
+			__syncwarp();
+		}
+		s_exit[tid] = f_pack(ex);
+		__syncthreads();
+		changed = false;
+		if (tid > 0) {
+			const ParseCarry ne = f_unpack(s_exit[tid - 1]);
+			changed = !carry_equal(ne, entry);
+			entry = ne;
+		}
+		if (!__syncthreads_or(changed ? 1 : 0)) break; // (also keeps s_exit stable until everybody has read it)
+	}
+	// ---- final pass: every warp (= round) emits its symbols at prefix-summed offsets into the round's slot ----
+	const uint32_t rbase = t0 + (uint32_t)warp * kRound;
+	if (rbase < n) { // warp-uniform
+		uint32_t incl = cnt;
+		for (int o = 1; o < 32; o <<= 1) {
+			const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+			if (lane >= o) incl += t;
+		}
+		uint32_t idx = incl - cnt;
+		uint32_t *sround = sym_local + off + rbase;
+		ParseCarry c = entry;
+		bool act = c.st.p < lim;
+		while (__any_sync(0xffffffffu, act)) {
+			if (act) {
+				c.last_top = c.st.p;
+				uint32_t s2;
+				if (parse_step(c.st, n, lp, strategy, tabf, bytef, slowf, s2)) sround[idx++] = s2;
+				act = c.st.p < lim;
+			}
+			__syncwarp();
+		}
+		const ParseCarry last = shfl_carry(c, 31);
+		const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+		if (lane == 0) {
+			RoundRec r;
+			r.p = last.st.p;
+			r.mlen = last.st.mlen;
+			r.mstart = last.st.mstart;
+			r.prevAvail = last.st.prevAvail;
+			r.last_top = last.last_top;
+			r.cnt = total;
+			(recs + rnd_off[td.x])[rbase / kRound] = r;
+		}
+	}
+	__syncthreads();
+	// ---- what was searched goes to the table for the fix-up; the rest is marked "not computed" ----
+	uint2 *out = mt + off + t0;
+	for (uint32_t i = tid; i < t1 - t0; i += kFThreads) {
+		const uint32_t m = s_memo[i];
+		out[i] = m == kFNone ? make_uint2(kFNone, kFNone) : make_uint2(m & ~kFNeedB, (m & kFNeedB) ? kFNone : (m & ~kFNeedB));
+	}
+}
