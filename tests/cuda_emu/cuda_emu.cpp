@@ -1,0 +1,104 @@
+// cuda_emu.cpp -- TEST INFRASTRUCTURE: the block scheduler of cuda_emu.h
+#include "cuda_emu.h"
+
+namespace emu {
+
+Block *g_block = nullptr;
+Fiber *g_cur = nullptr;
+
+static void fiber_main() {
+	g_block->body();
+	Fiber *f = g_cur;
+	Block &b = *g_block;
+	f->done = true;
+	// a thread that has left no longer takes part in barriers (CUDA: exited threads are not waited for)
+	Warp &w = b.warps[f->warp];
+	w.live--;
+	b.live--;
+	if (w.live > 0 && w.arrived >= w.live) {
+		w.arrived = 0;
+		w.gen++;
+	}
+	if (b.live > 0 && b.arrived >= b.live) {
+		b.arrived = 0;
+		b.gen++;
+	}
+	swapcontext(&f->ctx, &b.sched);
+}
+
+static std::vector<void *> g_stacks;
+static uint8_t *g_smem = nullptr;
+
+void launch(dim3 grid, dim3 block, size_t smem_bytes, std::function<void()> body) {
+	const int nt = (int)(block.x * block.y * block.z);
+	if (smem_bytes > kMaxSmem) {
+		fprintf(stderr, "cuda_emu: %zu bytes of dynamic shared memory\n", smem_bytes);
+		abort();
+	}
+	if (!g_smem) g_smem = (uint8_t *)aligned_alloc(256, kMaxSmem + 4096);
+	while ((int)g_stacks.size() < nt) {
+		void *s = mmap(nullptr, kStack, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
+		if (s == MAP_FAILED) abort();
+		g_stacks.push_back(s);
+	}
+	Block b;
+	b.bdim = block;
+	b.gdim = grid;
+	b.body = body;
+	b.smem = g_smem;
+	for (unsigned bz = 0; bz < grid.z; bz++)
+		for (unsigned by = 0; by < grid.y; by++)
+			for (unsigned bx = 0; bx < grid.x; bx++) {
+				b.bid = dim3(bx, by, bz);
+				memset(g_smem, 0xCD, smem_bytes + 64); // shared memory is not cleared between blocks
+				memset(g_smem + smem_bytes, 0xEE, 64);
+				b.fibers.assign((size_t)nt, Fiber());
+				b.warps.assign((size_t)(nt + 31) / 32, Warp());
+				b.live = nt;
+				b.arrived = 0;
+				b.gen = 0;
+				b.or_acc = 0;
+				g_block = &b;
+				for (int t = 0; t < nt; t++) {
+					Fiber &f = b.fibers[(size_t)t];
+					f.linear = t;
+					f.lane = t & 31;
+					f.warp = t >> 5;
+					f.tid = dim3((unsigned)t % block.x, ((unsigned)t / block.x) % block.y, (unsigned)t / (block.x * block.y));
+					b.warps[(size_t)f.warp].live++;
+					getcontext(&f.ctx);
+					f.ctx.uc_stack.ss_sp = g_stacks[(size_t)t];
+					f.ctx.uc_stack.ss_size = kStack;
+					f.ctx.uc_link = nullptr;
+					makecontext(&f.ctx, fiber_main, 0);
+				}
+				int remaining = nt;
+				uint64_t spins = 0;
+				while (remaining > 0) {
+					int progressed = 0;
+					for (int t = 0; t < nt; t++) {
+						Fiber &f = b.fibers[(size_t)t];
+						if (f.done) continue;
+						g_cur = &f;
+						swapcontext(&b.sched, &f.ctx);
+						if (f.done) {
+							remaining--;
+							progressed = 1;
+						}
+					}
+					if (!progressed && ++spins > 200000000ull) {
+						fprintf(stderr, "cuda_emu: block (%u,%u,%u) does not finish: a barrier some threads never reach?\n", bx, by, bz);
+						abort();
+					}
+				}
+				for (int i = 0; i < 64; i++)
+					if (g_smem[smem_bytes + (size_t)i] != 0xEE) {
+						fprintf(stderr, "cuda_emu: block (%u,%u,%u) wrote behind its %zu bytes of dynamic shared memory\n", bx, by, bz, smem_bytes);
+						abort();
+					}
+			}
+	g_block = nullptr;
+	g_cur = nullptr;
+}
+
+} // namespace emu
