@@ -5,12 +5,14 @@ namespace emu {
 
 Block *g_block = nullptr;
 Fiber *g_cur = nullptr;
+uint64_t g_events = 0;
 
 static void fiber_main() {
 	g_block->body();
 	Fiber *f = g_cur;
 	Block &b = *g_block;
 	f->done = true;
+	g_events++;
 	// a thread that has left no longer takes part in barriers (CUDA: exited threads are not waited for)
 	Warp &w = b.warps[f->warp];
 	w.live--;
@@ -73,21 +75,20 @@ void launch(dim3 grid, dim3 block, size_t smem_bytes, std::function<void()> body
 					makecontext(&f.ctx, fiber_main, 0);
 				}
 				int remaining = nt;
-				uint64_t spins = 0;
+				b.or_reset_gen = 0xFFFFFFFFu;
 				while (remaining > 0) {
-					int progressed = 0;
+					const uint64_t before = g_events;
 					for (int t = 0; t < nt; t++) {
 						Fiber &f = b.fibers[(size_t)t];
 						if (f.done) continue;
 						g_cur = &f;
 						swapcontext(&b.sched, &f.ctx);
-						if (f.done) {
-							remaining--;
-							progressed = 1;
-						}
+						if (f.done) remaining--;
 					}
-					if (!progressed && ++spins > 200000000ull) {
-						fprintf(stderr, "cuda_emu: block (%u,%u,%u) does not finish: a barrier some threads never reach?\n", bx, by, bz);
+					if (remaining > 0 && g_events == before) {
+						// every thread was resumed and none got past what it waits for
+						fprintf(stderr, "cuda_emu: deadlock in block (%u,%u,%u): %d of %d threads wait at barriers the others never reach\n",
+						        bx, by, bz, remaining, nt);
 						abort();
 					}
 				}

@@ -61,7 +61,8 @@ struct Block {
 	std::vector<Warp> warps;
 	int live = 0, arrived = 0;
 	uint32_t gen = 0;
-	int or_acc = 0, or_result = 0;
+	int or_acc = 0;
+	uint32_t or_reset_gen = 0xFFFFFFFFu;
 	dim3 bid, bdim, gdim;
 	uint8_t *smem = nullptr;
 	ucontext_t sched;
@@ -69,12 +70,14 @@ struct Block {
 };
 extern Block *g_block;
 extern Fiber *g_cur;
+extern uint64_t g_events; // barrier arrivals and thread exits: a scheduling round without any is a deadlock
 
 inline void yield() { swapcontext(&g_cur->ctx, &g_block->sched); }
 
 inline void block_barrier() {
 	Block &b = *g_block;
 	const uint32_t gen = b.gen;
+	g_events++; // an arrival is progress
 	if (++b.arrived >= b.live) {
 		b.arrived = 0;
 		b.gen++;
@@ -85,6 +88,7 @@ inline void block_barrier() {
 inline void warp_barrier() {
 	Warp &w = g_block->warps[g_cur->warp];
 	const uint32_t gen = w.gen;
+	g_events++;
 	if (++w.arrived >= w.live) {
 		w.arrived = 0;
 		w.gen++;
@@ -119,10 +123,12 @@ static inline int __syncthreads_or(int pred) {
 	emu::Block &b = *emu::g_block;
 	b.or_acc |= pred ? 1 : 0;
 	emu::block_barrier();
-	const int r = b.or_acc;
-	emu::block_barrier();
-	if (emu::g_cur->linear == 0 || emu::g_block->fibers[0].done) b.or_acc = 0;
-	emu::block_barrier();
+	const int r = b.or_acc; // everybody has contributed
+	emu::block_barrier();   // everybody has read
+	if (b.or_reset_gen != b.gen) { // the first thread to get here clears the accumulator for the next use
+		b.or_acc = 0;
+		b.or_reset_gen = b.gen;
+	}
 	return r;
 }
 static inline void __syncwarp(uint32_t = 0xffffffffu) { emu::warp_barrier(); }

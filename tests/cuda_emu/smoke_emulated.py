@@ -1,0 +1,72 @@
+"""TEST INFRASTRUCTURE: a small end-to-end pass over every kernel family on the CUDA emulator, against the oracle.
+Run by tests/test_cuda_emu.py in a subprocess (the emulator library must never sit in a process that also tests the real
+one).  Exit code 0 = everything matched."""
+import io
+import os
+import sys
+import zlib
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import run_emulated  # noqa: E402
+
+run_emulated.install()
+import numpy as np  # noqa: E402
+import oracle_lib as O  # noqa: E402
+import sharpziplib_b200 as z  # noqa: E402
+from helpers import oracle_calls  # noqa: E402
+from sharpziplib_b200 import datagen  # noqa: E402
+
+z.init(0)
+bufs = [datagen.silesia_mix(0, 20000).tobytes(), datagen.silesia_mix(3, 9000).tobytes(), b"", b"a", bytes(5000)]
+
+# deflate: lazy levels (k_links, k_match, k_parse_*, k_plan, k_scan, k_emit), greedy levels (k_fast), stored (k_stored)
+for level in (6, 9, 1, 0):
+    outs, _ = z.deflate_batch(bufs, level=level)
+    assert outs == [O.deflate(b, level=level) for b in bufs], level
+outs, checks = z.deflate_batch(bufs[:2], level=6, wrap=1)  # zlib framing: Adler-32 on the device (k_checksum)
+assert outs == [O.deflate(b, level=6, nowrap=False) for b in bufs[:2]]
+
+# inflate (k_inflate), framed inflate (k_wrap_head / k_wrap_tail), truncation and restart points
+comp = [O.deflate(b, level=6) for b in bufs]
+back, used, st = z.inflate_batch(comp, [len(b) for b in bufs])
+assert back == bufs and [int(u) for u in used] == [len(c) for c in comp]
+zl = [zlib.compress(b, 6) for b in bufs[:2]]
+back, used, st = z.inflate_batch(zl, [len(b) for b in bufs[:2]], wrap=1)
+assert back == bufs[:2]
+back, used, st = z.inflate_batch([comp[0][:3000]], [len(bufs[0])], raise_on_error=False)
+assert int(st[0]) & 0xFF == 8 and bufs[0].startswith(back[0])
+
+# checksums
+for b in bufs:
+    c = z.Crc32(); c.Update(b)
+    a = z.Adler32(); a.Update(b)
+    assert c.Value == zlib.crc32(b) and a.Value == zlib.adler32(b)
+
+# handles: a SetInput schedule with a Flush in the middle at a greedy level and at level 0; an Inflater fed in pieces
+text = datagen.gen_text(30000, 4).tobytes()
+for level in (1, 0, 6):
+    segs = [(text[:12000], [5000, 7000]), (text[12000:], [18000])]
+    d = z.Deflater(level, True)
+    out = bytearray()
+    buf = bytearray(1 << 16)
+    for i, (seg, chunks) in enumerate(segs):
+        pos = 0
+        for c in chunks:
+            d.SetInput(seg[pos:pos + c]); pos += c
+            while True:
+                k = d.Deflate(buf)
+                if k <= 0:
+                    break
+                out += buf[:k]
+        d.Flush() if i == 0 else d.Finish()
+        while True:
+            k = d.Deflate(buf)
+            if k <= 0:
+                break
+            out += buf[:k]
+    assert bytes(out) == oracle_calls(level, segs, None, True, nowrap=True), level
+c = O.deflate(text, level=6, nowrap=False)
+ins = z.InflaterInputStream(io.BytesIO(c), z.Inflater(False), 1024)
+assert ins.read() == text
+print("emulated smoke ok")

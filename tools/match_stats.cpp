@@ -124,7 +124,7 @@ int main(int argc, char **argv) {
 	// how well does a cheap proxy parse (tables from the first `hops` candidates only) predict the positions the real parse visits?
 	for (int hops : {1, 2, 4, 8}) {
 		rewind(f);
-		uint64_t vt = 0, vp = 0, both = 0;
+		uint64_t vt = 0, vp = 0, both = 0, cands_pred = 0, cands_miss = 0, misses = 0;
 		while (fread(buf.data(), 1, bs, f) == bs) {
 			const uint32_t n = bs;
 			std::vector<uint16_t> link;
@@ -157,10 +157,119 @@ int main(int argc, char **argv) {
 				vt += vis[p] & 1;
 				vp += (vis[p] >> 1) & 1;
 				both += vis[p] == 3;
+				if (vis[p] & 2) { // predicted: searched in full, balanced like k_match
+					Cnt c;
+					walk(buf.data(), link.data(), p, n, 2, (uint32_t)lp.chain, (uint32_t)lp.nice, c);
+					cands_pred += c.cands;
+				} else if (vis[p] & 1) { // visited by the real parse but not predicted: searched on demand inside the parse
+					Cnt c;
+					walk(buf.data(), link.data(), p, n, 2, (uint32_t)lp.chain, (uint32_t)lp.nice, c);
+					cands_miss += c.cands;
+					misses++;
+				}
 			}
 		}
-		printf("proxy parse with %d-hop tables: visits %.1f%% of positions, covers %.1f%% of the real parse's visits\n", hops,
-		       100.0 * vp / all.pos, 100.0 * both / (vt ? vt : 1));
+		printf("proxy parse with %d-hop tables: visits %.1f%% of positions, covers %.1f%% of the real parse's visits; searching the "
+		       "predicted set walks %.1f candidates per position (all positions: %.1f), the %.2f%% of positions it misses walk %.2f\n",
+		       hops, 100.0 * vp / all.pos, 100.0 * both / (vt ? vt : 1), (double)cands_pred / all.pos, (double)all.cands / all.pos,
+		       100.0 * misses / all.pos, (double)cands_miss / all.pos);
+	}
+	// ---- lock-step cost of the tile kernel (experimental/k_tile_parse.cuh): a warp's loop iteration costs what its slowest
+	// lane walks in that iteration; passes as the kernel runs them (speculative pass, hand-off passes with memo, emit pass)
+	{
+		rewind(f);
+		const uint32_t kSeg = 32, kFTile = 16384, kFThreads = 512;
+		uint64_t warp_steps = 0, lane_cands = 0, iters = 0, parse_steps = 0;
+		while (fread(buf.data(), 1, bs, f) == bs) {
+			const uint32_t n = bs;
+			std::vector<uint16_t> link;
+			links(buf.data(), n, link);
+			auto bytef = [&](uint32_t q) { return (uint32_t)buf[q]; };
+			auto slowf = [&](uint32_t p, uint32_t m0, uint32_t budget) { return match_search_above(buf.data(), link.data(), p, n, m0, budget, 0u); };
+			for (uint32_t t0 = 0; t0 < n; t0 += kFTile) {
+				std::vector<uint32_t> memoA(kFTile, 0xFFFFFFFFu), memoB(kFTile, 0);
+				std::vector<ParseCarry> entry(kFThreads), ex(kFThreads);
+				std::vector<uint32_t> lim(kFThreads);
+				std::vector<char> changed(kFThreads, 1);
+				auto clean = [&](uint32_t p) { ParseCarry c; parse_init(c.st); c.st.p = p; c.last_top = p; return c; };
+				for (uint32_t t = 0; t < kFThreads; t++) {
+					const uint32_t seg0 = t0 + t * kSeg;
+					lim[t] = seg0 + kSeg < n ? seg0 + kSeg : n;
+					entry[t] = clean(seg0);
+				}
+				uint32_t last_cost = 0;
+				auto tabf = [&](uint32_t p, uint32_t &a, uint32_t &b) {
+					last_cost = 1; // a memo hit still costs a step
+					if (memoA[p - t0] == 0xFFFFFFFFu) {
+						Cnt c;
+						match_search(buf.data(), link.data(), 0u, p, n, lp, memoA[p - t0], memoB[p - t0]);
+						walk(buf.data(), link.data(), p, n, 2, (uint32_t)lp.chain, (uint32_t)lp.nice, c);
+						last_cost = (uint32_t)c.cands + 1;
+						lane_cands += c.cands;
+					}
+					a = memoA[p - t0];
+					b = memoB[p - t0];
+				};
+				for (int pass = 0; pass < 64; pass++) {
+					// warps in lock step: iteration i runs the i-th parse step of every lane that (re-)parses
+					for (uint32_t w = 0; w < kFThreads / 32; w++) {
+						bool any = true;
+						for (uint32_t l = 0; l < 32; l++)
+							if (changed[w * 32 + l]) ex[w * 32 + l] = entry[w * 32 + l];
+						while (any) {
+							any = false;
+							uint32_t worst = 0;
+							for (uint32_t l = 0; l < 32; l++) {
+								const uint32_t t = w * 32 + l;
+								if (!changed[t] || ex[t].st.p >= lim[t]) continue;
+								any = true;
+								ex[t].last_top = ex[t].st.p;
+								uint32_t s2;
+								last_cost = 1;
+								parse_step(ex[t].st, n, lp, 0, tabf, bytef, slowf, s2);
+								parse_steps++;
+								if (last_cost > worst) worst = last_cost;
+							}
+							if (any) {
+								warp_steps += worst;
+								iters++;
+							}
+						}
+					}
+					bool again = false;
+					changed[0] = 0;
+					std::vector<ParseCarry> prev(ex);
+					for (uint32_t t = 1; t < kFThreads; t++) {
+						changed[t] = !carry_equal(prev[t - 1], entry[t]);
+						entry[t] = prev[t - 1];
+						again |= changed[t] != 0;
+					}
+					if (!again) break;
+				}
+				// emit pass: every lane parses its segment once more, all from the memo
+				for (uint32_t w = 0; w < kFThreads / 32; w++) {
+					uint32_t longest = 0;
+					for (uint32_t l = 0; l < 32; l++) {
+						ParseCarry c = entry[w * 32 + l];
+						uint32_t k = 0;
+						while (c.st.p < lim[w * 32 + l]) {
+							uint32_t s2;
+							parse_step(c.st, n, lp, 0, tabf, bytef, slowf, s2);
+							k++;
+						}
+						if (k > longest) longest = k;
+					}
+					warp_steps += longest;
+					iters += longest;
+				}
+			}
+		}
+		const double km_steps = (double)all.cands / 32.0 / (14.8 / 32.0); // k_match: measured 14.8 of 32 lanes per instruction
+		printf("tile kernel, lock-step model: %llu warp candidate-steps (%.2f per position), %llu loop iterations, lanes busy %.1f%%;\n"
+		       "   k_match at its measured lane occupancy: %.0f warp candidate-steps (%.2f per position) -> ratio %.2fx fewer\n",
+		       (unsigned long long)warp_steps, (double)warp_steps / all.pos, (unsigned long long)iters,
+		       100.0 * (double)(lane_cands + parse_steps) / (32.0 * (double)warp_steps), km_steps, km_steps / all.pos,
+		       km_steps / (double)warp_steps);
 	}
 	auto pr = [&](const char *name, const Cnt &c) {
 		printf("%s: positions %llu, searched %llu (%.1f%%), candidates %llu (%.1f per searched, %.1f per position)\n", name,
