@@ -176,3 +176,167 @@ __global__ void __launch_bounds__(kFThreads, 1)
 		out[i] = m == kFNone ? make_uint2(kFNone, kFNone) : make_uint2(m & ~kFNeedB, (m & kFNeedB) ? kFNone : (m & ~kFNeedB));
 	}
 }
+
+// ------------------------------------------------------------------------------------------------------------------
+// k_tile_parse2 -- "guess, batch, re-parse".  k_tile_parse above lets every lane search for itself, and the lock-step model
+// (tools/match_stats.cpp) predicts 18 % busy lanes: a warp iteration costs what its slowest lane walks.  Here a segment
+// that needs an entry nobody has computed yet takes a 1-hop PROXY for it (one candidate, cheap), notes the position in the
+// tile's request list and parses on; at the end of the pass the whole CTA serves the list as one batch (every thread takes
+// requests, all walks start together -- the shape k_match has), then the segments that used a proxy or whose entry changed
+// parse again.  Same tool, same workload: 5.6 passes per tile on average (11 at most), batches of 45 % / 3.7 % / 1.0 % /
+// 0.2 % ... of the tile's positions, 11.9 candidates per position in balanced batches instead of k_match's 34.3, parse
+// work of 0.08 lock-step iterations per position: about 2.4x less issue work than k_match + k_parse together.
+// Interface as k_tile_parse plus `scratch` (4 bytes per position that are free until k_parse_gather: the request list).
+// ------------------------------------------------------------------------------------------------------------------
+constexpr uint32_t kFReq = 0xFFFFFFFEu; // memo: requested, the batch has not run yet
+
+__global__ void __launch_bounds__(kFThreads, 1)
+    k_tile_parse2(const uint8_t *__restrict__ in, const uint16_t *__restrict__ link, uint2 *__restrict__ mt,
+                  uint32_t *__restrict__ sym_local, const int64_t *__restrict__ in_off, const int64_t *__restrict__ in_len,
+                  const int2 *__restrict__ tile_desc, const uint32_t *__restrict__ rnd_off, RoundRec *__restrict__ recs,
+                  const uint32_t *__restrict__ hist, const int64_t *__restrict__ bias, uint32_t *__restrict__ scratch, LevelParams lp,
+                  int strategy) {
+	extern __shared__ __align__(16) uint8_t smem[];
+	uint8_t *s_data = smem;
+	uint16_t *s_link = reinterpret_cast<uint16_t *>(smem + kFData);
+	uint32_t *s_memo = reinterpret_cast<uint32_t *>(smem + kFData + 2 * (kFHist + kFTile));
+	FCarry *s_exit = reinterpret_cast<FCarry *>(smem + kFData + 2 * (kFHist + kFTile) + 4 * kFTile);
+	__shared__ uint32_t s_nreq;
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const int2 td = tile_desc[blockIdx.x];
+	const uint32_t n = (uint32_t)in_len[td.x];
+	const int64_t off = in_off[td.x];
+	const uint8_t *data = in + off;
+	const uint16_t *lnk = link + off;
+	const uint32_t t0 = (uint32_t)td.y;
+	const uint32_t t1 = (n - t0 > (uint32_t)kFTile) ? t0 + kFTile : n;
+	const uint32_t w0 = t0 >= (uint32_t)kFHist ? t0 - kFHist : 0u;
+	uint32_t dend = t1 + 272;
+	if (dend > n) dend = n;
+	const uint32_t H = hist[td.x], ab = (uint32_t)bias[td.x];
+	uint16_t *req = reinterpret_cast<uint16_t *>(scratch + off + t0); // positions relative to t0, at most one entry per position
+	{
+		const uint32_t nbytes = dend - w0, nvec = nbytes >> 4;
+		const uint4 *src = reinterpret_cast<const uint4 *>(data + w0);
+		uint4 *dst = reinterpret_cast<uint4 *>(s_data);
+		for (uint32_t i = tid; i < nvec; i += kFThreads) dst[i] = __ldg(src + i);
+		for (uint32_t i = (nvec << 4) + tid; i < nbytes; i += kFThreads) s_data[i] = data[w0 + i];
+		const uint32_t nl = t1 - w0, nlv = nl >> 3;
+		const uint4 *lsrc = reinterpret_cast<const uint4 *>(lnk + w0);
+		uint4 *ldst = reinterpret_cast<uint4 *>(s_link);
+		for (uint32_t i = tid; i < nlv; i += kFThreads) ldst[i] = __ldg(lsrc + i);
+		for (uint32_t i = (nlv << 3) + tid; i < nl; i += kFThreads) s_link[i] = lnk[w0 + i];
+		for (uint32_t i = tid; i < (uint32_t)kFTile; i += kFThreads) s_memo[i] = kFNone;
+		if (tid == 0) s_nreq = 0;
+	}
+	__syncthreads();
+	LevelParams l1 = lp; // the proxy: the first chain candidate only
+	l1.chain = 1;
+	bool used_proxy = false;
+	auto tabf = [&](uint32_t p, uint32_t &a, uint32_t &b) {
+		const uint32_t m = s_memo[p - t0]; // only the owner of p's segment reads or writes this word outside the batch phase
+		if (m < kFReq) {
+			a = m & ~kFNeedB;
+			b = a;
+			if (m & kFNeedB) {
+				LevelParams lq = lp;
+				lq.chain = lp.chain >> 2;
+				uint32_t dummy;
+				match_search(s_data, s_link, w0, p, n, lq, b, dummy, ab);
+			}
+			return;
+		}
+		if (m == kFNone) {
+			s_memo[p - t0] = kFReq;
+			req[atomicAdd(&s_nreq, 1u)] = (uint16_t)(p - t0);
+		}
+		used_proxy = true;
+		match_search(s_data, s_link, w0, p, n, l1, a, b, ab);
+	};
+	auto bytef = [&](uint32_t q) { return (uint32_t)s_data[q - w0]; };
+	auto slowf = [&](uint32_t p, uint32_t m0, uint32_t budget) { return match_search_above(data, lnk, p, n, m0, budget, ab); };
+	const uint32_t seg0 = t0 + (uint32_t)tid * kSeg, seg_end = seg0 + kSeg;
+	const uint32_t lim = seg_end < n ? seg_end : n;
+	ParseCarry entry = clean_carry(seg0 > H ? seg0 : H), ex = entry;
+	uint32_t cnt = 0;
+	bool dirty = true;
+	for (int pass = 0; pass < 4 * kFThreads; pass++) {
+		// ---- parse: exact entries where there are, proxies elsewhere ----
+		if (dirty) {
+			ex = entry;
+			cnt = 0;
+			used_proxy = false;
+		}
+		bool act = dirty && ex.st.p < lim;
+		while (__any_sync(0xffffffffu, act)) {
+			if (act) {
+				ex.last_top = ex.st.p;
+				uint32_t s2;
+				cnt += (uint32_t)parse_step(ex.st, n, lp, strategy, tabf, bytef, slowf, s2);
+				act = ex.st.p < lim;
+			}
+			__syncwarp();
+		}
+		s_exit[tid] = f_pack(ex);
+		__syncthreads();
+		// ---- batch: the CTA serves the pass's requests ----
+		const uint32_t nreq = s_nreq;
+		for (uint32_t r = tid; r < nreq; r += kFThreads) {
+			const uint32_t i = req[r];
+			uint32_t a, b;
+			match_search(s_data, s_link, w0, t0 + i, n, lp, a, b, ab);
+			s_memo[i] = a | (a != b ? kFNeedB : 0u);
+		}
+		__syncthreads();
+		if (tid == 0) s_nreq = 0;
+		// ---- who parses again: a proxy was used (its entry is exact now), or the predecessor's exit moved ----
+		bool changed = false;
+		if (tid > 0) {
+			const ParseCarry ne = f_unpack(s_exit[tid - 1]);
+			changed = !carry_equal(ne, entry);
+			entry = ne;
+		}
+		dirty = changed || used_proxy;
+		if (!__syncthreads_or(dirty ? 1 : 0)) break;
+	}
+	// ---- final pass (every entry it reads is exact) and the table for the fix-up: as k_tile_parse ----
+	const uint32_t rbase = t0 + (uint32_t)warp * kRound;
+	if (rbase < n) {
+		uint32_t incl = cnt;
+		for (int o = 1; o < 32; o <<= 1) {
+			const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+			if (lane >= o) incl += t;
+		}
+		uint32_t idx = incl - cnt;
+		uint32_t *sround = sym_local + off + rbase;
+		ParseCarry c = entry;
+		bool act = c.st.p < lim;
+		while (__any_sync(0xffffffffu, act)) {
+			if (act) {
+				c.last_top = c.st.p;
+				uint32_t s2;
+				if (parse_step(c.st, n, lp, strategy, tabf, bytef, slowf, s2)) sround[idx++] = s2;
+				act = c.st.p < lim;
+			}
+			__syncwarp();
+		}
+		const ParseCarry last = shfl_carry(c, 31);
+		const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+		if (lane == 0) {
+			RoundRec r;
+			r.p = last.st.p;
+			r.mlen = last.st.mlen;
+			r.mstart = last.st.mstart;
+			r.prevAvail = last.st.prevAvail;
+			r.last_top = last.last_top;
+			r.cnt = total;
+			(recs + rnd_off[td.x])[rbase / kRound] = r;
+		}
+	}
+	__syncthreads();
+	uint2 *out = mt + off + t0;
+	for (uint32_t i = tid; i < t1 - t0; i += kFThreads) {
+		const uint32_t m = s_memo[i];
+		out[i] = m >= kFReq ? make_uint2(kFNone, kFNone) : make_uint2(m & ~kFNeedB, (m & kFNeedB) ? kFNone : (m & ~kFNeedB));
+	}
+}

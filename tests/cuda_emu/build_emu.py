@@ -75,8 +75,10 @@ def rewrite(src):
 
 
 def build(sanitize=False, verbose=False):
+    """sanitize: False, True / "ub" (UBSan) or "asan" (AddressSanitizer: cudaMalloc'ed memory is heap memory, so a kernel
+    that reads or writes outside its buffers is reported; run python with LD_PRELOAD=libasan and detect_leaks=0)"""
     os.makedirs(os.path.join(OUT, "src"), exist_ok=True)
-    so = os.path.join(OUT, "libb200z_emu%s.so" % ("_san" if sanitize else ""))
+    so = os.path.join(OUT, "libb200z_emu%s.so" % ("_asan" if sanitize == "asan" else "_san" if sanitize else ""))
     srcs = [os.path.join(CSRC, f) for f in FILES]
     deps = srcs + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")] + \
         [os.path.join(HERE, "cuda_emu.h"), os.path.join(HERE, "cuda_emu.cpp"), os.path.abspath(__file__),
@@ -99,7 +101,9 @@ def build(sanitize=False, verbose=False):
                 open(os.path.join(OUT, "src", "experimental", f), "w").write(rewrite(open(os.path.join(exp, f)).read()))
     flags = ["-std=c++17", "-O1", "-g", "-fPIC", "-shared", "-w", "-I", os.path.join(HERE, "include"),
              "-iquote", os.path.join(OUT, "src"), "-I", CSRC, "-iquote", CSRC]
-    if sanitize:
+    if sanitize == "asan":
+        flags += ["-fsanitize=address", "-fno-omit-frame-pointer"]
+    elif sanitize:
         flags += ["-fsanitize=undefined", "-fno-sanitize-recover=undefined", "-fno-sanitize=alignment"]
     cmd = ["g++"] + flags + ["-o", so] + gen + [os.path.join(HERE, "cuda_emu.cpp")]
     if verbose:
@@ -109,4 +113,4 @@ def build(sanitize=False, verbose=False):
 
 
 if __name__ == "__main__":
-    print(build(sanitize="--sanitize" in sys.argv, verbose=True))
+    print(build(sanitize="asan" if "--asan" in sys.argv else "--sanitize" in sys.argv, verbose=True))

@@ -48,7 +48,9 @@ def install(sanitize=False):
 if __name__ == "__main__":
     import pytest
     args = sys.argv[1:]
-    sanitize = "--sanitize" in args
-    args = [a for a in args if a != "--sanitize"]
+    # --sanitize: UBSan build; --asan: AddressSanitizer build (start python with LD_PRELOAD=$(gcc -print-file-name=libasan.so)
+    # ASAN_OPTIONS=detect_leaks=0): "device" buffers are heap memory, out-of-bounds kernel accesses get reported
+    sanitize = "asan" if "--asan" in args else "--sanitize" in args
+    args = [a for a in args if a not in ("--sanitize", "--asan")]
     print("emulator library:", install(sanitize))
     sys.exit(pytest.main(["-q", "-m", "gpu", "-p", "no:cacheprovider"] + args))

@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, HERE)
 import run_emulated  # noqa: E402
 
-run_emulated.install()
+run_emulated.install(sanitize="asan" if "--asan" in sys.argv else "--sanitize" in sys.argv)
 import numpy as np  # noqa: E402
 import oracle_lib as O  # noqa: E402
 import sharpziplib_b200 as z  # noqa: E402

@@ -271,6 +271,108 @@ int main(int argc, char **argv) {
 		       100.0 * (double)(lane_cands + parse_steps) / (32.0 * (double)warp_steps), km_steps, km_steps / all.pos,
 		       km_steps / (double)warp_steps);
 	}
+	// ---- variant: tile-local "guess, batch, re-parse".  Every 32-position segment parses with the exact entry where one is
+	// known and a 1-hop proxy entry otherwise, noting the positions it consulted without an exact entry; those are searched as
+	// one balanced batch (k_match's ordering), then the segments whose inputs changed parse again; until a pass consults
+	// nothing unknown and the hand-off is stable.
+	{
+		rewind(f);
+		const uint32_t kSeg = 32, kFTile = 16384, kFThreads = 512;
+		uint64_t batch_cands[16] = {0}, batch_req[16] = {0}, pass_iters[16] = {0}, tiles = 0, passes_total = 0;
+		int max_pass = 0;
+		LevelParams l1 = lp;
+		l1.chain = 1;
+		while (fread(buf.data(), 1, bs, f) == bs) {
+			const uint32_t n = bs;
+			std::vector<uint16_t> link;
+			links(buf.data(), n, link);
+			auto bytef = [&](uint32_t q) { return (uint32_t)buf[q]; };
+			auto slowf = [&](uint32_t p, uint32_t m0, uint32_t budget) { return match_search_above(buf.data(), link.data(), p, n, m0, budget, 0u); };
+			for (uint32_t t0 = 0; t0 < n; t0 += kFTile) {
+				tiles++;
+				std::vector<uint32_t> exA(kFTile, 0xFFFFFFFFu), exB(kFTile, 0), prA(kFTile, 0), prB(kFTile, 0);
+				std::vector<char> asked(kFTile, 0);
+				for (uint32_t i = 0; i < kFTile && t0 + i < n; i++) match_search(buf.data(), link.data(), 0u, t0 + i, n, l1, prA[i], prB[i]);
+				std::vector<ParseCarry> entry(kFThreads), ex(kFThreads);
+				std::vector<uint32_t> lim(kFThreads);
+				std::vector<char> dirty(kFThreads, 1); // segment must parse again (entry changed or an entry it used became exact)
+				std::vector<std::vector<uint32_t>> used(kFThreads); // inexact positions a segment consulted in its last parse
+				auto clean = [&](uint32_t p) { ParseCarry c; parse_init(c.st); c.st.p = p; c.last_top = p; return c; };
+				for (uint32_t t = 0; t < kFThreads; t++) {
+					const uint32_t seg0 = t0 + t * kSeg;
+					lim[t] = seg0 + kSeg < n ? seg0 + kSeg : n;
+					entry[t] = clean(seg0);
+					ex[t] = entry[t];
+				}
+				int pass = 0;
+				for (;; pass++) {
+					std::vector<uint32_t> req;
+					for (uint32_t w = 0; w < kFThreads / 32; w++) {
+						uint32_t longest = 0;
+						for (uint32_t l = 0; l < 32; l++) {
+							const uint32_t t = w * 32 + l;
+							if (!dirty[t]) continue;
+							used[t].clear();
+							ex[t] = entry[t];
+							uint32_t k = 0;
+							auto tabf = [&](uint32_t p, uint32_t &a, uint32_t &b) {
+								const uint32_t i = p - t0;
+								if (exA[i] != 0xFFFFFFFFu) { a = exA[i]; b = exB[i]; return; }
+								a = prA[i]; b = prB[i];
+								used[t].push_back(p);
+								if (!asked[i] && link[p]) { asked[i] = 1; req.push_back(p); }
+								else if (!link[p]) { exA[i] = 0; exB[i] = 0; }
+							};
+							while (ex[t].st.p < lim[t]) {
+								ex[t].last_top = ex[t].st.p;
+								uint32_t s2;
+								parse_step(ex[t].st, n, lp, 0, tabf, bytef, slowf, s2);
+								k++;
+							}
+							if (k > longest) longest = k;
+						}
+						if (pass < 16) pass_iters[pass] += longest;
+					}
+					// the batch
+					for (uint32_t p : req) {
+						Cnt c;
+						match_search(buf.data(), link.data(), 0u, p, n, lp, exA[p - t0], exB[p - t0]);
+						walk(buf.data(), link.data(), p, n, 2, (uint32_t)lp.chain, (uint32_t)lp.nice, c);
+						if (pass < 16) batch_cands[pass] += c.cands;
+					}
+					if (pass < 16) batch_req[pass] += req.size();
+					// who parses again: entry changed, or it used an entry that is exact now (and differs from the proxy)
+					bool again = false;
+					std::vector<ParseCarry> prev(ex);
+					for (uint32_t t = 0; t < kFThreads; t++) {
+						bool d = false;
+						if (t > 0 && !carry_equal(prev[t - 1], entry[t])) { entry[t] = prev[t - 1]; d = true; }
+						for (uint32_t p : used[t]) {
+							const uint32_t i = p - t0;
+							if (exA[i] != 0xFFFFFFFFu && (exA[i] != prA[i] || exB[i] != prB[i])) d = true;
+						}
+						// (an entry that is exact now and equals the proxy changes nothing)
+						dirty[t] = d;
+						again |= d;
+					}
+					if (!again) break;
+				}
+				passes_total += (uint64_t)pass + 1;
+				if (pass + 1 > max_pass) max_pass = pass + 1;
+			}
+		}
+		printf("guess / batch / re-parse per tile: %.2f passes per tile on average, %d at most\n", (double)passes_total / tiles, max_pass);
+		double tot_c = 0, tot_i = 0;
+		for (int k = 0; k < 8; k++) {
+			if (!batch_req[k] && !pass_iters[k]) continue;
+			printf("   pass %d: parse %.3f lock-step iterations per position; batch: %.2f%% of positions, %.2f candidates per position\n", k,
+			       (double)pass_iters[k] / all.pos, 100.0 * batch_req[k] / all.pos, (double)batch_cands[k] / all.pos);
+			tot_c += (double)batch_cands[k];
+			tot_i += (double)pass_iters[k];
+		}
+		printf("   total: %.2f candidates per position in balanced batches (k_match: %.2f), %.3f parse iterations per position + 1 proxy hop per position\n",
+		       tot_c / all.pos, (double)all.cands / all.pos, tot_i / all.pos);
+	}
 	auto pr = [&](const char *name, const Cnt &c) {
 		printf("%s: positions %llu, searched %llu (%.1f%%), candidates %llu (%.1f per searched, %.1f per position)\n", name,
 		       (unsigned long long)c.pos, (unsigned long long)c.searched, 100.0 * c.searched / c.pos, (unsigned long long)c.cands,
