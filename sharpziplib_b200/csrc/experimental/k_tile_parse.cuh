@@ -190,6 +190,95 @@ __global__ void __launch_bounds__(kFThreads, 1)
 // ------------------------------------------------------------------------------------------------------------------
 constexpr uint32_t kFReq = 0xFFFFFFFEu; // memo: requested, the batch has not run yet
 
+// k_match's chain walk (b200z_deflate.cu: bytes 2..9 of the scan string in registers, 4-byte extension compares on the
+// staged window, one budget test per candidate), as a function over a window whose byte 0 is stream position w0 and whose
+// link entries start at w0 as well.  Same results as match_search(); the byte-wise loop of match_search() ran with ~2 of 32
+// lanes active in k_match and took ~30 % of it.
+__device__ __forceinline__ void tile_walk(const uint8_t *s_data, const uint16_t *s_link, uint32_t w0, uint32_t p, uint32_t n,
+                                          const LevelParams &lp, uint32_t ab, uint32_t &resA, uint32_t &resB) {
+	resA = 0;
+	resB = 0;
+	const uint32_t la = n - p;
+	if (la < (uint32_t)kMinMatch) return;
+	uint32_t d = (uint32_t)s_link[p - w0];
+	if (d > (uint32_t)kMaxDist - (is_slide_pos(p + ab) ? 1u : 0u)) d = 0; // DeflaterEngine.cs:788 + trap T8
+	if (d == 0) return;
+	const uint32_t chain = (uint32_t)lp.chain, budgetB = chain >> 2;
+	const uint32_t maxlen = la < (uint32_t)kMaxMatch ? la : (uint32_t)kMaxMatch;
+	const uint32_t nice = la < (uint32_t)lp.nice ? la : (uint32_t)lp.nice;
+	const uint32_t is = p - w0;
+	const uint8_t *sp = s_data + is;
+	uint32_t m = kMinMatch - 1, bd = 0, dist = d, cnt = 0;
+	bool haveB = false;
+	uint32_t stop = budgetB ? budgetB : chain;
+	const uint32_t s0 = sp[0], s1 = sp[1];
+	uint32_t scan_end1 = s1, scan_end = sp[2];
+	uint32_t sw0, sw1;
+	{
+		const uint32_t as = is + 2;
+		const uint32_t *ws = reinterpret_cast<const uint32_t *>(s_data + (as & ~3u));
+		const uint32_t w1 = ws[1], sh = (as & 3u) * 8u;
+		sw0 = __funnelshift_r(ws[0], w1, sh);
+		sw1 = __funnelshift_r(w1, ws[2], sh);
+	}
+	for (;;) {
+		const uint32_t ic = is - dist;
+		const uint8_t *c = s_data + ic;
+		++cnt;
+		if (c[m] == scan_end && c[m - 1] == scan_end1 && c[0] == s0 && c[1] == s1) {
+			uint32_t l = 2;
+			if (maxlen >= 10) {
+				const uint32_t ac = ic + 2;
+				const uint32_t *wc = reinterpret_cast<const uint32_t *>(s_data + (ac & ~3u));
+				const uint32_t w1 = wc[1], sh = (ac & 3u) * 8u;
+				uint32_t x = __funnelshift_r(wc[0], w1, sh) ^ sw0;
+				if (x) {
+					l = 2 + ((uint32_t)(__ffs((int)x) - 1) >> 3);
+					goto lcp_done;
+				}
+				x = __funnelshift_r(w1, wc[2], sh) ^ sw1;
+				if (x) {
+					l = 6 + ((uint32_t)(__ffs((int)x) - 1) >> 3);
+					goto lcp_done;
+				}
+				l = 10;
+			}
+			while (l + 4 <= maxlen) {
+				const uint32_t ac = ic + l, as = is + l;
+				const uint32_t *wc = reinterpret_cast<const uint32_t *>(s_data + (ac & ~3u));
+				const uint32_t *ws = reinterpret_cast<const uint32_t *>(s_data + (as & ~3u));
+				const uint32_t x = __funnelshift_r(wc[0], wc[1], (ac & 3u) * 8u) ^ __funnelshift_r(ws[0], ws[1], (as & 3u) * 8u);
+				if (x) {
+					l += (uint32_t)(__ffs((int)x) - 1) >> 3;
+					goto lcp_done;
+				}
+				l += 4;
+			}
+			while (l < maxlen && c[l] == sp[l]) ++l;
+		lcp_done:
+			if (l > m) {
+				m = l;
+				bd = dist;
+				if (m >= nice) break;
+				scan_end1 = sp[m - 1];
+				scan_end = sp[m];
+			}
+		}
+		if (cnt == stop) { // one test per candidate: first the quarter budget (B's snapshot), then the full one
+			if (stop == chain) break;
+			resB = m >= (uint32_t)kMinMatch ? pack_match(m, bd) : 0u;
+			haveB = true;
+			stop = chain;
+		}
+		const uint32_t l2 = s_link[is - dist];
+		if (l2 == 0) break;
+		dist += l2;
+		if (dist >= (uint32_t)kMaxDist) break; // chain entries need distance < 32506 (T7)
+	}
+	resA = m >= (uint32_t)kMinMatch ? pack_match(m, bd) : 0u;
+	if (!haveB) resB = resA;
+}
+
 __global__ void __launch_bounds__(kFThreads, 1)
     k_tile_parse2(const uint8_t *__restrict__ in, const uint16_t *__restrict__ link, uint2 *__restrict__ mt,
                   uint32_t *__restrict__ sym_local, const int64_t *__restrict__ in_off, const int64_t *__restrict__ in_len,
@@ -284,7 +373,7 @@ __global__ void __launch_bounds__(kFThreads, 1)
 		for (uint32_t r = tid; r < nreq; r += kFThreads) {
 			const uint32_t i = req[r];
 			uint32_t a, b;
-			match_search(s_data, s_link, w0, t0 + i, n, lp, a, b, ab);
+			tile_walk(s_data, s_link, w0, t0 + i, n, lp, ab, a, b);
 			s_memo[i] = a | (a != b ? kFNeedB : 0u);
 		}
 		__syncthreads();
