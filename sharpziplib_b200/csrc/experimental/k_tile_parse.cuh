@@ -303,7 +303,12 @@ __global__ void __launch_bounds__(kFThreads, 1)
 	uint32_t dend = t1 + 272;
 	if (dend > n) dend = n;
 	const uint32_t H = hist[td.x], ab = (uint32_t)bias[td.x];
-	uint16_t *req = reinterpret_cast<uint16_t *>(scratch + off + t0); // positions relative to t0, at most one entry per position
+	// the tile's 4 x kFTile bytes of scratch: request list (2 bytes per position: relative to t0, at most one entry per
+	// position), the same list ordered by walk-length class, and the class of every request
+	uint16_t *req = reinterpret_cast<uint16_t *>(scratch + off + t0);
+	uint16_t *ord = req + (t1 - t0); // (a last, partial tile only owns 4 x (t1 - t0) bytes of scratch)
+	__shared__ uint32_t s_cls[2][kMatchClasses];
+	uint8_t *req_cls = reinterpret_cast<uint8_t *>(mt + off + t0); // the tile's table slots are written at the very end: 8 bytes per position free until then
 	{
 		const uint32_t nbytes = dend - w0, nvec = nbytes >> 4;
 		const uint4 *src = reinterpret_cast<const uint4 *>(data + w0);
@@ -336,6 +341,11 @@ __global__ void __launch_bounds__(kFThreads, 1)
 			return;
 		}
 		if (m == kFNone) {
+			if (s_link[p - w0] == 0) { // no chain: the exact answer is "nothing", no request needed
+				s_memo[p - t0] = 0;
+				a = b = 0;
+				return;
+			}
 			s_memo[p - t0] = kFReq;
 			req[atomicAdd(&s_nreq, 1u)] = (uint16_t)(p - t0);
 		}
@@ -370,8 +380,47 @@ __global__ void __launch_bounds__(kFThreads, 1)
 		__syncthreads();
 		// ---- batch: the CTA serves the pass's requests ----
 		const uint32_t nreq = s_nreq;
+		const uint16_t *work = req;
+		if (nreq >= 4u * kFThreads) {
+			// a big batch (the first one holds ~45 % of the tile) is ordered by expected walk length, longest first, the way
+			// k_match orders its tile (first eight hops exact, then their density extrapolated over the window): the lanes of
+			// a warp then hold walks of similar length.  The order only decides who computes what.
+			if (tid < 2 * kMatchClasses) (&s_cls[0][0])[tid] = 0;
+			__syncthreads();
+			for (uint32_t r = tid; r < nreq; r += kFThreads) {
+				const uint32_t is = (uint32_t)req[r] + (t0 - w0);
+				uint32_t dist = s_link[is], hops = 1, cls;
+				while (hops < 8) {
+					const uint32_t l2 = s_link[is - dist];
+					if (l2 == 0 || dist + l2 >= (uint32_t)kMaxDist) break;
+					dist += l2;
+					++hops;
+				}
+				if (hops < 8) cls = hops <= 1 ? 1u : hops <= 2 ? 2u : hops <= 4 ? 3u : hops <= 6 ? 4u : 5u;
+				else {
+					uint32_t est = (8u * (uint32_t)kMaxDist) / dist;
+					if (est > (uint32_t)lp.chain) est = (uint32_t)lp.chain;
+					cls = est <= 11 ? 6u : est <= 16 ? 7u : est <= 23 ? 8u : est <= 32 ? 9u : est <= 45 ? 10u : est <= 64 ? 11u
+					      : est <= 91 ? 12u : est <= 128 ? 13u : est <= 512 ? 14u : 15u;
+				}
+				req_cls[r] = (uint8_t)cls;
+				atomicAdd(&s_cls[0][cls], 1u);
+			}
+			__syncthreads();
+			if (tid == 0) {
+				uint32_t b = 0;
+				for (int c = kMatchClasses - 1; c >= 1; c--) {
+					s_cls[1][c] = b;
+					b += s_cls[0][c];
+				}
+			}
+			__syncthreads();
+			for (uint32_t r = tid; r < nreq; r += kFThreads) ord[atomicAdd(&s_cls[1][req_cls[r]], 1u)] = req[r];
+			__syncthreads();
+			work = ord;
+		}
 		for (uint32_t r = tid; r < nreq; r += kFThreads) {
-			const uint32_t i = req[r];
+			const uint32_t i = work[r];
 			uint32_t a, b;
 			tile_walk(s_data, s_link, w0, t0 + i, n, lp, ab, a, b);
 			s_memo[i] = a | (a != b ? kFNeedB : 0u);
