@@ -6,6 +6,7 @@ namespace emu {
 Block *g_block = nullptr;
 Fiber *g_cur = nullptr;
 uint64_t g_events = 0;
+size_t g_stack_bytes = 0;
 
 static void fiber_main() {
 	g_block->body();
@@ -38,8 +39,12 @@ void launch(dim3 grid, dim3 block, size_t smem_bytes, std::function<void()> body
 		abort();
 	}
 	if (!g_smem) g_smem = (uint8_t *)aligned_alloc(256, kMaxSmem + 4096);
+	if (!g_stack_bytes) {
+		const char *e = getenv("B200Z_EMU_STACK_KB");
+		g_stack_bytes = (size_t)(e ? atoi(e) : 1024) << 10;
+	}
 	while ((int)g_stacks.size() < nt) {
-		void *s = mmap(nullptr, kStack, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
+		void *s = mmap(nullptr, g_stack_bytes, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
 		if (s == MAP_FAILED) abort();
 		g_stacks.push_back(s);
 	}
@@ -70,7 +75,7 @@ void launch(dim3 grid, dim3 block, size_t smem_bytes, std::function<void()> body
 					b.warps[(size_t)f.warp].live++;
 					getcontext(&f.ctx);
 					f.ctx.uc_stack.ss_sp = g_stacks[(size_t)t];
-					f.ctx.uc_stack.ss_size = kStack;
+					f.ctx.uc_stack.ss_size = g_stack_bytes;
 					f.ctx.uc_link = nullptr;
 					makecontext(&f.ctx, fiber_main, 0);
 				}

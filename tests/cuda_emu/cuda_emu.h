@@ -40,7 +40,8 @@ static inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
 
 namespace emu {
 
-constexpr size_t kStack = 1 << 20;
+extern size_t g_stack_bytes; // per CUDA thread; B200Z_EMU_STACK_KB (default 1024; AddressSanitizer clears a context's whole
+                              // shadow stack on every switch, so its runs want this small)
 constexpr size_t kMaxSmem = 256 * 1024;
 
 struct Warp {
