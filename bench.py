@@ -218,6 +218,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200z", choices=["b200z", "reference"])
     ap.add_argument("--small", action="store_true", help="1/8 size workload for quick checks (not a bench value)")
+    ap.add_argument("--no-probe", dest="no_probe", action="store_true",
+                    help="skip the informational probe of the opt-in search kernels that follows the measurement")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -476,6 +478,25 @@ def main():
                "sample": "%d x 256 KiB deflate L6 + %d x 1 MiB inflate, single thread, %.1f s" % (ns_d, ns_i, r["seconds"]),
                "deflate_gbs": r["deflate_gbs"], "inflate_gbs": r["inflate_gbs"], "host_cores": ncpu,
                "note": "C++ restatement of SharpZipLib's managed path (oracle/); no .NET runtime on the box"}
+    # ---- opt-in search kernels (csrc/experimental/k_tile_parse.cuh): probed AFTER every timed region, in a process of their
+    # own (they had never run on a GPU when round 1 ended; a fault there must not touch this process).  Not part of
+    # value / e2e / roofline: the line only carries what the probe printed, for the next round to start from.
+    probe = None
+    if rank == 0 and world == 1 and not args.small and not args.no_probe and not os.environ.get("B200Z_TILE_PARSE"):
+        probe = {}
+        for variant in ("2", "1"):
+            try:
+                r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "tile_parse_check.py"), variant, "64"], cwd=ROOT,
+                                   stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=150)
+                last = (r.stdout.decode(errors="replace").strip().splitlines() or [""])[-1]
+                try:
+                    probe["tile_parse" + variant] = json.loads(last)
+                except ValueError:
+                    probe["tile_parse" + variant] = {"ok": False, "rc": r.returncode, "stderr": r.stderr.decode(errors="replace")[-400:]}
+            except subprocess.TimeoutExpired:
+                probe["tile_parse" + variant] = {"ok": False, "timeout_s": 150}
+            except Exception as e:  # the probe never costs the bench line
+                probe["tile_parse" + variant] = {"ok": False, "error": repr(e)[:200]}
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
@@ -484,7 +505,9 @@ def main():
             "config": {"workload": "C3 deflate L6 %dx256KiB + C2 inflate %dx1MiB per GPU" % (n_def, n_inf),
                        "l2": "inputs (256 MiB + 64 MiB compressed per leg) exceed the 126 MB L2; no flush needed",
                        "parity": "deflate bytes == oracle and inflate bytes == original, checked on 16 buffers each before timing",
-                       "ratio_deflate": U_def / max(1, C_def), "ratio_inflate": U_inf / max(1, C_inf), "setup_s": setup_s},
+                       "ratio_deflate": U_def / max(1, C_def), "ratio_inflate": U_inf / max(1, C_inf), "setup_s": setup_s,
+                       # opt-in search kernel (csrc/experimental/k_tile_parse.cuh); "" = the default k_match + k_parse_chunk
+                       "search_variant": ("tile_parse%s" % os.environ["B200Z_TILE_PARSE"]) if os.environ.get("B200Z_TILE_PARSE") in ("1", "2") else "default"},
             "deflate_gbs": U_def / (t_def / 1e3) / 1e9 if t_def else None,
             "inflate_gbs": U_inf / (t_inf / 1e3) / 1e9 if t_inf else None,
             "kernels_ms": acc,
@@ -501,6 +524,9 @@ def main():
             "gpu_launches": int(dplan.launches + iplan.launches) * args.steps,
             "gpu_launches_per_step": int(dplan.launches + iplan.launches),
             "clocks": clocks,
+            # separate process, after the timed regions, 64 x 256 KiB: bit-exactness and per-kernel ms of the opt-in search
+            # kernels next to the default path (tools/tile_parse_check.py); informational
+            "experimental_probe": probe,
         }
         out.write(json.dumps(line) + "\n")
         out.flush()

@@ -403,6 +403,9 @@ __device__ __forceinline__ ParseCarry rec_carry(const RoundRec &r) {
 
 // One round [base, base + kRound) of a stream, entered with `carry` (uniform across the warp; updated to the round's
 // exit state).  The round's symbols go to sround[0 .. cnt).  Returns cnt (uniform).
+// kLazyTab: behind the tile kernels (experimental/k_tile_parse.cuh) the table only holds the positions their speculative parse
+// searched; the fix-up then searches the others on demand.  false compiles to exactly the table read.
+template <bool kLazyTab>
 __device__ __forceinline__ uint32_t parse_round(uint8_t *smem, const uint8_t *data, const uint16_t *lnk, const uint2 *tab,
                                                 uint32_t n, uint32_t H, uint32_t ab, uint32_t base, const LevelParams &lp,
                                                 int strategy, ParseCarry &carry, uint32_t *sround) {
@@ -426,7 +429,10 @@ __device__ __forceinline__ uint32_t parse_round(uint8_t *smem, const uint8_t *da
 	const uint32_t seg_end = base + (uint32_t)(lane + 1) * kSeg;
 	auto tabf = [&](uint32_t p, uint32_t &a, uint32_t &b) {
 		const uint32_t i = p - base;
-		const uint2 t = s_tab[(i >> kSegShift) * kSegStride + (i & (kSeg - 1))];
+		uint2 &t = s_tab[(i >> kSegShift) * kSegStride + (i & (kSeg - 1))];
+		// behind the tile kernels: 0xFFFFFFFF = not searched (y alone: the quarter-budget answer has to be searched again);
+		// search in global memory, keep it for the next pass
+		if (kLazyTab && (t.x == 0xFFFFFFFFu || t.y == 0xFFFFFFFFu)) match_search(data, lnk, 0u, p, n, lp, t.x, t.y, ab);
 		a = t.x;
 		b = t.y;
 	};
@@ -505,7 +511,7 @@ __global__ void __launch_bounds__(32)
 	// a guess otherwise
 	ParseCarry carry = clean_carry(cd.c0 > H ? cd.c0 : H);
 	for (uint32_t base = cd.c0; base < cd.c1; base += kRound) {
-		const uint32_t cnt = parse_round(smem, in + off, link + off, mt + off, n, H, ab, base, lp, strategy, carry, sym_local + off + base);
+		const uint32_t cnt = parse_round<false>(smem, in + off, link + off, mt + off, n, H, ab, base, lp, strategy, carry, sym_local + off + base);
 		if (threadIdx.x == 0) {
 			RoundRec r;
 			r.p = carry.st.p;
@@ -519,12 +525,13 @@ __global__ void __launch_bounds__(32)
 	}
 }
 
-__global__ void __launch_bounds__(32)
-    k_parse_fix(const uint8_t *__restrict__ in, const uint16_t *__restrict__ link, const uint2 *__restrict__ mt,
-                uint32_t *__restrict__ sym_local, const int64_t *__restrict__ in_off, const int64_t *__restrict__ in_len,
-                const uint32_t *__restrict__ rnd_off, RoundRec *__restrict__ recs, uint32_t chunk, const uint32_t *__restrict__ hist,
-                const int64_t *__restrict__ bias, LevelParams lp, int strategy) {
-	extern __shared__ __align__(16) uint8_t smem[];
+template <bool kLazyTab>
+__device__ __forceinline__ void parse_fix_body(uint8_t *smem, const uint8_t *__restrict__ in, const uint16_t *__restrict__ link,
+                                               const uint2 *__restrict__ mt, uint32_t *__restrict__ sym_local,
+                                               const int64_t *__restrict__ in_off, const int64_t *__restrict__ in_len,
+                                               const uint32_t *__restrict__ rnd_off, RoundRec *__restrict__ recs, uint32_t chunk,
+                                               const uint32_t *__restrict__ hist, const int64_t *__restrict__ bias,
+                                               const LevelParams &lp, int strategy) {
 	const int stream = blockIdx.x;
 	const uint32_t n = (uint32_t)in_len[stream];
 	if (n <= chunk) return; // a single chunk was parsed from the true initial state
@@ -541,7 +548,7 @@ __global__ void __launch_bounds__(32)
 		}
 		for (uint32_t base = c0; base < c1; base += kRound) {
 			const ParseCarry old_exit = rec_carry(rr[base / kRound]);
-			const uint32_t cnt = parse_round(smem, in + off, link + off, mt + off, n, H, ab, base, lp, strategy, truth, sym_local + off + base);
+			const uint32_t cnt = parse_round<kLazyTab>(smem, in + off, link + off, mt + off, n, H, ab, base, lp, strategy, truth, sym_local + off + base);
 			__syncwarp();
 			if (threadIdx.x == 0) {
 				RoundRec r;
@@ -557,6 +564,25 @@ __global__ void __launch_bounds__(32)
 			if (carry_equal(truth, old_exit)) break; // re-synchronised: the rest of the chunk stands as parsed
 		}
 	}
+}
+
+__global__ void __launch_bounds__(32)
+    k_parse_fix(const uint8_t *__restrict__ in, const uint16_t *__restrict__ link, const uint2 *__restrict__ mt,
+                uint32_t *__restrict__ sym_local, const int64_t *__restrict__ in_off, const int64_t *__restrict__ in_len,
+                const uint32_t *__restrict__ rnd_off, RoundRec *__restrict__ recs, uint32_t chunk, const uint32_t *__restrict__ hist,
+                const int64_t *__restrict__ bias, LevelParams lp, int strategy) {
+	extern __shared__ __align__(16) uint8_t smem[];
+	parse_fix_body<false>(smem, in, link, mt, sym_local, in_off, in_len, rnd_off, recs, chunk, hist, bias, lp, strategy);
+}
+
+// the fix-up behind the tile kernels (B200Z_TILE_PARSE): table entries they did not compute are searched on demand
+__global__ void __launch_bounds__(32)
+    k_parse_fix_lazy(const uint8_t *__restrict__ in, const uint16_t *__restrict__ link, const uint2 *__restrict__ mt,
+                     uint32_t *__restrict__ sym_local, const int64_t *__restrict__ in_off, const int64_t *__restrict__ in_len,
+                     const uint32_t *__restrict__ rnd_off, RoundRec *__restrict__ recs, uint32_t chunk,
+                     const uint32_t *__restrict__ hist, const int64_t *__restrict__ bias, LevelParams lp, int strategy) {
+	extern __shared__ __align__(16) uint8_t smem[];
+	parse_fix_body<true>(smem, in, link, mt, sym_local, in_off, in_len, rnd_off, recs, chunk, hist, bias, lp, strategy);
 }
 
 // exclusive scan of the rounds' symbol counts of one stream; also the end-of-stream bookkeeping
@@ -658,6 +684,8 @@ __global__ void __launch_bounds__(128)
 		}
 	}
 }
+
+#include "experimental/k_tile_parse.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // Levels 1-4: DeflateFast.  The chains depend on the parse, so a stream is parsed serially by lane 0 with the
@@ -1087,6 +1115,13 @@ int deflate_plan_build(b200z_plan *p) {
 		const int64_t need = (maxlen / 1024 + kRound - 1) / kRound * kRound;
 		if (need > (int64_t)chunk) chunk = (uint32_t)need;
 	}
+	// B200Z_TILE_PARSE=1: k_tile_parse (search driven by the parse) instead of k_match + k_parse_chunk; the hand-off inside the
+	// kernel spans one tile, so tiles are the chunks k_parse_fix stitches -- streams of more than 1024 tiles keep the old path
+	// (1: k_tile_parse, every lane searches for itself; 2: k_tile_parse2, proxies + batched searches)
+	// Opt-in until it has been measured on a B200 (written without GPU time left; bit-exact on tests/cuda_emu).
+	p->tile_parse = (lp.func == 2 && getenv("B200Z_TILE_PARSE") && maxlen <= 1024ll * kFTile) ? atoi(getenv("B200Z_TILE_PARSE")) : 0;
+	if (p->tile_parse != 1 && p->tile_parse != 2) p->tile_parse = 0;
+	if (p->tile_parse) chunk = kFTile;
 	p->parse_chunk = chunk;
 	{
 		// levels 1-4: size of k_fast's prev[] table (see there)
@@ -1126,7 +1161,7 @@ int deflate_plan_build(b200z_plan *p) {
 		p->out_cap[i] = align_up(b200z_deflate_bound(len), kAlign);
 		oo += p->out_cap[i];
 		for (int64_t s = 0; s < len; s += kRun) runs.push_back(make_int2(i, (int)s));
-		for (int64_t s = 0; s < len; s += kTile) tiles.push_back(make_int2(i, (int)s));
+		for (int64_t s = 0; s < len; s += (p->tile_parse ? kFTile : kTile)) tiles.push_back(make_int2(i, (int)s));
 		for (int64_t s = 0; s < len; s += chunk)
 			chunks.push_back(ChunkDesc{i, (uint32_t)s, (uint32_t)(len - s > (int64_t)chunk ? s + chunk : len)});
 		rnd_off[i] = nrounds;
@@ -1292,7 +1327,9 @@ int deflate_plan_build(b200z_plan *p) {
 	B200Z_CUDA(cudaFuncSetAttribute(k_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, kFastSmem));
 	B200Z_CUDA(cudaFuncSetAttribute(k_links, cudaFuncAttributeMaxDynamicSharedMemorySize, kLinksSmem));
 	B200Z_CUDA(cudaFuncSetAttribute(k_match, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileData + 2 * 2 * kTile));
-	p->launches = (lp.func == 2 ? 9 : (lp.func == 1 ? 4 : 2)) + (p->wrap != B200Z_WRAP_RAW ? 3 : 0); // + one memset node
+	B200Z_CUDA(cudaFuncSetAttribute(k_tile_parse, cudaFuncAttributeMaxDynamicSharedMemorySize, kFSmem));
+	B200Z_CUDA(cudaFuncSetAttribute(k_tile_parse2, cudaFuncAttributeMaxDynamicSharedMemorySize, kFSmem));
+	p->launches = (lp.func == 2 ? (p->tile_parse ? 8 : 9) : (lp.func == 1 ? 4 : 2)) + (p->wrap != B200Z_WRAP_RAW ? 3 : 0); // + one memset node
 	return B200Z_OK;
 }
 
@@ -1362,10 +1399,18 @@ int deflate_plan_run(b200z_plan *p, const uint8_t *d_in, uint8_t *d_out, int64_t
 		p->mark(s, "k_links");
 		if (p->n_runs) k_links<<<p->n_runs, kLinkThreads, kLinksSmem, s>>>(d_in, link, in_off, in_len, ws.at<int2>(p->o_run_desc), hist,
 			                                                         ws.at<uint8_t>(p->o_hmask), ws.at<int64_t>(p->o_hm_off));
-		p->mark(s, "k_match");
-		if (p->n_tiles)
+		p->mark(s, p->tile_parse ? "k_tile_parse" : "k_match");
+		if (p->n_tiles && !p->tile_parse)
 			k_match<<<p->n_tiles, kMatchThreads, kTileData + 2 * 2 * kTile, s>>>(d_in, link, mt, in_off, in_len,
 			                                                                   ws.at<int2>(p->o_tile_desc), hist, bias, sym, lp);
+		if (p->n_tiles && p->tile_parse == 1) // (part of the SEARCH stage: it needs the whole shared memory like k_match)
+			k_tile_parse<<<p->n_tiles, kFThreads, kFSmem, s>>>(d_in, link, mt, ws.at<uint32_t>(p->o_sym_local), in_off, in_len,
+			                                                   ws.at<int2>(p->o_tile_desc), ws.at<uint32_t>(p->o_rnd_off),
+			                                                   ws.at<RoundRec>(p->o_recs), hist, bias, lp, p->strategy);
+		if (p->n_tiles && p->tile_parse == 2)
+			k_tile_parse2<<<p->n_tiles, kFThreads, kFSmem, s>>>(d_in, link, mt, ws.at<uint32_t>(p->o_sym_local), in_off, in_len,
+			                                                    ws.at<int2>(p->o_tile_desc), ws.at<uint32_t>(p->o_rnd_off),
+			                                                    ws.at<RoundRec>(p->o_recs), hist, bias, sym, lp, p->strategy);
 		}
 		if (!do_encode) {
 			B200Z_CUDA(cudaGetLastError());
@@ -1377,11 +1422,15 @@ int deflate_plan_run(b200z_plan *p, const uint8_t *d_in, uint8_t *d_out, int64_t
 			const uint32_t *rnd_off = ws.at<uint32_t>(p->o_rnd_off);
 			RoundRec *recs = ws.at<RoundRec>(p->o_recs);
 			uint32_t *rnd_symoff = ws.at<uint32_t>(p->o_rnd_symoff);
-			if (p->n_chunks)
+			if (p->n_chunks && !p->tile_parse)
 				k_parse_chunk<<<p->n_chunks, 32, kParseSmem, s>>>(d_in, link, mt, sym_local, in_off, in_len, ws.at<ChunkDesc>(p->o_chunks),
 				                                                 rnd_off, recs, hist, bias, lp, p->strategy);
-			k_parse_fix<<<n, 32, kParseSmem, s>>>(d_in, link, mt, sym_local, in_off, in_len, rnd_off, recs, p->parse_chunk, hist, bias,
-			                                      lp, p->strategy);
+			if (!p->tile_parse)
+				k_parse_fix<<<n, 32, kParseSmem, s>>>(d_in, link, mt, sym_local, in_off, in_len, rnd_off, recs, p->parse_chunk, hist, bias,
+				                                      lp, p->strategy);
+			else
+				k_parse_fix_lazy<<<n, 32, kParseSmem, s>>>(d_in, link, mt, sym_local, in_off, in_len, rnd_off, recs, p->parse_chunk, hist,
+				                                           bias, lp, p->strategy);
 			k_parse_scan<<<n, 256, 0, s>>>(d_in, in_off, in_len, rnd_off, recs, rnd_symoff, sym, nsyms, nblocks, blk_off, blk_start,
 			                               blk_ptop, hist, p->end_mode);
 			if (p->n_rgroups)

@@ -1,6 +1,8 @@
-// k_tile_parse.cuh -- EXPERIMENTAL, NOT PART OF libb200z.so (build.sh does not compile it; tools/check_experimental.sh only
-// compiles it to look at registers / shared memory / SASS).  Written at the end of round 1 without GPU time left: it has
-// never run.  It is the round-2 starting point that DESIGN.md 7b describes, kept next to the kernels it is meant to replace.
+// k_tile_parse.cuh -- EXPERIMENTAL, OPT-IN: compiled into libb200z.so (#included by b200z_deflate.cu) but launched only when
+// the environment holds B200Z_TILE_PARSE=1 (k_tile_parse) or =2 (k_tile_parse2) while a level 5-9 plan is built; the default
+// path (k_match + k_parse_chunk) does not change with it.  Written at the end of round 1 without GPU time left: it has
+// never run on a GPU.  Bit-exact against the oracle on the CUDA emulator (tests/cuda_emu) through the GPU-tier deflate tests.
+// It is the round-2 starting point that DESIGN.md 7b describes, kept next to the kernels it is meant to replace.
 //
 // Why: tools/match_stats.cpp shows that k_match (a match table for EVERY position) walks 7.0x the chain candidates the
 // reference walks at level 6 (24.6x at level 9): DeflateSlow only searches at the positions it visits (49.6 % on the bench
@@ -16,9 +18,9 @@
 // is what k_parse_chunk leaves today; tiles are stitched by k_parse_fix with chunk = kFTile, whose table function has to fall
 // back to a search in global memory where this kernel left "not computed" (mt[p].x == kFNone).
 //
-// Replaces: k_match + k_parse_chunk (k_links, k_parse_fix / _scan / _gather, k_plan, k_scan, k_emit stay).
-// To wire it (round 2): #include at the end of b200z_deflate.cu inside namespace b200z; tiles of kFTile instead of kTile in
-// deflate_plan_build; p->parse_chunk = kFTile; parse_round() needs the lazy table function for the fix-up.
+// Replaces: k_match + k_parse_chunk (k_links, k_parse_fix_lazy / _scan / _gather, k_plan, k_scan, k_emit stay).
+// Wiring (deflate_plan_build / deflate_plan_run): tiles of kFTile instead of kTile, p->parse_chunk = kFTile, the fix-up is
+// k_parse_fix_lazy (parse_round<true>: entries this kernel left "not computed" are searched in global memory).
 #pragma once
 
 constexpr int kFTile = 16384;                 // positions per CTA

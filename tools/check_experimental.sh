@@ -1,13 +1,7 @@
 #!/bin/bash
-# Compiles sharpziplib_b200/csrc/experimental/*.cuh for sm_100a next to the kernels they would join (nothing is linked, the
-# product build does not see them) and prints registers / shared memory / spills.
+# Registers / shared memory / spills of the opt-in kernels of sharpziplib_b200/csrc/experimental/ (they are compiled into
+# libb200z.so with b200z_deflate.cu and launched only with B200Z_TILE_PARSE=1|2), next to the kernels they would replace.
 set -e
 cd "$(dirname "$0")/../sharpziplib_b200/csrc"
-cat > /tmp/b200z_experimental_check.cu <<EOT
-#include "$(pwd)/b200z_deflate.cu"
-namespace b200z {
-#include "$(pwd)/experimental/k_tile_parse.cuh"
-}
-EOT
-nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -I"$(pwd)" -Xptxas -v -c /tmp/b200z_experimental_check.cu -o /tmp/b200z_experimental_check.o 2>&1 | grep -A2 "k_tile_parse" | head -8
-cuobjdump --dump-resource-usage /tmp/b200z_experimental_check.o 2>/dev/null | grep -A1 k_tile_parse | head -3
+nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xptxas -v -c b200z_deflate.cu -o /tmp/b200z_experimental_check.o 2>&1 \
+  | grep -A3 "Compiling entry function.*\(k_tile_parse\|k_parse_fix\|k_match\|k_parse_chunk\)" | grep -v "^--" | sed 's/_ZN5b200z[0-9]*//; s/EPK.*for/ for/'
