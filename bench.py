@@ -484,9 +484,9 @@ def main():
     probe = None
     if rank == 0 and world == 1 and not args.small and not args.no_probe and not os.environ.get("B200Z_TILE_PARSE"):
         probe = {}
-        for variant in ("2", "1"):
+        for variant in ("3", "2", "1"):
             try:
-                r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "tile_parse_check.py"), variant, "64"], cwd=ROOT,
+                r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "tile_parse_check.py"), variant, "256"], cwd=ROOT,
                                    stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=150)
                 last = (r.stdout.decode(errors="replace").strip().splitlines() or [""])[-1]
                 try:
@@ -507,7 +507,7 @@ def main():
                        "parity": "deflate bytes == oracle and inflate bytes == original, checked on 16 buffers each before timing",
                        "ratio_deflate": U_def / max(1, C_def), "ratio_inflate": U_inf / max(1, C_inf), "setup_s": setup_s,
                        # opt-in search kernel (csrc/experimental/k_tile_parse.cuh); "" = the default k_match + k_parse_chunk
-                       "search_variant": ("tile_parse%s" % os.environ["B200Z_TILE_PARSE"]) if os.environ.get("B200Z_TILE_PARSE") in ("1", "2") else "default"},
+                       "search_variant": ("tile_parse%s" % os.environ["B200Z_TILE_PARSE"]) if os.environ.get("B200Z_TILE_PARSE") in ("1", "2", "3") else "default"},
             "deflate_gbs": U_def / (t_def / 1e3) / 1e9 if t_def else None,
             "inflate_gbs": U_inf / (t_inf / 1e3) / 1e9 if t_inf else None,
             "kernels_ms": acc,
@@ -524,7 +524,7 @@ def main():
             "gpu_launches": int(dplan.launches + iplan.launches) * args.steps,
             "gpu_launches_per_step": int(dplan.launches + iplan.launches),
             "clocks": clocks,
-            # separate process, after the timed regions, 64 x 256 KiB: bit-exactness and per-kernel ms of the opt-in search
+            # separate process, after the timed regions, 256 x 256 KiB: bit-exactness and per-kernel ms of the opt-in search
             # kernels next to the default path (tools/tile_parse_check.py); informational
             "experimental_probe": probe,
         }

@@ -1117,10 +1117,10 @@ int deflate_plan_build(b200z_plan *p) {
 	}
 	// B200Z_TILE_PARSE=1: k_tile_parse (search driven by the parse) instead of k_match + k_parse_chunk; the hand-off inside the
 	// kernel spans one tile, so tiles are the chunks k_parse_fix stitches -- streams of more than 1024 tiles keep the old path
-	// (1: k_tile_parse, every lane searches for itself; 2: k_tile_parse2, proxies + batched searches)
+	// (1: k_tile_parse, every lane searches for itself; 2: k_tile_parse2, proxies + batched searches; 3: the same, 1024 threads)
 	// Opt-in until it has been measured on a B200 (written without GPU time left; bit-exact on tests/cuda_emu).
 	p->tile_parse = (lp.func == 2 && getenv("B200Z_TILE_PARSE") && maxlen <= 1024ll * kFTile) ? atoi(getenv("B200Z_TILE_PARSE")) : 0;
-	if (p->tile_parse != 1 && p->tile_parse != 2) p->tile_parse = 0;
+	if (p->tile_parse < 1 || p->tile_parse > 3) p->tile_parse = 0;
 	if (p->tile_parse) chunk = kFTile;
 	p->parse_chunk = chunk;
 	{
@@ -1328,7 +1328,8 @@ int deflate_plan_build(b200z_plan *p) {
 	B200Z_CUDA(cudaFuncSetAttribute(k_links, cudaFuncAttributeMaxDynamicSharedMemorySize, kLinksSmem));
 	B200Z_CUDA(cudaFuncSetAttribute(k_match, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileData + 2 * 2 * kTile));
 	B200Z_CUDA(cudaFuncSetAttribute(k_tile_parse, cudaFuncAttributeMaxDynamicSharedMemorySize, kFSmem));
-	B200Z_CUDA(cudaFuncSetAttribute(k_tile_parse2, cudaFuncAttributeMaxDynamicSharedMemorySize, kFSmem));
+	B200Z_CUDA(cudaFuncSetAttribute(k_tile_parse2<kFThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFSmem));
+	B200Z_CUDA(cudaFuncSetAttribute(k_tile_parse2<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFSmem));
 	p->launches = (lp.func == 2 ? (p->tile_parse ? 8 : 9) : (lp.func == 1 ? 4 : 2)) + (p->wrap != B200Z_WRAP_RAW ? 3 : 0); // + one memset node
 	return B200Z_OK;
 }
@@ -1408,9 +1409,13 @@ int deflate_plan_run(b200z_plan *p, const uint8_t *d_in, uint8_t *d_out, int64_t
 			                                                   ws.at<int2>(p->o_tile_desc), ws.at<uint32_t>(p->o_rnd_off),
 			                                                   ws.at<RoundRec>(p->o_recs), hist, bias, lp, p->strategy);
 		if (p->n_tiles && p->tile_parse == 2)
-			k_tile_parse2<<<p->n_tiles, kFThreads, kFSmem, s>>>(d_in, link, mt, ws.at<uint32_t>(p->o_sym_local), in_off, in_len,
-			                                                    ws.at<int2>(p->o_tile_desc), ws.at<uint32_t>(p->o_rnd_off),
-			                                                    ws.at<RoundRec>(p->o_recs), hist, bias, sym, lp, p->strategy);
+			k_tile_parse2<kFThreads><<<p->n_tiles, kFThreads, kFSmem, s>>>(d_in, link, mt, ws.at<uint32_t>(p->o_sym_local), in_off, in_len,
+			                                                               ws.at<int2>(p->o_tile_desc), ws.at<uint32_t>(p->o_rnd_off),
+			                                                               ws.at<RoundRec>(p->o_recs), hist, bias, sym, lp, p->strategy);
+		if (p->n_tiles && p->tile_parse == 3) // the same with 32 warps: the upper 16 only serve the batches
+			k_tile_parse2<1024><<<p->n_tiles, 1024, kFSmem, s>>>(d_in, link, mt, ws.at<uint32_t>(p->o_sym_local), in_off, in_len,
+			                                                     ws.at<int2>(p->o_tile_desc), ws.at<uint32_t>(p->o_rnd_off),
+			                                                     ws.at<RoundRec>(p->o_recs), hist, bias, sym, lp, p->strategy);
 		}
 		if (!do_encode) {
 			B200Z_CUDA(cudaGetLastError());

@@ -281,7 +281,12 @@ __device__ __forceinline__ void tile_walk(const uint8_t *s_data, const uint16_t 
 	if (!haveB) resB = resA;
 }
 
-__global__ void __launch_bounds__(kFThreads, 1)
+// kThreads = kFThreads (512): every thread owns a segment.  kThreads = 1024: the upper 16 warps own no segment and wait at the
+// barrier while the others parse; staging, the batch phase (classification, ordering, walks) and the table write-back run on
+// all 32 warps -- the walks are the bulk of the work and k_match needed its 32 warps per SM to hide the shared-memory hops
+// (64 registers at 1024 threads, no spills).
+template <int kThreads>
+__global__ void __launch_bounds__(kThreads, 1)
     k_tile_parse2(const uint8_t *__restrict__ in, const uint16_t *__restrict__ link, uint2 *__restrict__ mt,
                   uint32_t *__restrict__ sym_local, const int64_t *__restrict__ in_off, const int64_t *__restrict__ in_len,
                   const int2 *__restrict__ tile_desc, const uint32_t *__restrict__ rnd_off, RoundRec *__restrict__ recs,
@@ -315,14 +320,14 @@ __global__ void __launch_bounds__(kFThreads, 1)
 		const uint32_t nbytes = dend - w0, nvec = nbytes >> 4;
 		const uint4 *src = reinterpret_cast<const uint4 *>(data + w0);
 		uint4 *dst = reinterpret_cast<uint4 *>(s_data);
-		for (uint32_t i = tid; i < nvec; i += kFThreads) dst[i] = __ldg(src + i);
-		for (uint32_t i = (nvec << 4) + tid; i < nbytes; i += kFThreads) s_data[i] = data[w0 + i];
+		for (uint32_t i = tid; i < nvec; i += kThreads) dst[i] = __ldg(src + i);
+		for (uint32_t i = (nvec << 4) + tid; i < nbytes; i += kThreads) s_data[i] = data[w0 + i];
 		const uint32_t nl = t1 - w0, nlv = nl >> 3;
 		const uint4 *lsrc = reinterpret_cast<const uint4 *>(lnk + w0);
 		uint4 *ldst = reinterpret_cast<uint4 *>(s_link);
-		for (uint32_t i = tid; i < nlv; i += kFThreads) ldst[i] = __ldg(lsrc + i);
-		for (uint32_t i = (nlv << 3) + tid; i < nl; i += kFThreads) s_link[i] = lnk[w0 + i];
-		for (uint32_t i = tid; i < (uint32_t)kFTile; i += kFThreads) s_memo[i] = kFNone;
+		for (uint32_t i = tid; i < nlv; i += kThreads) ldst[i] = __ldg(lsrc + i);
+		for (uint32_t i = (nlv << 3) + tid; i < nl; i += kThreads) s_link[i] = lnk[w0 + i];
+		for (uint32_t i = tid; i < (uint32_t)kFTile; i += kThreads) s_memo[i] = kFNone;
 		if (tid == 0) s_nreq = 0;
 	}
 	__syncthreads();
@@ -356,11 +361,12 @@ __global__ void __launch_bounds__(kFThreads, 1)
 	};
 	auto bytef = [&](uint32_t q) { return (uint32_t)s_data[q - w0]; };
 	auto slowf = [&](uint32_t p, uint32_t m0, uint32_t budget) { return match_search_above(data, lnk, p, n, m0, budget, ab); };
-	const uint32_t seg0 = t0 + (uint32_t)tid * kSeg, seg_end = seg0 + kSeg;
-	const uint32_t lim = seg_end < n ? seg_end : n;
+	const bool owner = kThreads == kFThreads || tid < kFThreads; // (warp-uniform) this thread owns a segment
+	const uint32_t seg0 = t0 + (uint32_t)(owner ? tid : 0) * kSeg, seg_end = seg0 + kSeg;
+	const uint32_t lim = !owner ? 0u : seg_end < n ? seg_end : n;
 	ParseCarry entry = clean_carry(seg0 > H ? seg0 : H), ex = entry;
 	uint32_t cnt = 0;
-	bool dirty = true;
+	bool dirty = owner;
 	for (int pass = 0; pass < 4 * kFThreads; pass++) {
 		// ---- parse: exact entries where there are, proxies elsewhere ----
 		if (dirty) {
@@ -378,7 +384,7 @@ __global__ void __launch_bounds__(kFThreads, 1)
 			}
 			__syncwarp();
 		}
-		s_exit[tid] = f_pack(ex);
+		if (owner) s_exit[tid] = f_pack(ex);
 		__syncthreads();
 		// ---- batch: the CTA serves the pass's requests ----
 		const uint32_t nreq = s_nreq;
@@ -389,7 +395,7 @@ __global__ void __launch_bounds__(kFThreads, 1)
 			// a warp then hold walks of similar length.  The order only decides who computes what.
 			if (tid < 2 * kMatchClasses) (&s_cls[0][0])[tid] = 0;
 			__syncthreads();
-			for (uint32_t r = tid; r < nreq; r += kFThreads) {
+			for (uint32_t r = tid; r < nreq; r += kThreads) {
 				const uint32_t is = (uint32_t)req[r] + (t0 - w0);
 				uint32_t dist = s_link[is], hops = 1, cls;
 				while (hops < 8) {
@@ -417,11 +423,11 @@ __global__ void __launch_bounds__(kFThreads, 1)
 				}
 			}
 			__syncthreads();
-			for (uint32_t r = tid; r < nreq; r += kFThreads) ord[atomicAdd(&s_cls[1][req_cls[r]], 1u)] = req[r];
+			for (uint32_t r = tid; r < nreq; r += kThreads) ord[atomicAdd(&s_cls[1][req_cls[r]], 1u)] = req[r];
 			__syncthreads();
 			work = ord;
 		}
-		for (uint32_t r = tid; r < nreq; r += kFThreads) {
+		for (uint32_t r = tid; r < nreq; r += kThreads) {
 			const uint32_t i = work[r];
 			uint32_t a, b;
 			tile_walk(s_data, s_link, w0, t0 + i, n, lp, ab, a, b);
@@ -431,7 +437,7 @@ __global__ void __launch_bounds__(kFThreads, 1)
 		if (tid == 0) s_nreq = 0;
 		// ---- who parses again: a proxy was used (its entry is exact now), or the predecessor's exit moved ----
 		bool changed = false;
-		if (tid > 0) {
+		if (owner && tid > 0) {
 			const ParseCarry ne = f_unpack(s_exit[tid - 1]);
 			changed = !carry_equal(ne, entry);
 			entry = ne;
@@ -441,7 +447,7 @@ __global__ void __launch_bounds__(kFThreads, 1)
 	}
 	// ---- final pass (every entry it reads is exact) and the table for the fix-up: as k_tile_parse ----
 	const uint32_t rbase = t0 + (uint32_t)warp * kRound;
-	if (rbase < n) {
+	if (owner && rbase < n) {
 		uint32_t incl = cnt;
 		for (int o = 1; o < 32; o <<= 1) {
 			const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
@@ -475,7 +481,7 @@ __global__ void __launch_bounds__(kFThreads, 1)
 	}
 	__syncthreads();
 	uint2 *out = mt + off + t0;
-	for (uint32_t i = tid; i < t1 - t0; i += kFThreads) {
+	for (uint32_t i = tid; i < t1 - t0; i += kThreads) {
 		const uint32_t m = s_memo[i];
 		out[i] = m >= kFReq ? make_uint2(kFNone, kFNone) : make_uint2(m & ~kFNeedB, (m & kFNeedB) ? kFNone : (m & ~kFNeedB));
 	}
