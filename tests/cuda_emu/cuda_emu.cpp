@@ -1,6 +1,9 @@
 // cuda_emu.cpp -- TEST INFRASTRUCTURE: the block scheduler of cuda_emu.h
 #include "cuda_emu.h"
 
+#include <algorithm>
+#include <vector>
+
 namespace emu {
 
 Block *g_block = nullptr;
@@ -48,14 +51,43 @@ void launch(dim3 grid, dim3 block, size_t smem_bytes, std::function<void()> body
 		if (s == MAP_FAILED) abort();
 		g_stacks.push_back(s);
 	}
+	// B200Z_EMU_ORDER: the order in which the threads of a block are resumed in a scheduling round, and the order of the blocks
+	// of a grid.  "fwd" (default): ascending.  "rev": descending.  "rand:<seed>": a fresh pseudo-random permutation per round,
+	// blocks in a random order.  A kernel whose result depends on the order has a race (a read of another thread's write
+	// without a barrier in between, an assumption about which block runs first): run the tests under all three.
+	static int order_mode = -1;
+	static uint64_t rng = 0;
+	if (order_mode < 0) {
+		const char *e = getenv("B200Z_EMU_ORDER");
+		order_mode = 0;
+		if (e && !strcmp(e, "rev")) order_mode = 1;
+		if (e && !strncmp(e, "rand", 4)) {
+			order_mode = 2;
+			rng = 0x9E3779B97F4A7C15ull ^ (uint64_t)(e[4] == ':' ? atoll(e + 5) : 1);
+		}
+	}
+	auto next_rand = [&]() {
+		rng ^= rng << 13;
+		rng ^= rng >> 7;
+		rng ^= rng << 17;
+		return rng;
+	};
+	auto permute = [&](std::vector<int> &v) {
+		const int n = (int)v.size();
+		for (int i = 0; i < n; i++) v[(size_t)i] = order_mode == 1 ? n - 1 - i : i;
+		if (order_mode == 2)
+			for (int i = n - 1; i > 0; i--) std::swap(v[(size_t)i], v[(size_t)(next_rand() % (uint64_t)(i + 1))]);
+	};
+	std::vector<int> torder((size_t)nt), border((size_t)(grid.x * grid.y * grid.z));
+	permute(border);
 	Block b;
 	b.bdim = block;
 	b.gdim = grid;
 	b.body = body;
 	b.smem = g_smem;
-	for (unsigned bz = 0; bz < grid.z; bz++)
-		for (unsigned by = 0; by < grid.y; by++)
-			for (unsigned bx = 0; bx < grid.x; bx++) {
+	for (size_t bi = 0; bi < border.size(); bi++) {
+				const unsigned lin = (unsigned)border[bi];
+				const unsigned bx = lin % grid.x, by = (lin / grid.x) % grid.y, bz = lin / (grid.x * grid.y);
 				b.bid = dim3(bx, by, bz);
 				memset(g_smem, 0xCD, smem_bytes + 64); // shared memory is not cleared between blocks
 				memset(g_smem + smem_bytes, 0xEE, 64);
@@ -83,7 +115,9 @@ void launch(dim3 grid, dim3 block, size_t smem_bytes, std::function<void()> body
 				b.or_reset_gen = 0xFFFFFFFFu;
 				while (remaining > 0) {
 					const uint64_t before = g_events;
-					for (int t = 0; t < nt; t++) {
+					permute(torder);
+					for (int ti = 0; ti < nt; ti++) {
+						const int t = torder[(size_t)ti];
 						Fiber &f = b.fibers[(size_t)t];
 						if (f.done) continue;
 						g_cur = &f;
