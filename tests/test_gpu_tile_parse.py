@@ -16,16 +16,23 @@ import warnings
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_hung = []  # variants whose check did not come back in time
 
 
 @pytest.mark.gpu
 @pytest.mark.xfail(strict=False, reason="experimental kernels that have never run on a GPU (emulator-checked only); opt-in, not the product path")
 @pytest.mark.parametrize("variant", ["3", "2", "1"])
 def test_tile_parse_variant_is_bit_exact(variant):
+    if _hung:
+        pytest.skip("an earlier variant hung; the variants share most of their code")
     env = dict(os.environ)
     env.pop("B200Z_TILE_PARSE", None)
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "tile_parse_check.py"), variant, "64"], cwd=ROOT, env=env,
-                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=180)
+    try:
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "tile_parse_check.py"), variant, "64"], cwd=ROOT, env=env,
+                           stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=120)
+    except subprocess.TimeoutExpired:
+        _hung.append(variant)
+        raise
     out = r.stdout.decode(errors="replace").strip().splitlines()
     line = out[-1] if out else ""
     warnings.warn("tile_parse_check %s: rc=%d %s" % (variant, r.returncode, line[:1500]))
