@@ -89,6 +89,20 @@ def main():
     del os.environ["B200Z_TILE_PARSE"]
     t_def, outs = per_kernel_ms(z, bufs, 6)
     assert outs == refs, "default path"
+    # ---- level 9 (chain 4096: k_match walks 24.6x the candidates the reference walks there), 64 buffers ------------------
+    b9 = bufs[:64]
+    refs9 = O.batch(0, b9, level=9, threads=8)
+    os.environ["B200Z_TILE_PARSE"] = variant
+    t9_var, outs = per_kernel_ms(z, b9, 9, reps=2)
+    if outs != refs9:
+        res["mismatch"] = {"level": 9, "shape": "c3"}
+        print(json.dumps(res))
+        return 1
+    del os.environ["B200Z_TILE_PARSE"]
+    t9_def, outs = per_kernel_ms(z, b9, 9, reps=2)
+    assert outs == refs9, "default path, level 9"
+    res["level9_search_plus_parse_ms"] = {"buffers": len(b9), "default": t9_def.get("k_match", 0.0) + t9_def.get("k_parse", 0.0),
+                                          "variant": t9_var.get("k_tile_parse", 0.0) + t9_var.get("k_parse", 0.0)}
     search_def = t_def.get("k_match", 0.0) + t_def.get("k_parse", 0.0)
     search_var = t_var.get("k_tile_parse", 0.0) + t_var.get("k_parse", 0.0)
     res.update({"ok": True, "buffers": nbuf, "bytes": sum(len(b) for b in bufs), "default_ms": t_def, "variant_ms": t_var,
