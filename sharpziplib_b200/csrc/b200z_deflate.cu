@@ -50,7 +50,8 @@ constexpr int kLinksSmem = 65536 + 2 * kLinkChunk * 4;
 __global__ void __launch_bounds__(kLinkThreads) k_links(const uint8_t *__restrict__ in, uint16_t *__restrict__ link,
                                                         const int64_t *__restrict__ in_off, const int64_t *__restrict__ in_len,
                                                         const int2 *__restrict__ run_desc, const uint32_t *__restrict__ hist,
-                                                        const uint8_t *__restrict__ hmask, const int64_t *__restrict__ hm_off) {
+                                                        const uint8_t *__restrict__ hmask, const int64_t *__restrict__ hm_off,
+                                                        uint32_t run_len) {
 	extern __shared__ __align__(16) uint8_t lsm[];
 	uint16_t *head = reinterpret_cast<uint16_t *>(lsm);             // 32768 entries: position - winbase + 1, 0 = empty
 	uint32_t *info = reinterpret_cast<uint32_t *>(lsm + 65536);     // two buffers of kLinkChunk words
@@ -60,7 +61,7 @@ __global__ void __launch_bounds__(kLinkThreads) k_links(const uint8_t *__restric
 	const uint8_t *data = in + in_off[rd.x];
 	uint16_t *lnk = link + in_off[rd.x];
 	const uint32_t start = (uint32_t)rd.y;
-	const uint32_t run_end = (n - start > (uint32_t)kRun) ? start + kRun : n;
+	const uint32_t run_end = (n - start > run_len) ? start + run_len : n; // run_len: kRun, or what B200Z_LINK_RUN asked for
 	const uint32_t warm = start >= 32768u ? start - 32768u : 0u;
 	// history (preset dictionary / earlier segments of the same stream): positions the reference never inserted
 	// (the last two of a dictionary, DeflaterEngine.cs:217-226, or of a flushed segment, trap T9) are masked
@@ -1121,6 +1122,15 @@ int deflate_plan_build(b200z_plan *p) {
 	// Opt-in until it has been measured on a B200 (written without GPU time left; bit-exact on tests/cuda_emu).
 	p->tile_parse = (lp.func == 2 && getenv("B200Z_TILE_PARSE") && maxlen <= 1024ll * kFTile) ? atoi(getenv("B200Z_TILE_PARSE")) : 0;
 	if (p->tile_parse < 1 || p->tile_parse > 3) p->tile_parse = 0;
+	// B200Z_LINK_RUN=<positions>: run length of k_links (a multiple of 32768, 65536 .. 1048576).  Every run but a stream's first
+	// re-walks 32768 positions to warm its head table up, so 64 Ki runs do 37 % more steps than the stream has positions on
+	// 256 KiB buffers and 128 Ki runs 12 %; fewer, longer CTAs on the other hand fill the last wave worse.  Opt-in like the
+	// search kernels until both have been timed on a B200 (tools/tile_parse_check.py times k_links under both).
+	p->link_run = kRun;
+	if (const char *e = getenv("B200Z_LINK_RUN")) {
+		const long v = atol(e);
+		if (v >= 65536 && v <= 1048576 && v % 32768 == 0) p->link_run = (int)v;
+	}
 	if (p->tile_parse) chunk = kFTile;
 	p->parse_chunk = chunk;
 	{
@@ -1160,7 +1170,7 @@ int deflate_plan_build(b200z_plan *p) {
 		p->out_off[i] = oo;
 		p->out_cap[i] = align_up(b200z_deflate_bound(len), kAlign);
 		oo += p->out_cap[i];
-		for (int64_t s = 0; s < len; s += kRun) runs.push_back(make_int2(i, (int)s));
+		for (int64_t s = 0; s < len; s += p->link_run) runs.push_back(make_int2(i, (int)s));
 		for (int64_t s = 0; s < len; s += (p->tile_parse ? kFTile : kTile)) tiles.push_back(make_int2(i, (int)s));
 		for (int64_t s = 0; s < len; s += chunk)
 			chunks.push_back(ChunkDesc{i, (uint32_t)s, (uint32_t)(len - s > (int64_t)chunk ? s + chunk : len)});
@@ -1399,7 +1409,7 @@ int deflate_plan_run(b200z_plan *p, const uint8_t *d_in, uint8_t *d_out, int64_t
 		if (do_search) {
 		p->mark(s, "k_links");
 		if (p->n_runs) k_links<<<p->n_runs, kLinkThreads, kLinksSmem, s>>>(d_in, link, in_off, in_len, ws.at<int2>(p->o_run_desc), hist,
-			                                                         ws.at<uint8_t>(p->o_hmask), ws.at<int64_t>(p->o_hm_off));
+			                                                         ws.at<uint8_t>(p->o_hmask), ws.at<int64_t>(p->o_hm_off), (uint32_t)p->link_run);
 		p->mark(s, p->tile_parse ? "k_tile_parse" : "k_match");
 		if (p->n_tiles && !p->tile_parse)
 			k_match<<<p->n_tiles, kMatchThreads, kTileData + 2 * 2 * kTile, s>>>(d_in, link, mt, in_off, in_len,

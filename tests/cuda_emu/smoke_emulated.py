@@ -33,6 +33,14 @@ for variant in ("1", "2", "3"):
     outs, _ = z.deflate_batch(tile_bufs, level=6)
     assert outs == tile_refs, "B200Z_TILE_PARSE=" + variant
 del os.environ["B200Z_TILE_PARSE"]
+# k_links with longer runs (B200Z_LINK_RUN): a stream of two 64 Ki runs / one 128 Ki run + a tail
+long_buf = [datagen.silesia_mix(3, 140000).tobytes()]
+long_ref = [O.deflate(long_buf[0], level=6)]
+for run in ("65536", "131072"):
+    os.environ["B200Z_LINK_RUN"] = run
+    outs, _ = z.deflate_batch(long_buf, level=6)
+    assert outs == long_ref, "B200Z_LINK_RUN=" + run
+del os.environ["B200Z_LINK_RUN"]
 outs, checks = z.deflate_batch(bufs[:2], level=6, wrap=1)  # zlib framing: Adler-32 on the device (k_checksum)
 assert outs == [O.deflate(b, level=6, nowrap=False) for b in bufs[:2]]
 

@@ -22,6 +22,7 @@ done
 echo "fastest bit-exact variant: ${best:-none} ($best_ms ms search+parse on 256 x 256 KiB)" | tee -a $O/summary.txt
 python bench.py --no-probe > $O/bench_default.json 2> $O/bench_default.err; echo "bench default rc=$?" | tee -a $O/summary.txt
 if [ -n "$best" ]; then
+  B200Z_LINK_RUN=131072 python bench.py --no-probe > $O/bench_link_run_128k.json 2> $O/bench_link_run_128k.err; echo "bench link run 128Ki rc=$?" | tee -a $O/summary.txt
   B200Z_TILE_PARSE=$best python bench.py > $O/bench_tile_parse$best.json 2> $O/bench_tile_parse$best.err; echo "bench variant $best rc=$?" | tee -a $O/summary.txt
   B200Z_TILE_PARSE=$best timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_tile_parse -c 2 \
       -o $O/ncu_tile_parse$best python tools/prof_small.py > $O/ncu_tile_parse$best.log 2>&1; echo "ncu variant rc=$?" | tee -a $O/summary.txt
