@@ -5,7 +5,8 @@
 #   1. GPU test tier (is the product path still green; the opt-in kernels' subprocess test reports XPASS / xfail)
 #   2. tools/tile_parse_check.py for the three opt-in search kernels: bit-exactness + per-kernel ms next to the default path
 #   3. bench.py default, then with the fastest bit-exact variant (each line labels config.search_variant)
-#   4. ncu: launch list of the default bench, --set full of the opt-in kernels on tools/prof_small.py's workload
+#   4. ncu: --set full of the opt-in kernel and of k_inflate / k_links / k_plan on tools/prof_small.py's workload, launch list of
+#      the default bench
 set -u
 O=gpurun_out/r2_first
 mkdir -p $O
@@ -27,6 +28,10 @@ if [ -n "$best" ]; then
   B200Z_TILE_PARSE=$best timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_tile_parse -c 2 \
       -o $O/ncu_tile_parse$best python tools/prof_small.py > $O/ncu_tile_parse$best.log 2>&1; echo "ncu variant rc=$?" | tee -a $O/summary.txt
 fi
+for k in k_inflate k_links k_plan; do  # the next kernels in line once the search is faster (launch 0 is the warm-up run)
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:^$k --launch-skip 1 -c 1 \
+      -o $O/ncu_$k python tools/prof_small.py > $O/ncu_$k.log 2>&1; echo "ncu $k rc=$?" | tee -a $O/summary.txt
+done
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches_default.csv \
     python bench.py --steps 2 --warmup 1 --no-probe > $O/launches_default.log 2>&1; echo "ncu launch list rc=$?" | tee -a $O/summary.txt
 cat $O/summary.txt
