@@ -1,6 +1,6 @@
 #!/bin/bash
 # One gpurun call that answers the questions round 1 left open, in the order that matters if it is cut short:
-#   gpurun --timeout 1500 -- 'bash tools/round2_first_call.sh'
+#   gpurun --timeout 2400 -- 'bash tools/round2_first_call.sh'      (about 30 GPU-minutes: tests 2, checks 2, three bench runs 9, five ncu passes 17)
 # Everything lands in gpurun_out/r2_first/ (merged back by gpurun); copy what is to be judged into profiles/.
 #   1. GPU test tier (is the product path still green; the opt-in kernels' subprocess test reports XPASS / xfail)
 #   2. tools/tile_parse_check.py for the three opt-in search kernels: bit-exactness + per-kernel ms next to the default path
