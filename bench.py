@@ -485,7 +485,7 @@ def main():
     if rank == 0 and world == 1 and not args.small and not args.no_probe and not os.environ.get("B200Z_TILE_PARSE"):
         probe = {}
         t_probe = time.time()  # bounded: 90 s per variant, 150 s in all, and nothing after a variant that hung
-        for variant in ("3", "2", "1"):
+        for variant in ("4", "3", "2", "1"):
             left = 150.0 - (time.time() - t_probe)
             if left < 20.0:
                 probe["tile_parse" + variant] = {"ok": None, "skipped": "probe time budget spent"}
@@ -513,7 +513,7 @@ def main():
                        "parity": "deflate bytes == oracle and inflate bytes == original, checked on 16 buffers each before timing",
                        "ratio_deflate": U_def / max(1, C_def), "ratio_inflate": U_inf / max(1, C_inf), "setup_s": setup_s,
                        # opt-in search kernel (csrc/experimental/k_tile_parse.cuh); "" = the default k_match + k_parse_chunk
-                       "search_variant": ("tile_parse%s" % os.environ["B200Z_TILE_PARSE"]) if os.environ.get("B200Z_TILE_PARSE") in ("1", "2", "3") else "default",
+                       "search_variant": ("tile_parse%s" % os.environ["B200Z_TILE_PARSE"]) if os.environ.get("B200Z_TILE_PARSE") in ("1", "2", "3", "4") else "default",
                        "link_run": int(os.environ.get("B200Z_LINK_RUN", "65536"))},
             "deflate_gbs": U_def / (t_def / 1e3) / 1e9 if t_def else None,
             "inflate_gbs": U_inf / (t_inf / 1e3) / 1e9 if t_inf else None,

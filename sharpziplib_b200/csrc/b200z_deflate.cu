@@ -532,7 +532,7 @@ __device__ __forceinline__ void parse_fix_body(uint8_t *smem, const uint8_t *__r
                                                const int64_t *__restrict__ in_off, const int64_t *__restrict__ in_len,
                                                const uint32_t *__restrict__ rnd_off, RoundRec *__restrict__ recs, uint32_t chunk,
                                                const uint32_t *__restrict__ hist, const int64_t *__restrict__ bias,
-                                               const LevelParams &lp, int strategy) {
+                                               const LevelParams &lp, int strategy, const RoundRec *__restrict__ ent) {
 	const int stream = blockIdx.x;
 	const uint32_t n = (uint32_t)in_len[stream];
 	if (n <= chunk) return; // a single chunk was parsed from the true initial state
@@ -544,7 +544,15 @@ __device__ __forceinline__ void parse_fix_body(uint8_t *smem, const uint8_t *__r
 		ParseCarry truth = rec_carry(rr[c0 / kRound - 1]); // exit of the previous chunk's last round, exact by induction
 		{
 			ParseCarry guess = clean_carry(c0);
-			guess.last_top = truth.last_top; // irrelevant here: the chunk processes at least one loop top
+			bool recorded = false;
+			if (kLazyTab && ent) { // the tile kernel with a warm-up says which state its tile started from
+				const RoundRec e = (ent + rnd_off[stream])[c0 / kRound];
+				if (e.cnt) {
+					guess = rec_carry(e);
+					recorded = true;
+				}
+			}
+			if (!recorded) guess.last_top = truth.last_top; // irrelevant here: the chunk processes at least one loop top
 			if (carry_equal(truth, guess)) continue; // the guess was right
 		}
 		for (uint32_t base = c0; base < c1; base += kRound) {
@@ -573,7 +581,7 @@ __global__ void __launch_bounds__(32)
                 const uint32_t *__restrict__ rnd_off, RoundRec *__restrict__ recs, uint32_t chunk, const uint32_t *__restrict__ hist,
                 const int64_t *__restrict__ bias, LevelParams lp, int strategy) {
 	extern __shared__ __align__(16) uint8_t smem[];
-	parse_fix_body<false>(smem, in, link, mt, sym_local, in_off, in_len, rnd_off, recs, chunk, hist, bias, lp, strategy);
+	parse_fix_body<false>(smem, in, link, mt, sym_local, in_off, in_len, rnd_off, recs, chunk, hist, bias, lp, strategy, nullptr);
 }
 
 // the fix-up behind the tile kernels (B200Z_TILE_PARSE): table entries they did not compute are searched on demand
@@ -581,9 +589,10 @@ __global__ void __launch_bounds__(32)
     k_parse_fix_lazy(const uint8_t *__restrict__ in, const uint16_t *__restrict__ link, const uint2 *__restrict__ mt,
                      uint32_t *__restrict__ sym_local, const int64_t *__restrict__ in_off, const int64_t *__restrict__ in_len,
                      const uint32_t *__restrict__ rnd_off, RoundRec *__restrict__ recs, uint32_t chunk,
-                     const uint32_t *__restrict__ hist, const int64_t *__restrict__ bias, LevelParams lp, int strategy) {
+                     const uint32_t *__restrict__ hist, const int64_t *__restrict__ bias, LevelParams lp, int strategy,
+                     const RoundRec *__restrict__ ent) {
 	extern __shared__ __align__(16) uint8_t smem[];
-	parse_fix_body<true>(smem, in, link, mt, sym_local, in_off, in_len, rnd_off, recs, chunk, hist, bias, lp, strategy);
+	parse_fix_body<true>(smem, in, link, mt, sym_local, in_off, in_len, rnd_off, recs, chunk, hist, bias, lp, strategy, ent);
 }
 
 // exclusive scan of the rounds' symbol counts of one stream; also the end-of-stream bookkeeping
@@ -1118,10 +1127,10 @@ int deflate_plan_build(b200z_plan *p) {
 	}
 	// B200Z_TILE_PARSE=1: k_tile_parse (search driven by the parse) instead of k_match + k_parse_chunk; the hand-off inside the
 	// kernel spans one tile, so tiles are the chunks k_parse_fix stitches -- streams of more than 1024 tiles keep the old path
-	// (1: k_tile_parse, every lane searches for itself; 2: k_tile_parse2, proxies + batched searches; 3: the same, 1024 threads)
+	// (1: k_tile_parse, every lane searches for itself; 2: k_tile_parse2, proxies + batched searches; 3: the same, 1024 threads; 4: 3 + warm-up for the tile's entry state)
 	// Opt-in until it has been measured on a B200 (written without GPU time left; bit-exact on tests/cuda_emu).
 	p->tile_parse = (lp.func == 2 && getenv("B200Z_TILE_PARSE") && maxlen <= 1024ll * kFTile) ? atoi(getenv("B200Z_TILE_PARSE")) : 0;
-	if (p->tile_parse < 1 || p->tile_parse > 3) p->tile_parse = 0;
+	if (p->tile_parse < 1 || p->tile_parse > 4) p->tile_parse = 0;
 	// B200Z_LINK_RUN=<positions>: run length of k_links (a multiple of 32768, 65536 .. 1048576).  Every run but a stream's first
 	// re-walks 32768 positions to warm its head table up, so 64 Ki runs do 37 % more steps than the stream has positions on
 	// 256 KiB buffers and 128 Ki runs 12 %; fewer, longer CTAs on the other hand fill the last wave worse.  Opt-in like the
@@ -1250,6 +1259,7 @@ int deflate_plan_build(b200z_plan *p) {
 		p->o_rgroups = ws.reserve(8ll * (rgroups.size() + 1));
 		p->o_rnd_off = ws.reserve(4ll * (n + 1));
 		p->o_recs = ws.reserve((int64_t)sizeof(RoundRec) * (nrounds + 1));
+		if (p->tile_parse == 4) p->o_ent = ws.reserve((int64_t)sizeof(RoundRec) * (nrounds + 1)); // entry state of every tile
 		p->o_rnd_symoff = ws.reserve(4ll * (nrounds + 1));
 	}
 	if (lp.func != 0) p->o_sym = ws.reserve(4ll * io + 64);
@@ -1338,8 +1348,9 @@ int deflate_plan_build(b200z_plan *p) {
 	B200Z_CUDA(cudaFuncSetAttribute(k_links, cudaFuncAttributeMaxDynamicSharedMemorySize, kLinksSmem));
 	B200Z_CUDA(cudaFuncSetAttribute(k_match, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileData + 2 * 2 * kTile));
 	B200Z_CUDA(cudaFuncSetAttribute(k_tile_parse, cudaFuncAttributeMaxDynamicSharedMemorySize, kFSmem));
-	B200Z_CUDA(cudaFuncSetAttribute(k_tile_parse2<kFThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFSmem));
-	B200Z_CUDA(cudaFuncSetAttribute(k_tile_parse2<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFSmem));
+	B200Z_CUDA(cudaFuncSetAttribute((k_tile_parse2<kFThreads, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, kFSmem));
+	B200Z_CUDA(cudaFuncSetAttribute((k_tile_parse2<1024, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, kFSmem));
+	B200Z_CUDA(cudaFuncSetAttribute((k_tile_parse2<1024, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, kFSmem));
 	p->launches = (lp.func == 2 ? (p->tile_parse ? 8 : 9) : (lp.func == 1 ? 4 : 2)) + (p->wrap != B200Z_WRAP_RAW ? 3 : 0); // + one memset node
 	return B200Z_OK;
 }
@@ -1419,13 +1430,18 @@ int deflate_plan_run(b200z_plan *p, const uint8_t *d_in, uint8_t *d_out, int64_t
 			                                                   ws.at<int2>(p->o_tile_desc), ws.at<uint32_t>(p->o_rnd_off),
 			                                                   ws.at<RoundRec>(p->o_recs), hist, bias, lp, p->strategy);
 		if (p->n_tiles && p->tile_parse == 2)
-			k_tile_parse2<kFThreads><<<p->n_tiles, kFThreads, kFSmem, s>>>(d_in, link, mt, ws.at<uint32_t>(p->o_sym_local), in_off, in_len,
-			                                                               ws.at<int2>(p->o_tile_desc), ws.at<uint32_t>(p->o_rnd_off),
-			                                                               ws.at<RoundRec>(p->o_recs), hist, bias, sym, lp, p->strategy);
+			k_tile_parse2<kFThreads, false><<<p->n_tiles, kFThreads, kFSmem, s>>>(d_in, link, mt, ws.at<uint32_t>(p->o_sym_local), in_off, in_len,
+			                                                                      ws.at<int2>(p->o_tile_desc), ws.at<uint32_t>(p->o_rnd_off),
+			                                                                      ws.at<RoundRec>(p->o_recs), hist, bias, sym, lp, p->strategy, nullptr);
 		if (p->n_tiles && p->tile_parse == 3) // the same with 32 warps: the upper 16 only serve the batches
-			k_tile_parse2<1024><<<p->n_tiles, 1024, kFSmem, s>>>(d_in, link, mt, ws.at<uint32_t>(p->o_sym_local), in_off, in_len,
-			                                                     ws.at<int2>(p->o_tile_desc), ws.at<uint32_t>(p->o_rnd_off),
-			                                                     ws.at<RoundRec>(p->o_recs), hist, bias, sym, lp, p->strategy);
+			k_tile_parse2<1024, false><<<p->n_tiles, 1024, kFSmem, s>>>(d_in, link, mt, ws.at<uint32_t>(p->o_sym_local), in_off, in_len,
+			                                                            ws.at<int2>(p->o_tile_desc), ws.at<uint32_t>(p->o_rnd_off),
+			                                                            ws.at<RoundRec>(p->o_recs), hist, bias, sym, lp, p->strategy, nullptr);
+		if (p->n_tiles && p->tile_parse == 4) // 3 + the tile's entry from a 64-position warm-up, recorded for the fix-up
+			k_tile_parse2<1024, true><<<p->n_tiles, 1024, kFSmem, s>>>(d_in, link, mt, ws.at<uint32_t>(p->o_sym_local), in_off, in_len,
+			                                                           ws.at<int2>(p->o_tile_desc), ws.at<uint32_t>(p->o_rnd_off),
+			                                                           ws.at<RoundRec>(p->o_recs), hist, bias, sym, lp, p->strategy,
+			                                                           ws.at<RoundRec>(p->o_ent));
 		}
 		if (!do_encode) {
 			B200Z_CUDA(cudaGetLastError());
@@ -1445,7 +1461,8 @@ int deflate_plan_run(b200z_plan *p, const uint8_t *d_in, uint8_t *d_out, int64_t
 				                                      lp, p->strategy);
 			else
 				k_parse_fix_lazy<<<n, 32, kParseSmem, s>>>(d_in, link, mt, sym_local, in_off, in_len, rnd_off, recs, p->parse_chunk, hist,
-				                                           bias, lp, p->strategy);
+				                                           bias, lp, p->strategy,
+				                                           p->tile_parse == 4 ? ws.at<RoundRec>(p->o_ent) : (const RoundRec *)nullptr);
 			k_parse_scan<<<n, 256, 0, s>>>(d_in, in_off, in_len, rnd_off, recs, rnd_symoff, sym, nsyms, nblocks, blk_off, blk_start,
 			                               blk_ptop, hist, p->end_mode);
 			if (p->n_rgroups)

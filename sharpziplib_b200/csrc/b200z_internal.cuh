@@ -92,6 +92,7 @@ struct b200z_plan {
 	int64_t o_sym_local = 0, o_chunks = 0, o_rgroups = 0, o_rnd_off = 0, o_recs = 0, o_rnd_symoff = 0; // chunked parse
 	int n_chunks = 0, n_rgroups = 0;
 	uint32_t parse_chunk = 32768;
+	int64_t o_ent = 0; // B200Z_TILE_PARSE=4: entry state of every tile, for the fix-up
 	int link_run = 65536; // positions per k_links CTA (B200Z_LINK_RUN)
 	int tile_parse = 0; // experimental/k_tile_parse.cuh (1) / k_tile_parse2 (2) instead of k_match + k_parse_chunk
 	int fast_prev_entries = 32768; // k_fast's prev[] size for this batch

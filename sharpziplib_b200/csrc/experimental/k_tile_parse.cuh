@@ -29,7 +29,8 @@ constexpr int kFHist = 32768;                 // history staged in front of the 
 constexpr int kFData = kFHist + kFTile + 320; // bytes of window staged (tile + max match + pad), a multiple of 16
 constexpr uint32_t kFNone = 0xFFFFFFFFu;      // memo: position not searched yet
 constexpr uint32_t kFNeedB = 0x80000000u;     // memo: quarter-budget result differs from the full one, search again if asked
-constexpr int kFSmem = kFData + 2 * (kFHist + kFTile) + 4 * kFTile + kFThreads * 20 + 64;
+constexpr int kFWarm = 64;                    // k_tile_parse2<1024, true>: positions parsed in front of the tile for its entry state
+constexpr int kFSmem = kFData + 2 * (kFHist + kFTile) + 4 * kFTile + kFThreads * 20 + 64 + 4 * kFWarm + 32 + 64;
 static_assert(kFData % 16 == 0, "staging uses 16-byte copies");
 static_assert(kFSmem <= 227 * 1024, "one CTA per SM");
 
@@ -285,19 +286,28 @@ __device__ __forceinline__ void tile_walk(const uint8_t *s_data, const uint16_t 
 // barrier while the others parse; staging, the batch phase (classification, ordering, walks) and the table write-back run on
 // all 32 warps -- the walks are the bulk of the work and k_match needed its 32 warps per SM to hide the shared-memory hops
 // (64 registers at 1024 threads, no spills).
-template <int kThreads>
+// kWarm (1024 threads only): the tile's entry state is not the clean guess but what a parse of the kFWarm positions in front
+// of the tile ends in -- warp 16, idle while the others parse, searches those positions (two per lane, exact) and its lane 0
+// parses them; thread 0 takes the result like a hand-off from a segment -1.  tools/tile_fixup.cpp: the clean guess is wrong
+// at 92 % of the tile boundaries (one round parsed again by the fix-up each time), a 64-position warm-up leaves 0.2 %.  The
+// entry the tile finally used goes to `ent` (one record per round, only tile starts written) so that the fix-up compares the
+// true state with it instead of with the clean guess.
+template <int kThreads, bool kWarm>
 __global__ void __launch_bounds__(kThreads, 1)
     k_tile_parse2(const uint8_t *__restrict__ in, const uint16_t *__restrict__ link, uint2 *__restrict__ mt,
                   uint32_t *__restrict__ sym_local, const int64_t *__restrict__ in_off, const int64_t *__restrict__ in_len,
                   const int2 *__restrict__ tile_desc, const uint32_t *__restrict__ rnd_off, RoundRec *__restrict__ recs,
                   const uint32_t *__restrict__ hist, const int64_t *__restrict__ bias, uint32_t *__restrict__ scratch, LevelParams lp,
-                  int strategy) {
+                  int strategy, RoundRec *__restrict__ ent) {
+	static_assert(!kWarm || kThreads == 1024, "the warm-up runs on a warp that owns no segment");
 	extern __shared__ __align__(16) uint8_t smem[];
 	uint8_t *s_data = smem;
 	uint16_t *s_link = reinterpret_cast<uint16_t *>(smem + kFData);
 	uint32_t *s_memo = reinterpret_cast<uint32_t *>(smem + kFData + 2 * (kFHist + kFTile));
 	FCarry *s_exit = reinterpret_cast<FCarry *>(smem + kFData + 2 * (kFHist + kFTile) + 4 * kFTile);
 	__shared__ uint32_t s_nreq;
+	uint32_t *s_warm = reinterpret_cast<uint32_t *>(smem + kFSmem - 64 - 4 * kFWarm - 32); // kWarm: exact entries of the warm-up positions
+	FCarry *s_wexit = reinterpret_cast<FCarry *>(smem + kFSmem - 64 - 32);                // kWarm: where the warm-up parse ended
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const int2 td = tile_desc[blockIdx.x];
 	const uint32_t n = (uint32_t)in_len[td.x];
@@ -367,6 +377,38 @@ __global__ void __launch_bounds__(kThreads, 1)
 	ParseCarry entry = clean_carry(seg0 > H ? seg0 : H), ex = entry;
 	uint32_t cnt = 0;
 	bool dirty = owner;
+	// warm-up range [ws, t0): behind the history (the state at H is exactly clean) and only for tiles that start on a guess
+	const uint32_t ws = (!kWarm || t0 == 0 || t0 <= H) ? t0 : (t0 - H > (uint32_t)kFWarm ? t0 - kFWarm : H);
+	const bool has_warm = kWarm && ws < t0;
+	if (kWarm && has_warm && warp == kFThreads / 32) { // (warp-uniform) the first warp without segments
+		for (uint32_t p = ws + (uint32_t)lane; p < t0; p += 32) {
+			uint32_t a, b;
+			tile_walk(s_data, s_link, w0, p, n, lp, ab, a, b);
+			s_warm[p - ws] = a | (a != b ? kFNeedB : 0u);
+		}
+		__syncwarp();
+		if (lane == 0) {
+			auto tabw = [&](uint32_t p, uint32_t &a, uint32_t &b) {
+				const uint32_t m = s_warm[p - ws];
+				a = m & ~kFNeedB;
+				b = a;
+				if (m & kFNeedB) {
+					LevelParams lq = lp;
+					lq.chain = lp.chain >> 2;
+					uint32_t dummy;
+					match_search(s_data, s_link, w0, p, n, lq, b, dummy, ab);
+				}
+			};
+			ParseCarry c = clean_carry(ws);
+			while (c.st.p < t0) {
+				c.last_top = c.st.p;
+				uint32_t s2;
+				parse_step(c.st, n, lp, strategy, tabw, bytef, slowf, s2);
+			}
+			*s_wexit = f_pack(c);
+		}
+		__syncwarp();
+	}
 	for (int pass = 0; pass < 4 * kFThreads; pass++) {
 		// ---- parse: exact entries where there are, proxies elsewhere ----
 		if (dirty) {
@@ -441,11 +483,25 @@ __global__ void __launch_bounds__(kThreads, 1)
 			const ParseCarry ne = f_unpack(s_exit[tid - 1]);
 			changed = !carry_equal(ne, entry);
 			entry = ne;
+		} else if (kWarm && has_warm && tid == 0) { // (written before the first barrier of pass 0, never again)
+			const ParseCarry ne = f_unpack(*s_wexit);
+			changed = !carry_equal(ne, entry);
+			entry = ne;
 		}
 		dirty = changed || used_proxy;
 		if (!__syncthreads_or(dirty ? 1 : 0)) break;
 	}
 	// ---- final pass (every entry it reads is exact) and the table for the fix-up: as k_tile_parse ----
+	if (kWarm && tid == 0) { // the state this tile's records and symbols start from
+		RoundRec r;
+		r.p = entry.st.p;
+		r.mlen = entry.st.mlen;
+		r.mstart = entry.st.mstart;
+		r.prevAvail = entry.st.prevAvail;
+		r.last_top = entry.last_top;
+		r.cnt = has_warm ? 1u : 0u; // 0: the clean guess (compared without last_top, as the fix-up always did)
+		(ent + rnd_off[td.x])[t0 / kRound] = r;
+	}
 	const uint32_t rbase = t0 + (uint32_t)warp * kRound;
 	if (owner && rbase < n) {
 		uint32_t incl = cnt;

@@ -68,6 +68,8 @@ def rewrite(src):
                     break
             a1 += 1
         args = src[a0 + 1:a1]
+        if "," in name:  # template arguments: keep the macro from splitting them
+            name = "(" + name + ")"
         out += src[i:k] + "EMU_LAUNCH(%s, %s, %s, %s, %s)" % (name, cfg[0], cfg[1], cfg[2], args)
         i = a1 + 1
     out = re.sub(r"extern\s+__shared__\s+(?:__align__\(\d+\)\s+)?uint8_t\s+(\w+)\[\];", r"uint8_t *\1 = emu::dyn_smem();", out)

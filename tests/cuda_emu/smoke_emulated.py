@@ -28,7 +28,7 @@ for level in (6, 9, 1, 0):
 # the guessed tile entries and the lazy fix-up (k_parse_fix_lazy) all run
 tile_bufs = [datagen.silesia_mix(0, 40000).tobytes(), bufs[1], b"", bytes(5000)]
 tile_refs = [O.deflate(b, level=6) for b in tile_bufs]
-for variant in ("1", "2", "3"):
+for variant in ("1", "2", "3", "4"):
     os.environ["B200Z_TILE_PARSE"] = variant
     outs, _ = z.deflate_batch(tile_bufs, level=6)
     assert outs == tile_refs, "B200Z_TILE_PARSE=" + variant

@@ -1,4 +1,4 @@
-"""GPU tier: the opt-in search kernels of csrc/experimental/k_tile_parse.cuh (B200Z_TILE_PARSE=1|2|3) against the oracle.
+"""GPU tier: the opt-in search kernels of csrc/experimental/k_tile_parse.cuh (B200Z_TILE_PARSE=1|2|3|4) against the oracle.
 
 They replace k_match + k_parse_chunk when the environment asks for them; the default path does not change.  They were
 written after round 1's GPU minutes were spent and are bit-exact on the CUDA emulator (tests/cuda_emu) only, so their first
@@ -21,7 +21,7 @@ _hung = []  # variants whose check did not come back in time
 
 @pytest.mark.gpu
 @pytest.mark.xfail(strict=False, reason="experimental kernels that have never run on a GPU (emulator-checked only); opt-in, not the product path")
-@pytest.mark.parametrize("variant", ["3", "2", "1"])
+@pytest.mark.parametrize("variant", ["4", "3", "2", "1"])
 def test_tile_parse_variant_is_bit_exact(variant):
     if _hung:
         pytest.skip("an earlier variant hung; the variants share most of their code")
@@ -41,7 +41,7 @@ def test_tile_parse_variant_is_bit_exact(variant):
 
 
 def test_variant_switch_is_an_exact_match_on_the_environment():
-    """CPU tier: only "1", "2" and "3" select a variant (anything else is the default path), and bench.py labels its line."""
+    """CPU tier: only "1" .. "4" select a variant (anything else is the default path), and bench.py labels its line."""
     src = open(os.path.join(ROOT, "sharpziplib_b200", "csrc", "b200z_deflate.cu")).read()
-    assert 'getenv("B200Z_TILE_PARSE")' in src and "p->tile_parse < 1 || p->tile_parse > 3" in src
+    assert 'getenv("B200Z_TILE_PARSE")' in src and "p->tile_parse < 1 || p->tile_parse > 4" in src
     assert "search_variant" in open(os.path.join(ROOT, "bench.py")).read()

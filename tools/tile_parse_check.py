@@ -1,4 +1,4 @@
-"""Checks the opt-in search kernels (csrc/experimental/k_tile_parse.cuh, B200Z_TILE_PARSE=1|2|3) on cuda:0 against the oracle and
+"""Checks the opt-in search kernels (csrc/experimental/k_tile_parse.cuh, B200Z_TILE_PARSE=1|2|3|4) on cuda:0 against the oracle and
 times them next to the default path (k_match + k_parse_chunk).  Run in a process of its own: the kernels had never run on a
 GPU when this was written, and a faulting kernel takes the CUDA context of its process with it.
 
@@ -54,7 +54,7 @@ def per_kernel_ms(z, bufs, level, reps=3):
 def main():
     variant = sys.argv[1] if len(sys.argv) > 1 else "2"
     nbuf = int(sys.argv[2]) if len(sys.argv) > 2 else 64
-    assert variant in ("1", "2", "3")
+    assert variant in ("1", "2", "3", "4")
     import sharpziplib_b200 as z
     from sharpziplib_b200 import datagen
     import oracle_lib as O
