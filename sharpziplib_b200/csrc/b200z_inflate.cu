@@ -21,6 +21,9 @@
 //   4. the round's bytes are flushed from the ring to the output buffer with coalesced vector stores.
 // The ring starts zeroed: a distance reaching before the start of the stream reads zeros, which is what a fresh
 // reference window holds (trap T13: the reference does not check distances).
+#include <cstdlib>
+#include <cstring>
+
 #include "b200z_internal.cuh"
 
 namespace b200z {
@@ -331,13 +334,14 @@ __global__ void __launch_bounds__(kInfThreads)
               const int64_t *__restrict__ in_len, const int64_t *__restrict__ out_off, const int64_t *__restrict__ out_cap,
               int nstreams, int64_t *__restrict__ out_len, int64_t *__restrict__ in_used, int32_t *__restrict__ status,
               const uint32_t *__restrict__ dict_len, const uint32_t *__restrict__ start_bit, const int32_t *__restrict__ pre,
-              int64_t *__restrict__ restart) {
+              int64_t *__restrict__ restart, const int32_t *__restrict__ only) {
 	extern __shared__ __align__(16) uint8_t smem_raw[];
 	InfBlockShared &S = *reinterpret_cast<InfBlockShared *>(smem_raw);
 	const int lane = threadIdx.x & 31;
 	const bool isA = threadIdx.x < 32, isB1 = threadIdx.x >= 32 && threadIdx.x < 64;
 	const int stream = blockIdx.x;
 	if (stream >= nstreams) return;
+	if (only && !only[stream]) return; // behind the block-parallel pipeline: only the streams it handed back (k_chain)
 	if (pre && pre[stream] != B200Z_OK) { // the framing header was rejected (k_wrap_head): nothing to decode
 		if (threadIdx.x == 0) {
 			status[stream] = pre[stream];
@@ -868,6 +872,10 @@ __global__ void k_wrap_tail(const uint8_t *__restrict__ in, const int64_t *__res
 	in_used[i] = (int64_t)(used + want);
 }
 
+} // namespace b200z
+#include "b200z_inflate_par.cuh"
+namespace b200z {
+
 // ------------------------------------------------------------------------------------------------
 int inflate_plan_build(b200z_plan *p) {
 	const int n = p->n;
@@ -914,6 +922,67 @@ int inflate_plan_build(b200z_plan *p) {
 		p->o_ck_desc = ws.reserve((int64_t)sizeof(CkTile) * (ck_tiles.size() + 1));
 		p->o_ck_acc = ws.reserve(16ll * (n + 1));
 	}
+	// ---- block-parallel pipeline: candidate windows, finder tiles, pools (b200z_inflate_par.cuh) ----
+	{
+		const char *mode = getenv("B200Z_INFLATE");
+		p->inf_parallel = !(mode && strcmp(mode, "serial") == 0);
+	}
+	std::vector<uint32_t> win_base(n + 1, 0u), win_stream, match_cap(n, 0u);
+	std::vector<FTile> ftiles;
+	std::vector<int64_t> mt_off(n, 0);
+	if (p->inf_parallel && n) {
+		uint64_t nwin = 0, rounds = 0, bits = 0, mt = 0;
+		for (int i = 0; i < n; i++) {
+			const uint64_t len = (uint64_t)dev_len[i];
+			win_base[i] = (uint32_t)nwin;
+			const uint64_t w = len ? (len * 8 + kFWMask) >> kFWShift : 1;
+			for (uint64_t k = 0; k < w; k++) win_stream.push_back((uint32_t)i);
+			nwin += w;
+			bits += len * 8;
+			rounds += 4 * ((len * 8 + (uint64_t)kP1Threads * kSubBits - 1) / ((uint64_t)kP1Threads * kSubBits)) + 16;
+			const uint32_t nw = (uint32_t)((len + 3) >> 2);
+			for (uint32_t w0 = 0; w0 < nw; w0 += kFindTileWords) {
+				FTile t;
+				t.stream = (uint32_t)i;
+				t.word0 = w0;
+				t.nwords = nw - w0 < (uint32_t)kFindTileWords ? nw - w0 : (uint32_t)kFindTileWords;
+				t.pad = 0;
+				ftiles.push_back(t);
+			}
+			// a back-reference takes at least two bits of input and produces at least three bytes
+			uint64_t mc = (uint64_t)p->out_cap[i] / 3 + 2;
+			if (mc > 4 * len + 2) mc = 4 * len + 2;
+			if (mc > 0x7FFFFFFFull) mc = 0x7FFFFFFFull;
+			match_cap[i] = (uint32_t)mc;
+			mt_off[i] = (int64_t)mt;
+			mt += mc;
+		}
+		win_base[n] = (uint32_t)nwin;
+		if (nwin + (uint64_t)n > 0x7FFFFFF0ull || rounds > 0x7FFFFFF0ull) {
+			p->inf_parallel = false; // (beyond the 32-bit slot numbers: the serial kernel takes the plan)
+		} else {
+			p->nwin_total = (uint32_t)nwin;
+			p->n_ftiles = (uint32_t)ftiles.size();
+			p->fs_cap = (uint32_t)(bits / 256 + 1024 > 0x7FFFFFFFull ? 0x7FFFFFFFull : bits / 256 + 1024);
+			p->round_cap = (uint32_t)((rounds + kRoundBatch - 1) / kRoundBatch * kRoundBatch);
+			p->hdr_cap = p->round_cap / kRoundBatch;
+			p->o_win_base = ws.reserve(4ll * (n + 1));
+			p->o_win_stream = ws.reserve(4ll * (int64_t)nwin);
+			p->o_cand = ws.reserve(4ll * (int64_t)nwin);
+			p->o_ftiles = ws.reserve((int64_t)sizeof(FTile) * (int64_t)(ftiles.size() + 1));
+			p->o_fs_list = ws.reserve(8ll * p->fs_cap);
+			p->o_ctr = ws.reserve((int64_t)sizeof(PCounters));
+			p->o_segs = ws.reserve((int64_t)sizeof(PSeg) * (int64_t)(nwin + n));
+			p->o_seg_list = ws.reserve(4ll * (int64_t)(nwin + n));
+			p->o_rounds = ws.reserve((int64_t)sizeof(PRound) * p->round_cap);
+			p->o_hdrs = ws.reserve((int64_t)sizeof(PBlockHdr) * p->hdr_cap);
+			p->o_mlist = ws.reserve((int64_t)sizeof(MatchTok) * (int64_t)mt);
+			p->o_mt_off = ws.reserve(8ll * (n + 1));
+			p->o_match_cap = ws.reserve(4ll * (n + 1));
+			p->o_str_nm = ws.reserve(4ll * (n + 1));
+			p->o_fallback = ws.reserve(4ll * (n + 1));
+		}
+	}
 	int rc = ws.alloc();
 	if (rc) return rc;
 	if (n) {
@@ -924,9 +993,33 @@ int inflate_plan_build(b200z_plan *p) {
 			B200Z_CUDA(cudaMemcpy(ws.at<CkTile>(p->o_ck_desc), ck_tiles.data(), sizeof(CkTile) * ck_tiles.size(), cudaMemcpyHostToDevice));
 		B200Z_CUDA(cudaMemcpy(ws.at<int64_t>(p->o_out_off), p->out_off.data(), 8ll * n, cudaMemcpyHostToDevice));
 		B200Z_CUDA(cudaMemcpy(ws.at<int64_t>(p->o_out_cap), p->out_cap.data(), 8ll * n, cudaMemcpyHostToDevice));
+		if (p->inf_parallel) {
+			B200Z_CUDA(cudaMemcpy(ws.at<uint32_t>(p->o_win_base), win_base.data(), 4ll * (n + 1), cudaMemcpyHostToDevice));
+			B200Z_CUDA(cudaMemcpy(ws.at<uint32_t>(p->o_win_stream), win_stream.data(), 4ll * win_stream.size(), cudaMemcpyHostToDevice));
+			if (!ftiles.empty())
+				B200Z_CUDA(cudaMemcpy(ws.at<FTile>(p->o_ftiles), ftiles.data(), sizeof(FTile) * ftiles.size(), cudaMemcpyHostToDevice));
+			B200Z_CUDA(cudaMemcpy(ws.at<int64_t>(p->o_mt_off), mt_off.data(), 8ll * n, cudaMemcpyHostToDevice));
+			B200Z_CUDA(cudaMemcpy(ws.at<uint32_t>(p->o_match_cap), match_cap.data(), 4ll * n, cudaMemcpyHostToDevice));
+		}
 	}
 	B200Z_CUDA(cudaFuncSetAttribute(k_inflate, cudaFuncAttributeMaxDynamicSharedMemorySize, kInfSmem2));
-	p->launches = p->wrap == B200Z_WRAP_RAW ? 1 : (p->wrap == B200Z_WRAP_RAW_CRC32 ? 4 : 6);
+	int extra = 0;
+	if (p->inf_parallel && n) {
+		B200Z_CUDA(cudaFuncSetAttribute(k_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ResShared)));
+		int dev = 0, sms = 1, occ1 = 1, occ2 = 1;
+		B200Z_CUDA(cudaGetDevice(&dev));
+		B200Z_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+		B200Z_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ1, k_dec1, kP1Threads, sizeof(Dec1Shared)));
+		B200Z_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, k_dec2, kP1Threads, sizeof(Dec2Shared)));
+		if (occ1 < 1) occ1 = 1;
+		if (occ2 < 1) occ2 = 1;
+		const int64_t slots = (int64_t)p->nwin_total + n, batches = p->round_cap / kRoundBatch;
+		p->dec1_grid = (int)(slots < (int64_t)sms * occ1 ? slots : (int64_t)sms * occ1);
+		p->dec2_grid = (int)(batches < (int64_t)sms * occ2 ? batches : (int64_t)sms * occ2);
+		p->find3_grid = sms * 4;
+		extra = 7; // k_find, k_find3, k_seglist, k_dec1, k_chain, k_dec2, k_resolve (+ k_inflate for what they hand back)
+	}
+	p->launches = extra + (p->wrap == B200Z_WRAP_RAW ? 1 : (p->wrap == B200Z_WRAP_RAW_CRC32 ? 4 : 6));
 	return B200Z_OK;
 }
 
@@ -949,10 +1042,48 @@ int inflate_plan_run(b200z_plan *p, const uint8_t *d_in, uint8_t *d_out, int64_t
 		p->mark(s, "k_wrap");
 		k_wrap_head<<<(n + 127) / 128, 128, 0, s>>>(d_in, in_off, in_len, ws.at<uint32_t>(p->o_hist), n, wrap, start_bit, pre);
 	}
+	const uint32_t *dict_len = ws.at<uint32_t>(p->o_hist);
+	const int64_t *out_off = ws.at<int64_t>(p->o_out_off), *out_cap = ws.at<int64_t>(p->o_out_cap);
+	int64_t *restart = ws.at<int64_t>(p->o_restart);
+	const int32_t *only = nullptr;
+	if (p->inf_parallel) {
+		PCounters *ctr = ws.at<PCounters>(p->o_ctr);
+		uint32_t *cand = ws.at<uint32_t>(p->o_cand);
+		const uint32_t *win_base = ws.at<uint32_t>(p->o_win_base);
+		PSeg *segs = ws.at<PSeg>(p->o_segs);
+		uint32_t *seg_list = ws.at<uint32_t>(p->o_seg_list);
+		PRound *rounds = ws.at<PRound>(p->o_rounds);
+		PBlockHdr *hdrs = ws.at<PBlockHdr>(p->o_hdrs);
+		MatchTok *mlist = ws.at<MatchTok>(p->o_mlist);
+		const int64_t *mt_off = ws.at<int64_t>(p->o_mt_off);
+		uint32_t *str_nm = ws.at<uint32_t>(p->o_str_nm);
+		int32_t *fallback = ws.at<int32_t>(p->o_fallback);
+		unsigned long long *fs_list = ws.at<unsigned long long>(p->o_fs_list);
+		p->mark(s, "k_find");
+		B200Z_CUDA(cudaMemsetAsync(ctr, 0, sizeof(PCounters), s));
+		B200Z_CUDA(cudaMemsetAsync(cand, 0xFF, 4ull * p->nwin_total, s));
+		if (p->n_ftiles)
+			k_find<<<p->n_ftiles, 256, 0, s>>>(d_in, in_off, in_len, ws.at<FTile>(p->o_ftiles), start_bit, pre, fs_list, ctr, p->fs_cap);
+		k_find3<<<p->find3_grid, 128, 0, s>>>(d_in, in_off, in_len, fs_list, ctr, p->fs_cap, win_base, cand);
+		const uint32_t slots = p->nwin_total + (uint32_t)n;
+		k_seglist<<<(slots + 255) / 256, 256, 0, s>>>(n, p->nwin_total, win_base, ws.at<uint32_t>(p->o_win_stream), cand, start_bit, pre, segs,
+		                                            seg_list, ctr);
+		p->mark(s, "k_dec1");
+		k_dec1<<<p->dec1_grid, kP1Threads, sizeof(Dec1Shared), s>>>(d_in, in_off, in_len, segs, seg_list, ctr, win_base, cand, rounds,
+		                                                             p->round_cap, hdrs, p->hdr_cap);
+		p->mark(s, "k_chain");
+		k_chain<<<(n + 127) / 128, 128, 0, s>>>(n, segs, win_base, in_len, out_cap, ws.at<uint32_t>(p->o_match_cap), pre, d_out_len, d_in_used,
+		                                        d_status, restart, str_nm, fallback);
+		p->mark(s, "k_dec2");
+		k_dec2<<<p->dec2_grid, kP1Threads, sizeof(Dec2Shared), s>>>(d_in, d_out, in_off, in_len, out_off, segs, ctr, rounds, p->round_cap, hdrs,
+		                                                             mlist, mt_off);
+		p->mark(s, "k_resolve");
+		k_resolve<<<n, kResThreads, sizeof(ResShared), s>>>(d_in, d_out, in_off, out_off, dict_len, d_out_len, str_nm, fallback, mlist, mt_off, n);
+		only = fallback;
+	}
 	p->mark(s, "k_inflate");
-	k_inflate<<<n, kInfThreads, kInfSmem2, s>>>(d_in, d_out, in_off, in_len, ws.at<int64_t>(p->o_out_off), ws.at<int64_t>(p->o_out_cap),
-	                                           n, d_out_len, d_in_used, d_status, ws.at<uint32_t>(p->o_hist), start_bit, pre,
-	                                           ws.at<int64_t>(p->o_restart));
+	k_inflate<<<n, kInfThreads, kInfSmem2, s>>>(d_in, d_out, in_off, in_len, out_off, out_cap, n, d_out_len, d_in_used, d_status, dict_len,
+	                                           start_bit, pre, restart, only);
 	if (wrap != B200Z_WRAP_RAW) {
 		p->mark(s, "checksum");
 		int rc = checksum_launch(wrap == B200Z_WRAP_ZLIB ? 1 : 0, d_out, ws.at<int64_t>(p->o_out_off), d_out_len, n,

@@ -110,6 +110,12 @@ struct b200z_plan {
 	int64_t o_start_bit = 0, o_pre = 0; // inflate framing: first deflate bit and header verdict per stream
 	int64_t o_restart = 0;              // inflate: per stream (bit, output position) of the last block header reached
 	bool has_start_bits = false;        // raw inflate plans: caller-supplied first bit (b200z_inflate_plan_set_start_bits)
+	// inflate, block-parallel pipeline (b200z_inflate_par.cuh)
+	bool inf_parallel = true;           // false: the serial kernel only (B200Z_INFLATE=serial)
+	int64_t o_win_base = 0, o_win_stream = 0, o_cand = 0, o_ftiles = 0, o_fs_list = 0, o_ctr = 0, o_segs = 0, o_seg_list = 0;
+	int64_t o_rounds = 0, o_hdrs = 0, o_mlist = 0, o_mt_off = 0, o_match_cap = 0, o_str_nm = 0, o_fallback = 0;
+	uint32_t nwin_total = 0, n_ftiles = 0, fs_cap = 0, round_cap = 0, hdr_cap = 0;
+	int dec1_grid = 0, dec2_grid = 0, find3_grid = 0;
 	// checksum scratch
 	int64_t o_ck_desc = 0, o_ck_acc = 0;
 	int n_ck_tiles = 0;

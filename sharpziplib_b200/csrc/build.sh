@@ -3,13 +3,23 @@
 set -e
 cd "$(dirname "$0")"
 NVCC=${NVCC:-nvcc}
-FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xcompiler -Wall"
+FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xcompiler -Wall -diag-suppress 550"
 mkdir -p _build
+pids=()
 for f in b200z_deflate b200z_inflate b200z_checksum b200z_api; do
-  if [ ! -f _build/$f.o ] || [ $f.cu -nt _build/$f.o ] || [ b200z_core.cuh -nt _build/$f.o ] || [ b200z_internal.cuh -nt _build/$f.o ] || [ b200z_crc.cuh -nt _build/$f.o ] || [ experimental/k_tile_parse.cuh -nt _build/$f.o ] || [ ../../include/b200z.h -nt _build/$f.o ]; then
+  stale=0
+  [ -f _build/$f.o ] || stale=1
+  for dep in $f.cu *.cuh ../../include/b200z.h build.sh; do
+    [ $stale -eq 0 ] && [ $dep -nt _build/$f.o ] && stale=1
+  done
+  if [ $stale -eq 1 ]; then
+    rm -f _build/$f.o # a failed compile must not leave an older object for the link step
     $NVCC $FLAGS -c $f.cu -o _build/$f.o &
+    pids+=($!)
   fi
 done
-wait
+for pid in "${pids[@]}"; do
+  wait "$pid" || { echo "build.sh: a compile failed" >&2; exit 1; }
+done
 $NVCC -gencode arch=compute_100a,code=sm_100a -shared -o ../libb200z.so _build/b200z_deflate.o _build/b200z_inflate.o _build/b200z_checksum.o _build/b200z_api.o
 echo built ../libb200z.so

@@ -94,6 +94,12 @@ def build(sanitize=False, verbose=False):
         # headers are found next to the original sources
         open(dst, "w").write('#line 1 "%s"\n' % os.path.join(CSRC, f) + rewrite(text))
         gen.append(dst)
+    # headers with kernels of their own (dynamic shared memory declarations, launches): rewritten next to the sources
+    for f in os.listdir(CSRC):
+        if f.endswith(".cuh"):
+            text = open(os.path.join(CSRC, f)).read()
+            if "extern __shared__" in text or "<<<" in text:
+                open(os.path.join(OUT, "src", f), "w").write('#line 1 "%s"\n' % os.path.join(CSRC, f) + rewrite(text))
     # headers that declare dynamic shared memory themselves (experimental kernels #included by a patched source)
     exp = os.path.join(CSRC, "experimental")
     if os.path.isdir(exp):

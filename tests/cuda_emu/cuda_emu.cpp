@@ -97,6 +97,9 @@ void launch(dim3 grid, dim3 block, size_t smem_bytes, std::function<void()> body
 				b.arrived = 0;
 				b.gen = 0;
 				b.or_acc = 0;
+				b.or_reset_gen = 0xFFFFFFFFu;
+				b.cnt_acc = 0;
+				b.cnt_reset_gen = 0xFFFFFFFFu;
 				g_block = &b;
 				for (int t = 0; t < nt; t++) {
 					Fiber &f = b.fibers[(size_t)t];

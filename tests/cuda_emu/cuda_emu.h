@@ -64,6 +64,8 @@ struct Block {
 	uint32_t gen = 0;
 	int or_acc = 0;
 	uint32_t or_reset_gen = 0xFFFFFFFFu;
+	int cnt_acc = 0;
+	uint32_t cnt_reset_gen = 0xFFFFFFFFu;
 	dim3 bid, bdim, gdim;
 	uint8_t *smem = nullptr;
 	ucontext_t sched;
@@ -129,6 +131,18 @@ static inline int __syncthreads_or(int pred) {
 	if (b.or_reset_gen != b.gen) { // the first thread to get here clears the accumulator for the next use
 		b.or_acc = 0;
 		b.or_reset_gen = b.gen;
+	}
+	return r;
+}
+static inline int __syncthreads_count(int pred) {
+	emu::Block &b = *emu::g_block;
+	b.cnt_acc += pred ? 1 : 0;
+	emu::block_barrier();
+	const int r = b.cnt_acc; // everybody has contributed
+	emu::block_barrier();    // everybody has read
+	if (b.cnt_reset_gen != b.gen) {
+		b.cnt_acc = 0;
+		b.cnt_reset_gen = b.gen;
 	}
 	return r;
 }
@@ -212,6 +226,8 @@ static inline uint32_t __brev(uint32_t x) {
 }
 template <class T> static inline T atomicAdd(T *p, T v) { T o = *p; *p = (T)(o + v); return o; }
 template <class T> static inline T atomicOr(T *p, T v) { T o = *p; *p = (T)(o | v); return o; }
+template <class T> static inline T atomicMin(T *p, T v) { T o = *p; if (v < o) *p = v; return o; }
+template <class T> static inline T atomicMax(T *p, T v) { T o = *p; if (v > o) *p = v; return o; }
 template <class T> static inline T atomicXor(T *p, T v) { T o = *p; *p = (T)(o ^ v); return o; }
 static inline void __pipeline_memcpy_async(void *dst, const void *src, size_t n) { memcpy(dst, src, n); }
 static inline void __pipeline_commit() {}
@@ -250,6 +266,9 @@ static inline cudaError_t cudaEventDestroy(cudaEvent_t) { return cudaSuccess; }
 static inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t = nullptr) { return cudaSuccess; }
 static inline cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t, cudaEvent_t) { *ms = 0.f; return cudaSuccess; }
 template <class F> static inline cudaError_t cudaFuncSetAttribute(F, int, int) { return cudaSuccess; }
+enum { cudaDevAttrMultiProcessorCount = 16 };
+static inline cudaError_t cudaDeviceGetAttribute(int *v, int, int) { *v = 2; return cudaSuccess; } // "two SMs"
+template <class F> static inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int *n, F, int, size_t) { *n = 2; return cudaSuccess; }
 #define cudaMemcpyToSymbol(sym, src, n, ...) (memcpy((void *)&(sym), (src), (n)), cudaSuccess)
 
 // kernel<<<grid, block, smem, stream>>>(args...) is rewritten by build_emu.py into this
