@@ -40,7 +40,8 @@ enum {
 
 const char *b200z_last_error(void);
 int b200z_version(void);
-/* Selects the CUDA device for the calling process (one process per GPU) and creates the library context.
+/* Selects the CUDA device the calling thread creates plans, pipelines and handles on (one process per GPU: call it once;
+ * one process for several GPUs: see "one host process, several GPUs" below) and loads the device's constant tables.
  * Idempotent.  Mirrors nothing in the reference: the reference has no device. */
 int b200z_init(int device);
 /* Static Huffman tables (DeflaterHuffman static ctor :602-642 and InflaterHuffmanTree static ctor :34-70) as one
@@ -140,7 +141,17 @@ int b200z_inflate_plan_create_ex(int32_t n, const int64_t *comp_len, const int64
  * byte of the slot) and out_pos[i] (bytes of output in front of it).  A stream that ended with B200Z_E_NEED_INPUT is
  * continued from there once more input has arrived.  Host arrays of n entries; get_restart_points synchronises the stream. */
 int b200z_inflate_plan_set_start_bits(b200z_plan *plan, const int32_t *start_bit);
+/* Runs an inflate plan below the sizes it was created for: stream i's next run has comp_len[i] compressed bytes behind a
+ * dictionary / window image of dict_len[i] bytes (NULL = none), each at most what b200z_inflate_plan_create_ex was given.
+ * The dictionary still ends where the compressed bytes start: b200z_plan_in_offset(i) moves accordingly,
+ * b200z_plan_data_offset(i) stays.  This is how the Inflater handle keeps ONE plan between SetInput calls. */
+int b200z_inflate_plan_set_lengths(b200z_plan *plan, const int64_t *comp_len, const int64_t *dict_len);
 int b200z_plan_get_restart_points(b200z_plan *plan, int64_t *bit, int64_t *out_pos, void *cuda_stream);
+/* Diagnostics of the last run of an inflate plan (synchronises `stream`): v[0] positions that passed the finder's first
+ * two stages, v[1] segments decoded (stream starts + block-header candidates), v[2] round slots taken, v[3] Huffman blocks
+ * decoded, v[4] rounds, v[5] speculative passes over them, v[6] streams handed back to the serial kernel, v[7] 1 if the
+ * plan runs the block-parallel pipeline.  Mirrors nothing in the reference. */
+int b200z_plan_get_stats(b200z_plan *plan, uint32_t *v, int32_t cap, void *cuda_stream);
 int b200z_plan_destroy(b200z_plan *plan);
 int64_t b200z_plan_in_bytes(const b200z_plan *plan);          /* size of the input blob  */
 int64_t b200z_plan_out_bytes(const b200z_plan *plan);         /* size of the output blob */
@@ -177,13 +188,57 @@ int b200z_plan_run_stages(b200z_plan *plan, const uint8_t *d_in, uint8_t *d_out,
 int b200z_plan_pack(b200z_plan *plan, const uint8_t *d_out, const int64_t *d_out_len, uint8_t *d_packed,
                     int64_t *d_packed_off, void *cuda_stream);
 
-/* Host-buffer batch calls: the end-to-end path (pinned staging, H2D, kernels, D2H inside the call).
- * in[i]/out[i] are HOST pointers; status[i] is per stream.  The return value is the first non-OK status, if any. */
+/* ---------------------------------------------------------------------------------------------------------------
+ * Host-buffer pipelines -- the end-to-end path a host process drives (what DeflaterOutputStream / InflaterInputStream
+ * callers with many independent buffers amount to: ZipOutputStream entries, Streams/DeflaterOutputStream.cs:245-275).
+ * A pipeline owns the plan of one batch shape, `depth` (1..8) slots of pinned staging + device buffers and its own CUDA
+ * streams.  submit() takes HOST pointers (in[i]: stream i's bytes, the sizes given at creation), stages them and enqueues
+ * upload and kernels without waiting; collect() waits for the oldest submitted batch, moves exactly the produced bytes
+ * across PCIe and into out[i] (HOST pointers), and reports per stream what the batch calls below report.  With
+ * depth >= 2, submit(i+1) before collect(i) overlaps the upload of batch i+1 and the download of batch i-1 with the
+ * kernels of batch i.  Host memory CUDA knows as pinned (cudaHostAlloc / cudaHostRegister) is the DMA source / target
+ * directly; pageable memory goes through the slot's pinned staging.  wrap = B200Z_WRAP_GZIP on the deflate side writes
+ * GZipOutputStream's bytes with MTIME = 0 and no FNAME (GZip/GzipOutputStream.cs:315-375: 1F 8B 08 00 00000000 00 FF,
+ * raw stream, CRC32, ISIZE); a caller with its own MTIME / FNAME patches bytes 4..7 or uses B200Z_WRAP_RAW_CRC32.
+ * One pipeline = one host thread at a time.  E_STATE: submit with `depth` batches in flight, collect with none.
+ * ------------------------------------------------------------------------------------------------------------- */
+typedef struct b200z_pipeline b200z_pipeline;
+int b200z_deflate_pipeline_create(int32_t n, const int64_t *in_len, int level, int strategy, int wrap, int end_mode, int depth,
+                                  b200z_pipeline **pipe);
+int b200z_inflate_pipeline_create(int32_t n, const int64_t *comp_len, const int64_t *out_cap, int wrap, int depth,
+                                  b200z_pipeline **pipe);
+int b200z_pipeline_submit(b200z_pipeline *pipe, const uint8_t *const *in);
+int b200z_pipeline_collect(b200z_pipeline *pipe, uint8_t *const *out, const int64_t *out_cap, int64_t *out_len, int64_t *in_used,
+                           uint32_t *check, int32_t *status);
+int32_t b200z_pipeline_in_flight(const b200z_pipeline *pipe); /* batches submitted and not yet collected */
+int b200z_pipeline_destroy(b200z_pipeline *pipe);
+
+/* Host-buffer batch calls: one submit + collect on a pipeline of depth 1 that the calling thread keeps for the batch's
+ * shape (the last four shapes stay cached: plan, pinned staging and device buffers are not allocated again; 
+ * b200z_release_cached() frees them).  in[i]/out[i] are HOST pointers; status[i] is per stream.  The return value is the
+ * first non-OK status, if any. */
 int b200z_deflate_batch(const uint8_t *const *in, const int64_t *in_len, int32_t n, int level, int strategy, int wrap,
                         int end_mode, uint8_t *const *out, const int64_t *out_cap, int64_t *out_len, uint32_t *check,
                         int32_t *status);
 int b200z_inflate_batch(const uint8_t *const *in, const int64_t *in_len, int32_t n, int wrap, uint8_t *const *out,
                         const int64_t *out_cap, int64_t *out_len, int64_t *in_used, uint32_t *check, int32_t *status);
+int b200z_release_cached(void);
+
+/* ---- one host process, several GPUs ------------------------------------------------------------------------------
+ * b200z_init(device) may be called for several devices: it makes `device` the one the CALLING THREAD creates plans,
+ * pipelines and handles on.  Every such object stays on its device; its entry points run there whatever the thread's
+ * current device is and leave that as they found it.  The _multi batch calls cut a batch into contiguous ranges of about
+ * equal bytes (b200z_partition_by_bytes: part r starts at first[r], first[parts] = n), run range r on devices[r] -- all
+ * devices at the same time, every submit before the first collect -- and fill the caller's arrays as the single-device
+ * calls do.  The streams of a batch are independent, so there is no device-to-device traffic. */
+int b200z_device_count(void);
+int b200z_partition_by_bytes(const int64_t *len, int32_t n, int32_t parts, int32_t *first);
+int b200z_deflate_batch_multi(const int32_t *devices, int32_t n_devices, const uint8_t *const *in, const int64_t *in_len, int32_t n,
+                              int level, int strategy, int wrap, int end_mode, uint8_t *const *out, const int64_t *out_cap,
+                              int64_t *out_len, uint32_t *check, int32_t *status);
+int b200z_inflate_batch_multi(const int32_t *devices, int32_t n_devices, const uint8_t *const *in, const int64_t *in_len, int32_t n,
+                              int wrap, uint8_t *const *out, const int64_t *out_cap, int64_t *out_len, int64_t *in_used,
+                              uint32_t *check, int32_t *status);
 /* worst-case compressed size for `len` input bytes at any level (capacity a caller should provide) */
 int64_t b200z_deflate_bound(int64_t len);
 

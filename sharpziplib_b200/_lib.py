@@ -76,6 +76,8 @@ _SIGS = {
     "b200z_inflate_plan_create_ex": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]),
     "b200z_inflate_plan_set_start_bits": (C.c_int, [C.c_void_p, C.c_void_p]),
     "b200z_plan_get_restart_points": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "b200z_inflate_plan_set_lengths": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "b200z_plan_get_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "b200z_plan_data_offset": (C.c_int64, [C.c_void_p, C.c_int32]),
     "b200z_plan_destroy": (C.c_int, [C.c_void_p]),
     "b200z_plan_in_bytes": (C.c_int64, [C.c_void_p]),
@@ -93,6 +95,17 @@ _SIGS = {
                                         C.c_void_p]),
     "b200z_deflate_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "b200z_inflate_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "b200z_release_cached": (C.c_int, []),
+    "b200z_device_count": (C.c_int, []),
+    "b200z_partition_by_bytes": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
+    "b200z_deflate_batch_multi": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "b200z_inflate_batch_multi": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "b200z_deflate_pipeline_create": (C.c_int, [C.c_int32, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "b200z_inflate_pipeline_create": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "b200z_pipeline_submit": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "b200z_pipeline_collect": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "b200z_pipeline_in_flight": (C.c_int32, [C.c_void_p]),
+    "b200z_pipeline_destroy": (C.c_int, [C.c_void_p]),
     "b200z_deflate_bound": (C.c_int64, [C.c_int64]),
     "b200z_engine_state_bytes": (C.c_int64, []),
     "b200z_deflater_create": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_void_p)]),

@@ -123,6 +123,16 @@ class InflatePlan(_Plan):
         assert sb.size == self.n
         _lib.raise_for(_lib.lib().b200z_inflate_plan_set_start_bits(self._h, sb.ctypes.data))
 
+    def stats(self, stream=None):
+        """diagnostics of the last run (b200z_plan_get_stats): finder survivors, segments, round slots, blocks, rounds, passes,
+        streams handed back to the serial kernel, pipeline in use"""
+        import torch
+        s = stream if stream is not None else torch.cuda.current_stream()
+        v = np.zeros(8, dtype=np.uint32)
+        _lib.raise_for(_lib.lib().b200z_plan_get_stats(self._h, v.ctypes.data, 8, s.cuda_stream))
+        names = ("finder_survivors", "segments", "round_slots", "blocks", "rounds", "passes", "handed_back", "parallel")
+        return dict(zip(names, (int(x) for x in v)))
+
     def restart_points(self, stream=None):
         """(bit, out_pos) int64 arrays of the last run: where the last block header each stream's decoder reached lies
         (bits from the first compressed byte of the slot; output bytes in front of it).  Synchronises the stream."""
@@ -134,13 +144,70 @@ class InflatePlan(_Plan):
         return bit, pos
 
 
+class Pipeline:
+    """Host-buffer pipeline (b200z_*_pipeline_*): submit() stages one batch from host memory and enqueues upload and kernels
+    without waiting, collect() waits for the oldest batch and hands the produced bytes to host memory.  `ins` / `outs` are
+    sequences of integer host addresses (ctypes / numpy / torch data pointers), one per stream."""
+
+    def __init__(self, handle, n, depth):
+        self._h, self.n, self.depth = handle, n, depth
+        self.out_len = np.zeros(n, dtype=np.int64)
+        self.in_used = np.zeros(n, dtype=np.int64)
+        self.check = np.zeros(n, dtype=np.uint32)
+        self.status = np.zeros(n, dtype=np.int32)
+
+    @classmethod
+    def deflate(cls, in_lens, level=6, strategy=0, wrap=_lib.WRAP_RAW, end_mode=_lib.END_FINISH, depth=2):
+        lens = np.ascontiguousarray(in_lens, dtype=np.int64)
+        h = C.c_void_p()
+        _lib.raise_for(_lib.lib().b200z_deflate_pipeline_create(lens.size, lens.ctypes.data, level, strategy, wrap, end_mode, depth, C.byref(h)))
+        return cls(h, lens.size, depth)
+
+    @classmethod
+    def inflate(cls, comp_lens, out_caps, wrap=_lib.WRAP_RAW, depth=2):
+        cl = np.ascontiguousarray(comp_lens, dtype=np.int64)
+        oc = np.ascontiguousarray(out_caps, dtype=np.int64)
+        h = C.c_void_p()
+        _lib.raise_for(_lib.lib().b200z_inflate_pipeline_create(cl.size, cl.ctypes.data, oc.ctypes.data, wrap, depth, C.byref(h)))
+        return cls(h, cl.size, depth)
+
+    @staticmethod
+    def pointers(addresses):
+        return (C.c_void_p * len(addresses))(*[int(a) if a else None for a in addresses])
+
+    def submit(self, in_ptrs):
+        _lib.raise_for(_lib.lib().b200z_pipeline_submit(self._h, in_ptrs))
+
+    def collect(self, out_ptrs, out_caps, raise_on_error=True):
+        rc = _lib.lib().b200z_pipeline_collect(self._h, out_ptrs, out_caps.ctypes.data, self.out_len.ctypes.data, self.in_used.ctypes.data,
+                                              self.check.ctypes.data, self.status.ctypes.data)
+        if raise_on_error or rc in (_lib.E_CUDA, _lib.E_ARG, _lib.E_STATE):
+            _lib.raise_for(rc)
+        return rc
+
+    @property
+    def in_flight(self):
+        return int(_lib.lib().b200z_pipeline_in_flight(self._h))
+
+    def close(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            try:
+                _lib.lib().b200z_pipeline_destroy(h)
+            except Exception:
+                pass
+
+    __del__ = close
+
+
 def _ptr_array(arrs):
     return (C.c_void_p * len(arrs))(*[a.ctypes.data if a.size else None for a in arrs])
 
 
-def deflate_batch(buffers, level=6, strategy=0, wrap=_lib.WRAP_RAW, end_mode=_lib.END_FINISH):
+def deflate_batch(buffers, level=6, strategy=0, wrap=_lib.WRAP_RAW, end_mode=_lib.END_FINISH, devices=None):
     """Host buffers in, list of compressed bytes out (b200z_deflate_batch: H2D, kernels, D2H inside the call).
-    Returns (outputs, checks)."""
+    devices: a list of CUDA device indices -- the batch is cut by bytes and every range runs on its own GPU at the same
+    time (b200z_deflate_batch_multi, one host process for several GPUs).  Returns (outputs, checks)."""
     n = len(buffers)
     ins = [np.ascontiguousarray(np.frombuffer(b, dtype=np.uint8)) for b in buffers]
     lens = np.array([a.size for a in ins], dtype=np.int64)
@@ -149,14 +216,20 @@ def deflate_batch(buffers, level=6, strategy=0, wrap=_lib.WRAP_RAW, end_mode=_li
     out_len = np.zeros(n, dtype=np.int64)
     check = np.zeros(n, dtype=np.uint32)
     status = np.zeros(n, dtype=np.int32)
-    rc = _lib.lib().b200z_deflate_batch(_ptr_array(ins), lens.ctypes.data, n, level, strategy, wrap, end_mode,
-                                        _ptr_array(outs), caps.ctypes.data, out_len.ctypes.data, check.ctypes.data,
-                                        status.ctypes.data)
+    if devices is not None:
+        dv = np.ascontiguousarray(devices, dtype=np.int32)
+        rc = _lib.lib().b200z_deflate_batch_multi(dv.ctypes.data, dv.size, _ptr_array(ins), lens.ctypes.data, n, level, strategy, wrap,
+                                                  end_mode, _ptr_array(outs), caps.ctypes.data, out_len.ctypes.data,
+                                                  check.ctypes.data, status.ctypes.data)
+    else:
+        rc = _lib.lib().b200z_deflate_batch(_ptr_array(ins), lens.ctypes.data, n, level, strategy, wrap, end_mode,
+                                            _ptr_array(outs), caps.ctypes.data, out_len.ctypes.data, check.ctypes.data,
+                                            status.ctypes.data)
     _lib.raise_for(rc)
     return [outs[i][:out_len[i]].tobytes() for i in range(n)], check
 
 
-def inflate_batch(buffers, out_caps, raise_on_error=True, wrap=_lib.WRAP_RAW, return_checks=False):
+def inflate_batch(buffers, out_caps, raise_on_error=True, wrap=_lib.WRAP_RAW, return_checks=False, devices=None):
     """Host buffers in, (outputs, in_used, status) out.  status[i] = code | detail << 8.  wrap: WRAP_RAW (raw deflate),
     WRAP_ZLIB / WRAP_GZIP (header parsed, output checksum compared with the trailer on the device; gzip: one member,
     in_used says where the next one starts), WRAP_RAW_CRC32 (raw deflate, CRC-32 of the output reported: zip entries).
@@ -170,9 +243,15 @@ def inflate_batch(buffers, out_caps, raise_on_error=True, wrap=_lib.WRAP_RAW, re
     in_used = np.zeros(n, dtype=np.int64)
     check = np.zeros(n, dtype=np.uint32)
     status = np.zeros(n, dtype=np.int32)
-    rc = _lib.lib().b200z_inflate_batch(_ptr_array(ins), lens.ctypes.data, n, wrap, _ptr_array(outs),
-                                        caps.ctypes.data, out_len.ctypes.data, in_used.ctypes.data, check.ctypes.data,
-                                        status.ctypes.data)
+    if devices is not None:  # one host process, several GPUs (b200z_inflate_batch_multi)
+        dv = np.ascontiguousarray(devices, dtype=np.int32)
+        rc = _lib.lib().b200z_inflate_batch_multi(dv.ctypes.data, dv.size, _ptr_array(ins), lens.ctypes.data, n, wrap, _ptr_array(outs),
+                                                  caps.ctypes.data, out_len.ctypes.data, in_used.ctypes.data, check.ctypes.data,
+                                                  status.ctypes.data)
+    else:
+        rc = _lib.lib().b200z_inflate_batch(_ptr_array(ins), lens.ctypes.data, n, wrap, _ptr_array(outs),
+                                            caps.ctypes.data, out_len.ctypes.data, in_used.ctypes.data, check.ctypes.data,
+                                            status.ctypes.data)
     if raise_on_error:
         _lib.raise_for(rc)
     elif rc in (_lib.E_CUDA, _lib.E_ARG):

@@ -1,10 +1,14 @@
 // b200z_api.cu -- the C-ABI of libb200z.so (include/b200z.h): context, plans, host-buffer batch calls and the
 // streaming handles that mirror Deflater.cs / Inflater.cs member for member.  No CPU codec lives here: every byte of
 // compressed or decompressed data is produced by the kernels in b200z_deflate.cu / b200z_inflate.cu.
+#include <algorithm>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <functional>
 #include <mutex>
+#include <thread>
+#include <utility>
 
 #include "b200z_internal.cuh"
 
@@ -12,7 +16,7 @@ namespace b200z {
 
 static thread_local std::string g_err;
 static std::mutex g_mu;
-static int g_device = -1;
+static thread_local int t_device = -1; // what b200z_init() chose for this thread
 
 void set_error(const char *fmt, ...) {
 	char buf[512];
@@ -30,7 +34,7 @@ int cuda_fail(cudaError_t e, const char *what, const char *file, int line) {
 
 int ensure_init() {
 	std::lock_guard<std::mutex> lk(g_mu);
-	if (g_device >= 0) return B200Z_OK;
+	if (t_device >= 0) return B200Z_OK;
 	int cnt = 0;
 	cudaError_t e = cudaGetDeviceCount(&cnt);
 	if (e != cudaSuccess || cnt == 0) {
@@ -39,8 +43,15 @@ int ensure_init() {
 	}
 	int dev = 0;
 	B200Z_CUDA(cudaGetDevice(&dev));
-	g_device = dev;
+	t_device = dev;
 	return B200Z_OK;
+}
+
+int current_device() {
+	if (t_device >= 0) return t_device;
+	int dev = 0;
+	if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+	return dev;
 }
 
 int Arena::alloc() {
@@ -160,7 +171,10 @@ static int run_plan_host(b200z_plan *plan, const uint8_t *const *in, PinnedBuf &
 	for (int i = 0; i < n; i++)
 		if (plan->in_len[i]) memcpy(hin.p + plan->in_off[i], in[i], (size_t)plan->in_len[i]);
 	cudaStream_t s = 0;
-	B200Z_CUDA(cudaMemcpyAsync(din.p, hin.p, (size_t)plan->in_bytes, cudaMemcpyHostToDevice, s));
+	int64_t used = 0; // (a plan run below its capacity: b200z_inflate_plan_set_lengths)
+	for (int i = 0; i < n; i++) used = std::max(used, plan->in_off[i] + plan->in_len[i]);
+	used = std::min<int64_t>(plan->in_bytes, (used + 255) / 256 * 256);
+	B200Z_CUDA(cudaMemcpyAsync(din.p, hin.p, (size_t)used, cudaMemcpyHostToDevice, s));
 	int64_t *d_out_len = reinterpret_cast<int64_t *>(dmeta.p);
 	int64_t *d_in_used = d_out_len + n;
 	int32_t *d_status = reinterpret_cast<int32_t *>(d_in_used + n);
@@ -215,7 +229,7 @@ int b200z_init(int device) {
 			return B200Z_E_ARG;
 		}
 		B200Z_CUDA(cudaSetDevice(device));
-		g_device = device;
+		t_device = device;
 	}
 	return checksum_init_tables();
 }
@@ -271,7 +285,9 @@ int b200z_deflate_plan_create_ex(int32_t n, const int64_t *in_len, int level, in
 	}
 	int rc = ensure_init();
 	if (rc) return rc;
+	DeviceGuard guard(current_device());
 	b200z_plan *p = new b200z_plan();
+	p->device = current_device();
 	p->kind = 0;
 	p->n = n;
 	p->level = level;
@@ -377,7 +393,9 @@ int b200z_inflate_plan_create_ex(int32_t n, const int64_t *comp_len, const int64
 	}
 	int rc = ensure_init();
 	if (rc) return rc;
+	DeviceGuard guard(current_device());
 	b200z_plan *p = new b200z_plan();
+	p->device = current_device();
 	p->kind = 1;
 	p->n = n;
 	p->wrap = wrap;
@@ -406,6 +424,7 @@ int b200z_inflate_plan_create_ex(int32_t n, const int64_t *comp_len, const int64
 }
 
 int b200z_inflate_plan_set_start_bits(b200z_plan *plan, const int32_t *start_bit) {
+	DeviceGuard guard(plan ? plan->device : -1);
 	if (!plan || plan->kind != 1 || (plan->n > 0 && !start_bit)) {
 		set_error("bad arguments");
 		return B200Z_E_ARG;
@@ -427,7 +446,39 @@ int b200z_inflate_plan_set_start_bits(b200z_plan *plan, const int32_t *start_bit
 	return B200Z_OK;
 }
 
+int b200z_inflate_plan_set_lengths(b200z_plan *plan, const int64_t *comp_len, const int64_t *dict_len) {
+	DeviceGuard guard(plan ? plan->device : -1);
+	if (!plan || plan->kind != 1 || (plan->n > 0 && !comp_len)) {
+		set_error("bad arguments");
+		return B200Z_E_ARG;
+	}
+	const int n = plan->n;
+	std::vector<int64_t> dl((size_t)n);
+	std::vector<uint32_t> d32((size_t)n);
+	for (int i = 0; i < n; i++) {
+		const int64_t D = dict_len ? dict_len[i] : 0;
+		if (comp_len[i] < 0 || comp_len[i] > plan->comp_cap[(size_t)i] || D < 0 || D > plan->dict_cap[(size_t)i]) {
+			set_error("stream %d: %lld compressed / %lld dictionary bytes exceed what the plan was created for (%lld / %lld)", i,
+			          (long long)comp_len[i], (long long)D, (long long)plan->comp_cap[(size_t)i], (long long)plan->dict_cap[(size_t)i]);
+			return B200Z_E_ARG;
+		}
+		dl[(size_t)i] = comp_len[i];
+		d32[(size_t)i] = (uint32_t)D;
+	}
+	for (int i = 0; i < n; i++) { // the dictionary ends where the compressed bytes start
+		if (!plan->hist.empty()) plan->hist[(size_t)i] = d32[(size_t)i];
+		plan->in_off[(size_t)i] = plan->comp_off[(size_t)i] - d32[(size_t)i];
+		plan->in_len[(size_t)i] = comp_len[i] + d32[(size_t)i];
+	}
+	if (n) {
+		B200Z_CUDA(cudaMemcpy(plan->ws.at<int64_t>(plan->o_in_len), dl.data(), 8ull * n, cudaMemcpyHostToDevice));
+		B200Z_CUDA(cudaMemcpy(plan->ws.at<uint32_t>(plan->o_hist), d32.data(), 4ull * n, cudaMemcpyHostToDevice));
+	}
+	return B200Z_OK;
+}
+
 int b200z_plan_get_restart_points(b200z_plan *plan, int64_t *bit, int64_t *out_pos, void *cuda_stream) {
+	DeviceGuard guard(plan ? plan->device : -1);
 	if (!plan || plan->kind != 1 || (plan->n > 0 && (!bit || !out_pos))) {
 		set_error("bad arguments");
 		return B200Z_E_ARG;
@@ -444,6 +495,15 @@ int b200z_plan_get_restart_points(b200z_plan *plan, int64_t *bit, int64_t *out_p
 	return B200Z_OK;
 }
 
+int b200z_plan_get_stats(b200z_plan *plan, uint32_t *v, int32_t cap, void *cuda_stream) {
+	DeviceGuard guard(plan ? plan->device : -1);
+	if (!plan || plan->kind != 1 || !v || cap < 0) {
+		set_error("bad arguments");
+		return B200Z_E_ARG;
+	}
+	return inflate_plan_stats(plan, v, cap, (cudaStream_t)cuda_stream);
+}
+
 int b200z_plan_set_timing(b200z_plan *plan, int enable) {
 	if (!plan) return B200Z_E_ARG;
 	plan->timing = enable != 0;
@@ -452,6 +512,7 @@ int b200z_plan_set_timing(b200z_plan *plan, int enable) {
 }
 
 int b200z_plan_get_timings(b200z_plan *plan, char *names, int32_t names_cap, float *ms, int32_t cap, int32_t *count) {
+	DeviceGuard guard(plan ? plan->device : -1);
 	if (!plan || !ms || !count) return B200Z_E_ARG;
 	*count = 0;
 	std::string nm;
@@ -472,6 +533,7 @@ int b200z_plan_get_timings(b200z_plan *plan, char *names, int32_t names_cap, flo
 }
 
 int b200z_plan_destroy(b200z_plan *plan) {
+	DeviceGuard guard(plan ? plan->device : -1);
 	if (!plan) return B200Z_OK;
 	for (cudaEvent_t e : plan->ev) cudaEventDestroy(e);
 	plan->ws.release();
@@ -497,6 +559,7 @@ int b200z_plan_run(b200z_plan *plan, const uint8_t *d_in, uint8_t *d_out, int64_
 
 int b200z_plan_run_stages(b200z_plan *plan, const uint8_t *d_in, uint8_t *d_out, int64_t *d_out_len, int32_t *d_status,
                           uint32_t *d_check, int64_t *d_in_used, int stages, void *cuda_stream) {
+	DeviceGuard guard(plan ? plan->device : -1);
 	if (!plan || !d_in || !d_out || !d_out_len || !d_status || (stages & ~3) || stages == 0) {
 		set_error("bad arguments");
 		return B200Z_E_ARG;
@@ -554,6 +617,7 @@ __global__ void __launch_bounds__(256)
 
 extern "C" int b200z_plan_pack(b200z_plan *plan, const uint8_t *d_out, const int64_t *d_out_len, uint8_t *d_packed,
                                int64_t *d_packed_off, void *cuda_stream) {
+	DeviceGuard guard(plan ? plan->device : -1);
 	if (!plan || !d_out || !d_out_len || !d_packed || !d_packed_off) {
 		set_error("bad arguments");
 		return B200Z_E_ARG;
@@ -631,6 +695,8 @@ int b200z_checksum_batch_device(int kind, const uint8_t *d_data, const int64_t *
 	return rc;
 }
 
+static const char *inflate_detail_msg(int detail);
+
 // ---- host-buffer batch calls ----------------------------------------------------------------------------
 static void zlib_header(int level, uint8_t h[2], bool preset_dict = false) { // Deflater.cs:436-464 (trap T11)
 	int header = (8 + (7 << 4)) << 8;
@@ -643,6 +709,382 @@ static void zlib_header(int level, uint8_t h[2], bool preset_dict = false) { // 
 	h[1] = (uint8_t)header;
 }
 
+// ---- host-buffer pipelines ---------------------------------------------------------------------------------
+// What a host that keeps a GPU busy does, inside the library: a pipeline owns the plan of one batch shape, `depth` slots of
+// pinned staging + device buffers and three streams.  submit() stages a batch from host pointers and enqueues upload and
+// kernels without waiting; collect() waits for the oldest batch, fetches exactly the bytes produced and hands them to the
+// caller's buffers.  With depth >= 2 the upload of batch i+1 and the download of batch i-1 overlap the kernels of batch i.
+// Host pointers that CUDA knows as pinned (cudaHostAlloc / cudaHostRegister) are the DMA source / target directly; plain
+// pageable memory goes through the slot's pinned staging, copied by a few host threads.
+} // extern "C"
+
+namespace b200z {
+
+static void host_parallel_for(int n_items, int64_t total_bytes, const std::function<void(int, int)> &fn) {
+	// fn(first, last) over [0, n_items), on up to 8 threads when there is enough to copy
+	int nt = total_bytes >= (8ll << 20) ? 8 : 1;
+	const int hw = (int)std::thread::hardware_concurrency();
+	if (hw > 0 && nt > hw) nt = hw;
+	if (nt > n_items) nt = n_items > 0 ? n_items : 1;
+	if (nt <= 1) {
+		fn(0, n_items);
+		return;
+	}
+	std::vector<std::thread> th;
+	for (int t = 0; t < nt; t++) th.emplace_back([=, &fn] { fn((int)((int64_t)n_items * t / nt), (int)((int64_t)n_items * (t + 1) / nt)); });
+	for (auto &t : th) t.join();
+}
+
+static bool host_ptr_is_pinned(const void *p) {
+	cudaPointerAttributes a;
+	if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+		cudaGetLastError();
+		return false;
+	}
+	return a.type == cudaMemoryTypeHost;
+}
+
+struct PipeMeta { // per slot, pinned: what a run reports
+	int64_t *out_len, *in_used, *poff;
+	int32_t *status;
+	uint32_t *check;
+};
+
+struct PipeSlot {
+	PinnedBuf hin, hout, hmeta;
+	DevBuf din, dout, dpack, dmeta;
+	PipeMeta h, d;
+	cudaEvent_t ev_up = nullptr, ev_run = nullptr;
+	bool busy = false;
+};
+
+} // namespace b200z
+
+struct b200z_pipeline {
+	b200z_plan *plan = nullptr;
+	int depth = 1;
+	std::vector<b200z::PipeSlot> slots;
+	cudaStream_t s_up = nullptr, s_run = nullptr, s_down = nullptr;
+	int64_t head = 0, tail = 0; // batches submitted / collected
+	int64_t in_total = 0;
+	std::vector<int64_t> data_off; // where stream i's data goes in the input blob
+};
+
+namespace b200z {
+
+static void pipe_meta_layout(uint8_t *base, int n, PipeMeta &m) {
+	m.out_len = reinterpret_cast<int64_t *>(base);
+	m.in_used = m.out_len + n;
+	m.poff = m.in_used + n;
+	m.status = reinterpret_cast<int32_t *>(m.poff + n + 1);
+	m.check = reinterpret_cast<uint32_t *>(m.status + n);
+}
+static size_t pipe_meta_bytes(int n) { return (size_t)n * (8 + 8 + 8 + 4 + 4) + 8 + 256; }
+
+static int pipeline_finish_create(b200z_plan *plan, int depth, b200z_pipeline **out) {
+	DeviceGuard guard(plan->device);
+	if (depth < 1 || depth > 8) {
+		b200z_plan_destroy(plan);
+		set_error("depth");
+		return B200Z_E_ARG;
+	}
+	b200z_pipeline *p = new b200z_pipeline();
+	p->plan = plan;
+	p->depth = depth;
+	p->slots.resize((size_t)depth);
+	const int n = plan->n;
+	int rc = B200Z_OK;
+	auto fail = [&](int code) {
+		b200z_pipeline_destroy(p);
+		return code;
+	};
+	if (cudaStreamCreateWithFlags(&p->s_up, cudaStreamNonBlocking) != cudaSuccess || cudaStreamCreateWithFlags(&p->s_run, cudaStreamNonBlocking) != cudaSuccess ||
+	    cudaStreamCreateWithFlags(&p->s_down, cudaStreamNonBlocking) != cudaSuccess) {
+		set_error("cudaStreamCreate failed");
+		return fail(B200Z_E_CUDA);
+	}
+	for (auto &sl : p->slots) {
+		if ((rc = sl.hin.ensure((size_t)plan->in_bytes + 256))) return fail(rc);
+		if ((rc = sl.hout.ensure((size_t)plan->out_bytes + 256))) return fail(rc);
+		if ((rc = sl.hmeta.ensure(pipe_meta_bytes(n)))) return fail(rc);
+		if ((rc = sl.din.ensure((size_t)plan->in_bytes + 256))) return fail(rc);
+		if ((rc = sl.dout.ensure((size_t)plan->out_bytes + 256))) return fail(rc);
+		if (plan->kind == 0 && (rc = sl.dpack.ensure((size_t)plan->out_bytes + 256))) return fail(rc);
+		if ((rc = sl.dmeta.ensure(pipe_meta_bytes(n)))) return fail(rc);
+		pipe_meta_layout(sl.hmeta.p, n, sl.h);
+		pipe_meta_layout(sl.dmeta.p, n, sl.d);
+		memset(sl.hin.p, 0, (size_t)plan->in_bytes + 256);
+		if (cudaEventCreateWithFlags(&sl.ev_up, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&sl.ev_run, cudaEventDisableTiming) != cudaSuccess) {
+			set_error("cudaEventCreate failed");
+			return fail(B200Z_E_CUDA);
+		}
+		// the bytes between the slots of the input blob are never written again: clear them once
+		if (cudaMemset(sl.din.p, 0, (size_t)plan->in_bytes + 256) != cudaSuccess) return fail(B200Z_E_CUDA);
+	}
+	p->data_off.resize((size_t)n);
+	for (int i = 0; i < n; i++) {
+		p->data_off[(size_t)i] = b200z_plan_data_offset(plan, i);
+		p->in_total += plan->in_len[(size_t)i] - (plan->hist.empty() ? 0 : plan->hist[(size_t)i]);
+	}
+	*out = p;
+	return B200Z_OK;
+}
+
+} // namespace b200z
+
+extern "C" {
+
+int b200z_deflate_pipeline_create(int32_t n, const int64_t *in_len, int level, int strategy, int wrap, int end_mode, int depth,
+                                  b200z_pipeline **pipe) {
+	if (!pipe) {
+		set_error("bad arguments");
+		return B200Z_E_ARG;
+	}
+	if (level == -1) level = 6;
+	b200z_plan *plan = nullptr;
+	// gzip: the plan delivers the raw stream and the CRC-32; collect() writes header and trailer (GzipOutputStream.cs:315-375)
+	int rc = b200z_deflate_plan_create(n, in_len, level, strategy, wrap == B200Z_WRAP_GZIP ? B200Z_WRAP_RAW_CRC32 : wrap, end_mode, &plan);
+	if (rc) return rc;
+	plan->host_wrap = wrap;
+	return pipeline_finish_create(plan, depth, pipe);
+}
+
+int b200z_inflate_pipeline_create(int32_t n, const int64_t *comp_len, const int64_t *out_cap, int wrap, int depth, b200z_pipeline **pipe) {
+	if (!pipe) {
+		set_error("bad arguments");
+		return B200Z_E_ARG;
+	}
+	b200z_plan *plan = nullptr;
+	int rc = b200z_inflate_plan_create(n, comp_len, out_cap, wrap, &plan);
+	if (rc) return rc;
+	plan->host_wrap = wrap;
+	return pipeline_finish_create(plan, depth, pipe);
+}
+
+int b200z_pipeline_destroy(b200z_pipeline *p) {
+	DeviceGuard guard((p && p->plan) ? p->plan->device : -1);
+	if (!p) return B200Z_OK;
+	if (p->s_up) cudaStreamSynchronize(p->s_up);
+	if (p->s_run) cudaStreamSynchronize(p->s_run);
+	if (p->s_down) cudaStreamSynchronize(p->s_down);
+	for (auto &sl : p->slots) {
+		if (sl.ev_up) cudaEventDestroy(sl.ev_up);
+		if (sl.ev_run) cudaEventDestroy(sl.ev_run);
+	}
+	if (p->s_up) cudaStreamDestroy(p->s_up);
+	if (p->s_run) cudaStreamDestroy(p->s_run);
+	if (p->s_down) cudaStreamDestroy(p->s_down);
+	b200z_plan_destroy(p->plan);
+	delete p;
+	return B200Z_OK;
+}
+
+int32_t b200z_pipeline_in_flight(const b200z_pipeline *p) { return p ? (int32_t)(p->head - p->tail) : 0; }
+
+int b200z_pipeline_submit(b200z_pipeline *p, const uint8_t *const *in) {
+	DeviceGuard guard((p && p->plan) ? p->plan->device : -1);
+	if (!p || (p->plan->n > 0 && !in)) {
+		set_error("bad arguments");
+		return B200Z_E_ARG;
+	}
+	if (p->head - p->tail >= p->depth) {
+		set_error("pipeline: %d batches in flight, collect one first", p->depth);
+		return B200Z_E_STATE;
+	}
+	b200z_plan *plan = p->plan;
+	const int n = plan->n;
+	PipeSlot &sl = p->slots[(size_t)(p->head % p->depth)];
+	bool all_pinned = n > 0;
+	for (int i = 0; i < n && all_pinned; i++) {
+		const int64_t len = plan->in_len[(size_t)i];
+		if (len > 0 && !in[i]) {
+			set_error("stream %d: null input", i);
+			return B200Z_E_ARG;
+		}
+		if (len > 0 && (i < 4 || (i & 63) == 0)) all_pinned = host_ptr_is_pinned(in[i]); // (sampled: the check is not free)
+	}
+	if (all_pinned) {
+		for (int i = 0; i < n; i++)
+			if (plan->in_len[(size_t)i] > 0)
+				B200Z_CUDA(cudaMemcpyAsync(sl.din.p + plan->in_off[(size_t)i], in[i], (size_t)plan->in_len[(size_t)i], cudaMemcpyHostToDevice, p->s_up));
+	} else {
+		host_parallel_for(n, p->in_total, [&](int a, int b) {
+			for (int i = a; i < b; i++)
+				if (plan->in_len[(size_t)i] > 0) memcpy(sl.hin.p + plan->in_off[(size_t)i], in[i], (size_t)plan->in_len[(size_t)i]);
+		});
+		B200Z_CUDA(cudaMemcpyAsync(sl.din.p, sl.hin.p, (size_t)plan->in_bytes, cudaMemcpyHostToDevice, p->s_up));
+	}
+	B200Z_CUDA(cudaEventRecord(sl.ev_up, p->s_up));
+	B200Z_CUDA(cudaStreamWaitEvent(p->s_run, sl.ev_up, 0));
+	int rc = b200z_plan_run(plan, sl.din.p, sl.dout.p, sl.d.out_len, sl.d.status, sl.d.check, sl.d.in_used, (void *)p->s_run);
+	if (rc) return rc;
+	if (plan->kind == 0) {
+		rc = b200z_plan_pack(plan, sl.dout.p, sl.d.out_len, sl.dpack.p, sl.d.poff, (void *)p->s_run);
+		if (rc) return rc;
+	}
+	B200Z_CUDA(cudaMemcpyAsync(sl.hmeta.p, sl.dmeta.p, pipe_meta_bytes(n) - 256, cudaMemcpyDeviceToHost, p->s_run));
+	B200Z_CUDA(cudaEventRecord(sl.ev_run, p->s_run));
+	sl.busy = true;
+	++p->head;
+	return B200Z_OK;
+}
+
+int b200z_pipeline_collect(b200z_pipeline *p, uint8_t *const *out, const int64_t *out_cap, int64_t *out_len, int64_t *in_used,
+                           uint32_t *check, int32_t *status) {
+	DeviceGuard guard((p && p->plan) ? p->plan->device : -1);
+	if (!p || (p->plan->n > 0 && (!out || !out_cap || !out_len))) {
+		set_error("bad arguments");
+		return B200Z_E_ARG;
+	}
+	if (p->head == p->tail) {
+		set_error("pipeline: nothing submitted");
+		return B200Z_E_STATE;
+	}
+	b200z_plan *plan = p->plan;
+	const int n = plan->n;
+	PipeSlot &sl = p->slots[(size_t)(p->tail % p->depth)];
+	B200Z_CUDA(cudaEventSynchronize(sl.ev_run)); // the run's sizes, statuses and checksums are on the host
+	const int wrap = plan->host_wrap;
+	int first = B200Z_OK, first_detail = 0;
+	int64_t moved = 0;
+	if (plan->kind == 0) {
+		// ---- deflate: exactly the produced bytes cross PCIe (packed back to back on the device) ----
+		const int64_t total = n ? sl.h.poff[n] : 0;
+		if (total > 0) B200Z_CUDA(cudaMemcpyAsync(sl.hout.p, sl.dpack.p, (size_t)total, cudaMemcpyDeviceToHost, p->s_down));
+		B200Z_CUDA(cudaStreamSynchronize(p->s_down));
+		const int hdr = wrap == B200Z_WRAP_ZLIB ? 2 : (wrap == B200Z_WRAP_GZIP ? 10 : 0);
+		const int trl = wrap == B200Z_WRAP_ZLIB ? 4 : (wrap == B200Z_WRAP_GZIP ? 8 : 0);
+		for (int i = 0; i < n; i++) {
+			int st = sl.h.status[i] & 0xFF;
+			const int64_t need = sl.h.out_len[i] + hdr + trl;
+			if (st == B200Z_OK && need > out_cap[i]) st = B200Z_E_NOMEM;
+			out_len[i] = st == B200Z_OK ? need : 0;
+			if (status) status[i] = st;
+			if (check) check[i] = sl.h.check[i];
+			if (in_used) in_used[i] = 0;
+			if (st != B200Z_OK && first == B200Z_OK) first = st;
+			if (st == B200Z_OK) moved += need;
+		}
+		host_parallel_for(n, moved, [&](int a, int b) {
+			for (int i = a; i < b; i++) {
+				if (out_len[i] == 0) continue;
+				uint8_t *o = out[i];
+				if (wrap == B200Z_WRAP_ZLIB) {
+					zlib_header(plan->level, o);
+					o += 2;
+				} else if (wrap == B200Z_WRAP_GZIP) {
+					// GzipOutputStream.GetHeader (:339-375) with MTIME 0 and no FNAME: 1F 8B 08 00 <mtime> 00 FF (trap T15)
+					const uint8_t h[10] = {0x1F, 0x8B, 8, 0, 0, 0, 0, 0, 0, 0xFF};
+					memcpy(o, h, 10);
+					o += 10;
+				}
+				memcpy(o, sl.hout.p + sl.h.poff[i], (size_t)sl.h.out_len[i]);
+				o += sl.h.out_len[i];
+				const uint32_t a32 = sl.h.check[i];
+				if (wrap == B200Z_WRAP_ZLIB) { // Adler32 trailer, big endian (Deflater.cs:509-514)
+					o[0] = (uint8_t)(a32 >> 24);
+					o[1] = (uint8_t)(a32 >> 16);
+					o[2] = (uint8_t)(a32 >> 8);
+					o[3] = (uint8_t)a32;
+				} else if (wrap == B200Z_WRAP_GZIP) { // GetFooter (:315-337): CRC32, ISIZE = TotalIn & 0xFFFFFFFF, little endian
+					const uint32_t isz = (uint32_t)((uint64_t)plan->in_len[(size_t)i] & 0xFFFFFFFFull);
+					for (int k = 0; k < 4; k++) o[k] = (uint8_t)(a32 >> (8 * k));
+					for (int k = 0; k < 4; k++) o[4 + k] = (uint8_t)(isz >> (8 * k));
+				}
+			}
+		});
+	} else {
+		// ---- inflate: every stream's produced bytes; straight into the caller's buffers when CUDA knows them as pinned ----
+		bool all_pinned = n > 0;
+		for (int i = 0; i < n && all_pinned; i++)
+			if (sl.h.out_len[i] > 0 && (i < 4 || (i & 63) == 0)) all_pinned = host_ptr_is_pinned(out[i]);
+		for (int i = 0; i < n; i++) {
+			const int64_t L = sl.h.out_len[i];
+			if (L > 0)
+				B200Z_CUDA(cudaMemcpyAsync(all_pinned ? out[i] : sl.hout.p + plan->out_off[(size_t)i], sl.dout.p + plan->out_off[(size_t)i], (size_t)L,
+				                           cudaMemcpyDeviceToHost, p->s_down));
+			moved += L;
+		}
+		B200Z_CUDA(cudaStreamSynchronize(p->s_down));
+		if (!all_pinned)
+			host_parallel_for(n, moved, [&](int a, int b) {
+				for (int i = a; i < b; i++)
+					if (sl.h.out_len[i] > 0) memcpy(out[i], sl.hout.p + plan->out_off[(size_t)i], (size_t)sl.h.out_len[i]);
+			});
+		for (int i = 0; i < n; i++) {
+			const int st = sl.h.status[i];
+			out_len[i] = sl.h.out_len[i];
+			if (in_used) in_used[i] = sl.h.in_used[i];
+			if (status) status[i] = st;
+			if (check) check[i] = wrap != B200Z_WRAP_RAW ? sl.h.check[i] : 0u;
+			if ((st & 0xFF) != B200Z_OK && first == B200Z_OK) {
+				first = st & 0xFF;
+				first_detail = (st >> 8) & 0xFF;
+			}
+		}
+	}
+	sl.busy = false;
+	++p->tail;
+	if (first == B200Z_E_DATA && plan->kind == 1) set_error("%s", inflate_detail_msg(first_detail)); // the reference's exception message
+	else if (first != B200Z_OK) set_error("stream failed with status %d", first);
+	return first;
+}
+
+} // extern "C"
+
+// ---- host-buffer batch calls: one submit + collect on a cached pipeline of the batch's shape --------------------------
+namespace b200z {
+struct PipeKey {
+	int kind, n, level, strategy, wrap, end_mode;
+	std::vector<int64_t> a, b;
+	bool operator==(const PipeKey &o) const {
+		return kind == o.kind && n == o.n && level == o.level && strategy == o.strategy && wrap == o.wrap && end_mode == o.end_mode && a == o.a && b == o.b;
+	}
+};
+struct PipeCache { // per host thread: the last few shapes keep their plan, staging and device buffers
+	std::vector<std::pair<PipeKey, b200z_pipeline *>> items;
+	~PipeCache() {
+		for (auto &it : items) b200z_pipeline_destroy(it.second);
+	}
+	b200z_pipeline *find(const PipeKey &k) {
+		for (size_t i = 0; i < items.size(); i++)
+			if (items[i].first == k) {
+				auto it = items[i];
+				items.erase(items.begin() + (ptrdiff_t)i);
+				items.insert(items.begin(), it);
+				return it.second;
+			}
+		return nullptr;
+	}
+	void put(PipeKey k, b200z_pipeline *p) {
+		items.insert(items.begin(), std::make_pair(std::move(k), p));
+		while (items.size() > 4) {
+			b200z_pipeline_destroy(items.back().second);
+			items.pop_back();
+		}
+	}
+	void clear() {
+		for (auto &it : items) b200z_pipeline_destroy(it.second);
+		items.clear();
+	}
+};
+static thread_local PipeCache g_pipes;
+struct MultiKey {
+	int device;
+	PipeKey key;
+};
+static thread_local std::vector<std::pair<MultiKey, b200z_pipeline *>> g_multi_pipes; // b200z_*_batch_multi: a few per device
+} // namespace b200z
+
+extern "C" {
+
+int b200z_release_cached(void) { // frees what the host-buffer batch calls of this thread keep between calls
+	for (auto &it : g_multi_pipes) b200z_pipeline_destroy(it.second);
+	g_multi_pipes.clear();
+	g_pipes.clear();
+	return B200Z_OK;
+}
+
 int b200z_deflate_batch(const uint8_t *const *in, const int64_t *in_len, int32_t n, int level, int strategy, int wrap,
                         int end_mode, uint8_t *const *out, const int64_t *out_cap, int64_t *out_len, uint32_t *check,
                         int32_t *status) {
@@ -650,57 +1092,18 @@ int b200z_deflate_batch(const uint8_t *const *in, const int64_t *in_len, int32_t
 		set_error("bad arguments");
 		return B200Z_E_ARG;
 	}
-	if (wrap == B200Z_WRAP_GZIP) {
-		// GZipOutputStream's header carries caller state (MTIME, FNAME; GzipOutputStream.cs:339-375): the host shim
-		// writes header and trailer around the raw stream and takes the CRC32 from `check`.
-		set_error("gzip framing is written by the host stream layer; deflate with wrap=B200Z_WRAP_RAW_CRC32 and use check (CRC32)");
-		return B200Z_E_UNSUPPORTED;
-	}
 	if (level == -1) level = 6;
-	b200z_plan *plan = nullptr;
-	int rc = b200z_deflate_plan_create(n, in_len, level, strategy, wrap, end_mode, &plan);
-	if (rc) return rc;
-	PinnedBuf hin, hout;
-	DevBuf din, dout, dmeta;
-	HostRunResult r;
-	rc = run_plan_host(plan, in, hin, hout, din, dout, dmeta, r, false);
-	int first = B200Z_OK;
-	if (!rc) {
-		for (int i = 0; i < n; i++) {
-			int st = r.status[i] & 0xFF;
-			int64_t need = r.out_len[i] + (wrap == B200Z_WRAP_ZLIB ? 6 : 0);
-			if (st == B200Z_OK && need > out_cap[i]) st = B200Z_E_NOMEM;
-			if (st == B200Z_OK) {
-				uint8_t *o = out[i];
-				if (wrap == B200Z_WRAP_ZLIB) {
-					zlib_header(level, o);
-					o += 2;
-				}
-				memcpy(o, hout.p + plan->out_off[i], (size_t)r.out_len[i]);
-				o += r.out_len[i];
-				if (wrap == B200Z_WRAP_ZLIB) { // Adler32 trailer, big endian (Deflater.cs:509-514)
-					const uint32_t a = r.check[i];
-					o[0] = (uint8_t)(a >> 24);
-					o[1] = (uint8_t)(a >> 16);
-					o[2] = (uint8_t)(a >> 8);
-					o[3] = (uint8_t)a;
-				}
-				out_len[i] = need;
-			} else {
-				out_len[i] = 0;
-				if (first == B200Z_OK) first = st;
-			}
-			if (status) status[i] = st;
-			if (check) check[i] = r.check[i];
-		}
+	PipeKey key{0, n, level, strategy, wrap, end_mode, std::vector<int64_t>(in_len, in_len + n), {}};
+	b200z_pipeline *p = g_pipes.find(key);
+	if (!p) {
+		int rc = b200z_deflate_pipeline_create(n, in_len, level, strategy, wrap, end_mode, 1, &p);
+		if (rc) return rc;
+		g_pipes.put(std::move(key), p);
 	}
-	b200z_plan_destroy(plan);
+	int rc = b200z_pipeline_submit(p, in);
 	if (rc) return rc;
-	if (first != B200Z_OK) set_error("stream failed with status %d", first);
-	return first;
+	return b200z_pipeline_collect(p, out, out_cap, out_len, nullptr, check, status);
 }
-
-static const char *inflate_detail_msg(int detail);
 
 int b200z_inflate_batch(const uint8_t *const *in, const int64_t *in_len, int32_t n, int wrap, uint8_t *const *out,
                         const int64_t *out_cap, int64_t *out_len, int64_t *in_used, uint32_t *check, int32_t *status) {
@@ -708,33 +1111,135 @@ int b200z_inflate_batch(const uint8_t *const *in, const int64_t *in_len, int32_t
 		set_error("bad arguments");
 		return B200Z_E_ARG;
 	}
-	b200z_plan *plan = nullptr;
-	int rc = b200z_inflate_plan_create(n, in_len, out_cap, wrap, &plan);
-	if (rc) return rc;
-	PinnedBuf hin, hout;
-	DevBuf din, dout, dmeta;
-	HostRunResult r;
-	rc = run_plan_host(plan, in, hin, hout, din, dout, dmeta, r, false);
-	int first = B200Z_OK, first_detail = 0;
-	if (!rc) {
-		for (int i = 0; i < n; i++) {
-			const int st = r.status[i];
-			if (r.out_len[i] > 0) memcpy(out[i], hout.p + plan->out_off[i], (size_t)r.out_len[i]);
-			out_len[i] = r.out_len[i];
-			if (in_used) in_used[i] = r.in_used[i];
-			if (status) status[i] = st;
-			if (check) check[i] = wrap != B200Z_WRAP_RAW ? r.check[i] : 0u;
-			if ((st & 0xFF) != B200Z_OK && first == B200Z_OK) {
-				first = st & 0xFF;
-				first_detail = (st >> 8) & 0xFF;
-			}
-		}
+	PipeKey key{1, n, 0, 0, wrap, 0, std::vector<int64_t>(in_len, in_len + n), std::vector<int64_t>(out_cap, out_cap + n)};
+	b200z_pipeline *p = g_pipes.find(key);
+	if (!p) {
+		int rc = b200z_inflate_pipeline_create(n, in_len, out_cap, wrap, 1, &p);
+		if (rc) return rc;
+		g_pipes.put(std::move(key), p);
 	}
-	b200z_plan_destroy(plan);
+	int rc = b200z_pipeline_submit(p, in);
 	if (rc) return rc;
-	if (first == B200Z_E_DATA) set_error("%s", inflate_detail_msg(first_detail)); // the reference's exception message
-	else if (first != B200Z_OK) set_error("stream failed with status %d", first);
-	return first;
+	return b200z_pipeline_collect(p, out, out_cap, out_len, in_used, check, status);
+}
+
+// ---- one host thread, several GPUs ----------------------------------------------------------------------------------
+// The streams of a batch are independent (a fresh Deflater / Inflater each): they are cut into contiguous ranges of
+// about equal bytes, every range goes to one device's pipeline, all submits are issued before the first
+// collect -- the devices work at the same time, the calling thread only stages and waits.
+int b200z_device_count(void) {
+	int cnt = 0;
+	if (cudaGetDeviceCount(&cnt) != cudaSuccess) {
+		cudaGetLastError();
+		return 0;
+	}
+	return cnt;
+}
+
+int b200z_partition_by_bytes(const int64_t *len, int32_t n, int32_t parts, int32_t *first) {
+	if (n < 0 || parts < 1 || !first || (n > 0 && !len)) {
+		set_error("bad arguments");
+		return B200Z_E_ARG;
+	}
+	int64_t total = 0;
+	for (int i = 0; i < n; i++) total += len[i] > 0 ? len[i] : 0;
+	// part r starts at the first stream whose cumulative start offset is >= floor(r T / R)
+	int32_t i = 0;
+	int64_t start = 0; // cumulative start of stream i
+	first[0] = 0;
+	for (int r = 1; r < parts; r++) {
+		const int64_t cut = (int64_t)(((__int128)total * r) / parts);
+		while (i < n && start < cut) {
+			start += len[i] > 0 ? len[i] : 0;
+			++i;
+		}
+		first[r] = i;
+	}
+	first[parts] = n;
+	return B200Z_OK;
+}
+
+} // extern "C"
+
+namespace b200z {
+static b200z_pipeline *multi_find(int device, const PipeKey &k) {
+	for (auto &it : g_multi_pipes)
+		if (it.first.device == device && it.first.key == k) return it.second;
+	return nullptr;
+}
+static void multi_put(int device, PipeKey k, b200z_pipeline *p) {
+	int same = 0;
+	for (size_t i = 0; i < g_multi_pipes.size();) { // at most two shapes per device stay
+		if (g_multi_pipes[i].first.device == device && ++same >= 2) {
+			b200z_pipeline_destroy(g_multi_pipes[i].second);
+			g_multi_pipes.erase(g_multi_pipes.begin() + (ptrdiff_t)i);
+		} else ++i;
+	}
+	g_multi_pipes.push_back(std::make_pair(MultiKey{device, std::move(k)}, p));
+}
+
+static int multi_batch(int kind, const int32_t *devices, int32_t n_devices, const uint8_t *const *in, const int64_t *in_len, int32_t n, int level,
+                       int strategy, int wrap, int end_mode, uint8_t *const *out, const int64_t *out_cap, int64_t *out_len, int64_t *in_used,
+                       uint32_t *check, int32_t *status) {
+	if (n < 0 || n_devices < 1 || !devices || (n > 0 && (!in || !in_len || !out || !out_cap || !out_len))) {
+		set_error("bad arguments");
+		return B200Z_E_ARG;
+	}
+	const int ndev_all = b200z_device_count();
+	for (int d = 0; d < n_devices; d++)
+		if (devices[d] < 0 || devices[d] >= ndev_all) {
+			set_error("device %d out of range (%d devices)", devices[d], ndev_all);
+			return B200Z_E_ARG;
+		}
+	std::vector<int32_t> first((size_t)n_devices + 1);
+	int rc = b200z_partition_by_bytes(in_len, n, n_devices, first.data());
+	if (rc) return rc;
+	const int saved = t_device;
+	std::vector<b200z_pipeline *> pipes((size_t)n_devices, nullptr);
+	int result = B200Z_OK;
+	for (int d = 0; d < n_devices && result == B200Z_OK; d++) {
+		const int a = first[(size_t)d], cnt = first[(size_t)d + 1] - a;
+		if (cnt == 0) continue;
+		PipeKey key{kind, cnt, level, strategy, wrap, end_mode, std::vector<int64_t>(in_len + a, in_len + a + cnt),
+		            kind == 1 ? std::vector<int64_t>(out_cap + a, out_cap + a + cnt) : std::vector<int64_t>()};
+		b200z_pipeline *p = multi_find(devices[d], key);
+		if (!p) {
+			if ((rc = b200z_init(devices[d]))) { result = rc; break; } // (makes the device this thread's current one for the creation)
+			rc = kind == 0 ? b200z_deflate_pipeline_create(cnt, in_len + a, level, strategy, wrap, end_mode, 1, &p)
+			               : b200z_inflate_pipeline_create(cnt, in_len + a, out_cap + a, wrap, 1, &p);
+			if (rc) { result = rc; break; }
+			multi_put(devices[d], std::move(key), p);
+		}
+		pipes[(size_t)d] = p;
+		if ((rc = b200z_pipeline_submit(p, in + a))) result = rc;
+	}
+	for (int d = 0; d < n_devices; d++) { // everything that was submitted is collected, whatever happened to the others
+		b200z_pipeline *p = pipes[(size_t)d];
+		if (!p || b200z_pipeline_in_flight(p) == 0) continue;
+		const int a = first[(size_t)d];
+		rc = b200z_pipeline_collect(p, out + a, out_cap + a, out_len + a, in_used ? in_used + a : nullptr, check ? check + a : nullptr,
+		                            status ? status + a : nullptr);
+		if (rc && result == B200Z_OK) result = rc;
+	}
+	t_device = saved;
+	if (saved >= 0) cudaSetDevice(saved);
+	return result;
+}
+} // namespace b200z
+
+extern "C" {
+
+int b200z_deflate_batch_multi(const int32_t *devices, int32_t n_devices, const uint8_t *const *in, const int64_t *in_len, int32_t n, int level,
+                              int strategy, int wrap, int end_mode, uint8_t *const *out, const int64_t *out_cap, int64_t *out_len,
+                              uint32_t *check, int32_t *status) {
+	if (level == -1) level = 6;
+	return multi_batch(0, devices, n_devices, in, in_len, n, level, strategy, wrap, end_mode, out, out_cap, out_len, nullptr, check, status);
+}
+
+int b200z_inflate_batch_multi(const int32_t *devices, int32_t n_devices, const uint8_t *const *in, const int64_t *in_len, int32_t n, int wrap,
+                              uint8_t *const *out, const int64_t *out_cap, int64_t *out_len, int64_t *in_used, uint32_t *check,
+                              int32_t *status) {
+	return multi_batch(1, devices, n_devices, in, in_len, n, 0, 0, wrap, 0, out, out_cap, out_len, in_used, check, status);
 }
 
 // =====================================================================================================
@@ -1102,6 +1607,11 @@ struct InflaterH {
 	std::string error_msg;
 	PinnedBuf hin, hout;
 	DevBuf din, dout, dmeta;
+	// one plan per handle, created for capacities and run below them (b200z_inflate_plan_set_lengths): a SetInput + Inflate
+	// pair costs the copies and the kernels, no allocation
+	b200z_plan *plan = nullptr;
+	int64_t plan_comp_cap = 0, plan_out_cap = 0;
+	~InflaterH() { b200z_plan_destroy(plan); }
 	int64_t out_total() const { return out_base + (int64_t)output.size(); }
 };
 
@@ -1144,14 +1654,21 @@ static int inflater_run_device(InflaterH *d) {
 	}
 	int64_t cap = avail * 8 + 65536;
 	for (int attempt = 0; attempt < 8; attempt++) {
-		b200z_plan *plan = nullptr;
 		const int64_t D = (int64_t)d->window.size();
-		int rc = b200z_inflate_plan_create_ex(1, &avail, &cap, B200Z_WRAP_RAW, D ? &D : nullptr, &plan);
-		if (rc) return rc;
-		if (sbit && (rc = b200z_inflate_plan_set_start_bits(plan, &sbit))) {
-			b200z_plan_destroy(plan);
-			return rc;
+		int rc;
+		if (!d->plan || avail > d->plan_comp_cap || cap > d->plan_out_cap) {
+			b200z_plan_destroy(d->plan);
+			d->plan = nullptr;
+			int64_t cc = 65536;
+			while (cc < avail) cc *= 2;
+			const int64_t oc = std::max(cap, cc * 8 + 65536), dc = 32768;
+			if ((rc = b200z_inflate_plan_create_ex(1, &cc, &oc, B200Z_WRAP_RAW, &dc, &d->plan))) return rc;
+			d->plan_comp_cap = cc;
+			d->plan_out_cap = oc;
 		}
+		b200z_plan *plan = d->plan;
+		if ((rc = b200z_inflate_plan_set_lengths(plan, &avail, &D))) return rc;
+		if ((rc = b200z_inflate_plan_set_start_bits(plan, &sbit))) return rc;
 		const uint8_t *inp = d->input.data() + (slice_abs - d->in_base);
 		std::vector<uint8_t> slot;
 		if (D) { // window image (dictionary, earlier output) directly in front of the compressed bytes
@@ -1164,14 +1681,10 @@ static int inflater_run_device(InflaterH *d) {
 		rc = run_plan_host(plan, &inp, d->hin, d->hout, d->din, d->dout, d->dmeta, r, false);
 		int64_t rbit = 0, rout = 0;
 		if (!rc) rc = b200z_plan_get_restart_points(plan, &rbit, &rout, nullptr);
-		if (rc) {
-			b200z_plan_destroy(plan);
-			return rc;
-		}
+		if (rc) return rc;
 		const int st = r.status[0] & 0xFF, detail = (r.status[0] >> 8) & 0xFF;
 		if (st == B200Z_E_NOMEM) {
-			b200z_plan_destroy(plan);
-			cap *= 8;
+			cap = d->plan_out_cap * 8; // (the next attempt makes a larger plan)
 			continue;
 		}
 		// this run's output is output[rs_out, rs_out + out_len): it replaces what an earlier run decoded behind the
@@ -1179,7 +1692,6 @@ static int inflater_run_device(InflaterH *d) {
 		const uint8_t *o = d->hout.p + plan->out_off[0];
 		d->output.resize((size_t)(d->rs_out - d->out_base));
 		d->output.insert(d->output.end(), o, o + r.out_len[0]);
-		b200z_plan_destroy(plan);
 		if (st == B200Z_OK) {
 			d->finished = true;
 			d->consumed = slice_abs + r.in_used[0];

@@ -2,6 +2,8 @@
 // Checksum/Crc32.cs:138-159 + CrcUtilities.cs:94-156, and Adler32.Update, Checksum/Adler32.cs:134-161).
 // One CTA per 32 KiB tile, one 128-byte chunk per thread; the combination identities are in b200z_crc.cuh.
 #include "b200z_crc.cuh"
+#include <mutex>
+
 #include "b200z_internal.cuh"
 
 namespace b200z {
@@ -9,10 +11,14 @@ namespace b200z {
 __constant__ uint32_t c_crc_tab[4][256];   // slicing-by-4 tables (the first 4 slices of the reference's 16)
 __constant__ uint32_t c_xpow_chunk[kCkThreads]; // x^(8 * 128 * k)
 __constant__ uint32_t c_xpow_byte[kCkChunk];    // x^(8 * r)
-static bool g_tables_ready = false;
+static unsigned long long g_tables_ready = 0; // bit d: the constant tables of device d are loaded
 
 int checksum_init_tables() {
-	if (g_tables_ready) return B200Z_OK;
+	int dev = 0;
+	B200Z_CUDA(cudaGetDevice(&dev));
+	static std::mutex mu;
+	std::lock_guard<std::mutex> lk(mu);
+	if (dev < 64 && ((g_tables_ready >> dev) & 1ull)) return B200Z_OK;
 	static uint32_t tab[4][256];
 	for (uint32_t i = 0; i < 256; i++) {
 		uint32_t res = i;
@@ -27,7 +33,7 @@ int checksum_init_tables() {
 	B200Z_CUDA(cudaMemcpyToSymbol(c_crc_tab, tab, sizeof(tab)));
 	B200Z_CUDA(cudaMemcpyToSymbol(c_xpow_chunk, xc, sizeof(xc)));
 	B200Z_CUDA(cudaMemcpyToSymbol(c_xpow_byte, xb, sizeof(xb)));
-	g_tables_ready = true;
+	if (dev < 64) g_tables_ready |= 1ull << dev;
 	return B200Z_OK;
 }
 

@@ -10,6 +10,7 @@
 #include <cuda_pipeline.h>
 
 #include "b200z_internal.cuh"
+#include "b200z_tma.cuh"
 
 namespace b200z {
 
@@ -168,21 +169,26 @@ __global__ void __launch_bounds__(kMatchThreads, 1)
 	const uint32_t w0 = t0 >= (uint32_t)kTile ? t0 - kTile : 0u;
 	uint32_t dend = t1 + 272;
 	if (dend > n) dend = n;
-	// stage (w0 and the slot base are 16-byte aligned; tails are covered by the scalar loops)
+	// Stage the tile's 64 KiB data window and its link entries (w0 and the slot base are 16-byte aligned).  The bulk of both
+	// goes through the TMA engine: one thread arms an mbarrier with the byte count and issues cp.async.bulk copies, the
+	// CTA waits on the barrier; the tails that are not multiples of 16 bytes are covered by scalar loops meanwhile.
+	__shared__ BulkBarrier s_bar;
+	if (threadIdx.x == 0) bulk_barrier_init(&s_bar);
+	__syncthreads();
 	{
 		const uint32_t nbytes = dend - w0;
 		const uint32_t nvec = nbytes >> 4;
-		const uint4 *src = reinterpret_cast<const uint4 *>(data + w0);
-		uint4 *dst = reinterpret_cast<uint4 *>(s_data);
-		for (uint32_t i = threadIdx.x; i < nvec; i += kMatchThreads) dst[i] = __ldg(src + i);
-		for (uint32_t i = (nvec << 4) + threadIdx.x; i < nbytes; i += kMatchThreads) s_data[i] = data[w0 + i];
 		const uint32_t nl = t1 - w0;
 		const uint32_t nlv = nl >> 3;
-		const uint4 *lsrc = reinterpret_cast<const uint4 *>(lnk + w0);
-		uint4 *ldst = reinterpret_cast<uint4 *>(s_link);
-		for (uint32_t i = threadIdx.x; i < nlv; i += kMatchThreads) ldst[i] = __ldg(lsrc + i);
+		if (threadIdx.x == 0) {
+			bulk_expect(&s_bar, 16u * (nvec + nlv));
+			bulk_copy_start(&s_bar, s_data, data + w0, 16u * nvec);
+			bulk_copy_start(&s_bar, s_link, lnk + w0, 16u * nlv);
+		}
+		for (uint32_t i = (nvec << 4) + threadIdx.x; i < nbytes; i += kMatchThreads) s_data[i] = data[w0 + i];
 		for (uint32_t i = (nlv << 3) + threadIdx.x; i < nl; i += kMatchThreads) s_link[i] = lnk[w0 + i];
 	}
+	bulk_wait(&s_bar, 0);
 	__syncthreads();
 	uint2 *out = mt + off;
 	// match_search() of b200z_core.cuh with the byte-wise extension loop replaced by 4-byte compares on aligned
@@ -404,9 +410,6 @@ __device__ __forceinline__ ParseCarry rec_carry(const RoundRec &r) {
 
 // One round [base, base + kRound) of a stream, entered with `carry` (uniform across the warp; updated to the round's
 // exit state).  The round's symbols go to sround[0 .. cnt).  Returns cnt (uniform).
-// kLazyTab: behind the tile kernels (experimental/k_tile_parse.cuh) the table only holds the positions their speculative parse
-// searched; the fix-up then searches the others on demand.  false compiles to exactly the table read.
-template <bool kLazyTab>
 __device__ __forceinline__ uint32_t parse_round(uint8_t *smem, const uint8_t *data, const uint16_t *lnk, const uint2 *tab,
                                                 uint32_t n, uint32_t H, uint32_t ab, uint32_t base, const LevelParams &lp,
                                                 int strategy, ParseCarry &carry, uint32_t *sround) {
@@ -430,10 +433,7 @@ __device__ __forceinline__ uint32_t parse_round(uint8_t *smem, const uint8_t *da
 	const uint32_t seg_end = base + (uint32_t)(lane + 1) * kSeg;
 	auto tabf = [&](uint32_t p, uint32_t &a, uint32_t &b) {
 		const uint32_t i = p - base;
-		uint2 &t = s_tab[(i >> kSegShift) * kSegStride + (i & (kSeg - 1))];
-		// behind the tile kernels: 0xFFFFFFFF = not searched (y alone: the quarter-budget answer has to be searched again);
-		// search in global memory, keep it for the next pass
-		if (kLazyTab && (t.x == 0xFFFFFFFFu || t.y == 0xFFFFFFFFu)) match_search(data, lnk, 0u, p, n, lp, t.x, t.y, ab);
+		const uint2 t = s_tab[(i >> kSegShift) * kSegStride + (i & (kSeg - 1))];
 		a = t.x;
 		b = t.y;
 	};
@@ -512,7 +512,7 @@ __global__ void __launch_bounds__(32)
 	// a guess otherwise
 	ParseCarry carry = clean_carry(cd.c0 > H ? cd.c0 : H);
 	for (uint32_t base = cd.c0; base < cd.c1; base += kRound) {
-		const uint32_t cnt = parse_round<false>(smem, in + off, link + off, mt + off, n, H, ab, base, lp, strategy, carry, sym_local + off + base);
+		const uint32_t cnt = parse_round(smem, in + off, link + off, mt + off, n, H, ab, base, lp, strategy, carry, sym_local + off + base);
 		if (threadIdx.x == 0) {
 			RoundRec r;
 			r.p = carry.st.p;
@@ -526,13 +526,12 @@ __global__ void __launch_bounds__(32)
 	}
 }
 
-template <bool kLazyTab>
-__device__ __forceinline__ void parse_fix_body(uint8_t *smem, const uint8_t *__restrict__ in, const uint16_t *__restrict__ link,
-                                               const uint2 *__restrict__ mt, uint32_t *__restrict__ sym_local,
-                                               const int64_t *__restrict__ in_off, const int64_t *__restrict__ in_len,
-                                               const uint32_t *__restrict__ rnd_off, RoundRec *__restrict__ recs, uint32_t chunk,
-                                               const uint32_t *__restrict__ hist, const int64_t *__restrict__ bias,
-                                               const LevelParams &lp, int strategy, const RoundRec *__restrict__ ent) {
+__global__ void __launch_bounds__(32)
+    k_parse_fix(const uint8_t *__restrict__ in, const uint16_t *__restrict__ link, const uint2 *__restrict__ mt,
+                uint32_t *__restrict__ sym_local, const int64_t *__restrict__ in_off, const int64_t *__restrict__ in_len,
+                const uint32_t *__restrict__ rnd_off, RoundRec *__restrict__ recs, uint32_t chunk, const uint32_t *__restrict__ hist,
+                const int64_t *__restrict__ bias, LevelParams lp, int strategy) {
+	extern __shared__ __align__(16) uint8_t smem[];
 	const int stream = blockIdx.x;
 	const uint32_t n = (uint32_t)in_len[stream];
 	if (n <= chunk) return; // a single chunk was parsed from the true initial state
@@ -544,20 +543,12 @@ __device__ __forceinline__ void parse_fix_body(uint8_t *smem, const uint8_t *__r
 		ParseCarry truth = rec_carry(rr[c0 / kRound - 1]); // exit of the previous chunk's last round, exact by induction
 		{
 			ParseCarry guess = clean_carry(c0);
-			bool recorded = false;
-			if (kLazyTab && ent) { // the tile kernel with a warm-up says which state its tile started from
-				const RoundRec e = (ent + rnd_off[stream])[c0 / kRound];
-				if (e.cnt) {
-					guess = rec_carry(e);
-					recorded = true;
-				}
-			}
-			if (!recorded) guess.last_top = truth.last_top; // irrelevant here: the chunk processes at least one loop top
+			guess.last_top = truth.last_top; // irrelevant here: the chunk processes at least one loop top
 			if (carry_equal(truth, guess)) continue; // the guess was right
 		}
 		for (uint32_t base = c0; base < c1; base += kRound) {
 			const ParseCarry old_exit = rec_carry(rr[base / kRound]);
-			const uint32_t cnt = parse_round<kLazyTab>(smem, in + off, link + off, mt + off, n, H, ab, base, lp, strategy, truth, sym_local + off + base);
+			const uint32_t cnt = parse_round(smem, in + off, link + off, mt + off, n, H, ab, base, lp, strategy, truth, sym_local + off + base);
 			__syncwarp();
 			if (threadIdx.x == 0) {
 				RoundRec r;
@@ -573,26 +564,6 @@ __device__ __forceinline__ void parse_fix_body(uint8_t *smem, const uint8_t *__r
 			if (carry_equal(truth, old_exit)) break; // re-synchronised: the rest of the chunk stands as parsed
 		}
 	}
-}
-
-__global__ void __launch_bounds__(32)
-    k_parse_fix(const uint8_t *__restrict__ in, const uint16_t *__restrict__ link, const uint2 *__restrict__ mt,
-                uint32_t *__restrict__ sym_local, const int64_t *__restrict__ in_off, const int64_t *__restrict__ in_len,
-                const uint32_t *__restrict__ rnd_off, RoundRec *__restrict__ recs, uint32_t chunk, const uint32_t *__restrict__ hist,
-                const int64_t *__restrict__ bias, LevelParams lp, int strategy) {
-	extern __shared__ __align__(16) uint8_t smem[];
-	parse_fix_body<false>(smem, in, link, mt, sym_local, in_off, in_len, rnd_off, recs, chunk, hist, bias, lp, strategy, nullptr);
-}
-
-// the fix-up behind the tile kernels (B200Z_TILE_PARSE): table entries they did not compute are searched on demand
-__global__ void __launch_bounds__(32)
-    k_parse_fix_lazy(const uint8_t *__restrict__ in, const uint16_t *__restrict__ link, const uint2 *__restrict__ mt,
-                     uint32_t *__restrict__ sym_local, const int64_t *__restrict__ in_off, const int64_t *__restrict__ in_len,
-                     const uint32_t *__restrict__ rnd_off, RoundRec *__restrict__ recs, uint32_t chunk,
-                     const uint32_t *__restrict__ hist, const int64_t *__restrict__ bias, LevelParams lp, int strategy,
-                     const RoundRec *__restrict__ ent) {
-	extern __shared__ __align__(16) uint8_t smem[];
-	parse_fix_body<true>(smem, in, link, mt, sym_local, in_off, in_len, rnd_off, recs, chunk, hist, bias, lp, strategy, ent);
 }
 
 // exclusive scan of the rounds' symbol counts of one stream; also the end-of-stream bookkeeping
@@ -694,8 +665,6 @@ __global__ void __launch_bounds__(128)
 		}
 	}
 }
-
-#include "experimental/k_tile_parse.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // Levels 1-4: DeflateFast.  The chains depend on the parse, so a stream is parsed serially by lane 0 with the
@@ -1125,22 +1094,15 @@ int deflate_plan_build(b200z_plan *p) {
 		const int64_t need = (maxlen / 1024 + kRound - 1) / kRound * kRound;
 		if (need > (int64_t)chunk) chunk = (uint32_t)need;
 	}
-	// B200Z_TILE_PARSE=1: k_tile_parse (search driven by the parse) instead of k_match + k_parse_chunk; the hand-off inside the
-	// kernel spans one tile, so tiles are the chunks k_parse_fix stitches -- streams of more than 1024 tiles keep the old path
-	// (1: k_tile_parse, every lane searches for itself; 2: k_tile_parse2, proxies + batched searches; 3: the same, 1024 threads; 4: 3 + warm-up for the tile's entry state)
-	// Opt-in until it has been measured on a B200 (written without GPU time left; bit-exact on tests/cuda_emu).
-	p->tile_parse = (lp.func == 2 && getenv("B200Z_TILE_PARSE") && maxlen <= 1024ll * kFTile) ? atoi(getenv("B200Z_TILE_PARSE")) : 0;
-	if (p->tile_parse < 1 || p->tile_parse > 4) p->tile_parse = 0;
 	// B200Z_LINK_RUN=<positions>: run length of k_links (a multiple of 32768, 65536 .. 1048576).  Every run but a stream's first
 	// re-walks 32768 positions to warm its head table up, so 64 Ki runs do 37 % more steps than the stream has positions on
-	// 256 KiB buffers and 128 Ki runs 12 %; fewer, longer CTAs on the other hand fill the last wave worse.  Opt-in like the
-	// search kernels until both have been timed on a B200 (tools/tile_parse_check.py times k_links under both).
+	// 256 KiB buffers and 128 Ki runs 12 %; fewer, longer CTAs on the other hand fill the last wave worse.  Measured on the
+	// B200 (profiles/README.md): 64 Ki runs 0.42 ms, 128 Ki runs 0.57 ms on 64 x 256 KiB -- the default stands.
 	p->link_run = kRun;
 	if (const char *e = getenv("B200Z_LINK_RUN")) {
 		const long v = atol(e);
 		if (v >= 65536 && v <= 1048576 && v % 32768 == 0) p->link_run = (int)v;
 	}
-	if (p->tile_parse) chunk = kFTile;
 	p->parse_chunk = chunk;
 	{
 		// levels 1-4: size of k_fast's prev[] table (see there)
@@ -1180,7 +1142,7 @@ int deflate_plan_build(b200z_plan *p) {
 		p->out_cap[i] = align_up(b200z_deflate_bound(len), kAlign);
 		oo += p->out_cap[i];
 		for (int64_t s = 0; s < len; s += p->link_run) runs.push_back(make_int2(i, (int)s));
-		for (int64_t s = 0; s < len; s += (p->tile_parse ? kFTile : kTile)) tiles.push_back(make_int2(i, (int)s));
+		for (int64_t s = 0; s < len; s += kTile) tiles.push_back(make_int2(i, (int)s));
 		for (int64_t s = 0; s < len; s += chunk)
 			chunks.push_back(ChunkDesc{i, (uint32_t)s, (uint32_t)(len - s > (int64_t)chunk ? s + chunk : len)});
 		rnd_off[i] = nrounds;
@@ -1259,7 +1221,6 @@ int deflate_plan_build(b200z_plan *p) {
 		p->o_rgroups = ws.reserve(8ll * (rgroups.size() + 1));
 		p->o_rnd_off = ws.reserve(4ll * (n + 1));
 		p->o_recs = ws.reserve((int64_t)sizeof(RoundRec) * (nrounds + 1));
-		if (p->tile_parse == 4) p->o_ent = ws.reserve((int64_t)sizeof(RoundRec) * (nrounds + 1)); // entry state of every tile
 		p->o_rnd_symoff = ws.reserve(4ll * (nrounds + 1));
 	}
 	if (lp.func != 0) p->o_sym = ws.reserve(4ll * io + 64);
@@ -1347,11 +1308,7 @@ int deflate_plan_build(b200z_plan *p) {
 	B200Z_CUDA(cudaFuncSetAttribute(k_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, kFastSmem));
 	B200Z_CUDA(cudaFuncSetAttribute(k_links, cudaFuncAttributeMaxDynamicSharedMemorySize, kLinksSmem));
 	B200Z_CUDA(cudaFuncSetAttribute(k_match, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileData + 2 * 2 * kTile));
-	B200Z_CUDA(cudaFuncSetAttribute(k_tile_parse, cudaFuncAttributeMaxDynamicSharedMemorySize, kFSmem));
-	B200Z_CUDA(cudaFuncSetAttribute((k_tile_parse2<kFThreads, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, kFSmem));
-	B200Z_CUDA(cudaFuncSetAttribute((k_tile_parse2<1024, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, kFSmem));
-	B200Z_CUDA(cudaFuncSetAttribute((k_tile_parse2<1024, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, kFSmem));
-	p->launches = (lp.func == 2 ? (p->tile_parse ? 8 : 9) : (lp.func == 1 ? 4 : 2)) + (p->wrap != B200Z_WRAP_RAW ? 3 : 0); // + one memset node
+	p->launches = (lp.func == 2 ? 9 : (lp.func == 1 ? 4 : 2)) + (p->wrap != B200Z_WRAP_RAW ? 3 : 0); // + one memset node
 	return B200Z_OK;
 }
 
@@ -1421,27 +1378,10 @@ int deflate_plan_run(b200z_plan *p, const uint8_t *d_in, uint8_t *d_out, int64_t
 		p->mark(s, "k_links");
 		if (p->n_runs) k_links<<<p->n_runs, kLinkThreads, kLinksSmem, s>>>(d_in, link, in_off, in_len, ws.at<int2>(p->o_run_desc), hist,
 			                                                         ws.at<uint8_t>(p->o_hmask), ws.at<int64_t>(p->o_hm_off), (uint32_t)p->link_run);
-		p->mark(s, p->tile_parse ? "k_tile_parse" : "k_match");
-		if (p->n_tiles && !p->tile_parse)
+		p->mark(s, "k_match");
+		if (p->n_tiles)
 			k_match<<<p->n_tiles, kMatchThreads, kTileData + 2 * 2 * kTile, s>>>(d_in, link, mt, in_off, in_len,
 			                                                                   ws.at<int2>(p->o_tile_desc), hist, bias, sym, lp);
-		if (p->n_tiles && p->tile_parse == 1) // (part of the SEARCH stage: it needs the whole shared memory like k_match)
-			k_tile_parse<<<p->n_tiles, kFThreads, kFSmem, s>>>(d_in, link, mt, ws.at<uint32_t>(p->o_sym_local), in_off, in_len,
-			                                                   ws.at<int2>(p->o_tile_desc), ws.at<uint32_t>(p->o_rnd_off),
-			                                                   ws.at<RoundRec>(p->o_recs), hist, bias, lp, p->strategy);
-		if (p->n_tiles && p->tile_parse == 2)
-			k_tile_parse2<kFThreads, false><<<p->n_tiles, kFThreads, kFSmem, s>>>(d_in, link, mt, ws.at<uint32_t>(p->o_sym_local), in_off, in_len,
-			                                                                      ws.at<int2>(p->o_tile_desc), ws.at<uint32_t>(p->o_rnd_off),
-			                                                                      ws.at<RoundRec>(p->o_recs), hist, bias, sym, lp, p->strategy, nullptr);
-		if (p->n_tiles && p->tile_parse == 3) // the same with 32 warps: the upper 16 only serve the batches
-			k_tile_parse2<1024, false><<<p->n_tiles, 1024, kFSmem, s>>>(d_in, link, mt, ws.at<uint32_t>(p->o_sym_local), in_off, in_len,
-			                                                            ws.at<int2>(p->o_tile_desc), ws.at<uint32_t>(p->o_rnd_off),
-			                                                            ws.at<RoundRec>(p->o_recs), hist, bias, sym, lp, p->strategy, nullptr);
-		if (p->n_tiles && p->tile_parse == 4) // 3 + the tile's entry from a 64-position warm-up, recorded for the fix-up
-			k_tile_parse2<1024, true><<<p->n_tiles, 1024, kFSmem, s>>>(d_in, link, mt, ws.at<uint32_t>(p->o_sym_local), in_off, in_len,
-			                                                           ws.at<int2>(p->o_tile_desc), ws.at<uint32_t>(p->o_rnd_off),
-			                                                           ws.at<RoundRec>(p->o_recs), hist, bias, sym, lp, p->strategy,
-			                                                           ws.at<RoundRec>(p->o_ent));
 		}
 		if (!do_encode) {
 			B200Z_CUDA(cudaGetLastError());
@@ -1453,16 +1393,11 @@ int deflate_plan_run(b200z_plan *p, const uint8_t *d_in, uint8_t *d_out, int64_t
 			const uint32_t *rnd_off = ws.at<uint32_t>(p->o_rnd_off);
 			RoundRec *recs = ws.at<RoundRec>(p->o_recs);
 			uint32_t *rnd_symoff = ws.at<uint32_t>(p->o_rnd_symoff);
-			if (p->n_chunks && !p->tile_parse)
+			if (p->n_chunks)
 				k_parse_chunk<<<p->n_chunks, 32, kParseSmem, s>>>(d_in, link, mt, sym_local, in_off, in_len, ws.at<ChunkDesc>(p->o_chunks),
 				                                                 rnd_off, recs, hist, bias, lp, p->strategy);
-			if (!p->tile_parse)
-				k_parse_fix<<<n, 32, kParseSmem, s>>>(d_in, link, mt, sym_local, in_off, in_len, rnd_off, recs, p->parse_chunk, hist, bias,
-				                                      lp, p->strategy);
-			else
-				k_parse_fix_lazy<<<n, 32, kParseSmem, s>>>(d_in, link, mt, sym_local, in_off, in_len, rnd_off, recs, p->parse_chunk, hist,
-				                                           bias, lp, p->strategy,
-				                                           p->tile_parse == 4 ? ws.at<RoundRec>(p->o_ent) : (const RoundRec *)nullptr);
+			k_parse_fix<<<n, 32, kParseSmem, s>>>(d_in, link, mt, sym_local, in_off, in_len, rnd_off, recs, p->parse_chunk, hist, bias,
+			                                      lp, p->strategy);
 			k_parse_scan<<<n, 256, 0, s>>>(d_in, in_off, in_len, rnd_off, recs, rnd_symoff, sym, nsyms, nblocks, blk_off, blk_start,
 			                               blk_ptop, hist, p->end_mode);
 			if (p->n_rgroups)

@@ -275,7 +275,9 @@ __device__ __forceinline__ bool span_step(const InfShared &sh, const uint32_t *w
 		const uint32_t de = lane_decode_sym(v, sh.dist, kDistRoot, sh.dist_sorted, sh.dist_c, 1, dnb);
 		const uint32_t dk = (de >> 4) & 15;
 		if (dk != K_DIST) {
-			if (pos + 15 > end_rel) s.fl |= F_OVERRUN; // diagnosed from bits past the end of the input
+			// (InflaterHuffmanTree.GetSymbol :181-235: an entry without a code is diagnosed once 9 bits can be peeked, a code for an
+			// illegal symbol once its own bits are there; with fewer bits the decoder waits for more input)
+			if (pos + (dk == K_ILLEGAL ? dnb : 9u) > end_rel) s.fl |= F_OVERRUN;
 			else { s.fl |= F_ERR; s.det = dk == K_ILLEGAL ? D_REP_DIST : D_CODELEN0; }
 			return false;
 		}
@@ -295,7 +297,7 @@ __device__ __forceinline__ bool span_step(const InfShared &sh, const uint32_t *w
 		else { s.fl |= F_EOB; s.pos = spos + nb; }
 		return false;
 	}
-	if (spos + 15 > end_rel) s.fl |= F_OVERRUN; // diagnosed from bits past the end of the input
+	if (spos + (k == K_ILLEGAL ? nb : 9u) > end_rel) s.fl |= F_OVERRUN;
 	else { s.fl |= F_ERR; s.det = k == K_ILLEGAL ? D_REP_LEN : D_CODELEN0; }
 	return false;
 }
@@ -896,6 +898,9 @@ int inflate_plan_build(b200z_plan *p) {
 		p->in_off[i] = comp - D;
 		dev_off[i] = comp;
 		dev_len[i] = p->in_len[i] - D;
+		p->comp_off.push_back(comp);
+		p->comp_cap.push_back(dev_len[i]);
+		p->dict_cap.push_back(D);
 		dict32[i] = (uint32_t)D;
 		io = comp + align_up(dev_len[i] + 16, kAlign);
 		io = align_up(io, kAlign);
@@ -1016,10 +1021,34 @@ int inflate_plan_build(b200z_plan *p) {
 		const int64_t slots = (int64_t)p->nwin_total + n, batches = p->round_cap / kRoundBatch;
 		p->dec1_grid = (int)(slots < (int64_t)sms * occ1 ? slots : (int64_t)sms * occ1);
 		p->dec2_grid = (int)(batches < (int64_t)sms * occ2 ? batches : (int64_t)sms * occ2);
-		p->find3_grid = sms * 4;
+		{
+			const int64_t want = ((int64_t)p->fs_cap + 127) / 128;
+			p->find3_grid = (int)(want < (int64_t)sms * 16 ? want : (int64_t)sms * 16);
+		}
 		extra = 7; // k_find, k_find3, k_seglist, k_dec1, k_chain, k_dec2, k_resolve (+ k_inflate for what they hand back)
 	}
 	p->launches = extra + (p->wrap == B200Z_WRAP_RAW ? 1 : (p->wrap == B200Z_WRAP_RAW_CRC32 ? 4 : 6));
+	return B200Z_OK;
+}
+
+int inflate_plan_stats(b200z_plan *p, uint32_t *v, int32_t cap, cudaStream_t s) {
+	uint32_t r[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+	if (p->inf_parallel && p->n) {
+		PCounters c;
+		std::vector<int32_t> fb((size_t)p->n);
+		B200Z_CUDA(cudaMemcpyAsync(&c, p->ws.at<PCounters>(p->o_ctr), sizeof(c), cudaMemcpyDeviceToHost, s));
+		B200Z_CUDA(cudaMemcpyAsync(fb.data(), p->ws.at<int32_t>(p->o_fallback), 4ull * p->n, cudaMemcpyDeviceToHost, s));
+		B200Z_CUDA(cudaStreamSynchronize(s));
+		r[0] = c.fs_count;
+		r[1] = c.nseg;
+		r[2] = c.round_top;
+		r[3] = c.n_blocks;
+		r[4] = c.n_rounds;
+		r[5] = c.n_passes;
+		for (int i = 0; i < p->n; i++) r[6] += fb[(size_t)i] != 0;
+		r[7] = 1;
+	}
+	for (int i = 0; i < cap && i < 8; i++) v[i] = r[i];
 	return B200Z_OK;
 }
 
@@ -1064,7 +1093,9 @@ int inflate_plan_run(b200z_plan *p, const uint8_t *d_in, uint8_t *d_out, int64_t
 		B200Z_CUDA(cudaMemsetAsync(cand, 0xFF, 4ull * p->nwin_total, s));
 		if (p->n_ftiles)
 			k_find<<<p->n_ftiles, 256, 0, s>>>(d_in, in_off, in_len, ws.at<FTile>(p->o_ftiles), start_bit, pre, fs_list, ctr, p->fs_cap);
+		p->mark(s, "k_find3");
 		k_find3<<<p->find3_grid, 128, 0, s>>>(d_in, in_off, in_len, fs_list, ctr, p->fs_cap, win_base, cand);
+		p->mark(s, "k_seglist");
 		const uint32_t slots = p->nwin_total + (uint32_t)n;
 		k_seglist<<<(slots + 255) / 256, 256, 0, s>>>(n, p->nwin_total, win_base, ws.at<uint32_t>(p->o_win_stream), cand, start_bit, pre, segs,
 		                                            seg_list, ctr);

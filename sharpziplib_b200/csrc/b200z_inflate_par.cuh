@@ -78,7 +78,8 @@ struct __align__(16) PBlockHdr {
 };
 
 struct PCounters {
-	uint32_t fs_count, nseg, seg_next, round_top, hdr_top, pad[3];
+	uint32_t fs_count, nseg, seg_next, round_top, hdr_top;
+	uint32_t n_rounds, n_passes, n_blocks; // statistics (b200z_plan_get_stats)
 };
 
 // ---------------------------------------------------------------------------------------------------------
@@ -93,13 +94,17 @@ __device__ __forceinline__ uint32_t ld_stream_word(const uint32_t *gwords, uint3
 	return w;
 }
 
-// Stages 1 and 2.  32 bit offsets at a time: the fixed header fields as bit-parallel masks over funnel-shifted words, then
-// the Kraft sum of the code-length code (a complete code: sum of 2^(7-len) = 128) through a table of four lengths at a time.
+// Stages 1 and 2.  32 bit offsets at a time: the fixed header fields as bit-parallel masks over funnel-shifted words; the
+// positions that pass (11 %) are compacted per warp so that every lane has one to test, then the Kraft sum of the
+// code-length code (a complete code: sum of 2^(7-len) = 128) through a table of four lengths at a time.
 __global__ void __launch_bounds__(256)
     k_find(const uint8_t *__restrict__ in, const int64_t *__restrict__ in_off, const int64_t *__restrict__ in_len,
            const FTile *__restrict__ tiles, const uint32_t *__restrict__ start_bit, const int32_t *__restrict__ pre,
            unsigned long long *__restrict__ fs_list, PCounters *__restrict__ ctr, uint32_t fs_cap) {
 	__shared__ uint8_t lut[4096];
+	__shared__ uint32_t sw[kFindTileWords + 4];
+	__shared__ uint16_t queue[8][1024];
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	for (int i = threadIdx.x; i < 4096; i += 256) {
 		uint32_t s = 0;
 		for (int j = 0; j < 4; j++) {
@@ -108,7 +113,6 @@ __global__ void __launch_bounds__(256)
 		}
 		lut[i] = (uint8_t)(s > 255u ? 255u : s);
 	}
-	__syncthreads();
 	const FTile t = tiles[blockIdx.x];
 	if (pre && pre[t.stream] != B200Z_OK) return;
 	const uint32_t *gwords = reinterpret_cast<const uint32_t *>(in + in_off[t.stream]);
@@ -116,39 +120,65 @@ __global__ void __launch_bounds__(256)
 	const uint32_t nwords = (nbytes + 3) >> 2;
 	const uint64_t sb = start_bit ? start_bit[t.stream] : 0u;
 	const uint64_t total_bits = 8ull * nbytes;
-	for (uint32_t k = threadIdx.x; k < t.nwords; k += 256) {
-		const uint32_t wi = t.word0 + k;
-		const uint32_t w0 = ld_stream_word(gwords, wi, nwords, nbytes), w1 = ld_stream_word(gwords, wi + 1, nwords, nbytes);
+	for (uint32_t i = threadIdx.x; i < t.nwords + 4; i += 256) sw[i] = ld_stream_word(gwords, t.word0 + i, nwords, nbytes);
+	__syncthreads();
+	uint16_t *q = queue[warp];
+	for (uint32_t base = (uint32_t)warp * 32u; base < t.nwords; base += 256u) {
+		const uint32_t k = base + (uint32_t)lane;
+		uint32_t mask = 0;
+		if (k < t.nwords) {
+			const uint32_t w0 = sw[k], w1 = sw[k + 1];
 #define B200Z_S(kk) __funnelshift_r(w0, w1, kk)
-		uint32_t mask = ~w0 & ~B200Z_S(1) & B200Z_S(2);                            // BFINAL = 0, BTYPE = 2 (bits 1, 2 = 0, 1)
-		if (mask) mask &= ~(B200Z_S(4) & B200Z_S(5) & B200Z_S(6) & B200Z_S(7));    // HLIT <= 29
-		if (mask) mask &= ~(B200Z_S(9) & B200Z_S(10) & B200Z_S(11) & B200Z_S(12)); // HDIST <= 29
+			mask = ~w0 & ~B200Z_S(1) & B200Z_S(2);                           // BFINAL = 0, BTYPE = 2 (bits 1, 2 = 0, 1)
+			mask &= ~(B200Z_S(4) & B200Z_S(5) & B200Z_S(6) & B200Z_S(7));    // HLIT <= 29
+			mask &= ~(B200Z_S(9) & B200Z_S(10) & B200Z_S(11) & B200Z_S(12)); // HDIST <= 29
 #undef B200Z_S
-		const uint64_t wbit = 32ull * wi;
-		if (wbit + 32 <= sb) continue;
-		if (wbit <= sb) { // nothing in front of the stream's first block header, and not that header itself (segment 0 has it)
-			const uint32_t cut = (uint32_t)(sb - wbit) + 1;
-			mask = cut >= 32 ? 0u : (mask >> cut) << cut;
+			const uint64_t wbit = 32ull * (t.word0 + k);
+			if (wbit + 32 <= sb) mask = 0;
+			else if (wbit <= sb) { // nothing in front of the stream's first block header, and not that header itself (segment 0 has it)
+				const uint32_t cut = (uint32_t)(sb - wbit) + 1;
+				mask = cut >= 32 ? 0u : (mask >> cut) << cut;
+			}
 		}
-		if (!mask) continue;
-		const uint32_t w2 = ld_stream_word(gwords, wi + 2, nwords, nbytes), w3 = ld_stream_word(gwords, wi + 3, nwords, nbytes);
-		const uint64_t lo = (uint64_t)w0 | ((uint64_t)w1 << 32), hi = (uint64_t)w2 | ((uint64_t)w3 << 32);
-		while (mask) {
-			const uint32_t o = (uint32_t)__ffs((int)mask) - 1u;
-			mask &= mask - 1u;
-			const uint32_t sh = o + 13; // HCLEN and the code-length code's lengths: 4 + 57 bits
-			uint64_t v = (lo >> sh) | (hi << (64 - sh));
-			const uint32_t nmeta = (uint32_t)(v & 15u) + 4u;
-			v >>= 4;
-			v &= (1ull << (3 * nmeta)) - 1ull;
-			const uint32_t sum = (uint32_t)lut[v & 4095u] + lut[(v >> 12) & 4095u] + lut[(v >> 24) & 4095u] + lut[(v >> 36) & 4095u] +
-			                     lut[(v >> 48) & 4095u];
+		const uint32_t cnt = (uint32_t)__popc(mask);
+		uint32_t incl = cnt;
+		for (int o = 1; o < 32; o <<= 1) {
+			const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+			if (lane >= o) incl += v;
+		}
+		const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+		{
+			uint32_t pos = incl - cnt, m = mask;
+			while (m) {
+				const uint32_t o = (uint32_t)__ffs((int)m) - 1u;
+				m &= m - 1u;
+				q[pos++] = (uint16_t)(((uint32_t)lane << 5) | o);
+			}
+		}
+		__syncwarp();
+		for (uint32_t e = (uint32_t)lane; e < total; e += 32u) {
+			const uint32_t ent = q[e];
+			const uint32_t wl = base + (ent >> 5), o = ent & 31u;
+			const uint32_t sh = o + 13u; // HCLEN and the code-length code's lengths: 4 + 57 bits from here
+			const bool lowh = sh < 32u;
+			const uint32_t a = lowh ? sw[wl] : sw[wl + 1], b = lowh ? sw[wl + 1] : sw[wl + 2], c = lowh ? sw[wl + 2] : sw[wl + 3];
+			uint32_t v0 = __funnelshift_r(a, b, sh), v1 = __funnelshift_r(b, c, sh);
+			const uint32_t nmeta = (v0 & 15u) + 4u;
+			const uint32_t nb = 4u + 3u * nmeta; // 16 .. 61 bits in use
+			if (nb >= 32u) v1 &= (1u << (nb - 32u)) - 1u;
+			else {
+				v1 = 0;
+				v0 &= (1u << nb) - 1u;
+			}
+			const uint32_t sum = (uint32_t)lut[(v0 >> 4) & 4095u] + lut[(v0 >> 16) & 4095u] + lut[__funnelshift_r(v0, v1, 28) & 4095u] +
+			                     lut[(v1 >> 8) & 4095u] + lut[(v1 >> 20) & 4095u];
 			if (sum != 128u) continue;
-			const uint64_t pos = wbit + o;
+			const uint64_t pos = 32ull * (t.word0 + wl) + o;
 			if (pos + 17 + 3 * nmeta > total_bits) continue;
 			const uint32_t idx = atomicAdd(&ctr->fs_count, 1u);
 			if (idx < fs_cap) fs_list[idx] = ((unsigned long long)t.stream << 40) | pos;
 		}
+		__syncwarp();
 	}
 }
 
@@ -158,6 +188,7 @@ __global__ void __launch_bounds__(128)
     k_find3(const uint8_t *__restrict__ in, const int64_t *__restrict__ in_off, const int64_t *__restrict__ in_len,
             const unsigned long long *__restrict__ fs_list, const PCounters *__restrict__ ctr, uint32_t fs_cap,
             const uint32_t *__restrict__ win_base, uint32_t *__restrict__ cand) {
+	__shared__ uint8_t s_tab[128 * 128];
 	uint32_t count = ctr->fs_count;
 	if (count > fs_cap) count = fs_cap;
 	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
@@ -180,16 +211,20 @@ __global__ void __launch_bounds__(128)
 		}
 		br.get(3);
 		const int nlit = (int)br.get(5) + 257, ndist = (int)br.get(5) + 1, nmeta = (int)br.get(4) + 4;
-		uint8_t ml[19];
-		for (int k = 0; k < 19; k++) ml[k] = 0;
-		for (int k = 0; k < nmeta; k++) ml[c_meta_order[k]] = (uint8_t)br.get(3);
-		// 7-bit decode table of the code-length code: sym << 3 | len
-		uint8_t tab[128];
-		for (int k = 0; k < 128; k++) tab[k] = 0;
+		// the code-length code's lengths, 3 bits each, kept in one word per ten symbols
+		uint32_t mlo = 0, mhi = 0; // symbol s: bits 3 (s % 10) of (s < 10 ? mlo : mhi)
+		for (int k = 0; k < nmeta; k++) {
+			const uint32_t sym = c_meta_order[k], v = br.get(3);
+			if (sym < 10) mlo |= v << (3 * sym);
+			else mhi |= v << (3 * (sym - 10));
+		}
+		// 7-bit decode table of the code-length code in shared memory: sym << 3 | len; column tid of a [128][128] byte array
+		uint8_t *tab = s_tab + threadIdx.x;
+		for (int k = 0; k < 128; k++) tab[k * 128] = 0;
 		{
 			uint32_t cnt[8], nxt[8];
 			for (int L = 0; L < 8; L++) cnt[L] = 0;
-			for (int s = 0; s < 19; s++) cnt[ml[s]]++;
+			for (int s = 0; s < 19; s++) cnt[((s < 10 ? mlo >> (3 * s) : mhi >> (3 * (s - 10))) & 7u)]++;
 			cnt[0] = 0;
 			uint32_t code = 0;
 			for (int L = 1; L <= 7; L++) {
@@ -197,11 +232,11 @@ __global__ void __launch_bounds__(128)
 				code = (code + cnt[L]) << 1;
 			}
 			for (int s = 0; s < 19; s++) {
-				const int L = ml[s];
+				const uint32_t L = (s < 10 ? mlo >> (3 * s) : mhi >> (3 * (s - 10))) & 7u;
 				if (!L) continue;
 				const uint32_t c = nxt[L]++;
 				const uint32_t rev = __brev(c) >> (32 - L);
-				for (uint32_t k = rev; k < 128u; k += (1u << L)) tab[k] = (uint8_t)((s << 3) | L);
+				for (uint32_t k = rev; k < 128u; k += (1u << L)) tab[k * 128] = (uint8_t)((s << 3) | L);
 			}
 		}
 		const int total = nlit + ndist;
@@ -210,7 +245,7 @@ __global__ void __launch_bounds__(128)
 		bool ok = true;
 		while (ok && idx < total) {
 			br.refill();
-			const uint32_t te = tab[br.peek(7)];
+			const uint32_t te = tab[br.peek(7) * 128];
 			if (!te) { ok = false; break; }
 			br.drop((int)(te & 7u));
 			const int sym = (int)(te >> 3);
@@ -368,58 +403,78 @@ __device__ __forceinline__ void static_lens(uint8_t *lens) { // InflaterHuffmanT
 // span decode without per-lane caps.  MODE 0 counts; MODE 1 stores literals at out[o0 + o] and back-references at
 // ml[nm] (output positions relative to the stream).
 // ---------------------------------------------------------------------------------------------------------
+// One symbol per call, the common cases without a branch: the lanes of a warp step together, and with 32 of them some
+// lane always holds a literal and some lane a back-reference, so both paths would be paid for anyway.  Every lane peeks
+// twice (the literal/length code, and what follows its extra bits -- the distance code if it was a length) and selects.
+// Codes longer than the root tables, end of block and the error cases leave through rare branches.
+__device__ uint32_t long_code(uint32_t v, const uint16_t *sorted, const Canon &cn, int R, int kind) {
+	const uint32_t x = __brev(v) >> 17; // next 15 stream bits, first bit most significant
+	for (int L = R + 1; L <= 15; L++) {
+		const uint32_t c = x >> (15 - L);
+		const uint32_t idx = c - cn.first[L];
+		if (idx < cn.count[L]) {
+			const uint32_t s = sorted[cn.offs[L] + idx];
+			return kind == 0 ? litlen_entry(s, (uint32_t)L) : dist_entry(s, (uint32_t)L);
+		}
+	}
+	return 0; // K_INVALID, nb = 0
+}
+
 template <int MODE>
 __device__ __forceinline__ bool span_step2(const InfShared &sh, const uint32_t *words, Span &s, uint32_t limit, uint32_t end_rel,
                                            uint8_t *out, uint64_t o0, MatchTok *ml) {
 	const uint32_t spos = s.pos;
 	if (spos >= limit) return false;
-	uint32_t v = peek32(words, spos);
-	uint32_t nb;
-	const uint32_t e = lane_decode_sym(v, sh.lit, kLitRoot, sh.lit_sorted, sh.lit_c, 0, nb);
-	const uint32_t k = (e >> 4) & 15;
-	if (k == K_LIT) {
-		if (spos + nb > end_rel) { s.fl |= F_OVERRUN; return false; }
-		if (MODE) out[o0 + s.o] = (uint8_t)(e >> 16);
-		++s.o;
-		s.pos = spos + nb;
-		return true;
-	}
-	if (k == K_LEN) {
-		const uint32_t xb = (e >> 8) & 15;
-		const uint32_t len = (e >> 16) + ((v >> nb) & ((1u << xb) - 1u));
-		uint32_t pos = spos + nb + xb;
-		v = peek32(words, pos);
-		uint32_t dnb;
-		const uint32_t de = lane_decode_sym(v, sh.dist, kDistRoot, sh.dist_sorted, sh.dist_c, 1, dnb);
-		const uint32_t dk = (de >> 4) & 15;
-		if (dk != K_DIST) {
-			if (pos + 15 > end_rel) s.fl |= F_OVERRUN; // diagnosed from bits past the end of the input
-			else { s.fl |= F_ERR; s.det = dk == K_ILLEGAL ? D_REP_DIST : D_CODELEN0; }
-			return false;
-		}
-		const uint32_t dxb = (de >> 8) & 15;
-		const uint32_t dist = (de >> 16) + ((v >> dnb) & ((1u << dxb) - 1u));
-		pos += dnb + dxb;
-		if (pos > end_rel) { s.fl |= F_OVERRUN; return false; }
+	const uint32_t v = peek32(words, spos);
+	uint32_t e = sh.lit[v & ((1u << kLitRoot) - 1u)];
+	if (((e >> 4) & 15u) == K_LONG) e = long_code(v, sh.lit_sorted, sh.lit_c, kLitRoot, 0);
+	const uint32_t k = (e >> 4) & 15u, nb = e & 15u, xb = (e >> 8) & 15u;
+	const uint32_t val = (e >> 16) + ((v >> nb) & ((1u << xb) - 1u)); // the literal, or the length with its extra bits
+	const uint32_t pos1 = spos + nb + xb;
+	const uint32_t v2 = peek32(words, pos1);
+	uint32_t de = sh.dist[v2 & ((1u << kDistRoot) - 1u)];
+	if (k == K_LEN && ((de >> 4) & 15u) == K_LONG) de = long_code(v2, sh.dist_sorted, sh.dist_c, kDistRoot, 1);
+	const uint32_t dk = (de >> 4) & 15u, dnb = de & 15u, dxb = (de >> 8) & 15u;
+	const uint32_t dist = (de >> 16) + ((v2 >> dnb) & ((1u << dxb) - 1u));
+	const bool lit = k == K_LIT, rep = (k == K_LEN) & (dk == K_DIST);
+	if (lit | rep) {
+		const uint32_t npos = lit ? pos1 : pos1 + dnb + dxb;
+		if (npos > end_rel) { s.fl |= F_OVERRUN; return false; }
 		if (MODE) {
-			MatchTok t;
-			t.out_pos = (uint32_t)(o0 + s.o);
-			t.len = (uint16_t)len;
-			t.dist = (uint16_t)(dist & 0xFFFFu); // 32768 fits
-			ml[s.nm] = t;
+			if (lit) out[o0 + s.o] = (uint8_t)val;
+			else {
+				MatchTok t;
+				t.out_pos = (uint32_t)(o0 + s.o);
+				t.len = (uint16_t)val;
+				t.dist = (uint16_t)(dist & 0xFFFFu); // 32768 fits
+				ml[s.nm] = t;
+			}
 		}
-		++s.nm;
-		s.o += len;
-		s.pos = pos;
+		s.nm += rep ? 1u : 0u;
+		s.o += lit ? 1u : val;
+		s.pos = npos;
 		return true;
 	}
+	// ---- the rare rest: end of block, invalid or illegal codes (Inflater.cs:318-326, :351-359; InflaterHuffmanTree.cs:190-193)
 	if (k == K_EOB) {
 		if (spos + nb > end_rel) s.fl |= F_OVERRUN;
 		else { s.fl |= F_EOB; s.pos = spos + nb; }
 		return false;
 	}
-	if (spos + 15 > end_rel) s.fl |= F_OVERRUN; // diagnosed from bits past the end of the input
-	else { s.fl |= F_ERR; s.det = k == K_ILLEGAL ? D_REP_LEN : D_CODELEN0; }
+	// Invalid codes near the end of the input, as the reference classifies them (InflaterHuffmanTree.GetSymbol :181-235): a
+	// table entry without a code is diagnosed as soon as 9 bits can be peeked; a code for an illegal symbol (286, 287,
+	// distance 30, 31) once its own bits are there; with fewer bits the decoder waits for more input.
+	if (k == K_LEN) { // the distance code is the problem (its length's extra bits come first: without them, wait)
+		const uint32_t need = dk == K_ILLEGAL ? dnb : 9u;
+		if (pos1 + need > end_rel) s.fl |= F_OVERRUN;
+		else { s.fl |= F_ERR; s.det = dk == K_ILLEGAL ? D_REP_DIST : D_CODELEN0; }
+		return false;
+	}
+	{
+		const uint32_t need = k == K_ILLEGAL ? nb : 9u;
+		if (spos + need > end_rel) s.fl |= F_OVERRUN;
+		else { s.fl |= F_ERR; s.det = k == K_ILLEGAL ? D_REP_LEN : D_CODELEN0; }
+	}
 	return false;
 }
 
@@ -437,7 +492,7 @@ struct __align__(16) Dec1Shared {
 	unsigned long long h_bitpos;
 	uint32_t h_stored_len;
 	uint32_t q_idx, a_base;
-	int stop_lane;
+	int stop[2];
 };
 
 __device__ __forceinline__ void stage_round(uint32_t *words, const uint32_t *gwords, uint32_t w0, uint32_t nwords, uint32_t nbytes) {
@@ -631,7 +686,10 @@ __global__ void __launch_bounds__(kP1Threads)
 					break;
 				}
 			}
-			if (tid == 0) S.a_base = atomicAdd(&ctr->hdr_top, 1u);
+			if (tid == 0) {
+				S.a_base = atomicAdd(&ctr->hdr_top, 1u);
+				atomicAdd(&ctr->n_blocks, 1u);
+			}
 			__syncthreads();
 			const uint32_t hdr_idx = S.a_base;
 			if (hdr_idx >= hdr_cap) {
@@ -651,6 +709,7 @@ __global__ void __launch_bounds__(kP1Threads)
 			bool in_block = true;
 			while (in_block) {
 				__syncthreads();
+				if (tid == 0) S.stop[0] = S.stop[1] = kP1Threads - 1;
 				const uint32_t w0 = (uint32_t)(bitpos >> 5);
 				stage_round(S.in, gwords, w0, nwords, nbytes);
 				__syncthreads();
@@ -662,7 +721,13 @@ __global__ void __launch_bounds__(kP1Threads)
 				uint32_t entry = r0 + (uint32_t)tid * kSubBits;
 				uint32_t obytes = 0, nmatch = 0, flags = 0;
 				bool changed = true, dead = false;
-				for (int it = 0; it < kP1Threads + 2; it++) {
+				uint32_t passes = 0;
+				int lastlane = kP1Threads - 1;
+				// Lane 0 starts at the true position, the others at a guess; every pass a lane whose entry moved (to the
+				// previous lane's exit) decodes again.  The first lane that stops the block (end of block, error, end of
+				// input) kills the lanes behind it at once: S.stop[pass parity] collects the lowest such lane.
+				for (int it = 0; it < 2 * kP1Threads + 4; it++) {
+					++passes;
 					Span sp;
 					bool act = changed && !dead;
 					if (changed) {
@@ -684,23 +749,31 @@ __global__ void __launch_bounds__(kP1Threads)
 						S.flags[tid] = sp.fl;
 						S.dets[tid] = sp.det;
 					}
+					if (flags & (F_EOB | F_ERR | F_OVERRUN)) atomicMin(&S.stop[it & 1], tid);
+					if (tid == 0) S.stop[(it + 1) & 1] = kP1Threads - 1; // (last read before the previous pass's second barrier)
 					__syncthreads();
-					changed = false;
-					if (tid > 0) {
-						const uint32_t pe = S.exitp[tid - 1], pf = S.flags[tid - 1];
-						const bool nd = pf != 0; // the previous lane ended the block, failed or is dead itself
-						changed = (pe != entry) || (nd != dead);
+					lastlane = S.stop[it & 1];
+					const bool nd = tid > lastlane;
+					changed = nd != dead;
+					dead = nd;
+					if (tid > 0 && !nd) { // (a dead lane's entry does not matter; it is taken afresh should the lane come back)
+						const uint32_t pe = S.exitp[tid - 1];
+						if (pe != entry) changed = true;
 						entry = pe;
-						dead = nd;
 					}
+#ifdef B200Z_DEBUG_PASSES
+					{
+						const int nch = __syncthreads_count(changed ? 1 : 0);
+						if (tid == 0) printf("  pass %d: changed %d lastlane %d\n", it, nch, lastlane);
+					}
+#endif
 					if (!__syncthreads_or(changed ? 1 : 0)) break;
 				}
+				if (tid == 0) {
+					atomicAdd(&ctr->n_rounds, 1u);
+					atomicAdd(&ctr->n_passes, passes);
+				}
 				// lanes up to and including the first one that stopped the block are exact; the rest are dead
-				if (tid == 0) S.stop_lane = kP1Threads - 1;
-				__syncthreads();
-				if (flags & (F_EOB | F_ERR | F_OVERRUN)) atomicMin(&S.stop_lane, tid);
-				__syncthreads();
-				const int lastlane = S.stop_lane;
 				if (tid > lastlane) {
 					obytes = 0;
 					nmatch = 0;
@@ -936,12 +1009,19 @@ __global__ void __launch_bounds__(kP1Threads)
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// k_resolve: back-references, one CTA per stream, 16 KiB tiles in stream order
+// k_resolve: back-references, one CTA per stream, 16 KiB tiles in stream order.  The last 64 KiB of the stream's output
+// live in a shared-memory ring (ring[a & 65535] = output byte a; bytes in front of the stream: the preset dictionary's
+// tail, else zeros -- a fresh reference window holds zeros, trap T13), so every source byte of a back-reference is a
+// shared-memory read: sources in front of the tile are final, sources inside the tile are resolved by pointer jumping.
 // ---------------------------------------------------------------------------------------------------------
+constexpr int kResRing = 65536;
+constexpr int kResChunk = 1536; // back-references staged at a time
 struct __align__(16) ResShared {
-	uint8_t val[kResTile];
-	uint16_t ptr[kResTile];
-	MatchTok mch[kResThreads];
+	uint8_t ring[kResRing];
+	uint16_t ptr[kResTile];        // for a byte that is a copy: ring index of its source (of a byte further back after a jump)
+	uint16_t copied[kResThreads];  // bit b of copied[t]: byte 16 t + b of the tile is a copy
+	MatchTok mch[kResChunk];
+	int cnt_in, cnt_done;
 };
 
 __global__ void __launch_bounds__(kResThreads)
@@ -953,97 +1033,177 @@ __global__ void __launch_bounds__(kResThreads)
 	const int stream = blockIdx.x;
 	if (stream >= n || fallback[stream]) return;
 	const uint32_t nm = str_nm[stream];
-	if (nm == 0) return;
+	if (nm == 0) return; // no back-reference: the literals are in place
 	const int tid = threadIdx.x;
 	uint8_t *dst = out + out_off[stream];
 	const int64_t total = out_len[stream];
 	const MatchTok *ml = mlist + mt_off[stream];
-	const uint32_t D = dict_len[stream];
-	const uint8_t *dict = in + in_off[stream] - D; // the preset dictionary's tail lies in front of the compressed bytes
+	{
+		// what lies in front of the stream: ring[65536 - k] = byte -k
+		const uint32_t D = dict_len[stream];
+		const uint8_t *dict = in + in_off[stream] - D; // the preset dictionary's tail lies in front of the compressed bytes
+		for (int i = tid; i < kResRing / 2; i += kResThreads) {
+			const int k = kResRing / 2 - i; // 32768 .. 1 bytes in front of position 0
+			S.ring[kResRing - k] = (uint32_t)k <= D ? dict[D - (uint32_t)k] : (uint8_t)0;
+		}
+	}
 	uint32_t cur_m = 0;
-	for (int64_t T0 = 0; T0 < total && cur_m < nm; T0 += kResTile) {
+	const uint4 zero4 = make_uint4(0, 0, 0, 0);
+	// software pipeline: the next tile's bytes (as k_dec2 left them: literals in place) and the next chunk of
+	// back-references are loaded while the current tile is resolved
+	uint4 nxt_tile = zero4;
+	if ((int64_t)tid * 16 + 16 <= total) nxt_tile = *reinterpret_cast<const uint4 *>(dst + tid * 16);
+	MatchTok none;
+	none.out_pos = 0xFFFFFFFFu;
+	none.len = 0;
+	none.dist = 0;
+	MatchTok nxt_m0 = none, nxt_m1 = none; // entries tid and 1024 + tid of the next chunk
+	if ((uint32_t)tid < nm) nxt_m0 = ml[tid];
+	if (tid < kResChunk - kResThreads && (uint32_t)(kResThreads + tid) < nm) nxt_m1 = ml[kResThreads + tid];
+	const int a0 = tid * 16; // this thread's 16 bytes of the tile
+	for (int64_t T0 = 0; T0 < total; T0 += kResTile) {
 		const int tl = (int)(total - T0 < (int64_t)kResTile ? total - T0 : (int64_t)kResTile);
 		const int64_t T1 = T0 + tl;
-		if ((int64_t)ml[cur_m].out_pos >= T1) continue; // no back-reference touches this tile: the literals are in place
-		__syncthreads();
-		// the tile as k_dec2 left it (literals in place), every byte its own source
-		if (tid * 16 + 16 <= tl) {
-			*reinterpret_cast<uint4 *>(S.val + tid * 16) = *reinterpret_cast<const uint4 *>(dst + T0 + tid * 16);
+		const uint32_t rbase = (uint32_t)T0 & (uint32_t)(kResRing - 1);
+		__syncthreads(); // the previous tile is resolved and written back
+		if (a0 + 16 <= tl) {
+			*reinterpret_cast<uint4 *>(S.ring + rbase + a0) = nxt_tile;
 		} else {
-			for (int i = tid * 16; i < tl && i < tid * 16 + 16; i++) S.val[i] = dst[T0 + i];
+			for (int i = a0; i < tl && i < a0 + 16; i++) S.ring[rbase + i] = dst[T0 + i];
 		}
-		for (int i = tid; i < kResTile; i += kResThreads) S.ptr[i] = (uint16_t)i;
-		__syncthreads();
-		// back-references that reach into the tile, 1024 at a time, each expanded by a group of eight lanes
+		{
+			const int64_t a = T1 + (int64_t)a0;
+			nxt_tile = a + 16 <= total ? *reinterpret_cast<const uint4 *>(dst + a) : zero4;
+		}
+		if (cur_m >= nm) break; // nothing left to resolve (the remaining tiles are literals only)
+		uint32_t mine = 0; // which of this thread's bytes are copies
+		bool any = false;
+		// ---- the back-references that reach into the tile, a chunk at a time; every thread fills in its own 16 bytes ----
 		for (;;) {
-			const uint32_t mi = cur_m + (uint32_t)tid;
-			MatchTok m;
-			m.out_pos = 0xFFFFFFFFu;
-			m.len = 0;
-			m.dist = 0;
-			if (mi < nm) m = ml[mi];
-			const bool in_tile = mi < nm && (int64_t)m.out_pos < T1;
-			const bool done = in_tile && (int64_t)m.out_pos + m.len <= T1;
-			const int n_in = __syncthreads_count(in_tile ? 1 : 0);
-			const int n_done = __syncthreads_count(done ? 1 : 0);
-			S.mch[tid] = m;
+			if (tid == 0) {
+				S.cnt_in = 0;
+				S.cnt_done = 0;
+			}
 			__syncthreads();
-			const int grp = tid >> 3, sub = tid & 7;
-			for (int j = grp; j < n_in; j += kResThreads / 8) {
-				const MatchTok g = S.mch[j];
-				const int len = g.len;
-				const int dist = g.dist ? (int)g.dist : 65536; // (never 0 for a decoded back-reference; guards the modulo)
-				const int64_t dl64 = (int64_t)g.out_pos - T0;
-				const int dl = (int)dl64; // may be negative: the reference started in the previous tile
-				int k = sub;
-				if (dl < 0) k += (-dl) & ~7; // first step whose bytes can lie in the tile
-				for (; k < len; k += 8) {
-					const int p = dl + k;
-					if (p < 0) continue;
-					if (p >= tl) break;
-					const int so = dist >= len ? k : k % dist; // OutputWindow.Repeat: byte k comes from source byte k mod distance
-					const int sl = dl - dist + so;
-					if (sl >= 0) {
-						S.ptr[p] = S.ptr[sl]; // (an ancestor of sl, whatever the other groups have written so far)
-					} else {
-						const int64_t ab = T0 + sl;
-						uint8_t b = 0;
-						if (ab >= 0) b = dst[ab];                      // final: an earlier tile
-						else if (-ab <= (int64_t)D) b = dict[(int64_t)D + ab]; // preset dictionary (OutputWindow.CopyDict)
-						S.val[p] = b;                                  // (else: a fresh window holds zeros, trap T13)
+			{
+				const uint32_t mi0 = cur_m + (uint32_t)tid, mi1 = cur_m + (uint32_t)(kResThreads + tid);
+				int ci = 0, cd = 0;
+				S.mch[tid] = nxt_m0;
+				if (mi0 < nm && (int64_t)nxt_m0.out_pos < T1) {
+					ci++;
+					cd += (int64_t)nxt_m0.out_pos + nxt_m0.len <= T1;
+				}
+				if (tid < kResChunk - kResThreads) {
+					S.mch[kResThreads + tid] = nxt_m1;
+					if (mi1 < nm && (int64_t)nxt_m1.out_pos < T1) {
+						ci++;
+						cd += (int64_t)nxt_m1.out_pos + nxt_m1.len <= T1;
 					}
 				}
+				// (block-wide sums of two small counts)
+				for (int o = 16; o > 0; o >>= 1) {
+					ci += __shfl_xor_sync(0xffffffffu, ci, o);
+					cd += __shfl_xor_sync(0xffffffffu, cd, o);
+				}
+				if ((tid & 31) == 0 && ci) {
+					atomicAdd(&S.cnt_in, ci);
+					atomicAdd(&S.cnt_done, cd);
+				}
 			}
+			__syncthreads();
+			const int n_in = S.cnt_in, n_done = S.cnt_done;
 			cur_m += (uint32_t)n_done;
-			__syncthreads();
-			if (!(n_in == kResThreads && n_done == kResThreads)) break;
-		}
-		// pointer jumping until every byte points at a byte that is its own source
-		for (;;) {
-			int changed = 0;
-			for (int i = tid; i < tl; i += kResThreads) {
-				const uint16_t q = S.ptr[i];
-				if (q != (uint16_t)i) {
-					const uint16_t r = S.ptr[q];
-					if (r != q) {
-						S.ptr[i] = r;
-						changed = 1;
+			{
+				const uint32_t ni0 = cur_m + (uint32_t)tid, ni1 = cur_m + (uint32_t)(kResThreads + tid);
+				nxt_m0 = ni0 < nm ? ml[ni0] : none;
+				nxt_m1 = (tid < kResChunk - kResThreads && ni1 < nm) ? ml[ni1] : none;
+			}
+			if (n_in) {
+				any = true;
+				const int lo = (int)((int64_t)S.mch[0].out_pos - T0);
+				const MatchTok lastm = S.mch[n_in - 1];
+				const int hi = (int)((int64_t)lastm.out_pos - T0) + lastm.len;
+				if (a0 + 16 > lo && a0 < hi && a0 < tl) {
+					// the last back-reference that starts at or in front of this thread's first byte
+					int j = 0;
+					{
+						int l = 0, r = n_in; // invariant: starts of [0, l) <= a0 < starts of [r, n_in)
+						const int64_t key = T0 + a0;
+						while (l < r) {
+							const int mid = (l + r) >> 1;
+							if ((int64_t)S.mch[mid].out_pos <= key) l = mid + 1;
+							else r = mid;
+						}
+						j = l > 0 ? l - 1 : 0;
+					}
+					const int aend = a0 + 16 < tl ? a0 + 16 : tl;
+					for (; j < n_in; j++) {
+						const MatchTok g = S.mch[j];
+						const int dl = (int)((int64_t)g.out_pos - T0); // may be negative: the reference started in the previous tile
+						if (dl >= aend) break;
+						const int len = g.len, dist = g.dist ? (int)g.dist : 65536; // (never 0 for a decoded back-reference)
+						int p = dl > a0 ? dl : a0;
+						const int pe = dl + len < aend ? dl + len : aend;
+						const uint32_t sbase = rbase + (uint32_t)(dl - dist); // ring position of the source's first byte (mod 65536)
+						if (dist >= len) {
+							for (; p < pe; p++) {
+								S.ptr[p] = (uint16_t)(sbase + (uint32_t)(p - dl));
+								mine |= 1u << (p - a0);
+							}
+						} else { // OutputWindow.Repeat: byte k comes from source byte k mod distance
+							int so = (p - dl) % dist;
+							for (; p < pe; p++) {
+								S.ptr[p] = (uint16_t)(sbase + (uint32_t)so);
+								mine |= 1u << (p - a0);
+								if (++so == dist) so = 0;
+							}
+						}
 					}
 				}
 			}
-			if (!__syncthreads_or(changed)) break;
+			__syncthreads();
+			if (!(n_in == kResChunk && n_done == kResChunk)) break;
 		}
-		// write the tile back
-		if (tid * 16 + 16 <= tl) {
-			uint32_t w[4];
-			for (int q = 0; q < 4; q++) {
-				uint32_t x = 0;
-				for (int b = 0; b < 4; b++) x |= (uint32_t)S.val[S.ptr[tid * 16 + q * 4 + b]] << (8 * b);
-				w[q] = x;
+		if (!any) continue; // no back-reference touches this tile
+		S.copied[tid] = (uint16_t)mine;
+		__syncthreads();
+		// a copy whose source is itself a copy inside the tile is not final yet
+		uint32_t unres = 0;
+		for (uint32_t mm = mine; mm; mm &= mm - 1u) {
+			const int b = __ffs((int)mm) - 1;
+			const uint32_t ql = ((uint32_t)S.ptr[a0 + b] - rbase) & (uint32_t)(kResRing - 1);
+			if (ql < (uint32_t)tl && ((S.copied[ql >> 4] >> (ql & 15u)) & 1u)) unres |= 1u << b;
+		}
+		// pointer jumping: a byte takes over its source's source until that is a final byte
+		while (__syncthreads_or(unres != 0)) {
+			for (uint32_t mm = unres; mm; mm &= mm - 1u) {
+				const int b = __ffs((int)mm) - 1;
+				const uint32_t ql = ((uint32_t)S.ptr[a0 + b] - rbase) & (uint32_t)(kResRing - 1);
+				const uint32_t r = S.ptr[ql]; // (whatever ql's owner has made of it by now: always a byte ql is a copy of)
+				S.ptr[a0 + b] = (uint16_t)r;
+				const uint32_t rl = (r - rbase) & (uint32_t)(kResRing - 1);
+				if (!(rl < (uint32_t)tl && ((S.copied[rl >> 4] >> (rl & 15u)) & 1u))) unres &= ~(1u << b);
 			}
-			*reinterpret_cast<uint4 *>(dst + T0 + tid * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+		}
+		// the tile's bytes: copies fetch their final source; into the ring and out (nobody's pointer ends on a copy)
+		if (a0 + 16 <= tl) {
+			uint4 v = *reinterpret_cast<const uint4 *>(S.ring + rbase + a0);
+			uint32_t w[4] = {v.x, v.y, v.z, v.w};
+			for (uint32_t mm = mine; mm; mm &= mm - 1u) {
+				const int b = __ffs((int)mm) - 1;
+				const uint32_t x = S.ring[S.ptr[a0 + b]];
+				w[b >> 2] = (w[b >> 2] & ~(0xFFu << (8 * (b & 3)))) | (x << (8 * (b & 3)));
+			}
+			v = make_uint4(w[0], w[1], w[2], w[3]);
+			*reinterpret_cast<uint4 *>(S.ring + rbase + a0) = v;
+			*reinterpret_cast<uint4 *>(dst + T0 + a0) = v;
 		} else {
-			for (int i = tid * 16; i < tl && i < tid * 16 + 16; i++) dst[T0 + i] = S.val[S.ptr[i]];
+			for (uint32_t mm = mine; mm; mm &= mm - 1u) {
+				const int b = __ffs((int)mm) - 1;
+				const uint8_t x = S.ring[S.ptr[a0 + b]];
+				S.ring[rbase + a0 + b] = x;
+				dst[T0 + a0 + b] = x;
+			}
 		}
 	}
 }

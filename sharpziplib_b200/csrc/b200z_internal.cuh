@@ -21,6 +21,24 @@ int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
 	} while (0)
 
 int ensure_init(); // picks up the current device if b200z_init() was not called explicitly
+int current_device(); // the device b200z_init() chose for the calling thread (the CUDA current device otherwise)
+
+// Every object (plan, pipeline, handle) remembers the device it was created on; its entry points run there and leave the
+// calling thread's current device as they found it, so that one host thread can drive several GPUs.
+struct DeviceGuard {
+	int prev = -1;
+	explicit DeviceGuard(int dev) {
+		if (dev < 0) return;
+		int cur = -1;
+		if (cudaGetDevice(&cur) == cudaSuccess && cur != dev) {
+			prev = cur;
+			cudaSetDevice(dev);
+		}
+	}
+	~DeviceGuard() {
+		if (prev >= 0) cudaSetDevice(prev);
+	}
+};
 
 constexpr int64_t kAlign = 256; // stream slots in the blobs start on 256-byte boundaries (vector loads / bulk copies)
 inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
@@ -69,8 +87,10 @@ struct __align__(8) MatchTok {
 
 struct b200z_plan {
 	int kind = 0; // 0 deflate, 1 inflate
+	int device = -1; // the device the plan's workspace lives on
 	int n = 0;
 	int level = 6, strategy = 0, wrap = 0, end_mode = 0;
+	int host_wrap = 0; // the framing the host-buffer pipeline writes around this plan's streams (b200z_pipeline_*)
 	std::vector<int64_t> in_len, in_off, out_off, out_cap;
 	int64_t in_bytes = 0, out_bytes = 0;
 	// deflate with history (b200z_deflate_plan_create_ex): in_len[] is history + data; an inflate plan keeps the
@@ -92,9 +112,7 @@ struct b200z_plan {
 	int64_t o_sym_local = 0, o_chunks = 0, o_rgroups = 0, o_rnd_off = 0, o_recs = 0, o_rnd_symoff = 0; // chunked parse
 	int n_chunks = 0, n_rgroups = 0;
 	uint32_t parse_chunk = 32768;
-	int64_t o_ent = 0; // B200Z_TILE_PARSE=4: entry state of every tile, for the fix-up
 	int link_run = 65536; // positions per k_links CTA (B200Z_LINK_RUN)
-	int tile_parse = 0; // experimental/k_tile_parse.cuh (1) / k_tile_parse2 (2) instead of k_match + k_parse_chunk
 	int fast_prev_entries = 32768; // k_fast's prev[] size for this batch
 	int64_t o_stored = 0, o_slens = 0; // level 0: stored-block list and per-stream output lengths
 	// levels 0-4: the SetInput schedule of every stream (cumulative sizes), "Flush()/Finish() behind an undrained SetInput",
@@ -110,6 +128,7 @@ struct b200z_plan {
 	int64_t o_start_bit = 0, o_pre = 0; // inflate framing: first deflate bit and header verdict per stream
 	int64_t o_restart = 0;              // inflate: per stream (bit, output position) of the last block header reached
 	bool has_start_bits = false;        // raw inflate plans: caller-supplied first bit (b200z_inflate_plan_set_start_bits)
+	std::vector<int64_t> comp_off, comp_cap, dict_cap; // inflate: where the compressed bytes start in the blob; capacities (b200z_inflate_plan_set_lengths)
 	// inflate, block-parallel pipeline (b200z_inflate_par.cuh)
 	bool inf_parallel = true;           // false: the serial kernel only (B200Z_INFLATE=serial)
 	int64_t o_win_base = 0, o_win_stream = 0, o_cand = 0, o_ftiles = 0, o_fs_list = 0, o_ctr = 0, o_segs = 0, o_seg_list = 0;
@@ -144,6 +163,7 @@ int deflate_plan_build(b200z_plan *p);
 int deflate_plan_run(b200z_plan *p, const uint8_t *d_in, uint8_t *d_out, int64_t *d_out_len, int32_t *d_status,
                      uint32_t *d_check, int64_t *d_out_bits, cudaStream_t s, int stages);
 int inflate_plan_build(b200z_plan *p);
+int inflate_plan_stats(b200z_plan *p, uint32_t *v, int32_t cap, cudaStream_t s);
 int inflate_plan_run(b200z_plan *p, const uint8_t *d_in, uint8_t *d_out, int64_t *d_out_len, int32_t *d_status,
                      uint32_t *d_check, int64_t *d_in_used, cudaStream_t s);
 // checksum over n device buffers (kind 0 = CRC32, 1 = Adler32); d_acc = 2 x uint64 scratch per stream;

@@ -389,6 +389,31 @@ def text_buffer(index, n, config=2):
     return gen_text(n, seed_for(config, index))
 
 
-def log_stream(n, config=4):
-    """C4: one long log stream."""
-    return gen_log(n, seed_for(config, 0))
+def _log_piece(args):
+    k, n, config = args
+    # piece k of a long stream: its own seed, its timestamps behind the pieces in front of it (+1..2000 ms per ~90-byte line)
+    return gen_log(n, seed_for(config, k), t0=1577836800000 + k * (LOG_PIECE // 90 + 16) * 1001)
+
+
+LOG_PIECE = 32 << 20
+
+
+def log_stream(n, config=4, workers=None):
+    """C4: one long log stream.  Up to 64 MiB it is one generator run; longer streams are pieces of 32 MiB (each its own seed,
+    timestamps still increasing across the pieces) generated by a few processes -- the single run takes minutes per GiB."""
+    if n <= (64 << 20):
+        return gen_log(n, seed_for(config, 0))
+    import os
+    from concurrent.futures import ProcessPoolExecutor
+    pieces = [(k, min(LOG_PIECE, n - k * LOG_PIECE), config) for k in range((n + LOG_PIECE - 1) // LOG_PIECE)]
+    if workers is None:
+        try:
+            workers = len(os.sched_getaffinity(0))
+        except AttributeError:
+            workers = os.cpu_count() or 1
+        workers = max(1, min(workers, 32, len(pieces)))
+    out = np.empty(n, dtype=np.uint8)
+    with ProcessPoolExecutor(max_workers=workers) as ex:
+        for (k, m, _), piece in zip(pieces, ex.map(_log_piece, pieces)):
+            out[k * LOG_PIECE:k * LOG_PIECE + m] = piece
+    return out

@@ -8,17 +8,11 @@ from . import _lib
 def partition_by_bytes(lens, world_size):
     """Contiguous index ranges [lo, hi) per rank, balanced by cumulative byte count: rank r gets the buffers whose
     cumulative start offset falls in [r*T/R, (r+1)*T/R)."""
-    lens = np.asarray(lens, dtype=np.int64)
-    total = int(lens.sum())
-    starts = np.cumsum(lens) - lens
-    bounds = [0]
-    for r in range(1, world_size):
-        cut = (total * r) // world_size
-        bounds.append(int(np.searchsorted(starts, cut, side="left")))
-    bounds.append(len(lens))
-    for i in range(1, len(bounds)):
-        bounds[i] = max(bounds[i], bounds[i - 1])
-    return [(bounds[r], bounds[r + 1]) for r in range(world_size)]
+    lens = np.ascontiguousarray(lens, dtype=np.int64)
+    first = np.zeros(world_size + 1, dtype=np.int32)
+    # the library's own cut (b200z_partition_by_bytes): what b200z_*_batch_multi uses for one process and several GPUs
+    _lib.raise_for(_lib.lib().b200z_partition_by_bytes(lens.ctypes.data, lens.size, world_size, first.ctypes.data))
+    return [(int(first[r]), int(first[r + 1])) for r in range(world_size)]
 
 
 def broadcast_static_tables(dist, device=None):

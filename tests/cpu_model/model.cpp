@@ -358,175 +358,3 @@ emit_blocks:
 	*outlen = nbytes;
 	return 0;
 }
-
-// ---- the round-2 decomposition (sharpziplib_b200/csrc/experimental/k_tile_parse.cuh) executed thread by thread -----------
-// One "CTA" per tile of 16384 positions: the window is copied into a local array (so that the window-relative indexing is
-// exercised), thread t parses segment t speculatively with a table function that searches ON DEMAND and memoises, exits are
-// handed to the next thread until nothing changes, every "warp" (32 threads = one round of 1024 positions) emits its symbols
-// and leaves the round's exit state; tiles are stitched the way k_parse_fix does it (chunk = tile) with a table function
-// that searches in the whole buffer where the tile kernel left "not computed".  Checked against the straightforward
-// serial parse over eager tables: every round must end in the same state with the same symbols.  Returns 0 when equal.
-struct U2 { uint32_t x, y; };
-extern "C" int model_fused_check(const uint8_t *data, uint32_t n, int level, int strategy, uint64_t *searched, uint64_t *positions) {
-	const LevelParams lp = level_params(level);
-	if (lp.func != 2) return -1;
-	const uint32_t kSeg = 32, kRound = 1024, kFTile = 16384, kFThreads = kFTile / kSeg, kFHist = 32768;
-	const uint32_t kFNone = 0xFFFFFFFFu, kFNeedB = 0x80000000u;
-	std::vector<uint16_t> link;
-	model_links(data, n, link);
-	const uint32_t nr = (n + kRound - 1) / kRound;
-	auto bytef = [&](uint32_t q) { return (uint32_t)data[q]; };
-	auto slowf = [&](uint32_t p, uint32_t m0, uint32_t budget) { return match_search_above(data, link.data(), p, n, m0, budget, 0u); };
-	// ---- reference: eager tables, serial parse, cut into rounds ----
-	std::vector<uint32_t> tabA(n, 0), tabB(n, 0);
-	for (uint32_t p = 0; p < n; p++) match_search(data, link.data(), 0u, p, n, lp, tabA[p], tabB[p], 0u);
-	std::vector<std::vector<uint32_t>> ref_syms(nr);
-	std::vector<ParseCarry> ref_exit(nr);
-	{
-		auto tabf = [&](uint32_t p, uint32_t &a, uint32_t &b) { a = tabA[p]; b = tabB[p]; };
-		ParseCarry c;
-		parse_init(c.st);
-		c.st.p = 0;
-		c.last_top = 0;
-		for (uint32_t r = 0; r < nr; r++) {
-			parse_run<true>(c, (r + 1) * kRound, n, lp, strategy, tabf, bytef, slowf,
-			                [&](uint32_t, uint32_t sym, uint32_t, uint32_t) { ref_syms[r].push_back(sym); });
-			ref_exit[r] = c;
-		}
-	}
-	// ---- the tile kernel ----
-	std::vector<U2> mt(n, U2{kFNone, kFNone});
-	std::vector<std::vector<uint32_t>> got_syms(nr);
-	std::vector<ParseCarry> got_exit(nr);
-	uint64_t nsearch = 0;
-	auto clean = [&](uint32_t p) {
-		ParseCarry c;
-		parse_init(c.st);
-		c.st.p = p;
-		c.last_top = p;
-		return c;
-	};
-	for (uint32_t t0 = 0; t0 < n; t0 += kFTile) {
-		const uint32_t t1 = n - t0 > kFTile ? t0 + kFTile : n;
-		const uint32_t w0 = t0 >= kFHist ? t0 - kFHist : 0u;
-		const uint32_t dend = t1 + 272 > n ? n : t1 + 272;
-		std::vector<uint8_t> s_data(data + w0, data + dend);
-		s_data.resize(s_data.size() + 16, 0);
-		std::vector<uint16_t> s_link(link.begin() + w0, link.begin() + t1);
-		std::vector<uint32_t> s_memo(kFTile, kFNone);
-		auto tabf = [&](uint32_t p, uint32_t &a, uint32_t &b) {
-			const uint32_t m = s_memo[p - t0];
-			if (m == kFNone) {
-				match_search(s_data.data(), s_link.data(), w0, p, n, lp, a, b, 0u);
-				s_memo[p - t0] = a | (a != b ? kFNeedB : 0u);
-				++nsearch;
-			} else {
-				a = m & ~kFNeedB;
-				b = a;
-				if (m & kFNeedB) {
-					LevelParams lq = lp;
-					lq.chain = lp.chain >> 2;
-					uint32_t dummy;
-					match_search(s_data.data(), s_link.data(), w0, p, n, lq, b, dummy, 0u);
-				}
-			}
-		};
-		auto tbyte = [&](uint32_t q) { return (uint32_t)s_data[q - w0]; };
-		std::vector<ParseCarry> entry(kFThreads), ex(kFThreads), s_exit(kFThreads);
-		std::vector<uint32_t> cnt(kFThreads, 0), lim(kFThreads);
-		std::vector<char> changed(kFThreads, 1);
-		for (uint32_t t = 0; t < kFThreads; t++) {
-			const uint32_t seg0 = t0 + t * kSeg;
-			lim[t] = seg0 + kSeg < n ? seg0 + kSeg : n;
-			entry[t] = clean(seg0);
-			ex[t] = entry[t];
-		}
-		for (uint32_t it = 0; it < kFThreads + 2; it++) {
-			for (uint32_t t = 0; t < kFThreads; t++) {
-				if (!changed[t]) continue;
-				ex[t] = entry[t];
-				cnt[t] = 0;
-				while (ex[t].st.p < lim[t]) {
-					ex[t].last_top = ex[t].st.p;
-					uint32_t s2;
-					cnt[t] += (uint32_t)parse_step(ex[t].st, n, lp, strategy, tabf, tbyte, slowf, s2);
-				}
-			}
-			for (uint32_t t = 0; t < kFThreads; t++) s_exit[t] = ex[t];
-			bool any = false;
-			changed[0] = 0;
-			for (uint32_t t = 1; t < kFThreads; t++) {
-				changed[t] = !carry_equal(s_exit[t - 1], entry[t]);
-				entry[t] = s_exit[t - 1];
-				any |= changed[t] != 0;
-			}
-			if (getenv("B200Z_MODEL_VERBOSE")) {
-				uint32_t nch = 0;
-				for (uint32_t t = 0; t < kFThreads; t++) nch += changed[t] != 0;
-				fprintf(stderr, "tile %u: after pass %u, %u of %u segments re-parse\n", t0 / kFTile, it, nch, kFThreads);
-			}
-			if (!any) break;
-			if (it == kFThreads + 1) return 201; // did not converge
-		}
-		for (uint32_t w = 0; w < kFThreads / 32; w++) {
-			const uint32_t rbase = t0 + w * kRound;
-			if (rbase >= n) break;
-			std::vector<uint32_t> &out = got_syms[rbase / kRound];
-			ParseCarry c;
-			for (uint32_t l = 0; l < 32; l++) {
-				const uint32_t t = w * 32 + l;
-				c = entry[t];
-				uint32_t k = 0;
-				while (c.st.p < lim[t]) {
-					c.last_top = c.st.p;
-					uint32_t s2;
-					if (parse_step(c.st, n, lp, strategy, tabf, tbyte, slowf, s2)) {
-						out.push_back(s2);
-						++k;
-					}
-				}
-				if (k != cnt[t] || !carry_equal(c, ex[t])) return 202; // final pass disagrees with the converged pass
-			}
-			got_exit[rbase / kRound] = c;
-		}
-		for (uint32_t i = 0; i < t1 - t0; i++) {
-			const uint32_t m = s_memo[i];
-			mt[t0 + i] = m == kFNone ? U2{kFNone, kFNone} : U2{m & ~kFNeedB, (m & kFNeedB) ? kFNone : (m & ~kFNeedB)};
-		}
-	}
-	// ---- k_parse_fix with chunk = kFTile and the lazy table function ----
-	auto lazy = [&](uint32_t p, uint32_t &a, uint32_t &b) {
-		const U2 e = mt[p];
-		if (e.x == kFNone || e.y == kFNone) {
-			match_search(data, link.data(), 0u, p, n, lp, a, b, 0u);
-			mt[p] = U2{a, b};
-			++nsearch;
-		} else {
-			a = e.x;
-			b = e.y;
-		}
-	};
-	for (uint32_t c0 = kFTile; c0 < n; c0 += kFTile) {
-		const uint32_t c1 = n - c0 > kFTile ? c0 + kFTile : n;
-		ParseCarry truth = got_exit[c0 / kRound - 1];
-		ParseCarry guess = clean(c0);
-		guess.last_top = truth.last_top;
-		if (carry_equal(truth, guess)) continue;
-		for (uint32_t base = c0; base < c1; base += kRound) {
-			const ParseCarry old_exit = got_exit[base / kRound];
-			std::vector<uint32_t> &out = got_syms[base / kRound];
-			out.clear();
-			parse_run<true>(truth, base + kRound, n, lp, strategy, lazy, bytef, slowf,
-			                [&](uint32_t, uint32_t sym, uint32_t, uint32_t) { out.push_back(sym); });
-			got_exit[base / kRound] = truth;
-			if (carry_equal(truth, old_exit)) break;
-		}
-	}
-	for (uint32_t r = 0; r < nr; r++) {
-		if (got_syms[r] != ref_syms[r]) return 300;
-		if (!carry_equal(got_exit[r], ref_exit[r])) return 301;
-	}
-	if (searched) *searched = nsearch;
-	if (positions) *positions = n;
-	return 0;
-}

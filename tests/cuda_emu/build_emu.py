@@ -107,7 +107,7 @@ def build(sanitize=False, verbose=False):
         for f in os.listdir(exp):
             if f.endswith(".cuh"):
                 open(os.path.join(OUT, "src", "experimental", f), "w").write(rewrite(open(os.path.join(exp, f)).read()))
-    flags = ["-std=c++17", "-O1", "-g", "-fPIC", "-shared", "-w", "-I", os.path.join(HERE, "include"),
+    flags = ["-std=c++17", "-O1", "-g", "-fPIC", "-shared", "-w"] + os.environ.get("B200Z_EMU_CXXFLAGS", "").split() + [ "-I", os.path.join(HERE, "include"),
              "-iquote", os.path.join(OUT, "src"), "-I", CSRC, "-iquote", CSRC]
     if sanitize == "asan":
         flags += ["-fsanitize=address", "-fno-omit-frame-pointer"]

@@ -24,15 +24,6 @@ bufs = [datagen.silesia_mix(0, 20000).tobytes(), datagen.silesia_mix(3, 9000).to
 for level in (6, 9, 1, 0):
     outs, _ = z.deflate_batch(bufs, level=level)
     assert outs == [O.deflate(b, level=level) for b in bufs], level
-# the opt-in search kernels (csrc/experimental/k_tile_parse.cuh): a stream of three tiles, so that the hand-off inside a tile,
-# the guessed tile entries and the lazy fix-up (k_parse_fix_lazy) all run
-tile_bufs = [datagen.silesia_mix(0, 40000).tobytes(), bufs[1], b"", bytes(5000)]
-tile_refs = [O.deflate(b, level=6) for b in tile_bufs]
-for variant in ("1", "2", "3", "4"):
-    os.environ["B200Z_TILE_PARSE"] = variant
-    outs, _ = z.deflate_batch(tile_bufs, level=6)
-    assert outs == tile_refs, "B200Z_TILE_PARSE=" + variant
-del os.environ["B200Z_TILE_PARSE"]
 # k_links with longer runs (B200Z_LINK_RUN): a stream of two 64 Ki runs / one 128 Ki run + a tail
 long_buf = [datagen.silesia_mix(3, 140000).tobytes()]
 long_ref = [O.deflate(long_buf[0], level=6)]
@@ -44,7 +35,7 @@ del os.environ["B200Z_LINK_RUN"]
 outs, checks = z.deflate_batch(bufs[:2], level=6, wrap=1)  # zlib framing: Adler-32 on the device (k_checksum)
 assert outs == [O.deflate(b, level=6, nowrap=False) for b in bufs[:2]]
 
-# inflate (k_inflate), framed inflate (k_wrap_head / k_wrap_tail), truncation and restart points
+# inflate (block-parallel pipeline: k_find .. k_resolve, serial k_inflate for what it hands back), framed inflate (k_wrap_head / k_wrap_tail), truncation and restart points
 comp = [O.deflate(b, level=6) for b in bufs]
 back, used, st = z.inflate_batch(comp, [len(b) for b in bufs])
 assert back == bufs and [int(u) for u in used] == [len(c) for c in comp]

@@ -276,38 +276,3 @@ def test_model_setinput_schedules_and_flush_levels_0_to_4(model, oracle, level):
         # (DeflateStored takes lastBlock = finish even while input is still outside the window, DeflaterEngine.cs:631):
         # reproduced, not repaired
         assert back == whole or (level == 0 and not busy_last and whole.startswith(back))
-
-
-# ---- round-2 decomposition: the parse drives the search (sharpziplib_b200/csrc/experimental/k_tile_parse.cuh) -------------
-def test_tile_parse_decomposition_is_exact(model, oracle):
-    """tests/cpu_model/model.cpp::model_fused_check runs the experimental tile kernel's algorithm thread by thread (on-demand
-    memoised search from a window copy, CTA-wide exit -> entry hand-off, per-round emission, tile stitching with a lazy table)
-    and compares every round's symbols and exit state with the serial parse over eager tables."""
-    from sharpziplib_b200 import datagen
-    from helpers import crafted_t8
-    so = os.path.join(ROOT, "tests", "cpu_model", "_build", "libmodel.so")
-    M = C.CDLL(so)
-    M.model_fused_check.argtypes = [C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
-
-    def check(d, level, strategy=0):
-        a = np.frombuffer(d + bytes(32), dtype=np.uint8).copy()
-        s, p = C.c_uint64(0), C.c_uint64(0)
-        rc = M.model_fused_check(a.ctypes.data, len(d), level, strategy, C.byref(s), C.byref(p))
-        assert rc == 0, (rc, len(d), level, strategy)
-        return s.value, p.value
-
-    for name, d in corpus_small():
-        for level in (5, 6, 9):
-            check(d, level)
-    searched = positions = 0
-    for cls in range(8):
-        s, p = check(datagen.silesia_mix(cls, 262144).tobytes(), 6)
-        searched += s
-        positions += p
-    # the point of the exercise: about half of the positions are ever searched (k_match searches all of them), and they
-    # are the cheap ones (tools/match_stats.cpp)
-    assert searched < 0.6 * positions
-    long = crafted_t8() + datagen.gen_text(200000, 3).tobytes()
-    for level in (5, 7, 9):
-        for strategy in (0, 1):
-            check(long, level, strategy)
