@@ -1169,11 +1169,12 @@ static b200z_pipeline *multi_find(int device, const PipeKey &k) {
 }
 static void multi_put(int device, PipeKey k, b200z_pipeline *p) {
 	int same = 0;
-	for (size_t i = 0; i < g_multi_pipes.size();) { // at most two shapes per device stay
-		if (g_multi_pipes[i].first.device == device && ++same >= 2) {
+	for (size_t i = g_multi_pipes.size(); i-- > 0;) { // the newest four shapes per device stay; never one with a batch in flight
+		if (g_multi_pipes[i].first.device != device) continue;
+		if (++same >= 4 && b200z_pipeline_in_flight(g_multi_pipes[i].second) == 0) {
 			b200z_pipeline_destroy(g_multi_pipes[i].second);
 			g_multi_pipes.erase(g_multi_pipes.begin() + (ptrdiff_t)i);
-		} else ++i;
+		}
 	}
 	g_multi_pipes.push_back(std::make_pair(MultiKey{device, std::move(k)}, p));
 }
@@ -1465,6 +1466,14 @@ int b200z_deflater_set_input(void *h, const uint8_t *buf, int32_t len) {
 	if (len < 0 || (len > 0 && !buf)) {
 		set_error("buffer/count");
 		return B200Z_E_ARG;
+	}
+	// one plan slot addresses 4 GiB - 64 KiB (32-bit positions, the window phase included): refuse what could not be
+	// compressed instead of accepting it and failing at Flush() / Finish()
+	if ((int64_t)d->input.size() + len + 32768 > 0xFFFF0000ll || d->window_seen + (int64_t)d->input.size() + len > 0xFFFF0000ll) {
+		set_error("Deflater handle: more than 4 GiB - 64 KiB in one stream (TotalIn %lld, %lld buffered, %d more): use several "
+		          "streams or the batch API",
+		          (long long)d->total_in, (long long)d->input.size(), len);
+		return B200Z_E_UNSUPPORTED;
 	}
 	if (len > 0) d->flushed_once = false;
 	d->input.insert(d->input.end(), buf, buf + len);

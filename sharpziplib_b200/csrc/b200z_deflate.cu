@@ -201,6 +201,9 @@ __global__ void __launch_bounds__(kMatchThreads, 1)
 	// are bucketed by an estimate of their walk length (the first eight hops are exact, beyond that their hop density
 	// extrapolated over the window) and handed to the threads longest first: warps then hold walks of similar length.
 	// The order only decides who computes what; every position's result is unchanged.
+	// (Measured in round 2 and dropped: the walks as a flat state machine -- one candidate test or four bytes of extension per
+	// lane and iteration, free lanes refilled from the ordered list eight at a time.  Bit-exact, 41.5 ms instead of 21.2 ms on
+	// the bench workload: every iteration pays for every state's code.  profiles/README.md.)
 	__shared__ uint32_t s_cls[2][kMatchClasses];
 	if (threadIdx.x < 2 * kMatchClasses) (&s_cls[0][0])[threadIdx.x] = 0;
 	__syncthreads();

@@ -72,9 +72,8 @@ struct __align__(16) PRound {
 	uint32_t mpre[kP1Threads];
 };
 
-struct __align__(16) PBlockHdr {
-	uint16_t nlit, ndist, is_static, pad;
-	uint8_t lens[320];
+struct __align__(16) PBlockHdr { // a block's code tables as k_dec1 built them, for k_dec2
+	InfShared tab;
 };
 
 struct PCounters {
@@ -262,14 +261,16 @@ __global__ void __launch_bounds__(128)
 				rep = 11 + (int)br.get(7);
 			}
 			if (idx + rep > total) { ok = false; break; }
-			for (int r = 0; r < rep; r++, idx++) {
-				if (idx < nlit) {
-					if (val) kl += 32768u >> val;
-					if (idx == 256) eob_len = val;
-				} else if (val) {
-					kd += 32768u >> val;
-					nd++;
+			{
+				// `rep` entries of length `val` from index idx on: how many are literal/length codes, how many distance codes
+				const int nl = idx >= nlit ? 0 : (nlit - idx < rep ? nlit - idx : rep), ndc = rep - nl;
+				if (idx <= 256 && 256 < idx + rep) eob_len = val;
+				if (val) {
+					kl += (uint32_t)nl * (32768u >> val);
+					kd += (uint32_t)ndc * (32768u >> val);
+					nd += ndc;
 				}
+				idx += rep;
 			}
 			prev = val;
 			if (br.overrun()) ok = false;
@@ -420,61 +421,123 @@ __device__ uint32_t long_code(uint32_t v, const uint16_t *sorted, const Canon &c
 	return 0; // K_INVALID, nb = 0
 }
 
+// A lane's decode state: the bit position and, in registers, the next 33..64 bits of the stream from there (refilled 32 bits
+// at a time from the staged words), so that a literal costs one table lookup and a few shifts -- no shared-memory round
+// trip for the bits themselves.
+struct SpanB {
+	uint64_t bb;   // stream bits from `pos` on, least significant first
+	uint32_t nb;   // how many of them are valid
+	uint32_t widx; // next staged word to take
+	uint32_t pos, o, nm, fl, det;
+};
+
+__device__ __forceinline__ void span_begin(SpanB &s, const uint32_t *words, uint32_t pos) {
+	const uint32_t i = pos >> 5, sh = pos & 31u;
+	const uint64_t two = (uint64_t)words[in_slot(i)] | ((uint64_t)words[in_slot(i + 1)] << 32);
+	s.bb = two >> sh;
+	s.nb = 64u - sh;
+	s.widx = i + 2;
+	s.pos = pos;
+	s.o = 0;
+	s.nm = 0;
+	s.fl = 0;
+	s.det = 0;
+}
+__device__ __forceinline__ void span_refill(SpanB &s, const uint32_t *words) { // afterwards at least 33 bits are valid
+	if (s.nb <= 32u) {
+		s.bb |= (uint64_t)words[in_slot(s.widx)] << s.nb;
+		s.nb += 32u;
+		++s.widx;
+	}
+}
+__device__ __forceinline__ void span_drop(SpanB &s, uint32_t n) {
+	s.bb >>= n;
+	s.nb -= n;
+	s.pos += n;
+}
+
+// One symbol.  MODE 0 counts; MODE 1 stores literals at out[o0 + o] and back-references at ml[nm] (output positions relative
+// to the stream).  A symbol that needs bits past the end of the input is not consumed (pos stays at its first bit).
 template <int MODE>
-__device__ __forceinline__ bool span_step2(const InfShared &sh, const uint32_t *words, Span &s, uint32_t limit, uint32_t end_rel,
+__device__ __forceinline__ bool span_step2(const InfShared &sh, const uint32_t *words, SpanB &s, uint32_t limit, uint32_t end_rel,
                                            uint8_t *out, uint64_t o0, MatchTok *ml) {
 	const uint32_t spos = s.pos;
 	if (spos >= limit) return false;
-	const uint32_t v = peek32(words, spos);
+	span_refill(s, words);
+	const uint32_t v = (uint32_t)s.bb;
 	uint32_t e = sh.lit[v & ((1u << kLitRoot) - 1u)];
-	if (((e >> 4) & 15u) == K_LONG) e = long_code(v, sh.lit_sorted, sh.lit_c, kLitRoot, 0);
-	const uint32_t k = (e >> 4) & 15u, nb = e & 15u, xb = (e >> 8) & 15u;
-	const uint32_t val = (e >> 16) + ((v >> nb) & ((1u << xb) - 1u)); // the literal, or the length with its extra bits
-	const uint32_t pos1 = spos + nb + xb;
-	const uint32_t v2 = peek32(words, pos1);
-	uint32_t de = sh.dist[v2 & ((1u << kDistRoot) - 1u)];
-	if (k == K_LEN && ((de >> 4) & 15u) == K_LONG) de = long_code(v2, sh.dist_sorted, sh.dist_c, kDistRoot, 1);
-	const uint32_t dk = (de >> 4) & 15u, dnb = de & 15u, dxb = (de >> 8) & 15u;
-	const uint32_t dist = (de >> 16) + ((v2 >> dnb) & ((1u << dxb) - 1u));
-	const bool lit = k == K_LIT, rep = (k == K_LEN) & (dk == K_DIST);
-	if (lit | rep) {
-		const uint32_t npos = lit ? pos1 : pos1 + dnb + dxb;
+	uint32_t k = (e >> 4) & 15u;
+	if (k == K_LIT) {
+		const uint32_t nb = e & 15u;
+		if (spos + nb > end_rel) { s.fl |= F_OVERRUN; return false; }
+		if (MODE) out[o0 + s.o] = (uint8_t)(e >> 16);
+		++s.o;
+		span_drop(s, nb);
+		return true;
+	}
+	if (k == K_LONG) {
+		e = long_code(v, sh.lit_sorted, sh.lit_c, kLitRoot, 0);
+		k = (e >> 4) & 15u;
+		if (k == K_LIT) {
+			const uint32_t nb = e & 15u;
+			if (spos + nb > end_rel) { s.fl |= F_OVERRUN; return false; }
+			if (MODE) out[o0 + s.o] = (uint8_t)(e >> 16);
+			++s.o;
+			span_drop(s, nb);
+			return true;
+		}
+	}
+	const uint32_t nb = e & 15u;
+	if (k == K_LEN) {
+		// length code (<= 15 bits) + extra (<= 5) are in the buffer; the distance code + extra (<= 28) after a refill
+		const uint32_t xb = (e >> 8) & 15u;
+		const uint32_t len = (e >> 16) + ((v >> nb) & ((1u << xb) - 1u));
+		const uint32_t pos1 = spos + nb + xb;
+		uint64_t bb = s.bb >> (nb + xb);
+		uint32_t have = s.nb - (nb + xb), widx = s.widx;
+		if (have <= 32u) {
+			bb |= (uint64_t)words[in_slot(widx)] << have;
+			have += 32u;
+			++widx;
+		}
+		const uint32_t v2 = (uint32_t)bb;
+		uint32_t de = sh.dist[v2 & ((1u << kDistRoot) - 1u)];
+		if (((de >> 4) & 15u) == K_LONG) de = long_code(v2, sh.dist_sorted, sh.dist_c, kDistRoot, 1);
+		const uint32_t dk = (de >> 4) & 15u, dnb = de & 15u;
+		if (dk != K_DIST) {
+			// Invalid codes near the end of the input, as the reference classifies them (InflaterHuffmanTree.GetSymbol :181-235):
+			// a table entry without a code is diagnosed as soon as 9 bits can be peeked; a code for an illegal symbol (286, 287,
+			// distance 30, 31) once its own bits are there; with fewer bits the decoder waits for more input.
+			if (pos1 + (dk == K_ILLEGAL ? dnb : 9u) > end_rel) s.fl |= F_OVERRUN;
+			else { s.fl |= F_ERR; s.det = dk == K_ILLEGAL ? D_REP_DIST : D_CODELEN0; }
+			return false;
+		}
+		const uint32_t dxb = (de >> 8) & 15u;
+		const uint32_t dist = (de >> 16) + ((v2 >> dnb) & ((1u << dxb) - 1u));
+		const uint32_t npos = pos1 + dnb + dxb;
 		if (npos > end_rel) { s.fl |= F_OVERRUN; return false; }
 		if (MODE) {
-			if (lit) out[o0 + s.o] = (uint8_t)val;
-			else {
-				MatchTok t;
-				t.out_pos = (uint32_t)(o0 + s.o);
-				t.len = (uint16_t)val;
-				t.dist = (uint16_t)(dist & 0xFFFFu); // 32768 fits
-				ml[s.nm] = t;
-			}
+			MatchTok t;
+			t.out_pos = (uint32_t)(o0 + s.o);
+			t.len = (uint16_t)len;
+			t.dist = (uint16_t)(dist & 0xFFFFu); // 32768 fits
+			ml[s.nm] = t;
 		}
-		s.nm += rep ? 1u : 0u;
-		s.o += lit ? 1u : val;
+		++s.nm;
+		s.o += len;
+		s.bb = bb >> (dnb + dxb);
+		s.nb = have - (dnb + dxb);
+		s.widx = widx;
 		s.pos = npos;
 		return true;
 	}
-	// ---- the rare rest: end of block, invalid or illegal codes (Inflater.cs:318-326, :351-359; InflaterHuffmanTree.cs:190-193)
 	if (k == K_EOB) {
 		if (spos + nb > end_rel) s.fl |= F_OVERRUN;
 		else { s.fl |= F_EOB; s.pos = spos + nb; }
 		return false;
 	}
-	// Invalid codes near the end of the input, as the reference classifies them (InflaterHuffmanTree.GetSymbol :181-235): a
-	// table entry without a code is diagnosed as soon as 9 bits can be peeked; a code for an illegal symbol (286, 287,
-	// distance 30, 31) once its own bits are there; with fewer bits the decoder waits for more input.
-	if (k == K_LEN) { // the distance code is the problem (its length's extra bits come first: without them, wait)
-		const uint32_t need = dk == K_ILLEGAL ? dnb : 9u;
-		if (pos1 + need > end_rel) s.fl |= F_OVERRUN;
-		else { s.fl |= F_ERR; s.det = dk == K_ILLEGAL ? D_REP_DIST : D_CODELEN0; }
-		return false;
-	}
-	{
-		const uint32_t need = k == K_ILLEGAL ? nb : 9u;
-		if (spos + need > end_rel) s.fl |= F_OVERRUN;
-		else { s.fl |= F_ERR; s.det = k == K_ILLEGAL ? D_REP_LEN : D_CODELEN0; }
-	}
+	if (spos + (k == K_ILLEGAL ? nb : 9u) > end_rel) s.fl |= F_OVERRUN;
+	else { s.fl |= F_ERR; s.det = k == K_ILLEGAL ? D_REP_LEN : D_CODELEN0; }
 	return false;
 }
 
@@ -697,13 +760,9 @@ __global__ void __launch_bounds__(kP1Threads)
 				break;
 			}
 			{
-				PBlockHdr &h = hdrs[hdr_idx];
-				if (tid == 0) {
-					h.nlit = (uint16_t)nlit;
-					h.ndist = (uint16_t)ndist;
-					h.is_static = (uint16_t)(btype == 1);
-				}
-				for (int i = tid; i < 320; i += kP1Threads) h.lens[i] = S.sh.lens[i];
+				const uint4 *src = reinterpret_cast<const uint4 *>(&S.sh);
+				uint4 *dstv = reinterpret_cast<uint4 *>(&hdrs[hdr_idx].tab);
+				for (int i = tid; i < (int)(sizeof(InfShared) / 16); i += kP1Threads) dstv[i] = src[i];
 			}
 			// ---- rounds -------------------------------------------------------------------------------------------
 			bool in_block = true;
@@ -728,14 +787,11 @@ __global__ void __launch_bounds__(kP1Threads)
 				// input) kills the lanes behind it at once: S.stop[pass parity] collects the lowest such lane.
 				for (int it = 0; it < 2 * kP1Threads + 4; it++) {
 					++passes;
-					Span sp;
+					SpanB sp;
 					bool act = changed && !dead;
 					if (changed) {
-						sp.o = 0;
-						sp.nm = 0;
-						sp.fl = dead ? (uint32_t)F_DEAD : 0u;
-						sp.det = 0;
-						sp.pos = entry;
+						span_begin(sp, words, entry);
+						if (dead) sp.fl = (uint32_t)F_DEAD;
 					}
 					while (__any_sync(0xffffffffu, act)) {
 						if (act) act = span_step2<0>(S.sh, words, sp, limit, end_rel, nullptr, 0, nullptr);
@@ -942,7 +998,6 @@ __global__ void k_chain(int n, PSeg *__restrict__ segs, const uint32_t *__restri
 // ---------------------------------------------------------------------------------------------------------
 struct __align__(16) Dec2Shared {
 	InfShared sh;
-	TabScratch ts;
 	uint32_t in[kP1InSlots];
 };
 
@@ -975,23 +1030,18 @@ __global__ void __launch_bounds__(kP1Threads)
 			}
 			__syncthreads(); // the previous round's lanes are done with the staged words (and the tables)
 			if (!have_tab) {
-				const PBlockHdr &h = hdrs[r.hdr];
-				for (int i = tid; i < 320; i += kP1Threads) S.sh.lens[i] = h.lens[i];
-				__syncthreads();
-				build_tables_cta(S.sh, S.ts, h.nlit, h.ndist);
-				have_tab = true;
+				const uint4 *src = reinterpret_cast<const uint4 *>(&hdrs[r.hdr].tab);
+				uint4 *dstv = reinterpret_cast<uint4 *>(&S.sh);
+				for (int i = tid; i < (int)(sizeof(InfShared) / 16); i += kP1Threads) dstv[i] = src[i];
+				have_tab = true; // (the barrier behind the staging below covers the tables too)
 			}
 			const uint32_t nbytes = (uint32_t)in_len[stream];
 			stage_round(S.in, reinterpret_cast<const uint32_t *>(in + in_off[stream]), r.w0, (nbytes + 3) >> 2, nbytes);
 			__syncthreads();
 			{
 				const bool mine = (uint32_t)tid <= r.lastlane;
-				Span sp;
-				sp.o = 0;
-				sp.nm = 0;
-				sp.fl = 0;
-				sp.det = 0;
-				sp.pos = mine ? r.entry[tid] : 0u;
+				SpanB sp;
+				span_begin(sp, S.in, mine ? r.entry[tid] : 0u);
 				const uint32_t lim = r.r0 + (uint32_t)(tid + 1) * kSubBits;
 				const uint64_t o0 = obase + (mine ? r.opre[tid] : 0u);
 				MatchTok *ml = mlist + mt_off[stream] + seg.match_base + r.match_rel + (mine ? r.mpre[tid] : 0u);
@@ -1016,15 +1066,18 @@ __global__ void __launch_bounds__(kP1Threads)
 // ---------------------------------------------------------------------------------------------------------
 constexpr int kResRing = 65536;
 constexpr int kResChunk = 1536; // back-references staged at a time
+__device__ __forceinline__ uint32_t res_slot(uint32_t i) { return (i & 15u) * (uint32_t)kResThreads + (i >> 4); }
 struct __align__(16) ResShared {
 	uint8_t ring[kResRing];
-	uint16_t ptr[kResTile];        // for a byte that is a copy: ring index of its source (of a byte further back after a jump)
+	uint16_t ptr[kResTile];        // for a byte that is a copy: ring index of its source (of a byte further back after a jump);
+	                               // byte 16 t + k of the tile lives in slot k * 1024 + t (res_slot): a warp's accesses to its
+	                               // threads' k-th bytes fall into 16 consecutive words instead of four banks
 	uint16_t copied[kResThreads];  // bit b of copied[t]: byte 16 t + b of the tile is a copy
 	MatchTok mch[kResChunk];
 	int cnt_in, cnt_done;
 };
 
-__global__ void __launch_bounds__(kResThreads)
+__global__ void __launch_bounds__(kResThreads, 2) // two CTAs per SM: 32 registers per thread
     k_resolve(const uint8_t *__restrict__ in, uint8_t *out, const int64_t *__restrict__ in_off, const int64_t *__restrict__ out_off,
               const uint32_t *__restrict__ dict_len, const int64_t *__restrict__ out_len, const uint32_t *__restrict__ str_nm,
               const int32_t *__restrict__ fallback, const MatchTok *__restrict__ mlist, const int64_t *__restrict__ mt_off, int n) {
@@ -1147,13 +1200,13 @@ __global__ void __launch_bounds__(kResThreads)
 						const uint32_t sbase = rbase + (uint32_t)(dl - dist); // ring position of the source's first byte (mod 65536)
 						if (dist >= len) {
 							for (; p < pe; p++) {
-								S.ptr[p] = (uint16_t)(sbase + (uint32_t)(p - dl));
+								S.ptr[res_slot((uint32_t)p)] = (uint16_t)(sbase + (uint32_t)(p - dl));
 								mine |= 1u << (p - a0);
 							}
 						} else { // OutputWindow.Repeat: byte k comes from source byte k mod distance
 							int so = (p - dl) % dist;
 							for (; p < pe; p++) {
-								S.ptr[p] = (uint16_t)(sbase + (uint32_t)so);
+								S.ptr[res_slot((uint32_t)p)] = (uint16_t)(sbase + (uint32_t)so);
 								mine |= 1u << (p - a0);
 								if (++so == dist) so = 0;
 							}
@@ -1171,16 +1224,17 @@ __global__ void __launch_bounds__(kResThreads)
 		uint32_t unres = 0;
 		for (uint32_t mm = mine; mm; mm &= mm - 1u) {
 			const int b = __ffs((int)mm) - 1;
-			const uint32_t ql = ((uint32_t)S.ptr[a0 + b] - rbase) & (uint32_t)(kResRing - 1);
+			const uint32_t ql = ((uint32_t)S.ptr[(uint32_t)b * kResThreads + tid] - rbase) & (uint32_t)(kResRing - 1);
 			if (ql < (uint32_t)tl && ((S.copied[ql >> 4] >> (ql & 15u)) & 1u)) unres |= 1u << b;
 		}
 		// pointer jumping: a byte takes over its source's source until that is a final byte
 		while (__syncthreads_or(unres != 0)) {
 			for (uint32_t mm = unres; mm; mm &= mm - 1u) {
 				const int b = __ffs((int)mm) - 1;
-				const uint32_t ql = ((uint32_t)S.ptr[a0 + b] - rbase) & (uint32_t)(kResRing - 1);
-				const uint32_t r = S.ptr[ql]; // (whatever ql's owner has made of it by now: always a byte ql is a copy of)
-				S.ptr[a0 + b] = (uint16_t)r;
+				const uint32_t mys = (uint32_t)b * kResThreads + tid;
+				const uint32_t ql = ((uint32_t)S.ptr[mys] - rbase) & (uint32_t)(kResRing - 1);
+				const uint32_t r = S.ptr[res_slot(ql)]; // (whatever ql's owner has made of it by now: always a byte ql is a copy of)
+				S.ptr[mys] = (uint16_t)r;
 				const uint32_t rl = (r - rbase) & (uint32_t)(kResRing - 1);
 				if (!(rl < (uint32_t)tl && ((S.copied[rl >> 4] >> (rl & 15u)) & 1u))) unres &= ~(1u << b);
 			}
@@ -1191,7 +1245,7 @@ __global__ void __launch_bounds__(kResThreads)
 			uint32_t w[4] = {v.x, v.y, v.z, v.w};
 			for (uint32_t mm = mine; mm; mm &= mm - 1u) {
 				const int b = __ffs((int)mm) - 1;
-				const uint32_t x = S.ring[S.ptr[a0 + b]];
+				const uint32_t x = S.ring[S.ptr[(uint32_t)b * kResThreads + tid]];
 				w[b >> 2] = (w[b >> 2] & ~(0xFFu << (8 * (b & 3)))) | (x << (8 * (b & 3)));
 			}
 			v = make_uint4(w[0], w[1], w[2], w[3]);
@@ -1200,7 +1254,7 @@ __global__ void __launch_bounds__(kResThreads)
 		} else {
 			for (uint32_t mm = mine; mm; mm &= mm - 1u) {
 				const int b = __ffs((int)mm) - 1;
-				const uint8_t x = S.ring[S.ptr[a0 + b]];
+				const uint8_t x = S.ring[S.ptr[(uint32_t)b * kResThreads + tid]];
 				S.ring[rbase + a0 + b] = x;
 				dst[T0 + a0 + b] = x;
 			}
