@@ -24,6 +24,8 @@
 #include <cstdlib>
 #include <cstring>
 
+#include <cuda_pipeline.h>
+
 #include "b200z_internal.cuh"
 
 namespace b200z {
@@ -1011,6 +1013,11 @@ int inflate_plan_build(b200z_plan *p) {
 	int extra = 0;
 	if (p->inf_parallel && n) {
 		B200Z_CUDA(cudaFuncSetAttribute(k_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ResShared)));
+		// (the decode kernels want many small CTAs per SM: ask for the largest shared-memory carve-out)
+		B200Z_CUDA(cudaFuncSetAttribute(k_dec1, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+		B200Z_CUDA(cudaFuncSetAttribute(k_dec2, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+		B200Z_CUDA(cudaFuncSetAttribute(k_find, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+		B200Z_CUDA(cudaFuncSetAttribute(k_find3, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
 		int dev = 0, sms = 1, occ1 = 1, occ2 = 1;
 		B200Z_CUDA(cudaGetDevice(&dev));
 		B200Z_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));

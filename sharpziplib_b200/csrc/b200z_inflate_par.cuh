@@ -555,7 +555,8 @@ struct __align__(16) Dec1Shared {
 	unsigned long long h_bitpos;
 	uint32_t h_stored_len;
 	uint32_t q_idx, a_base;
-	int stop[2];
+	int stop[2], front[2];
+	uint32_t nlive[2];
 };
 
 __device__ __forceinline__ void stage_round(uint32_t *words, const uint32_t *gwords, uint32_t w0, uint32_t nwords, uint32_t nbytes) {
@@ -768,7 +769,11 @@ __global__ void __launch_bounds__(kP1Threads)
 			bool in_block = true;
 			while (in_block) {
 				__syncthreads();
-				if (tid == 0) S.stop[0] = S.stop[1] = kP1Threads - 1;
+				if (tid == 0) {
+					S.stop[0] = S.stop[1] = kP1Threads - 1;
+					S.front[0] = S.front[1] = kP1Threads;
+					S.nlive[0] = S.nlive[1] = 0;
+				}
 				const uint32_t w0 = (uint32_t)(bitpos >> 5);
 				stage_round(S.in, gwords, w0, nwords, nbytes);
 				__syncthreads();
@@ -779,51 +784,73 @@ __global__ void __launch_bounds__(kP1Threads)
 				const uint32_t limit = r0 + (uint32_t)(tid + 1) * kSubBits;
 				uint32_t entry = r0 + (uint32_t)tid * kSubBits;
 				uint32_t obytes = 0, nmatch = 0, flags = 0;
-				bool changed = true, dead = false;
-				uint32_t passes = 0;
-				int lastlane = kP1Threads - 1;
+				bool need = true, dead = false;
+				uint32_t passes = 0, nlive = kP1Threads, runs = 0;
+				int lastlane = kP1Threads - 1, front = 0;
 				// Lane 0 starts at the true position, the others at a guess; every pass a lane whose entry moved (to the
 				// previous lane's exit) decodes again.  The first lane that stops the block (end of block, error, end of
 				// input) kills the lanes behind it at once: S.stop[pass parity] collects the lowest such lane.
-				for (int it = 0; it < 2 * kP1Threads + 4; it++) {
+				// Codes that re-synchronise (text: within ~120 bits) settle in three or four passes.  Codes that do not (nearly
+				// flat ones: incompressible data in Huffman blocks) would have every lane behind the exact ones decode garbage
+				// again in every pass; so a lane decodes on a guess twice at most, and after that, while more than 16 lanes
+				// still wait, only the lowest waiting lane -- whose entry is exact, all lanes in front of it being settled --
+				// decodes: the round degrades to one serial decoder instead of 128 useless ones.
+				for (int it = 0; it < 2 * kP1Threads + 8; it++) {
 					++passes;
+					const bool run = need && !dead && (runs < 2u || nlive <= 16u || tid == front);
 					SpanB sp;
-					bool act = changed && !dead;
-					if (changed) {
-						span_begin(sp, words, entry);
-						if (dead) sp.fl = (uint32_t)F_DEAD;
-					}
+					bool act = run;
+					if (run) span_begin(sp, words, entry);
 					while (__any_sync(0xffffffffu, act)) {
 						if (act) act = span_step2<0>(S.sh, words, sp, limit, end_rel, nullptr, 0, nullptr);
 						__syncwarp();
 					}
-					if (changed) {
+					if (run) {
 						obytes = sp.o;
 						nmatch = sp.nm;
 						flags = sp.fl;
 						S.exitp[tid] = sp.pos;
 						S.flags[tid] = sp.fl;
 						S.dets[tid] = sp.det;
+						need = false;
+						++runs;
+					} else if (need && dead) {
+						flags = (uint32_t)F_DEAD;
+						S.flags[tid] = (uint32_t)F_DEAD;
+						need = false;
 					}
 					if (flags & (F_EOB | F_ERR | F_OVERRUN)) atomicMin(&S.stop[it & 1], tid);
 					if (tid == 0) S.stop[(it + 1) & 1] = kP1Threads - 1; // (last read before the previous pass's second barrier)
 					__syncthreads();
 					lastlane = S.stop[it & 1];
 					const bool nd = tid > lastlane;
-					changed = nd != dead;
+					if (nd != dead) {
+						need = true;
+						runs = 0; // (back from behind a stop that went away: its guesses count afresh)
+					}
 					dead = nd;
 					if (tid > 0 && !nd) { // (a dead lane's entry does not matter; it is taken afresh should the lane come back)
 						const uint32_t pe = S.exitp[tid - 1];
-						if (pe != entry) changed = true;
-						entry = pe;
+						if (pe != entry) {
+							entry = pe;
+							need = true;
+						}
 					}
+					if (tid == 0) { // (last read behind the previous pass's second barrier, in front of this pass's first)
+						S.front[(it + 1) & 1] = kP1Threads;
+						S.nlive[(it + 1) & 1] = 0;
+					}
+					if (need && !dead) {
+						atomicMin(&S.front[it & 1], tid);
+						atomicAdd(&S.nlive[it & 1], 1u);
+					}
+					const int pending = __syncthreads_count(need ? 1 : 0);
+					front = S.front[it & 1];
+					nlive = S.nlive[it & 1];
 #ifdef B200Z_DEBUG_PASSES
-					{
-						const int nch = __syncthreads_count(changed ? 1 : 0);
-						if (tid == 0) printf("  pass %d: changed %d lastlane %d\n", it, nch, lastlane);
-					}
+					if (tid == 0) printf("  pass %d: pending %d live %u front %d lastlane %d\n", it, pending, nlive, front, lastlane);
 #endif
-					if (!__syncthreads_or(changed ? 1 : 0)) break;
+					if (!pending) break;
 				}
 				if (tid == 0) {
 					atomicAdd(&ctr->n_rounds, 1u);
@@ -998,8 +1025,19 @@ __global__ void k_chain(int n, PSeg *__restrict__ segs, const uint32_t *__restri
 // ---------------------------------------------------------------------------------------------------------
 struct __align__(16) Dec2Shared {
 	InfShared sh;
-	uint32_t in[kP1InSlots];
+	uint32_t in[2][kP1InSlots]; // the round being decoded and the next one, staged with asynchronous copies meanwhile
 };
+
+// a round's words into shared memory, 4 bytes per asynchronous copy (LDGSTS): nobody waits for them here
+__device__ __forceinline__ void stage_round_async(uint32_t *words, const uint32_t *gwords, uint32_t w0, uint32_t nwords) {
+	for (int i = threadIdx.x; i < kP1InWords; i += blockDim.x) {
+		const uint32_t wi = w0 + (uint32_t)i;
+		// (bytes behind the stream's end inside its last word are never looked at: every symbol is checked against end_rel)
+		if (wi < nwords) __pipeline_memcpy_async(&words[in_slot((uint32_t)i)], gwords + wi, 4);
+		else words[in_slot((uint32_t)i)] = 0;
+	}
+	__pipeline_commit();
+}
 
 __global__ void __launch_bounds__(kP1Threads)
     k_dec2(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, const int64_t *__restrict__ in_off, const int64_t *__restrict__ in_len,
@@ -1012,49 +1050,58 @@ __global__ void __launch_bounds__(kP1Threads)
 	uint32_t top = ctr->round_top;
 	if (top > round_cap) top = round_cap;
 	for (uint32_t b0 = blockIdx.x * kRoundBatch; b0 < top; b0 += gridDim.x * kRoundBatch) {
-		bool have_tab = false;
-		for (int k = 0; k < kRoundBatch; k++) {
+		// a batch holds the rounds of ONE block of one segment (or one stored block in its first slot)
+		const PRound &r0 = rounds[b0];
+		if (r0.kind == RND_NONE) continue;
+		const PSeg &seg = segs[r0.seg];
+		if (!seg.valid) continue;
+		const uint32_t stream = seg.stream;
+		uint8_t *dst = out + out_off[stream];
+		if (r0.kind == RND_STORED) {
+			const uint8_t *src = in + in_off[stream] + r0.w0;
+			const uint64_t obase = seg.out_base + r0.out_rel;
+			const uint32_t len = r0.nbytes;
+			for (uint32_t i = tid; i < len; i += kP1Threads) dst[obase + i] = src[i];
+			continue;
+		}
+		const uint32_t nbytes = (uint32_t)in_len[stream], nwords = (nbytes + 3) >> 2;
+		const uint32_t *gwords = reinterpret_cast<const uint32_t *>(in + in_off[stream]);
+		int nr = 1;
+		while (nr < kRoundBatch && rounds[b0 + nr].kind == RND_HUFF) ++nr;
+		__syncthreads(); // the previous batch's lanes are done with the tables and the staged words
+		stage_round_async(S.in[0], gwords, r0.w0, nwords);
+		{
+			const uint4 *src = reinterpret_cast<const uint4 *>(&hdrs[r0.hdr].tab);
+			uint4 *dstv = reinterpret_cast<uint4 *>(&S.sh);
+			for (int i = tid; i < (int)(sizeof(InfShared) / 16); i += kP1Threads) dstv[i] = src[i];
+		}
+		for (int k = 0; k < nr; k++) {
 			const PRound &r = rounds[b0 + k];
-			const uint32_t kind = r.kind;
-			if (kind == RND_NONE) continue;
-			const PSeg &seg = segs[r.seg];
-			if (!seg.valid) continue;
-			const uint32_t stream = seg.stream;
-			uint8_t *dst = out + out_off[stream];
-			const uint64_t obase = seg.out_base + r.out_rel;
-			if (kind == RND_STORED) {
-				const uint8_t *src = in + in_off[stream] + r.w0;
-				const uint32_t len = r.nbytes;
-				for (uint32_t i = tid; i < len; i += kP1Threads) dst[obase + i] = src[i];
-				continue;
+			const uint32_t *words = S.in[k & 1];
+			if (k + 1 < nr) {
+				stage_round_async(S.in[(k + 1) & 1], gwords, rounds[b0 + k + 1].w0, nwords); // (its last readers left at the barrier below)
+				__pipeline_wait_prior(1);
+			} else {
+				__pipeline_wait_prior(0);
 			}
-			__syncthreads(); // the previous round's lanes are done with the staged words (and the tables)
-			if (!have_tab) {
-				const uint4 *src = reinterpret_cast<const uint4 *>(&hdrs[r.hdr].tab);
-				uint4 *dstv = reinterpret_cast<uint4 *>(&S.sh);
-				for (int i = tid; i < (int)(sizeof(InfShared) / 16); i += kP1Threads) dstv[i] = src[i];
-				have_tab = true; // (the barrier behind the staging below covers the tables too)
-			}
-			const uint32_t nbytes = (uint32_t)in_len[stream];
-			stage_round(S.in, reinterpret_cast<const uint32_t *>(in + in_off[stream]), r.w0, (nbytes + 3) >> 2, nbytes);
-			__syncthreads();
+			__syncthreads(); // round k's words (and, for k = 0, the tables) are in place
 			{
 				const bool mine = (uint32_t)tid <= r.lastlane;
 				SpanB sp;
-				span_begin(sp, S.in, mine ? r.entry[tid] : 0u);
+				span_begin(sp, words, mine ? r.entry[tid] : 0u);
 				const uint32_t lim = r.r0 + (uint32_t)(tid + 1) * kSubBits;
-				const uint64_t o0 = obase + (mine ? r.opre[tid] : 0u);
+				const uint64_t o0 = seg.out_base + r.out_rel + (mine ? r.opre[tid] : 0u);
 				MatchTok *ml = mlist + mt_off[stream] + seg.match_base + r.match_rel + (mine ? r.mpre[tid] : 0u);
 				const uint32_t end_rel = r.end_rel;
 				// warp-synchronous: the lanes step together and re-converge every symbol
 				bool act = mine;
 				while (__any_sync(0xffffffffu, act)) {
-					if (act) act = span_step2<1>(S.sh, S.in, sp, lim, end_rel, dst, o0, ml);
+					if (act) act = span_step2<1>(S.sh, words, sp, lim, end_rel, dst, o0, ml);
 					__syncwarp();
 				}
 			}
+			__syncthreads(); // everybody is done with round k's words: the round after next may overwrite them
 		}
-		__syncthreads();
 	}
 }
 
@@ -1065,15 +1112,14 @@ __global__ void __launch_bounds__(kP1Threads)
 // shared-memory read: sources in front of the tile are final, sources inside the tile are resolved by pointer jumping.
 // ---------------------------------------------------------------------------------------------------------
 constexpr int kResRing = 65536;
-constexpr int kResChunk = 1536; // back-references staged at a time
-__device__ __forceinline__ uint32_t res_slot(uint32_t i) { return (i & 15u) * (uint32_t)kResThreads + (i >> 4); }
+constexpr int kResChunk = 2048; // back-references a tile may hold: a tile ends early where the 2048th would start
 struct __align__(16) ResShared {
 	uint8_t ring[kResRing];
-	uint16_t ptr[kResTile];        // for a byte that is a copy: ring index of its source (of a byte further back after a jump);
-	                               // byte 16 t + k of the tile lives in slot k * 1024 + t (res_slot): a warp's accesses to its
-	                               // threads' k-th bytes fall into 16 consecutive words instead of four banks
-	uint16_t copied[kResThreads];  // bit b of copied[t]: byte 16 t + b of the tile is a copy
+	// per byte of the tile: first a mark (index + 1 of the back-reference that STARTS here, 0 = none), then the ring index of
+	// the byte it is a copy of (its own: a literal), after jumps of a byte further back
+	uint16_t ptr[kResTile];
 	MatchTok mch[kResChunk];
+	uint32_t wmax[kResThreads / 32];
 	int cnt_in, cnt_done;
 };
 
@@ -1087,7 +1133,7 @@ __global__ void __launch_bounds__(kResThreads, 2) // two CTAs per SM: 32 registe
 	if (stream >= n || fallback[stream]) return;
 	const uint32_t nm = str_nm[stream];
 	if (nm == 0) return; // no back-reference: the literals are in place
-	const int tid = threadIdx.x;
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	uint8_t *dst = out + out_off[stream];
 	const int64_t total = out_len[stream];
 	const MatchTok *ml = mlist + mt_off[stream];
@@ -1102,163 +1148,196 @@ __global__ void __launch_bounds__(kResThreads, 2) // two CTAs per SM: 32 registe
 	}
 	uint32_t cur_m = 0;
 	const uint4 zero4 = make_uint4(0, 0, 0, 0);
-	// software pipeline: the next tile's bytes (as k_dec2 left them: literals in place) and the next chunk of
-	// back-references are loaded while the current tile is resolved
-	uint4 nxt_tile = zero4;
-	if ((int64_t)tid * 16 + 16 <= total) nxt_tile = *reinterpret_cast<const uint4 *>(dst + tid * 16);
 	MatchTok none;
 	none.out_pos = 0xFFFFFFFFu;
 	none.len = 0;
 	none.dist = 0;
-	MatchTok nxt_m0 = none, nxt_m1 = none; // entries tid and 1024 + tid of the next chunk
-	if ((uint32_t)tid < nm) nxt_m0 = ml[tid];
-	if (tid < kResChunk - kResThreads && (uint32_t)(kResThreads + tid) < nm) nxt_m1 = ml[kResThreads + tid];
-	const int a0 = tid * 16; // this thread's 16 bytes of the tile
-	for (int64_t T0 = 0; T0 < total; T0 += kResTile) {
-		const int tl = (int)(total - T0 < (int64_t)kResTile ? total - T0 : (int64_t)kResTile);
-		const int64_t T1 = T0 + tl;
+	// software pipeline: the next tile's bytes (as k_dec2 left them: literals in place) and the next tile's
+	// back-references are loaded while the current tile is resolved
+	const int a0 = tid * 16; // the 16 consecutive bytes this thread loads, sets up and stores (jumps: bytes tid + 1024 k)
+	uint4 nxt_tile = zero4;
+	if ((int64_t)a0 + 16 <= total) nxt_tile = *reinterpret_cast<const uint4 *>(dst + a0);
+	int64_t nxt_at = 0; // the position nxt_tile was loaded for
+	MatchTok nxt_m0 = (uint32_t)tid < nm ? ml[tid] : none, nxt_m1 = (uint32_t)(kResThreads + tid) < nm ? ml[kResThreads + tid] : none;
+	for (int64_t T0 = 0; T0 < total;) { // T0 stays a multiple of 16
+		int tl = (int)(total - T0 < (int64_t)kResTile ? total - T0 : (int64_t)kResTile);
 		const uint32_t rbase = (uint32_t)T0 & (uint32_t)(kResRing - 1);
 		__syncthreads(); // the previous tile is resolved and written back
+		if (nxt_at != T0) nxt_tile = (int64_t)T0 + a0 + 16 <= total ? *reinterpret_cast<const uint4 *>(dst + T0 + a0) : zero4; // (behind a short tile)
 		if (a0 + 16 <= tl) {
-			*reinterpret_cast<uint4 *>(S.ring + rbase + a0) = nxt_tile;
+			*reinterpret_cast<uint4 *>(S.ring + ((rbase + (uint32_t)a0) & (uint32_t)(kResRing - 1))) = nxt_tile;
 		} else {
-			for (int i = a0; i < tl && i < a0 + 16; i++) S.ring[rbase + i] = dst[T0 + i];
+			for (int i = a0; i < tl && i < a0 + 16; i++) S.ring[(rbase + (uint32_t)i) & (uint32_t)(kResRing - 1)] = dst[T0 + i];
 		}
 		{
-			const int64_t a = T1 + (int64_t)a0;
+			nxt_at = T0 + kResTile;
+			const int64_t a = nxt_at + (int64_t)a0;
 			nxt_tile = a + 16 <= total ? *reinterpret_cast<const uint4 *>(dst + a) : zero4;
 		}
 		if (cur_m >= nm) break; // nothing left to resolve (the remaining tiles are literals only)
-		uint32_t mine = 0; // which of this thread's bytes are copies
-		bool any = false;
-		// ---- the back-references that reach into the tile, a chunk at a time; every thread fills in its own 16 bytes ----
-		for (;;) {
-			if (tid == 0) {
-				S.cnt_in = 0;
-				S.cnt_done = 0;
-			}
-			__syncthreads();
-			{
-				const uint32_t mi0 = cur_m + (uint32_t)tid, mi1 = cur_m + (uint32_t)(kResThreads + tid);
-				int ci = 0, cd = 0;
-				S.mch[tid] = nxt_m0;
-				if (mi0 < nm && (int64_t)nxt_m0.out_pos < T1) {
-					ci++;
-					cd += (int64_t)nxt_m0.out_pos + nxt_m0.len <= T1;
-				}
-				if (tid < kResChunk - kResThreads) {
-					S.mch[kResThreads + tid] = nxt_m1;
-					if (mi1 < nm && (int64_t)nxt_m1.out_pos < T1) {
-						ci++;
-						cd += (int64_t)nxt_m1.out_pos + nxt_m1.len <= T1;
-					}
-				}
-				// (block-wide sums of two small counts)
-				for (int o = 16; o > 0; o >>= 1) {
-					ci += __shfl_xor_sync(0xffffffffu, ci, o);
-					cd += __shfl_xor_sync(0xffffffffu, cd, o);
-				}
-				if ((tid & 31) == 0 && ci) {
-					atomicAdd(&S.cnt_in, ci);
-					atomicAdd(&S.cnt_done, cd);
-				}
-			}
-			__syncthreads();
-			const int n_in = S.cnt_in, n_done = S.cnt_done;
-			cur_m += (uint32_t)n_done;
-			{
-				const uint32_t ni0 = cur_m + (uint32_t)tid, ni1 = cur_m + (uint32_t)(kResThreads + tid);
-				nxt_m0 = ni0 < nm ? ml[ni0] : none;
-				nxt_m1 = (tid < kResChunk - kResThreads && ni1 < nm) ? ml[ni1] : none;
-			}
-			if (n_in) {
-				any = true;
-				const int lo = (int)((int64_t)S.mch[0].out_pos - T0);
-				const MatchTok lastm = S.mch[n_in - 1];
-				const int hi = (int)((int64_t)lastm.out_pos - T0) + lastm.len;
-				if (a0 + 16 > lo && a0 < hi && a0 < tl) {
-					// the last back-reference that starts at or in front of this thread's first byte
-					int j = 0;
-					{
-						int l = 0, r = n_in; // invariant: starts of [0, l) <= a0 < starts of [r, n_in)
-						const int64_t key = T0 + a0;
-						while (l < r) {
-							const int mid = (l + r) >> 1;
-							if ((int64_t)S.mch[mid].out_pos <= key) l = mid + 1;
-							else r = mid;
-						}
-						j = l > 0 ? l - 1 : 0;
-					}
-					const int aend = a0 + 16 < tl ? a0 + 16 : tl;
-					for (; j < n_in; j++) {
-						const MatchTok g = S.mch[j];
-						const int dl = (int)((int64_t)g.out_pos - T0); // may be negative: the reference started in the previous tile
-						if (dl >= aend) break;
-						const int len = g.len, dist = g.dist ? (int)g.dist : 65536; // (never 0 for a decoded back-reference)
-						int p = dl > a0 ? dl : a0;
-						const int pe = dl + len < aend ? dl + len : aend;
-						const uint32_t sbase = rbase + (uint32_t)(dl - dist); // ring position of the source's first byte (mod 65536)
-						if (dist >= len) {
-							for (; p < pe; p++) {
-								S.ptr[res_slot((uint32_t)p)] = (uint16_t)(sbase + (uint32_t)(p - dl));
-								mine |= 1u << (p - a0);
-							}
-						} else { // OutputWindow.Repeat: byte k comes from source byte k mod distance
-							int so = (p - dl) % dist;
-							for (; p < pe; p++) {
-								S.ptr[res_slot((uint32_t)p)] = (uint16_t)(sbase + (uint32_t)so);
-								mine |= 1u << (p - a0);
-								if (++so == dist) so = 0;
-							}
-						}
-					}
-				}
-			}
-			__syncthreads();
-			if (!(n_in == kResChunk && n_done == kResChunk)) break;
+		// ---- the back-references that reach into the tile ----
+		if (tid == 0) {
+			S.cnt_in = 0;
+			S.cnt_done = 0;
 		}
-		if (!any) continue; // no back-reference touches this tile
-		S.copied[tid] = (uint16_t)mine;
+		for (int i = tid; i < kResTile / 2; i += kResThreads) reinterpret_cast<uint32_t *>(S.ptr)[i] = 0; // no marks
+		S.mch[tid] = nxt_m0;
+		S.mch[kResThreads + tid] = nxt_m1;
 		__syncthreads();
-		// a copy whose source is itself a copy inside the tile is not final yet
-		uint32_t unres = 0;
-		for (uint32_t mm = mine; mm; mm &= mm - 1u) {
-			const int b = __ffs((int)mm) - 1;
-			const uint32_t ql = ((uint32_t)S.ptr[(uint32_t)b * kResThreads + tid] - rbase) & (uint32_t)(kResRing - 1);
-			if (ql < (uint32_t)tl && ((S.copied[ql >> 4] >> (ql & 15u)) & 1u)) unres |= 1u << b;
-		}
-		// pointer jumping: a byte takes over its source's source until that is a final byte
-		while (__syncthreads_or(unres != 0)) {
-			for (uint32_t mm = unres; mm; mm &= mm - 1u) {
-				const int b = __ffs((int)mm) - 1;
-				const uint32_t mys = (uint32_t)b * kResThreads + tid;
-				const uint32_t ql = ((uint32_t)S.ptr[mys] - rbase) & (uint32_t)(kResRing - 1);
-				const uint32_t r = S.ptr[res_slot(ql)]; // (whatever ql's owner has made of it by now: always a byte ql is a copy of)
-				S.ptr[mys] = (uint16_t)r;
-				const uint32_t rl = (r - rbase) & (uint32_t)(kResRing - 1);
-				if (!(rl < (uint32_t)tl && ((S.copied[rl >> 4] >> (rl & 15u)) & 1u))) unres &= ~(1u << b);
+		int64_t T1 = T0 + tl;
+		{
+			// a full chunk whose last reference still starts inside the tile: the tile ends (16-byte aligned) in front of it
+			const MatchTok lastm = S.mch[kResChunk - 1];
+			if (cur_m + (uint32_t)kResChunk <= nm && (int64_t)lastm.out_pos < T1) {
+				T1 = (int64_t)lastm.out_pos & ~15ll; // > T0: 2047 references in front of it cover more than 6 KiB
+				tl = (int)(T1 - T0);
 			}
+		}
+		{
+			const uint32_t mi0 = cur_m + (uint32_t)tid, mi1 = cur_m + (uint32_t)(kResThreads + tid);
+			int ci = 0, cd = 0;
+			// a back-reference marks its first byte in the tile with its index in the chunk + 1
+			if (mi0 < nm && (int64_t)nxt_m0.out_pos < T1) {
+				ci++;
+				cd += (int64_t)nxt_m0.out_pos + nxt_m0.len <= T1;
+				const int64_t dl = (int64_t)nxt_m0.out_pos - T0;
+				S.ptr[dl > 0 ? dl : 0] = (uint16_t)(tid + 1);
+			}
+			if (mi1 < nm && (int64_t)nxt_m1.out_pos < T1) {
+				ci++;
+				cd += (int64_t)nxt_m1.out_pos + nxt_m1.len <= T1;
+				const int64_t dl = (int64_t)nxt_m1.out_pos - T0;
+				S.ptr[dl > 0 ? dl : 0] = (uint16_t)(kResThreads + tid + 1);
+			}
+			for (int o = 16; o > 0; o >>= 1) {
+				ci += __shfl_xor_sync(0xffffffffu, ci, o);
+				cd += __shfl_xor_sync(0xffffffffu, cd, o);
+			}
+			if (lane == 0 && ci) {
+				atomicAdd(&S.cnt_in, ci);
+				atomicAdd(&S.cnt_done, cd);
+			}
+		}
+		__syncthreads();
+		const int n_in = S.cnt_in;
+		cur_m += (uint32_t)S.cnt_done;
+		{
+			const uint32_t ni0 = cur_m + (uint32_t)tid, ni1 = cur_m + (uint32_t)(kResThreads + tid);
+			nxt_m0 = ni0 < nm ? ml[ni0] : none;
+			nxt_m1 = ni1 < nm ? ml[ni1] : none;
+		}
+		if (n_in == 0) { // no back-reference touches this tile
+			T0 = T1;
+			continue;
+		}
+		// Which back-reference covers a byte: the last one that starts at or in front of it -- a running maximum over the
+		// marks (they grow with the position).  Every thread scans its 16 consecutive bytes, the threads' totals are scanned
+		// over the warp and the CTA, then every byte turns its owner into the ring index of its source (OutputWindow.Repeat:
+		// byte k of a copy comes from source byte k mod distance) -- a literal into its own.
+		const uint4 mlo = *reinterpret_cast<const uint4 *>(S.ptr + a0), mhi = *reinterpret_cast<const uint4 *>(S.ptr + a0 + 8);
+		uint32_t before;
+		{
+			const uint32_t w[8] = {mlo.x, mlo.y, mlo.z, mlo.w, mhi.x, mhi.y, mhi.z, mhi.w};
+			uint32_t run = 0;
+#pragma unroll
+			for (int k = 0; k < 8; k++) {
+				const uint32_t lo16 = w[k] & 0xFFFFu, hi16 = w[k] >> 16;
+				run = lo16 > run ? lo16 : run;
+				run = hi16 > run ? hi16 : run;
+			}
+			uint32_t incl = run;
+			for (int o = 1; o < 32; o <<= 1) {
+				const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+				if (lane >= o && t > incl) incl = t;
+			}
+			if (lane == 31) S.wmax[warp] = incl;
+			before = __shfl_up_sync(0xffffffffu, incl, 1);
+			if (lane == 0) before = 0;
+		}
+		__syncthreads();
+		for (int w = 0; w < warp; w++) {
+			const uint32_t t = S.wmax[w];
+			before = t > before ? t : before;
+		}
+		{
+			const uint32_t w[8] = {mlo.x, mlo.y, mlo.z, mlo.w, mhi.x, mhi.y, mhi.z, mhi.w};
+			uint32_t res[8];
+			uint32_t run = before;
+#pragma unroll
+			for (int k = 0; k < 16; k++) {
+				const uint32_t mark = (w[k >> 1] >> (16 * (k & 1))) & 0xFFFFu;
+				run = mark > run ? mark : run;
+				const int p = a0 + k;
+				uint32_t val = (rbase + (uint32_t)p) & 0xFFFFu; // a literal: its own source
+				if (run) {
+					const MatchTok g = S.mch[run - 1];
+					const int dl = (int)((int64_t)g.out_pos - T0); // may be negative: the reference started in the previous tile
+					const int kk = p - dl;
+					if (kk < (int)g.len) {
+						const int dist = g.dist ? (int)g.dist : 65536; // (never 0 for a decoded back-reference)
+						const int so = dist >= (int)g.len ? kk : kk % dist;
+						val = (rbase + (uint32_t)(dl - dist + so)) & 0xFFFFu;
+					}
+				}
+				if (k & 1) res[k >> 1] |= val << 16;
+				else res[k >> 1] = val;
+			}
+			*reinterpret_cast<uint4 *>(S.ptr + a0) = make_uint4(res[0], res[1], res[2], res[3]);
+			*reinterpret_cast<uint4 *>(S.ptr + a0 + 8) = make_uint4(res[4], res[5], res[6], res[7]);
+		}
+		__syncthreads();
+		// pointer jumping: a byte takes over its source's source until that is a final byte (one in front of the tile, or a
+		// literal of the tile, which is its own source).  Bytes tid + 1024 k: the warp's accesses are consecutive.
+		uint32_t live = 0xFFFFu;
+		for (;;) {
+			int changed = 0;
+#pragma unroll
+			for (int k = 0; k < 16; k++) {
+				if (!((live >> k) & 1u)) continue;
+				const int i = tid + k * kResThreads;
+				bool keep = false;
+				if (i < tl) {
+					const uint32_t q = S.ptr[i];
+					const uint32_t ql = (q - rbase) & (uint32_t)(kResRing - 1);
+					if (ql < (uint32_t)tl && ql != (uint32_t)i) {
+						const uint32_t r = S.ptr[ql];
+						if (r != q) {
+							S.ptr[i] = (uint16_t)r;
+							changed = 1;
+							keep = true;
+						}
+					}
+				}
+				if (!keep) live &= ~(1u << k);
+			}
+			if (!__syncthreads_or(changed)) break;
 		}
 		// the tile's bytes: copies fetch their final source; into the ring and out (nobody's pointer ends on a copy)
 		if (a0 + 16 <= tl) {
-			uint4 v = *reinterpret_cast<const uint4 *>(S.ring + rbase + a0);
-			uint32_t w[4] = {v.x, v.y, v.z, v.w};
-			for (uint32_t mm = mine; mm; mm &= mm - 1u) {
-				const int b = __ffs((int)mm) - 1;
-				const uint32_t x = S.ring[S.ptr[(uint32_t)b * kResThreads + tid]];
-				w[b >> 2] = (w[b >> 2] & ~(0xFFu << (8 * (b & 3)))) | (x << (8 * (b & 3)));
+			const uint4 lo = *reinterpret_cast<const uint4 *>(S.ptr + a0), hi = *reinterpret_cast<const uint4 *>(S.ptr + a0 + 8);
+			const uint32_t pw[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+			uint32_t w[4];
+#pragma unroll
+			for (int q = 0; q < 4; q++) {
+				uint32_t x = 0;
+#pragma unroll
+				for (int b2 = 0; b2 < 4; b2++) {
+					const int k = q * 4 + b2;
+					x |= (uint32_t)S.ring[(pw[k >> 1] >> (16 * (k & 1))) & 0xFFFFu] << (8 * b2);
+				}
+				w[q] = x;
 			}
-			v = make_uint4(w[0], w[1], w[2], w[3]);
-			*reinterpret_cast<uint4 *>(S.ring + rbase + a0) = v;
+			const uint4 v = make_uint4(w[0], w[1], w[2], w[3]);
+			*reinterpret_cast<uint4 *>(S.ring + ((rbase + (uint32_t)a0) & (uint32_t)(kResRing - 1))) = v;
 			*reinterpret_cast<uint4 *>(dst + T0 + a0) = v;
 		} else {
-			for (uint32_t mm = mine; mm; mm &= mm - 1u) {
-				const int b = __ffs((int)mm) - 1;
-				const uint8_t x = S.ring[S.ptr[(uint32_t)b * kResThreads + tid]];
-				S.ring[rbase + a0 + b] = x;
-				dst[T0 + a0 + b] = x;
+			for (int i = a0; i < tl && i < a0 + 16; i++) {
+				const uint8_t x = S.ring[S.ptr[i]];
+				S.ring[(rbase + (uint32_t)i) & (uint32_t)(kResRing - 1)] = x;
+				dst[T0 + i] = x;
 			}
 		}
+		T0 = T1;
 	}
 }
 

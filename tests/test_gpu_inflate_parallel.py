@@ -101,6 +101,12 @@ def test_foreign_streams_stored_static_and_mixed_blocks(z):
     items.append(zlib.compress(runs, 9)[2:-4])
     mixed = text[:100000] + rnd[:100000] + runs[:100000] + text[100000:200000]
     items.append(zlib.compress(mixed, 6)[2:-4])
+    import random
+    random.seed(3)
+    toks = [bytes(random.randrange(256) for _ in range(4)) for _ in range(40)]
+    dense = b"".join(random.choice(toks) for _ in range(60000))    # thousands of 4..8-byte references per 16 KiB of output
+    items.append(zlib.compress(dense, 6)[2:-4])
+    items.append(zlib.compress(dense[:50000] + runs[:90000] + dense[50000:150000], 4)[2:-4])
     want = [zlib.decompress(c, -15) for c in items]
     res, st, used, _, _, stats = _run_plan(z, items, [len(w) for w in want])
     assert not st.any() and res == want, st
