@@ -262,7 +262,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200z", choices=["b200z", "reference"])
-    ap.add_argument("--config", default="bench", choices=["bench", "c4", "c5"])
+    ap.add_argument("--config", default="bench", choices=["bench", "c4", "c5", "multi"])
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--small", action="store_true", help="1/8 size workload for quick checks (not a bench value)")
     ap.add_argument("--no-probe", dest="no_probe", action="store_true", help="(accepted for older command lines; no effect)")
@@ -278,6 +278,9 @@ def main():
         return
     if args.config == "c5":
         run_c5(args, rank, local_rank, world, out)
+        return
+    if args.config == "multi":
+        run_multi(args, rank, out)
         return
     run_bench(args, rank, local_rank, world, out)
 
@@ -692,6 +695,90 @@ def run_c5(args, rank, local_rank, world, out):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def run_multi(args, rank, out):
+    """ONE host process, 1 .. all visible GPUs: the C3 batch (1024 x 256 KiB, level 6) and the C2 batch (256 x 1 MiB) through
+    b200z_deflate_batch_multi / b200z_inflate_batch_multi on pinned host memory -- strong scaling through the C-ABI, host
+    clock around whole calls (staging, H2D, kernels, packed D2H, hand-over), outputs compared with the oracle / originals."""
+    import torch
+    import oracle_lib as O
+    import sharpziplib_b200 as z
+    if rank != 0:
+        return
+    z.init(0)
+    ndev = z.lib().b200z_device_count()
+    n_def = N_DEFLATE // (8 if args.small else 1)
+    n_inf = N_INFLATE // (8 if args.small else 1)
+    ncpu = host_threads()
+    d_np, t_np = make_inputs(0, n_def, n_inf, max(1, min(32, ncpu)))
+    O.build()
+    comp = O.batch(0, [a.tobytes() for a in t_np], level=6, threads=ncpu)
+    refs = O.batch(0, [a.tobytes() for a in d_np[::max(1, n_def // 32)]], level=6, threads=ncpu)
+
+    def pinned(arrs):
+        t = torch.empty(sum(len(a) for a in arrs) + 64, dtype=torch.uint8).pin_memory()
+        ptrs, pos = [], 0
+        for a in arrs:
+            n = len(a)
+            t[pos:pos + n] = torch.frombuffer(bytearray(a), dtype=torch.uint8) if isinstance(a, (bytes, bytearray)) else torch.from_numpy(a)
+            ptrs.append(t.data_ptr() + pos)
+            pos += n
+        return t, ptrs
+
+    P = z.Pipeline
+    h_din, din_ptrs = pinned(d_np)
+    h_iin, iin_ptrs = pinned(comp)
+    dlens = np.array([a.size for a in d_np], dtype=np.int64)
+    clens = np.array([len(c) for c in comp], dtype=np.int64)
+    dcaps = np.array([z.lib().b200z_deflate_bound(int(a.size)) + 16 for a in d_np], dtype=np.int64)
+    icaps = np.array([a.size for a in t_np], dtype=np.int64)
+    h_dout = torch.empty(int(dcaps.sum()) + 64, dtype=torch.uint8).pin_memory()
+    h_iout = torch.empty(int(icaps.sum()) + 64, dtype=torch.uint8).pin_memory()
+    dout_off = np.concatenate([[0], np.cumsum(dcaps)[:-1]]).astype(np.int64)
+    iout_off = np.concatenate([[0], np.cumsum(icaps)[:-1]]).astype(np.int64)
+    din_p, iin_p = P.pointers(din_ptrs), P.pointers(iin_ptrs)
+    dout_p = P.pointers([h_dout.data_ptr() + int(o) for o in dout_off])
+    iout_p = P.pointers([h_iout.data_ptr() + int(o) for o in iout_off])
+    dl, il, iu = np.zeros(n_def, dtype=np.int64), np.zeros(n_inf, dtype=np.int64), np.zeros(n_inf, dtype=np.int64)
+    dck, ick = np.zeros(n_def, dtype=np.uint32), np.zeros(n_inf, dtype=np.uint32)
+    dst, ist = np.zeros(n_def, dtype=np.int32), np.zeros(n_inf, dtype=np.int32)
+    L = z.lib()
+    U_def, U_inf = int(dlens.sum()), int(icaps.sum())
+    rows = []
+    nd = 1
+    while nd <= ndev:
+        dv = np.arange(nd, dtype=np.int32)
+
+        def step():
+            rc = L.b200z_deflate_batch_multi(dv.ctypes.data, nd, din_p, dlens.ctypes.data, n_def, 6, 0, 0, 0, dout_p, dcaps.ctypes.data,
+                                             dl.ctypes.data, dck.ctypes.data, dst.ctypes.data)
+            assert rc == 0, rc
+            rc = L.b200z_inflate_batch_multi(dv.ctypes.data, nd, iin_p, clens.ctypes.data, n_inf, 0, iout_p, icaps.ctypes.data, il.ctypes.data,
+                                             iu.ctypes.data, ick.ctypes.data, ist.ctypes.data)
+            assert rc == 0, rc
+        for _ in range(2):
+            step()
+        hd = h_dout.numpy()
+        for k, i in enumerate(range(0, n_def, max(1, n_def // 32))):
+            assert hd[dout_off[i]:dout_off[i] + int(dl[i])].tobytes() == refs[k], "deflate parity, %d devices, buffer %d" % (nd, i)
+        hi = h_iout.numpy()
+        for i in range(0, n_inf, max(1, n_inf // 16)):
+            assert np.array_equal(hi[iout_off[i]:iout_off[i] + t_np[i].size], t_np[i]), "inflate, %d devices, stream %d" % (nd, i)
+        reps = max(3, min(args.steps, 5))
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            step()
+        dt = (time.perf_counter() - t0) / reps
+        rows.append({"devices": nd, "ms_per_step": dt * 1e3, "gbs": (U_def + U_inf) / dt / 1e9})
+        nd *= 2
+    for r in rows:
+        r["efficiency_vs_1"] = r["gbs"] / (rows[0]["gbs"] * r["devices"])
+    out.write(json.dumps({"config": "multi", "workload": workload_name(n_def, n_inf).replace(" per GPU", " in all (strong scaling)"),
+                          "how": "one host process, b200z_*_batch_multi on pinned host memory, synchronous calls (no overlap between steps), host clock",
+                          "host_threads": ncpu, "rows": rows}) + "\n")
+    out.flush()
+    z.lib().b200z_release_cached()
 
 
 if __name__ == "__main__":

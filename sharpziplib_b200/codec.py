@@ -67,6 +67,8 @@ class Deflater:
         """Deflate(byte[] output, int offset, int length) -> bytes written (:427).  `output` is a writable buffer
         (bytearray / numpy uint8)."""
         buf = np.frombuffer(output, dtype=np.uint8) if not isinstance(output, np.ndarray) else output
+        if not buf.flags.writeable:
+            raise TypeError("Deflate() writes into `output`: pass a bytearray / writable array, not bytes")
         if length is None:
             length = buf.size - offset
         if offset < 0 or length < 0 or offset + length > buf.size:
@@ -136,6 +138,8 @@ class Inflater:
         if buffer is None:
             raise ValueError("buffer")
         buf = np.frombuffer(buffer, dtype=np.uint8) if not isinstance(buffer, np.ndarray) else buffer
+        if not buf.flags.writeable:
+            raise TypeError("Inflate() writes into `buffer`: pass a bytearray / writable array, not bytes")
         if count is None:
             count = buf.size - offset
         if count < 0:

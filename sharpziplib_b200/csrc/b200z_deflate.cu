@@ -1097,11 +1097,34 @@ int deflate_plan_build(b200z_plan *p) {
 		const int64_t need = (maxlen / 1024 + kRound - 1) / kRound * kRound;
 		if (need > (int64_t)chunk) chunk = (uint32_t)need;
 	}
-	// B200Z_LINK_RUN=<positions>: run length of k_links (a multiple of 32768, 65536 .. 1048576).  Every run but a stream's first
-	// re-walks 32768 positions to warm its head table up, so 64 Ki runs do 37 % more steps than the stream has positions on
-	// 256 KiB buffers and 128 Ki runs 12 %; fewer, longer CTAs on the other hand fill the last wave worse.  Measured on the
-	// B200 (profiles/README.md): 64 Ki runs 0.42 ms, 128 Ki runs 0.57 ms on 64 x 256 KiB -- the default stands.
+	// Run length of k_links (a multiple of 32768, 65536 .. 1048576).  Every run but a stream's first re-walks 32768 positions
+	// to warm its head table up (37 % more steps than positions with 64 Ki runs on 256 KiB buffers, 12 % with 128 Ki runs,
+	// none with 256 Ki runs), while fewer, longer CTAs fill the last wave worse (three CTAs fit an SM).  The plan takes the
+	// length with the smallest estimate of waves x steps per run; B200Z_LINK_RUN=<positions> overrides it for timing.
 	p->link_run = kRun;
+	{
+		int sms = 148;
+		int dev = 0;
+		if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+		const int64_t slots = 3ll * sms;
+		double best = 0;
+		for (int64_t run = 65536; run <= 1048576; run *= 2) {
+			int64_t ctas = 0, longest = 0;
+			for (int i = 0; i < n; i++) {
+				const int64_t len = p->in_len[i];
+				ctas += (len + run - 1) / run;
+				const int64_t first = len < run ? len : run;
+				const int64_t steps = len > run ? run + 32768 : first; // a run behind the first also walks its warm-up
+				longest = steps > longest ? steps : longest;
+			}
+			const double est = (double)((ctas + slots - 1) / slots) * (double)longest;
+			if (best == 0 || est < best * 0.97) { // (a longer run has to win clearly: its CTAs are the less balanced ones)
+				best = est;
+				p->link_run = (int)run;
+			}
+			if (run >= maxlen) break;
+		}
+	}
 	if (const char *e = getenv("B200Z_LINK_RUN")) {
 		const long v = atol(e);
 		if (v >= 65536 && v <= 1048576 && v % 32768 == 0) p->link_run = (int)v;

@@ -752,7 +752,10 @@ __global__ void __launch_bounds__(kInfThreads)
 			}
 		}
 		__syncthreads();
-		if (S.a_done && !S.ri[r0i].valid && !S.ri[r1i].valid) break; // A has nothing more, B1 and B2 nothing left to take over
+		// (the three flags into registers, then a second barrier: warp A's next iteration overwrites them)
+		const bool stop_now = S.a_done && !S.ri[r0i].valid && !S.ri[r1i].valid;
+		__syncthreads();
+		if (stop_now) break; // A has nothing more, B1 and B2 nothing left to take over
 	}
 	if (threadIdx.x == 0) {
 		status[stream] = st | (detail << 8);

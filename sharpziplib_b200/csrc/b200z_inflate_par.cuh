@@ -564,7 +564,7 @@ __device__ __forceinline__ void stage_round(uint32_t *words, const uint32_t *gwo
 		words[in_slot((uint32_t)i)] = ld_stream_word(gwords, w0 + (uint32_t)i, nwords, nbytes);
 }
 
-__global__ void __launch_bounds__(kP1Threads)
+__global__ void __launch_bounds__(kP1Threads, 10) // 48 registers: ten CTAs per SM (the header parse would take 64)
     k_dec1(const uint8_t *__restrict__ in, const int64_t *__restrict__ in_off, const int64_t *__restrict__ in_len, PSeg *__restrict__ segs,
            const uint32_t *__restrict__ seg_list, PCounters *__restrict__ ctr, const uint32_t *__restrict__ win_base,
            const uint32_t *__restrict__ cand, PRound *__restrict__ rounds, uint32_t round_cap, PBlockHdr *__restrict__ hdrs,

@@ -211,6 +211,8 @@ class GZipInputStream(InflaterInputStream):
     trailing garbage and ends the stream quietly (:107-123), a member cut short hands out what was decoded and then
     raises."""
 
+    MAX_MEMBER_OUTPUT = 1 << 32  # a member that inflates to more is refused (a 1 KiB gzip bomb asks for gigabytes otherwise)
+
     def __init__(self, baseInputStream, size=4096):
         super().__init__(baseInputStream, Inflater(True), size)
         self._data = None
@@ -228,7 +230,7 @@ class GZipInputStream(InflaterInputStream):
             return
         from . import _lib
         from .batch import inflate_batch
-        d = self._data = self.baseInputStream.read()
+        d = self._data = memoryview(self.baseInputStream.read())  # (members are slices of one buffer, not copies)
         pos, completed = 0, False
         while pos < len(d):
             blob = d[pos:]
@@ -236,15 +238,17 @@ class GZipInputStream(InflaterInputStream):
             while True:
                 outs, used, st = inflate_batch([blob], [cap], raise_on_error=False, wrap=_lib.WRAP_GZIP)
                 code, detail = int(st[0]) & 0xFF, int(st[0]) >> 8
-                if code != _lib.E_NOMEM or cap > (1 << 34):
+                if code != _lib.E_NOMEM:
                     break
-                cap *= 8
+                if cap >= self.MAX_MEMBER_OUTPUT:
+                    raise SharpZipBaseException("gzip member inflates to more than %d bytes (GZipInputStream.MAX_MEMBER_OUTPUT)" % self.MAX_MEMBER_OUTPUT)
+                cap = min(cap * 8, self.MAX_MEMBER_OUTPUT)
             header_failed = int(used[0]) == 0 and (code == _lib.E_NEED_INPUT or (code == _lib.E_DATA and 14 <= detail <= 18))
             if code == _lib.OK:
                 self._out += outs[0]
                 if blob[3] & 0x08:  # FNAME: zero terminated, behind the optional FEXTRA (:248-270)
                     q = 10 + ((2 + (blob[10] | (blob[11] << 8))) if blob[3] & 0x04 else 0)
-                    self._fileName = bytes(blob[q:blob.index(0, q)]).decode("cp1252", "replace")
+                    self._fileName = bytes(blob[q:q + bytes(blob[q:q + 65536]).index(0)]).decode("cp1252", "replace")
                 else:
                     self._fileName = None
                 pos += int(used[0])

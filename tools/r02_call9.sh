@@ -1,0 +1,26 @@
+#!/bin/bash
+# N GPUs of one box (N = number visible): weak and strong scaling under torchrun, one process on 1..N devices, config C5 on N GPUs
+set -u
+N=$(python -c "import torch; print(torch.cuda.device_count())")
+O=gpurun_out/r02_c9_n$N
+mkdir -p $O
+TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
+python -m pytest tests/test_gpu_inflate_parallel.py -m gpu -q -x --timeout 600 -k "several_devices" 2>&1 | tail -3
+timeout 900 $TR --master-port 29511 bench.py --gpus $N --steps 5 --warmup 3 > $O/weak.json 2> $O/weak.err; echo "weak rc=$?"
+timeout 900 $TR --master-port 29512 bench.py --gpus $N --steps 5 --warmup 3 --scaling strong > $O/strong.json 2> $O/strong.err; echo "strong rc=$?"
+timeout 900 python bench.py --config multi --steps 3 > $O/multi.json 2> $O/multi.err; echo "multi rc=$?"
+timeout 1500 $TR --master-port 29513 bench.py --gpus $N --config c5 > $O/c5.json 2> $O/c5.err; echo "c5 rc=$?"
+python - <<PY
+import json
+for f in ("weak","strong"):
+    try:
+        d=json.loads(open("$O/%s.json"%f).read().strip().splitlines()[-1]); print(f, d["n_gpus"], round(d["value"],2), round(d["e2e"]["value"],2), d["scaling"])
+    except Exception as e: print(f,"ERR",e)
+try:
+    d=json.loads(open("$O/multi.json").read().strip().splitlines()[-1]); print("multi", [(r["devices"], round(r["gbs"],2), round(r["efficiency_vs_1"],2)) for r in d["rows"]])
+except Exception as e: print("multi ERR", e)
+try:
+    d=json.loads(open("$O/c5.json").read().strip().splitlines()[-1]); print("c5", d["n_gpus"], d["all_parity"], [(p["level"],p["size"],round(p["gbs"],1)) for p in d["points"]])
+except Exception as e: print("c5 ERR", e)
+PY
+tail -3 $O/*.err
