@@ -297,8 +297,24 @@ struct FastEngine {
 	uint32_t inputOff;    // stream bytes handed to the window so far
 	uint32_t nsym;        // symbols tallied in the current block
 	int coop;             // 1: never slide inside the engine, report kFeNeedSlide instead (the kernel slides warp-wide)
+	                      // 2: also report kFeGroup at a loop top from which the kernel's warp-wide group step may run
 };
-constexpr int kFeFalse = 0, kFeTrue = 1, kFeNeedSlide = 2;
+constexpr int kFeFalse = 0, kFeTrue = 1, kFeNeedSlide = 2, kFeGroup = 3;
+constexpr int kFeGroupMin = 8; // fewer steady-state loop tops than this ahead: the serial loop takes them
+
+// How many of the next DeflateFast loop tops (strstart, strstart + 1, ...) are certain to be steady-state iterations
+// whatever the parse does: lookahead >= MIN_LOOKAHEAD at each (so maxlen = 258, niceLength = nice, every lookahead test of
+// :684-:715 true), no SlideWindow due (:668), no full block (:718) -- a literal or a match per loop top at most.
+B200Z_HD int fe_group_lanes(int strstart, int lookahead, uint32_t nsym) {
+	int nl = 32;
+	const int a = lookahead - (kMaxMatch + kMinMatch + 1) + 1;
+	const int b = 2 * kWSize - (kMaxMatch + kMinMatch + 1) + 1 - strstart;
+	const int c = kBlockSyms - 1 - (int)nsym;
+	if (a < nl) nl = a;
+	if (b < nl) nl = b;
+	if (c < nl) nl = c;
+	return nl;
+}
 
 // What DeflateFast carries from one Deflate() call to the next besides head[] / prev[] (DeflaterEngine's fields): saved
 // when a segment ends with Flush(), loaded when the stream goes on (b200z_history.engine_state).
@@ -498,6 +514,7 @@ B200Z_HDN int fe_deflate_fast(FastEngine &e, bool flush, bool finish, const Leve
 			if (e.coop) return kFeNeedSlide;
 			fe_slide(e);
 		}
+		if (e.coop == 2 && strategy != 2 && fe_group_lanes(e.strstart, e.lookahead, e.nsym) >= kFeGroupMin) return kFeGroup;
 		int hashHead;
 		if (e.lookahead >= kMinMatch && (hashHead = fe_insert_string(e)) != 0 && strategy != 2 &&
 		    e.strstart - hashHead <= kMaxDist && fe_find_longest_match(e, hashHead, lp)) {

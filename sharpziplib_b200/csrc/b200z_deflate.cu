@@ -674,23 +674,253 @@ __global__ void __launch_bounds__(128)
 // reference's own head[]/prev[] tables (shared memory, 128 KiB); SlideWindow's table sweep is done by the whole warp.
 // All streams of the batch run concurrently (one warp each).  Symbols and block cuts feed k_plan / k_scan / k_emit.
 // ------------------------------------------------------------------------------------------------
-constexpr int kFastSmem = 2 * 32768 * 2;
+constexpr int kFastSmem = 2 * 32768 * 2; // prev[] (+ head[] when a batch has no more streams than the GPU has SMs)
 
-__global__ void __launch_bounds__(32)
-    k_fast(const uint8_t *__restrict__ in, uint32_t *__restrict__ sym, const int64_t *__restrict__ in_off,
-           const int64_t *__restrict__ in_len, uint32_t *__restrict__ nsyms, uint32_t *__restrict__ nblocks,
-           const uint32_t *__restrict__ blk_off, uint32_t *__restrict__ blk_start, uint32_t *__restrict__ blk_ptop,
-           const uint32_t *__restrict__ hist, LevelParams lp, int strategy, int end_mode, int prev_entries,
-           const uint32_t *__restrict__ sched, const uint32_t *__restrict__ sched_off, const int32_t *__restrict__ undrained,
-           uint8_t *const *__restrict__ fstate, int cont) {
+// eight window bytes starting at slot byte `a`, first byte in the low bits of lo (aligned words; the slot is 256-byte
+// aligned and has 16 bytes of slack behind its data)
+__device__ __forceinline__ void fast_load8(const uint8_t *__restrict__ in, uint32_t a, uint32_t &lo, uint32_t &hi) {
+	const uint32_t *p = reinterpret_cast<const uint32_t *>(in + (a & ~3u));
+	const uint32_t w0 = p[0], w1 = p[1], w2 = p[2];
+	const uint32_t sh = (a & 3u) * 8u;
+	lo = __funnelshift_r(w0, w1, sh);
+	hi = __funnelshift_r(w1, w2, sh);
+}
+
+// The warp-wide group step of DeflateFast (DeflaterEngine.cs:651-739), `nl` consecutive loop tops at once.
+//
+// What makes DeflateFast serial is that a match longer than max_lazy leaves its inner positions out of the hash chains
+// (:699-715); a literal or a match of at most max_lazy bytes inserts every position it covers.  So as long as no long match
+// is taken, "every position of the group is a chain member" is the truth, and the searches of all loop tops can run at once:
+// lane j takes window index s0 + j, its chain head is the nearest lower lane with the same hash (else head[]), links of
+// group positions are written to prev[] up front (slots of positions further back than MAX_DIST are never read again), every
+// lane runs FindLongestMatch from matchLen = 2 with the level's chain budget and remembers which group positions it
+// tested (`used`).  The parse is replayed over the lanes' results in order by a cursor v that all lanes keep: a lane is
+// resolved once its walk is complete; a long match at lane v takes positions v+1 .. v+len-1 out (set N) and ends their
+// walks; a later lane whose walk touched N is not trusted -- the group ends in front of it and the next step starts there.
+// Lanes behind a long match that never touched N saw exactly the chains the reference sees (a walk that read a link into N
+// either tested that position -- then it is in `used` -- or had run out of budget).  At commit the links of the inserted
+// positions are recomputed over the inserted lanes only, head[] gets the last inserted position of every hash, the visited
+// lanes write their symbols in order.
+//
+// Latency is what this kernel pays for, so: a lane gathers up to four chain members before it loads any of them (one
+// memory round trip per four candidates); a candidate that still matches after 16 bytes waits until its lane is the
+// cursor and is then extended by the whole warp (8 bytes per lane) -- lanes inside a long repeat never get there, the match
+// of the lane in front of them covers them first.
+//
+// s0 / la / nsym / total: the engine's strstart, lookahead, symbols in the block, symbols written (uniform over the warp; the
+// caller keeps lane 0's FastEngine in step).  Returns 1 if the last action was a long match (UpdateHash is due, :712-714).
+__device__ __forceinline__ int fast_lcp8(uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi) {
+	uint32_t x = alo ^ blo;
+	if (x) return (__ffs((int)x) - 1) >> 3;
+	x = ahi ^ bhi;
+	if (x) return 4 + ((__ffs((int)x) - 1) >> 3);
+	return 8;
+}
+
+__device__ __forceinline__ int fast_group_step(const uint8_t *__restrict__ in, uint32_t woff, uint16_t *head, uint16_t *prev,
+                                               const LevelParams &lp, int lane, int nl, int &s0, int &la, uint32_t &nsym,
+                                               uint32_t *__restrict__ sout, uint32_t &total, int &last_h, int &match_start) {
+	const uint32_t full = 0xffffffffu;
+	const uint32_t lt = (1u << lane) - 1u;
+	const int q = s0 + lane;
+	const uint32_t qa = (uint32_t)q + woff;
+	const bool active = lane < nl;
+	uint32_t lo, hi;
+	fast_load8(in, qa, lo, hi);
+#if !defined(B200Z_EMU)
+	// the bytes a later step starts from: one 128-byte line per lane pair, 2 KiB ahead (reads past the slot stay inside the
+	// plan's input blob or its tail padding; a prefetch does not fault)
+	if (la > 4096 && (lane & 1)) asm volatile("prefetch.global.L2 [%0];" ::"l"(in + ((qa + 2048u + 64u * (uint32_t)lane) & ~127u)));
+#endif
+	const uint32_t h = hash3(lo & 255u, (lo >> 8) & 255u, (lo >> 16) & 255u);
+	const int hh = head[h];
+	const uint32_t same = __match_any_sync(full, active ? h : (0x8000u | (uint32_t)lane));
+	const uint32_t pm = same & lt;
+	const int cand0 = pm ? s0 + (31 - __clz((int)pm)) : hh;
+	if (active) prev[q & 32767] = (uint16_t)cand0;
+	__syncwarp();
+
+	// FindLongestMatch (:474-612) from matchLen = MIN_MATCH - 1: the longest common prefix with every chain member in chain
+	// order, the first longest wins, stop at nice_length; the reference's scan_end tests only skip members that cannot win
+	int best = kMinMatch - 1, bestc = 0, chain = lp.chain;
+	uint32_t used = 0;
+	const int limit = q - kMaxDist > 0 ? q - kMaxDist : 0;
+	int cand = (active && cand0 != 0 && q - cand0 <= kMaxDist) ? cand0 : 0; // next chain member to gather (0: none left)
+	bool go = cand != 0;    // the walk is not complete
+	bool pend = false;      // the member at bi matches for >= 16 bytes and waits for the warp
+	int c0 = 0, c1 = 0, c2 = 0, c3 = 0, nb = 0, bi = 0;
+	uint32_t l0 = 0, h0 = 0, l1 = 0, h1 = 0, l2 = 0, h2 = 0, l3 = 0, h3 = 0;
+	uint32_t visited = 0, N = 0;
+	int v = 0, last_long = 0;
+	bool stop = false;
+	for (;;) {
+		if (go && bi == nb) {
+			// the next (up to) four members: `do test while ((cur = prev[cur]) > limit && --chain)`
+			nb = 0;
+			bi = 0;
+#define B200Z_GATHER(C)                                                                                                           \
+	if (cand) {                                                                                                                    \
+		C = cand;                                                                                                                   \
+		++nb;                                                                                                                       \
+		const int nx = prev[cand & 32767];                                                                                          \
+		cand = (nx > limit && --chain != 0) ? nx : 0;                                                                               \
+	}
+			B200Z_GATHER(c0)
+			B200Z_GATHER(c1)
+			B200Z_GATHER(c2)
+			B200Z_GATHER(c3)
+#undef B200Z_GATHER
+			if (nb > 0) fast_load8(in, (uint32_t)c0 + woff, l0, h0);
+			if (nb > 1) fast_load8(in, (uint32_t)c1 + woff, l1, h1);
+			if (nb > 2) fast_load8(in, (uint32_t)c2 + woff, l2, h2);
+			if (nb > 3) fast_load8(in, (uint32_t)c3 + woff, l3, h3);
+			if (nb == 0) go = false;
+		}
+#define B200Z_TEST(K, C, CL, CH)                                                                                                 \
+	if (go && !pend && bi == K && K < nb) {                                                                                        \
+		if (C >= s0) used |= 1u << (C - s0);                                                                                        \
+		int l = fast_lcp8(CL, CH, lo, hi);                                                                                          \
+		if (l == 8) {                                                                                                               \
+			uint32_t a0, a1, b0, b1;                                                                                                 \
+			fast_load8(in, (uint32_t)C + woff + 8u, a0, a1);                                                                         \
+			fast_load8(in, qa + 8u, b0, b1);                                                                                         \
+			l += fast_lcp8(a0, a1, b0, b1);                                                                                          \
+		}                                                                                                                           \
+		if (l == 16) {                                                                                                              \
+			pend = true;                                                                                                             \
+		} else {                                                                                                                    \
+			if (l > best) {                                                                                                          \
+				best = l;                                                                                                             \
+				bestc = C;                                                                                                            \
+				if (best >= lp.nice) go = false;                                                                                      \
+			}                                                                                                                        \
+			bi = K + 1;                                                                                                              \
+		}                                                                                                                           \
+	}
+		B200Z_TEST(0, c0, l0, h0)
+		B200Z_TEST(1, c1, l1, h1)
+		B200Z_TEST(2, c2, l2, h2)
+		B200Z_TEST(3, c3, l3, h3)
+#undef B200Z_TEST
+		if (go && !pend && bi == nb && cand == 0) go = false; // every member tested
+		// the cursor's lane is extended by the warp: lane k compares bytes 16 + 8k .. 16 + 8k + 7 (MAX_MATCH = 258 < 16 + 256)
+		if (__shfl_sync(full, (int)pend, v)) {
+			const int pc = bi == 0 ? c0 : bi == 1 ? c1 : bi == 2 ? c2 : c3;
+			const uint32_t ca = (uint32_t)__shfl_sync(full, pc, v) + woff + 16u + 8u * (uint32_t)lane;
+			const uint32_t sa = (uint32_t)(s0 + v) + woff + 16u + 8u * (uint32_t)lane;
+			int first = 8;
+			if (16 + 8 * lane < kMaxMatch) {
+				uint32_t a0, a1, b0, b1;
+				fast_load8(in, ca, a0, a1);
+				fast_load8(in, sa, b0, b1);
+				first = fast_lcp8(a0, a1, b0, b1);
+			}
+			const uint32_t mm = __ballot_sync(full, first < 8);
+			const int fl = mm ? __ffs((int)mm) - 1 : 0;
+			const int ff = __shfl_sync(full, first, fl);
+			int ll = mm ? 16 + 8 * fl + ff : kMaxMatch;
+			if (ll > kMaxMatch) ll = kMaxMatch;
+			if (lane == v) {
+				pend = false;
+				if (ll > best) {
+					best = ll;
+					bestc = pc;
+					if (best >= lp.nice) go = false;
+				}
+				++bi;
+				if (go && bi == nb && cand == 0) go = false;
+			}
+		}
+		// replay: the cursor passes every lane whose walk is complete
+		const uint32_t fin = __ballot_sync(full, !go);
+		if ((fin >> v) & 1u) {
+			const uint32_t litm = __ballot_sync(full, active && best < kMinMatch);
+			const uint32_t shortm = __ballot_sync(full, best >= kMinMatch && best <= lp.lazy);
+			const uint32_t e0 = __ballot_sync(full, best & 1), e1 = __ballot_sync(full, best & 2), e2 = __ballot_sync(full, best & 4);
+			uint32_t bad = N ? __ballot_sync(full, (used & N) != 0) : 0u;
+			while (v < nl && ((fin >> v) & 1u)) {
+				if ((bad >> v) & 1u) {
+					stop = true;
+					break;
+				}
+				if ((litm >> v) & 1u) {
+					const uint32_t r = ~((litm & fin & ~bad) >> v); // a run of literals
+					const int run = r ? __ffs((int)r) - 1 : 32 - v;
+					visited |= (run >= 32 ? full : ((1u << run) - 1u)) << v;
+					v += run;
+					last_long = 0;
+				} else if ((shortm >> v) & 1u) {
+					const int L = (int)(((e0 >> v) & 1u) | (((e1 >> v) & 1u) << 1) | (((e2 >> v) & 1u) << 2));
+					if (v + L > nl) { // its inner positions would need inserting behind the group: the next step takes it
+						stop = true;
+						break;
+					}
+					visited |= 1u << v;
+					v += L;
+					last_long = 0;
+				} else {
+					const int L = __shfl_sync(full, best, v);
+					visited |= 1u << v;
+					const int lo_b = v + 1, hi_b = v + L < 32 ? v + L : 32; // positions v+1 .. v+L-1 are not inserted
+					if (hi_b > lo_b) N |= (hi_b >= 32 ? full : ((1u << hi_b) - 1u)) & ~((1u << lo_b) - 1u);
+					if ((N >> lane) & 1u) { // covered: nobody will ask for this lane's result
+						go = false;
+						pend = false;
+					}
+					bad = __ballot_sync(full, (used & N) != 0);
+					v += L;
+					last_long = 1;
+				}
+			}
+			if (stop || v >= nl) break;
+		}
+	}
+	const int len = best >= kMinMatch ? best : 0;
+	// commit
+	const uint32_t below = v >= 32 ? full : ((1u << v) - 1u);
+	const uint32_t ins = below & ~N & (nl >= 32 ? full : ((1u << nl) - 1u));
+	const bool inserted = (ins >> lane) & 1u;
+	if (inserted) {
+		if (N) {
+			const uint32_t pi = same & ins & lt;
+			prev[q & 32767] = (uint16_t)(pi ? s0 + (31 - __clz((int)pi)) : hh);
+		}
+		if (((same & ins) >> lane) == 1u) head[h] = (uint16_t)q;
+	}
+	if ((visited >> lane) & 1u)
+		sout[total + (uint32_t)__popc(visited & lt)] = len ? sym_match((uint32_t)len, (uint32_t)(q - bestc)) : sym_lit(lo & 255u);
+	const uint32_t vm = __ballot_sync(full, ((visited >> lane) & 1u) && len != 0);
+	if (vm) match_start = __shfl_sync(full, bestc, 31 - __clz((int)vm));
+	if (!last_long) last_h = (int)__shfl_sync(full, h, (v - 1) & 31);
+	const int nv = __popc(visited);
+	total += (uint32_t)nv;
+	nsym += (uint32_t)nv;
+	s0 += v;
+	la -= v;
+	__syncwarp();
+	return last_long;
+}
+
+// B200Z_FAST_GROUP=0 keeps every loop top on lane 0 (the serial statement; for measurements and for the tests that compare)
+static int fast_group_enabled() {
+	const char *e = getenv("B200Z_FAST_GROUP");
+	return !(e && e[0] == '0');
+}
+
+// One stream's DeflateFast run by one warp.  head[] (32768 entries, read once per loop top) lives in the CTA's slot of a
+// global pool and stays in L2; prev[] (read for every chain member) is the CTA's shared memory.
+__device__ __forceinline__ void fast_stream(const int stream, const int lane, uint16_t *head, uint16_t *prev, const uint8_t *__restrict__ in,
+                                            uint32_t *__restrict__ sym, const int64_t *__restrict__ in_off,
+                                            const int64_t *__restrict__ in_len, uint32_t *__restrict__ nsyms,
+                                            uint32_t *__restrict__ nblocks, const uint32_t *__restrict__ blk_off,
+                                            uint32_t *__restrict__ blk_start, uint32_t *__restrict__ blk_ptop,
+                                            const uint32_t *__restrict__ hist, const LevelParams &lp, int strategy, int end_mode,
+                                            int prev_entries, const uint32_t *__restrict__ sched, const uint32_t *__restrict__ sched_off,
+                                            const int32_t *__restrict__ undrained, uint8_t *const *__restrict__ fstate, int cont,
+                                            int group) {
 	// prev[] is indexed by window position & 32767; when no stream of the batch is longer than prev_entries - 2 bytes the
 	// positions never reach prev_entries, so the table (and the CTA's shared-memory footprint) can be that much smaller
-	// and three CTAs share an SM instead of one.  (Plans that carry engine state between segments use whole tables.)
-	extern __shared__ __align__(16) uint8_t fsm[];
-	uint16_t *head = reinterpret_cast<uint16_t *>(fsm);
-	uint16_t *prev = head + 32768;
-	const int lane = threadIdx.x;
-	const int stream = blockIdx.x;
+	// and more CTAs share an SM.  (Plans that carry engine state between segments use whole tables.)
 	const uint32_t n = (uint32_t)in_len[stream];
 	const int64_t off = in_off[stream];
 	uint32_t *sout = sym + off;
@@ -702,17 +932,19 @@ __global__ void __launch_bounds__(32)
 	if (resume) {
 		// the stream goes on behind a Flush(): tables and scalars as the previous segment's run left them
 		const uint4 *src = reinterpret_cast<const uint4 *>(st);
-		for (int i = lane; i < 131072 / 16; i += 32) reinterpret_cast<uint4 *>(fsm)[i] = src[i];
+		for (int i = lane; i < 65536 / 16; i += 32) reinterpret_cast<uint4 *>(head)[i] = src[i];
+		for (int i = lane; i < 65536 / 16; i += 32) reinterpret_cast<uint4 *>(prev)[i] = src[65536 / 16 + i];
 		__syncwarp();
 		FastCarry c = *reinterpret_cast<const FastCarry *>(st + 131072);
 		fe_load(e, c, in + off, n, hist[stream], head, prev);
 	} else {
-		for (int i = lane; i < (32768 + prev_entries) / 2; i += 32) reinterpret_cast<uint32_t *>(fsm)[i] = 0;
+		for (int i = lane; i < 65536 / 16; i += 32) reinterpret_cast<uint4 *>(head)[i] = make_uint4(0u, 0u, 0u, 0u);
+		for (int i = lane; i < prev_entries / 2; i += 32) reinterpret_cast<uint32_t *>(prev)[i] = 0;
 		__syncwarp();
 		fe_init(e, in + off, n, head, prev);
 		if (lane == 0) fe_set_dictionary(e, hist[stream]); // preset dictionary in front of the data (0 = none)
 	}
-	e.coop = 1;
+	e.coop = group ? 2 : 1;
 	// the SetInput schedule of the segment (fe_run in b200z_core.cuh is the serial statement of this loop)
 	const uint32_t *cum = sched + sched_off[stream];
 	const int nsched = (int)(sched_off[stream + 1] - sched_off[stream]);
@@ -725,6 +957,9 @@ __global__ void __launch_bounds__(32)
 		e.n = seg_base + (nsched > 0 ? cum[0] : seg_len);
 	}
 	uint32_t total = 0, nblk = 0;
+#ifdef B200Z_FAST_STATS
+	uint32_t st_steps = 0, st_pos = 0, st_lanes = 0;
+#endif
 	int ci = 0;
 	int phase = (nc == 1 && !busy_last) ? 1 : 0; // 0: BUSY_STATE drain of chunk ci, 1: Flush()/Finish()
 	bool in_deflate = false; // re-entering DeflateFast after a cooperative slide must not run FillWindow again
@@ -746,19 +981,62 @@ __global__ void __launch_bounds__(32)
 					    bptop[nblk] = ok ? 0xFFFFFFFEu : 0xFFFFFFFFu; // storedOffset sign decided by the engine (trap T4)
 					    ++nblk;
 				    });
-				if (r != kFeNeedSlide) in_deflate = false;
+				if (r != kFeNeedSlide && r != kFeGroup) in_deflate = false;
 			}
+		}
+		r = __shfl_sync(0xffffffffu, r, 0);
+		if (r == kFeGroup) {
+			// steady-state loop tops ahead: the warp takes them in groups (fast_group_step) until a slide, a full block or the
+			// end of the lookahead comes near; lane 0's engine is brought in step afterwards
+			int s0 = __shfl_sync(0xffffffffu, e.strstart, 0), la = __shfl_sync(0xffffffffu, e.lookahead, 0);
+			uint32_t nsym = __shfl_sync(0xffffffffu, e.nsym, 0);
+			const uint32_t woff = __shfl_sync(0xffffffffu, e.woff, 0);
+			total = __shfl_sync(0xffffffffu, total, 0);
+			int last_h = 0, match_start = __shfl_sync(0xffffffffu, e.matchStart, 0), last_long = 0, nl;
+			while ((nl = fe_group_lanes(s0, la, nsym)) >= kFeGroupMin) {
+#ifdef B200Z_FAST_STATS
+				const int s_before = s0;
+#endif
+				last_long = fast_group_step(in + off, woff, head, prev, lp, lane, nl, s0, la, nsym, sout, total, last_h, match_start);
+#ifdef B200Z_FAST_STATS
+				++st_steps;
+				st_pos += (uint32_t)(s0 - s_before);
+				st_lanes += (uint32_t)(s0 - s_before < 32 ? s0 - s_before : 32);
+#endif
+			}
+			if (lane == 0) {
+				e.strstart = s0;
+				e.lookahead = la;
+				e.nsym = nsym;
+				e.matchStart = match_start;
+				e.matchLen = kMinMatch - 1;
+				if (last_long)
+					fe_update_hash(e); // :712-714 (lookahead >= MIN_MATCH - 1 holds: it was >= 262 before a match of <= 258)
+				else
+					e.ins_h = last_h;
+				// back at the top of DeflateFast's loop: `while (lookahead >= MIN_LOOKAHEAD || flush)` (:658)
+				const bool flush = phase == 1 && e.inputOff == e.n;
+				if (e.lookahead < kMaxMatch + kMinMatch + 1 && !flush) {
+					in_deflate = false; // the loop ends, DeflateFast returns true (:738)
+					r = kFeTrue;
+				}
+			}
+			r = __shfl_sync(0xffffffffu, r, 0);
+			if (r == kFeGroup) continue; // lane 0 goes on inside DeflateFast (in_deflate is still set)
 		}
 		r = __shfl_sync(0xffffffffu, r, 0);
 		if (r == kFeNeedSlide) {
 			// SlideWindow (DeflaterEngine.cs:441-462): scalars by lane 0, both tables by the warp
 			if (lane == 0) fe_slide_scalars(e);
-			for (int i = lane; i < 32768; i += 32) { // 2 entries per 32-bit word, head and prev are contiguous
-				uint32_t v = reinterpret_cast<uint32_t *>(fsm)[i];
-				uint32_t lo = v & 0xFFFFu, hi = v >> 16;
-				lo = lo >= 32768u ? lo - 32768u : 0u;
-				hi = hi >= 32768u ? hi - 32768u : 0u;
-				reinterpret_cast<uint32_t *>(fsm)[i] = lo | (hi << 16);
+			for (int t = 0; t < 2; t++) { // 2 entries per 32-bit word (a slide means a stream beyond 64 KiB: whole tables)
+				uint32_t *tab = reinterpret_cast<uint32_t *>(t ? prev : head);
+				for (int i = lane; i < 16384; i += 32) {
+					const uint32_t v = tab[i];
+					uint32_t lo = v & 0xFFFFu, hi = v >> 16;
+					lo = lo >= 32768u ? lo - 32768u : 0u;
+					hi = hi >= 32768u ? hi - 32768u : 0u;
+					tab[i] = lo | (hi << 16);
+				}
 			}
 			__syncwarp();
 			continue;
@@ -778,19 +1056,50 @@ __global__ void __launch_bounds__(32)
 	if (lane == 0) {
 		nsyms[stream] = total;
 		nblocks[stream] = nblk;
+#ifdef B200Z_FAST_STATS
+		printf("k_fast stream %d: n %u, group steps %u, positions by groups %u (%.1f per step, %.1f lanes used), symbols %u\n", stream, n,
+		       st_steps, st_pos, st_steps ? (double)st_pos / st_steps : 0.0, st_steps ? (double)st_lanes / st_steps : 0.0, total);
+#endif
 	}
 	if (st) {
 		// what the next segment of this stream starts from
 		__syncwarp();
 		uint4 *dst = reinterpret_cast<uint4 *>(st);
-		const int words = (32768 + prev_entries) * 2 / 16;
-		for (int i = lane; i < words; i += 32) dst[i] = reinterpret_cast<const uint4 *>(fsm)[i];
-		for (int i = words + lane; i < 131072 / 16; i += 32) dst[i] = make_uint4(0u, 0u, 0u, 0u);
+		for (int i = lane; i < 65536 / 16; i += 32) dst[i] = reinterpret_cast<const uint4 *>(head)[i];
+		const int words = prev_entries * 2 / 16;
+		for (int i = lane; i < words; i += 32) dst[65536 / 16 + i] = reinterpret_cast<const uint4 *>(prev)[i];
+		for (int i = words + lane; i < 65536 / 16; i += 32) dst[65536 / 16 + i] = make_uint4(0u, 0u, 0u, 0u);
 		if (lane == 0) {
 			FastCarry c;
 			fe_save(e, c);
 			*reinterpret_cast<FastCarry *>(st + 131072) = c;
 		}
+	}
+}
+
+// persistent CTAs of one warp: streams are taken off a counter, so a batch of uneven streams keeps every CTA busy
+__global__ void __launch_bounds__(32)
+    k_fast(const uint8_t *__restrict__ in, uint32_t *__restrict__ sym, const int64_t *__restrict__ in_off,
+           const int64_t *__restrict__ in_len, uint32_t *__restrict__ nsyms, uint32_t *__restrict__ nblocks,
+           const uint32_t *__restrict__ blk_off, uint32_t *__restrict__ blk_start, uint32_t *__restrict__ blk_ptop,
+           const uint32_t *__restrict__ hist, LevelParams lp, int strategy, int end_mode, int prev_entries,
+           const uint32_t *__restrict__ sched, const uint32_t *__restrict__ sched_off, const int32_t *__restrict__ undrained,
+           uint8_t *const *__restrict__ fstate, int cont, int group, int nstreams, uint16_t *__restrict__ head_pool,
+           uint32_t *__restrict__ counter) {
+	extern __shared__ __align__(16) uint8_t fsm[];
+	uint16_t *prev = reinterpret_cast<uint16_t *>(fsm);
+	// head_pool == nullptr: a batch of at most one stream per SM -- head[] sits behind prev[] in shared memory (one CTA per
+	// SM then, whose L1 holds the stream's window: 1.7x faster per stream than with three CTAs sharing the SM)
+	uint16_t *head = head_pool ? head_pool + 32768ll * blockIdx.x : prev + prev_entries;
+	const int lane = threadIdx.x;
+	for (;;) {
+		int stream = 0;
+		if (lane == 0) stream = (int)atomicAdd(counter, 1u);
+		stream = __shfl_sync(0xffffffffu, stream, 0);
+		if (stream >= nstreams) break;
+		fast_stream(stream, lane, head, prev, in, sym, in_off, in_len, nsyms, nblocks, blk_off, blk_start, blk_ptop, hist, lp, strategy,
+		            end_mode, prev_entries, sched, sched_off, undrained, fstate, cont, group);
+		__syncwarp();
 	}
 }
 
@@ -1136,6 +1445,16 @@ int deflate_plan_build(b200z_plan *p) {
 		int pe = 32768;
 		if (need <= 32768 && p->engine_state.empty()) pe = (int)((need + 255) / 256 * 256); // (a carried state holds whole tables)
 		p->fast_prev_entries = pe;
+		// persistent one-warp CTAs: as many per SM as their prev[] tables fit (head[] is in the pool), 16 at most
+		int sms = 148, dev = 0;
+		if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+		int per_sm = (int)((227 * 1024) / (2 * pe + 1024));
+		if (per_sm > 16) per_sm = 16;
+		if (per_sm < 1) per_sm = 1;
+		const int64_t slots = (int64_t)sms * per_sm;
+		p->fast_ctas = (int)(n < slots ? n : slots);
+		p->fast_head_smem = n <= sms; // nothing to gain from sharing SMs: keep head[] next to prev[] (k_fast)
+		if (const char *e = getenv("B200Z_FAST_HEAD")) p->fast_head_smem = e[0] == 's'; // "smem" / "pool": for tests and timing
 	}
 	std::vector<uint32_t> blk_off(n + 1);
 	std::vector<int32_t> blk_desc;
@@ -1270,6 +1589,8 @@ int deflate_plan_build(b200z_plan *p) {
 		p->o_sched_off = ws.reserve(4ll * (n + 1));
 		p->o_undrained = ws.reserve(4ll * (n + 1));
 		p->o_fstate = ws.reserve(8ll * (n + 1));
+		p->o_fhead = ws.reserve(p->fast_head_smem ? 256 : 65536ll * p->fast_ctas);
+		p->o_fcounter = ws.reserve(256);
 	}
 	p->o_hist = ws.reserve(4ll * (n + 1));
 	p->o_bias = ws.reserve(8ll * (n + 1));
@@ -1394,11 +1715,12 @@ int deflate_plan_run(b200z_plan *p, const uint8_t *d_in, uint8_t *d_out, int64_t
 	}
 	if (lp.func == 1) {
 		p->mark(s, "k_fast");
-		k_fast<<<n, 32, 65536 + 2 * p->fast_prev_entries, s>>>(d_in, sym, in_off, in_len, nsyms, nblocks, blk_off, blk_start, blk_ptop,
-		                                                       hist, lp, p->strategy, p->end_mode, p->fast_prev_entries,
-		                                                       ws.at<uint32_t>(p->o_sched), ws.at<uint32_t>(p->o_sched_off),
-		                                                       ws.at<int32_t>(p->o_undrained), ws.at<uint8_t *>(p->o_fstate),
-		                                                       p->hist_kind == B200Z_HIST_CONTINUE ? 1 : 0);
+		B200Z_CUDA(cudaMemsetAsync(ws.at<uint32_t>(p->o_fcounter), 0, 4, s));
+		k_fast<<<p->fast_ctas, 32, 2 * p->fast_prev_entries + (p->fast_head_smem ? 65536 : 0), s>>>(
+		    d_in, sym, in_off, in_len, nsyms, nblocks, blk_off, blk_start, blk_ptop, hist, lp, p->strategy, p->end_mode,
+		    p->fast_prev_entries, ws.at<uint32_t>(p->o_sched), ws.at<uint32_t>(p->o_sched_off), ws.at<int32_t>(p->o_undrained),
+		    ws.at<uint8_t *>(p->o_fstate), p->hist_kind == B200Z_HIST_CONTINUE ? 1 : 0, fast_group_enabled(), n,
+		    p->fast_head_smem ? nullptr : ws.at<uint16_t>(p->o_fhead), ws.at<uint32_t>(p->o_fcounter));
 	} else {
 		if (do_search) {
 		p->mark(s, "k_links");

@@ -114,6 +114,8 @@ struct b200z_plan {
 	uint32_t parse_chunk = 32768;
 	int link_run = 65536; // positions per k_links CTA (B200Z_LINK_RUN)
 	int fast_prev_entries = 32768; // k_fast's prev[] size for this batch
+	int fast_ctas = 1;             // k_fast's persistent CTAs (each owns a head[] slot of the pool)
+	bool fast_head_smem = false;   // ... or keeps head[] in shared memory (few streams)
 	int64_t o_stored = 0, o_slens = 0; // level 0: stored-block list and per-stream output lengths
 	// levels 0-4: the SetInput schedule of every stream (cumulative sizes), "Flush()/Finish() behind an undrained SetInput",
 	// and the engine state carried between the segments of a stream (b200z_history)
@@ -121,7 +123,7 @@ struct b200z_plan {
 	std::vector<int32_t> undrained;
 	std::vector<void *> engine_state;             // device pointers (levels 1-4)
 	struct b200z_stored_state *stored_state = nullptr; // caller's host array (level 0), used while the plan is built
-	int64_t o_sched = 0, o_sched_off = 0, o_undrained = 0, o_fstate = 0;
+	int64_t o_sched = 0, o_sched_off = 0, o_undrained = 0, o_fstate = 0, o_fhead = 0, o_fcounter = 0;
 	int n_stored = 0;
 	// inflate workspace offsets
 	int64_t o_tok = 0, o_ntok = 0, o_tok_off = 0;

@@ -171,6 +171,31 @@ def test_deflate_fast_and_stored_levels(z, oracle, level):
             assert outs == [oracle.deflate(b, level=level, strategy=strategy) for b in bufs[:3]]
 
 
+@pytest.mark.parametrize("head", ["pool", "smem"])
+@pytest.mark.parametrize("level", [1, 2, 3, 4])
+def test_deflate_fast_group_steps_both_table_layouts(z, oracle, level, head, monkeypatch):
+    """k_fast's warp-wide group steps (DeflaterEngine.cs:651-739 taken 32 loop tops at a time) with head[] in the global pool
+    (many streams: several CTAs per SM) and in shared memory (few streams), and the same kernel with every loop top on lane 0:
+    all three give the oracle's bytes.  Long repeats (covered lanes), incompressible bytes, runs of one byte (chains through
+    the group itself), streams that end inside a group, a window slide."""
+    from sharpziplib_b200 import datagen
+    import numpy as np
+    rng = np.random.default_rng(level)
+    bufs = [datagen.silesia_mix(c, 90000 + 4099 * c, config=7).tobytes() for c in range(8)]
+    bufs += [bytes(70000), b"ab" * 40000, rng.integers(0, 256, 50000, dtype=np.uint8).tobytes(), crafted_t8()]
+    bufs += [datagen.text_buffer(1, k, config=7).tobytes() for k in (1, 2, 3, 261, 262, 263, 293, 294, 300, 555, 4096)]
+    rep = rng.integers(0, 4, 3000, dtype=np.uint8).tobytes()
+    bufs += [rep * 30, (rep[:700] + bytes(range(256))) * 120]
+    refs = [oracle.deflate(b, level=level) for b in bufs]
+    monkeypatch.setenv("B200Z_FAST_HEAD", head)
+    outs, _ = z.deflate_batch(bufs, level=level)
+    assert outs == refs
+    if head == "pool":
+        monkeypatch.setenv("B200Z_FAST_GROUP", "0")
+        outs, _ = z.deflate_batch(bufs, level=level)
+        assert outs == refs
+
+
 def _drain(d):
     out = bytearray()
     buf = bytearray(65536)
