@@ -281,6 +281,43 @@ int b200z_inflater_total_in(void *h, int64_t *v);                               
 int b200z_inflater_total_out(void *h, int64_t *v);                                  /* :848 */
 int b200z_inflater_adler(void *h, uint32_t *v);                                     /* :823 */
 
+/* ---- Entry ciphers applied to compressed bytes ---------------------------------------------------
+ * Encryption/ZipAESTransform.cs (WinZip AES: AES-CTR + HMAC-SHA1, keys by PBKDF2) and Encryption/PkzipClassic.cs, the
+ * ICryptoTransform objects Streams/DeflaterOutputStream.cs:227-231 (EncryptBlock) and Zip/ZipFile.cs feed with the codec's
+ * output.  AES-CTR is one thread per 16-byte block; SHA-1 and the classic cipher are serial per stream and run one thread
+ * per stream (they scale with the number of entries).  `keys` of the AES calls: per stream 2 * key_bytes + 2 bytes, key1 |
+ * key2 | password verifier, exactly the three GetBytes() results of ZipAESTransform.cs:62-68. */
+typedef struct b200z_aes_transform b200z_aes_transform;
+/* ZipAESTransform constructor :41-72 for n entries: pw_off[n + 1] offsets into the password blob, salts n x key_bytes / 2
+ * bytes, key_bytes 16 or 32 (:43-46), keys_out n x (2 * key_bytes + 2).  Host pointers; PBKDF2 runs on the device. */
+int b200z_aes_derive_keys(const uint8_t *passwords, const int64_t *pw_off, const uint8_t *salts, int32_t key_bytes, int32_t n,
+                          uint8_t *keys_out);
+/* bytes of per-stream state the device call carries between TransformBlock calls (zero-filled = a fresh transform) */
+int64_t b200z_aes_state_bytes(void);
+/* TransformBlock :75-112 on device memory for n streams at once: stream i is d_len[i] bytes at d_in + d_off[i] (d_out may be
+ * d_in), max_len >= every length.  d_state: n x b200z_aes_state_bytes().  finish != 0 also writes GetAuthCode() (:122, 20
+ * bytes per stream, the archive keeps the first 10) to d_auth.  No host synchronisation. */
+int b200z_aes_device(const uint8_t *d_in, uint8_t *d_out, const int64_t *d_off, const int64_t *d_len, int64_t max_len, int32_t n,
+                     int32_t key_bytes, const uint8_t *d_keys, int32_t write_mode, uint8_t *d_state, int32_t finish, uint8_t *d_auth,
+                     void *cuda_stream);
+/* the same for whole entries in host memory: out[i] = TransformBlock(in[i]), auth + 20 * i = GetAuthCode() */
+int b200z_aes_batch(const uint8_t *const *in, const int64_t *len, int32_t n, int32_t key_bytes, const uint8_t *keys, int32_t write_mode,
+                    uint8_t *const *out, uint8_t *auth);
+/* one ZipAESTransform as a handle: constructor :41, TransformBlock :75, PwdVerifier :117, GetAuthCode :122, Dispose :172 */
+int b200z_aes_transform_create(const uint8_t *password, int32_t password_len, const uint8_t *salt, int32_t key_bytes, int32_t write_mode,
+                               b200z_aes_transform **out);
+int b200z_aes_transform_block(b200z_aes_transform *t, const uint8_t *in, int64_t count, uint8_t *out);
+int b200z_aes_transform_pwd_verifier(const b200z_aes_transform *t, uint8_t *out2);
+int b200z_aes_transform_auth_code(b200z_aes_transform *t, uint8_t *out20);
+int b200z_aes_transform_destroy(b200z_aes_transform *t);
+/* PkzipClassic.GenerateKeys :19-50 (12 bytes: keys[0..2] little-endian, what SetKeys :84-100 takes) */
+int b200z_pkzip_generate_keys(const uint8_t *seed, int64_t n, uint8_t *keys12);
+/* PkzipClassicEncryptCryptoTransform.TransformBlock :170-178 / PkzipClassicDecryptCryptoTransform.TransformBlock :279-288 for
+ * n streams: d_keys n x 3 words, updated in place (a stream goes on where its last call ended) */
+int b200z_pkzip_device(const uint8_t *d_in, uint8_t *d_out, const int64_t *d_off, const int64_t *d_len, int32_t n, uint32_t *d_keys,
+                       int32_t encrypt, void *cuda_stream);
+int b200z_pkzip_batch(const uint8_t *const *in, const int64_t *len, int32_t n, uint8_t *keys12, int32_t encrypt, uint8_t *const *out);
+
 #ifdef __cplusplus
 }
 #endif

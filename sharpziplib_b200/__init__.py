@@ -10,3 +10,4 @@ from .checksum import Crc32, Adler32  # noqa: F401
 from .codec import Deflater, Inflater, DeflateStrategy  # noqa: F401
 from .streams import DeflaterOutputStream, InflaterInputStream, GZipOutputStream, GZipInputStream  # noqa: F401
 from .batch import DeflatePlan, InflatePlan, Pipeline, deflate_batch, inflate_batch, zip_entries, unzip_entries  # noqa: F401
+from . import encryption  # noqa: F401

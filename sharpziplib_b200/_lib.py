@@ -97,6 +97,19 @@ _SIGS = {
     "b200z_inflate_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "b200z_release_cached": (C.c_int, []),
     "b200z_device_count": (C.c_int, []),
+    "b200z_aes_derive_keys": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
+    "b200z_aes_state_bytes": (C.c_int64, []),
+    "b200z_aes_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_int32,
+                                   C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
+    "b200z_aes_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
+    "b200z_aes_transform_create": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]),
+    "b200z_aes_transform_block": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "b200z_aes_transform_pwd_verifier": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "b200z_aes_transform_auth_code": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "b200z_aes_transform_destroy": (C.c_int, [C.c_void_p]),
+    "b200z_pkzip_generate_keys": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p]),
+    "b200z_pkzip_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]),
+    "b200z_pkzip_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]),
     "b200z_partition_by_bytes": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     "b200z_deflate_batch_multi": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "b200z_inflate_batch_multi": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

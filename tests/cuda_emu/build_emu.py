@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 # B200Z_EMU_CSRC / B200Z_EMU_OUT: build from another copy of the kernel sources (e.g. one with an experimental patch applied)
 CSRC = os.environ.get("B200Z_EMU_CSRC", os.path.join(ROOT, "sharpziplib_b200", "csrc"))
 OUT = os.environ.get("B200Z_EMU_OUT", os.path.join(HERE, "_build"))
-FILES = ["b200z_deflate.cu", "b200z_inflate.cu", "b200z_checksum.cu", "b200z_api.cu"]
+FILES = ["b200z_deflate.cu", "b200z_inflate.cu", "b200z_checksum.cu", "b200z_api.cu", "b200z_crypto.cu"]
 
 
 def _split_top(s):

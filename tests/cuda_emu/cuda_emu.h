@@ -217,6 +217,13 @@ template <class T> static inline uint32_t __match_any_sync(uint32_t, T v) {
 template <class T> static inline T __ldg(const T *p) { return *p; }
 template <class T> static inline T __ldcg(const T *p) { return *p; }
 static inline uint32_t __funnelshift_r(uint32_t lo, uint32_t hi, uint32_t sh) { return (uint32_t)((((uint64_t)hi << 32) | lo) >> (sh & 31)); }
+static inline uint32_t __funnelshift_l(uint32_t lo, uint32_t hi, uint32_t sh) { return (uint32_t)(((((uint64_t)hi << 32) | lo) << (sh & 31)) >> 32); }
+static inline uint32_t __byte_perm(uint32_t a, uint32_t b, uint32_t sel) { // PRMT, default mode: selector nibble k picks byte k of (b:a)
+	const uint64_t v = ((uint64_t)b << 32) | a;
+	uint32_t r = 0;
+	for (int k = 0; k < 4; k++) r |= (uint32_t)((v >> (8 * ((sel >> (4 * k)) & 7))) & 0xFF) << (8 * k);
+	return r;
+}
 static inline int __ffs(int x) { return x ? __builtin_ctz((unsigned)x) + 1 : 0; }
 static inline int __popc(uint32_t x) { return __builtin_popcount(x); }
 static inline int __clz(int x) { return x ? __builtin_clz((unsigned)x) : 32; }

@@ -15,7 +15,7 @@ _SO = os.path.join(_ROOT, "oracle", "_build", "libszl_oracle.so")
 
 def build(force=False):
     srcs = [os.path.join(_ROOT, "oracle", f) for f in
-            ("szl_deflate.cpp", "szl_inflate.cpp", "szl_capi.cpp", "szl_oracle.hpp")]
+            ("szl_deflate.cpp", "szl_inflate.cpp", "szl_capi.cpp", "szl_crypto.cpp", "szl_oracle.hpp")]
     if (not force and os.path.exists(_SO)
             and all(os.path.getmtime(_SO) >= os.path.getmtime(s) for s in srcs if os.path.exists(s))):
         return _SO
@@ -53,6 +53,17 @@ def lib():
                                       C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
     L.szl_batch.restype = C.c_int
     L.szl_batch.argtypes = [C.c_int, u8p, u8p, u8p, C.c_int32, C.c_int, C.c_int, u8p, u8p, u8p, u8p, C.c_int32]
+    # entry ciphers (oracle/szl_crypto.cpp)
+    L.szl_aes_encrypt_block.argtypes = [u8p, C.c_int, u8p, u8p]
+    L.szl_sha1.argtypes = [u8p, C.c_uint64, u8p]
+    L.szl_hmac_sha1.argtypes = [u8p, C.c_uint64, u8p, C.c_uint64, u8p]
+    L.szl_pbkdf2_sha1.argtypes = [u8p, C.c_uint64, u8p, C.c_uint64, C.c_int, u8p, C.c_uint64]
+    L.szl_zip_aes.argtypes = [u8p, C.c_uint64, u8p, C.c_int, C.c_int, u8p, C.c_uint64, C.c_uint64, u8p, u8p, u8p]
+    L.szl_pkzip_generate_keys.argtypes = [u8p, C.c_uint64, u8p]
+    L.szl_pkzip_transform.argtypes = [u8p, C.c_int, u8p, C.c_uint64, u8p]
+    for name in ("szl_aes_encrypt_block", "szl_sha1", "szl_hmac_sha1", "szl_pbkdf2_sha1", "szl_zip_aes", "szl_pkzip_generate_keys",
+                 "szl_pkzip_transform"):
+        getattr(L, name).restype = None
     # handles
     L.szl_deflater_new.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_void_p)]
     L.szl_deflater_free.argtypes = [C.c_void_p]
@@ -132,6 +143,53 @@ def crc32_update(value, data):
 def adler32_update(value, data):
     a = _arr(data)
     return lib().szl_adler32_update(value, a.ctypes.data, a.size)
+
+
+def aes_encrypt_block(key, block16):
+    k, b, o = _arr(key), _arr(block16), np.zeros(16, np.uint8)
+    lib().szl_aes_encrypt_block(k.ctypes.data, k.size, b.ctypes.data, o.ctypes.data)
+    return o.tobytes()
+
+
+def sha1(data):
+    a, o = _arr(data), np.zeros(20, np.uint8)
+    lib().szl_sha1(_ptr(a), a.size, o.ctypes.data)
+    return o.tobytes()
+
+
+def hmac_sha1(key, data):
+    k, a, o = _arr(key), _arr(data), np.zeros(20, np.uint8)
+    lib().szl_hmac_sha1(_ptr(k), k.size, _ptr(a), a.size, o.ctypes.data)
+    return o.tobytes()
+
+
+def pbkdf2_sha1(password, salt, rounds, n):
+    p, s, o = _arr(password), _arr(salt), np.zeros(n, np.uint8)
+    lib().szl_pbkdf2_sha1(_ptr(p), p.size, _ptr(s), s.size, rounds, o.ctypes.data, n)
+    return o.tobytes()
+
+
+def zip_aes(password, salt, block_size, write_mode, data, piece=0):
+    """new ZipAESTransform(password, salt, blockSize, writeMode).TransformBlock(data) -> (bytes, PwdVerifier, GetAuthCode())"""
+    p, s, a = _arr(password), _arr(salt), _arr(data)
+    o, v, h = np.zeros(a.size, np.uint8), np.zeros(2, np.uint8), np.zeros(20, np.uint8)
+    lib().szl_zip_aes(_ptr(p), p.size, s.ctypes.data, block_size, 1 if write_mode else 0, _ptr(a), a.size, piece, _ptr(o),
+                      v.ctypes.data, h.ctypes.data)
+    return o.tobytes(), v.tobytes(), h.tobytes()
+
+
+def pkzip_generate_keys(seed):
+    s, o = _arr(seed), np.zeros(12, np.uint8)
+    lib().szl_pkzip_generate_keys(_ptr(s), s.size, o.ctypes.data)
+    return o.tobytes()
+
+
+def pkzip_transform(keys12, encrypt, data):
+    """PkzipClassic{Encrypt,Decrypt}CryptoTransform.TransformBlock -> (bytes, keys after)"""
+    k, a = np.array(np.frombuffer(keys12, dtype=np.uint8)), _arr(data)
+    o = np.zeros(a.size, np.uint8)
+    lib().szl_pkzip_transform(k.ctypes.data, 1 if encrypt else 0, _ptr(a), a.size, _ptr(o))
+    return o.tobytes(), k.tobytes()
 
 
 def dotnet_random_bytes(seed, n):

@@ -141,3 +141,100 @@ def test_handle_api_matches_oneshot(oracle):
             break
         back += got
     assert back == d and inf.remaining_input == 8 and inf.total_in == len(out)  # trap T14
+
+
+# ---- entry ciphers (oracle/szl_crypto.cpp) -------------------------------------------------------
+# The AES-encrypted archive the reference's own tests hold (test/.../Zip/ZipEncryptionHandling.cs:452-456: one entry "test",
+# AES-256, deflated, empty password; :461-482 expects the text below).
+AES_FIXTURE_B64 = """UEsDBDMACQBjACaj0FAyKbop//////////8EAB8AdGVzdAEAEAA4AAAA
+AAAAAFIAAAAAAAAAAZkHAAIAQUUDCABADvo3YqmCtIE+lhw26kjbqkGsLEOk6bVA+FnSpVD4yGP4Mr66Hs14aTtsPUaANX2
+Z6qZczEmwoaNQpNBnKl7p9YOG8GSHDfTCUU/AZvT4yGFhUEsHCDIpuilSAAAAAAAAADgAAAAAAAAAUEsBAjMAMwAJAGMAJq
+PQUDIpuin//////////wQAHwAAAAAAAAAAAAAAAAAAAHRlc3QBABAAOAAAAAAAAABSAAAAAAAAAAGZBwACAEFFAwgAUEsFBgAAAAABAAEAUQAAAKsAAAAAAA=="""
+AES_FIXTURE_TEXT = b"Lorem ipsum dolor sit amet, consectetur adipiscing elit."
+
+
+def aes_fixture_entry():
+    """(salt, password verifier, ciphertext, 10-byte auth code, key bytes, compression method) of the fixture's entry"""
+    import base64
+    import struct
+    z = base64.b64decode("".join(AES_FIXTURE_B64.split()))
+    sig, _, flags, method, _, _, _, _, _, nl, xl = struct.unpack("<IHHHHHIIIHH", z[:30])
+    assert sig == 0x04034B50 and method == 99 and flags & 1
+    extra, i, csize, strength, real = z[30 + nl:30 + nl + xl], 0, None, None, None
+    while i < len(extra):
+        tag, sz = struct.unpack("<HH", extra[i:i + 4])
+        body = extra[i + 4:i + 4 + sz]
+        i += 4 + sz
+        if tag == 1:
+            _, csize = struct.unpack("<QQ", body[:16])
+        if tag == 0x9901:
+            _, _, strength, real = struct.unpack("<H2sBH", body)
+    kb = {1: 16, 3: 32}[strength]
+    data = z[30 + nl + xl:30 + nl + xl + csize]
+    return data[:kb // 2], data[kb // 2:kb // 2 + 2], data[kb // 2 + 2:-10], data[-10:], kb, real
+
+
+def test_crypto_oracle_known_answers(oracle):
+    O = oracle
+    k16, k32, pt = bytes(range(16)), bytes(range(32)), bytes.fromhex("00112233445566778899aabbccddeeff")
+    assert O.aes_encrypt_block(k16, pt).hex() == "69c4e0d86a7b0430d8cdb78070b4c55a"  # FIPS 197 C.1
+    assert O.aes_encrypt_block(k32, pt).hex() == "8ea2b7ca516745bfeafc49904b496089"  # FIPS 197 C.3
+    assert O.sha1(b"abc").hex() == "a9993e364706816aba3e25717850c26c9cd0d89d"  # RFC 3174
+    assert O.sha1(b"").hex() == "da39a3ee5e6b4b0d3255bfef95601890afd80709"
+    assert O.pbkdf2_sha1(b"password", b"salt", 4096, 20).hex() == "4b007901b765489abead49d926f721d065a429c1"  # RFC 6070
+    assert O.hmac_sha1(b"Jefe", b"what do ya want for nothing?").hex() == "effcdf6ae5eb2fa2d27416d5f184df9c259a7c79"  # RFC 2202
+
+
+def test_crypto_oracle_reads_the_reference_aes_fixture(oracle):
+    O = oracle
+    salt, pv, ct, mac, kb, method = aes_fixture_entry()
+    plain, verifier, auth = O.zip_aes(b"", salt, kb, False, ct)
+    assert verifier == pv and auth[:10] == mac and method == 8
+    assert O.inflate(plain, nowrap=True)[0] == AES_FIXTURE_TEXT
+
+
+def test_crypto_oracle_against_an_independent_library(oracle):
+    O = oracle
+    hz = pytest.importorskip("cryptography.hazmat.primitives")
+    from cryptography.hazmat.primitives import hashes, hmac
+    from cryptography.hazmat.primitives.ciphers import Cipher, algorithms, modes
+    from cryptography.hazmat.primitives.kdf.pbkdf2 import PBKDF2HMAC
+    rng = np.random.default_rng(7)
+    for bs in (16, 32):
+        for n in (0, 1, 15, 16, 17, 63, 64, 65, 4096, 100003):
+            pw, salt, data = b"pass\xc3\xa9word", rng.bytes(bs // 2), rng.bytes(n)
+            kb = PBKDF2HMAC(hashes.SHA1(), 2 * bs + 2, salt, 1000).derive(pw)
+            enc = Cipher(algorithms.AES(kb[:bs]), modes.ECB()).encryptor()
+            ks = b"".join(enc.update((i + 1).to_bytes(16, "little")) for i in range((n + 15) // 16))
+            ct = bytes(a ^ b for a, b in zip(data, ks))
+            h = hmac.HMAC(kb[bs:2 * bs], hashes.SHA1())
+            h.update(ct)
+            mac = h.finalize()
+            assert O.zip_aes(pw, salt, bs, True, data, piece=777) == (ct, kb[2 * bs:], mac)
+            assert O.zip_aes(pw, salt, bs, False, ct) == (data, kb[2 * bs:], mac)
+
+
+def classic_zip(name, payload, crc, keys_after_header_fn):
+    """a one-entry stored archive with PKZIP classic encryption (flag bit 0), header + data already encrypted in `payload`"""
+    import struct
+    lh = struct.pack("<IHHHHHIIIHH", 0x04034B50, 20, 1, 0, 0, 0x21, crc, len(payload), len(payload) - 12, len(name), 0) + name
+    cd = struct.pack("<IHHHHHHIIIHHHHHII", 0x02014B50, 20, 20, 1, 0, 0, 0x21, crc, len(payload), len(payload) - 12, len(name), 0, 0, 0, 0, 0,
+                     0) + name
+    eocd = struct.pack("<IHHHHIIH", 0x06054B50, 0, 0, 1, 1, len(cd), len(lh) + len(payload), 0)
+    return lh + payload + cd + eocd
+
+
+def test_pkzip_classic_oracle_is_read_by_python_zipfile(oracle):
+    O = oracle
+    import io
+    import zipfile
+    import zlib
+    data = bytes(range(256)) * 37 + b"tail"
+    crc = zlib.crc32(data)
+    keys = O.pkzip_generate_keys(b"secret")
+    header = bytes(range(11)) + bytes([crc >> 24])  # ZipOutputStream.WriteEncryptionHeader: 11 random bytes + the CRC's top byte
+    enc, keys_after = O.pkzip_transform(keys, True, header + data)
+    zf = zipfile.ZipFile(io.BytesIO(classic_zip(b"f.bin", enc, crc, None)))
+    assert zf.read("f.bin", pwd=b"secret") == data
+    dec, keys_after2 = O.pkzip_transform(keys, False, enc)
+    assert dec == header + data and keys_after2 == keys_after
