@@ -371,6 +371,7 @@ __global__ void __launch_bounds__(kMatchThreads, 1)
 constexpr int kSegShift = 5;
 constexpr int kSeg = 1 << kSegShift; // 32 positions per lane: 9.6 KiB of shared memory per warp, 22 warps per SM (64: 4.5 ms, 32: 3.2 ms, 16: 3.4 ms)
 constexpr int kRound = 32 * kSeg;
+constexpr int kParseWarm = 128; // positions a chunk parses in front of its first one to find its entry state (k_parse_chunk)
 constexpr int kSegStride = kSeg + 2; // uint2 entries; +2 keeps 16-byte alignment for cp.async and staggers the banks
 constexpr int kParseDatOff = 32 * kSegStride * 8;
 constexpr int kParseSmem = kParseDatOff + kRound + 48;
@@ -504,16 +505,53 @@ __global__ void __launch_bounds__(32)
     k_parse_chunk(const uint8_t *__restrict__ in, const uint16_t *__restrict__ link, const uint2 *__restrict__ mt,
                   uint32_t *__restrict__ sym_local, const int64_t *__restrict__ in_off, const int64_t *__restrict__ in_len,
                   const ChunkDesc *__restrict__ chunks, const uint32_t *__restrict__ rnd_off, RoundRec *__restrict__ recs,
-                  const uint32_t *__restrict__ hist, const int64_t *__restrict__ bias, LevelParams lp, int strategy) {
+                  RoundRec *__restrict__ ents, const uint32_t *__restrict__ hist, const int64_t *__restrict__ bias, LevelParams lp,
+                  int strategy) {
 	extern __shared__ __align__(16) uint8_t smem[];
 	const ChunkDesc cd = chunks[blockIdx.x];
 	const uint32_t n = (uint32_t)in_len[cd.stream];
 	const int64_t off = in_off[cd.stream];
 	RoundRec *rr = recs + rnd_off[cd.stream];
 	const uint32_t H = hist[cd.stream], ab = (uint32_t)bias[cd.stream];
-	// exact for the first chunk (DeflaterEngine.Reset :234-253; also the state right after a dictionary or a flush),
-	// a guess otherwise
+	// exact for the first chunk (DeflaterEngine.Reset :234-253; also the state right after a dictionary or a flush).  Every
+	// other chunk parses kParseWarm positions in front of its first one from a clean state (lane 0, straight from global
+	// memory): DeflateSlow's state re-synchronises within a few symbols, so the state this reaches at c0 is the true one at
+	// 99.8 % of the boundaries (tools/tile_fixup.cpp).  It is recorded; k_parse_fix compares it with the exit of the chunk in
+	// front and parses again only where they differ.
 	ParseCarry carry = clean_carry(cd.c0 > H ? cd.c0 : H);
+	if (cd.c0 > H) {
+		if (threadIdx.x == 0) {
+			const uint8_t *data = in + off;
+			const uint16_t *lnk = link + off;
+			const uint2 *tab = mt + off;
+			const uint32_t ws = cd.c0 - H > (uint32_t)kParseWarm ? cd.c0 - (uint32_t)kParseWarm : H;
+			ParseCarry w = clean_carry(ws);
+			auto tabg = [&](uint32_t p, uint32_t &a, uint32_t &b) {
+				const uint2 t = tab[p];
+				a = t.x;
+				b = t.y;
+			};
+			auto byteg = [&](uint32_t q) { return (uint32_t)data[q]; };
+			auto slowg = [&](uint32_t p, uint32_t m0, uint32_t budget) { return match_search_above(data, lnk, p, n, m0, budget, ab); };
+			while (w.st.p < cd.c0) {
+				w.last_top = w.st.p;
+				uint32_t s2;
+				parse_step(w.st, n, lp, strategy, tabg, byteg, slowg, s2);
+			}
+			carry = w;
+		}
+		carry = shfl_carry(carry, 0);
+	}
+	if (threadIdx.x == 0) {
+		RoundRec e;
+		e.p = carry.st.p;
+		e.mlen = carry.st.mlen;
+		e.mstart = carry.st.mstart;
+		e.prevAvail = carry.st.prevAvail;
+		e.last_top = carry.last_top;
+		e.cnt = 0;
+		ents[rnd_off[cd.stream] + cd.c0 / kRound] = e;
+	}
 	for (uint32_t base = cd.c0; base < cd.c1; base += kRound) {
 		const uint32_t cnt = parse_round(smem, in + off, link + off, mt + off, n, H, ab, base, lp, strategy, carry, sym_local + off + base);
 		if (threadIdx.x == 0) {
@@ -532,28 +570,46 @@ __global__ void __launch_bounds__(32)
 __global__ void __launch_bounds__(32)
     k_parse_fix(const uint8_t *__restrict__ in, const uint16_t *__restrict__ link, const uint2 *__restrict__ mt,
                 uint32_t *__restrict__ sym_local, const int64_t *__restrict__ in_off, const int64_t *__restrict__ in_len,
-                const uint32_t *__restrict__ rnd_off, RoundRec *__restrict__ recs, uint32_t chunk, const uint32_t *__restrict__ hist,
-                const int64_t *__restrict__ bias, LevelParams lp, int strategy) {
+                const uint32_t *__restrict__ rnd_off, RoundRec *__restrict__ recs, const RoundRec *__restrict__ ents, uint32_t chunk,
+                const uint32_t *__restrict__ hist, const int64_t *__restrict__ bias, LevelParams lp, int strategy) {
 	extern __shared__ __align__(16) uint8_t smem[];
 	const int stream = blockIdx.x;
 	const uint32_t n = (uint32_t)in_len[stream];
 	if (n <= chunk) return; // a single chunk was parsed from the true initial state
 	const int64_t off = in_off[stream];
 	RoundRec *rr = recs + rnd_off[stream];
+	const RoundRec *en = ents + rnd_off[stream];
 	const uint32_t H = hist[stream], ab = (uint32_t)bias[stream];
-	for (uint32_t c0 = chunk; c0 < n; c0 += chunk) {
-		const uint32_t c1 = (n - c0 > chunk) ? c0 + chunk : n;
-		ParseCarry truth = rec_carry(rr[c0 / kRound - 1]); // exit of the previous chunk's last round, exact by induction
-		{
-			ParseCarry guess = clean_carry(c0);
-			guess.last_top = truth.last_top; // irrelevant here: the chunk processes at least one loop top
-			if (carry_equal(truth, guess)) continue; // the guess was right
+	const uint32_t nchunks = (n + chunk - 1) / chunk;
+	const int lane = threadIdx.x;
+	// Boundaries are checked 32 at a time: the entry a chunk used against the exit of the chunk in front (exact by induction
+	// once every boundary before it has been checked).  The first that differs is parsed again from the true state until a
+	// round's exit equals the recorded one; the scan then goes on behind it (its own exit may have changed).
+	uint32_t k0 = 1;
+	while (k0 < nchunks) {
+		const uint32_t k = k0 + (uint32_t)lane;
+		bool bad = false;
+		if (k < nchunks) {
+			const uint32_t c0 = k * chunk;
+			const ParseCarry truth = rec_carry(rr[c0 / kRound - 1]);
+			ParseCarry used = rec_carry(en[c0 / kRound]);
+			used.last_top = truth.last_top; // irrelevant here: the chunk processes at least one loop top
+			bad = !carry_equal(truth, used);
 		}
+		const uint32_t mask = __ballot_sync(0xffffffffu, bad);
+		if (!mask) {
+			k0 += 32;
+			continue;
+		}
+		const uint32_t kk = k0 + (uint32_t)(__ffs((int)mask) - 1);
+		const uint32_t c0 = kk * chunk;
+		const uint32_t c1 = (n - c0 > chunk) ? c0 + chunk : n;
+		ParseCarry truth = rec_carry(rr[c0 / kRound - 1]);
 		for (uint32_t base = c0; base < c1; base += kRound) {
 			const ParseCarry old_exit = rec_carry(rr[base / kRound]);
 			const uint32_t cnt = parse_round(smem, in + off, link + off, mt + off, n, H, ab, base, lp, strategy, truth, sym_local + off + base);
 			__syncwarp();
-			if (threadIdx.x == 0) {
+			if (lane == 0) {
 				RoundRec r;
 				r.p = truth.st.p;
 				r.mlen = truth.st.mlen;
@@ -566,6 +622,8 @@ __global__ void __launch_bounds__(32)
 			__syncwarp();
 			if (carry_equal(truth, old_exit)) break; // re-synchronised: the rest of the chunk stands as parsed
 		}
+		__syncwarp();
+		k0 = kk + 1;
 	}
 }
 
@@ -1400,10 +1458,11 @@ int deflate_plan_build(b200z_plan *p) {
 	uint32_t nrounds = 0;
 	int64_t maxlen = 0;
 	for (int i = 0; i < n; i++) maxlen = p->in_len[i] > maxlen ? p->in_len[i] : maxlen;
-	// chunk of the parse: 32 Ki positions, grown so that no stream has more than ~1024 chunks (k_parse_fix walks them serially)
+	// chunk of the parse: 32 Ki positions (one warp each); k_parse_fix only compares states at their boundaries, so a long
+	// stream may have tens of thousands of them (grown beyond 65536 chunks per stream)
 	uint32_t chunk = 32768;
 	{
-		const int64_t need = (maxlen / 1024 + kRound - 1) / kRound * kRound;
+		const int64_t need = (maxlen / 65536 + kRound - 1) / kRound * kRound;
 		if (need > (int64_t)chunk) chunk = (uint32_t)need;
 	}
 	// Run length of k_links (a multiple of 32768, 65536 .. 1048576).  Every run but a stream's first re-walks 32768 positions
@@ -1566,6 +1625,7 @@ int deflate_plan_build(b200z_plan *p) {
 		p->o_rgroups = ws.reserve(8ll * (rgroups.size() + 1));
 		p->o_rnd_off = ws.reserve(4ll * (n + 1));
 		p->o_recs = ws.reserve((int64_t)sizeof(RoundRec) * (nrounds + 1));
+		p->o_ents = ws.reserve((int64_t)sizeof(RoundRec) * (nrounds + 1));
 		p->o_rnd_symoff = ws.reserve(4ll * (nrounds + 1));
 	}
 	if (lp.func != 0) p->o_sym = ws.reserve(4ll * io + 64);
@@ -1743,9 +1803,9 @@ int deflate_plan_run(b200z_plan *p, const uint8_t *d_in, uint8_t *d_out, int64_t
 			uint32_t *rnd_symoff = ws.at<uint32_t>(p->o_rnd_symoff);
 			if (p->n_chunks)
 				k_parse_chunk<<<p->n_chunks, 32, kParseSmem, s>>>(d_in, link, mt, sym_local, in_off, in_len, ws.at<ChunkDesc>(p->o_chunks),
-				                                                 rnd_off, recs, hist, bias, lp, p->strategy);
-			k_parse_fix<<<n, 32, kParseSmem, s>>>(d_in, link, mt, sym_local, in_off, in_len, rnd_off, recs, p->parse_chunk, hist, bias,
-			                                      lp, p->strategy);
+				                                                 rnd_off, recs, ws.at<RoundRec>(p->o_ents), hist, bias, lp, p->strategy);
+			k_parse_fix<<<n, 32, kParseSmem, s>>>(d_in, link, mt, sym_local, in_off, in_len, rnd_off, recs, ws.at<RoundRec>(p->o_ents),
+			                                      p->parse_chunk, hist, bias, lp, p->strategy);
 			k_parse_scan<<<n, 256, 0, s>>>(d_in, in_off, in_len, rnd_off, recs, rnd_symoff, sym, nsyms, nblocks, blk_off, blk_start,
 			                               blk_ptop, hist, p->end_mode);
 			if (p->n_rgroups)

@@ -109,7 +109,7 @@ struct b200z_plan {
 	int64_t o_link = 0, o_mt = 0, o_sym = 0, o_nsyms = 0, o_nblocks = 0;
 	int64_t o_blk_start = 0, o_blk_ptop = 0, o_meta = 0, o_tables = 0;
 	int n_runs = 0, n_tiles = 0, n_blkmax = 0;
-	int64_t o_sym_local = 0, o_chunks = 0, o_rgroups = 0, o_rnd_off = 0, o_recs = 0, o_rnd_symoff = 0; // chunked parse
+	int64_t o_sym_local = 0, o_chunks = 0, o_rgroups = 0, o_rnd_off = 0, o_recs = 0, o_ents = 0, o_rnd_symoff = 0; // chunked parse
 	int n_chunks = 0, n_rgroups = 0;
 	uint32_t parse_chunk = 32768;
 	int link_run = 65536; // positions per k_links CTA (B200Z_LINK_RUN)
