@@ -513,30 +513,43 @@ def run_bench(args, rank, local_rank, world, out):
     handles = None
     if rank == 0:
         import io as _io
-        blob = b"".join(a.tobytes() for a in d_np[:16])[:(4 << 20) if args.small else (16 << 20)]
-        sink = _io.BytesIO()
-        t0 = time.perf_counter()
-        s = z.DeflaterOutputStream(sink, z.Deflater(6, True), bufferSize=65536)
-        for o in range(0, len(blob), 1 << 20):  # DeflaterOutputStream.Write in 1 MiB writes
-            s.Write(blob[o:o + (1 << 20)])
-        s.Finish()
-        t1 = time.perf_counter()
-        raw = sink.getvalue()
-        assert raw == O.deflate(blob, level=6), "DeflaterOutputStream bytes differ from the oracle's"
-        part = raw[:len(raw) // 4]
-        t2 = time.perf_counter()
-        r = z.InflaterInputStream(_io.BytesIO(raw), z.Inflater(True), bufferSize=4096)  # the reference's default 4 KiB feeds
-        back = bytearray()
-        while True:
-            chunk = r.read(1 << 16)
-            if not chunk:
-                break
-            back += chunk
-        t3 = time.perf_counter()
-        assert bytes(back) == blob, "InflaterInputStream round trip failed"
-        handles = {"deflater_output_stream_1MiB_writes_gbs": len(blob) / (t1 - t0) / 1e9,
-                   "inflater_input_stream_4KiB_feeds_gbs": len(blob) / (t3 - t2) / 1e9, "bytes": len(blob)}
-        del part
+        blob = b"".join(a.tobytes() for a in d_np[:16 if args.small else 256])  # 4 MiB / 64 MiB of the deflate leg's buffers as one stream
+        defl = z.Deflater(6, True)
+        write_gbs = []
+        for attempt in range(2):  # the second stream goes through the same Deflater after Reset(), as ZipOutputStream's entries do
+            if attempt:
+                defl.Reset()
+            sink = _io.BytesIO()
+            t0 = time.perf_counter()
+            s = z.DeflaterOutputStream(sink, defl, bufferSize=65536)
+            for o in range(0, len(blob), 1 << 20):  # DeflaterOutputStream.Write in 1 MiB writes
+                s.Write(blob[o:o + (1 << 20)])
+            s.Finish()
+            t1 = time.perf_counter()
+            write_gbs.append(len(blob) / (t1 - t0) / 1e9)
+            raw = sink.getvalue()
+            assert raw == O.deflate(blob, level=6), "DeflaterOutputStream bytes differ from the oracle's"
+
+        def read_back(buffer_size, limit):
+            r = z.InflaterInputStream(_io.BytesIO(raw), z.Inflater(True), bufferSize=buffer_size)
+            back = bytearray()
+            t = time.perf_counter()
+            while len(back) < limit:
+                chunk = r.read(1 << 16)
+                if not chunk:
+                    break
+                back += chunk
+            dt = time.perf_counter() - t
+            assert bytes(back) == blob[:len(back)] and len(back) >= limit, "InflaterInputStream round trip failed"
+            return len(back) / dt / 1e9
+        small_part = min(len(blob), 4 << 20)
+        handles = {"deflater_output_stream_1MiB_writes_gbs": write_gbs[1],
+                   "deflater_output_stream_first_stream_gbs": write_gbs[0],  # with the handle's one-time allocations
+                   # the reference's default buffer (InflaterInputStream.cs:358: 4096 bytes per Fill), first 4 MiB of the stream
+                   "inflater_input_stream_4KiB_feeds_gbs": read_back(4096, small_part),
+                   # the same class with its bufferSize constructor argument (:346) at 1 MiB, the whole stream
+                   "inflater_input_stream_1MiB_feeds_gbs": read_back(1 << 20, len(blob)),
+                   "bytes": len(blob), "bytes_4KiB_feeds": small_part}
 
     # ---- CPU baseline: the oracle on one host core, the whole step once ------------------------------------------------
     cpu = None
