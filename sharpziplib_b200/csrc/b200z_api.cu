@@ -1429,7 +1429,14 @@ int b200z_deflater_set_strategy(void *h, int strategy) {
 		set_error("strategy");
 		return B200Z_E_ARG;
 	}
-	((DeflaterH *)h)->strategy = strategy;
+	DeflaterH *d = (DeflaterH *)h;
+	if (strategy != d->strategy && !d->input.empty()) {
+		// the reference switches at the engine's current strstart (DeflaterEngine.cs:283-298), somewhere inside the input it
+		// holds -- like SetLevel in mid-stream; behind a completed Flush() the switch is exact and allowed
+		set_error("SetStrategy between SetInput and Flush()/Finish() is not accelerated");
+		return B200Z_E_UNSUPPORTED;
+	}
+	d->strategy = strategy;
 	return B200Z_OK;
 }
 int b200z_deflater_set_dictionary(void *h, const uint8_t *dict, int32_t len) {

@@ -287,13 +287,33 @@ def test_dictionary_state_errors(z):
         i.SetDictionary(b"abc")
 
 
-def test_unsupported_sequences_fail_loudly(z):
+def test_unsupported_sequences_fail_loudly(z, oracle):
+    from oracle_lib import Deflater as RefDeflater
     d = z.Deflater(6, True)
     d.SetInput(b"abc" * 100)
     d.Flush()
-    _drain(d)
+    got = _drain(d)
     with pytest.raises(z.B200zUnsupported):
         d.SetLevel(1)  # DeflaterEngine.SetLevel in mid-stream flushes a block first (trap T17): not accelerated, not emulated
+    d.SetStrategy(1)  # behind a completed Flush() the engine has nothing left: the switch is exact
+    d.SetInput(b"xyz" * 100)
+    with pytest.raises(z.B200zUnsupported):
+        d.SetStrategy(2)  # ... but not while input is held: the reference would switch somewhere inside it
+    d.Finish()
+    got += _drain(d)
+    r = RefDeflater(6, nowrap=True)
+    want = bytearray()
+    for seg, last in ((b"abc" * 100, False), (b"xyz" * 100, True)):
+        r.set_input(seg)
+        r.finish() if last else r.flush()
+        while True:
+            b = r.deflate(65536)
+            if not b:
+                break
+            want += b
+        if not last:
+            r.set_strategy(1)
+    assert got == bytes(want)
 
 
 def test_inflater_preset_dictionary(z, oracle):
