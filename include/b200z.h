@@ -49,6 +49,10 @@ int b200z_init(int device);
 int b200z_static_tables_size(void);
 int b200z_static_tables_export(uint8_t *blob, int32_t cap);
 int b200z_static_tables_import(const uint8_t *blob, int32_t len);
+/* The same collective inside the library, for a host process that owns an NCCL communicator (one process per GPU; SURVEY.md
+ * 8b): rank `root` exports, ncclBroadcast over `nccl_comm` (an ncclComm_t) on `cuda_stream`, every rank installs / verifies.
+ * NCCL is resolved from the process at run time (libnccl.so.2); B200Z_E_UNSUPPORTED when there is none. */
+int b200z_static_tables_broadcast(void *nccl_comm, int32_t root, int32_t rank, void *cuda_stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Checksums -- IChecksum (Checksum/IChecksum.cs), Crc32 (Checksum/Crc32.cs:47-171), Adler32 (Checksum/Adler32.cs:56-161).

@@ -97,6 +97,7 @@ _SIGS = {
     "b200z_inflate_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "b200z_release_cached": (C.c_int, []),
     "b200z_device_count": (C.c_int, []),
+    "b200z_static_tables_broadcast": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     "b200z_aes_derive_keys": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     "b200z_aes_state_bytes": (C.c_int64, []),
     "b200z_aes_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_int32,

@@ -11,6 +11,7 @@
 #include <utility>
 
 #include "b200z_internal.cuh"
+#include <dlfcn.h>
 
 namespace b200z {
 
@@ -257,6 +258,55 @@ int b200z_static_tables_import(const uint8_t *blob, int32_t len) {
 		return B200Z_E_DATA;
 	}
 	return B200Z_OK;
+}
+
+// ncclBroadcast inside the library, for a host that owns a communicator (one process per GPU).  NCCL is not linked: the
+// two entry points are taken from the libnccl the process has loaded (or can load) at run time.
+typedef int (*nccl_bcast_fn)(const void *, void *, size_t, int, int, void *, cudaStream_t);
+typedef const char *(*nccl_errstr_fn)(int);
+int b200z_static_tables_broadcast(void *nccl_comm, int32_t root, int32_t rank, void *cuda_stream) {
+	if (!nccl_comm || root < 0 || rank < 0) {
+		set_error("b200z_static_tables_broadcast: communicator, root and rank are required");
+		return B200Z_E_ARG;
+	}
+	int rc = ensure_init();
+	if (rc) return rc;
+	static nccl_bcast_fn bcast = nullptr;
+	static nccl_errstr_fn errstr = nullptr;
+	if (!bcast) {
+		void *h = nullptr;
+		const char *names[] = {"libnccl.so.2", "libnccl.so"};
+		for (int k = 0; k < 2 && !h; k++) h = dlopen(names[k], RTLD_NOW | RTLD_NOLOAD);
+		for (int k = 0; k < 2 && !h; k++) h = dlopen(names[k], RTLD_NOW | RTLD_GLOBAL);
+		if (h) {
+			bcast = (nccl_bcast_fn)dlsym(h, "ncclBroadcast");
+			errstr = (nccl_errstr_fn)dlsym(h, "ncclGetErrorString");
+		}
+		if (!bcast) {
+			set_error("b200z_static_tables_broadcast: no libnccl in this process (dlopen libnccl.so.2 failed)");
+			return B200Z_E_UNSUPPORTED;
+		}
+	}
+	cudaStream_t s = (cudaStream_t)cuda_stream;
+	uint8_t *d = nullptr;
+	B200Z_CUDA(cudaMalloc(&d, kStaticBlob));
+	uint8_t blob[kStaticBlob];
+	cudaError_t e = cudaSuccess;
+	if (rank == root) {
+		fill_static_blob(blob);
+		e = cudaMemcpyAsync(d, blob, kStaticBlob, cudaMemcpyHostToDevice, s);
+	}
+	int nr = 0;
+	if (e == cudaSuccess) nr = bcast(d, d, (size_t)kStaticBlob, /* ncclUint8 */ 1, root, nccl_comm, s);
+	if (e == cudaSuccess && nr == 0) e = cudaMemcpyAsync(blob, d, kStaticBlob, cudaMemcpyDeviceToHost, s);
+	if (e == cudaSuccess && nr == 0) e = cudaStreamSynchronize(s);
+	cudaFree(d);
+	if (nr != 0) {
+		set_error("ncclBroadcast failed: %s", errstr ? errstr(nr) : "?");
+		return B200Z_E_CUDA;
+	}
+	if (e != cudaSuccess) return cuda_fail(e, "b200z_static_tables_broadcast", __FILE__, __LINE__);
+	return b200z_static_tables_import(blob, kStaticBlob);
 }
 
 int64_t b200z_deflate_bound(int64_t len) { return len + (len >> 3) + 1024; }
