@@ -506,7 +506,7 @@ __global__ void __launch_bounds__(32)
                   uint32_t *__restrict__ sym_local, const int64_t *__restrict__ in_off, const int64_t *__restrict__ in_len,
                   const ChunkDesc *__restrict__ chunks, const uint32_t *__restrict__ rnd_off, RoundRec *__restrict__ recs,
                   RoundRec *__restrict__ ents, const uint32_t *__restrict__ hist, const int64_t *__restrict__ bias, LevelParams lp,
-                  int strategy) {
+                  int strategy, int warm) {
 	extern __shared__ __align__(16) uint8_t smem[];
 	const ChunkDesc cd = chunks[blockIdx.x];
 	const uint32_t n = (uint32_t)in_len[cd.stream];
@@ -519,12 +519,12 @@ __global__ void __launch_bounds__(32)
 	// 99.8 % of the boundaries (tools/tile_fixup.cpp).  It is recorded; k_parse_fix compares it with the exit of the chunk in
 	// front and parses again only where they differ.
 	ParseCarry carry = clean_carry(cd.c0 > H ? cd.c0 : H);
-	if (cd.c0 > H) {
+	if (cd.c0 > H && warm > 0) {
 		if (threadIdx.x == 0) {
 			const uint8_t *data = in + off;
 			const uint16_t *lnk = link + off;
 			const uint2 *tab = mt + off;
-			const uint32_t ws = cd.c0 - H > (uint32_t)kParseWarm ? cd.c0 - (uint32_t)kParseWarm : H;
+			const uint32_t ws = cd.c0 - H > (uint32_t)warm ? cd.c0 - (uint32_t)warm : H;
 			ParseCarry w = clean_carry(ws);
 			auto tabg = [&](uint32_t p, uint32_t &a, uint32_t &b) {
 				const uint2 t = tab[p];
@@ -957,6 +957,15 @@ __device__ __forceinline__ int fast_group_step(const uint8_t *__restrict__ in, u
 	la -= v;
 	__syncwarp();
 	return last_long;
+}
+
+// B200Z_PARSE_WARM=<positions> (0 .. 4096): how far in front of its first position a parse chunk starts (0: every chunk enters
+// with the clean guess and k_parse_fix parses again at most boundaries, as in round 1; for tests and timing)
+static int parse_warm() {
+	const char *e = getenv("B200Z_PARSE_WARM");
+	if (!e) return kParseWarm;
+	const long v = atol(e);
+	return v < 0 ? 0 : v > 4096 ? 4096 : (int)v;
 }
 
 // B200Z_FAST_GROUP=0 keeps every loop top on lane 0 (the serial statement; for measurements and for the tests that compare)
@@ -1803,7 +1812,7 @@ int deflate_plan_run(b200z_plan *p, const uint8_t *d_in, uint8_t *d_out, int64_t
 			uint32_t *rnd_symoff = ws.at<uint32_t>(p->o_rnd_symoff);
 			if (p->n_chunks)
 				k_parse_chunk<<<p->n_chunks, 32, kParseSmem, s>>>(d_in, link, mt, sym_local, in_off, in_len, ws.at<ChunkDesc>(p->o_chunks),
-				                                                 rnd_off, recs, ws.at<RoundRec>(p->o_ents), hist, bias, lp, p->strategy);
+				                                                 rnd_off, recs, ws.at<RoundRec>(p->o_ents), hist, bias, lp, p->strategy, parse_warm());
 			k_parse_fix<<<n, 32, kParseSmem, s>>>(d_in, link, mt, sym_local, in_off, in_len, rnd_off, recs, ws.at<RoundRec>(p->o_ents),
 			                                      p->parse_chunk, hist, bias, lp, p->strategy);
 			k_parse_scan<<<n, 256, 0, s>>>(d_in, in_off, in_len, rnd_off, recs, rnd_symoff, sym, nsyms, nblocks, blk_off, blk_start,

@@ -90,6 +90,16 @@ void launch(dim3 grid, dim3 block, size_t smem_bytes, std::function<void()> body
 				const unsigned bx = lin % grid.x, by = (lin / grid.x) % grid.y, bz = lin / (grid.x * grid.y);
 				b.bid = dim3(bx, by, bz);
 				memset(g_smem, 0xCD, smem_bytes + 64); // shared memory is not cleared between blocks
+				if (const char *fe = getenv("B200Z_EMU_FILL")) { // < 0: pseudo-random leftovers instead of a constant (static __shared__ arrays are host statics here and keep what the last block left, like the device)
+					const int fv = atoi(fe);
+					if (fv < 0) {
+						static uint64_t st = (uint64_t)(-fv) * 0xD1B54A32D192ED03ull + 7;
+						for (size_t i = 0; i < smem_bytes; i++) {
+							st = st * 6364136223846793005ull + 1442695040888963407ull;
+							g_smem[i] = (uint8_t)(st >> 56);
+						}
+					}
+				}
 				memset(g_smem + smem_bytes, 0xEE, 64);
 				b.fibers.assign((size_t)nt, Fiber());
 				b.warps.assign((size_t)(nt + 31) / 32, Warp());

@@ -256,7 +256,17 @@ static inline cudaError_t cudaGetDevice(int *d) { *d = 0; return cudaSuccess; }
 template <class T> static inline cudaError_t cudaMalloc(T **p, size_t n) {
 	void *q = nullptr;
 	if (posix_memalign(&q, 256, n ? n : 256)) return cudaErrorMemoryAllocation;
-	memset(q, 0xCD, n); // cudaMalloc does not clear either: make reads of unwritten memory visible
+	static const int fill = getenv("B200Z_EMU_FILL") ? atoi(getenv("B200Z_EMU_FILL")) : 0xCD; // B200Z_EMU_FILL=0: what a fresh device usually holds
+	if (fill < 0) { // B200Z_EMU_FILL=-<seed>: pseudo-random bytes, words of 0xFFFFFFFF sprinkled in (what other processes leave behind)
+		static uint64_t st = (uint64_t)(-fill) * 0x9E3779B97F4A7C15ull + 1;
+		uint32_t *w = (uint32_t *)q;
+		for (size_t i = 0; i < n / 4; i++) {
+			st = st * 6364136223846793005ull + 1442695040888963407ull;
+			const uint32_t r = (uint32_t)(st >> 32);
+			w[i] = (r & 7u) == 0 ? 0xFFFFFFFFu : (r & 7u) == 1 ? 0xFFFFFFFEu : r;
+		}
+	} else
+	memset(q, fill, n); // cudaMalloc does not clear either: make reads of unwritten memory visible
 	*p = (T *)q;
 	return cudaSuccess;
 }
