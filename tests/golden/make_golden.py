@@ -5,6 +5,8 @@ The reference's own tests hold known-answer vectors only for the checksums and t
 against them:
   * Checksum/ChecksumTests.cs      -> checksum KATs (values copied from the asserts)
   * Zip/ZipCorruptionHandling.cs   -> the raw deflate payloads of TestFileBadCDGoodCD64 and TestFileZeroCodeLength
+  * Zip/ZipEncryptionHandling.cs   -> the AES-256 encrypted archive of ZipFileAESReadWithEmptyPassword (:452-482) and the text it
+                                      must decrypt + inflate to (pins the oracle's AES-CTR / PBKDF2 / HMAC-SHA1)
 """
 import base64
 import json
@@ -54,6 +56,11 @@ def main():
                   {"ascii": "456", "value": 0xB1A8C371, "note": "unaligned slice of 123456789 (offset 3, count 3)"},
                   {"ascii": "789123456789123456", "value": 0x31CA9A2E, "note": "offset 6 count 18 of 123456789 x4"}],
     }
+    enc = open(os.path.join(REF, "Zip/ZipEncryptionHandling.cs"), encoding="utf-8-sig").read()
+    m = re.search(r'const string TestFileWithEmptyPassword\s*=\s*@"([^"]*)"', enc)
+    text = re.search(r'Is\.EqualTo\("(Lorem ipsum[^"]*)"\)', enc).group(1)
+    out["aes_empty_password_zip"] = {"source": "Zip/ZipEncryptionHandling.cs:452-482 TestFileWithEmptyPassword / ZipFileAESReadWithEmptyPassword",
+                                     "zip_base64": "".join(m.group(1).split()), "password": "", "entry": "test", "text": text}
     with open(os.path.join(HERE, "reference_fixtures.json"), "w") as f:
         json.dump(out, f, indent=1)
     print("wrote reference_fixtures.json:", {k: (len(v.get("raw_hex", "")) // 2 if isinstance(v, dict) else 0) for k, v in out.items()})

@@ -146,11 +146,8 @@ def test_handle_api_matches_oneshot(oracle):
 # ---- entry ciphers (oracle/szl_crypto.cpp) -------------------------------------------------------
 # The AES-encrypted archive the reference's own tests hold (test/.../Zip/ZipEncryptionHandling.cs:452-456: one entry "test",
 # AES-256, deflated, empty password; :461-482 expects the text below).
-AES_FIXTURE_B64 = """UEsDBDMACQBjACaj0FAyKbop//////////8EAB8AdGVzdAEAEAA4AAAA
-AAAAAFIAAAAAAAAAAZkHAAIAQUUDCABADvo3YqmCtIE+lhw26kjbqkGsLEOk6bVA+FnSpVD4yGP4Mr66Hs14aTtsPUaANX2
-Z6qZczEmwoaNQpNBnKl7p9YOG8GSHDfTCUU/AZvT4yGFhUEsHCDIpuilSAAAAAAAAADgAAAAAAAAAUEsBAjMAMwAJAGMAJq
-PQUDIpuin//////////wQAHwAAAAAAAAAAAAAAAAAAAHRlc3QBABAAOAAAAAAAAABSAAAAAAAAAAGZBwACAEFFAwgAUEsFBgAAAAABAAEAUQAAAKsAAAAAAA=="""
-AES_FIXTURE_TEXT = b"Lorem ipsum dolor sit amet, consectetur adipiscing elit."
+AES_FIXTURE_B64 = GOLD["aes_empty_password_zip"]["zip_base64"]  # extracted from the reference's test source by tests/golden/make_golden.py
+AES_FIXTURE_TEXT = GOLD["aes_empty_password_zip"]["text"].encode()
 
 
 def aes_fixture_entry():
