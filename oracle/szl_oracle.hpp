@@ -16,12 +16,19 @@
 //   * Inflater         : PINNED by the reference's foreign-compressor fixtures
 //                        (test/.../Zip/ZipCorruptionHandling.cs:12-69) and by
 //                        agreement with zlib on valid streams.
-//   * Deflater bytes   : PARITY UNPINNED -- the reference's tests hold no
-//                        compressed-byte golden vector and no .NET runtime exists
-//                        in the build container, so the emitted bytes rest on the
-//                        audit of this restatement against the cited lines plus
-//                        structural checks (every output inflates to its input
-//                        under zlib; feed-pattern invariance; debug invariants).
+//   * Deflater bytes   : PINNED IN PART.  The reference tree holds two raw deflate streams its own Deflater
+//                        wrote: the payload inside the AES-encrypted archive of
+//                        test/.../Zip/ZipEncryptionHandling.cs:452-456 (a DYNAMIC block for 56 bytes of text --
+//                        zlib emits a static block for that input at every level, SharpZipLib's tree
+//                        construction and block decision do not) and the entry of TestFileBadCDGoodCD64.
+//                        Both are reproduced byte for byte at levels 1-9 (tests/test_oracle.py
+//                        test_deflater_bytes_against_streams_the_reference_holds): that pins Tree.BuildTree /
+//                        BuildLength / BuildCodes, SendAllTrees / WriteTree, FlushBlock's decision,
+//                        CompressBlock and the bit writer.  Neither input has a repeated trigram, so the
+//                        match finding (FindLongestMatch / DeflateSlow / DeflateFast) is PARITY UNPINNED:
+//                        no .NET runtime exists here or on the GPU boxes, and those bytes rest on the audit
+//                        of this restatement against the cited lines plus structural checks (every output
+//                        inflates to its input under zlib; feed-pattern invariance; debug invariants).
 #pragma once
 #include <cstdint>
 #include <cstddef>

@@ -117,3 +117,18 @@ def test_pkzip_classic_matches_the_oracle_and_zipfile(z, oracle):
         assert outs[i] == w and after[i].tobytes() == ka
     back, _ = E.pkzip_batch(outs, ks, False)
     assert back == bufs
+
+
+def test_deflate_reproduces_the_streams_the_reference_holds(z):
+    """the GPU Deflater against the only emitted Deflater bytes in the reference tree (tests/test_oracle.py:
+    reference_held_deflate_streams): SharpZipLib's own dynamic block for 56 bytes of text, and a static one"""
+    from test_oracle import reference_held_deflate_streams
+    (text, dyn), (small, stat) = reference_held_deflate_streams()
+    for level in (1, 4, 5, 6, 9):
+        outs, _ = z.deflate_batch([text, small], level=level)
+        assert outs == [dyn, stat], level
+    d = z.Deflater(6, True)
+    d.SetInput(text)
+    d.Finish()
+    buf = bytearray(512)
+    assert bytes(buf[:d.Deflate(buf)]) == dyn

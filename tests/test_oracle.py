@@ -235,3 +235,30 @@ def test_pkzip_classic_oracle_is_read_by_python_zipfile(oracle):
     assert zf.read("f.bin", pwd=b"secret") == data
     dec, keys_after2 = O.pkzip_transform(keys, False, enc)
     assert dec == header + data and keys_after2 == keys_after
+
+
+def reference_held_deflate_streams():
+    """(input, raw deflate stream) pairs the reference's own tests hold: the payload inside its AES-encrypted archive (decrypted
+    with the oracle; written by SharpZipLib itself -- a DYNAMIC block for 56 bytes of text, where zlib emits a static one) and
+    the entry of TestFileBadCDGoodCD64"""
+    salt, pv, ct, mac, kb, method = aes_fixture_entry()
+    import oracle_lib
+    plain, verifier, auth = oracle_lib.zip_aes(b"", salt, kb, False, ct)
+    assert verifier == pv and auth[:10] == mac and method == 8
+    raw2 = bytes.fromhex(GOLD["inflate_ok"]["raw_hex"])
+    return [(AES_FIXTURE_TEXT, plain), (oracle_lib.inflate(raw2, nowrap=True)[0], raw2)]
+
+
+def test_deflater_bytes_against_streams_the_reference_holds(oracle):
+    """The only emitted Deflater bytes the reference tree holds.  They pin the Huffman half of the oracle's Deflater (Tree.BuildTree /
+    BuildLength / BuildCodes with the dummy codes of trap T3, SendAllTrees / WriteTree, the dynamic / static / stored decision of
+    FlushBlock, CompressBlock, the bit writer) against real SharpZipLib output; neither input has a repeated trigram, so match
+    finding stays unpinned."""
+    (text, dyn), (small, stat) = reference_held_deflate_streams()
+    assert dyn[0] & 7 == 0b101  # BFINAL = 1, BTYPE = 2: a dynamic block
+    for level in range(1, 10):
+        for strategy in (0, 1, 2):
+            assert oracle.deflate(text, level=level, strategy=strategy) == dyn, (level, strategy)
+        assert oracle.deflate(small, level=level) == stat
+        c = zlib.compressobj(level, zlib.DEFLATED, -15)
+        assert c.compress(text) + c.flush() != dyn  # zlib would not have written this stream: it is SharpZipLib's
