@@ -61,6 +61,12 @@ def main():
     text = re.search(r'Is\.EqualTo\("(Lorem ipsum[^"]*)"\)', enc).group(1)
     out["aes_empty_password_zip"] = {"source": "Zip/ZipEncryptionHandling.cs:452-482 TestFileWithEmptyPassword / ZipFileAESReadWithEmptyPassword",
                                      "zip_base64": "".join(m.group(1).split()), "password": "", "entry": "test", "text": text}
+    zf = open(os.path.join(REF, "Zip/ZipFileHandling.cs"), encoding="utf-8-sig").read()
+    zf = zf[zf.index("public void ShouldReadAESBZip2ZipCreatedBy7Zip"):]  # (the plain bzip2 test in front of it uses the same names)
+    text7 = re.search(r'const string originalText =\s*"([^"]*)"', zf).group(1)
+    out["aes_bzip2_zip_by_7zip"] = {"source": "Zip/ZipFileHandling.cs:1707-1745 ShouldReadAESBZip2ZipCreatedBy7Zip",
+                                    "zip_base64": const_string(zf, "bZip2CompressedZipCreatedBy7Zip"), "password": "password",
+                                    "entry": "Hello.txt", "method": "bzip2", "text": text7}
     with open(os.path.join(HERE, "reference_fixtures.json"), "w") as f:
         json.dump(out, f, indent=1)
     print("wrote reference_fixtures.json:", {k: (len(v.get("raw_hex", "")) // 2 if isinstance(v, dict) else 0) for k, v in out.items()})

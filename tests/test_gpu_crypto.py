@@ -27,6 +27,20 @@ def test_aes_reference_fixture_through_the_gpu(z):
     t.Dispose()
 
 
+def test_aes_7zip_fixture_through_the_gpu(z):
+    """test/.../Zip/ZipFileHandling.cs:1707-1745 (ShouldReadAESBZip2ZipCreatedBy7Zip): password "password", AES-256; the payload is
+    bzip2 (not this library's business: Python's bz2 reads it)"""
+    import bz2
+    from sharpziplib_b200.encryption import ZipAESTransform
+    from test_oracle import aes_7zip_fixture_entry
+    salt, pv, ct, mac, pw, text = aes_7zip_fixture_entry()
+    t = ZipAESTransform(pw.decode(), salt, 32, False)
+    plain = bytearray(len(ct))
+    t.TransformBlock(ct, 0, len(ct), plain, 0)
+    assert t.PwdVerifier == pv and t.GetAuthCode()[:10] == mac and bz2.decompress(bytes(plain)) == text
+    t.Dispose()
+
+
 @pytest.mark.parametrize("key_bytes", [16, 32])
 def test_aes_transform_handle_matches_the_oracle(z, oracle, key_bytes):
     """TransformBlock in uneven pieces (the CTR position and the HMAC go on across calls), both directions"""

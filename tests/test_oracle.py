@@ -190,6 +190,25 @@ def test_crypto_oracle_reads_the_reference_aes_fixture(oracle):
     assert O.inflate(plain, nowrap=True)[0] == AES_FIXTURE_TEXT
 
 
+def aes_7zip_fixture_entry():
+    """the entry of the AES-256 + bzip2 archive written by 7-zip that the reference's tests hold (ZipFileHandling.cs:1707-1745)"""
+    import base64
+    import struct
+    g = GOLD["aes_bzip2_zip_by_7zip"]
+    z = base64.b64decode(g["zip_base64"])
+    sig, _, flags, method, _, _, _, csize, _, nl, xl = struct.unpack("<IHHHHHIIIHH", z[:30])
+    assert sig == 0x04034B50 and method == 99 and flags & 1
+    data = z[30 + nl + xl:30 + nl + xl + csize]
+    return data[:16], data[16:18], data[18:-10], data[-10:], g["password"].encode(), g["text"].encode()
+
+
+def test_crypto_oracle_reads_the_reference_7zip_aes_fixture(oracle):
+    import bz2
+    salt, pv, ct, mac, pw, text = aes_7zip_fixture_entry()
+    plain, verifier, auth = oracle.zip_aes(pw, salt, 32, False, ct)
+    assert verifier == pv and auth[:10] == mac and bz2.decompress(plain) == text
+
+
 def test_crypto_oracle_against_an_independent_library(oracle):
     O = oracle
     hz = pytest.importorskip("cryptography.hazmat.primitives")
